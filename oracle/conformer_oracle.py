@@ -337,8 +337,8 @@ def ctc_loss_sum(log_probs: Array, targets: Array, input_lengths: Sequence[int],
                 alpha[1] = lp[0, b, ext[1]]
             for t in range(1, Tn):
                 prev = alpha
-                a1 = np.concatenate([[-np.inf], prev[:-1]])
-                a2 = np.concatenate([[-np.inf, -np.inf], prev[:-2]])
+                a1 = np.concatenate([[-np.inf], prev[:-1]])[:S]
+                a2 = np.concatenate([[-np.inf, -np.inf], prev[:-2]])[:S]
                 skip_ok = np.zeros(S, dtype=bool)
                 skip_ok[2:] = (ext[2:] != 0) & (ext[2:] != ext[:-2])
                 a2 = np.where(skip_ok, a2, -np.inf)
