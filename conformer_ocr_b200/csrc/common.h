@@ -1,0 +1,186 @@
+// Shared declarations of the cocr_b200 library (internal; the public ABI is include/cocr_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/cocr_b200.h"
+
+namespace cocr {
+
+struct HostTensor {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+    int64_t numel() const {
+        int64_t n = 1;
+        for (auto s : shape) n *= s;
+        return n;
+    }
+};
+
+// fp32 device pointers of one conformer block (encoder.py:67-100), BatchNorm already folded.
+struct LayerF32 {
+    const float *ffn_ln_g[2], *ffn_ln_b[2];      // sequential.{0,3}.module.sequential.0
+    const float *ffn_w1[2], *ffn_b1[2];          // (ff, d), (ff)
+    const float *ffn_w2[2], *ffn_b2[2];          // (d, ff), (d)
+    const float *att_ln_g, *att_ln_b;
+    const float *w_qkv, *b_qkv;                  // (3d, d) = [Wq; Wk; Wv], (3d)
+    const float *w_pos;                          // (d, d), no bias
+    const float *u_bias, *v_bias;                // (h, dh)
+    const float *w_out, *b_out;                  // (d, d), (d)
+    const float *conv_ln_g, *conv_ln_b;
+    const float *w_pw1, *b_pw1;                  // (2d, d), (2d)
+    const float *w_dw;                           // (d, K)
+    const float *bn_scale, *bn_shift;            // folded BatchNorm1d (eval)
+    const float *w_pw2, *b_pw2;                  // (d, d), (d)
+    const float *final_ln_g, *final_ln_b;
+};
+
+struct Dims {
+    int H, d, L, nh, dh, ff, K, cc, C;
+    int F2, F, feat;                             // height after conv 1 / conv 2, cc*F
+    float ffn_factor;
+};
+
+struct Workspace {
+    char *base = nullptr;
+    size_t bytes = 0;
+};
+
+struct Bf16State;   // defined in bf16_path.cu
+
+}  // namespace cocr
+
+struct cocr_handle {
+    cocr_hparams hp;
+    cocr::Dims dm;
+    int device = 0;
+    int num_sms = 148;
+    std::string err;
+    std::map<std::string, cocr::HostTensor> host_w;
+    std::map<std::string, std::vector<int64_t>> expect;   // key -> expected shape
+    bool finalized = false;
+
+    // fp32 weights on the device (one arena)
+    float *arena = nullptr;
+    size_t arena_floats = 0;
+    const float *sub_w1 = nullptr, *sub_b1 = nullptr;     // conv.0 (cc,9),(cc)
+    const float *sub_wdw = nullptr, *sub_bdw = nullptr;   // conv.2 (cc,9),(cc)
+    const float *sub_wpw = nullptr, *sub_bpw = nullptr;   // conv.3 (cc,cc),(cc)
+    const float *sub_wout = nullptr, *sub_bout = nullptr; // out.0 permuted to (d, F*cc) [f*cc+c]
+    const float *dec_w = nullptr, *dec_b = nullptr;       // (C,d),(C)
+    std::vector<cocr::LayerF32> layers;
+
+    // activation workspace (grown on demand) and cached positional projections
+    cocr::Workspace ws;
+    float *pos_proj = nullptr;      // (L, 2T-1, d) fp32
+    int pos_T = 0;
+
+    // staging for the *_host entry point
+    float *io_img = nullptr;
+    size_t io_img_bytes = 0;
+    char *io_res = nullptr;         // device result block
+    char *io_res_host = nullptr;    // pinned mirror
+    size_t io_res_bytes = 0;
+    int32_t *io_widths = nullptr;
+    size_t io_widths_n = 0;
+
+    int64_t launches = 0;
+    cocr::Bf16State *bf = nullptr;
+
+    // optional per-launch event timing (cocr_set_profiling)
+    bool profiling = false;
+    struct ProfRec { const char *name; cudaEvent_t a, b; double flops, bytes; };
+    std::vector<ProfRec> prof;
+};
+
+namespace cocr {
+
+int set_error(cocr_handle *h, int code, const char *fmt, ...);
+int check_cuda(cocr_handle *h, cudaError_t e, const char *what);
+void set_global_error(const char *msg);
+
+#define COCR_CUDA(h, call)                                               \
+    do {                                                                 \
+        int _rc = cocr::check_cuda((h), (call), #call);                  \
+        if (_rc != COCR_OK) return _rc;                                  \
+    } while (0)
+
+#define COCR_TRY(call)                   \
+    do {                                 \
+        int _rc = (call);                \
+        if (_rc != COCR_OK) return _rc;  \
+    } while (0)
+
+// after-launch check that also counts the launch
+#define COCR_LAUNCHED(h)                                                 \
+    do {                                                                 \
+        (h)->launches++;                                                 \
+        int _rc = cocr::check_cuda((h), cudaGetLastError(), "kernel launch"); \
+        if (_rc != COCR_OK) return _rc;                                  \
+    } while (0)
+
+// RAII event pair around one kernel launch; a no-op unless profiling is on.
+struct ProfScope {
+    cocr_handle *h;
+    cudaStream_t st;
+    cudaEvent_t b = nullptr;
+    ProfScope(cocr_handle *h_, const char *name, cudaStream_t st_, double flops, double bytes) : h(h_), st(st_) {
+        if (!h->profiling) return;
+        cudaEvent_t a;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+        h->prof.push_back({name, a, b, flops, bytes});
+    }
+    ~ProfScope() {
+        if (b) cudaEventRecord(b, st);
+    }
+};
+
+inline int out_len1(int n) { return (n + 2 - 3) / 2 + 1; }   // one stride-2 3x3 pad-1 conv; n >= 1
+
+// ---- fp32 path (fp32_path.cu) ------------------------------------------------------------
+struct Fp32Plan {      // workspace carve-up for one (B, W)
+    int B, W, T2, T, M;
+    size_t off_a1, off_a2, off_feat, off_x, off_xn, off_h, off_g, off_best_val, off_best_idx, total;
+};
+void fp32_plan(const cocr_handle *h, int B, int W, Fp32Plan *p);
+int fp32_encode(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths,
+                int B, int W, cudaStream_t st, float *enc_out /* may be null: stays in ws.x */, int32_t *out_lens);
+int fp32_logits(cocr_handle *h, const float *enc /* (M,d) */, int M, cudaStream_t st, float *logits);
+int launch_out_lens(cocr_handle *h, const int32_t *widths, int B, int W, int32_t *out_lens, cudaStream_t st);
+int launch_greedy_decode(cocr_handle *h, const float *logits, const int32_t *lens, int B, int T, int C,
+                         cudaStream_t st, float *best_val, int32_t *best_idx, int32_t *labels, int32_t *starts,
+                         int32_t *ends, float *conf, int32_t *counts);
+int launch_collapse(cocr_handle *h, const float *best_val, const int32_t *best_idx, const int32_t *lens, int B, int T,
+                    cudaStream_t st, int32_t *labels, int32_t *starts, int32_t *ends, float *conf, int32_t *counts);
+int ensure_workspace(cocr_handle *h, size_t bytes);
+int ensure_pos_proj(cocr_handle *h, int T, cudaStream_t st);
+
+// generic fp32 GEMM: C[m,n] = epi(sum_k A[m,k] W[n,k] + bias[n]); act 0 none / 1 SiLU / 2 ReLU;
+// res != null: C = res + alpha * value
+int launch_sgemm(cocr_handle *h, const float *A, int lda, const float *Wt, int ldw, const float *bias, float *Cout,
+                 int ldc, int M, int N, int K, int act, const float *res, int ldres, float alpha, cudaStream_t st);
+int launch_layernorm(cocr_handle *h, const float *x, float *y, const float *g, const float *b, int M, int d,
+                     cudaStream_t st);
+
+// ---- bf16 path (bf16_path.cu) ------------------------------------------------------------
+int bf16_init(cocr_handle *h);       // pack weights; called from cocr_finalize_weights when precision == bf16
+void bf16_destroy(cocr_handle *h);
+int bf16_encode(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths,
+                int B, int W, cudaStream_t st, float *enc_out, int32_t *out_lens);
+size_t bf16_workspace_bytes(const cocr_handle *h, int B, int W);
+// decode straight from the bf16 path's final activations (fused projection + argmax)
+int bf16_forward_decode(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh,
+                        const int32_t *widths, int B, int W, cudaStream_t st, int32_t *labels, int32_t *starts,
+                        int32_t *ends, float *conf, int32_t *counts, int32_t *out_lens);
+int bf16_logits(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths,
+                int B, int W, cudaStream_t st, float *logits, int32_t *out_lens);
+
+}  // namespace cocr

@@ -1,0 +1,218 @@
+"""Thin owner of one `cocr_handle`: weight upload and the forward / decode calls.
+
+PyTorch is used for plumbing only (device memory of inputs/outputs, the current CUDA stream);
+all arithmetic happens inside libcocr_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Mapping, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_PRECISIONS = {'fp32': _lib.COCR_FP32, 'float32': _lib.COCR_FP32, '32': _lib.COCR_FP32,
+               'bf16': _lib.COCR_BF16, 'bfloat16': _lib.COCR_BF16}
+_MASKS = {'reference_unmasked': _lib.COCR_MASK_REFERENCE_UNMASKED, 'ragged': _lib.COCR_MASK_RAGGED}
+
+
+def out_frames(widths):
+    """calc_length (conformer/convolution.py:240-247) for subsampling factor 4, on the host, with
+    the reference's float arithmetic; returns an int32 tensor like the reference does."""
+    t = torch.as_tensor(widths)
+    t = t.to(dtype=torch.float)
+    for _ in range(2):
+        t = torch.floor(torch.div(t + (2.0 - 3.0), 2) + 1.0)
+    return t.to(dtype=torch.int)
+
+
+class Engine:
+    """One device handle (encoder [+ decoder]) on one GPU."""
+
+    def __init__(self, *, height: int, encoder_dim: int, num_layers: int, num_heads: int,
+                 ff_expansion: int, conv_expansion: int, conv_kernel_size: int, half_step_residual: bool,
+                 subsampling_conv_channels: int, subsampling_factor: int, num_classes: int,
+                 device: torch.device, precision: str = 'fp32', mask_mode: str = 'reference_unmasked'):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        if precision not in _PRECISIONS:
+            raise ValueError(f'unknown precision {precision!r}; expected one of {sorted(_PRECISIONS)}')
+        if mask_mode not in _MASKS:
+            raise ValueError(f'unknown mask_mode {mask_mode!r}; expected one of {sorted(_MASKS)}')
+        device = torch.device(device)
+        if device.type != 'cuda':
+            raise RuntimeError('conformer_ocr_b200 computes on a CUDA device only (no CPU fallback); '
+                               f'got device {device}')
+        if not torch.cuda.is_available():
+            raise RuntimeError('no CUDA device available; conformer_ocr_b200 has no CPU fallback')
+        self.device = torch.device('cuda', device.index if device.index is not None else torch.cuda.current_device())
+        self.hp = _lib.cocr_hparams(height, encoder_dim, num_layers, num_heads, ff_expansion, conv_expansion,
+                                    conv_kernel_size, int(bool(half_step_residual)), subsampling_conv_channels,
+                                    subsampling_factor, num_classes, _PRECISIONS[precision], _MASKS[mask_mode])
+        self.precision = precision
+        self.mask_mode = mask_mode
+        rc = self._lib.cocr_create(C.byref(self.hp), self.device.index, C.byref(self._h))
+        _lib.raise_for_status(rc, None)
+        self.num_classes = num_classes
+        self.encoder_dim = encoder_dim
+        self.height = height
+        self._loaded = False
+
+    # -- life cycle -------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            self._lib.cocr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        _lib.raise_for_status(rc, self._h)
+
+    # -- weights ----------------------------------------------------------------------------
+    def load_state_dict(self, state: Mapping[str, object]):
+        """`state`: keys as in `PytorchRecognitionModel.nn.state_dict()` ("encoder.*", "decoder.*");
+        values torch tensors or numpy arrays."""
+        for key, val in state.items():
+            if key.endswith('num_batches_tracked'):
+                continue
+            if isinstance(val, torch.Tensor):
+                arr = val.detach().to(device='cpu', dtype=torch.float32).contiguous().numpy()
+            else:
+                arr = np.ascontiguousarray(np.asarray(val, dtype=np.float32))
+            shape = (C.c_int64 * max(arr.ndim, 1))(*arr.shape)
+            self._check(self._lib.cocr_set_weight(self._h, key.encode(), arr.ctypes.data_as(C.c_void_p), arr.ndim, shape))
+        self._check(self._lib.cocr_finalize_weights(self._h))
+        self._loaded = True
+
+    # -- helpers ----------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _prep(self, inputs: torch.Tensor, lens) -> Tuple[torch.Tensor, Optional[torch.Tensor], int, int]:
+        """inputs: (B, W, H) view (any strides) on this engine's device."""
+        if inputs.dim() != 3:
+            raise ValueError(f'expected (batch, width, height) input, got shape {tuple(inputs.shape)}')
+        if inputs.device != self.device:
+            if inputs.device.type != 'cuda':
+                raise RuntimeError('input tensor is on the CPU; move it to the GPU (no CPU fallback)')
+            raise RuntimeError(f'input on {inputs.device}, engine on {self.device}')
+        if inputs.dtype != torch.float32:
+            inputs = inputs.float()
+        B, W, H = inputs.shape
+        if H != self.height:
+            raise ValueError(f'input height {H} does not match model height {self.height}')
+        wd = None
+        if lens is not None:
+            wd = torch.as_tensor(lens).to(device=self.device, dtype=torch.int32, non_blocking=True).contiguous()
+            if wd.numel() != B:
+                raise ValueError(f'{wd.numel()} sequence lengths for a batch of {B}')
+        return inputs, wd, B, W
+
+    @staticmethod
+    def _ptr(t: Optional[torch.Tensor]):
+        return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p()
+
+    # -- forward calls ----------------------------------------------------------------------
+    def encode(self, inputs: torch.Tensor, lens=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """ConformerEncoder.forward: (B,W,H) -> ((B,T,d) fp32 on device, (B,) int32 device lens)."""
+        x, wd, B, W = self._prep(inputs, lens)
+        T = int(self._lib.cocr_out_frames(W))
+        out = torch.empty((B, T, self.encoder_dim), dtype=torch.float32, device=self.device)
+        olens = torch.empty((B,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.cocr_encode(self._h, self._ptr(x), x.stride(0), x.stride(1), x.stride(2), self._ptr(wd),
+                                              B, W, self._stream(), self._ptr(out), self._ptr(olens)))
+        return out, olens
+
+    def logits(self, inputs: torch.Tensor, lens=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        x, wd, B, W = self._prep(inputs, lens)
+        T = int(self._lib.cocr_out_frames(W))
+        out = torch.empty((B, T, self.num_classes), dtype=torch.float32, device=self.device)
+        olens = torch.empty((B,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.cocr_logits(self._h, self._ptr(x), x.stride(0), x.stride(1), x.stride(2), self._ptr(wd),
+                                              B, W, self._stream(), self._ptr(out), self._ptr(olens)))
+        return out, olens
+
+    def forward_decode(self, inputs: torch.Tensor, lens=None) -> Dict[str, torch.Tensor]:
+        """Fused encoder -> projection -> argmax -> CTC collapse; results stay on the device."""
+        x, wd, B, W = self._prep(inputs, lens)
+        T = int(self._lib.cocr_out_frames(W))
+        i32 = dict(dtype=torch.int32, device=self.device)
+        res = dict(labels=torch.empty((B, T), **i32), starts=torch.empty((B, T), **i32), ends=torch.empty((B, T), **i32),
+                   conf=torch.empty((B, T), dtype=torch.float32, device=self.device),
+                   counts=torch.empty((B,), **i32), out_lens=torch.empty((B,), **i32))
+        with torch.cuda.device(self.device):
+            self._check(self._lib.cocr_forward_decode(
+                self._h, self._ptr(x), x.stride(0), x.stride(1), x.stride(2), self._ptr(wd), B, W, self._stream(),
+                self._ptr(res['labels']), self._ptr(res['starts']), self._ptr(res['ends']), self._ptr(res['conf']),
+                self._ptr(res['counts']), self._ptr(res['out_lens'])))
+        return res
+
+    def greedy_decode(self, logits: torch.Tensor, lens=None) -> Dict[str, torch.Tensor]:
+        """greedy_decoder over device logits (B,T,C)."""
+        if logits.device != self.device or logits.dtype != torch.float32:
+            logits = logits.to(device=self.device, dtype=torch.float32)
+        logits = logits.contiguous()
+        B, T, Cn = logits.shape
+        ld = None
+        if lens is not None:
+            ld = torch.as_tensor(lens).to(device=self.device, dtype=torch.int32).contiguous()
+        i32 = dict(dtype=torch.int32, device=self.device)
+        res = dict(labels=torch.empty((B, T), **i32), starts=torch.empty((B, T), **i32), ends=torch.empty((B, T), **i32),
+                   conf=torch.empty((B, T), dtype=torch.float32, device=self.device), counts=torch.empty((B,), **i32))
+        with torch.cuda.device(self.device):
+            self._check(self._lib.cocr_greedy_decode(self._h, self._ptr(logits), self._ptr(ld), B, T, Cn, self._stream(),
+                                                     self._ptr(res['labels']), self._ptr(res['starts']),
+                                                     self._ptr(res['ends']), self._ptr(res['conf']), self._ptr(res['counts'])))
+        return res
+
+    def recognize_host(self, img: torch.Tensor, widths: Optional[torch.Tensor] = None) -> Dict[str, np.ndarray]:
+        """Host-buffer entry point (cli/test.py:185-191 equivalent): `img` (N,1,H,W) fp32 host tensor
+        (pinned for full speed), `widths` int32 host tensor.  H2D, forward, decode and D2H all happen
+        inside the call; returns numpy arrays."""
+        if img.device.type != 'cpu' or img.dtype != torch.float32 or not img.is_contiguous():
+            raise ValueError('recognize_host expects a contiguous fp32 host tensor (N,1,H,W)')
+        B, ch, H, W = img.shape
+        if ch != 1 or H != self.height:
+            raise ValueError(f'expected (N,1,{self.height},W) input, got {tuple(img.shape)}')
+        T = int(self._lib.cocr_out_frames(W))
+        wh = None
+        if widths is not None:
+            wh = torch.as_tensor(widths).to(dtype=torch.int32).contiguous()
+        res = dict(labels=np.empty((B, T), np.int32), starts=np.empty((B, T), np.int32), ends=np.empty((B, T), np.int32),
+                   conf=np.empty((B, T), np.float32), counts=np.empty((B,), np.int32), out_lens=np.empty((B,), np.int32))
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.cocr_recognize_host(
+                self._h, C.c_void_p(img.data_ptr()), self._ptr(wh), B, W, self._stream(), p(res['labels']),
+                p(res['starts']), p(res['ends']), p(res['conf']), p(res['counts']), p(res['out_lens'])))
+        return res
+
+    def workspace_bytes(self, B: int, W: int) -> int:
+        n = C.c_size_t()
+        self._check(self._lib.cocr_workspace_bytes(self._h, B, W, C.byref(n)))
+        return int(n.value)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.cocr_launch_count(self._h))
+
+
+def unpack_decoded(res: Mapping[str, object]) -> List[List[Tuple[int, int, int, float]]]:
+    """Device/host decode block -> the list-of-tuples format of kraken's greedy_decoder."""
+    def host(v):
+        return v.cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+    labels, starts, ends, conf, counts = (host(res[k]) for k in ('labels', 'starts', 'ends', 'conf', 'counts'))
+    out = []
+    for b in range(labels.shape[0]):
+        n = int(counts[b])
+        out.append(list(zip(labels[b, :n].tolist(), starts[b, :n].tolist(), ends[b, :n].tolist(), conf[b, :n].tolist())))
+    return out

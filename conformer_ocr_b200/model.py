@@ -1,0 +1,56 @@
+"""Host-side mirror of the hot-path slice of `conformer_ocr.model.RecognitionModel`
+(model.py:39-151): construction (`:99-116`) and `forward(x, seq_lens)` (`:125-127`).  The Lightning
+training loop, metrics and optimiser factory are out of scope."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .conformer.encoder import ConformerEncoder, EngineOwner
+from .engine import out_frames
+
+
+class RecognitionModel(EngineOwner):
+    def __init__(self, num_classes: int, height: int = 96, encoder_dim: int = 144, num_encoder_layers: int = 16,
+                 num_attention_heads: int = 4, feed_forward_expansion_factor: int = 4, conv_expansion_factor: int = 2,
+                 input_dropout_p: float = 0.1, feed_forward_dropout_p: float = 0.1, attention_dropout_p: float = 0.1,
+                 conv_dropout_p: float = 0.1, conv_kernel_size: int = 31, half_step_residual: bool = True,
+                 subsampling_conv_channels: int = 32, subsampling_factor: int = 4, precision: str = 'fp32',
+                 mask_mode: str = 'reference_unmasked', **kwargs):
+        super().__init__()
+        encoder = ConformerEncoder(in_channels=1, input_dim=height, encoder_dim=encoder_dim, num_layers=num_encoder_layers,
+                                   num_attention_heads=num_attention_heads,
+                                   feed_forward_expansion_factor=feed_forward_expansion_factor,
+                                   conv_expansion_factor=conv_expansion_factor, input_dropout_p=input_dropout_p,
+                                   feed_forward_dropout_p=feed_forward_dropout_p, attention_dropout_p=attention_dropout_p,
+                                   conv_dropout_p=conv_dropout_p, conv_kernel_size=conv_kernel_size,
+                                   half_step_residual=half_step_residual,
+                                   subsampling_conv_channels=subsampling_conv_channels,
+                                   subsampling_factor=subsampling_factor, precision=precision, mask_mode=mask_mode)
+        decoder = nn.Linear(encoder_dim, num_classes, bias=True)
+        for p in decoder.parameters():
+            p.requires_grad_(False)
+        self.nn = nn.ModuleDict({'encoder': encoder, 'decoder': decoder})    # model.py:115
+        self.num_classes = num_classes
+        self._init_engine_state(precision, mask_mode)
+        self.eval()
+
+    def _engine_kwargs(self):
+        return dict(num_classes=self.num_classes, **self.nn['encoder'].hparams)
+
+    def _engine_state(self):
+        return dict(self.nn.state_dict())
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError('conformer_ocr_b200 implements the inference path only')
+        return super().train(False)
+
+    def forward(self, x: torch.Tensor, seq_lens: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """x (N, W, H) as `_step` passes it (model.py:132-135) -> (logits (N,T,C), encoder_lens)."""
+        eng = self.engine_for(x.device)
+        logits, _ = eng.logits(x, seq_lens)
+        lens = out_frames(seq_lens if seq_lens is not None else torch.full((x.shape[0],), x.shape[1]))
+        return logits, lens

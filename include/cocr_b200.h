@@ -1,0 +1,164 @@
+/*
+ * cocr_b200.h — C ABI of the B200-native conformer_ocr hot path.
+ *
+ * The reference (mittagessen/conformer_ocr) is pure Python/torch and has no FFI of its
+ * own; its seam for this path is three Python call signatures.  Each entry
+ * point below names the reference interface it replaces (paths relative to
+ * /root/reference/conformer_ocr/).  No torch types cross this boundary: plain pointers,
+ * sizes, a `cudaStream_t` passed as `void*`, `int` status codes.  The ctypes binding that a
+ * maintainer of the reference would add is shown in INTEGRATION.md and lives in
+ * conformer_ocr_b200/_lib.py.
+ *
+ * Conventions
+ *  - every function returns COCR_OK (0) or a negative cocr_status; the message of the
+ *    last failure is available from cocr_last_error().  No exception crosses the ABI.
+ *  - "dev" pointers are device memory on the handle's device, "host" pointers are host
+ *    memory.  The library never frees caller memory and the caller never frees library
+ *    memory; packed weights and the activation workspace belong to the handle.
+ *  - all work is enqueued on the caller's stream; the only hidden synchronisation is
+ *    in the *_host entry points (which return host results) and when the handle has to
+ *    grow its workspace or rebuild the positional table for a new frame count.
+ *  - one handle per (process, device); calls on one handle are not re-entrant.
+ */
+#ifndef COCR_B200_H_
+#define COCR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cocr_handle cocr_handle;
+
+typedef enum cocr_status {
+    COCR_OK = 0,
+    COCR_ERR_BAD_ARG = -1,        /* -> ValueError in the Python shim                     */
+    COCR_ERR_UNSUPPORTED = -2,    /* shape/hyper-parameter the kernels do not implement    */
+    COCR_ERR_OOM = -3,            /* -> RuntimeError('CUDA out of memory. ...')             */
+    COCR_ERR_CUDA = -4,           /* any other CUDA runtime/driver failure                 */
+    COCR_ERR_STATE = -5           /* call order violated (weights missing/not finalised)   */
+} cocr_status;
+
+typedef enum cocr_precision {
+    COCR_FP32 = 0,   /* CUDA-core fp32 everywhere; logits within 1e-4 (max-norm rel.) of the reference */
+    COCR_BF16 = 1    /* tcgen05 bf16 operands, fp32 accumulate / residual stream / statistics         */
+} cocr_precision;
+
+typedef enum cocr_mask_mode {
+    COCR_MASK_REFERENCE_UNMASKED = 0, /* what the reference computes: no mask (encoder.py:67-103)  */
+    COCR_MASK_RAGGED = 1              /* keys beyond a line's own length are excluded             */
+} cocr_mask_mode;
+
+/* Hyper-parameters: the ctor arguments of ConformerEncoder (conformer/encoder.py:135-152)
+ * as PytorchRecognitionModel passes them (pred.py:51-89), plus num_classes of the decoder
+ * nn.Linear (pred.py:90). */
+typedef struct cocr_hparams {
+    int32_t height;                     /* input_dim                                   */
+    int32_t encoder_dim;
+    int32_t num_layers;
+    int32_t num_heads;
+    int32_t ff_expansion;               /* feed_forward_expansion_factor               */
+    int32_t conv_expansion;             /* conv_expansion_factor (must be 2)           */
+    int32_t conv_kernel_size;           /* odd                                          */
+    int32_t half_step_residual;         /* bool                                         */
+    int32_t subsampling_conv_channels;
+    int32_t subsampling_factor;         /* only 4 is implemented                        */
+    int32_t num_classes;                /* 0 = encoder only                             */
+    int32_t precision;                  /* cocr_precision                               */
+    int32_t mask_mode;                  /* cocr_mask_mode                               */
+} cocr_hparams;
+
+/* Library version / build information (static string). */
+const char *cocr_version(void);
+
+/* Message of the last failure on this handle (or of the last failed cocr_create when
+ * `h` is NULL).  Never NULL. */
+const char *cocr_last_error(const cocr_handle *h);
+
+/* Replaces ConformerEncoder.__init__ + nn.Linear decoder construction (pred.py:75-92,
+ * model.py:99-116).  Validates the hyper-parameters with the reference's own rules
+ * (attention.py:53, convolution.py:132-133,180-181). */
+int cocr_create(const cocr_hparams *hp, int device, cocr_handle **out);
+int cocr_destroy(cocr_handle *h);
+
+/* Replaces nn.Module.load_state_dict for `PytorchRecognitionModel.nn` (pred.py:194,209).
+ * `key` is the state-dict name below the ModuleDict: "encoder...." / "decoder.weight" /
+ * "decoder.bias" (SURVEY.md §8a "Weights").  `data` is host fp32, C-contiguous, `shape`
+ * has `ndim` entries.  Unknown keys -> COCR_ERR_BAD_ARG; "num_batches_tracked" is ignored. */
+int cocr_set_weight(cocr_handle *h, const char *key, const float *data_host, int ndim, const int64_t *shape);
+/* Folds BatchNorm (eval), packs/casts the tensors for the kernels, uploads them. */
+int cocr_finalize_weights(cocr_handle *h);
+
+/* calc_length (conformer/convolution.py:240-247) for subsampling factor 4. */
+int32_t cocr_out_frames(int32_t width);
+
+/* ConformerEncoder.forward (conformer/encoder.py:183-204).
+ *   img_dev     fp32 image batch addressed as img[b*stride_b + w*stride_w + y*stride_h]
+ *               (element strides), b < B, w < W (time axis), y < height; covers both the
+ *               (N,1,H,W) collate layout (pred.py:119 takes a transposed view of it) and a
+ *               contiguous (B,W,H) tensor.
+ *   widths_dev  int32 (B) true widths (`input_lengths`); may be NULL = all W.
+ *   enc_out_dev fp32 (B, T, encoder_dim), T = cocr_out_frames(W).
+ *   out_lens_dev int32 (B) = calc_length(widths); may be NULL.                        */
+int cocr_encode(cocr_handle *h, const float *img_dev, int64_t stride_b, int64_t stride_w, int64_t stride_h,
+                const int32_t *widths_dev, int32_t B, int32_t W, void *stream,
+                float *enc_out_dev, int32_t *out_lens_dev);
+
+/* PytorchRecognitionModel.forward / RecognitionModel.forward (pred.py:118-122,
+ * model.py:125-127): encoder + decoder nn.Linear -> raw logits ("probits") fp32 (B,T,C). */
+int cocr_logits(cocr_handle *h, const float *img_dev, int64_t stride_b, int64_t stride_w, int64_t stride_h,
+                const int32_t *widths_dev, int32_t B, int32_t W, void *stream,
+                float *logits_dev, int32_t *out_lens_dev);
+
+/* kraken.lib.ctc_decoder.greedy_decoder applied per line to logits[b,:len_b,:]
+ * (call sites pred.py:138-143,158-163,173-177; model.py:163-167): argmax over classes
+ * (lowest index wins ties), merge runs, drop blank 0.
+ *   logits_dev fp32 (B,T,C); lens_dev int32 (B) or NULL (= T)
+ *   labels/starts/ends int32 (B,T), conf fp32 (B,T): first counts[b] entries per line are
+ *   valid; counts int32 (B).  ends are inclusive frame indices; conf = max winning logit. */
+int cocr_greedy_decode(cocr_handle *h, const float *logits_dev, const int32_t *lens_dev,
+                       int32_t B, int32_t T, int32_t C, void *stream,
+                       int32_t *labels_dev, int32_t *starts_dev, int32_t *ends_dev, float *conf_dev,
+                       int32_t *counts_dev);
+
+/* predict_labels (pred.py:165-178) without the (B,C,T) logits round trip through the
+ * host: encoder -> projection -> argmax -> collapse, all on the device. */
+int cocr_forward_decode(cocr_handle *h, const float *img_dev, int64_t stride_b, int64_t stride_w, int64_t stride_h,
+                        const int32_t *widths_dev, int32_t B, int32_t W, void *stream,
+                        int32_t *labels_dev, int32_t *starts_dev, int32_t *ends_dev, float *conf_dev,
+                        int32_t *counts_dev, int32_t *out_lens_dev);
+
+/* The same call a `cocr test` batch makes (cli/test.py:185-191), with HOST buffers:
+ * image batch (B,1,H,W) fp32 contiguous + int32 widths on the host (pinned or pageable),
+ * H2D copy, forward, decode, D2H of the packed result.  Synchronises `stream` before
+ * returning.  labels/starts/ends/conf are (B,T) host arrays, counts/out_lens (B). */
+int cocr_recognize_host(cocr_handle *h, const float *img_host, const int32_t *widths_host,
+                        int32_t B, int32_t W, void *stream,
+                        int32_t *labels_host, int32_t *starts_host, int32_t *ends_host, float *conf_host,
+                        int32_t *counts_host, int32_t *out_lens_host);
+
+/* Bytes of device workspace the handle holds after a call with this (B, W). */
+int cocr_workspace_bytes(cocr_handle *h, int32_t B, int32_t W, size_t *bytes);
+
+/* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
+int64_t cocr_launch_count(const cocr_handle *h);
+
+/* Per-kernel-family timing with CUDA events on the launching stream (bench.py's roofline leg).
+ * While enabled, every kernel launch of this handle is bracketed by an event pair.
+ * cocr_profile_report synchronises the device and writes one line per family:
+ *   "<name> <launches> <total_ms> <algorithmic_flops> <algorithmic_bytes>\n"
+ * into buf (NUL-terminated, truncated to cap), then clears the records. */
+int cocr_set_profiling(cocr_handle *h, int enabled);
+int cocr_profile_report(cocr_handle *h, char *buf, size_t cap);
+
+/* Built-in self checks of individual kernels against a scalar device reference; used by
+ * tests/ on the GPU box.  `which`: see csrc/selftest.cu.  Returns COCR_OK or an error and
+ * writes the max abs error into *max_err (may be NULL). */
+int cocr_selftest(int device, int which, int64_t p0, int64_t p1, int64_t p2, double *max_err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COCR_B200_H_ */

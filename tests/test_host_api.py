@@ -1,0 +1,109 @@
+"""Host-side logic and the C-ABI surface, without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import conformer_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from conformer_ocr_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from conformer_ocr_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'cocr_b200.h')).read()
+    declared = set(re.findall(r'\b(cocr_[a-z_0-9]+)\s*\(', header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b'sm_100a' in lib.cocr_version()
+
+
+def test_out_frames_matches_calc_length(lib):
+    from conformer_ocr_b200.engine import out_frames
+    widths = np.array([1, 2, 3, 4, 5, 100, 1024, 1025, 1536, 2048, 4096])
+    want = O.calc_length(widths)
+    np.testing.assert_array_equal(out_frames(torch.from_numpy(widths)).numpy(), want)
+    np.testing.assert_array_equal([lib.cocr_out_frames(int(w)) for w in widths], want)
+
+
+def test_create_rejects_bad_hparams_like_the_reference(lib):
+    from conformer_ocr_b200 import _lib
+    hp = _lib.cocr_hparams(96, 144, 16, 5, 4, 2, 31, 1, 32, 4, 10, 0, 0)   # 144 % 5 != 0
+    h = ctypes.c_void_p()
+    rc = lib.cocr_create(ctypes.byref(hp), 0, ctypes.byref(h))
+    assert rc == _lib.COCR_ERR_BAD_ARG
+    assert b'num_heads' in lib.cocr_last_error(None)
+    with pytest.raises(ValueError):
+        _lib.raise_for_status(rc)
+    hp = _lib.cocr_hparams(96, 144, 16, 4, 4, 2, 30, 1, 32, 4, 10, 0, 0)   # even kernel size
+    assert lib.cocr_create(ctypes.byref(hp), 0, ctypes.byref(h)) == _lib.COCR_ERR_BAD_ARG
+
+
+def test_module_mirrors_reference_state_dict():
+    from conformer_ocr_b200 import PytorchRecognitionModel, ConformerEncoder, RECOGNITION_HYPER_PARAMS
+    hp = dict(RECOGNITION_HYPER_PARAMS)
+    net = PytorchRecognitionModel(num_classes=37, codec=['a', 'b'], **hp)
+    want = dict(O.weight_spec(O.DEFAULT_HPARAMS, 37))
+    got = {k: tuple(v.shape) for k, v in net.nn.state_dict().items() if not k.endswith('num_batches_tracked')}
+    assert got == want
+    assert net.nn['encoder'].count_parameters() == 8217904        # SURVEY.md §0 [probed on the reference]
+    assert (net.height, net.channels, net.width) == (96, 1, 0)
+    # constructor checks of the reference
+    with pytest.raises(AssertionError):
+        ConformerEncoder(input_dim=96, encoder_dim=144, num_attention_heads=5)
+    with pytest.raises(AssertionError):
+        ConformerEncoder(input_dim=96, encoder_dim=144, num_attention_heads=4, conv_kernel_size=30)
+    with pytest.raises(ValueError):
+        ConformerEncoder(input_dim=96, encoder_dim=144, num_attention_heads=4, subsampling_factor=6)
+
+
+def test_no_cpu_fallback():
+    from conformer_ocr_b200 import PytorchRecognitionModel, RECOGNITION_HYPER_PARAMS
+    net = PytorchRecognitionModel(num_classes=5, codec=None, **RECOGNITION_HYPER_PARAMS)
+    with pytest.raises(RuntimeError, match='no CPU fallback|CUDA'):
+        net(torch.zeros(1, 1, 96, 32), torch.tensor([32]))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'conformer_ocr_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.h', '.cuh')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'oracle' not in src.replace('test / baseline', ''), f'{f} mentions the oracle'
+
+
+def test_label_codec_decode_contract():
+    from conformer_ocr_b200.codec import LabelCodec
+    c = LabelCodec({'a': [1], 'b': [2]})
+    assert c.decode([(2, 0, 1, .5), (1, 3, 3, .25), (9, 4, 4, .1)]) == [('b', 0, 1, .5), ('a', 3, 3, .25)]
+    assert LabelCodec('xy').decode([(1, 0, 0, 1.0)]) == [('x', 0, 0, 1.0)]
+
+
+def test_product_synthetic_generator_equals_test_generator():
+    from conformer_ocr_b200 import synthetic as S
+    hp = dict(O.DEFAULT_HPARAMS, num_encoder_layers=2)
+    a, b = S.make_weights(hp, 17, seed=3), O.make_weights(hp, 17, seed=3)
+    assert list(a) == list(b)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k])
+    ia, la = S.make_lines(3, 96, 50, seed=4, widths=[50, 20, 7])
+    ib, lb = O.make_lines(3, 96, 50, seed=4, widths=[50, 20, 7])
+    np.testing.assert_array_equal(ia, ib)
+    np.testing.assert_array_equal(la, lb)
+    # 4.95 GF/line at W=1024,C=200 ; 8.11 at 1536 ; 11.71 at 2048 ; 33.57 at 4096/10k
+    for (W, C), want in {(1024, 200): 4.95, (1536, 200): 8.11, (2048, 200): 11.71, (4096, 10000): 33.57}.items():
+        assert abs(S.flops_per_line(W, C, O.DEFAULT_HPARAMS) / 1e9 - want) < 0.01

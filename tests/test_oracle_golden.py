@@ -86,3 +86,14 @@ def test_masked_mode_equals_unmasked_for_equal_widths_and_differs_for_ragged():
     b, olens = O.recognition_forward(img, lens, w, hp, masked=True)
     np.testing.assert_allclose(a[0], b[0], rtol=0, atol=1e-5)   # widest line: nothing masked
     assert np.abs(a[2, :olens[2]] - b[2, :olens[2]]).max() > 1e-3
+
+
+@pytest.mark.parametrize('name', GOLDEN_CASES)
+def test_torch_port_matches_reference_logits(name):
+    import torch
+    from oracle import torch_port as TP
+    meta, arrs = load_golden(name)
+    hp, w, img, lens = golden_inputs(meta)
+    logits, olens = TP.recognition_forward(torch.from_numpy(img), torch.from_numpy(lens), TP.to_torch(w), hp)
+    np.testing.assert_array_equal(olens.numpy(), arrs['enc_lens'])
+    assert rel_err(logits.numpy(), arrs['logits']) < ORACLE_TOL
