@@ -1,22 +1,525 @@
-// bf16 tensor-core path (placeholder until the tcgen05 kernels land in this file).
+// bf16 tensor-core path (cocr_precision COCR_BF16).
+//
+// Every dense contraction (subsampling out-projection, FFN, QKV / output projections, pointwise convs,
+// CTC projection) runs on tcgen05 tensor cores through k_gemm_tc (gemm_tc.cuh): bf16 operands staged by
+// TMA, fp32 accumulation in TMEM.  The residual stream, LayerNorm statistics and softmax stay fp32.
+// Reference symbols: same as fp32_path.cu.
+#include <math.h>
+
 #include "common.h"
+#include "gemm_tc.cuh"
 
 namespace cocr {
 
-struct Bf16State { int dummy; };
+typedef __nv_bfloat16 bf16;
 
-int bf16_init(cocr_handle *h) { return set_error(h, COCR_ERR_UNSUPPORTED, "bf16 path not built yet"); }
-void bf16_destroy(cocr_handle *h) { delete h->bf; h->bf = nullptr; }
-int bf16_encode(cocr_handle *h, const float *, int64_t, int64_t, int64_t, const int32_t *, int, int, cudaStream_t, float *, int32_t *) {
-    return set_error(h, COCR_ERR_UNSUPPORTED, "bf16 path not built yet");
+struct Bf16State {
+    bf16 *arena = nullptr;        // bf16 mirror of the fp32 weight arena (same offsets)
+    int smem_optin = 0;
+};
+
+// ------------------------------------------------------------------------------------------
+// driver entry point for tensor maps (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
 }
-size_t bf16_workspace_bytes(const cocr_handle *, int, int) { return 0; }
-int bf16_forward_decode(cocr_handle *h, const float *, int64_t, int64_t, int64_t, const int32_t *, int, int, cudaStream_t,
-                        int32_t *, int32_t *, int32_t *, float *, int32_t *, int32_t *) {
-    return set_error(h, COCR_ERR_UNSUPPORTED, "bf16 path not built yet");
+
+// 2-D row-major bf16 matrix (rows x cols, leading dimension ld elements) -> SWIZZLE_128B box (64 cols x box_rows)
+static int make_tmap_bf16(cocr_handle *h, CUtensorMap *m, const void *base, int64_t rows, int64_t cols, int64_t ld,
+                          int box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return set_error(h, COCR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error(h, COCR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box_rows=%d", (int)r,
+                         (long long)rows, (long long)cols, (long long)ld, box_rows);
+    return COCR_OK;
 }
-int bf16_logits(cocr_handle *h, const float *, int64_t, int64_t, int64_t, const int32_t *, int, int, cudaStream_t, float *, int32_t *) {
-    return set_error(h, COCR_ERR_UNSUPPORTED, "bf16 path not built yet");
+
+// ------------------------------------------------------------------------------------------
+// GEMM launcher
+// ------------------------------------------------------------------------------------------
+static int pick_block_n(int N) {
+    if (N <= 256) return (N + 15) / 16 * 16;
+    // largest multiple of 16 that divides N exactly and is <= 256, else 256 with a ragged last tile
+    for (int bn = 256; bn >= 64; bn -= 16)
+        if (N % bn == 0) return bn;
+    return 256;
+}
+
+int launch_gemm_tc(cocr_handle *h, int epi, const bf16 *A, int lda, const bf16 *W, int ldw, const float *bias, void *out,
+                   int ldc, unsigned long long *best, int M, int N, int K, cudaStream_t st, int block_n_override = 0) {
+    if (M <= 0 || N <= 0) return COCR_OK;
+    if (K % 16 != 0 || lda % 8 != 0 || ldw % 8 != 0)
+        return set_error(h, COCR_ERR_UNSUPPORTED, "tensor-core GEMM needs K %% 16 == 0 and 16-byte aligned rows (K=%d lda=%d ldw=%d)", K,
+                         lda, ldw);
+    GemmArgs p;
+    p.M = M; p.N = N; p.K = K;
+    p.block_n = block_n_override ? block_n_override : pick_block_n(N);
+    p.n_tiles = (N + p.block_n - 1) / p.block_n;
+    p.m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+    p.nkc = (K + GEMM_KC - 1) / GEMM_KC;
+    p.last_ksteps = (K - (p.nkc - 1) * GEMM_KC) / 16;
+    p.bias = bias; p.out = out; p.ldc = ldc; p.best = best;
+    int tm = 32;
+    while (tm < 2 * p.block_n) tm <<= 1;
+    p.tmem_cols = tm;
+    const uint32_t b_chunk = gemm_b_chunk_bytes(p.block_n);
+    const uint32_t fixed = 4 * 2 * 4096 + 2048 + 256 + 1024;        // staging + bias + barriers + alignment slack
+    const uint32_t budget = (uint32_t)h->bf->smem_optin;
+    // resident weights when the whole K extent of one N-slice fits next to >= 4 A slots
+    const uint32_t bres = (uint32_t)p.nkc * b_chunk;
+    p.resident = (bres + 4 * GEMM_A_CHUNK + fixed <= budget) && (p.n_tiles <= h->num_sms) ? 1 : 0;
+    const uint32_t slot = GEMM_A_CHUNK + (p.resident ? 0u : b_chunk);
+    const uint32_t avail = budget - fixed - (p.resident ? bres : 0u);
+    int stages = (int)(avail / slot);
+    if (stages > 8) stages = 8;
+    if (stages < 2) return set_error(h, COCR_ERR_UNSUPPORTED, "GEMM tile does not fit shared memory (N=%d K=%d)", N, K);
+    p.stages = stages;
+    const uint32_t smem = fixed + (p.resident ? bres : 0u) + (uint32_t)stages * slot;
+
+    CUtensorMap tmA, tmB;
+    COCR_TRY(make_tmap_bf16(h, &tmA, A, M, K, lda, GEMM_BM));
+    COCR_TRY(make_tmap_bf16(h, &tmB, W, N, K, ldw, p.block_n));
+
+    int grid;
+    if (p.resident) {
+        int groups = h->num_sms / p.n_tiles;
+        if (groups > p.m_tiles) groups = p.m_tiles;
+        if (groups < 1) groups = 1;
+        grid = groups * p.n_tiles;
+    } else {
+        grid = p.m_tiles * p.n_tiles;
+        if (grid > h->num_sms) grid = h->num_sms;
+    }
+    const double flops = 2.0 * M * (double)N * K;
+    const double bytes = 2.0 * ((double)M * K + (double)N * K) + (epi == EPI_ARGMAX ? 8.0 * M : (epi == EPI_F32 ? 4.0 : 2.0) * (double)M * N);
+    ProfScope ps(h, epi == EPI_ARGMAX ? "gemm_tc_argmax" : "gemm_tc_bf16", st, flops, bytes);
+#define COCR_GEMM_CASE(E)                                                                                              \
+    case E: {                                                                                                          \
+        static int attr_smem = 0;                                                                                      \
+        if ((int)smem > attr_smem) {                                                                                   \
+            COCR_CUDA(h, cudaFuncSetAttribute(k_gemm_tc<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget)); \
+            attr_smem = (int)budget;                                                                                   \
+        }                                                                                                              \
+        k_gemm_tc<E><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, p);                                                   \
+        break;                                                                                                         \
+    }
+    switch (epi) {
+        COCR_GEMM_CASE(EPI_BF16)
+        COCR_GEMM_CASE(EPI_BF16_SILU)
+        COCR_GEMM_CASE(EPI_F32)
+        COCR_GEMM_CASE(EPI_ARGMAX)
+        default: return set_error(h, COCR_ERR_BAD_ARG, "unknown GEMM epilogue %d", epi);
+    }
+#undef COCR_GEMM_CASE
+    COCR_LAUNCHED(h);
+    return COCR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// memory-bound row kernels of the bf16 path
+// ------------------------------------------------------------------------------------------
+__global__ void k_f32_to_bf16(const float *__restrict__ src, bf16 *__restrict__ dst, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// One warp per frame.  x (fp32 residual stream) <- [x +] alpha*y ; optional block-final LayerNorm applied to x
+// itself (encoder.py:99); then xn = bf16(LayerNorm(x; g1,b1)) for the next module (or bf16(x) when g1 == null).
+//   init != 0 : x = y   (start of the stream, after the subsampling projection)
+constexpr int ROW_MAXPER = 16;   // supports d <= 512
+__global__ void __launch_bounds__(256)
+k_resid_ln(float *__restrict__ x, const bf16 *__restrict__ y, float alpha, int init, const float *__restrict__ gf,
+           const float *__restrict__ bfin, const float *__restrict__ g1, const float *__restrict__ b1,
+           bf16 *__restrict__ xn, int M, int d) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    float v[ROW_MAXPER];
+    float *xr = x + (int64_t)row * d;
+    const bf16 *yr = y + (int64_t)row * d;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < ROW_MAXPER; ++i) {
+        int c = lane + 32 * i;
+        float t = 0.f;
+        if (c < d) {
+            float yy = __bfloat162float(yr[c]);
+            t = init ? yy : fmaf(alpha, yy, xr[c]);
+        }
+        v[i] = t;
+        s += t;
+    }
+    const float inv_d = 1.0f / (float)d;
+    if (gf) {   // block-final LayerNorm replaces the residual stream
+        float mean = warp_sum_f(s) * inv_d;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < ROW_MAXPER; ++i) {
+            int c = lane + 32 * i;
+            float t = (c < d) ? v[i] - mean : 0.f;
+            q = fmaf(t, t, q);
+        }
+        float rstd = rsqrtf(warp_sum_f(q) * inv_d + 1e-5f);
+        s = 0.f;
+#pragma unroll
+        for (int i = 0; i < ROW_MAXPER; ++i) {
+            int c = lane + 32 * i;
+            if (c < d) {
+                v[i] = (v[i] - mean) * rstd * gf[c] + bfin[c];
+                s += v[i];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < ROW_MAXPER; ++i) {
+        int c = lane + 32 * i;
+        if (c < d) xr[c] = v[i];
+    }
+    bf16 *nr = xn + (int64_t)row * d;
+    if (g1) {
+        float mean = warp_sum_f(s) * inv_d;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < ROW_MAXPER; ++i) {
+            int c = lane + 32 * i;
+            float t = (c < d) ? v[i] - mean : 0.f;
+            q = fmaf(t, t, q);
+        }
+        float rstd = rsqrtf(warp_sum_f(q) * inv_d + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < ROW_MAXPER; ++i) {
+            int c = lane + 32 * i;
+            if (c < d) nr[c] = __float2bfloat16_rn((v[i] - mean) * rstd * g1[c] + b1[c]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < ROW_MAXPER; ++i) {
+            int c = lane + 32 * i;
+            if (c < d) nr[c] = __float2bfloat16_rn(v[i]);
+        }
+    }
+}
+
+static int launch_resid_ln(cocr_handle *h, float *x, const bf16 *y, float alpha, int init, const float *gf, const float *bfin,
+                           const float *g1, const float *b1, bf16 *xn, int M, int d, cudaStream_t st) {
+    ProfScope ps(h, "resid_layernorm", st, 0.0, (double)M * d * (init ? 8.0 : 12.0));
+    k_resid_ln<<<(M + 7) / 8, 256, 0, st>>>(x, y, alpha, init, gf, bfin, g1, b1, xn, M, d);
+    COCR_LAUNCHED(h);
+    return COCR_OK;
+}
+
+__global__ void k_unpack_best(const unsigned long long *__restrict__ packed, int64_t M, float *__restrict__ val,
+                              int32_t *__restrict__ idx) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    float v;
+    int c;
+    unpack_best(packed[i], &v, &c);
+    val[i] = v;
+    idx[i] = c;
+}
+
+// ------------------------------------------------------------------------------------------
+// plan / forward
+// ------------------------------------------------------------------------------------------
+struct Bf16Plan {
+    int B, W, T2, T, M;
+    size_t off_a1, off_a2, off_feat, off_x, off_xn, off_y, off_h, off_g, off_best, off_best_val, off_best_idx, total;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static void bf16_plan(const cocr_handle *h, int B, int W, Bf16Plan *p) {
+    const Dims &dm = h->dm;
+    p->B = B; p->W = W;
+    p->T2 = out_len1(W);
+    p->T = out_len1(p->T2);
+    p->M = B * p->T;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+    const size_t M = (size_t)p->M;
+    p->off_a1 = take((size_t)B * p->T2 * dm.F2 * dm.cc * 4);
+    p->off_a2 = take(M * dm.F * dm.cc * 4);
+    p->off_feat = take(M * dm.feat * 2);
+    p->off_x = take(M * dm.d * 4);
+    p->off_xn = take(M * dm.d * 2);
+    p->off_y = take(M * dm.d * 2);
+    size_t wide = (size_t)dm.ff > (size_t)3 * dm.d ? dm.ff : 3 * dm.d;
+    p->off_h = take(M * wide * 2);
+    p->off_g = take(M * dm.d * 2);
+    p->off_best = take(M * 8);
+    p->off_best_val = take(M * 4);
+    p->off_best_idx = take(M * 4);
+    p->total = off;
+}
+
+size_t bf16_workspace_bytes(const cocr_handle *h, int B, int W) {
+    Bf16Plan p;
+    bf16_plan(h, B, W, &p);
+    return p.total;
+}
+
+int bf16_init(cocr_handle *h) {
+    const Dims &dm = h->dm;
+    if (dm.d % 16 != 0 || dm.ff % 16 != 0 || dm.feat % 16 != 0 || dm.d > 32 * ROW_MAXPER)
+        return set_error(h, COCR_ERR_UNSUPPORTED,
+                         "bf16 path needs encoder_dim, ff dim and subsampled feature dim to be multiples of 16 and encoder_dim <= %d "
+                         "(got %d, %d, %d)", 32 * ROW_MAXPER, dm.d, dm.ff, dm.feat);
+    if (!h->bf) h->bf = new Bf16State();
+    Bf16State *bs = h->bf;
+    if (bs->arena) { cudaFree(bs->arena); bs->arena = nullptr; }
+    void *p = nullptr;
+    COCR_CUDA(h, cudaMalloc(&p, h->arena_floats * sizeof(bf16)));
+    bs->arena = (bf16 *)p;
+    k_f32_to_bf16<<<1024, 256>>>(h->arena, bs->arena, h->arena_floats);
+    COCR_LAUNCHED(h);
+    COCR_CUDA(h, cudaDeviceSynchronize());
+    COCR_CUDA(h, cudaDeviceGetAttribute(&bs->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    if (!get_encode()) return set_error(h, COCR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    return COCR_OK;
+}
+
+void bf16_destroy(cocr_handle *h) {
+    if (!h->bf) return;
+    if (h->bf->arena) cudaFree(h->bf->arena);
+    delete h->bf;
+    h->bf = nullptr;
+}
+
+static inline const bf16 *WB(const cocr_handle *h, const float *w) { return h->bf->arena + (w - h->arena); }
+
+// encoder forward; leaves x (fp32) and xn = bf16(x) in the workspace
+static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths, int B,
+                        int W, cudaStream_t st, int32_t *out_lens, Bf16Plan &p) {
+    const Dims &dm = h->dm;
+    bf16_plan(h, B, W, &p);
+    COCR_TRY(ensure_workspace(h, p.total));
+    COCR_TRY(ensure_pos_proj(h, p.T, st));
+    char *ws = h->ws.base;
+    float *a1 = (float *)(ws + p.off_a1), *a2 = (float *)(ws + p.off_a2);
+    bf16 *feat = (bf16 *)(ws + p.off_feat);
+    float *x = (float *)(ws + p.off_x);
+    bf16 *xn = (bf16 *)(ws + p.off_xn), *y = (bf16 *)(ws + p.off_y), *hb = (bf16 *)(ws + p.off_h), *g = (bf16 *)(ws + p.off_g);
+    const int M = p.M, d = dm.d;
+
+    if (out_lens) COCR_TRY(launch_out_lens(h, widths, B, W, out_lens, st));
+    const int32_t *lens_dev = nullptr;
+    if (h->hp.mask_mode == COCR_MASK_RAGGED && widths) {
+        int32_t *tmp = (int32_t *)(ws + p.off_best_idx);
+        COCR_TRY(launch_out_lens(h, widths, B, W, tmp, st));
+        lens_dev = tmp;
+    }
+    // front-end (convolution.py:227-237): direct convs on CUDA cores, 1x1 conv as an fp32 GEMM writing bf16 features,
+    // 768->144 projection on tensor cores
+    COCR_TRY(launch_frontend_convs(h, img, sb, sw, sh, B, W, a1, a2, st));
+    COCR_TRY(launch_sgemm(h, a2, dm.cc, h->sub_wpw, dm.cc, h->sub_bpw, (float *)feat, dm.cc, M * dm.F, dm.cc, dm.cc, 2, nullptr, 0,
+                          0.f, st, /*out_bf16=*/1));
+    COCR_TRY(launch_gemm_tc(h, EPI_BF16, feat, dm.feat, WB(h, h->sub_wout), dm.feat, h->sub_bout, y, d, nullptr, M, d, dm.feat, st));
+    if (dm.L == 0) {
+        COCR_TRY(launch_resid_ln(h, x, y, 1.f, 1, nullptr, nullptr, nullptr, nullptr, xn, M, d, st));
+        return COCR_OK;
+    }
+    COCR_TRY(launch_resid_ln(h, x, y, 1.f, 1, nullptr, nullptr, h->layers[0].ffn_ln_g[0], h->layers[0].ffn_ln_b[0], xn, M, d, st));
+    for (int l = 0; l < dm.L; ++l) {
+        const LayerF32 &lw = h->layers[l];
+        // FFN 1 (feed_forward.py:45-55; half-step residual encoder.py:68-75)
+        COCR_TRY(launch_gemm_tc(h, EPI_BF16_SILU, xn, d, WB(h, lw.ffn_w1[0]), d, lw.ffn_b1[0], hb, dm.ff, nullptr, M, dm.ff, d, st));
+        COCR_TRY(launch_gemm_tc(h, EPI_BF16, hb, dm.ff, WB(h, lw.ffn_w2[0]), dm.ff, lw.ffn_b2[0], y, d, nullptr, M, d, dm.ff, st));
+        COCR_TRY(launch_resid_ln(h, x, y, dm.ffn_factor, 0, nullptr, nullptr, lw.att_ln_g, lw.att_ln_b, xn, M, d, st));
+        // MHSA (attention.py:72-151)
+        COCR_TRY(launch_gemm_tc(h, EPI_BF16, xn, d, WB(h, lw.w_qkv), d, lw.b_qkv, hb, 3 * d, nullptr, M, 3 * d, d, st));
+        COCR_TRY(launch_attn_simt_bf16(h, hb, h->pos_proj + (size_t)l * (2 * p.T - 1) * d, lw.u_bias, lw.v_bias, lens_dev, g, B,
+                                       p.T, st));
+        COCR_TRY(launch_gemm_tc(h, EPI_BF16, g, d, WB(h, lw.w_out), d, lw.b_out, y, d, nullptr, M, d, d, st));
+        COCR_TRY(launch_resid_ln(h, x, y, 1.f, 0, nullptr, nullptr, lw.conv_ln_g, lw.conv_ln_b, xn, M, d, st));
+        // convolution module (convolution.py:135-148)
+        COCR_TRY(launch_gemm_tc(h, EPI_BF16, xn, d, WB(h, lw.w_pw1), d, lw.b_pw1, hb, 2 * d, nullptr, M, 2 * d, d, st));
+        COCR_TRY(launch_glu_dw_bf16(h, hb, lw, g, B, p.T, st));
+        COCR_TRY(launch_gemm_tc(h, EPI_BF16, g, d, WB(h, lw.w_pw2), d, lw.b_pw2, y, d, nullptr, M, d, d, st));
+        COCR_TRY(launch_resid_ln(h, x, y, 1.f, 0, nullptr, nullptr, lw.ffn_ln_g[1], lw.ffn_ln_b[1], xn, M, d, st));
+        // FFN 2 + block-final LayerNorm (encoder.py:91-99) + next block's first LayerNorm
+        COCR_TRY(launch_gemm_tc(h, EPI_BF16_SILU, xn, d, WB(h, lw.ffn_w1[1]), d, lw.ffn_b1[1], hb, dm.ff, nullptr, M, dm.ff, d, st));
+        COCR_TRY(launch_gemm_tc(h, EPI_BF16, hb, dm.ff, WB(h, lw.ffn_w2[1]), dm.ff, lw.ffn_b2[1], y, d, nullptr, M, d, dm.ff, st));
+        const float *ng = (l + 1 < dm.L) ? h->layers[l + 1].ffn_ln_g[0] : nullptr;
+        const float *nb = (l + 1 < dm.L) ? h->layers[l + 1].ffn_ln_b[0] : nullptr;
+        COCR_TRY(launch_resid_ln(h, x, y, dm.ffn_factor, 0, lw.final_ln_g, lw.final_ln_b, ng, nb, xn, M, d, st));
+    }
+    return COCR_OK;
+}
+
+int bf16_encode(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths, int B, int W,
+                cudaStream_t st, float *enc_out, int32_t *out_lens) {
+    Bf16Plan p;
+    COCR_TRY(bf16_forward(h, img, sb, sw, sh, widths, B, W, st, out_lens, p));
+    COCR_CUDA(h, cudaMemcpyAsync(enc_out, h->ws.base + p.off_x, (size_t)p.M * h->dm.d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return COCR_OK;
+}
+
+int bf16_logits(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths, int B, int W,
+                cudaStream_t st, float *logits, int32_t *out_lens) {
+    Bf16Plan p;
+    COCR_TRY(bf16_forward(h, img, sb, sw, sh, widths, B, W, st, out_lens, p));
+    const Dims &dm = h->dm;
+    return launch_gemm_tc(h, EPI_F32, (const bf16 *)(h->ws.base + p.off_xn), dm.d, WB(h, h->dec_w), dm.d, h->dec_b, logits, dm.C,
+                          nullptr, p.M, dm.C, dm.d, st);
+}
+
+int bf16_forward_decode(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths, int B,
+                        int W, cudaStream_t st, int32_t *labels, int32_t *starts, int32_t *ends, float *conf, int32_t *counts,
+                        int32_t *out_lens) {
+    Bf16Plan p;
+    COCR_TRY(bf16_forward(h, img, sb, sw, sh, widths, B, W, st, out_lens, p));
+    const Dims &dm = h->dm;
+    char *ws = h->ws.base;
+    unsigned long long *best = (unsigned long long *)(ws + p.off_best);
+    float *bv = (float *)(ws + p.off_best_val);
+    int32_t *bi = (int32_t *)(ws + p.off_best_idx);
+    COCR_CUDA(h, cudaMemsetAsync(best, 0, (size_t)p.M * 8, st));
+    // CTC projection fused with the per-frame arg-max: logits never reach HBM (pred.py:121 + :138-143)
+    COCR_TRY(launch_gemm_tc(h, EPI_ARGMAX, (const bf16 *)(ws + p.off_xn), dm.d, WB(h, h->dec_w), dm.d, h->dec_b, nullptr, 0, best,
+                            p.M, dm.C, dm.d, st));
+    k_unpack_best<<<(p.M + 255) / 256, 256, 0, st>>>(best, p.M, bv, bi);
+    COCR_LAUNCHED(h);
+    return launch_collapse(h, bv, bi, out_lens, B, p.T, st, labels, starts, ends, conf, counts);
+}
+
+// ------------------------------------------------------------------------------------------
+// self test of the tensor-core GEMM against a scalar device reference
+// ------------------------------------------------------------------------------------------
+__global__ void k_ref_gemm(const bf16 *A, const bf16 *W, const float *bias, float *C, int M, int N, int K, int silu) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)M * N) return;
+    int m = (int)(idx / N), n = (int)(idx % N);
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc = fmaf(__bfloat162float(A[(int64_t)m * K + k]), __bfloat162float(W[(int64_t)n * K + k]), acc);
+    acc += bias[n];
+    if (silu) acc = acc / (1.0f + expf(-acc));
+    C[idx] = acc;
+}
+
+__global__ void k_fill_bf16(bf16 *p, size_t n, uint32_t seed, float scale) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s = (uint32_t)i * 2654435761u + seed;
+    s ^= s >> 16; s *= 2246822519u; s ^= s >> 13; s *= 3266489917u; s ^= s >> 16;
+    p[i] = __float2bfloat16_rn(((float)(s & 0xFFFF) / 32768.0f - 1.0f) * scale);
+}
+__global__ void k_fill_f32(float *p, size_t n, uint32_t seed, float scale) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s = (uint32_t)i * 2654435761u + seed;
+    s ^= s >> 16; s *= 2246822519u; s ^= s >> 13; s *= 3266489917u; s ^= s >> 16;
+    p[i] = ((float)(s & 0xFFFF) / 32768.0f - 1.0f) * scale;
+}
+
+// which: 10 + epi ; p0 = M, p1 = N, p2 = K  (block_n chosen as in production; p2 >= 100000 encodes an override:
+// K = p2 % 100000, block_n = p2 / 100000)
+int selftest_gemm(int device, int epi, int M, int N, int K, int block_n, double *max_err) {
+    cocr_hparams hp = {96, 144, 0, 4, 4, 2, 31, 1, 32, 4, 0, COCR_FP32, 0};
+    cocr_handle *h = nullptr;
+    int rc = cocr_create(&hp, device, &h);
+    if (rc != COCR_OK) return rc;
+    h->bf = new Bf16State();
+    cudaDeviceGetAttribute(&h->bf->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    bf16 *A = nullptr, *Wt = nullptr;
+    float *bias = nullptr, *ref = nullptr;
+    void *out = nullptr;
+    unsigned long long *best = nullptr;
+    auto fail = [&](int code, const char *msg) {
+        set_global_error(h->err.empty() ? msg : h->err.c_str());
+        cudaFree(A); cudaFree(Wt); cudaFree(bias); cudaFree(ref); cudaFree(out); cudaFree(best);
+        cocr_destroy(h);
+        return code;
+    };
+    cudaMalloc((void **)&A, (size_t)M * K * 2);
+    cudaMalloc((void **)&Wt, (size_t)N * K * 2);
+    cudaMalloc((void **)&bias, (size_t)N * 4);
+    cudaMalloc((void **)&ref, (size_t)M * N * 4);
+    cudaMalloc(&out, (size_t)M * N * 4);
+    cudaMalloc((void **)&best, (size_t)M * 8);
+    cudaMemset(best, 0, (size_t)M * 8);
+    cudaMemset(out, 0xFF, (size_t)M * N * 4);
+    k_fill_bf16<<<(unsigned)(((size_t)M * K + 255) / 256), 256>>>(A, (size_t)M * K, 1u, 1.0f);
+    k_fill_bf16<<<(unsigned)(((size_t)N * K + 255) / 256), 256>>>(Wt, (size_t)N * K, 2u, 0.25f);
+    k_fill_f32<<<(N + 255) / 256, 256>>>(bias, (size_t)N, 3u, 0.5f);
+    k_ref_gemm<<<(unsigned)(((size_t)M * N + 255) / 256), 256>>>(A, Wt, bias, ref, M, N, K, epi == EPI_BF16_SILU);
+    rc = launch_gemm_tc(h, epi, A, K, Wt, K, bias, out, N, best, M, N, K, 0, block_n);
+    if (rc != COCR_OK) return fail(rc, "launch failed");
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        set_error(h, COCR_ERR_CUDA, "selftest_gemm: %s", cudaGetErrorString(e));
+        return fail(COCR_ERR_CUDA, "sync failed");
+    }
+    std::vector<float> href((size_t)M * N);
+    cudaMemcpy(href.data(), ref, href.size() * 4, cudaMemcpyDeviceToHost);
+    double worst = 0.0;
+    if (epi == EPI_ARGMAX) {
+        std::vector<unsigned long long> hb(M);
+        cudaMemcpy(hb.data(), best, (size_t)M * 8, cudaMemcpyDeviceToHost);
+        for (int m = 0; m < M; ++m) {
+            uint32_t b = (uint32_t)(hb[m] >> 32);
+            b = (b & 0x80000000u) ? (b & 0x7FFFFFFFu) : ~b;
+            float v;
+            memcpy(&v, &b, 4);
+            int col = (int)(0xFFFFFFFFu - (uint32_t)(hb[m] & 0xFFFFFFFFull));
+            float rv = -INFINITY;
+            for (int n = 0; n < N; ++n) rv = fmaxf(rv, href[(size_t)m * N + n]);
+            double err = fabs((double)v - rv);
+            if (col < 0 || col >= N) err = 1e9;
+            else err = fmax(err, fabs((double)href[(size_t)m * N + col] - rv));   // the chosen column must be a (near-)maximum
+            worst = fmax(worst, err);
+        }
+    } else if (epi == EPI_F32) {
+        std::vector<float> ho((size_t)M * N);
+        cudaMemcpy(ho.data(), out, ho.size() * 4, cudaMemcpyDeviceToHost);
+        for (size_t i = 0; i < ho.size(); ++i) {
+            double err = fabs((double)ho[i] - href[i]);
+            if (!(err == err)) err = 1e9;
+            worst = fmax(worst, err);
+        }
+    } else {
+        std::vector<uint16_t> ho((size_t)M * N);
+        cudaMemcpy(ho.data(), out, ho.size() * 2, cudaMemcpyDeviceToHost);
+        for (size_t i = 0; i < ho.size(); ++i) {
+            uint32_t b = (uint32_t)ho[i] << 16;
+            float v;
+            memcpy(&v, &b, 4);
+            double err = fabs((double)v - href[i]) / (1.0 + fabs((double)href[i]));
+            if (!(err == err)) err = 1e9;
+            worst = fmax(worst, err);
+        }
+    }
+    if (max_err) *max_err = worst;
+    cudaFree(A); cudaFree(Wt); cudaFree(bias); cudaFree(ref); cudaFree(out); cudaFree(best);
+    cocr_destroy(h);
+    return COCR_OK;
 }
 
 }  // namespace cocr

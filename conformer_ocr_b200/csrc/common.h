@@ -166,7 +166,14 @@ int ensure_pos_proj(cocr_handle *h, int T, cudaStream_t st);
 // generic fp32 GEMM: C[m,n] = epi(sum_k A[m,k] W[n,k] + bias[n]); act 0 none / 1 SiLU / 2 ReLU;
 // res != null: C = res + alpha * value
 int launch_sgemm(cocr_handle *h, const float *A, int lda, const float *Wt, int ldw, const float *bias, float *Cout,
-                 int ldc, int M, int N, int K, int act, const float *res, int ldres, float alpha, cudaStream_t st);
+                 int ldc, int M, int N, int K, int act, const float *res, int ldres, float alpha, cudaStream_t st,
+                 int out_bf16 = 0);
+int launch_frontend_convs(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, int B, int W, float *a1,
+                          float *a2, cudaStream_t st);
+int launch_attn_simt_bf16(cocr_handle *h, const __nv_bfloat16 *qkv, const float *pos, const float *ub, const float *vb,
+                          const int32_t *lens, __nv_bfloat16 *ctx, int B, int T, cudaStream_t st);
+int launch_glu_dw_bf16(cocr_handle *h, const __nv_bfloat16 *u, const LayerF32 &lw, __nv_bfloat16 *g, int B, int T,
+                       cudaStream_t st);
 int launch_layernorm(cocr_handle *h, const float *x, float *y, const float *g, const float *b, int M, int d,
                      cudaStream_t st);
 

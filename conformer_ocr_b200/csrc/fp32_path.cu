@@ -21,6 +21,11 @@ namespace cocr {
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float silu_acc(float x) { return x * sigmoid_acc(x); }
 
+__device__ __forceinline__ float ldf(const float *p) { return *p; }
+__device__ __forceinline__ float ldf(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stf(float *p, float v) { *p = v; }
+__device__ __forceinline__ void stf(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -110,7 +115,8 @@ __global__ void k_sub_dw(const float *__restrict__ a1, const float *__restrict__
 template <int BM, int BN, int BK>
 __global__ void __launch_bounds__(256)
 k_sgemm(const float *__restrict__ A, int lda, const float *__restrict__ Wt, int ldw, const float *__restrict__ bias,
-        float *__restrict__ C, int ldc, int M, int N, int K, int act, const float *res, int ldres, float alpha) {
+        float *__restrict__ C, int ldc, int M, int N, int K, int act, const float *res, int ldres, float alpha,
+        int out_bf16) {
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Ws[BK][BN + 4];
     const int tid = threadIdx.x;
@@ -189,17 +195,19 @@ k_sgemm(const float *__restrict__ A, int lda, const float *__restrict__ Wt, int 
             if (act == 1) v = silu_acc(v);
             else if (act == 2) v = fmaxf(v, 0.0f);
             if (res) v = res[m * ldres + n] + alpha * v;
-            C[m * ldc + n] = v;
+            if (out_bf16) reinterpret_cast<__nv_bfloat16 *>(C)[m * ldc + n] = __float2bfloat16_rn(v);
+            else C[m * ldc + n] = v;
         }
     }
 }
 
 int launch_sgemm(cocr_handle *h, const float *A, int lda, const float *Wt, int ldw, const float *bias, float *Cout,
-                 int ldc, int M, int N, int K, int act, const float *res, int ldres, float alpha, cudaStream_t st) {
+                 int ldc, int M, int N, int K, int act, const float *res, int ldres, float alpha, cudaStream_t st,
+                 int out_bf16) {
     if (M <= 0 || N <= 0) return COCR_OK;
     dim3 grid((M + 63) / 64, (N + 63) / 64);
     ProfScope ps(h, "sgemm_f32", st, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N));
-    k_sgemm<64, 64, 16><<<grid, 256, 0, st>>>(A, lda, Wt, ldw, bias, Cout, ldc, M, N, K, act, res, ldres, alpha);
+    k_sgemm<64, 64, 16><<<grid, 256, 0, st>>>(A, lda, Wt, ldw, bias, Cout, ldc, M, N, K, act, res, ldres, alpha, out_bf16);
     COCR_LAUNCHED(h);
     return COCR_OK;
 }
@@ -242,10 +250,10 @@ int launch_layernorm(cocr_handle *h, const float *x, float *y, const float *g, c
 constexpr int AQT = 32;
 constexpr int AKT = 64;
 
-template <int DH>
+template <int DH, typename TA>
 __global__ void __launch_bounds__(256)
-k_attn_f32(const float *__restrict__ qkv, const float *__restrict__ pos, const float *__restrict__ ub,
-           const float *__restrict__ vb, const int32_t *__restrict__ lens, float *__restrict__ ctx, int T, int d,
+k_attn_f32(const TA *__restrict__ qkv, const float *__restrict__ pos, const float *__restrict__ ub,
+           const float *__restrict__ vb, const int32_t *__restrict__ lens, TA *__restrict__ ctx, int T, int d,
            int dh, float inv_sqrt_dim) {
     extern __shared__ float sm[];
     constexpr int LD = DH + 1;
@@ -262,12 +270,12 @@ k_attn_f32(const float *__restrict__ qkv, const float *__restrict__ pos, const f
     const int i = i0 + ti;
     const int Tk = lens ? min(max(lens[b], 0), T) : T;    // ragged mode: keys beyond the line are excluded
     const int ld = 3 * d;
-    const float *base = qkv + (int64_t)b * T * ld;
+    const TA *base = qkv + (int64_t)b * T * ld;
 
     float qu[DH], qv[DH];
 #pragma unroll
     for (int c = 0; c < DH; ++c) {
-        float q = (c < dh && i < T) ? base[(int64_t)i * ld + hd * dh + c] : 0.0f;
+        float q = (c < dh && i < T) ? ldf(base + (int64_t)i * ld + hd * dh + c) : 0.0f;
         qu[c] = (c < dh) ? q + ub[hd * dh + c] : 0.0f;
         qv[c] = (c < dh) ? q + vb[hd * dh + c] : 0.0f;
     }
@@ -282,8 +290,8 @@ k_attn_f32(const float *__restrict__ qkv, const float *__restrict__ pos, const f
             int r = e / DH, c = e % DH;
             int j = j0 + r;
             bool ok = (j < Tk) && (c < dh);
-            ks[r * LD + c] = ok ? base[(int64_t)j * ld + d + hd * dh + c] : 0.0f;
-            vs[r * LD + c] = ok ? base[(int64_t)j * ld + 2 * d + hd * dh + c] : 0.0f;
+            ks[r * LD + c] = ok ? ldf(base + (int64_t)j * ld + d + hd * dh + c) : 0.0f;
+            vs[r * LD + c] = ok ? ldf(base + (int64_t)j * ld + 2 * d + hd * dh + c) : 0.0f;
         }
         const int pbase = T - 1 - (i0 + AQT - 1) + j0;    // table row of local row 0
         for (int e = tid; e < (AQT + AKT - 1) * DH; e += 256) {
@@ -345,34 +353,43 @@ k_attn_f32(const float *__restrict__ qkv, const float *__restrict__ pos, const f
 #pragma unroll
         for (int k = 0; k < (DH + 7) / 8; ++k) {
             int c = tj + 8 * k;
-            if (c < dh) ctx[((int64_t)b * T + i) * d + hd * dh + c] = o[k] * inv;
+            if (c < dh) stf(ctx + ((int64_t)b * T + i) * d + hd * dh + c, o[k] * inv);
         }
     }
 }
 
-template <int DH>
-static int launch_attn_t(cocr_handle *h, const float *qkv, const float *pos, const float *ub, const float *vb,
-                         const int32_t *lens, float *ctx, int B, int T, int d, int nh, int dh, cudaStream_t st) {
+template <int DH, typename TA>
+static int launch_attn_t(cocr_handle *h, const TA *qkv, const float *pos, const float *ub, const float *vb,
+                         const int32_t *lens, TA *ctx, int B, int T, int d, int nh, int dh, cudaStream_t st) {
     size_t smem = sizeof(float) * ((size_t)(2 * AKT + AQT + AKT - 1) * (DH + 1) + (size_t)AQT * (AKT + 1));
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(k_attn_f32<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_attn_f32<DH, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_done = true;
     }
     dim3 grid((T + AQT - 1) / AQT, nh, B);
     ProfScope ps(h, "attention_f32", st, 6.0 * B * T * (double)T * d, 16.0 * B * T * d);
-    k_attn_f32<DH><<<grid, 256, smem, st>>>(qkv, pos, ub, vb, lens, ctx, T, d, dh, 1.0f / sqrtf((float)dh));
+    k_attn_f32<DH, TA><<<grid, 256, smem, st>>>(qkv, pos, ub, vb, lens, ctx, T, d, dh, 1.0f / sqrtf((float)dh));
     COCR_LAUNCHED(h);
     return COCR_OK;
 }
 
+template <typename TA>
+static int launch_attn_any(cocr_handle *h, const TA *qkv, const float *pos, const float *ub, const float *vb,
+                           const int32_t *lens, TA *ctx, int B, int T, cudaStream_t st) {
+    const Dims &dm = h->dm;
+    if (dm.dh <= 16) return launch_attn_t<16, TA>(h, qkv, pos, ub, vb, lens, ctx, B, T, dm.d, dm.nh, dm.dh, st);
+    if (dm.dh <= 36) return launch_attn_t<36, TA>(h, qkv, pos, ub, vb, lens, ctx, B, T, dm.d, dm.nh, dm.dh, st);
+    if (dm.dh <= 64) return launch_attn_t<64, TA>(h, qkv, pos, ub, vb, lens, ctx, B, T, dm.d, dm.nh, dm.dh, st);
+    return set_error(h, COCR_ERR_UNSUPPORTED, "SIMT attention supports head dim <= 64 (got %d)", dm.dh);
+}
 static int launch_attn(cocr_handle *h, const float *qkv, const float *pos, const float *ub, const float *vb,
                        const int32_t *lens, float *ctx, int B, int T, cudaStream_t st) {
-    const Dims &dm = h->dm;
-    if (dm.dh <= 16) return launch_attn_t<16>(h, qkv, pos, ub, vb, lens, ctx, B, T, dm.d, dm.nh, dm.dh, st);
-    if (dm.dh <= 36) return launch_attn_t<36>(h, qkv, pos, ub, vb, lens, ctx, B, T, dm.d, dm.nh, dm.dh, st);
-    if (dm.dh <= 64) return launch_attn_t<64>(h, qkv, pos, ub, vb, lens, ctx, B, T, dm.d, dm.nh, dm.dh, st);
-    return set_error(h, COCR_ERR_UNSUPPORTED, "fp32 attention supports head dim <= 64 (got %d)", dm.dh);
+    return launch_attn_any<float>(h, qkv, pos, ub, vb, lens, ctx, B, T, st);
+}
+int launch_attn_simt_bf16(cocr_handle *h, const __nv_bfloat16 *qkv, const float *pos, const float *ub, const float *vb,
+                          const int32_t *lens, __nv_bfloat16 *ctx, int B, int T, cudaStream_t st) {
+    return launch_attn_any<__nv_bfloat16>(h, qkv, pos, ub, vb, lens, ctx, B, T, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -381,9 +398,10 @@ static int launch_attn(cocr_handle *h, const float *qkv, const float *pos, const
 // ------------------------------------------------------------------------------------------
 constexpr int DW_TT = 32;
 
+template <typename TA>
 __global__ void __launch_bounds__(256)
-k_glu_dw_bn_silu(const float *__restrict__ u, const float *__restrict__ wdw, const float *__restrict__ scale,
-                 const float *__restrict__ shift, float *__restrict__ g, int T, int d, int K) {
+k_glu_dw_bn_silu(const TA *__restrict__ u, const float *__restrict__ wdw, const float *__restrict__ scale,
+                 const float *__restrict__ shift, TA *__restrict__ g, int T, int d, int K) {
     extern __shared__ float sm[];
     float *tile = sm;                                // [DW_TT + K - 1][d]
     float *wt = sm + (size_t)(DW_TT + K - 1) * d;    // [K][d]
@@ -396,8 +414,8 @@ k_glu_dw_bn_silu(const float *__restrict__ u, const float *__restrict__ wdw, con
         int t = t0 - pad + r;
         float v = 0.0f;
         if (t >= 0 && t < T) {
-            const float *p = u + ((int64_t)b * T + t) * 2 * d;
-            v = p[c] * sigmoid_acc(p[d + c]);
+            const TA *p = u + ((int64_t)b * T + t) * 2 * d;
+            v = ldf(p + c) * sigmoid_acc(ldf(p + d + c));
         }
         tile[e] = v;
     }
@@ -413,24 +431,32 @@ k_glu_dw_bn_silu(const float *__restrict__ u, const float *__restrict__ wdw, con
         float acc = 0.0f;
         for (int k = 0; k < K; ++k) acc = fmaf(wt[k * d + c], tile[(tt + k) * d + c], acc);
         float y = acc * scale[c] + shift[c];
-        g[((int64_t)b * T + t) * d + c] = silu_acc(y);
+        stf(g + ((int64_t)b * T + t) * d + c, silu_acc(y));
     }
 }
 
-static int launch_glu_dw(cocr_handle *h, const float *u, const LayerF32 &lw, float *g, int B, int T, cudaStream_t st) {
+template <typename TA>
+static int launch_glu_dw_any(cocr_handle *h, const TA *u, const LayerF32 &lw, TA *g, int B, int T, cudaStream_t st) {
     const Dims &dm = h->dm;
     size_t smem = sizeof(float) * (size_t)(DW_TT + 2 * dm.K - 1) * dm.d;
     if (smem > 200 * 1024) return set_error(h, COCR_ERR_UNSUPPORTED, "conv module tile needs %zu B of shared memory", smem);
     static size_t attr = 0;
     if (smem > attr) {
-        cudaFuncSetAttribute(k_glu_dw_bn_silu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_glu_dw_bn_silu<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = smem;
     }
     dim3 grid((T + DW_TT - 1) / DW_TT, B);
     ProfScope ps(h, "glu_dwconv_bn_silu_f32", st, 2.0 * dm.K * B * (double)T * dm.d, 12.0 * B * T * dm.d);
-    k_glu_dw_bn_silu<<<grid, 256, smem, st>>>(u, lw.w_dw, lw.bn_scale, lw.bn_shift, g, T, dm.d, dm.K);
+    k_glu_dw_bn_silu<TA><<<grid, 256, smem, st>>>(u, lw.w_dw, lw.bn_scale, lw.bn_shift, g, T, dm.d, dm.K);
     COCR_LAUNCHED(h);
     return COCR_OK;
+}
+static int launch_glu_dw(cocr_handle *h, const float *u, const LayerF32 &lw, float *g, int B, int T, cudaStream_t st) {
+    return launch_glu_dw_any<float>(h, u, lw, g, B, T, st);
+}
+int launch_glu_dw_bf16(cocr_handle *h, const __nv_bfloat16 *u, const LayerF32 &lw, __nv_bfloat16 *g, int B, int T,
+                       cudaStream_t st) {
+    return launch_glu_dw_any<__nv_bfloat16>(h, u, lw, g, B, T, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -534,6 +560,27 @@ int launch_greedy_decode(cocr_handle *h, const float *logits, const int32_t *len
     return launch_collapse(h, best_val, best_idx, lens, B, T, st, labels, starts, ends, conf, counts);
 }
 
+// Conv2d(1->cc)+ReLU and the depthwise Conv2d of the subsampling front-end (channel-last outputs)
+int launch_frontend_convs(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, int B, int W, float *a1,
+                          float *a2, cudaStream_t st) {
+    const Dims &dm = h->dm;
+    const int T2 = out_len1(W), T = out_len1(T2);
+    int64_t n1 = (int64_t)B * T2 * dm.F2 * dm.cc;
+    {
+        ProfScope ps(h, "sub_conv1_f32", st, 18.0 * n1, 4.0 * ((double)B * W * dm.H + n1));
+        k_sub_conv1<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(img, sb, sw, sh, h->sub_w1, h->sub_b1, a1, B, W, dm.H, T2,
+                                                                    dm.F2, dm.cc);
+        COCR_LAUNCHED(h);
+    }
+    int64_t n2 = (int64_t)B * T * dm.F * dm.cc;
+    {
+        ProfScope ps(h, "sub_dwconv_f32", st, 18.0 * n2, 4.0 * ((double)n1 + n2));
+        k_sub_dw<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(a1, h->sub_wdw, h->sub_bdw, a2, B, T2, dm.F2, T, dm.F, dm.cc);
+        COCR_LAUNCHED(h);
+    }
+    return COCR_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // forward driver
 // ------------------------------------------------------------------------------------------
@@ -582,20 +629,9 @@ int fp32_encode(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_
         lens_dev = tmp;
     }
     {
-        int64_t n1 = (int64_t)B * p.T2 * dm.F2 * dm.cc;
-        {
-        ProfScope ps(h, "sub_conv1_f32", st, 18.0 * n1, 4.0 * ((double)B * W * dm.H + n1));
-        k_sub_conv1<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(img, sb, sw, sh, h->sub_w1, h->sub_b1, a1, B, W, dm.H,
-                                                                    p.T2, dm.F2, dm.cc);
-        COCR_LAUNCHED(h);
-        }
-        int64_t n2 = (int64_t)M * dm.F * dm.cc;
-        {
-        ProfScope ps(h, "sub_dwconv_f32", st, 18.0 * n2, 4.0 * ((double)n1 + n2));
-        k_sub_dw<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(a1, h->sub_wdw, h->sub_bdw, a2, B, p.T2, dm.F2, p.T, dm.F,
-                                                                 dm.cc);
-        COCR_LAUNCHED(h);
-        }
+        COCR_TRY(launch_frontend_convs(h, img, sb, sw, sh, B, W, a1, a2, st));
+    }
+    {
         // 1x1 conv + ReLU as a GEMM over (b,t,f) rows; output row (b,t) holds f*cc+c
         COCR_TRY(launch_sgemm(h, a2, dm.cc, h->sub_wpw, dm.cc, h->sub_bpw, feat, dm.cc, M * dm.F, dm.cc, dm.cc, 2, nullptr,
                               0, 0.f, st));

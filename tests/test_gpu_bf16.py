@@ -1,0 +1,111 @@
+"""bf16 tensor-core path: kernel self checks through the C ABI + end-to-end parity with the reference goldens.
+
+Tolerance (BASELINE.json north_star): bf16 logits max-norm relative error <= 2e-2; top-1 agreement is
+reported per case and gated on frames whose fp32 top-2 margin exceeds the bf16 noise floor."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, golden_inputs, load_golden, rel_err
+from oracle import conformer_oracle as O
+
+pytestmark = pytest.mark.gpu
+BF16_TOL = 2e-2
+DROP = dict(input_dropout_p=0.1, feed_forward_dropout_p=0.1, attention_dropout_p=0.1, conv_dropout_p=0.1)
+
+EPI_BF16, EPI_SILU, EPI_F32, EPI_ARGMAX = 0, 1, 2, 3
+GEMM_CASES = [
+    # (epilogue, M, N, K, block_n override)
+    (EPI_BF16, 128, 64, 64, 0), (EPI_BF16, 128, 144, 144, 0), (EPI_BF16, 300, 144, 144, 0),
+    (EPI_SILU, 4096, 576, 144, 0), (EPI_BF16, 4096, 144, 576, 0), (EPI_BF16, 5000, 432, 144, 0),
+    (EPI_BF16, 3000, 288, 144, 0), (EPI_BF16, 2500, 144, 768, 0), (EPI_BF16, 777, 32, 32, 0),
+    (EPI_F32, 1000, 256, 144, 0), (EPI_F32, 515, 11, 32, 0), (EPI_F32, 2048, 10000, 144, 0),
+    (EPI_ARGMAX, 1000, 256, 144, 0), (EPI_ARGMAX, 3000, 10000, 144, 0), (EPI_ARGMAX, 130, 11, 32, 0),
+    (EPI_BF16, 40000, 576, 144, 0), (EPI_BF16, 40000, 144, 576, 0), (EPI_BF16, 1000, 144, 144, 48),
+]
+
+
+@pytest.mark.parametrize('epi,M,N,K,bn', GEMM_CASES)
+def test_tcgen05_gemm_selftest(epi, M, N, K, bn, cuda_device):
+    from conformer_ocr_b200 import _lib
+    lib = _lib.load()
+    err = ctypes.c_double(-1.0)
+    rc = lib.cocr_selftest(0, 10 + epi, M, N, K + 100000 * bn, ctypes.byref(err))
+    _lib.raise_for_status(rc, None)
+    # bf16 outputs: error relative to 1+|ref| bounded by bf16 rounding (2^-8) (+ tanh.approx for SiLU);
+    # fp32 / arg-max outputs: accumulation-order differences only
+    tol = {EPI_BF16: 6e-3, EPI_SILU: 8e-3, EPI_F32: 2e-3, EPI_ARGMAX: 2e-3}[epi]
+    assert 0.0 <= err.value < tol, f'max err {err.value}'
+
+
+def build_net(hp, C, w, device, **kw):
+    from conformer_ocr_b200 import PytorchRecognitionModel
+    net = PytorchRecognitionModel(num_classes=C, codec=None, precision='bf16', **hp, **DROP, **kw)
+    net.nn.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=False)
+    return net.to(device)
+
+
+def top1_report(got, ref):
+    """agreement overall and on frames whose reference top-2 margin is above 4x the observed max error."""
+    agree = got.argmax(-1) == ref.argmax(-1)
+    srt = np.sort(ref, axis=-1)
+    margin = srt[..., -1] - srt[..., -2]
+    noise = np.abs(got - ref).max()
+    clear = margin > 4 * noise
+    return float(agree.mean()), float(agree[clear].mean()) if clear.any() else 1.0, float(clear.mean())
+
+
+@pytest.mark.parametrize('name', GOLDEN_CASES)
+def test_bf16_logits_match_reference_golden(name, cuda_device):
+    meta, arrs = load_golden(name)
+    hp, w, img, lens = golden_inputs(meta)
+    net = build_net(hp, meta['num_classes'], w, cuda_device)
+    logits, olens = net(torch.from_numpy(img).to(cuda_device), torch.from_numpy(lens))
+    got = logits.cpu().numpy()
+    np.testing.assert_array_equal(olens.cpu().numpy(), arrs['enc_lens'])
+    err = rel_err(got, arrs['logits'])
+    overall, clear, frac_clear = top1_report(got, arrs['logits'])
+    print(f'{name}: bf16 rel err {err:.3e}; top-1 agreement {overall:.4f} overall, {clear:.4f} on the '
+          f'{frac_clear:.2%} frames with a clear margin')
+    assert err < BF16_TOL
+    assert clear == 1.0
+
+
+def test_bf16_decode_consistent_with_own_logits(cuda_device):
+    """the fused projection+arg-max kernel must pick exactly the arg-max of the logits the same path emits,
+    and the collapse must be bit-exact given that arg-max."""
+    meta, _ = load_golden('default_ragged')
+    hp, w, img, lens = golden_inputs(meta)
+    net = build_net(hp, meta['num_classes'], w, cuda_device)
+    x = torch.from_numpy(img).to(cuda_device)
+    logits, olens = net(x, torch.from_numpy(lens))
+    got = net.predict_labels(x, torch.from_numpy(lens))
+    lg = logits.cpu().numpy()
+    ref = [O.greedy_decoder(lg[b, :int(olens[b])].T) for b in range(lg.shape[0])]
+    assert [[t[:3] for t in l] for l in got] == [[t[:3] for t in l] for l in ref]
+
+
+def test_bf16_full_width_batch(cuda_device):
+    """BASELINE config 1 shape (batch 8 x 1024 px, default spec) against the fp32 CUDA path (itself pinned to
+    the reference within 1e-4): tolerance + line independence."""
+    from conformer_ocr_b200 import PytorchRecognitionModel
+    hp = dict(O.DEFAULT_HPARAMS)
+    C = 256
+    w = O.make_weights(hp, C, seed=21)
+    img, lens = O.make_lines(8, 96, 1024, seed=22)
+    x = torch.from_numpy(img).to(cuda_device)
+    net16 = build_net(hp, C, w, cuda_device)
+    net32 = PytorchRecognitionModel(num_classes=C, codec=None, precision='fp32', **hp, **DROP)
+    net32.nn.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=False)
+    l16, _ = net16(x, torch.from_numpy(lens))
+    l32, _ = net32(x, torch.from_numpy(lens))
+    a, b = l16.cpu().numpy(), l32.cpu().numpy()
+    err = rel_err(a, b)
+    overall, clear, frac_clear = top1_report(a, b)
+    print(f'b8 w1024: bf16 vs fp32 rel err {err:.3e}; top-1 {overall:.4f} overall, {clear:.4f} on {frac_clear:.2%} clear frames')
+    assert err < BF16_TOL
+    assert clear == 1.0
+    sub, _ = net16(x[3:6], torch.from_numpy(lens[3:6]))
+    assert torch.equal(l16[3:6], sub)
