@@ -8,6 +8,7 @@
 
 #include "common.h"
 #include "gemm_tc.cuh"
+#include "attn_tc.cuh"
 
 namespace cocr {
 
@@ -16,6 +17,15 @@ typedef __nv_bfloat16 bf16;
 struct Bf16State {
     bf16 *arena = nullptr;        // bf16 mirror of the fp32 weight arena (same offsets)
     int smem_optin = 0;
+    // tensor-core attention (attn_tc.cuh): fused Qe|Kx|Vx projection weights and position tables
+    bool tc_attn = false;
+    int qe_cols = 0, nx = 0, nchunk = 0;
+    bf16 *w_qkvx = nullptr;       // (L, nx, d)
+    float *b_qkvx = nullptr;      // (L, nx)
+    int16_t *meta = nullptr;      // (nx / 16)
+    float2 *trig = nullptr;       // (T, d/2) (sin, cos)(t * omega_m)
+    bf16 *etab = nullptr;         // (T, d - 16) (cos, sin) interleaved
+    int tab_T = 0;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -65,8 +75,11 @@ static int pick_block_n(int N) {
     return 256;
 }
 
+struct PosArgs { const int16_t *meta; const float2 *trig; int trig_ld, T; };
+
 int launch_gemm_tc(cocr_handle *h, int epi, const bf16 *A, int lda, const bf16 *W, int ldw, const float *bias, void *out,
-                   int ldc, unsigned long long *best, int M, int N, int K, cudaStream_t st, int block_n_override = 0) {
+                   int ldc, unsigned long long *best, int M, int N, int K, cudaStream_t st, int block_n_override = 0,
+                   const PosArgs *pos = nullptr) {
     if (M <= 0 || N <= 0) return COCR_OK;
     if (K % 16 != 0 || lda % 8 != 0 || ldw % 8 != 0)
         return set_error(h, COCR_ERR_UNSUPPORTED, "tensor-core GEMM needs K %% 16 == 0 and 16-byte aligned rows (K=%d lda=%d ldw=%d)", K,
@@ -79,6 +92,9 @@ int launch_gemm_tc(cocr_handle *h, int epi, const bf16 *A, int lda, const bf16 *
     p.nkc = (K + GEMM_KC - 1) / GEMM_KC;
     p.last_ksteps = (K - (p.nkc - 1) * GEMM_KC) / 16;
     p.bias = bias; p.out = out; p.ldc = ldc; p.best = best;
+    p.col_meta = pos ? pos->meta : nullptr; p.trig = pos ? pos->trig : nullptr;
+    p.trig_ld = pos ? pos->trig_ld : 0; p.T = pos ? pos->T : 1;
+    if (epi == EPI_BF16_POS && (!pos || p.block_n % 16 != 0)) return set_error(h, COCR_ERR_BAD_ARG, "POS epilogue needs position tables");
     int tm = 32;
     while (tm < 2 * p.block_n) tm <<= 1;
     p.tmem_cols = tm;
@@ -128,6 +144,7 @@ int launch_gemm_tc(cocr_handle *h, int epi, const bf16 *A, int lda, const bf16 *
         COCR_GEMM_CASE(EPI_BF16_SILU)
         COCR_GEMM_CASE(EPI_F32)
         COCR_GEMM_CASE(EPI_ARGMAX)
+        COCR_GEMM_CASE(EPI_BF16_POS)
         default: return set_error(h, COCR_ERR_BAD_ARG, "unknown GEMM epilogue %d", epi);
     }
 #undef COCR_GEMM_CASE
@@ -254,6 +271,8 @@ struct Bf16Plan {
     size_t off_a1, off_a2, off_feat, off_x, off_xn, off_y, off_h, off_g, off_best, off_best_val, off_best_idx, total;
 };
 
+static bool use_tc_attn(const cocr_handle *h) { return h->bf && h->bf->tc_attn; }
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static void bf16_plan(const cocr_handle *h, int B, int W, Bf16Plan *p) {
@@ -272,6 +291,7 @@ static void bf16_plan(const cocr_handle *h, int B, int W, Bf16Plan *p) {
     p->off_xn = take(M * dm.d * 2);
     p->off_y = take(M * dm.d * 2);
     size_t wide = (size_t)dm.ff > (size_t)3 * dm.d ? dm.ff : 3 * dm.d;
+    if (use_tc_attn(h) && (size_t)h->bf->nx > wide) wide = h->bf->nx;
     p->off_h = take(M * wide * 2);
     p->off_g = take(M * dm.d * 2);
     p->off_best = take(M * 8);
@@ -284,6 +304,157 @@ size_t bf16_workspace_bytes(const cocr_handle *h, int B, int W) {
     Bf16Plan p;
     bf16_plan(h, B, W, &p);
     return p.total;
+}
+
+
+static uint16_t f2bf(float f) {   // round-to-nearest-even, host side
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+// Fused projection for the tensor-core attention: per layer one (nx, d) weight producing
+//   [Qe(h=0..nh-1) | Kx(h) | Vx(h)]  (layouts in attn_tc.cuh).  a~ = R(i)^T Wp_h^T (Wq_h x + bq_h + v_h) is folded into a
+//   (d, d) merged weight Wa_h = Wp_h^T Wq_h (fp32 product, rounded once to bf16) and a bias Wp_h^T (bq_h + v_h).
+static int pack_attention(cocr_handle *h) {
+    Bf16State *bs = h->bf;
+    const Dims &dm = h->dm;
+    const int d = dm.d, nh = dm.nh, dh = dm.dh, L = dm.L;
+    bs->tc_attn = (dh <= 48) && (d >= 80) && ((d - 16) % 64 == 0) && ((48 + d) / 64 <= ATT_MAXCHUNK) && L > 0;
+    if (getenv("COCR_SIMT_ATTENTION")) bs->tc_attn = false;
+    if (!bs->tc_attn) return COCR_OK;
+    bs->qe_cols = 48 + d;
+    bs->nchunk = bs->qe_cols / 64;
+    bs->nx = nh * (bs->qe_cols + 64 + 64);
+    const int nx = bs->nx, qc = bs->qe_cols;
+    std::vector<uint16_t> W((size_t)L * nx * d, 0);
+    std::vector<float> Bv((size_t)L * nx, 0.0f);
+    std::vector<int16_t> meta(nx / 16, 0);
+    const int tail_pair = (d - 16) / 2;
+    for (int hd = 0; hd < nh; ++hd) {
+        for (int g = 0; g < qc / 16; ++g) {
+            int16_t m = 0;
+            if (g == 3) m = (int16_t)((1 << 12) | tail_pair);
+            else if (g >= 4) m = (int16_t)((1 << 12) | ((g - 4) * 8));
+            meta[(hd * qc) / 16 + g] = m;
+        }
+        meta[(nh * qc + hd * 64) / 16 + 3] = (int16_t)((2 << 12) | tail_pair);
+    }
+    std::vector<float> wa((size_t)d * d);
+    for (int l = 0; l < L; ++l) {
+        const std::string q = "encoder.layers." + std::to_string(l) + ".sequential.1.module.attention.";
+        const std::vector<float> &Wq = h->host_w.at(q + "query_proj.linear.weight").data, &bq = h->host_w.at(q + "query_proj.linear.bias").data;
+        const std::vector<float> &Wk = h->host_w.at(q + "key_proj.linear.weight").data, &bk = h->host_w.at(q + "key_proj.linear.bias").data;
+        const std::vector<float> &Wv = h->host_w.at(q + "value_proj.linear.weight").data, &bv = h->host_w.at(q + "value_proj.linear.bias").data;
+        const std::vector<float> &Wp = h->host_w.at(q + "pos_proj.linear.weight").data;
+        const std::vector<float> &ub = h->host_w.at(q + "u_bias").data, &vb = h->host_w.at(q + "v_bias").data;
+        uint16_t *Wl = W.data() + (size_t)l * nx * d;
+        float *Bl = Bv.data() + (size_t)l * nx;
+        for (int hd = 0; hd < nh; ++hd) {
+            // merged positional weight of this head: wa[m][:] = sum_c Wp[hd*dh+c][m] * Wq[hd*dh+c][:]
+            std::vector<double> acc((size_t)d * d, 0.0), accb(d, 0.0);
+            for (int c = 0; c < dh; ++c) {
+                const float *wp = &Wp[(size_t)(hd * dh + c) * d];
+                const float *wq = &Wq[(size_t)(hd * dh + c) * d];
+                const double bb = (double)bq[hd * dh + c] + (double)vb[hd * dh + c];
+                for (int m = 0; m < d; ++m) {
+                    const double wpm = wp[m];
+                    accb[m] += wpm * bb;
+                    double *row = &acc[(size_t)m * d];
+                    for (int k = 0; k < d; ++k) row[k] += wpm * (double)wq[k];
+                }
+            }
+            const int qbase = hd * qc;
+            for (int r = 0; r < dh; ++r) {
+                for (int k = 0; k < d; ++k) Wl[(size_t)(qbase + r) * d + k] = f2bf(Wq[(size_t)(hd * dh + r) * d + k]);
+                Bl[qbase + r] = bq[hd * dh + r] + ub[hd * dh + r];
+            }
+            for (int col = 48; col < qc; ++col) {
+                const int m = (col < 64) ? (d - 16) + (col - 48) : (col - 64);
+                for (int k = 0; k < d; ++k) Wl[(size_t)(qbase + col) * d + k] = f2bf((float)acc[(size_t)m * d + k]);
+                Bl[qbase + col] = (float)accb[m];
+            }
+            const int kbase = nh * qc + hd * 64, vbase = nh * qc + nh * 64 + hd * 64;
+            for (int r = 0; r < dh; ++r) {
+                for (int k = 0; k < d; ++k) {
+                    Wl[(size_t)(kbase + r) * d + k] = f2bf(Wk[(size_t)(hd * dh + r) * d + k]);
+                    Wl[(size_t)(vbase + r) * d + k] = f2bf(Wv[(size_t)(hd * dh + r) * d + k]);
+                }
+                Bl[kbase + r] = bk[hd * dh + r];
+                Bl[vbase + r] = bv[hd * dh + r];
+            }
+        }
+    }
+    if (bs->w_qkvx) { cudaFree(bs->w_qkvx); bs->w_qkvx = nullptr; }
+    if (bs->b_qkvx) { cudaFree(bs->b_qkvx); bs->b_qkvx = nullptr; }
+    if (bs->meta) { cudaFree(bs->meta); bs->meta = nullptr; }
+    void *p = nullptr;
+    COCR_CUDA(h, cudaMalloc(&p, W.size() * 2)); bs->w_qkvx = (bf16 *)p;
+    COCR_CUDA(h, cudaMalloc(&p, Bv.size() * 4)); bs->b_qkvx = (float *)p;
+    COCR_CUDA(h, cudaMalloc(&p, meta.size() * 2)); bs->meta = (int16_t *)p;
+    COCR_CUDA(h, cudaMemcpy(bs->w_qkvx, W.data(), W.size() * 2, cudaMemcpyHostToDevice));
+    COCR_CUDA(h, cudaMemcpy(bs->b_qkvx, Bv.data(), Bv.size() * 4, cudaMemcpyHostToDevice));
+    COCR_CUDA(h, cudaMemcpy(bs->meta, meta.data(), meta.size() * 2, cudaMemcpyHostToDevice));
+    bs->tab_T = 0;
+    return COCR_OK;
+}
+
+// (sin, cos)(t w_m) and the shared key-side table E(t) for a batch whose lines have T frames (embedding.py:42-47 angles)
+static int ensure_tables(cocr_handle *h, int T, cudaStream_t st) {
+    Bf16State *bs = h->bf;
+    if (bs->tab_T == T) return COCR_OK;
+    const int d = h->dm.d, np = d / 2, ecols = d - 16;
+    if (bs->trig) { COCR_CUDA(h, cudaDeviceSynchronize()); cudaFree(bs->trig); cudaFree(bs->etab); bs->trig = nullptr; bs->etab = nullptr; }
+    std::vector<float> trig((size_t)T * np * 2);
+    std::vector<uint16_t> et((size_t)T * ecols);
+    const float neg = (float)(-(log(10000.0) / (double)d));
+    for (int t = 0; t < T; ++t)
+        for (int m = 0; m < np; ++m) {
+            const float div = expf((float)(2 * m) * neg);
+            const float arg = (float)t * div;
+            const float sn = sinf(arg), cs = cosf(arg);
+            trig[((size_t)t * np + m) * 2] = sn;
+            trig[((size_t)t * np + m) * 2 + 1] = cs;
+            if (2 * m + 1 < ecols) {
+                et[(size_t)t * ecols + 2 * m] = f2bf(cs);
+                et[(size_t)t * ecols + 2 * m + 1] = f2bf(sn);
+            }
+        }
+    void *p = nullptr;
+    COCR_CUDA(h, cudaMalloc(&p, trig.size() * 4)); bs->trig = (float2 *)p;
+    COCR_CUDA(h, cudaMalloc(&p, et.size() * 2)); bs->etab = (bf16 *)p;
+    COCR_CUDA(h, cudaMemcpyAsync(bs->trig, trig.data(), trig.size() * 4, cudaMemcpyHostToDevice, st));
+    COCR_CUDA(h, cudaMemcpyAsync(bs->etab, et.data(), et.size() * 2, cudaMemcpyHostToDevice, st));
+    COCR_CUDA(h, cudaStreamSynchronize(st));
+    bs->tab_T = T;
+    return COCR_OK;
+}
+
+static int launch_attn_tc(cocr_handle *h, const bf16 *qkvx, const int32_t *lens, bf16 *ctx, int B, int T, cudaStream_t st) {
+    Bf16State *bs = h->bf;
+    const Dims &dm = h->dm;
+    const int64_t M = (int64_t)B * T;
+    CUtensorMap tmQ, tmK, tmV, tmE;
+    COCR_TRY(make_tmap_bf16(h, &tmQ, qkvx, M, dm.nh * bs->qe_cols, bs->nx, ATT_BQ));
+    COCR_TRY(make_tmap_bf16(h, &tmK, qkvx + dm.nh * bs->qe_cols, M, dm.nh * 64, bs->nx, ATT_BK));
+    COCR_TRY(make_tmap_bf16(h, &tmV, qkvx + dm.nh * bs->qe_cols + dm.nh * 64, M, dm.nh * 64, bs->nx, ATT_BK));
+    COCR_TRY(make_tmap_bf16(h, &tmE, bs->etab, T, dm.d - 16, dm.d - 16, ATT_BK));
+    AttnArgs a;
+    a.B = B; a.T = T; a.nh = dm.nh; a.dh = dm.dh; a.d = dm.d; a.nchunk = bs->nchunk; a.lens = lens; a.ctx = ctx;
+    a.scale_log2 = 1.4426950408889634f / sqrtf((float)dm.dh);
+    const uint32_t smem = attn_smem_bytes(bs->nchunk);
+    static bool attr = false;
+    if (!attr) {
+        COCR_CUDA(h, cudaFuncSetAttribute(k_attn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->smem_optin));
+        attr = true;
+    }
+    dim3 grid((T + ATT_BQ - 1) / ATT_BQ, dm.nh, B);
+    ProfScope ps(h, "attention_tc", st, 6.0 * B * T * (double)T * dm.d, 2.0 * M * (bs->nx + dm.d));
+    k_attn_tc<<<grid, ATT_THREADS, smem, st>>>(tmQ, tmK, tmV, tmE, a);
+    COCR_LAUNCHED(h);
+    return COCR_OK;
 }
 
 int bf16_init(cocr_handle *h) {
@@ -303,12 +474,18 @@ int bf16_init(cocr_handle *h) {
     COCR_CUDA(h, cudaDeviceSynchronize());
     COCR_CUDA(h, cudaDeviceGetAttribute(&bs->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     if (!get_encode()) return set_error(h, COCR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    return COCR_OK;
+    return pack_attention(h);
 }
 
 void bf16_destroy(cocr_handle *h) {
     if (!h->bf) return;
-    if (h->bf->arena) cudaFree(h->bf->arena);
+    Bf16State *bs = h->bf;
+    if (bs->arena) cudaFree(bs->arena);
+    if (bs->w_qkvx) cudaFree(bs->w_qkvx);
+    if (bs->b_qkvx) cudaFree(bs->b_qkvx);
+    if (bs->meta) cudaFree(bs->meta);
+    if (bs->trig) cudaFree(bs->trig);
+    if (bs->etab) cudaFree(bs->etab);
     delete h->bf;
     h->bf = nullptr;
 }
@@ -321,7 +498,9 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
     const Dims &dm = h->dm;
     bf16_plan(h, B, W, &p);
     COCR_TRY(ensure_workspace(h, p.total));
-    COCR_TRY(ensure_pos_proj(h, p.T, st));
+    const bool tc_attn = use_tc_attn(h);
+    if (tc_attn) COCR_TRY(ensure_tables(h, p.T, st));
+    else COCR_TRY(ensure_pos_proj(h, p.T, st));
     char *ws = h->ws.base;
     float *a1 = (float *)(ws + p.off_a1), *a2 = (float *)(ws + p.off_a2);
     bf16 *feat = (bf16 *)(ws + p.off_feat);
@@ -354,9 +533,17 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
         COCR_TRY(launch_gemm_tc(h, EPI_BF16, hb, dm.ff, WB(h, lw.ffn_w2[0]), dm.ff, lw.ffn_b2[0], y, d, nullptr, M, d, dm.ff, st));
         COCR_TRY(launch_resid_ln(h, x, y, dm.ffn_factor, 0, nullptr, nullptr, lw.att_ln_g, lw.att_ln_b, xn, M, d, st));
         // MHSA (attention.py:72-151)
-        COCR_TRY(launch_gemm_tc(h, EPI_BF16, xn, d, WB(h, lw.w_qkv), d, lw.b_qkv, hb, 3 * d, nullptr, M, 3 * d, d, st));
-        COCR_TRY(launch_attn_simt_bf16(h, hb, h->pos_proj + (size_t)l * (2 * p.T - 1) * d, lw.u_bias, lw.v_bias, lens_dev, g, B,
-                                       p.T, st));
+        if (tc_attn) {
+            Bf16State *bs = h->bf;
+            PosArgs pa = {bs->meta, bs->trig, d / 2, p.T};
+            COCR_TRY(launch_gemm_tc(h, EPI_BF16_POS, xn, d, bs->w_qkvx + (size_t)l * bs->nx * d, d, bs->b_qkvx + (size_t)l * bs->nx, hb,
+                                    bs->nx, nullptr, M, bs->nx, d, st, 0, &pa));
+            COCR_TRY(launch_attn_tc(h, hb, lens_dev, g, B, p.T, st));
+        } else {
+            COCR_TRY(launch_gemm_tc(h, EPI_BF16, xn, d, WB(h, lw.w_qkv), d, lw.b_qkv, hb, 3 * d, nullptr, M, 3 * d, d, st));
+            COCR_TRY(launch_attn_simt_bf16(h, hb, h->pos_proj + (size_t)l * (2 * p.T - 1) * d, lw.u_bias, lw.v_bias, lens_dev, g,
+                                           B, p.T, st));
+        }
         COCR_TRY(launch_gemm_tc(h, EPI_BF16, g, d, WB(h, lw.w_out), d, lw.b_out, y, d, nullptr, M, d, d, st));
         COCR_TRY(launch_resid_ln(h, x, y, 1.f, 0, nullptr, nullptr, lw.conv_ln_g, lw.conv_ln_b, xn, M, d, st));
         // convolution module (convolution.py:135-148)

@@ -19,6 +19,9 @@ enum GemmEpi : int {
     EPI_BF16_SILU = 1,   // out bf16 = silu(acc + bias)
     EPI_F32 = 2,         // out fp32 = acc + bias
     EPI_ARGMAX = 3,      // best[row] = max over columns of (acc + bias), lowest column wins ties (packed u64)
+    EPI_BF16_POS = 4,    // out bf16 = acc + bias, with per-16-column-group position handling (attention operands):
+                         //   kind 0 plain; kind 1 rotate pairs by the row's angle (relative-position term);
+                         //   kind 2 fill with (cos, sin) of the row's angle
 };
 
 struct GemmArgs {
@@ -34,6 +37,10 @@ struct GemmArgs {
     void *out;               // bf16 / fp32 (M, ldc) row-major, or unused for EPI_ARGMAX
     int ldc;
     unsigned long long *best;   // EPI_ARGMAX: (M) packed keys, zero-initialised by the caller
+    // EPI_BF16_POS
+    const int16_t *col_meta;    // (N/16): kind << 12 | first pair index
+    const float2 *trig;         // (T, trig_ld): (sin, cos)(t * omega_m)
+    int trig_ld, T;             // row r of the GEMM is frame t = r % T of its line
 };
 
 constexpr int GEMM_THREADS = 192;
@@ -234,19 +241,51 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             }
                         }
                     } else {
+                        int trow = 0;
+                        if constexpr (EPI == EPI_BF16_POS) trow = (int)((grow0 + lane) % p.T);
 #pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) {
-                            if (jj * 8 < ncol) {
-                                uint32_t pk[4];
+                        for (int g = 0; g < 4; ++g) {
+                            if (g * 16 < ncol) {
+                                float f[16];
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    float a = __uint_as_float(r[jj * 8 + 2 * e]) + sb[c0 + jj * 8 + 2 * e];
-                                    float b = __uint_as_float(r[jj * 8 + 2 * e + 1]) + sb[c0 + jj * 8 + 2 * e + 1];
-                                    if constexpr (EPI == EPI_BF16_SILU) { a = silu_fast(a); b = silu_fast(b); }
-                                    __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
-                                    pk[e] = *reinterpret_cast<uint32_t *>(&h2);
+                                for (int e = 0; e < 16; ++e) {
+                                    f[e] = __uint_as_float(r[g * 16 + e]) + sb[c0 + g * 16 + e];
+                                    if constexpr (EPI == EPI_BF16_SILU) f[e] = silu_fast(f[e]);
                                 }
-                                *reinterpret_cast<uint4 *>(sbuf + sw128_offset(lane, jj)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                                if constexpr (EPI == EPI_BF16_POS) {
+                                    const int meta = p.col_meta[(n0 + c0) / 16 + g];
+                                    const int kind = meta >> 12;
+                                    if (kind != 0) {
+                                        const float4 *tp = reinterpret_cast<const float4 *>(p.trig + (size_t)trow * p.trig_ld + (meta & 0xFFF));
+#pragma unroll
+                                        for (int q4 = 0; q4 < 4; ++q4) {
+                                            const float4 sc = tp[q4];     // (sin, cos) of pairs 2*q4, 2*q4+1
+                                            const float sn[2] = {sc.x, sc.z}, cs[2] = {sc.y, sc.w};
+#pragma unroll
+                                            for (int u = 0; u < 2; ++u) {
+                                                const int e0 = (q4 * 2 + u) * 2;
+                                                const float as = f[e0], ac = f[e0 + 1];
+                                                if (kind == 1) {
+                                                    f[e0] = as * sn[u] + ac * cs[u];
+                                                    f[e0 + 1] = ac * sn[u] - as * cs[u];
+                                                } else {
+                                                    f[e0] = cs[u];
+                                                    f[e0 + 1] = sn[u];
+                                                }
+                                            }
+                                        }
+                                    }
+                                }
+#pragma unroll
+                                for (int hh = 0; hh < 2; ++hh) {
+                                    uint32_t pk[4];
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[hh * 8 + 2 * e], f[hh * 8 + 2 * e + 1]);
+                                        pk[e] = *reinterpret_cast<uint32_t *>(&h2);
+                                    }
+                                    *reinterpret_cast<uint4 *>(sbuf + sw128_offset(lane, g * 2 + hh)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                                }
                             }
                         }
                     }
