@@ -79,7 +79,7 @@ struct PosArgs { const int16_t *meta; const float2 *trig; int trig_ld, T; };
 
 int launch_gemm_tc(cocr_handle *h, int epi, const bf16 *A, int lda, const bf16 *W, int ldw, const float *bias, void *out,
                    int ldc, unsigned long long *best, int M, int N, int K, cudaStream_t st, int block_n_override = 0,
-                   const PosArgs *pos = nullptr) {
+                   const PosArgs *pos = nullptr, const char *tag = "gemm_tc") {
     if (M <= 0 || N <= 0) return COCR_OK;
     if (K % 16 != 0 || lda % 8 != 0 || ldw % 8 != 0)
         return set_error(h, COCR_ERR_UNSUPPORTED, "tensor-core GEMM needs K %% 16 == 0 and 16-byte aligned rows (K=%d lda=%d ldw=%d)", K,
@@ -128,7 +128,7 @@ int launch_gemm_tc(cocr_handle *h, int epi, const bf16 *A, int lda, const bf16 *
     }
     const double flops = 2.0 * M * (double)N * K;
     const double bytes = 2.0 * ((double)M * K + (double)N * K) + (epi == EPI_ARGMAX ? 8.0 * M : (epi == EPI_F32 ? 4.0 : 2.0) * (double)M * N);
-    ProfScope ps(h, epi == EPI_ARGMAX ? "gemm_tc_argmax" : "gemm_tc_bf16", st, flops, bytes);
+    ProfScope ps(h, tag, st, flops, bytes);
 #define COCR_GEMM_CASE(E)                                                                                              \
     case E: {                                                                                                          \
         static int attr_smem = 0;                                                                                      \
@@ -517,10 +517,15 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
     }
     // front-end (convolution.py:227-237): direct convs on CUDA cores, 1x1 conv as an fp32 GEMM writing bf16 features,
     // 768->144 projection on tensor cores
-    COCR_TRY(launch_frontend_convs(h, img, sb, sw, sh, B, W, a1, a2, st));
-    COCR_TRY(launch_sgemm(h, a2, dm.cc, h->sub_wpw, dm.cc, h->sub_bpw, (float *)feat, dm.cc, M * dm.F, dm.cc, dm.cc, 2, nullptr, 0,
-                          0.f, st, /*out_bf16=*/1));
-    COCR_TRY(launch_gemm_tc(h, EPI_BF16, feat, dm.feat, WB(h, h->sub_wout), dm.feat, h->sub_bout, y, d, nullptr, M, d, dm.feat, st));
+    int rc_fe = launch_frontend_fused(h, img, sb, sw, sh, B, W, feat, st);
+    if (rc_fe == COCR_ERR_UNSUPPORTED) {
+        COCR_TRY(launch_frontend_convs(h, img, sb, sw, sh, B, W, a1, a2, st));
+        COCR_TRY(launch_sgemm(h, a2, dm.cc, h->sub_wpw, dm.cc, h->sub_bpw, (float *)feat, dm.cc, M * dm.F, dm.cc, dm.cc, 2, nullptr,
+                              0, 0.f, st, /*out_bf16=*/1));
+    } else if (rc_fe != COCR_OK) {
+        return rc_fe;
+    }
+    COCR_TRY(launch_gemm_tc(h, EPI_BF16, feat, dm.feat, WB(h, h->sub_wout), dm.feat, h->sub_bout, y, d, nullptr, M, d, dm.feat, st, 0, nullptr, "gemm_sub_out"));
     if (dm.L == 0) {
         COCR_TRY(launch_resid_ln(h, x, y, 1.f, 1, nullptr, nullptr, nullptr, nullptr, xn, M, d, st));
         return COCR_OK;
@@ -529,31 +534,33 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
     for (int l = 0; l < dm.L; ++l) {
         const LayerF32 &lw = h->layers[l];
         // FFN 1 (feed_forward.py:45-55; half-step residual encoder.py:68-75)
-        COCR_TRY(launch_gemm_tc(h, EPI_BF16_SILU, xn, d, WB(h, lw.ffn_w1[0]), d, lw.ffn_b1[0], hb, dm.ff, nullptr, M, dm.ff, d, st));
-        COCR_TRY(launch_gemm_tc(h, EPI_BF16, hb, dm.ff, WB(h, lw.ffn_w2[0]), dm.ff, lw.ffn_b2[0], y, d, nullptr, M, d, dm.ff, st));
+        COCR_TRY(launch_gemm_tc(h, EPI_BF16_SILU, xn, d, WB(h, lw.ffn_w1[0]), d, lw.ffn_b1[0], hb, dm.ff, nullptr, M, dm.ff, d, st, 0, nullptr, "gemm_ffn_up"));
+        COCR_TRY(launch_gemm_tc(h, EPI_BF16, hb, dm.ff, WB(h, lw.ffn_w2[0]), dm.ff, lw.ffn_b2[0], y, d, nullptr, M, d, dm.ff, st, 0, nullptr, "gemm_ffn_down"));
         COCR_TRY(launch_resid_ln(h, x, y, dm.ffn_factor, 0, nullptr, nullptr, lw.att_ln_g, lw.att_ln_b, xn, M, d, st));
         // MHSA (attention.py:72-151)
         if (tc_attn) {
             Bf16State *bs = h->bf;
             PosArgs pa = {bs->meta, bs->trig, d / 2, p.T};
             COCR_TRY(launch_gemm_tc(h, EPI_BF16_POS, xn, d, bs->w_qkvx + (size_t)l * bs->nx * d, d, bs->b_qkvx + (size_t)l * bs->nx, hb,
-                                    bs->nx, nullptr, M, bs->nx, d, st, 0, &pa));
+                                    bs->nx, nullptr, M, bs->nx, d, st, 0, &pa, "gemm_qkvx_pos"));
             COCR_TRY(launch_attn_tc(h, hb, lens_dev, g, B, p.T, st));
         } else {
-            COCR_TRY(launch_gemm_tc(h, EPI_BF16, xn, d, WB(h, lw.w_qkv), d, lw.b_qkv, hb, 3 * d, nullptr, M, 3 * d, d, st));
+            COCR_TRY(launch_gemm_tc(h, EPI_BF16, xn, d, WB(h, lw.w_qkv), d, lw.b_qkv, hb, 3 * d, nullptr, M, 3 * d, d, st, 0, nullptr, "gemm_qkv"));
             COCR_TRY(launch_attn_simt_bf16(h, hb, h->pos_proj + (size_t)l * (2 * p.T - 1) * d, lw.u_bias, lw.v_bias, lens_dev, g,
                                            B, p.T, st));
         }
-        COCR_TRY(launch_gemm_tc(h, EPI_BF16, g, d, WB(h, lw.w_out), d, lw.b_out, y, d, nullptr, M, d, d, st));
+        COCR_TRY(launch_gemm_tc(h, EPI_BF16, g, d, WB(h, lw.w_out), d, lw.b_out, y, d, nullptr, M, d, d, st, 0, nullptr, "gemm_attn_out"));
         COCR_TRY(launch_resid_ln(h, x, y, 1.f, 0, nullptr, nullptr, lw.conv_ln_g, lw.conv_ln_b, xn, M, d, st));
         // convolution module (convolution.py:135-148)
-        COCR_TRY(launch_gemm_tc(h, EPI_BF16, xn, d, WB(h, lw.w_pw1), d, lw.b_pw1, hb, 2 * d, nullptr, M, 2 * d, d, st));
-        COCR_TRY(launch_glu_dw_bf16(h, hb, lw, g, B, p.T, st));
-        COCR_TRY(launch_gemm_tc(h, EPI_BF16, g, d, WB(h, lw.w_pw2), d, lw.b_pw2, y, d, nullptr, M, d, d, st));
+        COCR_TRY(launch_gemm_tc(h, EPI_BF16, xn, d, WB(h, lw.w_pw1), d, lw.b_pw1, hb, 2 * d, nullptr, M, 2 * d, d, st, 0, nullptr, "gemm_pw1"));
+        int rc_dw = launch_glu_dw_fast(h, hb, lw, g, B, p.T, st);
+        if (rc_dw == COCR_ERR_UNSUPPORTED) rc_dw = launch_glu_dw_bf16(h, hb, lw, g, B, p.T, st);
+        if (rc_dw != COCR_OK) return rc_dw;
+        COCR_TRY(launch_gemm_tc(h, EPI_BF16, g, d, WB(h, lw.w_pw2), d, lw.b_pw2, y, d, nullptr, M, d, d, st, 0, nullptr, "gemm_pw2"));
         COCR_TRY(launch_resid_ln(h, x, y, 1.f, 0, nullptr, nullptr, lw.ffn_ln_g[1], lw.ffn_ln_b[1], xn, M, d, st));
         // FFN 2 + block-final LayerNorm (encoder.py:91-99) + next block's first LayerNorm
-        COCR_TRY(launch_gemm_tc(h, EPI_BF16_SILU, xn, d, WB(h, lw.ffn_w1[1]), d, lw.ffn_b1[1], hb, dm.ff, nullptr, M, dm.ff, d, st));
-        COCR_TRY(launch_gemm_tc(h, EPI_BF16, hb, dm.ff, WB(h, lw.ffn_w2[1]), dm.ff, lw.ffn_b2[1], y, d, nullptr, M, d, dm.ff, st));
+        COCR_TRY(launch_gemm_tc(h, EPI_BF16_SILU, xn, d, WB(h, lw.ffn_w1[1]), d, lw.ffn_b1[1], hb, dm.ff, nullptr, M, dm.ff, d, st, 0, nullptr, "gemm_ffn_up"));
+        COCR_TRY(launch_gemm_tc(h, EPI_BF16, hb, dm.ff, WB(h, lw.ffn_w2[1]), dm.ff, lw.ffn_b2[1], y, d, nullptr, M, d, dm.ff, st, 0, nullptr, "gemm_ffn_down"));
         const float *ng = (l + 1 < dm.L) ? h->layers[l + 1].ffn_ln_g[0] : nullptr;
         const float *nb = (l + 1 < dm.L) ? h->layers[l + 1].ffn_ln_b[0] : nullptr;
         COCR_TRY(launch_resid_ln(h, x, y, dm.ffn_factor, 0, lw.final_ln_g, lw.final_ln_b, ng, nb, xn, M, d, st));
@@ -575,7 +582,7 @@ int bf16_logits(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_
     COCR_TRY(bf16_forward(h, img, sb, sw, sh, widths, B, W, st, out_lens, p));
     const Dims &dm = h->dm;
     return launch_gemm_tc(h, EPI_F32, (const bf16 *)(h->ws.base + p.off_xn), dm.d, WB(h, h->dec_w), dm.d, h->dec_b, logits, dm.C,
-                          nullptr, p.M, dm.C, dm.d, st);
+                          nullptr, p.M, dm.C, dm.d, st, 0, nullptr, "gemm_logits");
 }
 
 int bf16_forward_decode(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths, int B,
@@ -591,7 +598,7 @@ int bf16_forward_decode(cocr_handle *h, const float *img, int64_t sb, int64_t sw
     COCR_CUDA(h, cudaMemsetAsync(best, 0, (size_t)p.M * 8, st));
     // CTC projection fused with the per-frame arg-max: logits never reach HBM (pred.py:121 + :138-143)
     COCR_TRY(launch_gemm_tc(h, EPI_ARGMAX, (const bf16 *)(ws + p.off_xn), dm.d, WB(h, h->dec_w), dm.d, h->dec_b, nullptr, 0, best,
-                            p.M, dm.C, dm.d, st));
+                            p.M, dm.C, dm.d, st, 0, nullptr, "gemm_ctc_argmax"));
     k_unpack_best<<<(p.M + 255) / 256, 256, 0, st>>>(best, p.M, bv, bi);
     COCR_LAUNCHED(h);
     return launch_collapse(h, bv, bi, out_lens, B, p.T, st, labels, starts, ends, conf, counts);

@@ -177,6 +177,12 @@ int launch_glu_dw_bf16(cocr_handle *h, const __nv_bfloat16 *u, const LayerF32 &l
 int launch_layernorm(cocr_handle *h, const float *x, float *y, const float *g, const float *b, int M, int d,
                      cudaStream_t st);
 
+// ---- optimised memory-bound kernels (mem_kernels.cu); return COCR_ERR_UNSUPPORTED when the geometry is not covered
+int launch_glu_dw_fast(cocr_handle *h, const __nv_bfloat16 *u, const LayerF32 &lw, __nv_bfloat16 *g, int B, int T,
+                       cudaStream_t st);
+int launch_frontend_fused(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, int B, int W,
+                          __nv_bfloat16 *feat, cudaStream_t st);
+
 // ---- bf16 path (bf16_path.cu) ------------------------------------------------------------
 int bf16_init(cocr_handle *h);       // pack weights; called from cocr_finalize_weights when precision == bf16
 void bf16_destroy(cocr_handle *h);

@@ -1,0 +1,264 @@
+// Memory-bound kernels of the bf16 path, written for HBM/L2 efficiency: 16-byte vector accesses, shared-memory
+// staging with halos, register sliding windows.
+//   * k_glu_dw_fast   : GLU -> depthwise conv (K taps) -> folded BatchNorm -> SiLU      (convolution.py:139-142)
+//   * k_frontend_fused: Conv2d(1->32,3x3,s2)+ReLU -> depthwise Conv2d(3x3,s2) -> 1x1 conv+ReLU -> (t, f*32+c) bf16
+//                       features for the 768->144 projection                              (convolution.py:190-237)
+#include "common.h"
+
+namespace cocr {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t u) {
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u));
+}
+__device__ __forceinline__ uint32_t f2_to_bf2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// conv module middle.  u (B,T,2d) bf16 [value | gate]  ->  g (B,T,d) bf16.   One CTA = DW_TT frames of one line,
+// thread = (channel pair, segment of DW_SEG consecutive frames); the K-tap window slides through registers.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int DWF_TT = 64;
+constexpr int DWF_SEG = 8;
+
+template <int K>
+__global__ void __launch_bounds__(576)
+k_glu_dw_fast(const bf16 *__restrict__ u, const float *__restrict__ wdw, const float *__restrict__ scale,
+              const float *__restrict__ shift, bf16 *__restrict__ g, int T, int d) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    const int P = d >> 1;                                   // channel pairs
+    constexpr int ROWS = DWF_TT + K - 1;
+    uint32_t *xs = reinterpret_cast<uint32_t *>(sm_raw);    // [ROWS][P] bf16x2 (GLU output)
+    float2 *ws = reinterpret_cast<float2 *>(xs + ROWS * P); // [K][P]
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * DWF_TT;
+    constexpr int pad = (K - 1) / 2;
+    const int nthr = blockDim.x;
+
+    // phase 1: GLU of rows [t0-pad, t0+TT+pad) into shared memory (zeros outside the line: conv zero padding)
+    const int c8n = d >> 3;                                 // 16-byte chunks per half row
+    for (int e = threadIdx.x; e < ROWS * c8n; e += nthr) {
+        const int row = e / c8n, c8 = e - row * c8n;
+        const int t = t0 - pad + row;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (t >= 0 && t < T) {
+            const bf16 *src = u + ((int64_t)b * T + t) * 2 * d + c8 * 8;
+            const uint4 va = *reinterpret_cast<const uint4 *>(src);
+            const uint4 vg = *reinterpret_cast<const uint4 *>(src + d);
+            const uint32_t a[4] = {va.x, va.y, va.z, va.w}, gt[4] = {vg.x, vg.y, vg.z, vg.w};
+            uint32_t r[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 fa = bf2_to_f2(a[i]), fg = bf2_to_f2(gt[i]);
+                r[i] = f2_to_bf2(fa.x * sigmoid_fast(fg.x), fa.y * sigmoid_fast(fg.y));
+            }
+            o = make_uint4(r[0], r[1], r[2], r[3]);
+        }
+        *reinterpret_cast<uint4 *>(xs + row * P + c8 * 4) = o;
+    }
+    for (int e = threadIdx.x; e < K * P; e += nthr) {
+        const int k = e / P, pr = e - k * P;
+        ws[e] = make_float2(wdw[(2 * pr) * K + k], wdw[(2 * pr + 1) * K + k]);
+    }
+    __syncthreads();
+
+    // phase 2
+    const int pr = threadIdx.x % P, seg = threadIdx.x / P;
+    if (seg * DWF_SEG >= DWF_TT) return;
+    float2 x[DWF_SEG + K - 1];
+#pragma unroll
+    for (int i = 0; i < DWF_SEG + K - 1; ++i) x[i] = bf2_to_f2(xs[(seg * DWF_SEG + i) * P + pr]);
+    float2 acc[DWF_SEG];
+#pragma unroll
+    for (int i = 0; i < DWF_SEG; ++i) acc[i] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float2 w = ws[k * P + pr];
+#pragma unroll
+        for (int i = 0; i < DWF_SEG; ++i) {
+            acc[i].x = fmaf(w.x, x[i + k].x, acc[i].x);
+            acc[i].y = fmaf(w.y, x[i + k].y, acc[i].y);
+        }
+    }
+    const float2 sc = make_float2(scale[2 * pr], scale[2 * pr + 1]);
+    const float2 sh = make_float2(shift[2 * pr], shift[2 * pr + 1]);
+#pragma unroll
+    for (int i = 0; i < DWF_SEG; ++i) {
+        const int t = t0 + seg * DWF_SEG + i;
+        if (t < T) {
+            const float y0 = fmaf(acc[i].x, sc.x, sh.x), y1 = fmaf(acc[i].y, sc.y, sh.y);
+            *reinterpret_cast<uint32_t *>(g + ((int64_t)b * T + t) * d + 2 * pr) = f2_to_bf2(y0 * sigmoid_fast(y0), y1 * sigmoid_fast(y1));
+        }
+    }
+}
+
+// returns COCR_ERR_UNSUPPORTED (without touching h->err) when the geometry is not covered; the caller then uses
+// the generic kernel of fp32_path.cu
+int launch_glu_dw_fast(cocr_handle *h, const bf16 *u, const LayerF32 &lw, bf16 *g, int B, int T, cudaStream_t st) {
+    const Dims &dm = h->dm;
+    const int P = dm.d / 2;
+    const int nthr = P * (DWF_TT / DWF_SEG);
+    if (dm.K != 31 || (dm.d & 7) != 0 || nthr > 576) return COCR_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)(DWF_TT + 30) * P * 4 + (size_t)31 * P * 8;
+    static bool attr = false;
+    if (!attr) {
+        COCR_CUDA(h, cudaFuncSetAttribute(k_glu_dw_fast<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    dim3 grid((T + DWF_TT - 1) / DWF_TT, B);
+    ProfScope ps(h, "glu_dwconv_bn_silu_bf16", st, 2.0 * 31 * B * (double)T * dm.d, 6.0 * B * T * dm.d);
+    k_glu_dw_fast<31><<<grid, nthr, smem, st>>>(u, lw.w_dw, lw.bn_scale, lw.bn_shift, g, T, dm.d);
+    COCR_LAUNCHED(h);
+    return COCR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// fused subsampling front-end for 32 conv channels (lane = channel).  One CTA = FE_TT output frames of one line.
+//   stage A: input patch (H x (4*TT+3)) -> shared (zero padded)
+//   stage B: conv1+ReLU  -> a1 tile [(2*TT+1)][F2][32] bf16 in shared; warp = one t2 row, lane = channel,
+//            input row broadcast from shared with 16-byte loads, 9 weights per lane in registers
+//   stage C: depthwise 3x3 s2 -> a2 [TT][F][32] fp32 in shared
+//   stage D: 1x1 conv 32->32 + ReLU, weights Wpw[lane][0..31] in registers, a2 broadcast; writes bf16 features
+// ------------------------------------------------------------------------------------------------------------
+constexpr int FE_TT = 8;
+constexpr int FE_THREADS = 256;
+
+__global__ void __launch_bounds__(FE_THREADS)
+k_frontend_fused(const float *__restrict__ img, int64_t sb, int64_t sw, int64_t sh, const float *__restrict__ w1,
+                 const float *__restrict__ b1, const float *__restrict__ wdw, const float *__restrict__ bdw,
+                 const float *__restrict__ wpw, const float *__restrict__ bpw, bf16 *__restrict__ feat, int W, int H, int T2,
+                 int T, int F2, int F) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    constexpr int NW = 4 * FE_TT + 3;               // input columns (time) needed
+    constexpr int NT2 = 2 * FE_TT + 1;              // conv1 rows needed
+    const int HP = (H + 2 + 3) & ~3;                // padded input row: y = -1 .. H, rounded to 4 floats
+    float *patch = reinterpret_cast<float *>(sm_raw);                     // [NW][HP], patch[wl][y+1]
+    bf16 *a1 = reinterpret_cast<bf16 *>(patch + NW * HP);                 // [NT2][F2][32]
+    float *a2 = reinterpret_cast<float *>(a1 + (size_t)NT2 * F2 * 32);    // [TT][F][32]
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * FE_TT;
+    const int w0 = 4 * t0 - 3;                      // first input column of the patch
+    const int t20 = 2 * t0 - 1;                     // first conv1 row of the tile
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // stage A
+    for (int e = threadIdx.x; e < NW * HP; e += FE_THREADS) {
+        int wl, y;
+        if (sw == 1) { y = e / NW; wl = e - y * NW; }           // (N,1,H,W) layout: time is contiguous
+        else { wl = e / HP; y = e - wl * HP; }                  // (B,W,H) layout: height is contiguous
+        const int w = w0 + wl, yy = y - 1;
+        float v = 0.0f;
+        if (w >= 0 && w < W && yy >= 0 && yy < H) v = img[b * sb + w * sw + yy * sh];
+        patch[wl * HP + y] = v;
+    }
+    __syncthreads();
+
+    // stage B: conv1 (convolution.py:192-198); conv "height" = time, conv "width" = image height
+    {
+        float wr[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) wr[i] = w1[lane * 9 + i];
+        const float bias = b1[lane];
+        for (int r = warp; r < NT2; r += FE_THREADS / 32) {
+            const int t2 = t20 + r;
+            bf16 *dst = a1 + (size_t)r * F2 * 32 + lane;
+            if (t2 < 0 || t2 >= T2) {                            // outside the conv1 output: zero padding of the dw conv
+                for (int f2 = 0; f2 < F2; ++f2) dst[f2 * 32] = __float2bfloat16_rn(0.0f);
+                continue;
+            }
+            // local input columns of this row: wl = 2*r + kh  (w = 2*t2 - 1 + kh)
+            const float *p0 = patch + (2 * r) * HP, *p1 = p0 + HP, *p2 = p1 + HP;
+            for (int f2 = 0; f2 < F2; f2 += 2) {                 // two outputs per iteration share one 16-byte window
+                // y indices (padded by +1): outputs f2, f2+1 use y' = 2*f2 .. 2*f2+4
+                const float4 q0 = *reinterpret_cast<const float4 *>(p0 + 2 * f2);
+                const float4 q1 = *reinterpret_cast<const float4 *>(p1 + 2 * f2);
+                const float4 q2 = *reinterpret_cast<const float4 *>(p2 + 2 * f2);
+                const float e0 = p0[2 * f2 + 4], e1 = p1[2 * f2 + 4], e2 = p2[2 * f2 + 4];
+                float o0 = bias, o1 = bias;
+                o0 = fmaf(wr[0], q0.x, o0); o0 = fmaf(wr[1], q0.y, o0); o0 = fmaf(wr[2], q0.z, o0);
+                o0 = fmaf(wr[3], q1.x, o0); o0 = fmaf(wr[4], q1.y, o0); o0 = fmaf(wr[5], q1.z, o0);
+                o0 = fmaf(wr[6], q2.x, o0); o0 = fmaf(wr[7], q2.y, o0); o0 = fmaf(wr[8], q2.z, o0);
+                o1 = fmaf(wr[0], q0.z, o1); o1 = fmaf(wr[1], q0.w, o1); o1 = fmaf(wr[2], e0, o1);
+                o1 = fmaf(wr[3], q1.z, o1); o1 = fmaf(wr[4], q1.w, o1); o1 = fmaf(wr[5], e1, o1);
+                o1 = fmaf(wr[6], q2.z, o1); o1 = fmaf(wr[7], q2.w, o1); o1 = fmaf(wr[8], e2, o1);
+                dst[f2 * 32] = __float2bfloat16_rn(fmaxf(o0, 0.0f));
+                if (f2 + 1 < F2) dst[(f2 + 1) * 32] = __float2bfloat16_rn(fmaxf(o1, 0.0f));
+            }
+        }
+    }
+    __syncthreads();
+
+    // stage C: depthwise conv (convolution.py:200-205): a2[t][f][c] = b + sum a1[2t-1+kh][2f-1+kw][c] w[c][kh][kw]
+    {
+        float wr[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) wr[i] = wdw[lane * 9 + i];
+        const float bias = bdw[lane];
+        for (int tl = warp; tl < FE_TT; tl += FE_THREADS / 32) {
+            for (int f = 0; f < F; ++f) {
+                float o = bias;
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+                    const int r = 2 * tl + kh;                   // local conv1 row (t2 = 2t-1+kh, t20 = 2*t0-1)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const int f2 = 2 * f - 1 + kw;
+                        if (f2 >= 0 && f2 < F2) o = fmaf(wr[kh * 3 + kw], __bfloat162float(a1[((size_t)r * F2 + f2) * 32 + lane]), o);
+                    }
+                }
+                a2[(tl * F + f) * 32 + lane] = o;
+            }
+        }
+    }
+    __syncthreads();
+
+    // stage D: 1x1 conv + ReLU (convolution.py:207-213) and the (t, f*32+c) feature layout the projection consumes
+    {
+        float wr[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) wr[i] = wpw[lane * 32 + i];
+        const float bias = bpw[lane];
+        for (int e = warp; e < FE_TT * F; e += FE_THREADS / 32) {
+            const int tl = e / F, f = e - tl * F;
+            const int t = t0 + tl;
+            if (t >= T) continue;
+            const float4 *src = reinterpret_cast<const float4 *>(a2 + (tl * F + f) * 32);
+            float o = bias;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 v = src[i];
+                o = fmaf(wr[4 * i + 0], v.x, o); o = fmaf(wr[4 * i + 1], v.y, o);
+                o = fmaf(wr[4 * i + 2], v.z, o); o = fmaf(wr[4 * i + 3], v.w, o);
+            }
+            feat[((int64_t)b * T + t) * (F * 32) + f * 32 + lane] = __float2bfloat16_rn(fmaxf(o, 0.0f));
+        }
+    }
+}
+
+int launch_frontend_fused(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, int B, int W, bf16 *feat,
+                          cudaStream_t st) {
+    const Dims &dm = h->dm;
+    if (dm.cc != 32 || (dm.F2 & 1) != 0) return COCR_ERR_UNSUPPORTED;
+    const int T2 = out_len1(W), T = out_len1(T2);
+    const int HP = (dm.H + 2 + 3) & ~3;
+    const size_t smem = (size_t)(4 * FE_TT + 3) * HP * 4 + (size_t)(2 * FE_TT + 1) * dm.F2 * 32 * 2 + (size_t)FE_TT * dm.F * 32 * 4;
+    if (smem > 200 * 1024) return COCR_ERR_UNSUPPORTED;
+    static size_t attr = 0;
+    if (smem > attr) {
+        COCR_CUDA(h, cudaFuncSetAttribute(k_frontend_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    dim3 grid((T + FE_TT - 1) / FE_TT, B);
+    const double n1 = (double)B * T2 * dm.F2 * 32, n2 = (double)B * T * dm.F * 32;
+    ProfScope ps(h, "frontend_fused", st, 18.0 * n1 + 18.0 * n2 + 64.0 * n2, 4.0 * B * (double)W * dm.H + 2.0 * n2);
+    k_frontend_fused<<<grid, FE_THREADS, smem, st>>>(img, sb, sw, sh, h->sub_w1, h->sub_b1, h->sub_wdw, h->sub_bdw, h->sub_wpw,
+                                                    h->sub_bpw, feat, W, dm.H, T2, T, dm.F2, dm.F);
+    COCR_LAUNCHED(h);
+    return COCR_OK;
+}
+
+}  // namespace cocr
