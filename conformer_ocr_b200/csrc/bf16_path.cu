@@ -76,10 +76,11 @@ static int pick_block_n(int N) {
 }
 
 struct PosArgs { const int16_t *meta; const float2 *trig; int trig_ld, T; };
+struct ResidArgs { float *x; float alpha; int init; const float *gf, *bf, *g1, *b1; };
 
 int launch_gemm_tc(cocr_handle *h, int epi, const bf16 *A, int lda, const bf16 *W, int ldw, const float *bias, void *out,
                    int ldc, unsigned long long *best, int M, int N, int K, cudaStream_t st, int block_n_override = 0,
-                   const PosArgs *pos = nullptr, const char *tag = "gemm_tc") {
+                   const PosArgs *pos = nullptr, const char *tag = "gemm_tc", const ResidArgs *res = nullptr) {
     if (M <= 0 || N <= 0) return COCR_OK;
     if (K % 16 != 0 || lda % 8 != 0 || ldw % 8 != 0)
         return set_error(h, COCR_ERR_UNSUPPORTED, "tensor-core GEMM needs K %% 16 == 0 and 16-byte aligned rows (K=%d lda=%d ldw=%d)", K,
@@ -95,15 +96,19 @@ int launch_gemm_tc(cocr_handle *h, int epi, const bf16 *A, int lda, const bf16 *
     p.col_meta = pos ? pos->meta : nullptr; p.trig = pos ? pos->trig : nullptr;
     p.trig_ld = pos ? pos->trig_ld : 0; p.T = pos ? pos->T : 1;
     if (epi == EPI_BF16_POS && (!pos || p.block_n % 16 != 0)) return set_error(h, COCR_ERR_BAD_ARG, "POS epilogue needs position tables");
+    p.x = res ? res->x : nullptr; p.alpha = res ? res->alpha : 1.f; p.init = res ? res->init : 0;
+    p.gf = res ? res->gf : nullptr; p.bf = res ? res->bf : nullptr; p.g1 = res ? res->g1 : nullptr; p.b1 = res ? res->b1 : nullptr;
+    if (epi == EPI_RESID && (!res || p.n_tiles != 1 || p.block_n != N || N > 192))
+        return set_error(h, COCR_ERR_BAD_ARG, "residual epilogue needs a single N tile of at most 192 columns (N=%d)", N);
     int tm = 32;
     while (tm < 2 * p.block_n) tm <<= 1;
     p.tmem_cols = tm;
     const uint32_t b_chunk = gemm_b_chunk_bytes(p.block_n);
-    const uint32_t fixed = 4 * 2 * 4096 + 2048 + 256 + 1024;        // staging + bias + barriers + alignment slack
+    const uint32_t fixed = GEMM_FIXED_SMEM;        // staging + bias / LayerNorm vectors + barriers + alignment slack
     const uint32_t budget = (uint32_t)h->bf->smem_optin;
     // resident weights when the whole K extent of one N-slice fits next to >= 4 A slots
     const uint32_t bres = (uint32_t)p.nkc * b_chunk;
-    p.resident = (bres + 4 * GEMM_A_CHUNK + fixed <= budget) && (p.n_tiles <= h->num_sms) ? 1 : 0;
+    p.resident = (bres + 3 * GEMM_A_CHUNK + fixed <= budget) && (p.n_tiles <= h->num_sms) ? 1 : 0;
     const uint32_t slot = GEMM_A_CHUNK + (p.resident ? 0u : b_chunk);
     const uint32_t avail = budget - fixed - (p.resident ? bres : 0u);
     int stages = (int)(avail / slot);
@@ -145,6 +150,7 @@ int launch_gemm_tc(cocr_handle *h, int epi, const bf16 *A, int lda, const bf16 *
         COCR_GEMM_CASE(EPI_F32)
         COCR_GEMM_CASE(EPI_ARGMAX)
         COCR_GEMM_CASE(EPI_BF16_POS)
+        COCR_GEMM_CASE(EPI_RESID)
         default: return set_error(h, COCR_ERR_BAD_ARG, "unknown GEMM epilogue %d", epi);
     }
 #undef COCR_GEMM_CASE
@@ -525,18 +531,25 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
     } else if (rc_fe != COCR_OK) {
         return rc_fe;
     }
-    COCR_TRY(launch_gemm_tc(h, EPI_BF16, feat, dm.feat, WB(h, h->sub_wout), dm.feat, h->sub_bout, y, d, nullptr, M, d, dm.feat, st, 0, nullptr, "gemm_sub_out"));
-    if (dm.L == 0) {
-        COCR_TRY(launch_resid_ln(h, x, y, 1.f, 1, nullptr, nullptr, nullptr, nullptr, xn, M, d, st));
-        return COCR_OK;
-    }
-    COCR_TRY(launch_resid_ln(h, x, y, 1.f, 1, nullptr, nullptr, h->layers[0].ffn_ln_g[0], h->layers[0].ffn_ln_b[0], xn, M, d, st));
+    // Residual-stream GEMMs: with encoder_dim <= 192 the update x += alpha*(..) and the LayerNorm feeding the next module
+    // run in the GEMM epilogue (EPI_RESID); otherwise GEMM -> bf16 y -> k_resid_ln.
+    const bool fused = (d <= 192);
+    auto resid_gemm = [&](const bf16 *A, int K, const float *Wf, const float *bias, float alpha, int init, const float *gf,
+                          const float *bfin, const float *g1, const float *b1, const char *tag) -> int {
+        if (fused) {
+            ResidArgs ra = {x, alpha, init, gf, bfin, g1, b1};
+            return launch_gemm_tc(h, EPI_RESID, A, K, WB(h, Wf), K, bias, xn, d, nullptr, M, d, K, st, 0, nullptr, tag, &ra);
+        }
+        COCR_TRY(launch_gemm_tc(h, EPI_BF16, A, K, WB(h, Wf), K, bias, y, d, nullptr, M, d, K, st, 0, nullptr, tag));
+        return launch_resid_ln(h, x, y, alpha, init, gf, bfin, g1, b1, xn, M, d, st);
+    };
+    const float *g0 = dm.L > 0 ? h->layers[0].ffn_ln_g[0] : nullptr, *b0 = dm.L > 0 ? h->layers[0].ffn_ln_b[0] : nullptr;
+    COCR_TRY(resid_gemm(feat, dm.feat, h->sub_wout, h->sub_bout, 1.f, 1, nullptr, nullptr, g0, b0, "gemm_sub_out"));
     for (int l = 0; l < dm.L; ++l) {
         const LayerF32 &lw = h->layers[l];
-        // FFN 1 (feed_forward.py:45-55; half-step residual encoder.py:68-75)
+        // FFN 1 (feed_forward.py:45-55; half-step residual encoder.py:68-75) -> LayerNorm of the attention module
         COCR_TRY(launch_gemm_tc(h, EPI_BF16_SILU, xn, d, WB(h, lw.ffn_w1[0]), d, lw.ffn_b1[0], hb, dm.ff, nullptr, M, dm.ff, d, st, 0, nullptr, "gemm_ffn_up"));
-        COCR_TRY(launch_gemm_tc(h, EPI_BF16, hb, dm.ff, WB(h, lw.ffn_w2[0]), dm.ff, lw.ffn_b2[0], y, d, nullptr, M, d, dm.ff, st, 0, nullptr, "gemm_ffn_down"));
-        COCR_TRY(launch_resid_ln(h, x, y, dm.ffn_factor, 0, nullptr, nullptr, lw.att_ln_g, lw.att_ln_b, xn, M, d, st));
+        COCR_TRY(resid_gemm(hb, dm.ff, lw.ffn_w2[0], lw.ffn_b2[0], dm.ffn_factor, 0, nullptr, nullptr, lw.att_ln_g, lw.att_ln_b, "gemm_ffn_down"));
         // MHSA (attention.py:72-151)
         if (tc_attn) {
             Bf16State *bs = h->bf;
@@ -549,21 +562,18 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
             COCR_TRY(launch_attn_simt_bf16(h, hb, h->pos_proj + (size_t)l * (2 * p.T - 1) * d, lw.u_bias, lw.v_bias, lens_dev, g,
                                            B, p.T, st));
         }
-        COCR_TRY(launch_gemm_tc(h, EPI_BF16, g, d, WB(h, lw.w_out), d, lw.b_out, y, d, nullptr, M, d, d, st, 0, nullptr, "gemm_attn_out"));
-        COCR_TRY(launch_resid_ln(h, x, y, 1.f, 0, nullptr, nullptr, lw.conv_ln_g, lw.conv_ln_b, xn, M, d, st));
+        COCR_TRY(resid_gemm(g, d, lw.w_out, lw.b_out, 1.f, 0, nullptr, nullptr, lw.conv_ln_g, lw.conv_ln_b, "gemm_attn_out"));
         // convolution module (convolution.py:135-148)
         COCR_TRY(launch_gemm_tc(h, EPI_BF16, xn, d, WB(h, lw.w_pw1), d, lw.b_pw1, hb, 2 * d, nullptr, M, 2 * d, d, st, 0, nullptr, "gemm_pw1"));
         int rc_dw = launch_glu_dw_fast(h, hb, lw, g, B, p.T, st);
         if (rc_dw == COCR_ERR_UNSUPPORTED) rc_dw = launch_glu_dw_bf16(h, hb, lw, g, B, p.T, st);
         if (rc_dw != COCR_OK) return rc_dw;
-        COCR_TRY(launch_gemm_tc(h, EPI_BF16, g, d, WB(h, lw.w_pw2), d, lw.b_pw2, y, d, nullptr, M, d, d, st, 0, nullptr, "gemm_pw2"));
-        COCR_TRY(launch_resid_ln(h, x, y, 1.f, 0, nullptr, nullptr, lw.ffn_ln_g[1], lw.ffn_ln_b[1], xn, M, d, st));
+        COCR_TRY(resid_gemm(g, d, lw.w_pw2, lw.b_pw2, 1.f, 0, nullptr, nullptr, lw.ffn_ln_g[1], lw.ffn_ln_b[1], "gemm_pw2"));
         // FFN 2 + block-final LayerNorm (encoder.py:91-99) + next block's first LayerNorm
         COCR_TRY(launch_gemm_tc(h, EPI_BF16_SILU, xn, d, WB(h, lw.ffn_w1[1]), d, lw.ffn_b1[1], hb, dm.ff, nullptr, M, dm.ff, d, st, 0, nullptr, "gemm_ffn_up"));
-        COCR_TRY(launch_gemm_tc(h, EPI_BF16, hb, dm.ff, WB(h, lw.ffn_w2[1]), dm.ff, lw.ffn_b2[1], y, d, nullptr, M, d, dm.ff, st, 0, nullptr, "gemm_ffn_down"));
         const float *ng = (l + 1 < dm.L) ? h->layers[l + 1].ffn_ln_g[0] : nullptr;
         const float *nb = (l + 1 < dm.L) ? h->layers[l + 1].ffn_ln_b[0] : nullptr;
-        COCR_TRY(launch_resid_ln(h, x, y, dm.ffn_factor, 0, lw.final_ln_g, lw.final_ln_b, ng, nb, xn, M, d, st));
+        COCR_TRY(resid_gemm(hb, dm.ff, lw.ffn_w2[1], lw.ffn_b2[1], dm.ffn_factor, 0, lw.final_ln_g, lw.final_ln_b, ng, nb, "gemm_ffn_down_final"));
     }
     return COCR_OK;
 }
@@ -715,5 +725,79 @@ int selftest_gemm(int device, int epi, int M, int N, int K, int block_n, double 
     cocr_destroy(h);
     return COCR_OK;
 }
+
+// residual epilogue vs host reference.  flags: bit0 init, bit1 block-final LayerNorm, bit2 next LayerNorm
+int selftest_resid(int device, int M, int N, int K, int flags, double *max_err) {
+    cocr_hparams hp = {96, 144, 0, 4, 4, 2, 31, 1, 32, 4, 0, COCR_FP32, 0};
+    cocr_handle *h = nullptr;
+    int rc = cocr_create(&hp, device, &h);
+    if (rc != COCR_OK) return rc;
+    h->bf = new Bf16State();
+    cudaDeviceGetAttribute(&h->bf->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    bf16 *A, *Wt, *xn;
+    float *bias, *ref, *x, *ln;
+    cudaMalloc((void **)&A, (size_t)M * K * 2); cudaMalloc((void **)&Wt, (size_t)N * K * 2); cudaMalloc((void **)&xn, (size_t)M * N * 2);
+    cudaMalloc((void **)&bias, (size_t)N * 4); cudaMalloc((void **)&ref, (size_t)M * N * 4); cudaMalloc((void **)&x, (size_t)M * N * 4);
+    cudaMalloc((void **)&ln, (size_t)4 * N * 4);
+    k_fill_bf16<<<(unsigned)(((size_t)M * K + 255) / 256), 256>>>(A, (size_t)M * K, 1u, 1.0f);
+    k_fill_bf16<<<(unsigned)(((size_t)N * K + 255) / 256), 256>>>(Wt, (size_t)N * K, 2u, 0.25f);
+    k_fill_f32<<<(N + 255) / 256, 256>>>(bias, (size_t)N, 3u, 0.5f);
+    k_fill_f32<<<(unsigned)(((size_t)M * N + 255) / 256), 256>>>(x, (size_t)M * N, 4u, 2.0f);
+    k_fill_f32<<<(4 * N + 255) / 256, 256>>>(ln, (size_t)4 * N, 5u, 1.0f);
+    k_ref_gemm<<<(unsigned)(((size_t)M * N + 255) / 256), 256>>>(A, Wt, bias, ref, M, N, K, 0);
+    std::vector<float> hx((size_t)M * N), href((size_t)M * N), hln(4 * N);
+    cudaMemcpy(hx.data(), x, hx.size() * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(hln.data(), ln, hln.size() * 4, cudaMemcpyDeviceToHost);
+    const bool init = flags & 1, fin = flags & 2, nxt = flags & 4;
+    const float alpha = 0.5f;
+    ResidArgs ra = {x, alpha, init ? 1 : 0, fin ? ln : nullptr, fin ? ln + N : nullptr, nxt ? ln + 2 * N : nullptr, nxt ? ln + 3 * N : nullptr};
+    rc = launch_gemm_tc(h, EPI_RESID, A, K, Wt, K, bias, xn, N, nullptr, M, N, K, 0, 0, nullptr, "selftest", &ra);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (rc == COCR_OK && e != cudaSuccess) rc = set_error(h, COCR_ERR_CUDA, "selftest_resid: %s", cudaGetErrorString(e));
+    double worst = 0.0;
+    if (rc == COCR_OK) {
+        cudaMemcpy(href.data(), ref, href.size() * 4, cudaMemcpyDeviceToHost);
+        std::vector<float> gx((size_t)M * N);
+        std::vector<uint16_t> gn((size_t)M * N);
+        cudaMemcpy(gx.data(), x, gx.size() * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(gn.data(), xn, gn.size() * 2, cudaMemcpyDeviceToHost);
+        std::vector<double> v(N);
+        auto lnorm = [&](const float *g, const float *b) {
+            double mu = 0, var = 0;
+            for (int n = 0; n < N; ++n) mu += v[n];
+            mu /= N;
+            for (int n = 0; n < N; ++n) var += (v[n] - mu) * (v[n] - mu);
+            var /= N;
+            const double r = 1.0 / sqrt(var + 1e-5);
+            for (int n = 0; n < N; ++n) v[n] = (v[n] - mu) * r * g[n] + b[n];
+        };
+        for (int m = 0; m < M; ++m) {
+            for (int n = 0; n < N; ++n)
+                v[n] = init ? (double)href[(size_t)m * N + n] : (double)hx[(size_t)m * N + n] + alpha * (double)href[(size_t)m * N + n];
+            if (fin) lnorm(hln.data(), hln.data() + N);
+            for (int n = 0; n < N; ++n) {
+                double err = fabs((double)gx[(size_t)m * N + n] - v[n]) / (1.0 + fabs(v[n]));
+                if (!(err == err)) err = 1e9;
+                worst = fmax(worst, err * 8.0);      // fp32 stream: weighted 8x so one threshold covers both outputs
+            }
+            if (nxt) lnorm(hln.data() + 2 * N, hln.data() + 3 * N);
+            for (int n = 0; n < N; ++n) {
+                uint32_t b = (uint32_t)gn[(size_t)m * N + n] << 16;
+                float f;
+                memcpy(&f, &b, 4);
+                double err = fabs((double)f - v[n]) / (1.0 + fabs(v[n]));
+                if (!(err == err)) err = 1e9;
+                worst = fmax(worst, err);
+            }
+        }
+    } else {
+        set_global_error(h->err.c_str());
+    }
+    if (max_err) *max_err = worst;
+    cudaFree(A); cudaFree(Wt); cudaFree(xn); cudaFree(bias); cudaFree(ref); cudaFree(x); cudaFree(ln);
+    cocr_destroy(h);
+    return rc;
+}
+
 
 }  // namespace cocr

@@ -4,11 +4,20 @@
 //   * W (weights, row-major [N,K] bf16, i.e. K-major "B" operand) is either RESIDENT in shared memory for
 //     the whole kernel (one N-slice per CTA; all K=144 layers) or streamed through the same ring (K=576/768);
 //   * one elected thread issues tcgen05.mma (UMMA 128 x block_n x 16) into a double-buffered TMEM accumulator;
-//   * four epilogue warps read TMEM with tcgen05.ld (thread = row), apply bias / SiLU / arg-max, transpose
-//     through a per-warp swizzled staging tile and write 128-byte row segments with coalesced 16-byte stores.
+//   * NE (8) epilogue warps - two per TMEM lane quarter, splitting the columns in 32-wide pieces - read TMEM with
+//     tcgen05.ld (thread = row), apply the fused epilogue, transpose through a per-warp swizzled staging tile
+//     and move 64/128-byte row segments with coalesced 16-byte accesses.
 //
-// Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+// Epilogues: bias (+SiLU) -> bf16; bias -> fp32; bias -> running arg-max (CTC decode, logits never stored);
+// bias + rotation by the frame angle (attention operands, see attn_tc.cuh); and the residual epilogue
+//   x <- x + alpha*(acc + bias) [-> LayerNorm_final(x)] ; xn = bf16(LayerNorm_next(x))
+// which keeps the fp32 residual stream and both LayerNorms of a conformer block inside the GEMM
+// (modules.py:31-32, encoder.py:99, feed_forward.py:46, attention.py:148, convolution.py:136).
+//
+// Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..2+NE-1 = epilogue.
 #pragma once
+
+#include <cuda_fp16.h>
 
 #include "tc_utils.cuh"
 
@@ -22,6 +31,7 @@ enum GemmEpi : int {
     EPI_BF16_POS = 4,    // out bf16 = acc + bias, with per-16-column-group position handling (attention operands):
                          //   kind 0 plain; kind 1 rotate pairs by the row's angle (relative-position term);
                          //   kind 2 fill with (cos, sin) of the row's angle
+    EPI_RESID = 5,       // fp32 residual stream update + LayerNorm(s); requires N == block_n (one N tile)
 };
 
 struct GemmArgs {
@@ -34,19 +44,28 @@ struct GemmArgs {
     int stages;              // ring slots
     int tmem_cols;           // power of two >= 2*block_n
     const float *bias;       // (N) or null
-    void *out;               // bf16 / fp32 (M, ldc) row-major, or unused for EPI_ARGMAX
+    void *out;               // bf16 / fp32 (M, ldc) row-major; EPI_RESID: bf16 xn (M, ldc)
     int ldc;
     unsigned long long *best;   // EPI_ARGMAX: (M) packed keys, zero-initialised by the caller
     // EPI_BF16_POS
     const int16_t *col_meta;    // (N/16): kind << 12 | first pair index
     const float2 *trig;         // (T, trig_ld): (sin, cos)(t * omega_m)
     int trig_ld, T;             // row r of the GEMM is frame t = r % T of its line
+    // EPI_RESID
+    float *x;                   // (M, N) fp32 residual stream, updated in place
+    float alpha;                // module factor (0.5 for the half-step FFNs)
+    int init;                   // 1: x = acc + bias (start of the stream)
+    const float *gf, *bf;       // block-final LayerNorm applied to x itself (or null)
+    const float *g1, *b1;       // LayerNorm of the next module -> xn (null: xn = bf16(x))
 };
 
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_NE = 8;                          // epilogue warps
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_NE;
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_KC = 64;                       // k-chunk (elements) = one 128-byte swizzle span of bf16
 constexpr uint32_t GEMM_A_CHUNK = GEMM_BM * 128;  // bytes of one A k-chunk tile
+constexpr uint32_t GEMM_STAGE_BYTES = 4096;       // per-warp staging buffer (32 rows x 128 B), two per warp
+constexpr uint32_t GEMM_FIXED_SMEM = GEMM_NE * 2 * GEMM_STAGE_BYTES + 7 * 256 * 4 + 2 * 128 * 2 * 4 * 2 + 512 + 1024;
 
 __host__ __device__ inline uint32_t gemm_b_chunk_bytes(int block_n) { return (uint32_t)block_n * 128u; }
 
@@ -63,11 +82,25 @@ __device__ __forceinline__ void unpack_best(unsigned long long k, float *v, int 
     *col = (int)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
 }
 
-__device__ __forceinline__ float silu_fast(float v) {
-    // x*sigmoid(x) = 0.5*x*(1 + tanh(0.5*x)); one MUFU op
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
-    return 0.5f * v * (1.0f + t);
+// silu(a), silu(b) -> packed bf16x2.  x*sigmoid(x) = h + h*tanh(h), h = x/2, evaluated as f16x2 (one MUFU op for
+// two elements; 11-bit mantissa, then rounded once to bf16).  |x| is clamped to the f16 range.
+__device__ __forceinline__ uint32_t silu2_bf16(float a, float b) {
+    a = fminf(fmaxf(a, -60000.0f), 60000.0f);
+    b = fminf(fmaxf(b, -60000.0f), 60000.0f);
+    __half2 h = __floats2half2_rn(0.5f * a, 0.5f * b);
+    uint32_t hu = *reinterpret_cast<uint32_t *>(&h), tu;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(tu) : "r"(hu));
+    __half2 t = *reinterpret_cast<__half2 *>(&tu);
+    __half2 r = __hfma2(h, t, h);
+    float2 f = __half22float2(r);
+    __nv_bfloat162 o = __floats2bfloat162_rn(f.x, f.y);
+    return *reinterpret_cast<uint32_t *>(&o);
+}
+
+// byte offset of (row, 16-byte chunk 0..3) in a [32 rows][64 B] staging tile, conflict-free for row-wise 16-byte
+// writes (thread = row) and for 4-lanes-per-row reads
+__device__ __forceinline__ uint32_t stg64_offset(uint32_t row, uint32_t chunk) {
+    return row * 64u + (((chunk ^ (row >> 1)) & 3u) << 4);
 }
 
 template <int EPI>
@@ -83,9 +116,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const uint32_t slot_bytes = GEMM_A_CHUNK + (p.resident ? 0u : b_chunk);
     uint8_t *bres = smem;
     uint8_t *ring = smem + bres_bytes;
-    uint8_t *staging = ring + (uint32_t)p.stages * slot_bytes;           // 4 warps x 2 x 4 KB
-    float *sbias = reinterpret_cast<float *>(staging + 4 * 2 * 4096);     // 2 x 256 floats
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sbias + 512);
+    uint8_t *staging = ring + (uint32_t)p.stages * slot_bytes;                        // NE warps x 2 x 4 KB
+    float *sbias = reinterpret_cast<float *>(staging + GEMM_NE * 2 * GEMM_STAGE_BYTES); // [2][256] bias (per acc stage)
+    float *sln = sbias + 512;                                                           // [4][256] gf, bf, g1, b1
+    float *spad = sln + 1024;                                                           // [256] spare
+    float2 *sred = reinterpret_cast<float2 *>(spad + 256);                              // [2 rounds][2 halves][128] partial sums
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sred + 2 * 2 * 128);
     uint64_t *full = bars;                       // [stages]
     uint64_t *empty = bars + p.stages;           // [stages]
     uint64_t *bfull = bars + 2 * p.stages;       // [1]
@@ -122,10 +158,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(bfull, 1);
         mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
-        mbar_init(&tempty[0], 4); mbar_init(&tempty[1], 4);
+        mbar_init(&tempty[0], GEMM_NE); mbar_init(&tempty[1], GEMM_NE);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if constexpr (EPI == EPI_RESID) {
+        // LayerNorm parameters are tile independent (single N tile)
+        for (int c = threadIdx.x; c < 256; c += GEMM_THREADS) {
+            const bool in = c < p.N;
+            sln[c] = (in && p.gf) ? p.gf[c] : 1.0f;
+            sln[256 + c] = (in && p.bf) ? p.bf[c] : 0.0f;
+            sln[512 + c] = (in && p.g1) ? p.g1[c] : 1.0f;
+            sln[768 + c] = (in && p.b1) ? p.b1[c] : 0.0f;
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -185,10 +231,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
     } else {
         // ================= epilogue =================
+        const int ew = warp - 2;                         // 0 .. NE-1
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
-        const int et = (warp - 2) * 32 + lane;           // 0..127
-        uint8_t *stage_base = staging + (uint32_t)(warp - 2) * 2 * 4096;
-        constexpr int CH = (EPI == EPI_F32) ? 32 : 64;   // columns per 128-byte row segment
+        const int half = ew >> 2;                        // which of the NE/4 column shares
+        constexpr int NSH = GEMM_NE / 4;                 // warps sharing one lane quarter
+        const int et = ew * 32 + lane;                   // 0 .. 32*NE-1
+        uint8_t *stage_base = staging + (uint32_t)ew * 2 * GEMM_STAGE_BYTES;
+        const int npieces = (p.block_n + 31) / 32;       // 32-column pieces
         for (int j = 0; j < my_count; ++j) {
             int mt, nt;
             tile_mn(j, mt, nt);
@@ -196,74 +245,264 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const uint32_t acc_phase = (uint32_t)(j >> 1) & 1u;
             const int n0 = nt * p.block_n;
             float *sb = sbias + acc * 256;
-            for (int c = et; c < p.block_n; c += 128) sb[c] = (p.bias && n0 + c < p.N) ? p.bias[n0 + c] : 0.0f;
-            named_bar_sync(1, 128);
-            mbar_wait(&tfull[acc], acc_phase);
-            tc_fence_after();
+            if (et < p.block_n) sb[et] = (p.bias && n0 + et < p.N) ? p.bias[n0 + et] : 0.0f;
+            named_bar_sync(1, 32 * GEMM_NE);
             const uint32_t t_row = tmem_base + (uint32_t)(acc * p.block_n) + ((uint32_t)(q * 32) << 16);
             const int64_t grow0 = (int64_t)mt * GEMM_BM + q * 32;    // first global row of this warp
-            float best_v = -INFINITY;
-            int best_c = 0x7fffffff;
-            int buf = 0;
-            for (int c0 = 0; c0 < p.block_n; c0 += CH) {
-                const int ncol = min(CH, p.block_n - c0);            // multiple of 16
-                uint32_t r[CH];
+
+            if constexpr (EPI == EPI_RESID) {
+                // ---- fp32 residual update + LayerNorm(s); this warp owns rows [grow0, +32) x its column pieces ----
+                constexpr int MAXP = 3;                    // pieces per warp: block_n <= 192 -> 6 pieces / 2 warps
+                float v[MAXP][32];
+                // (1) pull the x pieces in through the staging tile (coalesced 128-byte row segments)
+                if (!p.init) {
 #pragma unroll
-                for (int pc = 0; pc < CH / 16; ++pc) {
-                    if (pc * 16 < ncol) {
-                        uint32_t t16[16];
-                        tmem_ld_32x32b_x16(t_row + (uint32_t)(c0 + pc * 16), t16);
+                    for (int k = 0; k < MAXP; ++k) {
+                        const int pi = half + NSH * k;
+                        if (pi < npieces) {
+                            const int c0 = pi * 32, ncol = min(32, p.block_n - c0);
+                            uint8_t *sbuf = stage_base + (k & 1) * GEMM_STAGE_BYTES;
+                            const int cj = lane & 7;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) r[pc * 16 + i] = t16[i];
-                    }
-                }
-                tmem_ld_wait();
-                if constexpr (EPI == EPI_ARGMAX) {
+                            for (int i = 0; i < 8; ++i) {
+                                const int row = i * 4 + (lane >> 3);
+                                const int64_t grow = grow0 + row;
+                                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (cj * 4 < ncol && grow < p.M) t = *reinterpret_cast<const float4 *>(p.x + grow * p.N + c0 + cj * 4);
+                                *reinterpret_cast<float4 *>(sbuf + sw128_offset(row, cj)) = t;
+                            }
+                            __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < CH; ++i) {
-                        if (i < ncol && n0 + c0 + i < p.N) {
-                            float v = __uint_as_float(r[i]) + sb[c0 + i];
-                            if (v > best_v) { best_v = v; best_c = n0 + c0 + i; }
+                            for (int jj = 0; jj < 8; ++jj) {
+                                const float4 t = *reinterpret_cast<const float4 *>(sbuf + sw128_offset(lane, jj));
+                                v[k][jj * 4 + 0] = t.x; v[k][jj * 4 + 1] = t.y; v[k][jj * 4 + 2] = t.z; v[k][jj * 4 + 3] = t.w;
+                            }
+                            __syncwarp();
                         }
                     }
-                } else {
-                    uint8_t *sbuf = stage_base + buf * 4096;
-                    if constexpr (EPI == EPI_F32) {
+                }
+                // (2) accumulator -> x_new = x + alpha * (acc + bias); partial LayerNorm sums
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_after();
+                float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) {
-                            if (jj * 4 < ncol) {
-                                float4 o;
-                                o.x = __uint_as_float(r[jj * 4 + 0]) + sb[c0 + jj * 4 + 0];
-                                o.y = __uint_as_float(r[jj * 4 + 1]) + sb[c0 + jj * 4 + 1];
-                                o.z = __uint_as_float(r[jj * 4 + 2]) + sb[c0 + jj * 4 + 2];
-                                o.w = __uint_as_float(r[jj * 4 + 3]) + sb[c0 + jj * 4 + 3];
-                                *reinterpret_cast<float4 *>(sbuf + sw128_offset(lane, jj)) = o;
+                for (int k = 0; k < MAXP; ++k) {
+                    const int pi = half + NSH * k;
+                    if (pi < npieces) {
+                        const int c0 = pi * 32, ncol = min(32, p.block_n - c0);
+                        uint32_t r[32];
+                        if (ncol == 32) {
+                            tmem_ld_32x32b_x32(t_row + (uint32_t)c0, r);
+                        } else {
+                            uint32_t t16[16];
+                            tmem_ld_32x32b_x16(t_row + (uint32_t)c0, t16);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) { r[i] = t16[i]; r[16 + i] = 0u; }
+                        }
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            const float a = __uint_as_float(r[e]) + sb[c0 + e];
+                            const float t = p.init ? a : fmaf(p.alpha, a, v[k][e]);
+                            const float tv = (e < ncol) ? t : 0.0f;
+                            v[k][e] = tv;
+                            s1 += tv;
+                            s2 = fmaf(tv, tv, s2);
+                        }
+                    }
+                }
+                // the accumulator stage can be reused by the MMA warp from here on
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+
+                const float inv_n = 1.0f / (float)p.N;
+                const int rix = q * 32 + lane;                               // row inside the tile
+                float mean, rstd;
+                auto exchange = [&](int round) {
+                    sred[(round * 2 + half) * 128 + rix] = make_float2(s1, s2);
+                    named_bar_sync(2 + q, 32 * NSH);
+                    const float2 o = sred[(round * 2 + (half ^ 1)) * 128 + rix];
+                    const float t1 = s1 + o.x, t2 = s2 + o.y;
+                    mean = t1 * inv_n;
+                    rstd = rsqrtf(fmaxf(t2 * inv_n - mean * mean, 0.0f) + 1e-5f);
+                };
+                if (p.gf) {   // block-final LayerNorm replaces the residual stream (encoder.py:99)
+                    exchange(0);
+                    s1 = 0.f; s2 = 0.f;
+#pragma unroll
+                    for (int k = 0; k < MAXP; ++k) {
+                        const int pi = half + NSH * k;
+                        if (pi < npieces) {
+                            const int c0 = pi * 32, ncol = min(32, p.block_n - c0);
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) {
+                                const float t = (e < ncol) ? (v[k][e] - mean) * rstd * sln[c0 + e] + sln[256 + c0 + e] : 0.0f;
+                                v[k][e] = t;
+                                s1 += t;
+                                s2 = fmaf(t, t, s2);
+                            }
+                        }
+                    }
+                }
+                // (3) write x_new (fp32, coalesced through staging)
+#pragma unroll
+                for (int k = 0; k < MAXP; ++k) {
+                    const int pi = half + NSH * k;
+                    if (pi < npieces) {
+                        const int c0 = pi * 32, ncol = min(32, p.block_n - c0);
+                        uint8_t *sbuf = stage_base + (k & 1) * GEMM_STAGE_BYTES;
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj)
+                            *reinterpret_cast<float4 *>(sbuf + sw128_offset(lane, jj)) =
+                                make_float4(v[k][jj * 4], v[k][jj * 4 + 1], v[k][jj * 4 + 2], v[k][jj * 4 + 3]);
+                        __syncwarp();
+                        const int cj = lane & 7;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int row = i * 4 + (lane >> 3);
+                            const int64_t grow = grow0 + row;
+                            if (cj * 4 < ncol && grow < p.M)
+                                *reinterpret_cast<float4 *>(p.x + grow * p.N + c0 + cj * 4) =
+                                    *reinterpret_cast<const float4 *>(sbuf + sw128_offset(row, cj));
+                        }
+                        __syncwarp();
+                    }
+                }
+                // (4) xn = bf16(LayerNorm_next(x_new)) (or bf16(x_new))
+                if (p.g1) exchange(1);
+#pragma unroll
+                for (int k = 0; k < MAXP; ++k) {
+                    const int pi = half + NSH * k;
+                    if (pi < npieces) {
+                        const int c0 = pi * 32, ncol = min(32, p.block_n - c0);
+                        uint8_t *sbuf = stage_base + (k & 1) * GEMM_STAGE_BYTES;
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int c = jj * 8 + 2 * e;
+                                float a = v[k][c], b = v[k][c + 1];
+                                if (p.g1) {
+                                    a = (a - mean) * rstd * sln[512 + c0 + c] + sln[768 + c0 + c];
+                                    b = (b - mean) * rstd * sln[512 + c0 + c + 1] + sln[768 + c0 + c + 1];
+                                }
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+                                pk[e] = *reinterpret_cast<uint32_t *>(&h2);
+                            }
+                            *reinterpret_cast<uint4 *>(sbuf + stg64_offset(lane, jj)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                        __syncwarp();
+                        const int cj = lane & 3;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int row = i * 8 + (lane >> 2);
+                            const int64_t grow = grow0 + row;
+                            if (cj * 8 < ncol && grow < p.M)
+                                *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + grow * p.ldc + c0 + cj * 8) =
+                                    *reinterpret_cast<const uint4 *>(sbuf + stg64_offset(row, cj));
+                        }
+                        __syncwarp();
+                    }
+                }
+            } else {
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_after();
+                float best_v = -INFINITY;
+                int best_c = 0x7fffffff;
+                int buf = 0;
+                int trow = 0;
+                if constexpr (EPI == EPI_BF16_POS) trow = (int)((grow0 + lane) % p.T);
+                for (int pi = half; pi < npieces; pi += NSH) {
+                    const int c0 = pi * 32;
+                    const int ncol = min(32, p.block_n - c0);            // 32 or 16
+                    uint32_t r[32];
+                    if (ncol == 32) {
+                        tmem_ld_32x32b_x32(t_row + (uint32_t)c0, r);
+                    } else {
+                        uint32_t t16[16];
+                        tmem_ld_32x32b_x16(t_row + (uint32_t)c0, t16);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { r[i] = t16[i]; r[16 + i] = 0u; }
+                    }
+                    tmem_ld_wait();
+                    float f[32];
+#pragma unroll
+                    for (int e4 = 0; e4 < 8; ++e4) {
+                        const float4 b4 = *reinterpret_cast<const float4 *>(sb + c0 + e4 * 4);
+                        f[e4 * 4 + 0] = __uint_as_float(r[e4 * 4 + 0]) + b4.x;
+                        f[e4 * 4 + 1] = __uint_as_float(r[e4 * 4 + 1]) + b4.y;
+                        f[e4 * 4 + 2] = __uint_as_float(r[e4 * 4 + 2]) + b4.z;
+                        f[e4 * 4 + 3] = __uint_as_float(r[e4 * 4 + 3]) + b4.w;
+                    }
+                    if constexpr (EPI == EPI_ARGMAX) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            if (i < ncol && n0 + c0 + i < p.N && f[i] > best_v) { best_v = f[i]; best_c = n0 + c0 + i; }
+                        }
+                    } else if constexpr (EPI == EPI_F32) {
+                        // two 16-column halves, each a [32 rows][64 B] staging tile
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            if (hh * 16 < ncol) {
+                                uint8_t *sbuf = stage_base + buf * GEMM_STAGE_BYTES;
+#pragma unroll
+                                for (int jj = 0; jj < 4; ++jj)
+                                    *reinterpret_cast<float4 *>(sbuf + stg64_offset(lane, jj)) =
+                                        make_float4(f[hh * 16 + jj * 4], f[hh * 16 + jj * 4 + 1], f[hh * 16 + jj * 4 + 2], f[hh * 16 + jj * 4 + 3]);
+                                __syncwarp();
+                                const int cj = lane & 3;
+                                const int gcol = n0 + c0 + hh * 16 + cj * 4;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const int row = i * 8 + (lane >> 2);
+                                    const int64_t grow = grow0 + row;
+                                    if (grow < p.M && gcol < p.N) {
+                                        const float4 t = *reinterpret_cast<const float4 *>(sbuf + stg64_offset(row, cj));
+                                        float *dst = reinterpret_cast<float *>(p.out) + grow * p.ldc + gcol;
+                                        if (gcol + 3 < p.N && (p.ldc & 3) == 0) {
+                                            *reinterpret_cast<float4 *>(dst) = t;
+                                        } else {
+                                            const float tv[4] = {t.x, t.y, t.z, t.w};
+                                            for (int e = 0; e < 4; ++e)
+                                                if (gcol + e < p.N) dst[e] = tv[e];
+                                        }
+                                    }
+                                }
+                                buf ^= 1;
                             }
                         }
                     } else {
-                        int trow = 0;
-                        if constexpr (EPI == EPI_BF16_POS) trow = (int)((grow0 + lane) % p.T);
+                        uint8_t *sbuf = stage_base + buf * GEMM_STAGE_BYTES;
+                        if constexpr (EPI == EPI_BF16_POS) {
+                            // rotation / fill of the positional columns; the (sin, cos) rows of this warp's 32 frames are
+                            // pulled in coalesced and transposed through the other staging buffer
+                            uint8_t *tbuf = stage_base + (buf ^ 1) * GEMM_STAGE_BYTES;
+                            __syncwarp();     // readers of the previous piece are done with that buffer
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            if (g * 16 < ncol) {
-                                float f[16];
-#pragma unroll
-                                for (int e = 0; e < 16; ++e) {
-                                    f[e] = __uint_as_float(r[g * 16 + e]) + sb[c0 + g * 16 + e];
-                                    if constexpr (EPI == EPI_BF16_SILU) f[e] = silu_fast(f[e]);
-                                }
-                                if constexpr (EPI == EPI_BF16_POS) {
+                            for (int g = 0; g < 2; ++g) {
+                                if (g * 16 < ncol) {
                                     const int meta = p.col_meta[(n0 + c0) / 16 + g];
                                     const int kind = meta >> 12;
-                                    if (kind != 0) {
-                                        const float4 *tp = reinterpret_cast<const float4 *>(p.trig + (size_t)trow * p.trig_ld + (meta & 0xFFF));
+                                    if (kind != 0) {   // warp-uniform
+                                        const int pbase = meta & 0xFFF;
+                                        // 32 rows x 8 pairs x 8 B = 32 x 64 B ; lane -> (row = i*8 + lane/4, 16-byte chunk lane%4)
+#pragma unroll
+                                        for (int i = 0; i < 4; ++i) {
+                                            const int row = i * 8 + (lane >> 2);
+                                            const int tr = (int)((grow0 + row) % p.T);
+                                            const float4 t = *reinterpret_cast<const float4 *>(p.trig + (size_t)tr * p.trig_ld + pbase + (lane & 3) * 2);
+                                            *reinterpret_cast<float4 *>(tbuf + stg64_offset(row, lane & 3)) = t;
+                                        }
+                                        __syncwarp();
 #pragma unroll
                                         for (int q4 = 0; q4 < 4; ++q4) {
-                                            const float4 sc = tp[q4];     // (sin, cos) of pairs 2*q4, 2*q4+1
+                                            const float4 sc = *reinterpret_cast<const float4 *>(tbuf + stg64_offset(lane, q4));
                                             const float sn[2] = {sc.x, sc.z}, cs[2] = {sc.y, sc.w};
 #pragma unroll
                                             for (int u = 0; u < 2; ++u) {
-                                                const int e0 = (q4 * 2 + u) * 2;
+                                                const int e0 = g * 16 + (q4 * 2 + u) * 2;
                                                 const float as = f[e0], ac = f[e0 + 1];
                                                 if (kind == 1) {
                                                     f[e0] = as * sn[u] + ac * cs[u];
@@ -274,63 +513,60 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                                 }
                                             }
                                         }
+                                        __syncwarp();
                                     }
-                                }
-#pragma unroll
-                                for (int hh = 0; hh < 2; ++hh) {
-                                    uint32_t pk[4];
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[hh * 8 + 2 * e], f[hh * 8 + 2 * e + 1]);
-                                        pk[e] = *reinterpret_cast<uint32_t *>(&h2);
-                                    }
-                                    *reinterpret_cast<uint4 *>(sbuf + sw128_offset(lane, g * 2 + hh)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                                 }
                             }
+                            (void)trow;
                         }
-                    }
-                    __syncwarp();
-                    // coalesced write-out: 8 lanes cover one 128-byte row segment, 4 rows per instruction
-                    constexpr int EPC = (EPI == EPI_F32) ? 4 : 8;     // elements per 16-byte piece
-                    const int cj = lane & 7;
-                    const int gcol = n0 + c0 + cj * EPC;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int row = i * 4 + (lane >> 3);
-                        const int64_t grow = grow0 + row;
-                        if (cj * EPC < ncol && grow < p.M && gcol < p.N) {
-                            uint4 v = *reinterpret_cast<const uint4 *>(sbuf + sw128_offset(row, cj));
-                            if constexpr (EPI == EPI_F32) {
-                                float *dst = reinterpret_cast<float *>(p.out) + grow * p.ldc + gcol;
-                                if (gcol + 3 < p.N && (p.ldc & 3) == 0) {
-                                    *reinterpret_cast<uint4 *>(dst) = v;
-                                } else {
-                                    const float *vf = reinterpret_cast<const float *>(&v);
-                                    for (int e = 0; e < 4; ++e)
-                                        if (gcol + e < p.N) dst[e] = vf[e];
+                        for (int jj = 0; jj < 4; ++jj) {
+                            if (jj * 8 < ncol) {
+                                uint32_t pk[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float a = f[jj * 8 + 2 * e], b = f[jj * 8 + 2 * e + 1];
+                                    if constexpr (EPI == EPI_BF16_SILU) {
+                                        pk[e] = silu2_bf16(a, b);
+                                    } else {
+                                        __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+                                        pk[e] = *reinterpret_cast<uint32_t *>(&h2);
+                                    }
                                 }
-                            } else {
+                                *reinterpret_cast<uint4 *>(sbuf + stg64_offset(lane, jj)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            }
+                        }
+                        __syncwarp();
+                        // coalesced write-out: 4 lanes cover one 64-byte row segment, 8 rows per instruction
+                        const int cj = lane & 3;
+                        const int gcol = n0 + c0 + cj * 8;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int row = i * 8 + (lane >> 2);
+                            const int64_t grow = grow0 + row;
+                            if (cj * 8 < ncol && grow < p.M && gcol < p.N) {
+                                const uint4 t = *reinterpret_cast<const uint4 *>(sbuf + stg64_offset(row, cj));
                                 __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.out) + grow * p.ldc + gcol;
                                 if (gcol + 7 < p.N && (p.ldc & 7) == 0) {
-                                    *reinterpret_cast<uint4 *>(dst) = v;
+                                    *reinterpret_cast<uint4 *>(dst) = t;
                                 } else {
-                                    const __nv_bfloat16 *vh = reinterpret_cast<const __nv_bfloat16 *>(&v);
+                                    const __nv_bfloat16 *vh = reinterpret_cast<const __nv_bfloat16 *>(&t);
                                     for (int e = 0; e < 8; ++e)
                                         if (gcol + e < p.N) dst[e] = vh[e];
                                 }
                             }
                         }
+                        buf ^= 1;     // the other buffer is free: its readers finished before the last __syncwarp
                     }
-                    buf ^= 1;     // the other buffer is free: its readers finished before the last __syncwarp
                 }
+                if constexpr (EPI == EPI_ARGMAX) {
+                    const int64_t grow = grow0 + lane;
+                    if (grow < p.M && best_c != 0x7fffffff) atomicMax(p.best + grow, pack_best(best_v, best_c));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
             }
-            if constexpr (EPI == EPI_ARGMAX) {
-                const int64_t grow = grow0 + lane;
-                if (grow < p.M && best_c != 0x7fffffff) atomicMax(p.best + grow, pack_best(best_v, best_c));
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
         }
     }
     tc_fence_before();

@@ -40,6 +40,19 @@ def test_tcgen05_gemm_selftest(epi, M, N, K, bn, cuda_device):
     assert 0.0 <= err.value < tol, f'max err {err.value}'
 
 
+@pytest.mark.parametrize('M,N,K,flags', [(1000, 144, 144, 4), (4096, 144, 576, 4), (777, 144, 576, 6), (5000, 144, 576, 2),
+                                          (3000, 144, 768, 5), (300, 144, 144, 0), (2000, 80, 64, 6), (2000, 192, 144, 4),
+                                          (40000, 144, 576, 6)])
+def test_residual_layernorm_epilogue_selftest(M, N, K, flags, cuda_device):
+    from conformer_ocr_b200 import _lib
+    lib = _lib.load()
+    err = ctypes.c_double(-1.0)
+    rc = lib.cocr_selftest(0, 20, M, N, K + 100000 * flags, ctypes.byref(err))
+    _lib.raise_for_status(rc, None)
+    # xn is bf16 (2^-8 rounding); the fp32 stream error is weighted 8x inside the self test
+    assert 0.0 <= err.value < 6e-3, f'max err {err.value}'
+
+
 def build_net(hp, C, w, device, **kw):
     from conformer_ocr_b200 import PytorchRecognitionModel
     net = PytorchRecognitionModel(num_classes=C, codec=None, precision='bf16', **hp, **DROP, **kw)
