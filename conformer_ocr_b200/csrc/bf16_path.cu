@@ -23,7 +23,7 @@ struct Bf16State {
     bf16 *w_qkvx = nullptr;       // (L, nx, d)
     float *b_qkvx = nullptr;      // (L, nx)
     int16_t *meta = nullptr;      // (nx / 16)
-    float2 *trig = nullptr;       // (T, d/2) (sin, cos)(t * omega_m)
+    float *omega = nullptr;       // (d/2) angular frequencies omega_m (embedding.py:42-44)
     bf16 *etab = nullptr;         // (T, d - 16) (cos, sin) interleaved
     int tab_T = 0;
 };
@@ -46,21 +46,22 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-// 2-D row-major bf16 matrix (rows x cols, leading dimension ld elements) -> SWIZZLE_128B box (64 cols x box_rows)
+// 2-D row-major bf16 matrix (rows x cols, leading dimension ld elements) -> box (box_cols x box_rows).
+// Operand tiles use 64-column SWIZZLE_128B boxes; epilogue stores use 32-column SWIZZLE_64B boxes.
 static int make_tmap_bf16(cocr_handle *h, CUtensorMap *m, const void *base, int64_t rows, int64_t cols, int64_t ld,
-                          int box_rows) {
+                          int box_rows, int box_cols = 64, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return set_error(h, COCR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
-        return set_error(h, COCR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box_rows=%d", (int)r,
-                         (long long)rows, (long long)cols, (long long)ld, box_rows);
+        return set_error(h, COCR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box=%dx%d", (int)r,
+                         (long long)rows, (long long)cols, (long long)ld, box_rows, box_cols);
     return COCR_OK;
 }
 
@@ -69,13 +70,13 @@ static int make_tmap_bf16(cocr_handle *h, CUtensorMap *m, const void *base, int6
 // ------------------------------------------------------------------------------------------
 static int pick_block_n(int N) {
     if (N <= 256) return (N + 15) / 16 * 16;
-    // largest multiple of 16 that divides N exactly and is <= 256, else 256 with a ragged last tile
-    for (int bn = 256; bn >= 64; bn -= 16)
+    // several N tiles: the epilogue stores 32-column pieces, so tiles are multiples of 32; prefer an exact divisor
+    for (int bn = 256; bn >= 64; bn -= 32)
         if (N % bn == 0) return bn;
     return 256;
 }
 
-struct PosArgs { const int16_t *meta; const float2 *trig; int trig_ld, T; };
+struct PosArgs { const int16_t *meta; const float *omega; int n_omega, T; };
 struct ResidArgs { float *x; float alpha; int init; const float *gf, *bf, *g1, *b1; };
 
 int launch_gemm_tc(cocr_handle *h, int epi, const bf16 *A, int lda, const bf16 *W, int ldw, const float *bias, void *out,
@@ -93,18 +94,19 @@ int launch_gemm_tc(cocr_handle *h, int epi, const bf16 *A, int lda, const bf16 *
     p.nkc = (K + GEMM_KC - 1) / GEMM_KC;
     p.last_ksteps = (K - (p.nkc - 1) * GEMM_KC) / 16;
     p.bias = bias; p.out = out; p.ldc = ldc; p.best = best;
-    p.col_meta = pos ? pos->meta : nullptr; p.trig = pos ? pos->trig : nullptr;
-    p.trig_ld = pos ? pos->trig_ld : 0; p.T = pos ? pos->T : 1;
-    if (epi == EPI_BF16_POS && (!pos || p.block_n % 16 != 0)) return set_error(h, COCR_ERR_BAD_ARG, "POS epilogue needs position tables");
+    p.col_meta = pos ? pos->meta : nullptr; p.omega = pos ? pos->omega : nullptr;
+    p.n_omega = pos ? pos->n_omega : 0; p.T = pos ? pos->T : 1;
+    if (epi == EPI_BF16_POS && (!pos || p.n_omega > 256 || N / 16 > 1536)) return set_error(h, COCR_ERR_BAD_ARG, "POS epilogue needs position tables");
+    if (p.n_tiles > 1 && p.block_n % 32 != 0) return set_error(h, COCR_ERR_BAD_ARG, "block_n %d must be a multiple of 32 with several N tiles", p.block_n);
     p.x = res ? res->x : nullptr; p.alpha = res ? res->alpha : 1.f; p.init = res ? res->init : 0;
     p.gf = res ? res->gf : nullptr; p.bf = res ? res->bf : nullptr; p.g1 = res ? res->g1 : nullptr; p.b1 = res ? res->b1 : nullptr;
-    if (epi == EPI_RESID && (!res || p.n_tiles != 1 || p.block_n != N || N > 192))
-        return set_error(h, COCR_ERR_BAD_ARG, "residual epilogue needs a single N tile of at most 192 columns (N=%d)", N);
+    if (epi == EPI_RESID && (!res || p.n_tiles != 1 || p.block_n != N || N != 8 * GEMM_RESID_NG || ldc % 4 != 0))
+        return set_error(h, COCR_ERR_BAD_ARG, "residual epilogue is built for N = %d (got N=%d)", 8 * GEMM_RESID_NG, N);
     int tm = 32;
     while (tm < 2 * p.block_n) tm <<= 1;
     p.tmem_cols = tm;
     const uint32_t b_chunk = gemm_b_chunk_bytes(p.block_n);
-    const uint32_t fixed = GEMM_FIXED_SMEM;        // staging + bias / LayerNorm vectors + barriers + alignment slack
+    const uint32_t fixed = gemm_fixed_smem(epi);   // staging + bias / LayerNorm vectors + barriers + alignment slack
     const uint32_t budget = (uint32_t)h->bf->smem_optin;
     // resident weights when the whole K extent of one N-slice fits next to >= 4 A slots
     const uint32_t bres = (uint32_t)p.nkc * b_chunk;
@@ -117,9 +119,15 @@ int launch_gemm_tc(cocr_handle *h, int epi, const bf16 *A, int lda, const bf16 *
     p.stages = stages;
     const uint32_t smem = fixed + (p.resident ? bres : 0u) + (uint32_t)stages * slot;
 
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmC;
     COCR_TRY(make_tmap_bf16(h, &tmA, A, M, K, lda, GEMM_BM));
     COCR_TRY(make_tmap_bf16(h, &tmB, W, N, K, ldw, p.block_n));
+    if (epi == EPI_BF16 || epi == EPI_BF16_SILU || epi == EPI_BF16_POS) {
+        if (ldc % 8 != 0) return set_error(h, COCR_ERR_UNSUPPORTED, "bf16 GEMM output rows must be 16-byte aligned (ldc=%d)", ldc);
+        COCR_TRY(make_tmap_bf16(h, &tmC, out, M, N, ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+    } else {
+        tmC = tmA;   // unused
+    }
 
     int grid;
     if (p.resident) {
@@ -141,7 +149,7 @@ int launch_gemm_tc(cocr_handle *h, int epi, const bf16 *A, int lda, const bf16 *
             COCR_CUDA(h, cudaFuncSetAttribute(k_gemm_tc<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget)); \
             attr_smem = (int)budget;                                                                                   \
         }                                                                                                              \
-        k_gemm_tc<E><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, p);                                                   \
+        k_gemm_tc<E><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, p);                                                  \
         break;                                                                                                         \
     }
     switch (epi) {
@@ -407,31 +415,28 @@ static int pack_attention(cocr_handle *h) {
     return COCR_OK;
 }
 
-// (sin, cos)(t w_m) and the shared key-side table E(t) for a batch whose lines have T frames (embedding.py:42-47 angles)
+// omega_m and the shared key-side table E(t) for a batch whose lines have T frames (embedding.py:42-47 angles)
 static int ensure_tables(cocr_handle *h, int T, cudaStream_t st) {
     Bf16State *bs = h->bf;
     if (bs->tab_T == T) return COCR_OK;
     const int d = h->dm.d, np = d / 2, ecols = d - 16;
-    if (bs->trig) { COCR_CUDA(h, cudaDeviceSynchronize()); cudaFree(bs->trig); cudaFree(bs->etab); bs->trig = nullptr; bs->etab = nullptr; }
-    std::vector<float> trig((size_t)T * np * 2);
+    if (bs->etab) { COCR_CUDA(h, cudaDeviceSynchronize()); cudaFree(bs->omega); cudaFree(bs->etab); bs->omega = nullptr; bs->etab = nullptr; }
+    std::vector<float> om(np);
     std::vector<uint16_t> et((size_t)T * ecols);
     const float neg = (float)(-(log(10000.0) / (double)d));
+    for (int m = 0; m < np; ++m) om[m] = expf((float)(2 * m) * neg);
     for (int t = 0; t < T; ++t)
         for (int m = 0; m < np; ++m) {
-            const float div = expf((float)(2 * m) * neg);
-            const float arg = (float)t * div;
-            const float sn = sinf(arg), cs = cosf(arg);
-            trig[((size_t)t * np + m) * 2] = sn;
-            trig[((size_t)t * np + m) * 2 + 1] = cs;
+            const float arg = (float)t * om[m];
             if (2 * m + 1 < ecols) {
-                et[(size_t)t * ecols + 2 * m] = f2bf(cs);
-                et[(size_t)t * ecols + 2 * m + 1] = f2bf(sn);
+                et[(size_t)t * ecols + 2 * m] = f2bf(cosf(arg));
+                et[(size_t)t * ecols + 2 * m + 1] = f2bf(sinf(arg));
             }
         }
     void *p = nullptr;
-    COCR_CUDA(h, cudaMalloc(&p, trig.size() * 4)); bs->trig = (float2 *)p;
+    COCR_CUDA(h, cudaMalloc(&p, om.size() * 4)); bs->omega = (float *)p;
     COCR_CUDA(h, cudaMalloc(&p, et.size() * 2)); bs->etab = (bf16 *)p;
-    COCR_CUDA(h, cudaMemcpyAsync(bs->trig, trig.data(), trig.size() * 4, cudaMemcpyHostToDevice, st));
+    COCR_CUDA(h, cudaMemcpyAsync(bs->omega, om.data(), om.size() * 4, cudaMemcpyHostToDevice, st));
     COCR_CUDA(h, cudaMemcpyAsync(bs->etab, et.data(), et.size() * 2, cudaMemcpyHostToDevice, st));
     COCR_CUDA(h, cudaStreamSynchronize(st));
     bs->tab_T = T;
@@ -490,7 +495,7 @@ void bf16_destroy(cocr_handle *h) {
     if (bs->w_qkvx) cudaFree(bs->w_qkvx);
     if (bs->b_qkvx) cudaFree(bs->b_qkvx);
     if (bs->meta) cudaFree(bs->meta);
-    if (bs->trig) cudaFree(bs->trig);
+    if (bs->omega) cudaFree(bs->omega);
     if (bs->etab) cudaFree(bs->etab);
     delete h->bf;
     h->bf = nullptr;
@@ -531,9 +536,9 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
     } else if (rc_fe != COCR_OK) {
         return rc_fe;
     }
-    // Residual-stream GEMMs: with encoder_dim <= 192 the update x += alpha*(..) and the LayerNorm feeding the next module
+    // Residual-stream GEMMs: with encoder_dim 144 the update x += alpha*(..) and the LayerNorm feeding the next module
     // run in the GEMM epilogue (EPI_RESID); otherwise GEMM -> bf16 y -> k_resid_ln.
-    const bool fused = (d <= 192);
+    const bool fused = (d == 8 * GEMM_RESID_NG) && !getenv("COCR_SPLIT_RESIDUAL");
     auto resid_gemm = [&](const bf16 *A, int K, const float *Wf, const float *bias, float alpha, int init, const float *gf,
                           const float *bfin, const float *g1, const float *b1, const char *tag) -> int {
         if (fused) {
@@ -553,7 +558,7 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
         // MHSA (attention.py:72-151)
         if (tc_attn) {
             Bf16State *bs = h->bf;
-            PosArgs pa = {bs->meta, bs->trig, d / 2, p.T};
+            PosArgs pa = {bs->meta, bs->omega, d / 2, p.T};
             COCR_TRY(launch_gemm_tc(h, EPI_BF16_POS, xn, d, bs->w_qkvx + (size_t)l * bs->nx * d, d, bs->b_qkvx + (size_t)l * bs->nx, hb,
                                     bs->nx, nullptr, M, bs->nx, d, st, 0, &pa, "gemm_qkvx_pos"));
             COCR_TRY(launch_attn_tc(h, hb, lens_dev, g, B, p.T, st));

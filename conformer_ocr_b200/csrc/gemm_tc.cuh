@@ -4,17 +4,22 @@
 //   * W (weights, row-major [N,K] bf16, i.e. K-major "B" operand) is either RESIDENT in shared memory for
 //     the whole kernel (one N-slice per CTA; all K=144 layers) or streamed through the same ring (K=576/768);
 //   * one elected thread issues tcgen05.mma (UMMA 128 x block_n x 16) into a double-buffered TMEM accumulator;
-//   * NE (8) epilogue warps - two per TMEM lane quarter, splitting the columns in 32-wide pieces - read TMEM with
-//     tcgen05.ld (thread = row), apply the fused epilogue, transpose through a per-warp swizzled staging tile
-//     and move 64/128-byte row segments with coalesced 16-byte accesses.
+//   * 8 epilogue warps (two per TMEM lane quarter) drain the accumulator.
 //
-// Epilogues: bias (+SiLU) -> bf16; bias -> fp32; bias -> running arg-max (CTC decode, logits never stored);
-// bias + rotation by the frame angle (attention operands, see attn_tc.cuh); and the residual epilogue
-//   x <- x + alpha*(acc + bias) [-> LayerNorm_final(x)] ; xn = bf16(LayerNorm_next(x))
-// which keeps the fp32 residual stream and both LayerNorms of a conformer block inside the GEMM
-// (modules.py:31-32, encoder.py:99, feed_forward.py:46, attention.py:148, convolution.py:136).
+// Epilogues
+//   bf16 outputs (bias | bias+SiLU | bias+position handling): thread = row (tcgen05.ld 32x32b), the next 32-column
+//     piece is loaded from TMEM while the current one is converted; each piece goes through a per-warp ring of
+//     SWIZZLE_64B staging tiles and leaves with one asynchronous TMA store (cp.async.bulk.tensor), so no thread
+//     ever waits on a global store and rows / columns outside the matrix are clipped by the tensor map;
+//   residual (EPI_RESID):  x <- x + alpha*(acc + bias) [-> LayerNorm_final(x)] ; xn = bf16(LayerNorm_next(x))
+//     keeps the fp32 residual stream and both LayerNorms of a conformer block inside the GEMM
+//     (modules.py:31-32, encoder.py:99, feed_forward.py:46, attention.py:148, convolution.py:136).  It reads TMEM in
+//     the 16x256b fragment layout (a quad of lanes owns 8 consecutive columns of a row), so x is read and written
+//     straight from registers in full 32-byte sectors, LayerNorm statistics need two quad shuffles, and no shared
+//     memory or barrier is involved; the two warps of a lane quarter take alternate tiles;
+//   fp32 logits and the fused arg-max (CTC decode; logits never stored) keep a staged scalar path (cold).
 //
-// Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..2+NE-1 = epilogue.
+// Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
 #pragma once
 
 #include <cuda_fp16.h>
@@ -31,12 +36,12 @@ enum GemmEpi : int {
     EPI_BF16_POS = 4,    // out bf16 = acc + bias, with per-16-column-group position handling (attention operands):
                          //   kind 0 plain; kind 1 rotate pairs by the row's angle (relative-position term);
                          //   kind 2 fill with (cos, sin) of the row's angle
-    EPI_RESID = 5,       // fp32 residual stream update + LayerNorm(s); requires N == block_n (one N tile)
+    EPI_RESID = 5,       // fp32 residual stream update + LayerNorm(s); N == block_n == 8 * GEMM_RESID_NG (one N tile)
 };
 
 struct GemmArgs {
     int M, N, K;             // K % 16 == 0
-    int block_n;             // UMMA N: multiple of 16, 16..256
+    int block_n;             // UMMA N: multiple of 16, 16..256 (multiple of 32 when there is more than one N tile)
     int n_tiles, m_tiles;
     int nkc;                 // ceil(K / 64) k-chunks
     int last_ksteps;         // k-steps (of 16) in the last chunk
@@ -44,13 +49,13 @@ struct GemmArgs {
     int stages;              // ring slots
     int tmem_cols;           // power of two >= 2*block_n
     const float *bias;       // (N) or null
-    void *out;               // bf16 / fp32 (M, ldc) row-major; EPI_RESID: bf16 xn (M, ldc)
+    void *out;               // fp32 (M, ldc) for EPI_F32; EPI_RESID: bf16 xn (M, ldc); bf16 epilogues write through tmC
     int ldc;
     unsigned long long *best;   // EPI_ARGMAX: (M) packed keys, zero-initialised by the caller
     // EPI_BF16_POS
     const int16_t *col_meta;    // (N/16): kind << 12 | first pair index
-    const float2 *trig;         // (T, trig_ld): (sin, cos)(t * omega_m)
-    int trig_ld, T;             // row r of the GEMM is frame t = r % T of its line
+    const float *omega;         // (n_omega) angular frequencies: the angle of pair m at frame t is t * omega[m]
+    int n_omega, T;             // row r of the GEMM is frame t = r % T of its line
     // EPI_RESID
     float *x;                   // (M, N) fp32 residual stream, updated in place
     float alpha;                // module factor (0.5 for the half-step FFNs)
@@ -63,11 +68,16 @@ constexpr int GEMM_NE = 8;                          // epilogue warps
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_NE;
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_KC = 64;                       // k-chunk (elements) = one 128-byte swizzle span of bf16
+constexpr int GEMM_RESID_NG = 18;                 // EPI_RESID: 8-column groups per row (encoder_dim 144)
 constexpr uint32_t GEMM_A_CHUNK = GEMM_BM * 128;  // bytes of one A k-chunk tile
-constexpr uint32_t GEMM_STAGE_BYTES = 4096;       // per-warp staging buffer (32 rows x 128 B), two per warp
-constexpr uint32_t GEMM_FIXED_SMEM = GEMM_NE * 2 * GEMM_STAGE_BYTES + 7 * 256 * 4 + 2 * 128 * 2 * 4 * 2 + 512 + 1024;
+constexpr uint32_t GEMM_STAGE_BYTES = 2048;       // one staging tile: 32 rows x 64 B (32 bf16 / 16 fp32 columns)
+constexpr int GEMM_NSTG = 4;                      // staging tiles per epilogue warp
+constexpr uint32_t GEMM_MISC_SMEM = 2 * 256 * 4 + 4 * 256 * 4 + 512 + 1024;   // bias, LayerNorm / position tables, barriers, slack
 
 __host__ __device__ inline uint32_t gemm_b_chunk_bytes(int block_n) { return (uint32_t)block_n * 128u; }
+__host__ __device__ inline uint32_t gemm_fixed_smem(int epi) {
+    return GEMM_MISC_SMEM + (epi == EPI_RESID ? 0u : (uint32_t)GEMM_NE * GEMM_NSTG * GEMM_STAGE_BYTES);
+}
 
 // orderable key: larger float -> larger key; among equal floats the LOWER column index wins
 __device__ __forceinline__ unsigned long long pack_best(float v, int col) {
@@ -97,37 +107,46 @@ __device__ __forceinline__ uint32_t silu2_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&o);
 }
 
-// byte offset of (row, 16-byte chunk 0..3) in a [32 rows][64 B] staging tile, conflict-free for row-wise 16-byte
-// writes (thread = row) and for 4-lanes-per-row reads
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h2);
+}
+
+// byte offset of (row, 16-byte chunk 0..3) in a [32 rows][64 B] tile in the SWIZZLE_64B pattern (address bits 4-5 xor
+// bits 7-8): conflict-free for row-wise 16-byte writes (thread = row), and what a SWIZZLE_64B tensor map expects
 __device__ __forceinline__ uint32_t stg64_offset(uint32_t row, uint32_t chunk) {
     return row * 64u + (((chunk ^ (row >> 1)) & 3u) << 4);
 }
 
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+          const __grid_constant__ CUtensorMap tmC, const GemmArgs p) {
     using namespace tc;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for SWIZZLE_128B tiles
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
+    constexpr bool kTmaStore = (EPI == EPI_BF16 || EPI == EPI_BF16_SILU || EPI == EPI_BF16_POS);
+    constexpr uint32_t kStagingBytes = (EPI == EPI_RESID) ? 0u : (uint32_t)GEMM_NE * GEMM_NSTG * GEMM_STAGE_BYTES;
     const uint32_t b_chunk = gemm_b_chunk_bytes(p.block_n);
     const uint32_t bres_bytes = p.resident ? (uint32_t)p.nkc * b_chunk : 0u;
     const uint32_t slot_bytes = GEMM_A_CHUNK + (p.resident ? 0u : b_chunk);
     uint8_t *bres = smem;
     uint8_t *ring = smem + bres_bytes;
-    uint8_t *staging = ring + (uint32_t)p.stages * slot_bytes;                        // NE warps x 2 x 4 KB
-    float *sbias = reinterpret_cast<float *>(staging + GEMM_NE * 2 * GEMM_STAGE_BYTES); // [2][256] bias (per acc stage)
-    float *sln = sbias + 512;                                                           // [4][256] gf, bf, g1, b1
-    float *spad = sln + 1024;                                                           // [256] spare
-    float2 *sred = reinterpret_cast<float2 *>(spad + 256);                              // [2 rounds][2 halves][128] partial sums
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sred + 2 * 2 * 128);
+    uint8_t *staging = ring + (uint32_t)p.stages * slot_bytes;                        // NE warps x NSTG x 2 KB
+    float *sbias = reinterpret_cast<float *>(staging + kStagingBytes);                  // [2][256] bias (per acc stage)
+    float *sln = sbias + 512;                                                           // [4][256] gf, bf, g1, b1  | position tables
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sln + 1024);
     uint64_t *full = bars;                       // [stages]
     uint64_t *empty = bars + p.stages;           // [stages]
     uint64_t *bfull = bars + 2 * p.stages;       // [1]
     uint64_t *tfull = bfull + 1;                 // [2]
     uint64_t *tempty = tfull + 2;                // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    // EPI_BF16_POS tables (alias of sln)
+    float *somega = sln;                                               // [<= 256]
+    int16_t *smeta = reinterpret_cast<int16_t *>(sln + 256);           // [<= 1536]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -151,14 +170,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (p.resident) { mt = t; nt = n_fixed; }
         else { mt = t / p.n_tiles; nt = t % p.n_tiles; }
     };
+    // one N offset for the whole kernel: the bias slice is staged once, before the roles start
+    const bool bias_once = p.resident || p.n_tiles == 1;
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
+        if constexpr (kTmaStore) prefetch_tmap(&tmC);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(bfull, 1);
         mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
-        mbar_init(&tempty[0], GEMM_NE); mbar_init(&tempty[1], GEMM_NE);
+        constexpr uint32_t drainers = (EPI == EPI_RESID) ? GEMM_NE / 2 : GEMM_NE;   // warps draining one accumulator stage
+        mbar_init(&tempty[0], drainers); mbar_init(&tempty[1], drainers);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -170,6 +193,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             sln[256 + c] = (in && p.bf) ? p.bf[c] : 0.0f;
             sln[512 + c] = (in && p.g1) ? p.g1[c] : 1.0f;
             sln[768 + c] = (in && p.b1) ? p.b1[c] : 0.0f;
+        }
+    }
+    if constexpr (EPI == EPI_BF16_POS) {
+        for (int c = threadIdx.x; c < p.n_omega; c += GEMM_THREADS) somega[c] = p.omega[c];
+        for (int c = threadIdx.x; c < p.N / 16; c += GEMM_THREADS) smeta[c] = p.col_meta[c];
+    }
+    if (bias_once) {
+        const int n0 = n_fixed * p.block_n;
+        for (int c = threadIdx.x; c < 256; c += GEMM_THREADS) {
+            const float b = (p.bias && c < p.block_n && n0 + c < p.N) ? p.bias[n0 + c] : 0.0f;
+            sbias[c] = b;
+            sbias[256 + c] = b;
         }
     }
     tc_fence_before();
@@ -233,11 +268,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // ================= epilogue =================
         const int ew = warp - 2;                         // 0 .. NE-1
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
-        const int half = ew >> 2;                        // which of the NE/4 column shares
-        constexpr int NSH = GEMM_NE / 4;                 // warps sharing one lane quarter
+        const int half = ew >> 2;                        // which of the two warps of the quarter
+        constexpr int NSH = GEMM_NE / 4;                 // warps sharing one lane quarter (2)
         const int et = ew * 32 + lane;                   // 0 .. 32*NE-1
-        uint8_t *stage_base = staging + (uint32_t)ew * 2 * GEMM_STAGE_BYTES;
+        uint8_t *stage_base = staging + (uint32_t)ew * GEMM_NSTG * GEMM_STAGE_BYTES;
         const int npieces = (p.block_n + 31) / 32;       // 32-column pieces
+        uint32_t bufctr = 0;                             // staging ring position (TMA-store epilogues)
         for (int j = 0; j < my_count; ++j) {
             int mt, nt;
             tile_mn(j, mt, nt);
@@ -245,188 +281,251 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const uint32_t acc_phase = (uint32_t)(j >> 1) & 1u;
             const int n0 = nt * p.block_n;
             float *sb = sbias + acc * 256;
-            if (et < p.block_n) sb[et] = (p.bias && n0 + et < p.N) ? p.bias[n0 + et] : 0.0f;
-            named_bar_sync(1, 32 * GEMM_NE);
-            const uint32_t t_row = tmem_base + (uint32_t)(acc * p.block_n) + ((uint32_t)(q * 32) << 16);
-            const int64_t grow0 = (int64_t)mt * GEMM_BM + q * 32;    // first global row of this warp
-
-            if constexpr (EPI == EPI_RESID) {
-                // ---- fp32 residual update + LayerNorm(s); this warp owns rows [grow0, +32) x its column pieces ----
-                constexpr int MAXP = 3;                    // pieces per warp: block_n <= 192 -> 6 pieces / 2 warps
-                float v[MAXP][32];
-                // (1) pull the x pieces in through the staging tile (coalesced 128-byte row segments)
-                if (!p.init) {
-#pragma unroll
-                    for (int k = 0; k < MAXP; ++k) {
-                        const int pi = half + NSH * k;
-                        if (pi < npieces) {
-                            const int c0 = pi * 32, ncol = min(32, p.block_n - c0);
-                            uint8_t *sbuf = stage_base + (k & 1) * GEMM_STAGE_BYTES;
-                            const int cj = lane & 7;
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int row = i * 4 + (lane >> 3);
-                                const int64_t grow = grow0 + row;
-                                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (cj * 4 < ncol && grow < p.M) t = *reinterpret_cast<const float4 *>(p.x + grow * p.N + c0 + cj * 4);
-                                *reinterpret_cast<float4 *>(sbuf + sw128_offset(row, cj)) = t;
-                            }
-                            __syncwarp();
-#pragma unroll
-                            for (int jj = 0; jj < 8; ++jj) {
-                                const float4 t = *reinterpret_cast<const float4 *>(sbuf + sw128_offset(lane, jj));
-                                v[k][jj * 4 + 0] = t.x; v[k][jj * 4 + 1] = t.y; v[k][jj * 4 + 2] = t.z; v[k][jj * 4 + 3] = t.w;
-                            }
-                            __syncwarp();
-                        }
-                    }
-                }
-                // (2) accumulator -> x_new = x + alpha * (acc + bias); partial LayerNorm sums
-                mbar_wait(&tfull[acc], acc_phase);
-                tc_fence_after();
-                float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                for (int k = 0; k < MAXP; ++k) {
-                    const int pi = half + NSH * k;
-                    if (pi < npieces) {
-                        const int c0 = pi * 32, ncol = min(32, p.block_n - c0);
-                        uint32_t r[32];
-                        if (ncol == 32) {
-                            tmem_ld_32x32b_x32(t_row + (uint32_t)c0, r);
-                        } else {
-                            uint32_t t16[16];
-                            tmem_ld_32x32b_x16(t_row + (uint32_t)c0, t16);
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) { r[i] = t16[i]; r[16 + i] = 0u; }
-                        }
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            const float a = __uint_as_float(r[e]) + sb[c0 + e];
-                            const float t = p.init ? a : fmaf(p.alpha, a, v[k][e]);
-                            const float tv = (e < ncol) ? t : 0.0f;
-                            v[k][e] = tv;
-                            s1 += tv;
-                            s2 = fmaf(tv, tv, s2);
-                        }
-                    }
-                }
-                // the accumulator stage can be reused by the MMA warp from here on
+            if (!bias_once) {
+                if (et < p.block_n) sb[et] = (p.bias && n0 + et < p.N) ? p.bias[n0 + et] : 0.0f;
+                named_bar_sync(1, 32 * GEMM_NE);
+            }
+            const uint32_t t_acc = tmem_base + (uint32_t)(acc * p.block_n);
+            const uint32_t t_row = t_acc + ((uint32_t)(q * 32) << 16);
+            const int grow0 = mt * GEMM_BM + q * 32;                 // first global row of this warp
+            auto release_acc = [&]() {                               // this warp is done reading the accumulator stage
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[acc]);
+            };
 
-                const float inv_n = 1.0f / (float)p.N;
-                const int rix = q * 32 + lane;                               // row inside the tile
-                float mean, rstd;
-                auto exchange = [&](int round) {
-                    sred[(round * 2 + half) * 128 + rix] = make_float2(s1, s2);
-                    named_bar_sync(2 + q, 32 * NSH);
-                    const float2 o = sred[(round * 2 + (half ^ 1)) * 128 + rix];
-                    const float t1 = s1 + o.x, t2 = s2 + o.y;
-                    mean = t1 * inv_n;
-                    rstd = rsqrtf(fmaxf(t2 * inv_n - mean * mean, 0.0f) + 1e-5f);
+            if constexpr (EPI == EPI_RESID) {
+                // ---- fp32 residual update + LayerNorm(s), fragment layout, alternate tiles per warp ----
+                if ((j & 1) != half) continue;
+                constexpr int NG = GEMM_RESID_NG;
+                const int r_in = lane >> 2, qd = lane & 3;
+                const float inv_n = 1.0f / (float)(8 * NG);
+#pragma unroll 1
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int64_t rowA = (int64_t)grow0 + hh * 16 + r_in, rowB = rowA + 8;
+                    const bool okA = rowA < p.M, okB = rowB < p.M;
+                    float2 va[NG], vb[NG];
+                    float *xa = p.x + rowA * (8 * NG) + 2 * qd, *xb = p.x + rowB * (8 * NG) + 2 * qd;
+                    if (!p.init) {
+#pragma unroll
+                        for (int g = 0; g < NG; ++g) {
+                            va[g] = okA ? *reinterpret_cast<const float2 *>(xa + 8 * g) : make_float2(0.f, 0.f);
+                            vb[g] = okB ? *reinterpret_cast<const float2 *>(xb + 8 * g) : make_float2(0.f, 0.f);
+                        }
+                    }
+                    if (hh == 0) {
+                        mbar_wait(&tfull[acc], acc_phase);
+                        tc_fence_after();
+                    }
+                    // accumulator in three column blocks (64 + 64 + 16) to bound the live registers
+                    const uint32_t taddr = t_acc + ((uint32_t)(q * 32 + hh * 16) << 16);
+                    auto combine = [&](int g, float a0, float a1, float c0, float c1) {
+                        const float2 b2 = *reinterpret_cast<const float2 *>(sb + 8 * g + 2 * qd);
+                        a0 += b2.x; a1 += b2.y; c0 += b2.x; c1 += b2.y;
+                        if (p.init) {
+                            va[g] = make_float2(a0, a1);
+                            vb[g] = make_float2(c0, c1);
+                        } else {
+                            va[g].x = fmaf(p.alpha, a0, va[g].x); va[g].y = fmaf(p.alpha, a1, va[g].y);
+                            vb[g].x = fmaf(p.alpha, c0, vb[g].x); vb[g].y = fmaf(p.alpha, c1, vb[g].y);
+                        }
+                    };
+#pragma unroll
+                    for (int blk = 0; blk < 2; ++blk) {
+                        uint32_t t0[32];
+                        tmem_ld_16x256b_x8(taddr + 64u * blk, t0);
+                        tmem_ld_wait_dep(t0);
+#pragma unroll
+                        for (int gg = 0; gg < 8; ++gg)
+                            combine(8 * blk + gg, __uint_as_float(t0[4 * gg]), __uint_as_float(t0[4 * gg + 1]), __uint_as_float(t0[4 * gg + 2]),
+                                    __uint_as_float(t0[4 * gg + 3]));
+                    }
+                    {
+                        uint32_t t1[8];
+                        tmem_ld_16x256b_x2(taddr + 128u, t1);
+                        tmem_ld_wait_dep(t1);
+                        if (hh == 1) release_acc();
+#pragma unroll
+                        for (int gg = 0; gg < 2; ++gg)
+                            combine(16 + gg, __uint_as_float(t1[4 * gg]), __uint_as_float(t1[4 * gg + 1]), __uint_as_float(t1[4 * gg + 2]),
+                                    __uint_as_float(t1[4 * gg + 3]));
+                    }
+                    // LayerNorm statistics of rows A and B (two passes in registers; a row lives in one quad of lanes)
+                    auto stats = [&](float &meanA, float &rstdA, float &meanB, float &rstdB) {
+                        float sA = 0.f, sB = 0.f;
+#pragma unroll
+                        for (int g = 0; g < NG; ++g) { sA += va[g].x + va[g].y; sB += vb[g].x + vb[g].y; }
+                        sA += __shfl_xor_sync(0xffffffffu, sA, 1); sB += __shfl_xor_sync(0xffffffffu, sB, 1);
+                        sA += __shfl_xor_sync(0xffffffffu, sA, 2); sB += __shfl_xor_sync(0xffffffffu, sB, 2);
+                        meanA = sA * inv_n; meanB = sB * inv_n;
+                        float qA = 0.f, qB = 0.f;
+#pragma unroll
+                        for (int g = 0; g < NG; ++g) {
+                            float d0 = va[g].x - meanA, d1 = va[g].y - meanA;
+                            qA = fmaf(d0, d0, qA); qA = fmaf(d1, d1, qA);
+                            d0 = vb[g].x - meanB; d1 = vb[g].y - meanB;
+                            qB = fmaf(d0, d0, qB); qB = fmaf(d1, d1, qB);
+                        }
+                        qA += __shfl_xor_sync(0xffffffffu, qA, 1); qB += __shfl_xor_sync(0xffffffffu, qB, 1);
+                        qA += __shfl_xor_sync(0xffffffffu, qA, 2); qB += __shfl_xor_sync(0xffffffffu, qB, 2);
+                        rstdA = rsqrtf(qA * inv_n + 1e-5f); rstdB = rsqrtf(qB * inv_n + 1e-5f);
+                    };
+                    if (p.gf) {   // block-final LayerNorm replaces the residual stream (encoder.py:99)
+                        float mA, rA, mB, rB;
+                        stats(mA, rA, mB, rB);
+#pragma unroll
+                        for (int g = 0; g < NG; ++g) {
+                            const float2 gg = *reinterpret_cast<const float2 *>(sln + 8 * g + 2 * qd);
+                            const float2 bb = *reinterpret_cast<const float2 *>(sln + 256 + 8 * g + 2 * qd);
+                            va[g].x = (va[g].x - mA) * rA * gg.x + bb.x; va[g].y = (va[g].y - mA) * rA * gg.y + bb.y;
+                            vb[g].x = (vb[g].x - mB) * rB * gg.x + bb.x; vb[g].y = (vb[g].y - mB) * rB * gg.y + bb.y;
+                        }
+                    }
+                    // x_new: 8 rows x 32-byte sectors per store instruction
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) {
+                        if (okA) *reinterpret_cast<float2 *>(xa + 8 * g) = va[g];
+                        if (okB) *reinterpret_cast<float2 *>(xb + 8 * g) = vb[g];
+                    }
+                    // xn = bf16(LayerNorm_next(x_new)) (or bf16(x_new))
+                    float mA = 0.f, rA = 1.f, mB = 0.f, rB = 1.f;
+                    if (p.g1) stats(mA, rA, mB, rB);
+                    uint32_t pa[NG], pb[NG];
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) {
+                        float a0 = va[g].x, a1 = va[g].y, c0 = vb[g].x, c1 = vb[g].y;
+                        if (p.g1) {
+                            const float2 gg = *reinterpret_cast<const float2 *>(sln + 512 + 8 * g + 2 * qd);
+                            const float2 bb = *reinterpret_cast<const float2 *>(sln + 768 + 8 * g + 2 * qd);
+                            a0 = (a0 - mA) * rA * gg.x + bb.x; a1 = (a1 - mA) * rA * gg.y + bb.y;
+                            c0 = (c0 - mB) * rB * gg.x + bb.x; c1 = (c1 - mB) * rB * gg.y + bb.y;
+                        }
+                        pa[g] = pack_bf16x2(a0, a1);
+                        pb[g] = pack_bf16x2(c0, c1);
+                    }
+                    // neighbouring lanes swap one packed pair so that every lane stores 8 bytes and a quad writes the
+                    // 32 contiguous bytes of two column groups
+                    __nv_bfloat16 *na = reinterpret_cast<__nv_bfloat16 *>(p.out) + rowA * p.ldc;
+                    __nv_bfloat16 *nb = reinterpret_cast<__nv_bfloat16 *>(p.out) + rowB * p.ldc;
+                    const bool odd = qd & 1;
+#pragma unroll
+                    for (int g = 0; g < NG; g += 2) {
+                        const uint32_t sendA = odd ? pa[g] : pa[g + 1], sendB = odd ? pb[g] : pb[g + 1];
+                        const uint32_t recvA = __shfl_xor_sync(0xffffffffu, sendA, 1), recvB = __shfl_xor_sync(0xffffffffu, sendB, 1);
+                        const int col = odd ? 8 * (g + 1) + 2 * (qd - 1) : 8 * g + 2 * qd;
+                        const uint2 oA = odd ? make_uint2(recvA, pa[g + 1]) : make_uint2(pa[g], recvA);
+                        const uint2 oB = odd ? make_uint2(recvB, pb[g + 1]) : make_uint2(pb[g], recvB);
+                        if (okA) *reinterpret_cast<uint2 *>(na + col) = oA;
+                        if (okB) *reinterpret_cast<uint2 *>(nb + col) = oB;
+                    }
+                }
+            } else if constexpr (kTmaStore) {
+                // ---- bf16 output through per-warp staging tiles and TMA stores; TMEM loads run one piece ahead ----
+                const int my_np = (npieces - half + NSH - 1) / NSH;        // pieces half, half + 2, ...
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_after();
+                float tf = 0.0f;
+                if constexpr (EPI == EPI_BF16_POS) tf = (float)((grow0 + lane) % p.T);
+                uint32_t ra[32], rb[32];
+                auto issue = [&](int k, uint32_t (&r)[32]) {
+                    const int c0 = (half + NSH * k) * 32;
+                    if (p.block_n - c0 >= 32) tmem_ld_32x32b_x32(t_row + (uint32_t)c0, r);
+                    else tmem_ld_32x32b_x16_lo(t_row + (uint32_t)c0, r);
                 };
-                if (p.gf) {   // block-final LayerNorm replaces the residual stream (encoder.py:99)
-                    exchange(0);
-                    s1 = 0.f; s2 = 0.f;
+                auto process = [&](int k, uint32_t (&r)[32]) {
+                    const int c0 = (half + NSH * k) * 32;
+                    const int gcol = n0 + c0;
+                    if (gcol >= p.N) return;                               // warp-uniform
+                    if (p.block_n - c0 < 32) {
 #pragma unroll
-                    for (int k = 0; k < MAXP; ++k) {
-                        const int pi = half + NSH * k;
-                        if (pi < npieces) {
-                            const int c0 = pi * 32, ncol = min(32, p.block_n - c0);
-#pragma unroll
-                            for (int e = 0; e < 32; ++e) {
-                                const float t = (e < ncol) ? (v[k][e] - mean) * rstd * sln[c0 + e] + sln[256 + c0 + e] : 0.0f;
-                                v[k][e] = t;
-                                s1 += t;
-                                s2 = fmaf(t, t, s2);
-                            }
-                        }
+                        for (int i = 16; i < 32; ++i) r[i] = 0u;
                     }
-                }
-                // (3) write x_new (fp32, coalesced through staging)
+                    float f[32];
 #pragma unroll
-                for (int k = 0; k < MAXP; ++k) {
-                    const int pi = half + NSH * k;
-                    if (pi < npieces) {
-                        const int c0 = pi * 32, ncol = min(32, p.block_n - c0);
-                        uint8_t *sbuf = stage_base + (k & 1) * GEMM_STAGE_BYTES;
-#pragma unroll
-                        for (int jj = 0; jj < 8; ++jj)
-                            *reinterpret_cast<float4 *>(sbuf + sw128_offset(lane, jj)) =
-                                make_float4(v[k][jj * 4], v[k][jj * 4 + 1], v[k][jj * 4 + 2], v[k][jj * 4 + 3]);
-                        __syncwarp();
-                        const int cj = lane & 7;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int row = i * 4 + (lane >> 3);
-                            const int64_t grow = grow0 + row;
-                            if (cj * 4 < ncol && grow < p.M)
-                                *reinterpret_cast<float4 *>(p.x + grow * p.N + c0 + cj * 4) =
-                                    *reinterpret_cast<const float4 *>(sbuf + sw128_offset(row, cj));
-                        }
-                        __syncwarp();
+                    for (int e4 = 0; e4 < 8; ++e4) {
+                        const float4 b4 = *reinterpret_cast<const float4 *>(sb + c0 + e4 * 4);
+                        f[e4 * 4 + 0] = __uint_as_float(r[e4 * 4 + 0]) + b4.x;
+                        f[e4 * 4 + 1] = __uint_as_float(r[e4 * 4 + 1]) + b4.y;
+                        f[e4 * 4 + 2] = __uint_as_float(r[e4 * 4 + 2]) + b4.z;
+                        f[e4 * 4 + 3] = __uint_as_float(r[e4 * 4 + 3]) + b4.w;
                     }
-                }
-                // (4) xn = bf16(LayerNorm_next(x_new)) (or bf16(x_new))
-                if (p.g1) exchange(1);
+                    if constexpr (EPI == EPI_BF16_POS) {
+                        // rotation / fill of the positional columns by the angle of this thread's frame
 #pragma unroll
-                for (int k = 0; k < MAXP; ++k) {
-                    const int pi = half + NSH * k;
-                    if (pi < npieces) {
-                        const int c0 = pi * 32, ncol = min(32, p.block_n - c0);
-                        uint8_t *sbuf = stage_base + (k & 1) * GEMM_STAGE_BYTES;
+                        for (int g = 0; g < 2; ++g) {
+                            const int meta = smeta[(gcol >> 4) + g];
+                            const int kind = meta >> 12;                   // warp-uniform
+                            if (kind != 0) {
+                                const int pbase = meta & 0xFFF;
 #pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {
-                            uint32_t pk[4];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int c = jj * 8 + 2 * e;
-                                float a = v[k][c], b = v[k][c + 1];
-                                if (p.g1) {
-                                    a = (a - mean) * rstd * sln[512 + c0 + c] + sln[768 + c0 + c];
-                                    b = (b - mean) * rstd * sln[512 + c0 + c + 1] + sln[768 + c0 + c + 1];
+                                for (int u = 0; u < 8; ++u) {
+                                    float sn, cs;
+                                    __sincosf(tf * somega[pbase + u], &sn, &cs);
+                                    const int e0 = g * 16 + 2 * u;
+                                    const float as = f[e0], ac = f[e0 + 1];
+                                    if (kind == 1) {
+                                        f[e0] = as * sn + ac * cs;
+                                        f[e0 + 1] = ac * sn - as * cs;
+                                    } else {
+                                        f[e0] = cs;
+                                        f[e0 + 1] = sn;
+                                    }
                                 }
-                                __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
-                                pk[e] = *reinterpret_cast<uint32_t *>(&h2);
                             }
-                            *reinterpret_cast<uint4 *>(sbuf + stg64_offset(lane, jj)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
-                        __syncwarp();
-                        const int cj = lane & 3;
+                    }
+                    uint32_t pk[16];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int row = i * 8 + (lane >> 2);
-                            const int64_t grow = grow0 + row;
-                            if (cj * 8 < ncol && grow < p.M)
-                                *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + grow * p.ldc + c0 + cj * 8) =
-                                    *reinterpret_cast<const uint4 *>(sbuf + stg64_offset(row, cj));
-                        }
-                        __syncwarp();
+                    for (int e = 0; e < 16; ++e) {
+                        if constexpr (EPI == EPI_BF16_SILU) pk[e] = silu2_bf16(f[2 * e], f[2 * e + 1]);
+                        else pk[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+                    }
+                    uint8_t *sbuf = stage_base + (bufctr % GEMM_NSTG) * GEMM_STAGE_BYTES;
+                    ++bufctr;
+                    if (lane == 0) tma_store_wait_read<GEMM_NSTG - 1>();    // the store that last used this tile has read it
+                    __syncwarp();
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+                        *reinterpret_cast<uint4 *>(sbuf + stg64_offset(lane, jj)) = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmC, sbuf, gcol, grow0);
+                        tma_store_commit();
+                    }
+                };
+                if (my_np > 0) issue(0, ra);
+                else release_acc();
+                for (int k = 0; k < my_np; k += 2) {
+                    tmem_ld_wait_dep(ra);
+                    if (k + 1 < my_np) issue(k + 1, rb);
+                    else release_acc();
+                    process(k, ra);
+                    if (k + 1 < my_np) {
+                        tmem_ld_wait_dep(rb);
+                        if (k + 2 < my_np) issue(k + 2, ra);
+                        else release_acc();
+                        process(k + 1, rb);
                     }
                 }
             } else {
+                // ---- fp32 logits / fused arg-max (cold paths) ----
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
                 float best_v = -INFINITY;
                 int best_c = 0x7fffffff;
                 int buf = 0;
-                int trow = 0;
-                if constexpr (EPI == EPI_BF16_POS) trow = (int)((grow0 + lane) % p.T);
                 for (int pi = half; pi < npieces; pi += NSH) {
                     const int c0 = pi * 32;
                     const int ncol = min(32, p.block_n - c0);            // 32 or 16
                     uint32_t r[32];
-                    if (ncol == 32) {
-                        tmem_ld_32x32b_x32(t_row + (uint32_t)c0, r);
-                    } else {
-                        uint32_t t16[16];
-                        tmem_ld_32x32b_x16(t_row + (uint32_t)c0, t16);
+                    if (ncol == 32) tmem_ld_32x32b_x32(t_row + (uint32_t)c0, r);
+                    else tmem_ld_32x32b_x16_lo(t_row + (uint32_t)c0, r);
+                    tmem_ld_wait_dep(r);
+                    if (ncol < 32) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) { r[i] = t16[i]; r[16 + i] = 0u; }
+                        for (int i = 16; i < 32; ++i) r[i] = 0u;
                     }
-                    tmem_ld_wait();
                     float f[32];
 #pragma unroll
                     for (int e4 = 0; e4 < 8; ++e4) {
@@ -441,8 +540,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         for (int i = 0; i < 32; ++i) {
                             if (i < ncol && n0 + c0 + i < p.N && f[i] > best_v) { best_v = f[i]; best_c = n0 + c0 + i; }
                         }
-                    } else if constexpr (EPI == EPI_F32) {
-                        // two 16-column halves, each a [32 rows][64 B] staging tile
+                    } else {
+                        // EPI_F32: two 16-column halves, each a [32 rows][64 B] staging tile, coalesced 16-byte row segments
 #pragma unroll
                         for (int hh = 0; hh < 2; ++hh) {
                             if (hh * 16 < ncol) {
@@ -457,7 +556,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
                                     const int row = i * 8 + (lane >> 2);
-                                    const int64_t grow = grow0 + row;
+                                    const int64_t grow = (int64_t)grow0 + row;
                                     if (grow < p.M && gcol < p.N) {
                                         const float4 t = *reinterpret_cast<const float4 *>(sbuf + stg64_offset(row, cj));
                                         float *dst = reinterpret_cast<float *>(p.out) + grow * p.ldc + gcol;
@@ -470,103 +569,21 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                         }
                                     }
                                 }
+                                __syncwarp();
                                 buf ^= 1;
                             }
                         }
-                    } else {
-                        uint8_t *sbuf = stage_base + buf * GEMM_STAGE_BYTES;
-                        if constexpr (EPI == EPI_BF16_POS) {
-                            // rotation / fill of the positional columns; the (sin, cos) rows of this warp's 32 frames are
-                            // pulled in coalesced and transposed through the other staging buffer
-                            uint8_t *tbuf = stage_base + (buf ^ 1) * GEMM_STAGE_BYTES;
-                            __syncwarp();     // readers of the previous piece are done with that buffer
-#pragma unroll
-                            for (int g = 0; g < 2; ++g) {
-                                if (g * 16 < ncol) {
-                                    const int meta = p.col_meta[(n0 + c0) / 16 + g];
-                                    const int kind = meta >> 12;
-                                    if (kind != 0) {   // warp-uniform
-                                        const int pbase = meta & 0xFFF;
-                                        // 32 rows x 8 pairs x 8 B = 32 x 64 B ; lane -> (row = i*8 + lane/4, 16-byte chunk lane%4)
-#pragma unroll
-                                        for (int i = 0; i < 4; ++i) {
-                                            const int row = i * 8 + (lane >> 2);
-                                            const int tr = (int)((grow0 + row) % p.T);
-                                            const float4 t = *reinterpret_cast<const float4 *>(p.trig + (size_t)tr * p.trig_ld + pbase + (lane & 3) * 2);
-                                            *reinterpret_cast<float4 *>(tbuf + stg64_offset(row, lane & 3)) = t;
-                                        }
-                                        __syncwarp();
-#pragma unroll
-                                        for (int q4 = 0; q4 < 4; ++q4) {
-                                            const float4 sc = *reinterpret_cast<const float4 *>(tbuf + stg64_offset(lane, q4));
-                                            const float sn[2] = {sc.x, sc.z}, cs[2] = {sc.y, sc.w};
-#pragma unroll
-                                            for (int u = 0; u < 2; ++u) {
-                                                const int e0 = g * 16 + (q4 * 2 + u) * 2;
-                                                const float as = f[e0], ac = f[e0 + 1];
-                                                if (kind == 1) {
-                                                    f[e0] = as * sn[u] + ac * cs[u];
-                                                    f[e0 + 1] = ac * sn[u] - as * cs[u];
-                                                } else {
-                                                    f[e0] = cs[u];
-                                                    f[e0 + 1] = sn[u];
-                                                }
-                                            }
-                                        }
-                                        __syncwarp();
-                                    }
-                                }
-                            }
-                            (void)trow;
-                        }
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {
-                            if (jj * 8 < ncol) {
-                                uint32_t pk[4];
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float a = f[jj * 8 + 2 * e], b = f[jj * 8 + 2 * e + 1];
-                                    if constexpr (EPI == EPI_BF16_SILU) {
-                                        pk[e] = silu2_bf16(a, b);
-                                    } else {
-                                        __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
-                                        pk[e] = *reinterpret_cast<uint32_t *>(&h2);
-                                    }
-                                }
-                                *reinterpret_cast<uint4 *>(sbuf + stg64_offset(lane, jj)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                            }
-                        }
-                        __syncwarp();
-                        // coalesced write-out: 4 lanes cover one 64-byte row segment, 8 rows per instruction
-                        const int cj = lane & 3;
-                        const int gcol = n0 + c0 + cj * 8;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int row = i * 8 + (lane >> 2);
-                            const int64_t grow = grow0 + row;
-                            if (cj * 8 < ncol && grow < p.M && gcol < p.N) {
-                                const uint4 t = *reinterpret_cast<const uint4 *>(sbuf + stg64_offset(row, cj));
-                                __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.out) + grow * p.ldc + gcol;
-                                if (gcol + 7 < p.N && (p.ldc & 7) == 0) {
-                                    *reinterpret_cast<uint4 *>(dst) = t;
-                                } else {
-                                    const __nv_bfloat16 *vh = reinterpret_cast<const __nv_bfloat16 *>(&t);
-                                    for (int e = 0; e < 8; ++e)
-                                        if (gcol + e < p.N) dst[e] = vh[e];
-                                }
-                            }
-                        }
-                        buf ^= 1;     // the other buffer is free: its readers finished before the last __syncwarp
                     }
                 }
                 if constexpr (EPI == EPI_ARGMAX) {
-                    const int64_t grow = grow0 + lane;
+                    const int64_t grow = (int64_t)grow0 + lane;
                     if (grow < p.M && best_c != 0x7fffffff) atomicMax(p.best + grow, pack_best(best_v, best_c));
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);
+                release_acc();
             }
+        }
+        if constexpr (kTmaStore) {
+            if (lane == 0) tma_store_wait_all<0>();      // every store of this warp has landed before the CTA retires
         }
     }
     tc_fence_before();

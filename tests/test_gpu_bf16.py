@@ -23,7 +23,9 @@ GEMM_CASES = [
     (EPI_BF16, 3000, 288, 144, 0), (EPI_BF16, 2500, 144, 768, 0), (EPI_BF16, 777, 32, 32, 0),
     (EPI_F32, 1000, 256, 144, 0), (EPI_F32, 515, 11, 32, 0), (EPI_F32, 2048, 10000, 144, 0),
     (EPI_ARGMAX, 1000, 256, 144, 0), (EPI_ARGMAX, 3000, 10000, 144, 0), (EPI_ARGMAX, 130, 11, 32, 0),
-    (EPI_BF16, 40000, 576, 144, 0), (EPI_BF16, 40000, 144, 576, 0), (EPI_BF16, 1000, 144, 144, 48),
+    (EPI_BF16, 40000, 576, 144, 0), (EPI_BF16, 40000, 144, 576, 0), (EPI_BF16, 1000, 144, 144, 32), (EPI_BF16, 1000, 144, 144, 96),
+    (EPI_BF16, 5000, 1280, 144, 0), (EPI_SILU, 777, 576, 144, 0), (EPI_BF16, 333, 288, 144, 0), (EPI_BF16, 1000, 600, 144, 0),
+    (EPI_SILU, 60000, 576, 144, 0), (EPI_BF16, 129, 96, 48, 0),
 ]
 
 
@@ -41,8 +43,8 @@ def test_tcgen05_gemm_selftest(epi, M, N, K, bn, cuda_device):
 
 
 @pytest.mark.parametrize('M,N,K,flags', [(1000, 144, 144, 4), (4096, 144, 576, 4), (777, 144, 576, 6), (5000, 144, 576, 2),
-                                          (3000, 144, 768, 5), (300, 144, 144, 0), (2000, 80, 64, 6), (2000, 192, 144, 4),
-                                          (40000, 144, 576, 6)])
+                                          (3000, 144, 768, 5), (300, 144, 144, 0), (100, 144, 64, 6), (2000, 144, 144, 7),
+                                          (40000, 144, 576, 6), (40001, 144, 144, 4)])
 def test_residual_layernorm_epilogue_selftest(M, N, K, flags, cuda_device):
     from conformer_ocr_b200 import _lib
     lib = _lib.load()
