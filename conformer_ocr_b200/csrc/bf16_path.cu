@@ -455,13 +455,20 @@ static int launch_attn_tc(cocr_handle *h, const bf16 *qkvx, const int32_t *lens,
     AttnArgs a;
     a.B = B; a.T = T; a.nh = dm.nh; a.dh = dm.dh; a.d = dm.d; a.nchunk = bs->nchunk; a.lens = lens; a.ctx = ctx;
     a.scale_log2 = 1.4426950408889634f / sqrtf((float)dm.dh);
-    const uint32_t smem = attn_smem_bytes(bs->nchunk);
+    a.nqt = (T + ATT_BQ - 1) / ATT_BQ;
+    a.n_items = B * dm.nh * a.nqt;
+    // E table resident in shared memory when it leaves room for the Q tile and a two-deep K/V ring
+    a.e_resident = (a.nqt <= ATT_ERES_TILES && attn_smem_bytes(bs->nchunk, 1, 2, T) <= (uint32_t)bs->smem_optin && !getenv("COCR_ATTN_STREAM_E")) ? 1 : 0;
+    a.kv_stages = 2;
+    while (a.kv_stages < ATT_MAXSTAGES && attn_smem_bytes(bs->nchunk, a.e_resident, a.kv_stages + 1, T) <= (uint32_t)bs->smem_optin) ++a.kv_stages;
+    const uint32_t smem = attn_smem_bytes(bs->nchunk, a.e_resident, a.kv_stages, T);
+    if (smem > (uint32_t)bs->smem_optin) return set_error(h, COCR_ERR_UNSUPPORTED, "attention tiles do not fit shared memory");
     static bool attr = false;
     if (!attr) {
         COCR_CUDA(h, cudaFuncSetAttribute(k_attn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->smem_optin));
         attr = true;
     }
-    dim3 grid((T + ATT_BQ - 1) / ATT_BQ, dm.nh, B);
+    const int grid = a.n_items < h->num_sms ? a.n_items : h->num_sms;
     ProfScope ps(h, "attention_tc", st, 6.0 * B * T * (double)T * dm.d, 2.0 * M * (bs->nx + dm.d));
     k_attn_tc<<<grid, ATT_THREADS, smem, st>>>(tmQ, tmK, tmV, tmE, a);
     COCR_LAUNCHED(h);
