@@ -13,7 +13,9 @@
 //
 // Persistent kernel: one CTA per SM walks over work items (line, head, 128-query tile), q-tile fastest so that
 // the CTAs working at the same time share K/V in L2.  Roles: warps 0-3 online softmax + output (thread = query row
-// = TMEM lane), warp 4 TMA producer (runs ahead across items), warp 5 TMEM allocator + MMA issuer.
+// = TMEM lane), warp 4 TMA producer of Q and K(+E) (runs ahead across items), warp 5 TMEM allocator + MMA issuer,
+// warp 6 TMA producer of V.  K and V have separate rings: a K slot is free as soon as its S MMA has run, a V slot
+// when its P V has run, so the K loads run several tiles ahead of the softmax.
 //   * S = Qe Ke^T is double-buffered in TMEM; the MMA of the next tile (also across items) is issued before the
 //     P V of the current one, so the tensor pipe works under the softmax;
 //   * the softmax reads its whole 128-key row into registers with one wait, rescales the running output only when
@@ -33,13 +35,24 @@ struct AttnArgs {
     int nqt;                    // query tiles per line
     int n_items;                // B * nh * nqt
     int e_resident;             // 1: E table resident in shared memory
-    int kv_stages;              // K/V(/E) ring slots
+    int k_stages, v_stages;     // ring slots of the K(+E) tiles and of the V tiles
     const int32_t *lens;        // ragged mode: valid frames per line, else null
     __nv_bfloat16 *ctx;         // (B*T, d) head-major context
     float scale_log2;           // log2(e) / sqrt(dh)
+    long long *trace;           // debug: (tag, clock) pairs of CTA 0 (COCR_ATTN_TRACE), else null
 };
 
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_TRACE_EVENTS = 2048;     // per role (0 softmax warp 0, 1 MMA thread, 2 K loader)
+#define ATT_TRACE(role, tag)                                                                      \
+    do {                                                                                          \
+        if (p.trace && blockIdx.x == 0 && tr_n < ATT_TRACE_EVENTS) {                              \
+            p.trace[((role) * ATT_TRACE_EVENTS + tr_n) * 2] = (tag);                              \
+            p.trace[((role) * ATT_TRACE_EVENTS + tr_n) * 2 + 1] = clock64();                      \
+            ++tr_n;                                                                               \
+        }                                                                                         \
+    } while (0)
+
+constexpr int ATT_THREADS = 224;
 constexpr int ATT_BQ = 128;
 constexpr int ATT_BK = 128;
 constexpr uint32_t ATT_CHUNK = 128 * 128;      // bytes of a 128-row x 64-col bf16 SWIZZLE_128B tile
@@ -51,15 +64,15 @@ constexpr uint32_t ATT_TMEM_COLS = 512;
 constexpr uint32_t ATT_S_COL0 = 0, ATT_S_COL1 = 128, ATT_O_COL = 256;
 constexpr float ATT_LAZY_LOG2 = 8.0f;          // rescale only when the maximum grew by more than 2^8
 
-__host__ __device__ inline uint32_t attn_stage_bytes(int nchunk, int e_resident) {
-    return (uint32_t)(e_resident ? 2 : nchunk + 1) * ATT_CHUNK;          // K chunk 0 [+ E chunks] + V
+__host__ __device__ inline uint32_t attn_kstage_bytes(int nchunk, int e_resident) {
+    return (uint32_t)(e_resident ? 1 : nchunk) * ATT_CHUNK;              // K chunk 0 [+ E chunks]
 }
 __host__ __device__ inline uint32_t attn_eres_bytes(int nchunk, int T) {
     return (uint32_t)((T + ATT_BK - 1) / ATT_BK) * (uint32_t)(nchunk - 1) * ATT_CHUNK;
 }
-__host__ __device__ inline uint32_t attn_smem_bytes(int nchunk, int e_resident, int stages, int T) {
+__host__ __device__ inline uint32_t attn_smem_bytes(int nchunk, int e_resident, int k_stages, int v_stages, int T) {
     return (uint32_t)nchunk * ATT_CHUNK + (e_resident ? attn_eres_bytes(nchunk, T) : 0u) +
-           (uint32_t)stages * attn_stage_bytes(nchunk, e_resident) + 256 + 1024;
+           (uint32_t)k_stages * attn_kstage_bytes(nchunk, e_resident) + (uint32_t)v_stages * ATT_CHUNK + 256 + 1024;
 }
 
 __device__ __forceinline__ float ex2_fast(float x) {
@@ -83,21 +96,24 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     using namespace tc;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const uint32_t stage_bytes = attn_stage_bytes(p.nchunk, p.e_resident);
+    const uint32_t kstage_bytes = attn_kstage_bytes(p.nchunk, p.e_resident);
     const int ne = p.nchunk - 1;                                         // E chunks per key tile
     uint8_t *sQ = smem;                                                  // nchunk tiles
     uint8_t *sE = sQ + (uint32_t)p.nchunk * ATT_CHUNK;                   // resident E: [key tile][chunk]
-    uint8_t *sKV = sE + (p.e_resident ? attn_eres_bytes(p.nchunk, p.T) : 0u);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sKV + (uint32_t)p.kv_stages * stage_bytes);
+    uint8_t *sK = sE + (p.e_resident ? attn_eres_bytes(p.nchunk, p.T) : 0u);
+    uint8_t *sV = sK + (uint32_t)p.k_stages * kstage_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sV + (uint32_t)p.v_stages * ATT_CHUNK);
     uint64_t *qfull = bars;             // [1]
     uint64_t *qempty = bars + 1;        // [1]
     uint64_t *efull = bars + 2;         // [1]
     uint64_t *sfull = bars + 3;         // [2]
     uint64_t *pfull = bars + 5;         // [2]
     uint64_t *pvdone = bars + 7;        // [2]
-    uint64_t *kfull = bars + 9;         // [stages]
+    uint64_t *kfull = bars + 9;         // [k_stages]
     uint64_t *kempty = kfull + ATT_MAXSTAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(kempty + ATT_MAXSTAGES);
+    uint64_t *vfull = kempty + ATT_MAXSTAGES;   // [v_stages]
+    uint64_t *vempty = vfull + ATT_MAXSTAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(vempty + ATT_MAXSTAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qe_cols = 48 + p.d;                                         // columns of one head's Qe block
@@ -117,7 +133,8 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
         prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmE);
         mbar_init(qfull, 1); mbar_init(qempty, 1); mbar_init(efull, 1);
         for (int s = 0; s < 2; ++s) { mbar_init(&sfull[s], 1); mbar_init(&pfull[s], 4); mbar_init(&pvdone[s], 1); }
-        for (int s = 0; s < p.kv_stages; ++s) { mbar_init(&kfull[s], 1); mbar_init(&kempty[s], 1); }
+        for (int s = 0; s < p.k_stages; ++s) { mbar_init(&kfull[s], 1); mbar_init(&kempty[s], 1); }
+        for (int s = 0; s < p.v_stages; ++s) { mbar_init(&vfull[s], 1); mbar_init(&vempty[s], 1); }
         mbar_fence_init();
     }
     if (warp == 5) tmem_alloc(tmem_slot, ATT_TMEM_COLS);
@@ -137,31 +154,72 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                         tma_load_2d(sE + (uint32_t)(j * ne + c) * ATT_CHUNK, &tmE, efull, c * 64, j * ATT_BK);
             }
             uint32_t g = 0, nq = 0;                                       // global key-tile counter, Q loads issued
+            int tr_n = 0;
             auto load_kv = [&](int b, int hd, int j) {
-                const int st = (int)(g % (uint32_t)p.kv_stages);
-                const uint32_t ph = (g / (uint32_t)p.kv_stages) & 1u;
-                const int row0 = b * p.T;
+                const int st = (int)(g % (uint32_t)p.k_stages);
+                const uint32_t ph = (g / (uint32_t)p.k_stages) & 1u;
+                ATT_TRACE(2, 100 + j);
                 mbar_wait(&kempty[st], ph ^ 1u);
-                mbar_expect_tx(&kfull[st], stage_bytes);
-                uint8_t *dst = sKV + (uint32_t)st * stage_bytes;
-                tma_load_2d(dst, &tmK, &kfull[st], hd * 64, row0 + j * ATT_BK);
+                ATT_TRACE(2, 110 + j);
+                mbar_expect_tx(&kfull[st], kstage_bytes);
+                uint8_t *dst = sK + (uint32_t)st * kstage_bytes;
+                tma_load_2d(dst, &tmK, &kfull[st], hd * 64, b * p.T + j * ATT_BK);
                 if (!p.e_resident)
                     for (int c = 0; c < ne; ++c) tma_load_2d(dst + (uint32_t)(c + 1) * ATT_CHUNK, &tmE, &kfull[st], c * 64, j * ATT_BK);
-                tma_load_2d(dst + stage_bytes - ATT_CHUNK, &tmV, &kfull[st], hd * 64, row0 + j * ATT_BK);
                 ++g;
             };
+            // the tiles of the NEXT item are requested into L2 while the current one is processed: the activations do
+            // not fit L2 between kernels, so a tile fetched only when its ring slot frees would pay HBM latency
+            auto prefetch_item = [&](int item) {
+                if (item >= p.n_items) return;
+                int b, hd, qt;
+                decode(item, b, hd, qt);
+                const int ntiles = key_tiles(b);
+                if (ntiles == 0) return;
+                for (int c = 0; c < p.nchunk; ++c) tma_prefetch_2d(&tmQ, hd * qe_cols + c * 64, b * p.T + qt * ATT_BQ);
+                for (int j = 0; j < ntiles; ++j) tma_prefetch_2d(&tmK, hd * 64, b * p.T + j * ATT_BK);
+            };
+            prefetch_item(blockIdx.x);
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 int b, hd, qt;
                 decode(item, b, hd, qt);
                 const int ntiles = key_tiles(b);
+                prefetch_item(item + gridDim.x);
                 if (ntiles == 0) continue;
                 load_kv(b, hd, 0);                                        // does not depend on the Q buffer
+                ATT_TRACE(2, 120);
                 mbar_wait(qempty, (nq & 1u) ^ 1u);                        // last S MMA of the previous item has read Q
+                ATT_TRACE(2, 121);
                 mbar_expect_tx(qfull, (uint32_t)p.nchunk * ATT_CHUNK);
                 for (int c = 0; c < p.nchunk; ++c)
                     tma_load_2d(sQ + (uint32_t)c * ATT_CHUNK, &tmQ, qfull, hd * qe_cols + c * 64, b * p.T + qt * ATT_BQ);
                 ++nq;
                 for (int j = 1; j < ntiles; ++j) load_kv(b, hd, j);
+            }
+        }
+    } else if (warp == 6) {
+        // ================= TMA producer of V =================
+        if (lane == 0) {
+            uint32_t g = 0;
+            auto prefetch_item = [&](int item) {
+                if (item >= p.n_items) return;
+                int b, hd, qt;
+                decode(item, b, hd, qt);
+                const int ntiles = key_tiles(b);
+                for (int j = 0; j < ntiles; ++j) tma_prefetch_2d(&tmV, hd * 64, b * p.T + j * ATT_BK);
+            };
+            prefetch_item(blockIdx.x);
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                int b, hd, qt;
+                decode(item, b, hd, qt);
+                const int ntiles = key_tiles(b);
+                prefetch_item(item + gridDim.x);
+                for (int j = 0; j < ntiles; ++j, ++g) {
+                    const int st = (int)(g % (uint32_t)p.v_stages);
+                    mbar_wait(&vempty[st], ((g / (uint32_t)p.v_stages) & 1u) ^ 1u);
+                    mbar_expect_tx(&vfull[st], ATT_CHUNK);
+                    tma_load_2d(sV + (uint32_t)st * ATT_CHUNK, &tmV, &vfull[st], hd * 64, b * p.T + j * ATT_BK);
+                }
             }
         }
     } else if (warp == 5) {
@@ -187,12 +245,16 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                 return first_from(c.item + gridDim.x);
             };
             uint32_t nq = 0;                                                          // Q buffers consumed
+            int tr_n = 0;
             auto issue_s = [&](const Cur &c, uint32_t g) {
+                ATT_TRACE(1, 200 + c.j);
                 if (c.j == 0) { mbar_wait(qfull, nq & 1u); ++nq; }
-                const int st = (int)(g % (uint32_t)p.kv_stages);
-                mbar_wait(&kfull[st], (g / (uint32_t)p.kv_stages) & 1u);
+                ATT_TRACE(1, 210 + c.j);
+                const int st = (int)(g % (uint32_t)p.k_stages);
+                mbar_wait(&kfull[st], (g / (uint32_t)p.k_stages) & 1u);
+                ATT_TRACE(1, 220 + c.j);
                 tc_fence_after();
-                const uint32_t k_base = smem_u32(sKV + (uint32_t)st * stage_bytes);
+                const uint32_t k_base = smem_u32(sK + (uint32_t)st * kstage_bytes);
                 const uint32_t q_base = smem_u32(sQ);
                 const uint32_t d_s = tmem_base + ((g & 1u) ? ATT_S_COL1 : ATT_S_COL0);
                 for (int cc = 0; cc < p.nchunk; ++cc) {
@@ -207,6 +269,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                     }
                 }
                 umma_commit(&sfull[g & 1u]);
+                umma_commit(&kempty[st]);                                             // K(+E) slot may be refilled
                 if (c.j == c.ntiles - 1) umma_commit(qempty);                         // Q buffer free once this MMA has run
             };
             uint32_t g = 0;
@@ -216,16 +279,20 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                 const Cur nxt = next_of(cur);
                 if (nxt.valid) issue_s(nxt, g + 1);
                 // O (+)= P V for the current tile
+                const int st = (int)(g % (uint32_t)p.v_stages);
+                ATT_TRACE(1, 230 + cur.j);
+                mbar_wait(&vfull[st], (g / (uint32_t)p.v_stages) & 1u);
+                ATT_TRACE(1, 240 + cur.j);
                 mbar_wait(&pfull[g & 1u], (g >> 1) & 1u);
+                ATT_TRACE(1, 250 + cur.j);
                 tc_fence_after();
-                const int st = (int)(g % (uint32_t)p.kv_stages);
-                const uint32_t v_base = smem_u32(sKV + (uint32_t)st * stage_bytes + stage_bytes - ATT_CHUNK);
+                const uint32_t v_base = smem_u32(sV + (uint32_t)st * ATT_CHUNK);
                 const uint32_t p_tmem = tmem_base + ((g & 1u) ? ATT_S_COL1 : ATT_S_COL0);
                 for (int ks = 0; ks < ATT_BK / 16; ++ks) {
                     const uint64_t bd = make_smem_desc_sw128(v_base + ks * 2048, 1024);
                     umma_bf16_ts(tmem_base + ATT_O_COL, p_tmem + (uint32_t)ks * 8u, bd, idesc_o, (cur.j | ks) ? 1u : 0u);
                 }
-                umma_commit(&kempty[st]);          // K/V stage may be refilled
+                umma_commit(&vempty[st]);          // V slot may be refilled
                 umma_commit(&pvdone[g & 1u]);      // O up to date
                 cur = nxt;
                 ++g;
@@ -236,6 +303,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
         const int r = warp * 32 + lane;                         // row in the tile == TMEM lane
         const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
         uint32_t g = 0;
+        int tr_n = (threadIdx.x == 0) ? 0 : ATT_TRACE_EVENTS;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int b, hd, qt;
             decode(item, b, hd, qt);
@@ -245,7 +313,9 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
             float m_run = -INFINITY, l_run = 0.0f;
             for (int j = 0; j < ntiles; ++j, ++g) {
                 const uint32_t sb = g & 1u;
+                ATT_TRACE(0, 300 + j);
                 mbar_wait(&sfull[sb], (g >> 1) & 1u);
+                ATT_TRACE(0, 310 + j);
                 tc_fence_after();
                 const uint32_t s_addr = tmem_base + (sb ? ATT_S_COL1 : ATT_S_COL0) + lane_base;
                 uint32_t v0[32], v1[32], v2[32], v3[32];
@@ -254,6 +324,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                 tmem_ld_32x32b_x32(s_addr + 64, v2);
                 tmem_ld_32x32b_x32(s_addr + 96, v3);
                 tmem_ld_wait_dep(v0); tmem_ld_wait_dep(v1); tmem_ld_wait_dep(v2); tmem_ld_wait_dep(v3);
+                ATT_TRACE(0, 320 + j);
                 const int kv0 = j * ATT_BK;
                 const int nvalid = Tk - kv0;                         // >= 1; keys >= nvalid of this tile are masked
                 if (nvalid < ATT_BK) {
@@ -312,16 +383,20 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                 };
                 emit(v0, 0); emit(v1, 1); emit(v2, 2); emit(v3, 3);
                 l_run += ps0 + ps1;
+                ATT_TRACE(0, 330 + j);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&pfull[sb]);
+                ATT_TRACE(0, 340 + j);
             }
             // output: O / l -> ctx (head-major columns hd*dh .. +dh)
             const float inv = (l_run > 0.0f) ? 1.0f / l_run : 0.0f;
             uint32_t o0[32], o1[16];
             if (ntiles > 0) {
+                ATT_TRACE(0, 350);
                 mbar_wait(&pvdone[(g - 1) & 1u], ((g - 1) >> 1) & 1u);
+                ATT_TRACE(0, 351);
                 tc_fence_after();
                 tmem_ld_32x32b_x32(tmem_base + ATT_O_COL + lane_base, o0);
                 tmem_ld_32x32b_x16(tmem_base + ATT_O_COL + lane_base + 32, o1);
@@ -345,6 +420,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                     }
                 }
             }
+            ATT_TRACE(0, 360);
             // the O reads above are complete (wait::ld); the next item's first P V is ordered behind them by pfull
         }
     }
