@@ -12,17 +12,23 @@
 // and E main (d-16 columns) comes from a table shared by all lines / heads / layers.
 //
 // Persistent kernel: one CTA per SM walks over work items (line, head, 128-query tile), q-tile fastest so that
-// the CTAs working at the same time share K/V in L2.  Roles: warps 0-3 online softmax + output (thread = query row
-// = TMEM lane), warp 4 TMA producer of Q and K(+E) (runs ahead across items), warp 5 TMEM allocator + MMA issuer,
-// warp 6 TMA producer of V.  K and V have separate rings: a K slot is free as soon as its S MMA has run, a V slot
-// when its P V has run, so the K loads run several tiles ahead of the softmax.
-//   * S = Qe Ke^T is double-buffered in TMEM; the MMA of the next tile (also across items) is issued before the
-//     P V of the current one, so the tensor pipe works under the softmax;
-//   * the softmax reads its whole 128-key row into registers with one wait, rescales the running output only when
-//     the row maximum grew by more than 2^8 (lazy rescale; exact because the final division uses the same reference
-//     point), and writes P as packed bf16 back into TMEM over the S columns it has just consumed;
-//   * P V takes its A operand straight from TMEM (tcgen05.mma with A in tensor memory): P never touches shared memory;
-//   * the E table stays resident in shared memory when T <= ATT_ERES_TILES*128, else it streams with K/V.
+// the CTAs working at the same time share K/V in L2.
+//   warps 0-7  online softmax + output: thread = (query row = TMEM lane, half of the 128 keys of a tile); the two
+//              warps of a lane quarter exchange their row maxima / sums through shared memory
+//   warp 8     TMA producer of Q and K(+E), runs ahead across items and requests the next item into L2
+//   warp 9     TMEM allocator + MMA issuer
+//   warp 10    TMA producer of V
+// Tensor memory (512 columns):  S0 | S1 (2 x 128, fp32 scores, double-buffered)  O (64)  Q0 | Q1 (2 x 96, bf16 pairs).
+//   * Both MMAs take their A operand from TENSOR MEMORY: the softmax warps copy each Qe tile from its TMA staging
+//     buffer into TMEM once per item (one item ahead), and write P as packed bf16 over the S columns they have just
+//     consumed.  An SS-mode 128x128x16 MMA would read 8 KB of shared memory per 64 tensor cycles - exactly the
+//     128 B/clk shared-memory limit - and measured 110 cycles instead of 64; with A in TMEM only K/E/V stream from smem.
+//   * S of the next tile (also across items) is issued while the softmax of the current one runs; the P V of the
+//     current tile is slipped between the k-chunks of that S as soon as P is complete (it unblocks the output).
+//   * lazy rescale: the running output is rescaled only when a row maximum grew by more than 2^8 (exact, because
+//     the final division uses the same reference point).
+//   * K and V have separate rings (a K slot frees when its S MMA has run, a V slot when its P V has run); the E table
+//     stays resident in shared memory when T <= ATT_ERES_TILES*128, else it streams with K.
 #pragma once
 
 #include "tc_utils.cuh"
@@ -52,7 +58,8 @@ constexpr int ATT_TRACE_EVENTS = 2048;     // per role (0 softmax warp 0, 1 MMA 
         }                                                                                         \
     } while (0)
 
-constexpr int ATT_THREADS = 224;
+constexpr int ATT_SM_WARPS = 8;
+constexpr int ATT_THREADS = 32 * (ATT_SM_WARPS + 3);
 constexpr int ATT_BQ = 128;
 constexpr int ATT_BK = 128;
 constexpr uint32_t ATT_CHUNK = 128 * 128;      // bytes of a 128-row x 64-col bf16 SWIZZLE_128B tile
@@ -61,8 +68,10 @@ constexpr int ATT_MAXSTAGES = 4;
 constexpr int ATT_ERES_TILES = 3;              // E resident for T <= 384
 constexpr int ATT_DV = 64;                     // padded head dim of the V operand / O accumulator
 constexpr uint32_t ATT_TMEM_COLS = 512;
-constexpr uint32_t ATT_S_COL0 = 0, ATT_S_COL1 = 128, ATT_O_COL = 256;
+constexpr uint32_t ATT_S_COL0 = 0, ATT_S_COL1 = 128, ATT_O_COL = 256, ATT_Q_COL0 = 320, ATT_Q_COL1 = 416;
 constexpr float ATT_LAZY_LOG2 = 8.0f;          // rescale only when the maximum grew by more than 2^8
+constexpr uint32_t ATT_XCH_BYTES = 2 * 2 * 128 * 4;   // [parity][half][row] float
+constexpr uint32_t ATT_BAR_BYTES = 256;
 
 __host__ __device__ inline uint32_t attn_kstage_bytes(int nchunk, int e_resident) {
     return (uint32_t)(e_resident ? 1 : nchunk) * ATT_CHUNK;              // K chunk 0 [+ E chunks]
@@ -72,7 +81,7 @@ __host__ __device__ inline uint32_t attn_eres_bytes(int nchunk, int T) {
 }
 __host__ __device__ inline uint32_t attn_smem_bytes(int nchunk, int e_resident, int k_stages, int v_stages, int T) {
     return (uint32_t)nchunk * ATT_CHUNK + (e_resident ? attn_eres_bytes(nchunk, T) : 0u) +
-           (uint32_t)k_stages * attn_kstage_bytes(nchunk, e_resident) + (uint32_t)v_stages * ATT_CHUNK + 256 + 1024;
+           (uint32_t)k_stages * attn_kstage_bytes(nchunk, e_resident) + (uint32_t)v_stages * ATT_CHUNK + ATT_XCH_BYTES + ATT_BAR_BYTES;
 }
 
 __device__ __forceinline__ float ex2_fast(float x) {
@@ -80,36 +89,32 @@ __device__ __forceinline__ float ex2_fast(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-
-__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
+__device__ __forceinline__ uint32_t attn_pack_bf16x2(float a, float b) {
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h2);
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
           const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmE, const AttnArgs p) {
     using namespace tc;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem[];          // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t kstage_bytes = attn_kstage_bytes(p.nchunk, p.e_resident);
     const int ne = p.nchunk - 1;                                         // E chunks per key tile
-    uint8_t *sQ = smem;                                                  // nchunk tiles
+    uint8_t *sQ = smem;                                                  // Q staging: nchunk tiles
     uint8_t *sE = sQ + (uint32_t)p.nchunk * ATT_CHUNK;                   // resident E: [key tile][chunk]
     uint8_t *sK = sE + (p.e_resident ? attn_eres_bytes(p.nchunk, p.T) : 0u);
     uint8_t *sV = sK + (uint32_t)p.k_stages * kstage_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sV + (uint32_t)p.v_stages * ATT_CHUNK);
-    uint64_t *qfull = bars;             // [1]
-    uint64_t *qempty = bars + 1;        // [1]
+    float *xch = reinterpret_cast<float *>(sV + (uint32_t)p.v_stages * ATT_CHUNK);   // [2][2][128]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(xch) + ATT_XCH_BYTES);
+    uint64_t *qfull = bars;             // [1]  Q staging filled by TMA
+    uint64_t *qsempty = bars + 1;       // [1]  Q staging copied out (8 warps)
     uint64_t *efull = bars + 2;         // [1]
-    uint64_t *sfull = bars + 3;         // [2]
-    uint64_t *pfull = bars + 5;         // [2]
-    uint64_t *pvdone = bars + 7;        // [2]
-    uint64_t *kfull = bars + 9;         // [k_stages]
+    uint64_t *qtfull = bars + 3;        // [2]  Q copy in TMEM buffer complete (8 warps)
+    uint64_t *sfull = bars + 5;         // [2]
+    uint64_t *pfull = bars + 7;         // [2]  (8 warps)
+    uint64_t *pvdone = bars + 9;        // [2]
+    uint64_t *kfull = bars + 11;        // [k_stages]
     uint64_t *kempty = kfull + ATT_MAXSTAGES;
     uint64_t *vfull = kempty + ATT_MAXSTAGES;   // [v_stages]
     uint64_t *vempty = vfull + ATT_MAXSTAGES;
@@ -124,27 +129,38 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
         hd = bh % p.nh;
         b = bh / p.nh;
     };
-    auto key_tiles = [&](int b) {
-        const int Tk = p.lens ? min(max(p.lens[b], 0), p.T) : p.T;       // keys beyond are masked
-        return (Tk + ATT_BK - 1) / ATT_BK;
+    auto valid_keys = [&](int b) { return p.lens ? min(max(p.lens[b], 0), p.T) : p.T; };   // keys beyond are masked
+    auto key_tiles = [&](int item) {
+        int b, hd, qt;
+        decode(item, b, hd, qt);
+        return (valid_keys(b) + ATT_BK - 1) / ATT_BK;
+    };
+    // first item >= `item` of this CTA's sequence that has at least one key tile (n_items when there is none)
+    auto next_active = [&](int item) {
+        for (; item < p.n_items; item += gridDim.x)
+            if (key_tiles(item) > 0) return item;
+        return p.n_items;
     };
 
     if (threadIdx.x == 0) {
+        if ((smem_u32(smem) & 1023u) != 0u) __trap();
         prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmE);
-        mbar_init(qfull, 1); mbar_init(qempty, 1); mbar_init(efull, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&sfull[s], 1); mbar_init(&pfull[s], 4); mbar_init(&pvdone[s], 1); }
+        mbar_init(qfull, 1); mbar_init(qsempty, ATT_SM_WARPS); mbar_init(efull, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&qtfull[s], ATT_SM_WARPS); mbar_init(&sfull[s], 1); mbar_init(&pfull[s], ATT_SM_WARPS); mbar_init(&pvdone[s], 1);
+        }
         for (int s = 0; s < p.k_stages; ++s) { mbar_init(&kfull[s], 1); mbar_init(&kempty[s], 1); }
         for (int s = 0; s < p.v_stages; ++s) { mbar_init(&vfull[s], 1); mbar_init(&vempty[s], 1); }
         mbar_fence_init();
     }
-    if (warp == 5) tmem_alloc(tmem_slot, ATT_TMEM_COLS);
+    if (warp == ATT_SM_WARPS + 1) tmem_alloc(tmem_slot, ATT_TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4) {
-        // ================= TMA producer =================
+    if (warp == ATT_SM_WARPS) {
+        // ================= TMA producer of Q and K(+E) =================
         if (lane == 0) {
             if (p.e_resident) {
                 const int nt = (p.T + ATT_BK - 1) / ATT_BK;
@@ -155,10 +171,9 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
             }
             uint32_t g = 0, nq = 0;                                       // global key-tile counter, Q loads issued
             int tr_n = 0;
-            auto load_kv = [&](int b, int hd, int j) {
+            auto load_k = [&](int b, int hd, int j) {
                 const int st = (int)(g % (uint32_t)p.k_stages);
                 const uint32_t ph = (g / (uint32_t)p.k_stages) & 1u;
-                ATT_TRACE(2, 100 + j);
                 mbar_wait(&kempty[st], ph ^ 1u);
                 ATT_TRACE(2, 110 + j);
                 mbar_expect_tx(&kfull[st], kstage_bytes);
@@ -174,7 +189,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                 if (item >= p.n_items) return;
                 int b, hd, qt;
                 decode(item, b, hd, qt);
-                const int ntiles = key_tiles(b);
+                const int ntiles = key_tiles(item);
                 if (ntiles == 0) return;
                 for (int c = 0; c < p.nchunk; ++c) tma_prefetch_2d(&tmQ, hd * qe_cols + c * 64, b * p.T + qt * ATT_BQ);
                 for (int j = 0; j < ntiles; ++j) tma_prefetch_2d(&tmK, hd * 64, b * p.T + j * ATT_BK);
@@ -183,21 +198,20 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 int b, hd, qt;
                 decode(item, b, hd, qt);
-                const int ntiles = key_tiles(b);
+                const int ntiles = key_tiles(item);
                 prefetch_item(item + gridDim.x);
                 if (ntiles == 0) continue;
-                load_kv(b, hd, 0);                                        // does not depend on the Q buffer
-                ATT_TRACE(2, 120);
-                mbar_wait(qempty, (nq & 1u) ^ 1u);                        // last S MMA of the previous item has read Q
+                load_k(b, hd, 0);                                         // does not depend on the Q staging buffer
+                mbar_wait(qsempty, (nq & 1u) ^ 1u);                       // the previous Q has been copied into TMEM
                 ATT_TRACE(2, 121);
                 mbar_expect_tx(qfull, (uint32_t)p.nchunk * ATT_CHUNK);
                 for (int c = 0; c < p.nchunk; ++c)
                     tma_load_2d(sQ + (uint32_t)c * ATT_CHUNK, &tmQ, qfull, hd * qe_cols + c * 64, b * p.T + qt * ATT_BQ);
                 ++nq;
-                for (int j = 1; j < ntiles; ++j) load_kv(b, hd, j);
+                for (int j = 1; j < ntiles; ++j) load_k(b, hd, j);
             }
         }
-    } else if (warp == 6) {
+    } else if (warp == ATT_SM_WARPS + 2) {
         // ================= TMA producer of V =================
         if (lane == 0) {
             uint32_t g = 0;
@@ -205,14 +219,14 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                 if (item >= p.n_items) return;
                 int b, hd, qt;
                 decode(item, b, hd, qt);
-                const int ntiles = key_tiles(b);
+                const int ntiles = key_tiles(item);
                 for (int j = 0; j < ntiles; ++j) tma_prefetch_2d(&tmV, hd * 64, b * p.T + j * ATT_BK);
             };
             prefetch_item(blockIdx.x);
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 int b, hd, qt;
                 decode(item, b, hd, qt);
-                const int ntiles = key_tiles(b);
+                const int ntiles = key_tiles(item);
                 prefetch_item(item + gridDim.x);
                 for (int j = 0; j < ntiles; ++j, ++g) {
                     const int st = (int)(g % (uint32_t)p.v_stages);
@@ -222,94 +236,143 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == ATT_SM_WARPS + 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc_s = make_idesc_bf16(ATT_BQ, ATT_BK);                 // S = Qe Ke^T  (both K-major)
+        // All 32 lanes walk the schedule (identical values in every lane, so they live in uniform registers) and one
+        // elected lane issues the tcgen05 instructions: under a divergent `lane == 0` branch the compiler wraps every
+        // UTCHMMA in an elect/branch loop that costs more than a 64-cycle MMA.
+        {
+            const uint32_t idesc_s = make_idesc_bf16(ATT_BQ, ATT_BK);                 // S = Qe Ke^T  (Q in TMEM, K/E K-major)
             const uint32_t idesc_o = make_idesc_bf16(ATT_BQ, ATT_DV, 0, 1);           // O += P V     (P in TMEM, V MN-major)
             if (p.e_resident) mbar_wait(efull, 0);
             // flat walk over (item, key tile) with one tile of look-ahead
-            struct Cur { int item, j, ntiles; bool valid; };
-            auto first_from = [&](int item) {
-                Cur c{item, 0, 0, false};
-                for (; c.item < p.n_items; c.item += gridDim.x) {
-                    int b, hd, qt;
-                    decode(c.item, b, hd, qt);
-                    c.ntiles = key_tiles(b);
-                    if (c.ntiles > 0) { c.valid = true; break; }
-                }
+            struct Cur { int item, j, ntiles; uint32_t a; bool valid; };             // a = index among the active items
+            auto first_from = [&](int item, uint32_t a) {
+                Cur c{next_active(item), 0, 0, a, false};
+                if (c.item < p.n_items) { c.ntiles = key_tiles(c.item); c.valid = true; }
                 return c;
             };
             auto next_of = [&](const Cur &c) {
-                if (c.j + 1 < c.ntiles) return Cur{c.item, c.j + 1, c.ntiles, true};
-                return first_from(c.item + gridDim.x);
+                if (c.j + 1 < c.ntiles) return Cur{c.item, c.j + 1, c.ntiles, c.a, true};
+                return first_from(c.item + gridDim.x, c.a + 1);
             };
-            uint32_t nq = 0;                                                          // Q buffers consumed
-            int tr_n = 0;
-            auto issue_s = [&](const Cur &c, uint32_t g) {
+            int tr_n = (lane == 0) ? 0 : ATT_TRACE_EVENTS;
+            uint32_t g = 0;
+            Cur cur = first_from(blockIdx.x, 0);
+            bool pv_done = true;                                                      // no P V pending before the first tile
+            auto try_pv = [&](bool block) {
+                if (pv_done) return;
+                const int st = (int)(g % (uint32_t)p.v_stages);
+                const uint32_t vph = (g / (uint32_t)p.v_stages) & 1u, pph = (g >> 1) & 1u;
+                if (block) {
+                    mbar_wait(&vfull[st], vph);
+                    mbar_wait(&pfull[g & 1u], pph);
+                } else if (!__all_sync(0xffffffffu, mbar_test(&pfull[g & 1u], pph) && mbar_test(&vfull[st], vph))) {
+                    return;
+                }
+                ATT_TRACE(1, 250 + cur.j);
+                tc_fence_after();
+                const uint32_t v_base = smem_u32(sV + (uint32_t)st * ATT_CHUNK);
+                const uint32_t p_tmem = tmem_base + ((g & 1u) ? ATT_S_COL1 : ATT_S_COL0);
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < ATT_BK / 16; ++ks) {
+                        const uint64_t bd = make_smem_desc_sw128(v_base + ks * 2048, 1024);
+                        umma_bf16_ts(tmem_base + ATT_O_COL, p_tmem + (uint32_t)ks * 8u, bd, idesc_o, (cur.j | ks) ? 1u : 0u);
+                    }
+                    umma_commit(&vempty[st]);          // V slot may be refilled
+                    umma_commit(&pvdone[g & 1u]);      // O up to date
+                }
+                __syncwarp();
+                pv_done = true;
+            };
+            // S of tile c (global index gs); the pending P V of the current tile is slipped in as soon as it is ready
+            auto issue_s = [&](const Cur &c, uint32_t gs) {
                 ATT_TRACE(1, 200 + c.j);
-                if (c.j == 0) { mbar_wait(qfull, nq & 1u); ++nq; }
-                ATT_TRACE(1, 210 + c.j);
-                const int st = (int)(g % (uint32_t)p.k_stages);
-                mbar_wait(&kfull[st], (g / (uint32_t)p.k_stages) & 1u);
+                if (c.j == 0)
+                    while (!__all_sync(0xffffffffu, mbar_test(&qtfull[c.a & 1u], (c.a >> 1) & 1u))) try_pv(false);
+                const int st = (int)(gs % (uint32_t)p.k_stages);
+                while (!__all_sync(0xffffffffu, mbar_test(&kfull[st], (gs / (uint32_t)p.k_stages) & 1u))) try_pv(false);
                 ATT_TRACE(1, 220 + c.j);
                 tc_fence_after();
                 const uint32_t k_base = smem_u32(sK + (uint32_t)st * kstage_bytes);
-                const uint32_t q_base = smem_u32(sQ);
-                const uint32_t d_s = tmem_base + ((g & 1u) ? ATT_S_COL1 : ATT_S_COL0);
+                const uint32_t q_tmem = tmem_base + ((c.a & 1u) ? ATT_Q_COL1 : ATT_Q_COL0);
+                const uint32_t d_s = tmem_base + ((gs & 1u) ? ATT_S_COL1 : ATT_S_COL0);
                 for (int cc = 0; cc < p.nchunk; ++cc) {
                     uint32_t b_base;
                     if (cc == 0) b_base = k_base;
                     else if (p.e_resident) b_base = smem_u32(sE + (uint32_t)(c.j * ne + cc - 1) * ATT_CHUNK);
                     else b_base = k_base + (uint32_t)cc * ATT_CHUNK;
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t ad = make_smem_desc_sw128(q_base + (uint32_t)cc * ATT_CHUNK + ks * 32, 1024);
-                        const uint64_t bd = make_smem_desc_sw128(b_base + ks * 32, 1024);
-                        umma_bf16_ss(d_s, ad, bd, idesc_s, (cc | ks) ? 1u : 0u);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t bd = make_smem_desc_sw128(b_base + ks * 32, 1024);
+                            umma_bf16_ts(d_s, q_tmem + (uint32_t)(cc * 32 + ks * 8), bd, idesc_s, (cc | ks) ? 1u : 0u);
+                        }
+                        if (cc == p.nchunk - 1) {
+                            umma_commit(&sfull[gs & 1u]);
+                            umma_commit(&kempty[st]);                                 // K(+E) slot may be refilled
+                        }
                     }
+                    __syncwarp();
+                    if (cc + 1 < p.nchunk) try_pv(false);
                 }
-                umma_commit(&sfull[g & 1u]);
-                umma_commit(&kempty[st]);                                             // K(+E) slot may be refilled
-                if (c.j == c.ntiles - 1) umma_commit(qempty);                         // Q buffer free once this MMA has run
             };
-            uint32_t g = 0;
-            Cur cur = first_from(blockIdx.x);
             if (cur.valid) issue_s(cur, 0);
             while (cur.valid) {
                 const Cur nxt = next_of(cur);
+                pv_done = false;
                 if (nxt.valid) issue_s(nxt, g + 1);
-                // O (+)= P V for the current tile
-                const int st = (int)(g % (uint32_t)p.v_stages);
-                ATT_TRACE(1, 230 + cur.j);
-                mbar_wait(&vfull[st], (g / (uint32_t)p.v_stages) & 1u);
-                ATT_TRACE(1, 240 + cur.j);
-                mbar_wait(&pfull[g & 1u], (g >> 1) & 1u);
-                ATT_TRACE(1, 250 + cur.j);
-                tc_fence_after();
-                const uint32_t v_base = smem_u32(sV + (uint32_t)st * ATT_CHUNK);
-                const uint32_t p_tmem = tmem_base + ((g & 1u) ? ATT_S_COL1 : ATT_S_COL0);
-                for (int ks = 0; ks < ATT_BK / 16; ++ks) {
-                    const uint64_t bd = make_smem_desc_sw128(v_base + ks * 2048, 1024);
-                    umma_bf16_ts(tmem_base + ATT_O_COL, p_tmem + (uint32_t)ks * 8u, bd, idesc_o, (cur.j | ks) ? 1u : 0u);
-                }
-                umma_commit(&vempty[st]);          // V slot may be refilled
-                umma_commit(&pvdone[g & 1u]);      // O up to date
+                try_pv(true);
                 cur = nxt;
                 ++g;
             }
         }
     } else {
-        // ================= softmax / output (thread = query row) =================
-        const int r = warp * 32 + lane;                         // row in the tile == TMEM lane
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-        uint32_t g = 0;
+        // ================= softmax / output =================
+        const int q = warp & 3, hf = warp >> 2;                  // TMEM lane quarter, half of the keys of a tile
+        const int r = q * 32 + lane;                             // row in the tile == TMEM lane
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        uint32_t g = 0, xr = 0, na = 0;                          // key tiles, exchange rounds, active items seen
         int tr_n = (threadIdx.x == 0) ? 0 : ATT_TRACE_EVENTS;
+        // copy the staged Qe tile of active item #a into TMEM buffer a&1: this thread moves its half of row r
+        auto copy_q = [&](uint32_t a) {
+            mbar_wait(qfull, a & 1u);
+            const uint32_t q_tmem = tmem_base + ((a & 1u) ? ATT_Q_COL1 : ATT_Q_COL0) + lane_base + (uint32_t)(hf * p.nchunk * 16);
+#pragma unroll
+            for (int u = 0; u < ATT_MAXCHUNK; ++u) {
+                if (u < p.nchunk) {
+                    uint32_t w[16];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int pi = hf * p.nchunk * 4 + u * 4 + k;                  // 16-byte piece of the row
+                        const uint4 t = *reinterpret_cast<const uint4 *>(sQ + (uint32_t)(pi >> 3) * ATT_CHUNK + sw128_offset(r, pi & 7));
+                        w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w;
+                    }
+                    tmem_st_32x32b_x16n(q_tmem + (uint32_t)u * 16u, w);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(qsempty); mbar_arrive(&qtfull[a & 1u]); }
+        };
+        {
+            const int first = next_active(blockIdx.x);
+            if (first < p.n_items) copy_q(0);
+        }
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int b, hd, qt;
             decode(item, b, hd, qt);
-            const int Tk = p.lens ? min(max(p.lens[b], 0), p.T) : p.T;
+            const int Tk = valid_keys(b);
             const int ntiles = (Tk + ATT_BK - 1) / ATT_BK;
-            const int i = qt * ATT_BQ + r;                          // frame index of this query inside its line
+            if (ntiles == 0) {
+                // no keys: emit zeros like the SIMT path
+                const int i = qt * ATT_BQ + r;
+                if (i < p.T)
+                    for (int c = hf; c < p.dh; c += 2) p.ctx[((int64_t)b * p.T + i) * p.d + hd * p.dh + c] = __float2bfloat16_rn(0.0f);
+                continue;
+            }
             float m_run = -INFINITY, l_run = 0.0f;
             for (int j = 0; j < ntiles; ++j, ++g) {
                 const uint32_t sb = g & 1u;
@@ -317,106 +380,157 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                 mbar_wait(&sfull[sb], (g >> 1) & 1u);
                 ATT_TRACE(0, 310 + j);
                 tc_fence_after();
-                const uint32_t s_addr = tmem_base + (sb ? ATT_S_COL1 : ATT_S_COL0) + lane_base;
-                uint32_t v0[32], v1[32], v2[32], v3[32];
-                tmem_ld_32x32b_x32(s_addr, v0);
-                tmem_ld_32x32b_x32(s_addr + 32, v1);
-                tmem_ld_32x32b_x32(s_addr + 64, v2);
-                tmem_ld_32x32b_x32(s_addr + 96, v3);
-                tmem_ld_wait_dep(v0); tmem_ld_wait_dep(v1); tmem_ld_wait_dep(v2); tmem_ld_wait_dep(v3);
-                ATT_TRACE(0, 320 + j);
-                const int kv0 = j * ATT_BK;
-                const int nvalid = Tk - kv0;                         // >= 1; keys >= nvalid of this tile are masked
-                if (nvalid < ATT_BK) {
+                const uint32_t s_base = tmem_base + (sb ? ATT_S_COL1 : ATT_S_COL0) + lane_base;
+                uint32_t v0[32], v1[32];
+                tmem_ld_32x32b_x32(s_base + (uint32_t)(hf * 64), v0);
+                tmem_ld_32x32b_x32(s_base + (uint32_t)(hf * 64 + 32), v1);
+                tmem_ld_wait_dep(v0); tmem_ld_wait_dep(v1);
+                const int nvalid = Tk - j * ATT_BK - hf * 64;        // keys >= nvalid of this thread's 64 are masked
+                if (nvalid < 64) {
                     const uint32_t ninf = __float_as_uint(-INFINITY);
 #pragma unroll
                     for (int e = 0; e < 32; ++e) {
                         if (e >= nvalid) v0[e] = ninf;
                         if (32 + e >= nvalid) v1[e] = ninf;
-                        if (64 + e >= nvalid) v2[e] = ninf;
-                        if (96 + e >= nvalid) v3[e] = ninf;
                     }
                 }
-                float t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;
+                float t0 = -INFINITY, t1 = -INFINITY;
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    t0 = fmaxf(t0, __uint_as_float(v0[e])); t1 = fmaxf(t1, __uint_as_float(v1[e]));
-                    t2 = fmaxf(t2, __uint_as_float(v2[e])); t3 = fmaxf(t3, __uint_as_float(v3[e]));
-                }
-                const float m_new = fmaxf(m_run, fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)));
+                for (int e = 0; e < 32; ++e) { t0 = fmaxf(t0, __uint_as_float(v0[e])); t1 = fmaxf(t1, __uint_as_float(v1[e])); }
+                // row maximum over both halves (the partner warp holds the other 64 keys); the barrier also orders the
+                // partner's S loads before this warp's P stores into the same TMEM columns
+                float *xb = xch + (xr & 1u) * 256;
+                xb[hf * 128 + r] = fmaxf(t0, t1);
+                named_bar_sync(1 + q, 64);
+                const float m_new = fmaxf(m_run, fmaxf(fmaxf(t0, t1), xb[(hf ^ 1) * 128 + r]));
+                ++xr;
                 if (j == 0) {
                     m_run = m_new;
                 } else {
                     const bool need = (m_new - m_run) * p.scale_log2 > ATT_LAZY_LOG2;
-                    if (__any_sync(0xffffffffu, need)) {
-                        // rescale the running output of every row of this warp to its new maximum (TMEM round trip)
+                    if (__any_sync(0xffffffffu, need)) {       // same rows, same values in both warps of the quarter
                         const float corr = ex2_fast((m_run - m_new) * p.scale_log2);
                         m_run = m_new;
                         l_run *= corr;
                         mbar_wait(&pvdone[(g - 1) & 1u], ((g - 1) >> 1) & 1u);
                         tc_fence_after();
+                        // this warp rescales O columns [hf*32, hf*32+32) (48 columns cover dh <= 48)
+                        if (hf == 0) {
+                            uint32_t o[32];
+                            tmem_ld_32x32b_x32(tmem_base + ATT_O_COL + lane_base, o);
+                            tmem_ld_wait_dep(o);
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) {                  // 48 columns cover dh <= 48
+                            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * corr);
+                            tmem_st_32x32b_x32(tmem_base + ATT_O_COL + lane_base, o);
+                        } else {
                             uint32_t o[16];
-                            tmem_ld_32x32b_x16(tmem_base + ATT_O_COL + lane_base + c * 16, o);
+                            tmem_ld_32x32b_x16(tmem_base + ATT_O_COL + lane_base + 32, o);
                             tmem_ld_wait_dep(o);
 #pragma unroll
                             for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * corr);
-                            tmem_st_32x32b_x16(tmem_base + ATT_O_COL + lane_base + c * 16, o);
+                            tmem_st_32x32b_x16n(tmem_base + ATT_O_COL + lane_base + 32, o);
                         }
                     }
                 }
-                // probabilities -> packed bf16 in TMEM over the first 64 columns of this S buffer
+                ATT_TRACE(0, 320 + j);
+                // probabilities -> packed bf16 in TMEM: keys [hf*64, hf*64+64) of P live in columns [hf*32, hf*32+32)
                 const float mb = m_run * p.scale_log2;
                 float ps0 = 0.f, ps1 = 0.f;
-                auto emit = [&](uint32_t (&v)[32], int cidx) {
-                    uint32_t pk[16];
+                uint32_t pk[32];
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const float p0 = ex2_fast(fmaf(__uint_as_float(v[2 * e]), p.scale_log2, -mb));
-                        const float p1 = ex2_fast(fmaf(__uint_as_float(v[2 * e + 1]), p.scale_log2, -mb));
-                        ps0 += p0; ps1 += p1;
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
-                        pk[e] = *reinterpret_cast<uint32_t *>(&h2);
-                    }
-                    tmem_st_32x32b_x16(s_addr + (uint32_t)cidx * 16u, pk);
-                };
-                emit(v0, 0); emit(v1, 1); emit(v2, 2); emit(v3, 3);
+                for (int e = 0; e < 16; ++e) {
+                    const float p0 = ex2_fast(fmaf(__uint_as_float(v0[2 * e]), p.scale_log2, -mb));
+                    const float p1 = ex2_fast(fmaf(__uint_as_float(v0[2 * e + 1]), p.scale_log2, -mb));
+                    ps0 += p0; ps1 += p1;
+                    pk[e] = attn_pack_bf16x2(p0, p1);
+                }
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const float p0 = ex2_fast(fmaf(__uint_as_float(v1[2 * e]), p.scale_log2, -mb));
+                    const float p1 = ex2_fast(fmaf(__uint_as_float(v1[2 * e + 1]), p.scale_log2, -mb));
+                    ps0 += p0; ps1 += p1;
+                    pk[16 + e] = attn_pack_bf16x2(p0, p1);
+                }
+                tmem_st_32x32b_x32(s_base + (uint32_t)(hf * 32), pk);
                 l_run += ps0 + ps1;
-                ATT_TRACE(0, 330 + j);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&pfull[sb]);
                 ATT_TRACE(0, 340 + j);
+                if (j == 0) {
+                    // one item ahead: stage the next active item's Q into the other TMEM buffer
+                    const int nx = next_active(item + gridDim.x);
+                    if (nx < p.n_items) copy_q(na + 1);
+                }
             }
-            // output: O / l -> ctx (head-major columns hd*dh .. +dh)
-            const float inv = (l_run > 0.0f) ? 1.0f / l_run : 0.0f;
-            uint32_t o0[32], o1[16];
-            if (ntiles > 0) {
-                ATT_TRACE(0, 350);
-                mbar_wait(&pvdone[(g - 1) & 1u], ((g - 1) >> 1) & 1u);
-                ATT_TRACE(0, 351);
-                tc_fence_after();
-                tmem_ld_32x32b_x32(tmem_base + ATT_O_COL + lane_base, o0);
-                tmem_ld_32x32b_x16(tmem_base + ATT_O_COL + lane_base + 32, o1);
-                tmem_ld_wait_dep(o0); tmem_ld_wait_dep(o1);
-            } else {
+            ++na;
+            // ---- output: O / l -> ctx (head-major columns hd*dh .. +dh), fragment layout, 16 rows per warp ----
+            float *xb = xch + (xr & 1u) * 256;
+            xb[hf * 128 + r] = l_run;
+            named_bar_sync(1 + q, 64);
+            ++xr;
+            const int rin = lane >> 2, qd = lane & 3;
+            const int rowA = q * 32 + hf * 16 + rin, rowB = rowA + 8;                 // rows of the tile
+            const float lA = xb[rowA] + xb[128 + rowA], lB = xb[rowB] + xb[128 + rowB];
+            const float invA = (lA > 0.0f) ? 1.0f / lA : 0.0f, invB = (lB > 0.0f) ? 1.0f / lB : 0.0f;
+            ATT_TRACE(0, 350);
+            mbar_wait(&pvdone[(g - 1) & 1u], ((g - 1) >> 1) & 1u);
+            ATT_TRACE(0, 351);
+            tc_fence_after();
+            uint32_t o0[16], o1[4];
+            const uint32_t o_addr = tmem_base + ATT_O_COL + ((uint32_t)(q * 32 + hf * 16) << 16);
+            tmem_ld_16x256b_x4(o_addr, o0);
+            tmem_ld_16x256b_x1(o_addr + 32, o1);
+            tmem_ld_wait_dep(o0); tmem_ld_wait_dep(o1);
+            // packed pairs: pa[gq] = row A columns 8*gq + 2*qd, +1
+            uint32_t pa[5], pb[5];
 #pragma unroll
-                for (int e = 0; e < 32; ++e) o0[e] = 0u;
-#pragma unroll
-                for (int e = 0; e < 16; ++e) o1[e] = 0u;
+            for (int gq = 0; gq < 4; ++gq) {
+                pa[gq] = attn_pack_bf16x2(__uint_as_float(o0[4 * gq]) * invA, __uint_as_float(o0[4 * gq + 1]) * invA);
+                pb[gq] = attn_pack_bf16x2(__uint_as_float(o0[4 * gq + 2]) * invB, __uint_as_float(o0[4 * gq + 3]) * invB);
             }
-            if (i < p.T) {
-                __nv_bfloat16 *dst = p.ctx + ((int64_t)b * p.T + i) * p.d + hd * p.dh;
+            pa[4] = attn_pack_bf16x2(__uint_as_float(o1[0]) * invA, __uint_as_float(o1[1]) * invA);
+            pb[4] = attn_pack_bf16x2(__uint_as_float(o1[2]) * invB, __uint_as_float(o1[3]) * invB);
+            const int iA = qt * ATT_BQ + rowA, iB = qt * ATT_BQ + rowB;               // frame inside the line
+            const bool okA = iA < p.T, okB = iB < p.T;
+            __nv_bfloat16 *dA = p.ctx + ((int64_t)b * p.T + iA) * p.d + hd * p.dh;
+            __nv_bfloat16 *dB = p.ctx + ((int64_t)b * p.T + iB) * p.d + hd * p.dh;
+            const bool odd = qd & 1;
+            const bool vec_ok = (p.dh % 4 == 0) && (p.d % 4 == 0);                     // 8-byte aligned row segments
 #pragma unroll
-                for (int e = 0; e < 48; e += 2) {
-                    if (e + 1 < p.dh) {
-                        const float a = __uint_as_float(e < 32 ? o0[e & 31] : o1[e & 15]) * inv;
-                        const float c = __uint_as_float(e + 1 < 32 ? o0[(e + 1) & 31] : o1[(e + 1) & 15]) * inv;
-                        *reinterpret_cast<__nv_bfloat162 *>(dst + e) = __floats2bfloat162_rn(a, c);
-                    } else if (e < p.dh) {
-                        dst[e] = __float2bfloat16_rn(__uint_as_float(e < 32 ? o0[e & 31] : o1[e & 15]) * inv);
+            for (int gq = 0; gq < 4; gq += 2) {
+                // neighbouring lanes swap one pair: every lane then owns 4 consecutive columns (8 bytes)
+                const uint32_t sA = odd ? pa[gq] : pa[gq + 1], sB = odd ? pb[gq] : pb[gq + 1];
+                const uint32_t rA = __shfl_xor_sync(0xffffffffu, sA, 1), rB = __shfl_xor_sync(0xffffffffu, sB, 1);
+                const int col = odd ? 8 * (gq + 1) + 2 * (qd - 1) : 8 * gq + 2 * qd;
+                const uint2 oA = odd ? make_uint2(rA, pa[gq + 1]) : make_uint2(pa[gq], rA);
+                const uint2 oB = odd ? make_uint2(rB, pb[gq + 1]) : make_uint2(pb[gq], rB);
+                if (vec_ok && col + 4 <= p.dh) {
+                    if (okA) *reinterpret_cast<uint2 *>(dA + col) = oA;
+                    if (okB) *reinterpret_cast<uint2 *>(dB + col) = oB;
+                } else {
+                    const __nv_bfloat16 *hA = reinterpret_cast<const __nv_bfloat16 *>(&oA), *hB = reinterpret_cast<const __nv_bfloat16 *>(&oB);
+                    for (int e = 0; e < 4; ++e) {
+                        if (col + e < p.dh) {
+                            if (okA) dA[col + e] = hA[e];
+                            if (okB) dB[col + e] = hB[e];
+                        }
+                    }
+                }
+            }
+            {
+                const int col = 32 + 2 * qd;
+                const __nv_bfloat16 *hA = reinterpret_cast<const __nv_bfloat16 *>(&pa[4]), *hB = reinterpret_cast<const __nv_bfloat16 *>(&pb[4]);
+                if (col + 2 <= p.dh && (p.dh % 2 == 0) && (p.d % 2 == 0)) {
+                    if (okA) *reinterpret_cast<uint32_t *>(dA + col) = pa[4];
+                    if (okB) *reinterpret_cast<uint32_t *>(dB + col) = pb[4];
+                } else {
+                    for (int e = 0; e < 2; ++e) {
+                        if (col + e < p.dh) {
+                            if (okA) dA[col + e] = hA[e];
+                            if (okB) dB[col + e] = hB[e];
+                        }
                     }
                 }
             }
@@ -426,7 +540,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == ATT_SM_WARPS + 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, ATT_TMEM_COLS);
     }

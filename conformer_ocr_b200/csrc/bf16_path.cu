@@ -336,7 +336,7 @@ static int pack_attention(cocr_handle *h) {
     Bf16State *bs = h->bf;
     const Dims &dm = h->dm;
     const int d = dm.d, nh = dm.nh, dh = dm.dh, L = dm.L;
-    bs->tc_attn = (dh <= 48) && (d >= 80) && ((d - 16) % 64 == 0) && ((48 + d) / 64 <= ATT_MAXCHUNK) && L > 0;
+    bs->tc_attn = (dh <= 40) && (d >= 80) && ((d - 16) % 64 == 0) && ((48 + d) / 64 <= ATT_MAXCHUNK) && L > 0;
     if (getenv("COCR_SIMT_ATTENTION")) bs->tc_attn = false;
     if (!bs->tc_attn) return COCR_OK;
     bs->qe_cols = 48 + d;

@@ -236,7 +236,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        // all lanes walk the loop (uniform values), one elected lane issues: a divergent `lane == 0` branch would make
+        // the compiler wrap every UTCHMMA in an elect/branch loop
+        {
             const uint32_t idesc = make_idesc_bf16(GEMM_BM, p.block_n);
             if (p.resident && my_count > 0) mbar_wait(bfull, 0);
             int slot = 0;
@@ -253,15 +255,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const uint32_t a_base = smem_u32(ring + (uint32_t)slot * slot_bytes);
                     const uint32_t b_base = p.resident ? smem_u32(bres + (uint32_t)kc * b_chunk) : a_base + GEMM_A_CHUNK;
                     const int nks = (kc == p.nkc - 1) ? p.last_ksteps : 4;
-                    for (int ks = 0; ks < nks; ++ks) {
-                        const uint64_t ad = make_smem_desc_sw128(a_base + ks * 32, 1024);
-                        const uint64_t bd = make_smem_desc_sw128(b_base + ks * 32, 1024);
-                        umma_bf16_ss(d_tmem, ad, bd, idesc, (kc | ks) ? 1u : 0u);
+                    if (elect_one()) {
+                        for (int ks = 0; ks < nks; ++ks) {
+                            const uint64_t ad = make_smem_desc_sw128(a_base + ks * 32, 1024);
+                            const uint64_t bd = make_smem_desc_sw128(b_base + ks * 32, 1024);
+                            umma_bf16_ss(d_tmem, ad, bd, idesc, (kc | ks) ? 1u : 0u);
+                        }
+                        umma_commit(&empty[slot]);
+                        if (kc == p.nkc - 1) umma_commit(&tfull[acc]);
                     }
-                    umma_commit(&empty[slot]);
+                    __syncwarp();
                     if (++slot == p.stages) { slot = 0; phase ^= 1u; }
                 }
-                umma_commit(&tfull[acc]);
             }
         }
     } else {
