@@ -130,13 +130,16 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
         b = bh / p.nh;
     };
     auto valid_keys = [&](int b) { return p.lens ? min(max(p.lens[b], 0), p.T) : p.T; };   // keys beyond are masked
+    const int full_tiles = (p.T + ATT_BK - 1) / ATT_BK;
     auto key_tiles = [&](int item) {
+        if (!p.lens) return full_tiles;                                   // unmasked: no per-line lookup (and no divisions)
         int b, hd, qt;
         decode(item, b, hd, qt);
         return (valid_keys(b) + ATT_BK - 1) / ATT_BK;
     };
     // first item >= `item` of this CTA's sequence that has at least one key tile (n_items when there is none)
     auto next_active = [&](int item) {
+        if (!p.lens) return min(item, p.n_items);
         for (; item < p.n_items; item += gridDim.x)
             if (key_tiles(item) > 0) return item;
         return p.n_items;

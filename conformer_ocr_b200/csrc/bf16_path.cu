@@ -6,6 +6,8 @@
 // Reference symbols: same as fp32_path.cu.
 #include <math.h>
 
+#include <algorithm>
+
 #include "common.h"
 #include "gemm_tc.cuh"
 #include "attn_tc.cuh"
@@ -22,9 +24,14 @@ struct Bf16State {
     int qe_cols = 0, nx = 0, nchunk = 0;
     bf16 *w_qkvx = nullptr;       // (L, nx, d)
     float *b_qkvx = nullptr;      // (L, nx)
-    int16_t *meta = nullptr;      // (nx / 16)
+    int16_t *meta = nullptr;      // (nx / 16), in GEMM column order
+    int16_t *piece_dst = nullptr; // (nx / 32): output column / 32 of every 32-column piece of the GEMM
     float *omega = nullptr;       // (d/2) angular frequencies omega_m (embedding.py:42-44)
     bf16 *etab = nullptr;         // (T, d - 16) (cos, sin) interleaved
+    // conv module: first pointwise conv with (value, gate) rows interleaved and scaled by 1/2 for the GLU epilogue
+    bf16 *w_pw1g = nullptr;       // (L, 2d, d)
+    float *b_pw1g = nullptr;      // (L, 2d)
+    float *dw_taps = nullptr;     // (L, K*d + d): depthwise taps [k][pair](2) * bn_scale / 2, then bn_shift / 2
     int tab_T = 0;
 };
 
@@ -76,7 +83,7 @@ static int pick_block_n(int N) {
     return 256;
 }
 
-struct PosArgs { const int16_t *meta; const float *omega; int n_omega, T; };
+struct PosArgs { const int16_t *meta; const float *omega; int n_omega, T; const int16_t *piece_dst; };
 struct ResidArgs { float *x; float alpha; int init; const float *gf, *bf, *g1, *b1; };
 
 int launch_gemm_tc(cocr_handle *h, int epi, const bf16 *A, int lda, const bf16 *W, int ldw, const float *bias, void *out,
@@ -95,13 +102,15 @@ int launch_gemm_tc(cocr_handle *h, int epi, const bf16 *A, int lda, const bf16 *
     p.last_ksteps = (K - (p.nkc - 1) * GEMM_KC) / 16;
     p.bias = bias; p.out = out; p.ldc = ldc; p.best = best;
     p.col_meta = pos ? pos->meta : nullptr; p.omega = pos ? pos->omega : nullptr;
-    p.n_omega = pos ? pos->n_omega : 0; p.T = pos ? pos->T : 1;
-    if (epi == EPI_BF16_POS && (!pos || p.n_omega > 256 || N / 16 > 1536)) return set_error(h, COCR_ERR_BAD_ARG, "POS epilogue needs position tables");
+    p.n_omega = pos ? pos->n_omega : 0; p.T = pos ? pos->T : 1; p.piece_dst = pos ? pos->piece_dst : nullptr;
+    if (epi == EPI_BF16_POS && (!pos || p.n_omega > 256 || N / 16 > 1024)) return set_error(h, COCR_ERR_BAD_ARG, "POS epilogue needs position tables");
+    if (epi == EPI_BF16_GLU && (N % 32 != 0 || ldc % 8 != 0)) return set_error(h, COCR_ERR_BAD_ARG, "GLU epilogue needs N %% 32 == 0 and 16-byte aligned output rows");
     if (p.n_tiles > 1 && p.block_n % 32 != 0) return set_error(h, COCR_ERR_BAD_ARG, "block_n %d must be a multiple of 32 with several N tiles", p.block_n);
     p.x = res ? res->x : nullptr; p.alpha = res ? res->alpha : 1.f; p.init = res ? res->init : 0;
     p.gf = res ? res->gf : nullptr; p.bf = res ? res->bf : nullptr; p.g1 = res ? res->g1 : nullptr; p.b1 = res ? res->b1 : nullptr;
     if (epi == EPI_RESID && (!res || p.n_tiles != 1 || p.block_n != N || N != 8 * GEMM_RESID_NG || ldc % 4 != 0))
         return set_error(h, COCR_ERR_BAD_ARG, "residual epilogue is built for N = %d (got N=%d)", 8 * GEMM_RESID_NG, N);
+    { static const int dbg = getenv("COCR_GEMM_DBG") ? atoi(getenv("COCR_GEMM_DBG")) : 0; p.dbg = dbg; }
     int tm = 32;
     while (tm < 2 * p.block_n) tm <<= 1;
     p.tmem_cols = tm;
@@ -142,6 +151,23 @@ int launch_gemm_tc(cocr_handle *h, int epi, const bf16 *A, int lda, const bf16 *
     const double flops = 2.0 * M * (double)N * K;
     const double bytes = 2.0 * ((double)M * K + (double)N * K) + (epi == EPI_ARGMAX ? 8.0 * M : (epi == EPI_F32 ? 4.0 : 2.0) * (double)M * N);
     ProfScope ps(h, tag, st, flops, bytes);
+    // COCR_GEMM_TRACE=<tag>:<file>: the 5th launch with that tag writes a (role, tag, clock) trace of CTA 0
+    p.trace = nullptr;
+    long long *trace_dev = nullptr;
+    const char *trace_file = nullptr;
+    {
+        static int seen = 0;
+        const char *spec = getenv("COCR_GEMM_TRACE");
+        if (spec) {
+            const char *colon = strchr(spec, ':');
+            if (colon && strncmp(spec, tag, (size_t)(colon - spec)) == 0 && strlen(tag) == (size_t)(colon - spec) && ++seen == 5) {
+                COCR_CUDA(h, cudaMalloc((void **)&trace_dev, (size_t)3 * GEMM_TRACE_EVENTS * 16));
+                COCR_CUDA(h, cudaMemset(trace_dev, 0, (size_t)3 * GEMM_TRACE_EVENTS * 16));
+                p.trace = trace_dev;
+                trace_file = colon + 1;
+            }
+        }
+    }
 #define COCR_GEMM_CASE(E)                                                                                              \
     case E: {                                                                                                          \
         static int attr_smem = 0;                                                                                      \
@@ -159,16 +185,38 @@ int launch_gemm_tc(cocr_handle *h, int epi, const bf16 *A, int lda, const bf16 *
         COCR_GEMM_CASE(EPI_ARGMAX)
         COCR_GEMM_CASE(EPI_BF16_POS)
         COCR_GEMM_CASE(EPI_RESID)
+        COCR_GEMM_CASE(EPI_BF16_GLU)
         default: return set_error(h, COCR_ERR_BAD_ARG, "unknown GEMM epilogue %d", epi);
     }
 #undef COCR_GEMM_CASE
     COCR_LAUNCHED(h);
+    if (trace_dev) {
+        COCR_CUDA(h, cudaStreamSynchronize(st));
+        std::vector<long long> hb((size_t)3 * GEMM_TRACE_EVENTS * 2);
+        COCR_CUDA(h, cudaMemcpy(hb.data(), trace_dev, hb.size() * 8, cudaMemcpyDeviceToHost));
+        cudaFree(trace_dev);
+        if (FILE *fp = fopen(trace_file, "w")) {
+            for (int role = 0; role < 3; ++role)
+                for (int e = 0; e < GEMM_TRACE_EVENTS; ++e)
+                    if (hb[((size_t)role * GEMM_TRACE_EVENTS + e) * 2]) fprintf(fp, "%d %lld %lld\n", role, hb[((size_t)role * GEMM_TRACE_EVENTS + e) * 2], hb[((size_t)role * GEMM_TRACE_EVENTS + e) * 2 + 1]);
+            fclose(fp);
+        }
+    }
     return COCR_OK;
 }
 
 // ------------------------------------------------------------------------------------------
 // memory-bound row kernels of the bf16 path
 // ------------------------------------------------------------------------------------------
+__global__ void k_scale_bf16(bf16 *p, size_t n, float s) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = __float2bfloat16_rn(__bfloat162float(p[i]) * s);
+}
+__global__ void k_scale_f32(float *p, size_t n, float s) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] *= s;
+}
+
 __global__ void k_f32_to_bf16(const float *__restrict__ src, bf16 *__restrict__ dst, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -401,10 +449,52 @@ static int pack_attention(cocr_handle *h) {
             }
         }
     }
+    // GEMM column order: a permutation of the 32-column pieces of the layout above.  A 256-column tile is drained by
+    // two warps per lane quarter taking alternate pieces (even / odd).  For the default spec the pieces are arranged so
+    // that (a) the rotated pieces a warp sees in a tile use the SAME 16 frequency pairs (angles evaluated once per
+    // tile and warp instead of once per piece) and (b) every tile carries the same mix of rotated and plain pieces, so
+    // the CTAs (one N tile each) finish together:
+    //   tiles 0..3 (pair block j): even = [main j head 0, main j head 1, q+u head j, K head j (first half)]
+    //                              odd  = [main j head 2, main j head 3, V piece 2j, V piece 2j+1]
+    //   tile 4:                    even = K second halves (E-tail fill) of heads 0..3, odd = [q+u rest | a~ tail] of heads 0..3
+    const int npieces = nx / 32;
+    std::vector<int16_t> pdst(npieces);
+    for (int i = 0; i < npieces; ++i) pdst[i] = (int16_t)i;
+    if (qc == 192 && nh == 4 && !getenv("COCR_QKVX_NO_PERMUTE")) {
+        for (int j = 0; j < 4; ++j) {
+            int16_t *t = &pdst[8 * j];
+            t[0] = (int16_t)(6 * 0 + 2 + j); t[2] = (int16_t)(6 * 1 + 2 + j); t[4] = (int16_t)(6 * j); t[6] = (int16_t)(24 + 2 * j);
+            t[1] = (int16_t)(6 * 2 + 2 + j); t[3] = (int16_t)(6 * 3 + 2 + j); t[5] = (int16_t)(32 + 2 * j); t[7] = (int16_t)(33 + 2 * j);
+        }
+        for (int hd = 0; hd < 4; ++hd) {
+            pdst[32 + 2 * hd] = (int16_t)(24 + 2 * hd + 1);
+            pdst[32 + 2 * hd + 1] = (int16_t)(6 * hd + 1);
+        }
+        std::vector<int> seen(npieces, 0);
+        for (int i = 0; i < npieces; ++i) seen[pdst[i]]++;
+        for (int i = 0; i < npieces; ++i)
+            if (seen[i] != 1) return set_error(h, COCR_ERR_STATE, "internal: QKVX column permutation is not a bijection");
+    }
+    {
+        std::vector<uint16_t> W2(W.size());
+        std::vector<float> B2(Bv.size());
+        std::vector<int16_t> meta2(meta.size());
+        for (int l = 0; l < L; ++l)
+            for (int gp = 0; gp < npieces; ++gp) {
+                const int dp = pdst[gp];
+                memcpy(&W2[((size_t)l * nx + gp * 32) * d], &W[((size_t)l * nx + dp * 32) * d], (size_t)32 * d * 2);
+                memcpy(&B2[(size_t)l * nx + gp * 32], &Bv[(size_t)l * nx + dp * 32], 32 * 4);
+            }
+        for (int gp = 0; gp < npieces; ++gp) { meta2[2 * gp] = meta[2 * pdst[gp]]; meta2[2 * gp + 1] = meta[2 * pdst[gp] + 1]; }
+        W.swap(W2); Bv.swap(B2); meta.swap(meta2);
+    }
     if (bs->w_qkvx) { cudaFree(bs->w_qkvx); bs->w_qkvx = nullptr; }
     if (bs->b_qkvx) { cudaFree(bs->b_qkvx); bs->b_qkvx = nullptr; }
     if (bs->meta) { cudaFree(bs->meta); bs->meta = nullptr; }
+    if (bs->piece_dst) { cudaFree(bs->piece_dst); bs->piece_dst = nullptr; }
     void *p = nullptr;
+    COCR_CUDA(h, cudaMalloc(&p, pdst.size() * 2)); bs->piece_dst = (int16_t *)p;
+    COCR_CUDA(h, cudaMemcpy(bs->piece_dst, pdst.data(), pdst.size() * 2, cudaMemcpyHostToDevice));
     COCR_CUDA(h, cudaMalloc(&p, W.size() * 2)); bs->w_qkvx = (bf16 *)p;
     COCR_CUDA(h, cudaMalloc(&p, Bv.size() * 4)); bs->b_qkvx = (float *)p;
     COCR_CUDA(h, cudaMalloc(&p, meta.size() * 2)); bs->meta = (int16_t *)p;
@@ -516,6 +606,58 @@ int bf16_init(cocr_handle *h) {
     k_f32_to_bf16<<<1024, 256>>>(h->arena, bs->arena, h->arena_floats);
     COCR_LAUNCHED(h);
     COCR_CUDA(h, cudaDeviceSynchronize());
+    // EPI_BF16_SILU evaluates silu(x) = h + h*tanh(h) from h = x/2: scale the FFN-up weights (bf16 mirror) and biases
+    // (this handle's fp32 arena is not used by any other kernel in bf16 mode) by 1/2 - exact
+    for (int l = 0; l < dm.L; ++l)
+        for (int f = 0; f < 2; ++f) {
+            const size_t nw = (size_t)dm.ff * dm.d;
+            k_scale_bf16<<<(unsigned)((nw + 255) / 256), 256>>>(bs->arena + (h->layers[l].ffn_w1[f] - h->arena), nw, 0.5f);
+            k_scale_f32<<<(dm.ff + 255) / 256, 256>>>(h->arena + (h->layers[l].ffn_b1[f] - h->arena), (size_t)dm.ff, 0.5f);
+        }
+    COCR_LAUNCHED(h);
+    {
+        // pw1 for the GLU epilogue (convolution.py:138-139): GEMM column 2c = value channel c, 2c+1 = gate channel d + c
+        const int d = dm.d;
+        std::vector<uint16_t> W((size_t)dm.L * 2 * d * d);
+        std::vector<float> Bv((size_t)dm.L * 2 * d);
+        for (int l = 0; l < dm.L; ++l) {
+            const std::string q = "encoder.layers." + std::to_string(l) + ".sequential.2.module.sequential.2.conv.";
+            const std::vector<float> &w = h->host_w.at(q + "weight").data, &b = h->host_w.at(q + "bias").data;
+            for (int c = 0; c < d; ++c)
+                for (int half = 0; half < 2; ++half) {
+                    const int src = half * d + c, dst = 2 * c + half;
+                    for (int k = 0; k < d; ++k) W[((size_t)l * 2 * d + dst) * d + k] = f2bf(0.5f * w[(size_t)src * d + k]);
+                    Bv[(size_t)l * 2 * d + dst] = 0.5f * b[src];
+                }
+        }
+        // depthwise taps transposed to [k][channel] with half the BatchNorm scale folded in; half shift behind them
+        const int Kt = dm.K;
+        std::vector<float> taps((size_t)dm.L * (Kt + 1) * d);
+        for (int l = 0; l < dm.L; ++l) {
+            const std::string q = "encoder.layers." + std::to_string(l) + ".sequential.2.module.sequential.";
+            const std::vector<float> &w = h->host_w.at(q + "4.conv.weight").data;
+            const std::vector<float> &gm = h->host_w.at(q + "5.weight").data, &bt = h->host_w.at(q + "5.bias").data;
+            const std::vector<float> &mu = h->host_w.at(q + "5.running_mean").data, &var = h->host_w.at(q + "5.running_var").data;
+            float *dst = taps.data() + (size_t)l * (Kt + 1) * d;
+            for (int c = 0; c < d; ++c) {
+                const float sc = gm[c] * (1.0f / sqrtf(var[c] + 1e-5f)), sh = bt[c] - mu[c] * sc;
+                for (int k = 0; k < Kt; ++k) dst[(size_t)k * d + c] = 0.5f * sc * w[(size_t)c * Kt + k];
+                dst[(size_t)Kt * d + c] = 0.5f * sh;
+            }
+        }
+        if (bs->dw_taps) { cudaFree(bs->dw_taps); bs->dw_taps = nullptr; }
+        void *pt = nullptr;
+        COCR_CUDA(h, cudaMalloc(&pt, taps.size() * 4)); bs->dw_taps = (float *)pt;
+        COCR_CUDA(h, cudaMemcpy(bs->dw_taps, taps.data(), taps.size() * 4, cudaMemcpyHostToDevice));
+        if (bs->w_pw1g) { cudaFree(bs->w_pw1g); bs->w_pw1g = nullptr; }
+        if (bs->b_pw1g) { cudaFree(bs->b_pw1g); bs->b_pw1g = nullptr; }
+        void *pp = nullptr;
+        COCR_CUDA(h, cudaMalloc(&pp, W.size() * 2)); bs->w_pw1g = (bf16 *)pp;
+        COCR_CUDA(h, cudaMalloc(&pp, Bv.size() * 4)); bs->b_pw1g = (float *)pp;
+        COCR_CUDA(h, cudaMemcpy(bs->w_pw1g, W.data(), W.size() * 2, cudaMemcpyHostToDevice));
+        COCR_CUDA(h, cudaMemcpy(bs->b_pw1g, Bv.data(), Bv.size() * 4, cudaMemcpyHostToDevice));
+    }
+    COCR_CUDA(h, cudaDeviceSynchronize());
     COCR_CUDA(h, cudaDeviceGetAttribute(&bs->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     if (!get_encode()) return set_error(h, COCR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     return pack_attention(h);
@@ -528,8 +670,12 @@ void bf16_destroy(cocr_handle *h) {
     if (bs->w_qkvx) cudaFree(bs->w_qkvx);
     if (bs->b_qkvx) cudaFree(bs->b_qkvx);
     if (bs->meta) cudaFree(bs->meta);
+    if (bs->piece_dst) cudaFree(bs->piece_dst);
     if (bs->omega) cudaFree(bs->omega);
     if (bs->etab) cudaFree(bs->etab);
+    if (bs->w_pw1g) cudaFree(bs->w_pw1g);
+    if (bs->b_pw1g) cudaFree(bs->b_pw1g);
+    if (bs->dw_taps) cudaFree(bs->dw_taps);
     delete h->bf;
     h->bf = nullptr;
 }
@@ -572,29 +718,61 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
     // Residual-stream GEMMs: with encoder_dim 144 the update x += alpha*(..) and the LayerNorm feeding the next module
     // run in the GEMM epilogue (EPI_RESID); otherwise GEMM -> bf16 y -> k_resid_ln.
     const bool fused = (d == 8 * GEMM_RESID_NG) && !getenv("COCR_SPLIT_RESIDUAL");
+    // rows [r0, r0 + rows) of the residual stream; A points at the first of those rows
+    auto resid_rows = [&](const bf16 *A, int K, const float *Wf, const float *bias, float alpha, int init, const float *gf,
+                          const float *bfin, const float *g1, const float *b1, const char *tag, int r0, int rows) -> int {
+        float *xr = x + (size_t)r0 * d;
+        bf16 *xnr = xn + (size_t)r0 * d;
+        if (fused) {
+            ResidArgs ra = {xr, alpha, init, gf, bfin, g1, b1};
+            return launch_gemm_tc(h, EPI_RESID, A, K, WB(h, Wf), K, bias, xnr, d, nullptr, rows, d, K, st, 0, nullptr, tag, &ra);
+        }
+        bf16 *yr = y + (size_t)r0 * d;
+        COCR_TRY(launch_gemm_tc(h, EPI_BF16, A, K, WB(h, Wf), K, bias, yr, d, nullptr, rows, d, K, st, 0, nullptr, tag));
+        return launch_resid_ln(h, xr, yr, alpha, init, gf, bfin, g1, b1, xnr, rows, d, st);
+    };
     auto resid_gemm = [&](const bf16 *A, int K, const float *Wf, const float *bias, float alpha, int init, const float *gf,
                           const float *bfin, const float *g1, const float *b1, const char *tag) -> int {
-        if (fused) {
-            ResidArgs ra = {x, alpha, init, gf, bfin, g1, b1};
-            return launch_gemm_tc(h, EPI_RESID, A, K, WB(h, Wf), K, bias, xn, d, nullptr, M, d, K, st, 0, nullptr, tag, &ra);
+        return resid_rows(A, K, Wf, bias, alpha, init, gf, bfin, g1, b1, tag, 0, M);
+    };
+    // Optional L2-residency experiment (COCR_FFN_CHUNKS / COCR_ATT_CHUNKS = number of chunks): producer and consumer of
+    // the wide intermediates (FFN hidden M x 4d, attention operands M x nx) run on chunks of whole lines that fit L2.
+    // Default is one chunk: measured slower (12.1 vs 10.7 ms/step at 2/4 chunks), the kernels are not HBM-bound.
+    auto chunk_lines = [&](size_t bytes_per_row, const char *env) {
+        int n = 1;
+        if (const char *e = getenv(env)) n = atoi(e);
+        (void)bytes_per_row;   // measured on B200: every extra launch costs 5-10 us of ramp-up/tail, more than the L2 hits return
+        if (n < 1) n = 1;
+        return (B + n - 1) / n;                      // lines per chunk
+    };
+    const int ffn_lines = chunk_lines((size_t)dm.ff * 2, "COCR_FFN_CHUNKS");
+    auto ffn_module = [&](int l, int f, const float *gf, const float *bfin, const float *g1, const float *b1, const char *tag_down) -> int {
+        const LayerF32 &lw = h->layers[l];
+        for (int b0 = 0; b0 < B; b0 += ffn_lines) {
+            const int nb = std::min(ffn_lines, B - b0), r0 = b0 * p.T, rows = nb * p.T;
+            COCR_TRY(launch_gemm_tc(h, EPI_BF16_SILU, xn + (size_t)r0 * d, d, WB(h, lw.ffn_w1[f]), d, lw.ffn_b1[f], hb, dm.ff, nullptr, rows,
+                                    dm.ff, d, st, 0, nullptr, "gemm_ffn_up"));
+            COCR_TRY(resid_rows(hb, dm.ff, lw.ffn_w2[f], lw.ffn_b2[f], dm.ffn_factor, 0, gf, bfin, g1, b1, tag_down, r0, rows));
         }
-        COCR_TRY(launch_gemm_tc(h, EPI_BF16, A, K, WB(h, Wf), K, bias, y, d, nullptr, M, d, K, st, 0, nullptr, tag));
-        return launch_resid_ln(h, x, y, alpha, init, gf, bfin, g1, b1, xn, M, d, st);
+        return COCR_OK;
     };
     const float *g0 = dm.L > 0 ? h->layers[0].ffn_ln_g[0] : nullptr, *b0 = dm.L > 0 ? h->layers[0].ffn_ln_b[0] : nullptr;
     COCR_TRY(resid_gemm(feat, dm.feat, h->sub_wout, h->sub_bout, 1.f, 1, nullptr, nullptr, g0, b0, "gemm_sub_out"));
     for (int l = 0; l < dm.L; ++l) {
         const LayerF32 &lw = h->layers[l];
         // FFN 1 (feed_forward.py:45-55; half-step residual encoder.py:68-75) -> LayerNorm of the attention module
-        COCR_TRY(launch_gemm_tc(h, EPI_BF16_SILU, xn, d, WB(h, lw.ffn_w1[0]), d, lw.ffn_b1[0], hb, dm.ff, nullptr, M, dm.ff, d, st, 0, nullptr, "gemm_ffn_up"));
-        COCR_TRY(resid_gemm(hb, dm.ff, lw.ffn_w2[0], lw.ffn_b2[0], dm.ffn_factor, 0, nullptr, nullptr, lw.att_ln_g, lw.att_ln_b, "gemm_ffn_down"));
+        COCR_TRY(ffn_module(l, 0, nullptr, nullptr, lw.att_ln_g, lw.att_ln_b, "gemm_ffn_down"));
         // MHSA (attention.py:72-151)
         if (tc_attn) {
             Bf16State *bs = h->bf;
-            PosArgs pa = {bs->meta, bs->omega, d / 2, p.T};
-            COCR_TRY(launch_gemm_tc(h, EPI_BF16_POS, xn, d, bs->w_qkvx + (size_t)l * bs->nx * d, d, bs->b_qkvx + (size_t)l * bs->nx, hb,
-                                    bs->nx, nullptr, M, bs->nx, d, st, 0, &pa, "gemm_qkvx_pos"));
-            COCR_TRY(launch_attn_tc(h, hb, lens_dev, g, B, p.T, st));
+            PosArgs pa = {bs->meta, bs->omega, d / 2, p.T, bs->piece_dst};
+            const int att_lines = chunk_lines((size_t)bs->nx * 2, "COCR_ATT_CHUNKS");
+            for (int b0 = 0; b0 < B; b0 += att_lines) {
+                const int nb = std::min(att_lines, B - b0), r0 = b0 * p.T, rows = nb * p.T;
+                COCR_TRY(launch_gemm_tc(h, EPI_BF16_POS, xn + (size_t)r0 * d, d, bs->w_qkvx + (size_t)l * bs->nx * d, d,
+                                        bs->b_qkvx + (size_t)l * bs->nx, hb, bs->nx, nullptr, rows, bs->nx, d, st, 0, &pa, "gemm_qkvx_pos"));
+                COCR_TRY(launch_attn_tc(h, hb, lens_dev ? lens_dev + b0 : nullptr, g + (size_t)r0 * d, nb, p.T, st));
+            }
         } else {
             COCR_TRY(launch_gemm_tc(h, EPI_BF16, xn, d, WB(h, lw.w_qkv), d, lw.b_qkv, hb, 3 * d, nullptr, M, 3 * d, d, st, 0, nullptr, "gemm_qkv"));
             COCR_TRY(launch_attn_simt_bf16(h, hb, h->pos_proj + (size_t)l * (2 * p.T - 1) * d, lw.u_bias, lw.v_bias, lens_dev, g,
@@ -602,16 +780,26 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
         }
         COCR_TRY(resid_gemm(g, d, lw.w_out, lw.b_out, 1.f, 0, nullptr, nullptr, lw.conv_ln_g, lw.conv_ln_b, "gemm_attn_out"));
         // convolution module (convolution.py:135-148)
-        COCR_TRY(launch_gemm_tc(h, EPI_BF16, xn, d, WB(h, lw.w_pw1), d, lw.b_pw1, hb, 2 * d, nullptr, M, 2 * d, d, st, 0, nullptr, "gemm_pw1"));
-        int rc_dw = launch_glu_dw_fast(h, hb, lw, g, B, p.T, st);
-        if (rc_dw == COCR_ERR_UNSUPPORTED) rc_dw = launch_glu_dw_bf16(h, hb, lw, g, B, p.T, st);
+        int rc_dw = COCR_ERR_UNSUPPORTED;
+        if (d % 16 == 0) {
+            // pointwise conv 1 with the GLU in its epilogue (value, gate interleaved) -> depthwise conv + BatchNorm + SiLU
+            Bf16State *bs = h->bf;
+            COCR_TRY(launch_gemm_tc(h, EPI_BF16_GLU, xn, d, bs->w_pw1g + (size_t)l * 2 * d * d, d, bs->b_pw1g + (size_t)l * 2 * d, hb, d,
+                                    nullptr, M, 2 * d, d, st, 0, nullptr, "gemm_pw1_glu"));
+            const float *taps = bs->dw_taps + (size_t)l * (dm.K + 1) * d;
+            rc_dw = launch_dw_fast(h, hb, taps, taps + (size_t)dm.K * d, g, B, p.T, st);
+        }
+        if (rc_dw == COCR_ERR_UNSUPPORTED) {
+            COCR_TRY(launch_gemm_tc(h, EPI_BF16, xn, d, WB(h, lw.w_pw1), d, lw.b_pw1, hb, 2 * d, nullptr, M, 2 * d, d, st, 0, nullptr, "gemm_pw1"));
+            rc_dw = launch_glu_dw_fast(h, hb, lw, g, B, p.T, st);
+            if (rc_dw == COCR_ERR_UNSUPPORTED) rc_dw = launch_glu_dw_bf16(h, hb, lw, g, B, p.T, st);
+        }
         if (rc_dw != COCR_OK) return rc_dw;
         COCR_TRY(resid_gemm(g, d, lw.w_pw2, lw.b_pw2, 1.f, 0, nullptr, nullptr, lw.ffn_ln_g[1], lw.ffn_ln_b[1], "gemm_pw2"));
         // FFN 2 + block-final LayerNorm (encoder.py:91-99) + next block's first LayerNorm
-        COCR_TRY(launch_gemm_tc(h, EPI_BF16_SILU, xn, d, WB(h, lw.ffn_w1[1]), d, lw.ffn_b1[1], hb, dm.ff, nullptr, M, dm.ff, d, st, 0, nullptr, "gemm_ffn_up"));
         const float *ng = (l + 1 < dm.L) ? h->layers[l + 1].ffn_ln_g[0] : nullptr;
         const float *nb = (l + 1 < dm.L) ? h->layers[l + 1].ffn_ln_b[0] : nullptr;
-        COCR_TRY(resid_gemm(hb, dm.ff, lw.ffn_w2[1], lw.ffn_b2[1], dm.ffn_factor, 0, lw.final_ln_g, lw.final_ln_b, ng, nb, "gemm_ffn_down_final"));
+        COCR_TRY(ffn_module(l, 1, lw.final_ln_g, lw.final_ln_b, ng, nb, "gemm_ffn_down_final"));
     }
     return COCR_OK;
 }
@@ -662,7 +850,7 @@ __global__ void k_ref_gemm(const bf16 *A, const bf16 *W, const float *bias, floa
     float acc = 0.f;
     for (int k = 0; k < K; ++k) acc = fmaf(__bfloat162float(A[(int64_t)m * K + k]), __bfloat162float(W[(int64_t)n * K + k]), acc);
     acc += bias[n];
-    if (silu) acc = acc / (1.0f + expf(-acc));
+    if (silu) acc = 2.0f * acc / (1.0f + expf(-2.0f * acc));   // the SiLU epilogue receives x/2
     C[idx] = acc;
 }
 

@@ -180,6 +180,8 @@ int launch_layernorm(cocr_handle *h, const float *x, float *y, const float *g, c
 // ---- optimised memory-bound kernels (mem_kernels.cu); return COCR_ERR_UNSUPPORTED when the geometry is not covered
 int launch_glu_dw_fast(cocr_handle *h, const __nv_bfloat16 *u, const LayerF32 &lw, __nv_bfloat16 *g, int B, int T,
                        cudaStream_t st);
+int launch_dw_fast(cocr_handle *h, const __nv_bfloat16 *x, const float *taps_dev, const float *hshift_dev, __nv_bfloat16 *g, int B, int T,
+                   cudaStream_t st);
 int launch_frontend_fused(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, int B, int W,
                           __nv_bfloat16 *feat, cudaStream_t st);
 

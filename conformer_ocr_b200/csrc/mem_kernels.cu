@@ -117,6 +117,127 @@ int launch_glu_dw_fast(cocr_handle *h, const bf16 *u, const LayerF32 &lw, bf16 *
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// conv module middle when the GLU already ran in the pw1 GEMM epilogue: x (B,T,d) bf16 -> depthwise conv (K taps,
+// zero padding at the line ends) -> folded BatchNorm -> SiLU -> g (B,T,d) bf16.  One CTA = DWF_TT frames of one line;
+// the input rows (with halo) are staged in shared memory with 16-byte copies, thread = (channel pair, DWF_SEG frames),
+// the K-tap window slides through registers and both channels of a pair share one packed FFMA2 per tap.
+// BatchNorm's scale is folded into the taps when they are staged.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 dw_ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)),
+        "l"(*reinterpret_cast<unsigned long long *>(&c)));
+    return *reinterpret_cast<float2 *>(&r);
+}
+__device__ __forceinline__ float dw_tanh(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Persistent: each CTA stages the (pre-scaled, pre-transposed) taps once and walks over (line, time tile) items; the rows
+// of the next item stream into the other shared-memory buffer with cp.async (zero fill outside the line) while the
+// current item is computed.
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    const int n = valid ? 16 : 0;                            // src-size 0: the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int K>
+__global__ void __launch_bounds__(576)
+k_dw_fast(const bf16 *__restrict__ x, const float2 *__restrict__ taps /* [K][P] w*scale/2 */, const float2 *__restrict__ hshift /* [P] */,
+          bf16 *__restrict__ g, int T, int d, int n_tt, int n_items) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    const int P = d >> 1;                                   // channel pairs
+    constexpr int ROWS = DWF_TT + K - 1;
+    constexpr int pad = (K - 1) / 2;
+    float2 *ws = reinterpret_cast<float2 *>(sm_raw);        // [K][P]
+    uint32_t *xs0 = reinterpret_cast<uint32_t *>(ws + K * P);   // 2 x [ROWS][P] bf16x2
+    const int nthr = blockDim.x;
+    const int c8n = d >> 3;                                 // 16-byte chunks per row
+    auto stage = [&](int item, int buf) {
+        const int b = item / n_tt, t0 = (item - b * n_tt) * DWF_TT;
+        uint32_t *xs = xs0 + buf * ROWS * P;
+        for (int e = threadIdx.x; e < ROWS * c8n; e += nthr) {
+            const int row = e / c8n, c8 = e - row * c8n;
+            const int t = t0 - pad + row;
+            const bool ok = t >= 0 && t < T;
+            cp_async16(xs + row * P + c8 * 4, x + ((int64_t)b * T + (ok ? t : 0)) * d + c8 * 8, ok);
+        }
+        cp_async_commit();
+    };
+    int item = blockIdx.x;
+    if (item < n_items) stage(item, 0);
+    for (int e = threadIdx.x; e < K * P; e += nthr) ws[e] = taps[e];
+    const int pr = threadIdx.x % P, seg = threadIdx.x / P;
+    const float2 hs = hshift[pr];
+    int buf = 0;
+    for (; item < n_items; item += gridDim.x, buf ^= 1) {
+        cp_async_wait<0>();
+        __syncthreads();                                    // rows of `item` visible; everyone is done with the other buffer
+        if (item + (int)gridDim.x < n_items) stage(item + gridDim.x, buf ^ 1);
+        if (seg * DWF_SEG < DWF_TT) {
+            const int b = item / n_tt, t0 = (item - b * n_tt) * DWF_TT;
+            const uint32_t *xs = xs0 + buf * ROWS * P;
+            float2 xw[DWF_SEG + K - 1];
+#pragma unroll
+            for (int i = 0; i < DWF_SEG + K - 1; ++i) xw[i] = bf2_to_f2(xs[(seg * DWF_SEG + i) * P + pr]);
+            float2 acc[DWF_SEG];
+#pragma unroll
+            for (int i = 0; i < DWF_SEG; ++i) acc[i] = hs;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float2 w = ws[k * P + pr];
+#pragma unroll
+                for (int i = 0; i < DWF_SEG; ++i) {
+#ifndef COCR_DW_SCALAR
+                    acc[i] = dw_ffma2(w, xw[i + k], acc[i]);
+#else
+                    acc[i].x = fmaf(w.x, xw[i + k].x, acc[i].x);
+                    acc[i].y = fmaf(w.y, xw[i + k].y, acc[i].y);
+#endif
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < DWF_SEG; ++i) {
+                const int t = t0 + seg * DWF_SEG + i;
+                if (t < T) {
+                    const float2 hh = acc[i];
+                    const float2 r = dw_ffma2(hh, make_float2(dw_tanh(hh.x), dw_tanh(hh.y)), hh);
+                    *reinterpret_cast<uint32_t *>(g + ((int64_t)b * T + t) * d + 2 * pr) = f2_to_bf2(r.x, r.y);
+                }
+            }
+        }
+    }
+}
+
+// taps_dev: [K][P] float2 = w * bn_scale / 2 ; hshift_dev: [P] float2 = bn_shift / 2  (packed once per layer at load)
+int launch_dw_fast(cocr_handle *h, const bf16 *x, const float *taps_dev, const float *hshift_dev, bf16 *g, int B, int T, cudaStream_t st) {
+    const Dims &dm = h->dm;
+    const int P = dm.d / 2;
+    const int nthr = P * (DWF_TT / DWF_SEG);
+    if (dm.K != 31 || (dm.d & 7) != 0 || nthr > 576 || !taps_dev) return COCR_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)2 * (DWF_TT + 30) * P * 4 + (size_t)31 * P * 8;
+    static bool attr = false;
+    if (!attr) {
+        COCR_CUDA(h, cudaFuncSetAttribute(k_dw_fast<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    const int n_tt = (T + DWF_TT - 1) / DWF_TT, n_items = n_tt * B;
+    int grid = 2 * h->num_sms;
+    if (grid > n_items) grid = n_items;
+    ProfScope ps(h, "dwconv_bn_silu_bf16", st, 2.0 * 31 * B * (double)T * dm.d, 4.0 * B * T * dm.d);
+    k_dw_fast<31><<<grid, nthr, smem, st>>>(x, reinterpret_cast<const float2 *>(taps_dev), reinterpret_cast<const float2 *>(hshift_dev), g, T, dm.d,
+                                            n_tt, n_items);
+    COCR_LAUNCHED(h);
+    return COCR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // fused subsampling front-end for 32 conv channels (lane = channel).  One CTA = FE_TT output frames of one line.
 //   stage A: input patch (H x (4*TT+3)) -> shared (zero padded)
 //   stage B: conv1+ReLU  -> a1 tile [(2*TT+1)][F2][32] bf16 in shared; warp = one t2 row, lane = channel,

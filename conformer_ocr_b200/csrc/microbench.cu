@@ -1,0 +1,138 @@
+// Micro-benchmarks of the tensor pipe (cocr_selftest which = 40): cycles of a chain of tcgen05.mma instructions for a
+// given N, number of independent accumulators the chain alternates between, and A operand source (shared / tensor memory).
+#include "common.h"
+#include "tc_utils.cuh"
+
+namespace cocr {
+
+__global__ void __launch_bounds__(128, 1) k_mma_bench(int N, int chains, int a_tmem, int count, long long *out) {
+    using namespace tc;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (64 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(&slot, 512);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = slot;
+    if (warp == 1) {
+        const uint32_t idesc = make_idesc_bf16(128, N);
+        const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem + 16384);
+        long long t0 = 0, t1 = 0;
+        for (int rep = 0; rep < 3; ++rep) {
+            t0 = clock64();
+            if (elect_one()) {
+                for (int i = 0; i < count; ++i) {
+                    const uint32_t d = tb + (uint32_t)((i % chains) * N);
+                    const uint64_t bd = make_smem_desc_sw128(b_base + (i & 3) * 32, 1024);
+                    if (a_tmem) umma_bf16_ts(d, tb + 448u + (uint32_t)((i & 3) * 8), bd, idesc, i >= chains ? 1u : 0u);
+                    else umma_bf16_ss(d, make_smem_desc_sw128(a_base + (i & 3) * 32, 1024), bd, idesc, i >= chains ? 1u : 0u);
+                }
+                umma_commit(&bar);
+            }
+            __syncwarp();
+            mbar_wait(&bar, rep & 1);
+            t1 = clock64();
+        }
+        if (threadIdx.x == 32) out[0] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tb, 512); }
+}
+
+// TMEM read bandwidth: 8 warps (two per lane quarter) loop over tcgen05.ld 32x32b.x32 (4 KB per warp-load), `depth`
+// loads in flight per warp; optionally warp 8 keeps the tensor pipe busy with N=256 MMAs into other columns.
+__global__ void __launch_bounds__(320, 1) k_tmem_ld_bench(int iters, int depth, int with_mma, int shape, long long *out) {
+    using namespace tc;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    __shared__ volatile int stop;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (64 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); stop = 0; }
+    if (warp == 9) tmem_alloc(&slot, 512);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = slot;
+    if (warp < 8) {
+        const uint32_t base = tb + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
+        uint32_t acc = 0;
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            uint32_t a[32], b[32];
+            if (shape == 0) {
+                tmem_ld_32x32b_x32(base, a);
+                if (depth > 1) tmem_ld_32x32b_x32(base + 32, b);
+            } else {
+                tmem_ld_16x256b_x8(base, a);
+                if (depth > 1) tmem_ld_16x256b_x8(base + ((uint32_t)16 << 16), b);
+            }
+            tmem_ld_wait_dep(a);
+            if (depth > 1) tmem_ld_wait_dep(b);
+            acc ^= a[0] ^ a[31];
+            if (depth > 1) acc ^= b[0] ^ b[31];
+        }
+        const long long t1 = clock64();
+        if (acc == 0x12345u) out[7] = acc;
+        if (threadIdx.x == 0) { out[0] = t1 - t0; stop = 1; }
+    } else if (warp == 8 && with_mma) {
+        const uint32_t idesc = make_idesc_bf16(128, 256);
+        const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem + 16384);
+        int n = 0;
+        while (!stop) {
+            if (elect_one()) {
+                for (int i = 0; i < 8; ++i)
+                    umma_bf16_ss(tb + 256u, make_smem_desc_sw128(a_base + (i & 3) * 32, 1024), make_smem_desc_sw128(b_base + (i & 3) * 32, 1024), idesc, 1u);
+                umma_commit(&bar);
+            }
+            __syncwarp();
+            mbar_wait(&bar, n & 1);
+            ++n;
+        }
+        if (lane == 0) out[1] = n;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) { tc_fence_after(); tmem_dealloc(tb, 512); }
+}
+
+int selftest_tmem_bench(int device, int depth, int with_mma, int shape, double *bytes_per_cycle) {
+    const int iters = 2000;
+    long long *d = nullptr, hres[8] = {0};
+    cudaMalloc((void **)&d, 64);
+    cudaMemset(d, 0, 64);
+    cudaFuncSetAttribute(k_tmem_ld_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    k_tmem_ld_bench<<<1, 320, 64 * 1024>>>(iters, depth, with_mma, shape, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(d); return set_error(nullptr, COCR_ERR_CUDA, "tmem bench: %s", cudaGetErrorString(e)); }
+    cudaMemcpy(hres, d, 64, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    const double bytes = 8.0 * iters * (depth > 1 ? 2 : 1) * 4096.0;
+    if (bytes_per_cycle) *bytes_per_cycle = bytes / (double)hres[0];
+    return COCR_OK;
+}
+
+int selftest_mma_bench(int device, int N, int chains, int a_tmem, double *cycles_per_mma) {
+    const int count = 64;
+    if (N < 16 || N > 256 || N % 16 || chains < 1 || chains * N > 448) return set_error(nullptr, COCR_ERR_BAD_ARG, "bad microbench shape");
+    long long *d = nullptr, hres = 0;
+    cudaMalloc((void **)&d, 8);
+    cudaFuncSetAttribute(k_mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    k_mma_bench<<<1, 128, 64 * 1024>>>(N, chains, a_tmem, count, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(d); return set_error(nullptr, COCR_ERR_CUDA, "mma bench: %s", cudaGetErrorString(e)); }
+    cudaMemcpy(&hres, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (cycles_per_mma) *cycles_per_mma = (double)hres / count;
+    return COCR_OK;
+}
+
+}  // namespace cocr
