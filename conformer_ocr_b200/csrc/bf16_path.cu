@@ -175,7 +175,7 @@ int launch_gemm_tc(cocr_handle *h, int epi, const bf16 *A, int lda, const bf16 *
             COCR_CUDA(h, cudaFuncSetAttribute(k_gemm_tc<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget)); \
             attr_smem = (int)budget;                                                                                   \
         }                                                                                                              \
-        k_gemm_tc<E><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, p);                                                  \
+        k_gemm_tc<E><<<grid, gemm_threads(E), smem, st>>>(tmA, tmB, tmC, p);                                                  \
         break;                                                                                                         \
     }
     switch (epi) {

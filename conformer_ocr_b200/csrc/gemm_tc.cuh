@@ -81,19 +81,24 @@ constexpr int GEMM_TRACE_EVENTS = 1024;    // per role: 0 epilogue warp 0, 1 MMA
         }                                                                                         \
     } while (0)
 
-constexpr int GEMM_NE = 8;                          // epilogue warps
-constexpr int GEMM_THREADS = 64 + 32 * GEMM_NE;
+// epilogue warps: the thread-per-row bf16 epilogues are chains of dependent latencies (TMEM load -> math -> staging ->
+// proxy fence -> TMA store), so they run 16 warps (4 per scheduler, <= 112 registers) to overlap them.  The residual
+// epilogue keeps 8 warps: with 16 (and 96 registers) it spilled and measured slower - it is bound by the number of
+// 32-byte sector requests its fragment-layout loads/stores generate, not by latency.
+__host__ __device__ constexpr bool gemm_row_pieces(int epi) { return epi == 0 || epi == 1 || epi == 4 || epi == 6; }
+__host__ __device__ constexpr int gemm_ne(int epi) { return gemm_row_pieces(epi) ? 16 : 8; }
+__host__ __device__ constexpr int gemm_threads(int epi) { return 64 + 32 * gemm_ne(epi); }
+__host__ __device__ constexpr int gemm_nstg(int epi) { return gemm_row_pieces(epi) ? 2 : 4; }     // staging tiles per warp
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_KC = 64;                       // k-chunk (elements) = one 128-byte swizzle span of bf16
 constexpr int GEMM_RESID_NG = 18;                 // EPI_RESID: 8-column groups per row (encoder_dim 144)
 constexpr uint32_t GEMM_A_CHUNK = GEMM_BM * 128;  // bytes of one A k-chunk tile
 constexpr uint32_t GEMM_STAGE_BYTES = 2048;       // one staging tile: 32 rows x 64 B (32 bf16 / 16 fp32 columns)
-constexpr int GEMM_NSTG = 4;                      // staging tiles per epilogue warp
 constexpr uint32_t GEMM_MISC_SMEM = 2 * 256 * 4 + 4 * 256 * 4 + 512 + 1024;   // bias, LayerNorm / position tables, barriers, slack
 
 __host__ __device__ inline uint32_t gemm_b_chunk_bytes(int block_n) { return (uint32_t)block_n * 128u; }
 __host__ __device__ inline uint32_t gemm_fixed_smem(int epi) {
-    return GEMM_MISC_SMEM + (epi == EPI_RESID ? 0u : (uint32_t)GEMM_NE * GEMM_NSTG * GEMM_STAGE_BYTES);
+    return GEMM_MISC_SMEM + (epi == EPI_RESID ? 0u : (uint32_t)(gemm_ne(epi) * gemm_nstg(epi)) * GEMM_STAGE_BYTES);
 }
 
 // orderable key: larger float -> larger key; among equal floats the LOWER column index wins
@@ -144,7 +149,7 @@ __device__ __forceinline__ uint32_t stg64_offset(uint32_t row, uint32_t chunk) {
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads(EPI), 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmC, const GemmArgs p) {
     using namespace tc;
@@ -153,6 +158,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // generic LD/ST and a full MEMBAR.ALL.CTA in front of every fence.proxy.async.
     extern __shared__ __align__(1024) uint8_t smem[];
 
+    constexpr int GEMM_NE = gemm_ne(EPI), GEMM_THREADS = gemm_threads(EPI), GEMM_NSTG = gemm_nstg(EPI);
     constexpr bool kTmaStore = (EPI == EPI_BF16 || EPI == EPI_BF16_SILU || EPI == EPI_BF16_POS);
     constexpr bool kRowPieces = kTmaStore || EPI == EPI_BF16_GLU;      // thread = row, 32-column pieces, TMEM loads one ahead
     constexpr uint32_t kStagingBytes = (EPI == EPI_RESID) ? 0u : (uint32_t)GEMM_NE * GEMM_NSTG * GEMM_STAGE_BYTES;
@@ -309,8 +315,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // ================= epilogue =================
         const int ew = warp - 2;                         // 0 .. NE-1
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
-        const int half = ew >> 2;                        // which of the two warps of the quarter
-        constexpr int NSH = GEMM_NE / 4;                 // warps sharing one lane quarter (2)
+        const int half = ew >> 2;                        // which of the NSH warps of the quarter
+        constexpr int NSH = GEMM_NE / 4;                 // warps sharing one lane quarter
         const int et = ew * 32 + lane;                   // 0 .. 32*NE-1
         uint8_t *stage_base = staging + (uint32_t)ew * GEMM_NSTG * GEMM_STAGE_BYTES;
         const int npieces = (p.block_n + 31) / 32;       // 32-column pieces
@@ -376,23 +382,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         }
                     };
 #pragma unroll
-                    for (int blk = 0; blk < 2; ++blk) {
-                        uint32_t t0[32];
-                        tmem_ld_16x256b_x8(taddr + 64u * blk, t0);
-                        tmem_ld_wait_dep(t0);
-#pragma unroll
-                        for (int gg = 0; gg < 8; ++gg)
-                            combine(8 * blk + gg, __uint_as_float(t0[4 * gg]), __uint_as_float(t0[4 * gg + 1]), __uint_as_float(t0[4 * gg + 2]),
-                                    __uint_as_float(t0[4 * gg + 3]));
-                    }
-                    {
+                    for (int blk = 0; blk < NG / 2; ++blk) {              // 16 columns (two groups) per load keeps the live set small
                         uint32_t t1[8];
-                        tmem_ld_16x256b_x2(taddr + 128u, t1);
+                        tmem_ld_16x256b_x2(taddr + 16u * blk, t1);
                         tmem_ld_wait_dep(t1);
-                        if (hh == 1) release_acc();
+                        if (blk == NG / 2 - 1 && hh == 1) release_acc();
 #pragma unroll
                         for (int gg = 0; gg < 2; ++gg)
-                            combine(16 + gg, __uint_as_float(t1[4 * gg]), __uint_as_float(t1[4 * gg + 1]), __uint_as_float(t1[4 * gg + 2]),
+                            combine(2 * blk + gg, __uint_as_float(t1[4 * gg]), __uint_as_float(t1[4 * gg + 1]), __uint_as_float(t1[4 * gg + 2]),
                                     __uint_as_float(t1[4 * gg + 3]));
                     }
                     GEMM_TRACE(0, 430 + hh);
@@ -475,11 +472,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 tc_fence_after();
                 float tf = 0.0f;
                 if constexpr (EPI == EPI_BF16_POS) tf = (float)((grow0 + lane) % p.T);
-                // (sin, cos) of this thread's frame for the 2 x 8 pairs of a piece; the column permutation makes the pieces
-                // a warp handles in one tile reuse them (one evaluation per tile instead of one per head)
-                float c_sn[16], c_cs[16];
-                int c_base[2] = {-1, -1};
-                uint32_t ra[32], rb[32];
+                uint32_t ra[32];
                 auto issue = [&](int k, uint32_t (&r)[32]) {
                     const int c0 = (half + NSH * k) * 32;
                     if (p.block_n - c0 >= 32) tmem_ld_32x32b_x32(t_row + (uint32_t)c0, r);
@@ -500,7 +493,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         f2[2 * e4] = fadd2(make_float2(__uint_as_float(r[4 * e4]), __uint_as_float(r[4 * e4 + 1])), make_float2(b4.x, b4.y));
                         f2[2 * e4 + 1] = fadd2(make_float2(__uint_as_float(r[4 * e4 + 2]), __uint_as_float(r[4 * e4 + 3])), make_float2(b4.z, b4.w));
                     }
-                    GEMM_TRACE(0, 330);
                     if constexpr (EPI == EPI_BF16_POS) {
                         // rotation / fill of the positional columns by the angle of this thread's frame
 #pragma unroll
@@ -509,24 +501,19 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             const int kind = meta >> 12;                   // warp-uniform
                             if (kind != 0 && !(p.dbg & 2)) {
                                 const int pbase = meta & 0xFFF;            // multiple of 4 (16-byte aligned omega reads)
-                                if (c_base[g] != pbase) {                  // warp-uniform
-                                    c_base[g] = pbase;
 #pragma unroll
-                                    for (int u4 = 0; u4 < 2; ++u4) {
-                                        const float4 om = *reinterpret_cast<const float4 *>(somega + pbase + 4 * u4);
-                                        __sincosf(tf * om.x, &c_sn[g * 8 + u4 * 4 + 0], &c_cs[g * 8 + u4 * 4 + 0]);
-                                        __sincosf(tf * om.y, &c_sn[g * 8 + u4 * 4 + 1], &c_cs[g * 8 + u4 * 4 + 1]);
-                                        __sincosf(tf * om.z, &c_sn[g * 8 + u4 * 4 + 2], &c_cs[g * 8 + u4 * 4 + 2]);
-                                        __sincosf(tf * om.w, &c_sn[g * 8 + u4 * 4 + 3], &c_cs[g * 8 + u4 * 4 + 3]);
+                                for (int u4 = 0; u4 < 2; ++u4) {
+                                    const float4 om = *reinterpret_cast<const float4 *>(somega + pbase + 4 * u4);
+                                    const float omv[4] = {om.x, om.y, om.z, om.w};
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        float sn, cs;
+                                        __sincosf(tf * omv[u], &sn, &cs);
+                                        float2 &v = f2[g * 8 + u4 * 4 + u];
+                                        const float as = v.x, ac = v.y;
+                                        if (kind == 1) v = make_float2(fmaf(as, sn, ac * cs), fmaf(ac, sn, -as * cs));
+                                        else v = make_float2(cs, sn);
                                     }
-                                }
-#pragma unroll
-                                for (int u = 0; u < 8; ++u) {
-                                    const float sn = c_sn[g * 8 + u], cs = c_cs[g * 8 + u];
-                                    float2 &v = f2[g * 8 + u];
-                                    const float as = v.x, ac = v.y;
-                                    if (kind == 1) v = make_float2(fmaf(as, sn, ac * cs), fmaf(ac, sn, -as * cs));
-                                    else v = make_float2(cs, sn);
                                 }
                             }
                         }
@@ -555,7 +542,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         if constexpr (EPI == EPI_BF16_SILU) f2[e] = silu_from_half(f2[e]);
                         pk[e] = pack_bf16x2(f2[e].x, f2[e].y);
                     }
-                    GEMM_TRACE(0, 331);
                     uint8_t *sbuf = stage_base + (bufctr % GEMM_NSTG) * GEMM_STAGE_BYTES;
                     ++bufctr;
                     if (lane == 0 && !(p.dbg & 16)) tma_store_wait_read<GEMM_NSTG - 1>();    // the store that last used this tile has read it
@@ -580,23 +566,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     release_acc();
                     continue;
                 }
-                if (my_np > 0) issue(0, ra);
-                else release_acc();
-                for (int k = 0; k < my_np; k += 2) {
+                if (my_np == 0) release_acc();
+                for (int k = 0; k < my_np; ++k) {
+                    issue(k, ra);
                     tmem_ld_wait_dep(ra);
                     GEMM_TRACE(0, 310 + k);
-                    if (k + 1 < my_np) issue(k + 1, rb);
-                    else release_acc();
+                    if (k + 1 == my_np) release_acc();          // last TMEM read of this warp for this tile
                     process(k, ra);
                     GEMM_TRACE(0, 320 + k);
-                    if (k + 1 < my_np) {
-                        tmem_ld_wait_dep(rb);
-                        GEMM_TRACE(0, 311 + k);
-                        if (k + 2 < my_np) issue(k + 2, ra);
-                        else release_acc();
-                        process(k + 1, rb);
-                        GEMM_TRACE(0, 321 + k);
-                    }
                 }
             } else {
                 // ---- fp32 logits / fused arg-max (cold paths) ----
