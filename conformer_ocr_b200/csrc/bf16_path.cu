@@ -333,6 +333,15 @@ struct Bf16Plan {
     size_t off_a1, off_a2, off_feat, off_x, off_xn, off_y, off_h, off_g, off_best, off_best_val, off_best_idx, total;
 };
 
+// Row pitch (elements) of xn, the bf16 A operand of every K = d GEMM.  Dense by default.  COCR_XN_PAD=1 pads the pitch to
+// a multiple of 64 elements so that every 128-byte TMA box row stays inside one cache line (with d = 144 three of four
+// rows straddle two lines); measured on B200 it changes nothing (pw1 27.0 us either way), so the A stream is not bound
+// by L2 request count.
+static int xn_pitch(const cocr_handle *h) {
+    static const bool pad = getenv("COCR_XN_PAD") != nullptr;
+    return (pad && h->dm.d == 8 * GEMM_RESID_NG) ? (h->dm.d + 63) / 64 * 64 : h->dm.d;
+}
+
 static bool use_tc_attn(const cocr_handle *h) { return h->bf && h->bf->tc_attn; }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -350,7 +359,7 @@ static void bf16_plan(const cocr_handle *h, int B, int W, Bf16Plan *p) {
     p->off_a2 = take(M * dm.F * dm.cc * 4);
     p->off_feat = take(M * dm.feat * 2);
     p->off_x = take(M * dm.d * 4);
-    p->off_xn = take(M * dm.d * 2);
+    p->off_xn = take(M * (size_t)xn_pitch(h) * 2);
     p->off_y = take(M * dm.d * 2);
     size_t wide = (size_t)dm.ff > (size_t)3 * dm.d ? dm.ff : 3 * dm.d;
     if (use_tc_attn(h) && (size_t)h->bf->nx > wide) wide = h->bf->nx;
@@ -697,6 +706,7 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
     float *x = (float *)(ws + p.off_x);
     bf16 *xn = (bf16 *)(ws + p.off_xn), *y = (bf16 *)(ws + p.off_y), *hb = (bf16 *)(ws + p.off_h), *g = (bf16 *)(ws + p.off_g);
     const int M = p.M, d = dm.d;
+    const int ldx = xn_pitch(h);
 
     if (out_lens) COCR_TRY(launch_out_lens(h, widths, B, W, out_lens, st));
     const int32_t *lens_dev = nullptr;
@@ -722,10 +732,10 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
     auto resid_rows = [&](const bf16 *A, int K, const float *Wf, const float *bias, float alpha, int init, const float *gf,
                           const float *bfin, const float *g1, const float *b1, const char *tag, int r0, int rows) -> int {
         float *xr = x + (size_t)r0 * d;
-        bf16 *xnr = xn + (size_t)r0 * d;
+        bf16 *xnr = xn + (size_t)r0 * ldx;
         if (fused) {
             ResidArgs ra = {xr, alpha, init, gf, bfin, g1, b1};
-            return launch_gemm_tc(h, EPI_RESID, A, K, WB(h, Wf), K, bias, xnr, d, nullptr, rows, d, K, st, 0, nullptr, tag, &ra);
+            return launch_gemm_tc(h, EPI_RESID, A, K, WB(h, Wf), K, bias, xnr, ldx, nullptr, rows, d, K, st, 0, nullptr, tag, &ra);
         }
         bf16 *yr = y + (size_t)r0 * d;
         COCR_TRY(launch_gemm_tc(h, EPI_BF16, A, K, WB(h, Wf), K, bias, yr, d, nullptr, rows, d, K, st, 0, nullptr, tag));
@@ -750,7 +760,7 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
         const LayerF32 &lw = h->layers[l];
         for (int b0 = 0; b0 < B; b0 += ffn_lines) {
             const int nb = std::min(ffn_lines, B - b0), r0 = b0 * p.T, rows = nb * p.T;
-            COCR_TRY(launch_gemm_tc(h, EPI_BF16_SILU, xn + (size_t)r0 * d, d, WB(h, lw.ffn_w1[f]), d, lw.ffn_b1[f], hb, dm.ff, nullptr, rows,
+            COCR_TRY(launch_gemm_tc(h, EPI_BF16_SILU, xn + (size_t)r0 * ldx, ldx, WB(h, lw.ffn_w1[f]), d, lw.ffn_b1[f], hb, dm.ff, nullptr, rows,
                                     dm.ff, d, st, 0, nullptr, "gemm_ffn_up"));
             COCR_TRY(resid_rows(hb, dm.ff, lw.ffn_w2[f], lw.ffn_b2[f], dm.ffn_factor, 0, gf, bfin, g1, b1, tag_down, r0, rows));
         }
@@ -769,12 +779,12 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
             const int att_lines = chunk_lines((size_t)bs->nx * 2, "COCR_ATT_CHUNKS");
             for (int b0 = 0; b0 < B; b0 += att_lines) {
                 const int nb = std::min(att_lines, B - b0), r0 = b0 * p.T, rows = nb * p.T;
-                COCR_TRY(launch_gemm_tc(h, EPI_BF16_POS, xn + (size_t)r0 * d, d, bs->w_qkvx + (size_t)l * bs->nx * d, d,
+                COCR_TRY(launch_gemm_tc(h, EPI_BF16_POS, xn + (size_t)r0 * ldx, ldx, bs->w_qkvx + (size_t)l * bs->nx * d, d,
                                         bs->b_qkvx + (size_t)l * bs->nx, hb, bs->nx, nullptr, rows, bs->nx, d, st, 0, &pa, "gemm_qkvx_pos"));
                 COCR_TRY(launch_attn_tc(h, hb, lens_dev ? lens_dev + b0 : nullptr, g + (size_t)r0 * d, nb, p.T, st));
             }
         } else {
-            COCR_TRY(launch_gemm_tc(h, EPI_BF16, xn, d, WB(h, lw.w_qkv), d, lw.b_qkv, hb, 3 * d, nullptr, M, 3 * d, d, st, 0, nullptr, "gemm_qkv"));
+            COCR_TRY(launch_gemm_tc(h, EPI_BF16, xn, ldx, WB(h, lw.w_qkv), d, lw.b_qkv, hb, 3 * d, nullptr, M, 3 * d, d, st, 0, nullptr, "gemm_qkv"));
             COCR_TRY(launch_attn_simt_bf16(h, hb, h->pos_proj + (size_t)l * (2 * p.T - 1) * d, lw.u_bias, lw.v_bias, lens_dev, g,
                                            B, p.T, st));
         }
@@ -784,13 +794,13 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
         if (d % 16 == 0) {
             // pointwise conv 1 with the GLU in its epilogue (value, gate interleaved) -> depthwise conv + BatchNorm + SiLU
             Bf16State *bs = h->bf;
-            COCR_TRY(launch_gemm_tc(h, EPI_BF16_GLU, xn, d, bs->w_pw1g + (size_t)l * 2 * d * d, d, bs->b_pw1g + (size_t)l * 2 * d, hb, d,
+            COCR_TRY(launch_gemm_tc(h, EPI_BF16_GLU, xn, ldx, bs->w_pw1g + (size_t)l * 2 * d * d, d, bs->b_pw1g + (size_t)l * 2 * d, hb, d,
                                     nullptr, M, 2 * d, d, st, 0, nullptr, "gemm_pw1_glu"));
             const float *taps = bs->dw_taps + (size_t)l * (dm.K + 1) * d;
             rc_dw = launch_dw_fast(h, hb, taps, taps + (size_t)dm.K * d, g, B, p.T, st);
         }
         if (rc_dw == COCR_ERR_UNSUPPORTED) {
-            COCR_TRY(launch_gemm_tc(h, EPI_BF16, xn, d, WB(h, lw.w_pw1), d, lw.b_pw1, hb, 2 * d, nullptr, M, 2 * d, d, st, 0, nullptr, "gemm_pw1"));
+            COCR_TRY(launch_gemm_tc(h, EPI_BF16, xn, ldx, WB(h, lw.w_pw1), d, lw.b_pw1, hb, 2 * d, nullptr, M, 2 * d, d, st, 0, nullptr, "gemm_pw1"));
             rc_dw = launch_glu_dw_fast(h, hb, lw, g, B, p.T, st);
             if (rc_dw == COCR_ERR_UNSUPPORTED) rc_dw = launch_glu_dw_bf16(h, hb, lw, g, B, p.T, st);
         }
@@ -817,7 +827,7 @@ int bf16_logits(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_
     Bf16Plan p;
     COCR_TRY(bf16_forward(h, img, sb, sw, sh, widths, B, W, st, out_lens, p));
     const Dims &dm = h->dm;
-    return launch_gemm_tc(h, EPI_F32, (const bf16 *)(h->ws.base + p.off_xn), dm.d, WB(h, h->dec_w), dm.d, h->dec_b, logits, dm.C,
+    return launch_gemm_tc(h, EPI_F32, (const bf16 *)(h->ws.base + p.off_xn), xn_pitch(h), WB(h, h->dec_w), dm.d, h->dec_b, logits, dm.C,
                           nullptr, p.M, dm.C, dm.d, st, 0, nullptr, "gemm_logits");
 }
 
@@ -833,7 +843,7 @@ int bf16_forward_decode(cocr_handle *h, const float *img, int64_t sb, int64_t sw
     int32_t *bi = (int32_t *)(ws + p.off_best_idx);
     COCR_CUDA(h, cudaMemsetAsync(best, 0, (size_t)p.M * 8, st));
     // CTC projection fused with the per-frame arg-max: logits never reach HBM (pred.py:121 + :138-143)
-    COCR_TRY(launch_gemm_tc(h, EPI_ARGMAX, (const bf16 *)(ws + p.off_xn), dm.d, WB(h, h->dec_w), dm.d, h->dec_b, nullptr, 0, best,
+    COCR_TRY(launch_gemm_tc(h, EPI_ARGMAX, (const bf16 *)(ws + p.off_xn), xn_pitch(h), WB(h, h->dec_w), dm.d, h->dec_b, nullptr, 0, best,
                             p.M, dm.C, dm.d, st, 0, nullptr, "gemm_ctc_argmax"));
     k_unpack_best<<<(p.M + 255) / 256, 256, 0, st>>>(best, p.M, bv, bi);
     COCR_LAUNCHED(h);

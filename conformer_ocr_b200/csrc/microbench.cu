@@ -120,8 +120,9 @@ int selftest_tmem_bench(int device, int depth, int with_mma, int shape, double *
     return COCR_OK;
 }
 
-int selftest_mma_bench(int device, int N, int chains, int a_tmem, double *cycles_per_mma) {
-    const int count = 64;
+int selftest_mma_bench(int device, int N, int chains, int a_tmem_and_count, double *cycles_per_mma) {
+    const int a_tmem = a_tmem_and_count % 10;
+    const int count = a_tmem_and_count >= 10 ? a_tmem_and_count / 10 : 64;     // MMAs per commit group
     if (N < 16 || N > 256 || N % 16 || chains < 1 || chains * N > 448) return set_error(nullptr, COCR_ERR_BAD_ARG, "bad microbench shape");
     long long *d = nullptr, hres = 0;
     cudaMalloc((void **)&d, 8);

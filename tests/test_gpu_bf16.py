@@ -124,3 +124,57 @@ def test_bf16_full_width_batch(cuda_device):
     assert clear == 1.0
     sub, _ = net16(x[3:6], torch.from_numpy(lens[3:6]))
     assert torch.equal(l16[3:6], sub)
+
+
+def test_bf16_long_lines_large_alphabet(cuda_device):
+    """BASELINE config 5 shape at reduced depth: 4096-px lines (T = 1024 frames: 8 query tiles per line, the E table
+    streams with K instead of staying resident) and a 2 500-class alphabet (10 N tiles in the fused arg-max projection),
+    against the fp32 CUDA path.  Also checks that the fused decode equals the arg-max of the path's own logits."""
+    from conformer_ocr_b200 import PytorchRecognitionModel
+    hp = dict(O.DEFAULT_HPARAMS)
+    hp['num_encoder_layers'] = 3
+    C = 2500
+    w = O.make_weights(hp, C, seed=31)
+    img, lens = O.make_lines(3, 96, 4096, seed=32)
+    x = torch.from_numpy(img).to(cuda_device)
+    tl = torch.from_numpy(lens)
+    net16 = build_net(hp, C, w, cuda_device)
+    net32 = PytorchRecognitionModel(num_classes=C, codec=None, precision='fp32', **hp, **DROP)
+    net32.nn.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=False)
+    l16, ol = net16(x, tl)
+    l32, _ = net32(x, tl)
+    assert l16.shape == (3, 1024, C)
+    a, b = l16.cpu().numpy(), l32.cpu().numpy()
+    err = rel_err(a, b)
+    overall, clear, frac_clear = top1_report(a, b)
+    print(f'b3 w4096 C2500: bf16 vs fp32 rel err {err:.3e}; top-1 {overall:.4f} overall, {clear:.4f} on {frac_clear:.2%} clear frames')
+    assert err < BF16_TOL
+    assert clear == 1.0
+    got = net16.predict_labels(x, tl)
+    ref = [O.greedy_decoder(a[i, :int(ol[i])].T) for i in range(3)]
+    assert [[t[:3] for t in l] for l in got] == [[t[:3] for t in l] for l in ref]
+
+
+def test_bf16_ragged_mask_mode(cuda_device):
+    """mask_mode='ragged' on the tensor-core path: keys beyond a line's own length are excluded.  Checked against the
+    fp32 CUDA path in the same mode (itself pinned to the masked oracle), on lines whose lengths end inside a key tile,
+    exactly on a tile boundary and below one tile."""
+    from conformer_ocr_b200 import PytorchRecognitionModel
+    hp = dict(O.DEFAULT_HPARAMS)
+    hp['num_encoder_layers'] = 2
+    C = 64
+    w = O.make_weights(hp, C, seed=41)
+    widths = [1536, 1100, 1024, 512, 300, 40]
+    img, lens = O.make_lines(len(widths), 96, 1536, seed=42, widths=widths)
+    x = torch.from_numpy(img).to(cuda_device)
+    tl = torch.from_numpy(lens)
+    net16 = build_net(hp, C, w, cuda_device, mask_mode='ragged')
+    net32 = PytorchRecognitionModel(num_classes=C, codec=None, precision='fp32', mask_mode='ragged', **hp, **DROP)
+    net32.nn.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=False)
+    l16, ol = net16(x, tl)
+    l32, _ = net32(x, tl)
+    a, b = l16.cpu().numpy(), l32.cpu().numpy()
+    for i in range(len(widths)):
+        n = int(ol[i])
+        err = rel_err(a[i, :n], b[i, :n])
+        assert err < BF16_TOL, f'line {i} (width {widths[i]}): rel err {err}'
