@@ -252,14 +252,23 @@ def run_ours(args):
     # ---- end to end through the host-buffer entry point (H2D + D2H inside the timed region) ----
     e2e = None
     if not args.no_e2e:
-        x_host = torch.empty((B, 1, hp['height'], W), dtype=torch.float32).pin_memory()
-        x_host.copy_(x_dev)
+        # two pinned host batches alternate through the handle's two slots: the H2D copy of step i+1 runs on the copy
+        # stream while step i computes; every step's input crosses PCIe and every step's records come back to the host
+        x_hosts = [torch.empty((B, 1, hp['height'], W), dtype=torch.float32).pin_memory() for _ in range(2)]
+        for xh in x_hosts:
+            xh.copy_(x_dev)
         for _ in range(2):
-            eng.recognize_host(x_host, widths)
+            eng.recognize_host(x_hosts[0], widths)
         fence()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            r = eng.recognize_host(x_host, widths)
+        pending = None
+        for i in range(args.steps):
+            slot = i & 1
+            eng.recognize_host_begin(slot, x_hosts[slot], widths)
+            if pending is not None:
+                r = eng.recognize_host_end(pending)
+            pending = slot
+        r = eng.recognize_host_end(pending)
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -269,7 +278,8 @@ def run_ours(args):
         d2h = 4 * (4 * B * T + 2 * B)
         e2e = dict(value=world * B * args.steps / dt, unit='lines/s', h2d_bytes_per_step=in_bytes + 4 * B,
                    d2h_bytes_per_step=d2h, ms_per_step=1e3 * dt / args.steps,
-                   api='Engine.recognize_host -> cocr_recognize_host (pinned fp32 (N,1,H,W) in, decoded records out)')
+                   api='Engine.recognize_host_begin/_end -> cocr_recognize_host_begin/_end (pinned fp32 (N,1,H,W) in, decoded '
+                       'records out; two slots, H2D of step i+1 overlaps the forward pass of step i)')
         assert int(r['counts'].sum()) >= 0
 
     # ---- per-kernel CUDA-event timing for the roofline of the dominant kernel (rank 0) ----
@@ -303,6 +313,14 @@ def run_ours(args):
                 ach = f['bytes_per_step'] / (f['ms_per_step'] * 1e-3) / 1e9
                 roofline = dict(kernel=top, bound='hbm', achieved=ach, peak=peaks['hbm_gbs'], unit='GB/s',
                                 frac=ach / peaks['hbm_gbs'], traffic=None)
+            tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+            if os.path.exists(tpath):
+                with open(tpath) as fp:
+                    tr = json.load(fp).get(top)
+                if tr and (args.batch, args.width) == (256, 1536):      # the capture is of this workload
+                    roofline['traffic'] = tr['dram_bytes_per_launch']
+                    roofline['traffic_source'] = tr['source']
+                    roofline['algorithmic_bytes_per_launch'] = f['bytes_per_step'] / max(f['launches'], 1)
             roofline.update(peak_source=peaks['source'] + (' (sustained bf16 cuBLAS)' if tensor_bound else ' (copy)'),
                             launches_per_step=f['launches'], avg_launch_ms=per_launch_ms,
                             share_of_step=f['ms_per_step'] / max(sum(v['ms_per_step'] for v in families.values()), 1e-9),

@@ -228,10 +228,15 @@ int cocr_destroy(cocr_handle *h) {
     if (h->arena) cudaFree(h->arena);
     if (h->ws.base) cudaFree(h->ws.base);
     if (h->pos_proj) cudaFree(h->pos_proj);
-    if (h->io_img) cudaFree(h->io_img);
-    if (h->io_res) cudaFree(h->io_res);
-    if (h->io_res_host) cudaFreeHost(h->io_res_host);
-    if (h->io_widths) cudaFree(h->io_widths);
+    for (auto &sl : h->slots) {
+        if (sl.img) cudaFree(sl.img);
+        if (sl.widths) cudaFree(sl.widths);
+        if (sl.res) cudaFree(sl.res);
+        if (sl.res_host) cudaFreeHost(sl.res_host);
+        if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     delete h;
     return COCR_OK;
 }
@@ -447,62 +452,97 @@ int cocr_forward_decode(cocr_handle *h, const float *img, int64_t sb, int64_t sw
                                 (int32_t *)(h->ws.base + p.off_best_idx), labels, starts, ends, conf, counts);
 }
 
-int cocr_recognize_host(cocr_handle *h, const float *img_host, const int32_t *widths_host, int32_t B, int32_t W,
-                        void *stream, int32_t *labels, int32_t *starts, int32_t *ends, float *conf, int32_t *counts,
-                        int32_t *out_lens) {
+int cocr_recognize_host_begin(cocr_handle *h, int32_t slot, const float *img_host, const int32_t *widths_host, int32_t B, int32_t W,
+                              void *stream) {
     COCR_TRY(check_call(h, img_host, B, W));
-    if (!labels || !starts || !ends || !conf || !counts || !out_lens)
-        return set_error(h, COCR_ERR_BAD_ARG, "cocr_recognize_host: null output");
+    if (slot < 0 || slot > 1) return set_error(h, COCR_ERR_BAD_ARG, "cocr_recognize_host_begin: slot must be 0 or 1");
+    cocr_handle::HostSlot &sl = h->slots[slot];
+    if (sl.busy) return set_error(h, COCR_ERR_STATE, "cocr_recognize_host_begin: slot %d still holds an unfinished batch", slot);
     cudaStream_t st = (cudaStream_t)stream;
     const int H = h->dm.H;
     const int T = cocr_out_frames(W);
-    size_t img_bytes = sizeof(float) * (size_t)B * H * W;
-    if (img_bytes > h->io_img_bytes) {
-        if (h->io_img) { COCR_CUDA(h, cudaDeviceSynchronize()); COCR_CUDA(h, cudaFree(h->io_img)); h->io_img = nullptr; h->io_img_bytes = 0; }
+    if (!h->copy_stream) COCR_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (!sl.h2d_done) {
+        COCR_CUDA(h, cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+        COCR_CUDA(h, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    }
+    const size_t img_bytes = sizeof(float) * (size_t)B * H * W;
+    if (img_bytes > sl.img_bytes) {
+        if (sl.img) { COCR_CUDA(h, cudaDeviceSynchronize()); COCR_CUDA(h, cudaFree(sl.img)); sl.img = nullptr; sl.img_bytes = 0; }
         void *p = nullptr;
         COCR_CUDA(h, cudaMalloc(&p, img_bytes));
-        h->io_img = (float *)p;
-        h->io_img_bytes = img_bytes;
+        sl.img = (float *)p;
+        sl.img_bytes = img_bytes;
     }
-    if ((size_t)B > h->io_widths_n) {
-        if (h->io_widths) { COCR_CUDA(h, cudaDeviceSynchronize()); COCR_CUDA(h, cudaFree(h->io_widths)); h->io_widths = nullptr; }
+    if ((size_t)B > sl.widths_n) {
+        if (sl.widths) { COCR_CUDA(h, cudaDeviceSynchronize()); COCR_CUDA(h, cudaFree(sl.widths)); sl.widths = nullptr; }
         void *p = nullptr;
         COCR_CUDA(h, cudaMalloc(&p, sizeof(int32_t) * B));
-        h->io_widths = (int32_t *)p;
-        h->io_widths_n = B;
+        sl.widths = (int32_t *)p;
+        sl.widths_n = B;
     }
     const size_t bt = (size_t)B * T;
     const size_t res_bytes = 4 * (4 * bt + 2 * (size_t)B);
-    if (res_bytes > h->io_res_bytes) {
-        if (h->io_res) { COCR_CUDA(h, cudaDeviceSynchronize()); COCR_CUDA(h, cudaFree(h->io_res)); COCR_CUDA(h, cudaFreeHost(h->io_res_host)); }
-        h->io_res = nullptr; h->io_res_host = nullptr; h->io_res_bytes = 0;
+    if (res_bytes > sl.res_bytes) {
+        if (sl.res) { COCR_CUDA(h, cudaDeviceSynchronize()); COCR_CUDA(h, cudaFree(sl.res)); COCR_CUDA(h, cudaFreeHost(sl.res_host)); }
+        sl.res = nullptr; sl.res_host = nullptr; sl.res_bytes = 0;
         void *p = nullptr;
         COCR_CUDA(h, cudaMalloc(&p, res_bytes));
-        h->io_res = (char *)p;
+        sl.res = (char *)p;
         COCR_CUDA(h, cudaMallocHost(&p, res_bytes));
-        h->io_res_host = (char *)p;
-        h->io_res_bytes = res_bytes;
+        sl.res_host = (char *)p;
+        sl.res_bytes = res_bytes;
     }
-    COCR_CUDA(h, cudaMemcpyAsync(h->io_img, img_host, img_bytes, cudaMemcpyHostToDevice, st));
+    // H2D on the copy stream: it may run while the previous batch (other slot) is still computing on `stream`.  The
+    // slot's own previous forward pass finished before its results were collected (cocr_recognize_host_end), so the
+    // image buffer is free.
+    COCR_CUDA(h, cudaMemcpyAsync(sl.img, img_host, img_bytes, cudaMemcpyHostToDevice, h->copy_stream));
     const int32_t *wd = nullptr;
     if (widths_host) {
-        COCR_CUDA(h, cudaMemcpyAsync(h->io_widths, widths_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
-        wd = h->io_widths;
+        COCR_CUDA(h, cudaMemcpyAsync(sl.widths, widths_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, h->copy_stream));
+        wd = sl.widths;
     }
-    int32_t *d_lab = (int32_t *)h->io_res, *d_st = d_lab + bt, *d_en = d_st + bt;
+    COCR_CUDA(h, cudaEventRecord(sl.h2d_done, h->copy_stream));
+    COCR_CUDA(h, cudaStreamWaitEvent(st, sl.h2d_done, 0));
+    int32_t *d_lab = (int32_t *)sl.res, *d_st = d_lab + bt, *d_en = d_st + bt;
     float *d_cf = (float *)(d_en + bt);
     int32_t *d_cnt = (int32_t *)(d_cf + bt), *d_len = d_cnt + B;
-    COCR_TRY(cocr_forward_decode(h, h->io_img, (int64_t)H * W, 1, W, wd, B, W, stream, d_lab, d_st, d_en, d_cf, d_cnt, d_len));
-    COCR_CUDA(h, cudaMemcpyAsync(h->io_res_host, h->io_res, res_bytes, cudaMemcpyDeviceToHost, st));
-    COCR_CUDA(h, cudaStreamSynchronize(st));
-    const char *r = h->io_res_host;
+    COCR_TRY(cocr_forward_decode(h, sl.img, (int64_t)H * W, 1, W, wd, B, W, stream, d_lab, d_st, d_en, d_cf, d_cnt, d_len));
+    COCR_CUDA(h, cudaMemcpyAsync(sl.res_host, sl.res, res_bytes, cudaMemcpyDeviceToHost, st));
+    COCR_CUDA(h, cudaEventRecord(sl.done, st));
+    sl.B = B; sl.T = T; sl.busy = true;
+    return COCR_OK;
+}
+
+int cocr_recognize_host_end(cocr_handle *h, int32_t slot, int32_t *labels, int32_t *starts, int32_t *ends, float *conf, int32_t *counts,
+                            int32_t *out_lens) {
+    if (!h) return COCR_ERR_BAD_ARG;
+    if (slot < 0 || slot > 1) return set_error(h, COCR_ERR_BAD_ARG, "cocr_recognize_host_end: slot must be 0 or 1");
+    if (!labels || !starts || !ends || !conf || !counts || !out_lens) return set_error(h, COCR_ERR_BAD_ARG, "cocr_recognize_host_end: null output");
+    cocr_handle::HostSlot &sl = h->slots[slot];
+    if (!sl.busy) return set_error(h, COCR_ERR_STATE, "cocr_recognize_host_end: slot %d holds no batch", slot);
+    COCR_CUDA(h, cudaSetDevice(h->device));
+    COCR_CUDA(h, cudaEventSynchronize(sl.done));
+    sl.busy = false;
+    const size_t bt = (size_t)sl.B * sl.T, B = (size_t)sl.B;
+    const char *r = sl.res_host;
     memcpy(labels, r, 4 * bt); r += 4 * bt;
     memcpy(starts, r, 4 * bt); r += 4 * bt;
     memcpy(ends, r, 4 * bt); r += 4 * bt;
     memcpy(conf, r, 4 * bt); r += 4 * bt;
-    memcpy(counts, r, 4 * (size_t)B); r += 4 * (size_t)B;
-    memcpy(out_lens, r, 4 * (size_t)B);
+    memcpy(counts, r, 4 * B); r += 4 * B;
+    memcpy(out_lens, r, 4 * B);
     return COCR_OK;
+}
+
+int cocr_recognize_host(cocr_handle *h, const float *img_host, const int32_t *widths_host, int32_t B, int32_t W,
+                        void *stream, int32_t *labels, int32_t *starts, int32_t *ends, float *conf, int32_t *counts,
+                        int32_t *out_lens) {
+    if (h && (!labels || !starts || !ends || !conf || !counts || !out_lens))
+        return set_error(h, COCR_ERR_BAD_ARG, "cocr_recognize_host: null output");
+    const int slot = (h && h->slots[0].busy) ? 1 : 0;
+    COCR_TRY(cocr_recognize_host_begin(h, slot, img_host, widths_host, B, W, stream));
+    return cocr_recognize_host_end(h, slot, labels, starts, ends, conf, counts, out_lens);
 }
 
 int cocr_workspace_bytes(cocr_handle *h, int32_t B, int32_t W, size_t *bytes) {

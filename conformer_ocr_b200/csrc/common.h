@@ -81,14 +81,21 @@ struct cocr_handle {
     float *pos_proj = nullptr;      // (L, 2T-1, d) fp32
     int pos_T = 0;
 
-    // staging for the *_host entry point
-    float *io_img = nullptr;
-    size_t io_img_bytes = 0;
-    char *io_res = nullptr;         // device result block
-    char *io_res_host = nullptr;    // pinned mirror
-    size_t io_res_bytes = 0;
-    int32_t *io_widths = nullptr;
-    size_t io_widths_n = 0;
+    // staging for the *_host entry points: two slots so that the H2D copy of one batch (copy stream) overlaps the
+    // forward pass of the previous one
+    struct HostSlot {
+        float *img = nullptr;          // device image batch
+        size_t img_bytes = 0;
+        int32_t *widths = nullptr;
+        size_t widths_n = 0;
+        char *res = nullptr;           // device result block
+        char *res_host = nullptr;      // pinned mirror
+        size_t res_bytes = 0;
+        cudaEvent_t h2d_done = nullptr, done = nullptr;
+        int B = 0, T = 0;
+        bool busy = false;
+    } slots[2];
+    cudaStream_t copy_stream = nullptr;
 
     int64_t launches = 0;
     cocr::Bf16State *bf = nullptr;

@@ -196,6 +196,40 @@ class Engine:
                 p(res['starts']), p(res['ends']), p(res['conf']), p(res['counts']), p(res['out_lens'])))
         return res
 
+    def recognize_host_begin(self, slot: int, img: torch.Tensor, widths: Optional[torch.Tensor] = None) -> None:
+        """Enqueue one host batch in `slot` (0 or 1) without waiting: H2D on the handle's copy stream, forward + decode
+        + D2H on the current stream.  Keep `img` / `widths` alive and unchanged until `recognize_host_end(slot)`.
+        Two slots let the copy of batch i+1 overlap the forward pass of batch i."""
+        if img.device.type != 'cpu' or img.dtype != torch.float32 or not img.is_contiguous():
+            raise ValueError('recognize_host_begin expects a contiguous fp32 host tensor (N,1,H,W)')
+        B, ch, H, W = img.shape
+        if ch != 1 or H != self.height:
+            raise ValueError(f'expected (N,1,{self.height},W) input, got {tuple(img.shape)}')
+        wh = None
+        if widths is not None:
+            wh = torch.as_tensor(widths).to(dtype=torch.int32).contiguous()
+        with torch.cuda.device(self.device):
+            self._check(self._lib.cocr_recognize_host_begin(self._h, slot, C.c_void_p(img.data_ptr()), self._ptr(wh), B, W,
+                                                            self._stream()))
+        self._pending = getattr(self, '_pending', {})
+        self._pending[slot] = (img, wh, B, int(self._lib.cocr_out_frames(W)))      # keeps the host buffers alive
+
+    def recognize_host_end(self, slot: int) -> Dict[str, np.ndarray]:
+        pending = getattr(self, '_pending', {})
+        if slot not in pending:
+            dummy = np.empty((1,), np.int32)
+            q = dummy.ctypes.data_as(C.c_void_p)
+            self._check(self._lib.cocr_recognize_host_end(self._h, slot, q, q, q, q, q, q))     # raises: nothing pending
+            raise RuntimeError(f'slot {slot} holds no batch')
+        _, _, B, T = pending.pop(slot)
+        res = dict(labels=np.empty((B, T), np.int32), starts=np.empty((B, T), np.int32), ends=np.empty((B, T), np.int32),
+                   conf=np.empty((B, T), np.float32), counts=np.empty((B,), np.int32), out_lens=np.empty((B,), np.int32))
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.cocr_recognize_host_end(self._h, slot, p(res['labels']), p(res['starts']), p(res['ends']),
+                                                          p(res['conf']), p(res['counts']), p(res['out_lens'])))
+        return res
+
     def workspace_bytes(self, B: int, W: int) -> int:
         n = C.c_size_t()
         self._check(self._lib.cocr_workspace_bytes(self._h, B, W, C.byref(n)))

@@ -139,6 +139,17 @@ int cocr_recognize_host(cocr_handle *h, const float *img_host, const int32_t *wi
                         int32_t *labels_host, int32_t *starts_host, int32_t *ends_host, float *conf_host,
                         int32_t *counts_host, int32_t *out_lens_host);
 
+/* The same, split in two so that a caller can keep two batches in flight (slot 0 / 1): `begin` enqueues the H2D copy
+ * of the batch on the handle's copy stream, the forward pass + decode + D2H on `stream`, and returns without waiting;
+ * `end` waits for that slot and unpacks the results.  While batch i computes, the H2D copy of batch i+1 (other slot)
+ * proceeds: this is how a DataLoader loop (cli/test.py:185-191) hides PCIe behind the forward pass.  A slot must be
+ * ended before it is begun again; img_host / widths_host must stay valid (and unchanged) until the slot is ended. */
+int cocr_recognize_host_begin(cocr_handle *h, int32_t slot, const float *img_host, const int32_t *widths_host,
+                              int32_t B, int32_t W, void *stream);
+int cocr_recognize_host_end(cocr_handle *h, int32_t slot,
+                            int32_t *labels_host, int32_t *starts_host, int32_t *ends_host, float *conf_host,
+                            int32_t *counts_host, int32_t *out_lens_host);
+
 /* Bytes of device workspace the handle holds after a call with this (B, W). */
 int cocr_workspace_bytes(cocr_handle *h, int32_t B, int32_t W, size_t *bytes);
 

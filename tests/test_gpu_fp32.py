@@ -111,6 +111,35 @@ def test_host_buffer_entry_point_equals_device_path(cuda_device):
     np.testing.assert_array_equal(host['out_lens'], O.calc_length(lens))
 
 
+def test_pipelined_host_entry_points(cuda_device):
+    """cocr_recognize_host_begin/_end with two batches in flight return what the one-shot call returns, and the slot
+    protocol is enforced."""
+    from conformer_ocr_b200.engine import Engine
+    meta, _ = load_golden('default_ragged')
+    hp, w, img, lens = golden_inputs(meta)
+    net = build_net(hp, meta['num_classes'], w, cuda_device)
+    eng = net.engine_for(cuda_device)
+    a = torch.from_numpy(img).contiguous().pin_memory()
+    b = torch.from_numpy(img[::-1].copy()).contiguous().pin_memory()
+    la, lb = torch.from_numpy(lens).int(), torch.from_numpy(lens[::-1].copy()).int()
+    ref_a, ref_b = eng.recognize_host(a, la), eng.recognize_host(b, lb)
+    eng.recognize_host_begin(0, a, la)
+    eng.recognize_host_begin(1, b, lb)
+    with pytest.raises(RuntimeError):
+        eng.recognize_host_begin(1, b, lb)          # slot still busy
+    got_a, got_b = eng.recognize_host_end(0), eng.recognize_host_end(1)
+    for got, ref in ((got_a, ref_a), (got_b, ref_b)):
+        for k in ('labels', 'starts', 'ends', 'counts', 'out_lens'):
+            n = ref['counts']
+            if k in ('labels', 'starts', 'ends'):
+                for i in range(len(n)):
+                    np.testing.assert_array_equal(got[k][i, :n[i]], ref[k][i, :n[i]])
+            else:
+                np.testing.assert_array_equal(got[k], ref[k])
+    with pytest.raises(RuntimeError):
+        eng.recognize_host_end(0)                    # nothing pending
+
+
 def test_errors_cross_the_abi_as_python_exceptions(cuda_device):
     meta, _ = load_golden('tiny_equal')
     hp, w, img, lens = golden_inputs(meta)
