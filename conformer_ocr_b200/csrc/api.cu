@@ -371,6 +371,14 @@ int cocr_finalize_weights(cocr_handle *h) {
         w.w_pw2 = A + v[n++]; w.b_pw2 = A + v[n++];
         w.final_ln_g = A + v[n++]; w.final_ln_b = A + v[n++];
     }
+    // conv.0 / conv.2 of the front-end in kernel-parameter order (w1[32*9], b1[32], wdw[32*9], bdw[32])
+    h->fe_weights.clear();
+    if (dm.cc == 32) {
+        for (const char *k : {"conv.0.weight", "conv.0.bias", "conv.2.weight", "conv.2.bias"}) {
+            const std::vector<float> &v = W(s + k).data;
+            h->fe_weights.insert(h->fe_weights.end(), v.begin(), v.end());
+        }
+    }
     h->pos_T = 0;   // positional projections depend on the weights
     if (h->hp.precision == COCR_BF16) COCR_TRY(bf16_init(h));
     h->finalized = true;

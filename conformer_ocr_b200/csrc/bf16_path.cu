@@ -31,6 +31,7 @@ struct Bf16State {
     // conv module: first pointwise conv with (value, gate) rows interleaved and scaled by 1/2 for the GLU epilogue
     bf16 *w_pw1g = nullptr;       // (L, 2d, d)
     float *b_pw1g = nullptr;      // (L, 2d)
+    bf16 *w_fe_pw2 = nullptr;     // (cc, 2 cc): [Wpw | Wpw] for the hi/lo split 1x1 conv GEMM of the front-end
     float *dw_taps = nullptr;     // (L, K*d + d): depthwise taps [k][pair](2) * bn_scale / 2, then bn_shift / 2
     int tab_T = 0;
 };
@@ -88,7 +89,7 @@ struct ResidArgs { float *x; float alpha; int init; const float *gf, *bf, *g1, *
 
 int launch_gemm_tc(cocr_handle *h, int epi, const bf16 *A, int lda, const bf16 *W, int ldw, const float *bias, void *out,
                    int ldc, unsigned long long *best, int M, int N, int K, cudaStream_t st, int block_n_override = 0,
-                   const PosArgs *pos = nullptr, const char *tag = "gemm_tc", const ResidArgs *res = nullptr) {
+                   const PosArgs *pos = nullptr, const char *tag = "gemm_tc", const ResidArgs *res = nullptr, int relu = 0) {
     if (M <= 0 || N <= 0) return COCR_OK;
     if (K % 16 != 0 || lda % 8 != 0 || ldw % 8 != 0)
         return set_error(h, COCR_ERR_UNSUPPORTED, "tensor-core GEMM needs K %% 16 == 0 and 16-byte aligned rows (K=%d lda=%d ldw=%d)", K,
@@ -100,7 +101,7 @@ int launch_gemm_tc(cocr_handle *h, int epi, const bf16 *A, int lda, const bf16 *
     p.m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
     p.nkc = (K + GEMM_KC - 1) / GEMM_KC;
     p.last_ksteps = (K - (p.nkc - 1) * GEMM_KC) / 16;
-    p.bias = bias; p.out = out; p.ldc = ldc; p.best = best;
+    p.bias = bias; p.out = out; p.ldc = ldc; p.best = best; p.relu = relu;
     p.col_meta = pos ? pos->meta : nullptr; p.omega = pos ? pos->omega : nullptr;
     p.n_omega = pos ? pos->n_omega : 0; p.T = pos ? pos->T : 1; p.piece_dst = pos ? pos->piece_dst : nullptr;
     if (epi == EPI_BF16_POS && (!pos || p.n_omega > 256 || N / 16 > 1024)) return set_error(h, COCR_ERR_BAD_ARG, "POS epilogue needs position tables");
@@ -363,6 +364,7 @@ static void bf16_plan(const cocr_handle *h, int B, int W, Bf16Plan *p) {
     p->off_y = take(M * dm.d * 2);
     size_t wide = (size_t)dm.ff > (size_t)3 * dm.d ? dm.ff : 3 * dm.d;
     if (use_tc_attn(h) && (size_t)h->bf->nx > wide) wide = h->bf->nx;
+    if ((size_t)dm.feat > wide) wide = dm.feat;              // the front-end parks a2 (M*F, cc) here
     p->off_h = take(M * wide * 2);
     p->off_g = take(M * dm.d * 2);
     p->off_best = take(M * 8);
@@ -658,6 +660,17 @@ int bf16_init(cocr_handle *h) {
         void *pt = nullptr;
         COCR_CUDA(h, cudaMalloc(&pt, taps.size() * 4)); bs->dw_taps = (float *)pt;
         COCR_CUDA(h, cudaMemcpy(bs->dw_taps, taps.data(), taps.size() * 4, cudaMemcpyHostToDevice));
+        {
+            const int cc = dm.cc;
+            const std::vector<float> &wp = h->host_w.at("encoder.conv_subsample.conv.3.weight").data;
+            std::vector<uint16_t> w2((size_t)cc * 2 * cc);
+            for (int n = 0; n < cc; ++n)
+                for (int k = 0; k < cc; ++k) w2[(size_t)n * 2 * cc + k] = w2[(size_t)n * 2 * cc + cc + k] = f2bf(wp[(size_t)n * cc + k]);
+            if (bs->w_fe_pw2) { cudaFree(bs->w_fe_pw2); bs->w_fe_pw2 = nullptr; }
+            void *pw = nullptr;
+            COCR_CUDA(h, cudaMalloc(&pw, w2.size() * 2)); bs->w_fe_pw2 = (bf16 *)pw;
+            COCR_CUDA(h, cudaMemcpy(bs->w_fe_pw2, w2.data(), w2.size() * 2, cudaMemcpyHostToDevice));
+        }
         if (bs->w_pw1g) { cudaFree(bs->w_pw1g); bs->w_pw1g = nullptr; }
         if (bs->b_pw1g) { cudaFree(bs->b_pw1g); bs->b_pw1g = nullptr; }
         void *pp = nullptr;
@@ -685,6 +698,7 @@ void bf16_destroy(cocr_handle *h) {
     if (bs->w_pw1g) cudaFree(bs->w_pw1g);
     if (bs->b_pw1g) cudaFree(bs->b_pw1g);
     if (bs->dw_taps) cudaFree(bs->dw_taps);
+    if (bs->w_fe_pw2) cudaFree(bs->w_fe_pw2);
     delete h->bf;
     h->bf = nullptr;
 }
@@ -717,7 +731,16 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
     }
     // front-end (convolution.py:227-237): direct convs on CUDA cores, 1x1 conv as an fp32 GEMM writing bf16 features,
     // 768->144 projection on tensor cores
-    int rc_fe = launch_frontend_fused(h, img, sb, sw, sh, B, W, feat, st);
+    // conv1 + depthwise conv on CUDA cores -> a2 (M*F, [hi | lo] 2x32) bf16, then the 1x1 conv + ReLU as a K = 64
+    // tensor-core GEMM whose (M*F, 32) output IS the (M, F*32) feature matrix of the 768 -> 144 projection
+    bf16 *a2hl = (bf16 *)a2;                                       // (M*F, 2 cc) bf16 = the fp32 a2 region of the plan
+    int rc_fe = getenv("COCR_FRONTEND_V1") ? COCR_ERR_UNSUPPORTED : launch_frontend_convs2(h, img, sb, sw, sh, B, W, a2hl, st);
+    if (rc_fe == COCR_OK) {
+        rc_fe = launch_gemm_tc(h, EPI_BF16, a2hl, 2 * dm.cc, h->bf->w_fe_pw2, 2 * dm.cc, h->sub_bpw, feat, dm.cc, nullptr, M * dm.F, dm.cc,
+                               2 * dm.cc, st, 0, nullptr, "gemm_frontend_pw", nullptr, /*relu=*/1);
+    } else if (rc_fe == COCR_ERR_UNSUPPORTED) {
+        rc_fe = launch_frontend_fused(h, img, sb, sw, sh, B, W, feat, st);
+    }
     if (rc_fe == COCR_ERR_UNSUPPORTED) {
         COCR_TRY(launch_frontend_convs(h, img, sb, sw, sh, B, W, a1, a2, st));
         COCR_TRY(launch_sgemm(h, a2, dm.cc, h->sub_wpw, dm.cc, h->sub_bpw, (float *)feat, dm.cc, M * dm.F, dm.cc, dm.cc, 2, nullptr,

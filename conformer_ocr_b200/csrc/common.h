@@ -97,6 +97,7 @@ struct cocr_handle {
     } slots[2];
     cudaStream_t copy_stream = nullptr;
 
+    std::vector<float> fe_weights;   // conv.0 / conv.2 weights + biases in kernel-parameter order (mem_kernels.cu: FrontendWeights)
     int64_t launches = 0;
     cocr::Bf16State *bf = nullptr;
 
@@ -189,6 +190,8 @@ int launch_glu_dw_fast(cocr_handle *h, const __nv_bfloat16 *u, const LayerF32 &l
                        cudaStream_t st);
 int launch_dw_fast(cocr_handle *h, const __nv_bfloat16 *x, const float *taps_dev, const float *hshift_dev, __nv_bfloat16 *g, int B, int T,
                    cudaStream_t st);
+int launch_frontend_convs2(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, int B, int W, __nv_bfloat16 *a2,
+                           cudaStream_t st);
 int launch_frontend_fused(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, int B, int W,
                           __nv_bfloat16 *feat, cudaStream_t st);
 

@@ -67,6 +67,7 @@ struct GemmArgs {
     int init;                   // 1: x = acc + bias (start of the stream)
     const float *gf, *bf;       // block-final LayerNorm applied to x itself (or null)
     const float *g1, *b1;       // LayerNorm of the next module -> xn (null: xn = bf16(x))
+    int relu;                   // EPI_BF16: out = max(acc + bias, 0)
     int dbg;                    // experiments (COCR_GEMM_DBG): 1 skip the TMA stores, 2 skip the position math
     long long *trace;           // debug: (tag, clock) pairs of CTA 0 (COCR_GEMM_TRACE=<tag>:<file>), else null
 };
@@ -540,6 +541,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
                         if constexpr (EPI == EPI_BF16_SILU) f2[e] = silu_from_half(f2[e]);
+                        if constexpr (EPI == EPI_BF16) {
+                            if (p.relu) f2[e] = make_float2(fmaxf(f2[e].x, 0.0f), fmaxf(f2[e].y, 0.0f));
+                        }
                         pk[e] = pack_bf16x2(f2[e].x, f2[e].y);
                     }
                     uint8_t *sbuf = stage_base + (bufctr % GEMM_NSTG) * GEMM_STAGE_BYTES;

@@ -3,6 +3,8 @@
 //   * k_glu_dw_fast   : GLU -> depthwise conv (K taps) -> folded BatchNorm -> SiLU      (convolution.py:139-142)
 //   * k_frontend_fused: Conv2d(1->32,3x3,s2)+ReLU -> depthwise Conv2d(3x3,s2) -> 1x1 conv+ReLU -> (t, f*32+c) bf16
 //                       features for the 768->144 projection                              (convolution.py:190-237)
+#include <string.h>
+
 #include "common.h"
 
 namespace cocr {
@@ -378,6 +380,163 @@ int launch_frontend_fused(cocr_handle *h, const float *img, int64_t sb, int64_t 
     ProfScope ps(h, "frontend_fused", st, 18.0 * n1 + 18.0 * n2 + 64.0 * n2, 4.0 * B * (double)W * dm.H + 2.0 * n2);
     k_frontend_fused<<<grid, FE_THREADS, smem, st>>>(img, sb, sw, sh, h->sub_w1, h->sub_b1, h->sub_wdw, h->sub_bdw, h->sub_wpw,
                                                     h->sub_bpw, feat, W, dm.H, T2, T, dm.F2, dm.F);
+    COCR_LAUNCHED(h);
+    return COCR_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Front-end, version 2 (32 conv channels): conv1 3x3 s2 + ReLU and the depthwise 3x3 s2 conv on CUDA cores with
+// the weights as immediate/constant operands, the 1x1 conv + ReLU as a tcgen05 GEMM over the (frame, f) rows.
+//   * the weights travel in the kernel parameter block (constant bank): every FFMA takes its weight as a constant
+//     operand, so the inner loops are pure FFMA streams with no weight loads;
+//   * conv1: thread = one (t2, f2) position, all 32 channels in registers (9 input loads, 288 FFMA);
+//   * depthwise: thread = one (t, f) position x 8 channels (warp-uniform channel group), 16-byte a1 reads;
+//   * a2 leaves as bf16 rows [(b, t, f)][32 channels] - exactly the row-major (t, f*32 + c) feature layout - and the
+//     1x1 conv is  feat = relu(a2 * Wpw^T + b)  on tensor cores (k_gemm_tc, EPI_BF16 with relu).
+// ------------------------------------------------------------------------------------------------------------
+struct FrontendWeights {
+    float w1[32 * 9], b1[32], wdw[32 * 9], bdw[32];
+};
+
+constexpr int FE2_TT = 8;
+constexpr int FE2_THREADS = 256;
+
+// 16-byte chunk g (8 channels) of position pos inside a1[pos][32 ch] bf16, xor-swizzled so that lanes writing / reading
+// consecutive positions spread over the banks
+__device__ __forceinline__ uint32_t a1_offset(int pos, int g) { return (uint32_t)pos * 64u + (uint32_t)((g ^ (pos >> 1)) & 3) * 16u; }
+
+template <int G>
+__device__ __forceinline__ void dw_group(const FrontendWeights &fw, const uint8_t *a1, int tl, int f, int F2, float (&o)[8]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) o[c] = fw.bdw[G * 8 + c];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+        const int r = 2 * tl + kh;                               // local conv1 row (t2 = 2t - 1 + kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            const int f2 = 2 * f - 1 + kw;
+            if (f2 >= 0 && f2 < F2) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(a1 + a1_offset(r * F2 + f2, G));
+                const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int c2 = 0; c2 < 4; ++c2) {
+                    const float2 x = bf2_to_f2(u[c2]);
+                    o[2 * c2] = fmaf(fw.wdw[(G * 8 + 2 * c2) * 9 + kh * 3 + kw], x.x, o[2 * c2]);
+                    o[2 * c2 + 1] = fmaf(fw.wdw[(G * 8 + 2 * c2 + 1) * 9 + kh * 3 + kw], x.y, o[2 * c2 + 1]);
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FE2_THREADS, 2)
+k_frontend_convs2(const float *__restrict__ img, int64_t sb, int64_t sw, int64_t sh, const __grid_constant__ FrontendWeights fw,
+                  bf16 *__restrict__ a2, int W, int H, int T2, int T, int F2, int F) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    constexpr int NW = 4 * FE2_TT + 3;              // input columns (time) needed
+    constexpr int NT2 = 2 * FE2_TT + 1;             // conv1 rows needed
+    const int HP = (H + 2 + 3) & ~3;                // padded input row: y = -1 .. H, rounded to 4 floats
+    float *patch = reinterpret_cast<float *>(sm_raw);                     // [NW][HP], patch[wl][y+1]
+    uint8_t *a1 = reinterpret_cast<uint8_t *>(patch + NW * HP);           // [NT2 * F2 positions][64 B], swizzled chunks
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * FE2_TT;
+    const int w0 = 4 * t0 - 3;                      // first input column of the patch
+    const int t20 = 2 * t0 - 1;                     // first conv1 row of the tile
+
+    // stage A: input patch (zero padded)
+    for (int e = threadIdx.x; e < NW * HP; e += FE2_THREADS) {
+        int wl, y;
+        if (sw == 1) { y = e / NW; wl = e - y * NW; }           // (N,1,H,W) layout: time is contiguous
+        else { wl = e / HP; y = e - wl * HP; }                  // (B,W,H) layout: height is contiguous
+        const int w = w0 + wl, yy = y - 1;
+        float v = 0.0f;
+        if (w >= 0 && w < W && yy >= 0 && yy < H) v = img[b * sb + w * sw + yy * sh];
+        patch[wl * HP + y] = v;
+    }
+    __syncthreads();
+
+    // stage B: conv1 + ReLU (convolution.py:192-198); conv "height" = time, conv "width" = image height
+    for (int pos = threadIdx.x; pos < NT2 * F2; pos += FE2_THREADS) {
+        const int r = pos / F2, f2 = pos - r * F2;
+        const int t2 = t20 + r;
+        uint32_t pk[16];
+        if (t2 < 0 || t2 >= T2) {                               // outside the conv1 output: zero padding of the dw conv
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = 0u;
+        } else {
+            float in[9];
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) in[kh * 3 + kw] = patch[(2 * r + kh) * HP + 2 * f2 + kw];
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+                float o0 = fw.b1[c], o1 = fw.b1[c + 1];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    o0 = fmaf(fw.w1[c * 9 + k], in[k], o0);
+                    o1 = fmaf(fw.w1[(c + 1) * 9 + k], in[k], o1);
+                }
+                pk[c >> 1] = f2_to_bf2(fmaxf(o0, 0.0f), fmaxf(o1, 0.0f));
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4 *>(a1 + a1_offset(pos, g)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+    }
+    __syncthreads();
+
+    // stage C: depthwise conv (convolution.py:200-205): a2[t][f][c] = b + sum a1[2t-1+kh][2f-1+kw][c] w[c][kh][kw]
+    const int npos = FE2_TT * F;                                  // multiple of 32 for F = 24: a warp stays inside one group
+    for (int item = threadIdx.x; item < 4 * npos; item += FE2_THREADS) {
+        const int g = item / npos, p2 = item - g * npos;
+        const int tl = p2 / F, f = p2 - tl * F;
+        const int t = t0 + tl;
+        float o[8];
+        switch (g) {
+            case 0: dw_group<0>(fw, a1, tl, f, F2, o); break;
+            case 1: dw_group<1>(fw, a1, tl, f, F2, o); break;
+            case 2: dw_group<2>(fw, a1, tl, f, F2, o); break;
+            default: dw_group<3>(fw, a1, tl, f, F2, o); break;
+        }
+        if (t < T) {
+            // a2 row = [hi (32 bf16) | lo (32 bf16)], hi + lo = the fp32 value to 16 mantissa bits: the 1x1 conv GEMM runs
+            // with K = 64 against [Wpw | Wpw], so the activation side of that GEMM is not rounded to 8 bits
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int c2 = 0; c2 < 4; ++c2) {
+                hi[c2] = f2_to_bf2(o[2 * c2], o[2 * c2 + 1]);
+                const float2 hf = bf2_to_f2(hi[c2]);
+                lo[c2] = f2_to_bf2(o[2 * c2] - hf.x, o[2 * c2 + 1] - hf.y);
+            }
+            bf16 *row = a2 + (((int64_t)b * T + t) * F + f) * 64 + g * 8;
+            *reinterpret_cast<uint4 *>(row) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4 *>(row + 32) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+    }
+}
+
+// conv1 + depthwise conv -> a2 (B*T*F, 64) bf16 [hi | lo]; the caller runs the 1x1 conv as a K = 64 GEMM.  COCR_ERR_UNSUPPORTED when the
+// geometry is not covered.
+int launch_frontend_convs2(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, int B, int W, bf16 *a2, cudaStream_t st) {
+    const Dims &dm = h->dm;
+    if (dm.cc != 32 || ((FE2_TT * dm.F) & 31) != 0 || h->fe_weights.size() != sizeof(FrontendWeights) / 4) return COCR_ERR_UNSUPPORTED;
+    const int T2 = out_len1(W), T = out_len1(T2);
+    const int HP = (dm.H + 2 + 3) & ~3;
+    const size_t smem = (size_t)(4 * FE2_TT + 3) * HP * 4 + (size_t)(2 * FE2_TT + 1) * dm.F2 * 64;
+    if (smem > 200 * 1024) return COCR_ERR_UNSUPPORTED;
+    static size_t attr = 0;
+    if (smem > attr) {
+        COCR_CUDA(h, cudaFuncSetAttribute(k_frontend_convs2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    FrontendWeights fw;
+    memcpy(&fw, h->fe_weights.data(), sizeof(fw));
+    dim3 grid((T + FE2_TT - 1) / FE2_TT, B);
+    const double n1 = (double)B * T2 * dm.F2 * 32, n2 = (double)B * T * dm.F * 32;
+    ProfScope ps(h, "frontend_convs", st, 18.0 * n1 + 18.0 * n2, 4.0 * B * (double)W * dm.H + 2.0 * n2);
+    k_frontend_convs2<<<grid, FE2_THREADS, smem, st>>>(img, sb, sw, sh, fw, a2, W, dm.H, T2, T, dm.F2, dm.F);
     COCR_LAUNCHED(h);
     return COCR_OK;
 }
