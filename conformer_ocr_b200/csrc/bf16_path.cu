@@ -935,6 +935,18 @@ int selftest_gemm(int device, int epi, int M, int N, int K, int block_n, double 
     k_ref_gemm<<<(unsigned)(((size_t)M * N + 255) / 256), 256>>>(A, Wt, bias, ref, M, N, K, epi == EPI_BF16_SILU);
     rc = launch_gemm_tc(h, epi, A, K, Wt, K, bias, out, N, best, M, N, K, 0, block_n);
     if (rc != COCR_OK) return fail(rc, "launch failed");
+    if (getenv("COCR_SELFTEST_TIME")) {     // timing aid for experiments: mean of 5 launches after the first
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, 0);
+        for (int i = 0; i < 5; ++i) launch_gemm_tc(h, epi, A, K, Wt, K, bias, out, N, best, M, N, K, 0, block_n);
+        cudaEventRecord(e1, 0);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        fprintf(stderr, "selftest_gemm epi=%d M=%d N=%d K=%d block_n=%d: %.1f us/launch\n", epi, M, N, K, block_n, 1e3f * ms / 5);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         set_error(h, COCR_ERR_CUDA, "selftest_gemm: %s", cudaGetErrorString(e));
