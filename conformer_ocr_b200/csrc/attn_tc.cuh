@@ -13,11 +13,15 @@
 //
 // Persistent kernel: one CTA per SM walks over work items (line, head, 128-query tile), q-tile fastest so that
 // the CTAs working at the same time share K/V in L2.
-//   warps 0-7  online softmax + output: thread = (query row = TMEM lane, half of the 128 keys of a tile); the two
-//              warps of a lane quarter exchange their row maxima / sums through shared memory
-//   warp 8     TMA producer of Q and K(+E), runs ahead across items and requests the next item into L2
-//   warp 9     TMEM allocator + MMA issuer
-//   warp 10    TMA producer of V
+//   warps 0-7   online softmax: thread = (query row = TMEM lane, half of the 128 keys of a tile); the two warps of a
+//               lane quarter exchange their row maxima through shared memory.  They do nothing else: the softmax is the
+//               critical path (MUFU bound), everything around it runs on other warps
+//   warps 8-11  auxiliary, one per lane quarter: copy the staged Qe tile of the NEXT item into TMEM and, when the last
+//               P V of an item has run, scale O by 1/l and write the context rows (the softmax warps are already on the
+//               next item by then)
+//   warp 12     TMA producer of Q and K(+E), runs ahead across items and requests the next item into L2
+//   warp 13     TMEM allocator + MMA issuer
+//   warp 14     TMA producer of V
 // Tensor memory (512 columns):  S0 | S1 (2 x 128, fp32 scores, double-buffered)  O (64)  Q0 | Q1 (2 x 96, bf16 pairs).
 //   * Both MMAs take their A operand from TENSOR MEMORY: the softmax warps copy each Qe tile from its TMA staging
 //     buffer into TMEM once per item (one item ahead), and write P as packed bf16 over the S columns they have just
@@ -58,8 +62,10 @@ constexpr int ATT_TRACE_EVENTS = 2048;     // per role (0 softmax warp 0, 1 MMA 
         }                                                                                         \
     } while (0)
 
-constexpr int ATT_SM_WARPS = 8;
-constexpr int ATT_THREADS = 32 * (ATT_SM_WARPS + 3);
+constexpr int ATT_SM_WARPS = 8;                   // softmax warps
+constexpr int ATT_AUX_WARPS = 4;                  // Q staging + output warps (one per TMEM lane quarter)
+constexpr int ATT_W_LOADK = ATT_SM_WARPS + ATT_AUX_WARPS, ATT_W_MMA = ATT_W_LOADK + 1, ATT_W_LOADV = ATT_W_LOADK + 2;
+constexpr int ATT_THREADS = 32 * (ATT_SM_WARPS + ATT_AUX_WARPS + 3);
 constexpr int ATT_BQ = 128;
 constexpr int ATT_BK = 128;
 constexpr uint32_t ATT_CHUNK = 128 * 128;      // bytes of a 128-row x 64-col bf16 SWIZZLE_128B tile
@@ -70,7 +76,7 @@ constexpr int ATT_DV = 64;                     // padded head dim of the V opera
 constexpr uint32_t ATT_TMEM_COLS = 512;
 constexpr uint32_t ATT_S_COL0 = 0, ATT_S_COL1 = 128, ATT_O_COL = 256, ATT_Q_COL0 = 320, ATT_Q_COL1 = 416;
 constexpr float ATT_LAZY_LOG2 = 8.0f;          // rescale only when the maximum grew by more than 2^8
-constexpr uint32_t ATT_XCH_BYTES = 2 * 2 * 128 * 4;   // [parity][half][row] float
+constexpr uint32_t ATT_XCH_BYTES = 2 * 2 * 128 * 2 + 2 * 128 * 4;   // row maxima [parity][half][row] bf16 + row sums [half][row] fp32
 constexpr uint32_t ATT_BAR_BYTES = 256;
 
 __host__ __device__ inline uint32_t attn_kstage_bytes(int nchunk, int e_resident) {
@@ -105,12 +111,13 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     uint8_t *sE = sQ + (uint32_t)p.nchunk * ATT_CHUNK;                   // resident E: [key tile][chunk]
     uint8_t *sK = sE + (p.e_resident ? attn_eres_bytes(p.nchunk, p.T) : 0u);
     uint8_t *sV = sK + (uint32_t)p.k_stages * kstage_bytes;
-    float *xch = reinterpret_cast<float *>(sV + (uint32_t)p.v_stages * ATT_CHUNK);   // [2][2][128]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(xch) + ATT_XCH_BYTES);
+    __nv_bfloat16 *xmax = reinterpret_cast<__nv_bfloat16 *>(sV + (uint32_t)p.v_stages * ATT_CHUNK);   // [2][2][128] row maxima
+    float *xl = reinterpret_cast<float *>(xmax + 2 * 2 * 128);                                           // [2][128] row sums
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(xmax) + ATT_XCH_BYTES);
     uint64_t *qfull = bars;             // [1]  Q staging filled by TMA
-    uint64_t *qsempty = bars + 1;       // [1]  Q staging copied out (8 warps)
+    uint64_t *qsempty = bars + 1;       // [1]  Q staging copied out (aux warps)
     uint64_t *efull = bars + 2;         // [1]
-    uint64_t *qtfull = bars + 3;        // [2]  Q copy in TMEM buffer complete (8 warps)
+    uint64_t *qtfull = bars + 3;        // [2]  Q copy in TMEM buffer complete (aux warps)
     uint64_t *sfull = bars + 5;         // [2]
     uint64_t *pfull = bars + 7;         // [2]  (8 warps)
     uint64_t *pvdone = bars + 9;        // [2]
@@ -118,7 +125,10 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     uint64_t *kempty = kfull + ATT_MAXSTAGES;
     uint64_t *vfull = kempty + ATT_MAXSTAGES;   // [v_stages]
     uint64_t *vempty = vfull + ATT_MAXSTAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(vempty + ATT_MAXSTAGES);
+    uint64_t *lfull = vempty + ATT_MAXSTAGES;    // [1]  row sums of an item written (softmax warps)
+    uint64_t *lempty = lfull + 1;                // [1]  row sums read (aux warps)
+    uint64_t *oempty = lfull + 2;                // [1]  O read out (aux warps): the next item's first P V may overwrite it
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(lfull + 3);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qe_cols = 48 + p.d;                                         // columns of one head's Qe block
@@ -148,21 +158,22 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     if (threadIdx.x == 0) {
         if ((smem_u32(smem) & 1023u) != 0u) __trap();
         prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmE);
-        mbar_init(qfull, 1); mbar_init(qsempty, ATT_SM_WARPS); mbar_init(efull, 1);
+        mbar_init(qfull, 1); mbar_init(qsempty, ATT_AUX_WARPS); mbar_init(efull, 1);
+        mbar_init(lfull, ATT_SM_WARPS); mbar_init(lempty, ATT_AUX_WARPS); mbar_init(oempty, ATT_AUX_WARPS);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&qtfull[s], ATT_SM_WARPS); mbar_init(&sfull[s], 1); mbar_init(&pfull[s], ATT_SM_WARPS); mbar_init(&pvdone[s], 1);
+            mbar_init(&qtfull[s], ATT_AUX_WARPS); mbar_init(&sfull[s], 1); mbar_init(&pfull[s], ATT_SM_WARPS); mbar_init(&pvdone[s], 1);
         }
         for (int s = 0; s < p.k_stages; ++s) { mbar_init(&kfull[s], 1); mbar_init(&kempty[s], 1); }
         for (int s = 0; s < p.v_stages; ++s) { mbar_init(&vfull[s], 1); mbar_init(&vempty[s], 1); }
         mbar_fence_init();
     }
-    if (warp == ATT_SM_WARPS + 1) tmem_alloc(tmem_slot, ATT_TMEM_COLS);
+    if (warp == ATT_W_MMA) tmem_alloc(tmem_slot, ATT_TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == ATT_SM_WARPS) {
+    if (warp == ATT_W_LOADK) {
         // ================= TMA producer of Q and K(+E) =================
         if (lane == 0) {
             if (p.e_resident) {
@@ -214,7 +225,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                 for (int j = 1; j < ntiles; ++j) load_k(b, hd, j);
             }
         }
-    } else if (warp == ATT_SM_WARPS + 2) {
+    } else if (warp == ATT_W_LOADV) {
         // ================= TMA producer of V =================
         if (lane == 0) {
             uint32_t g = 0;
@@ -239,7 +250,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                 }
             }
         }
-    } else if (warp == ATT_SM_WARPS + 1) {
+    } else if (warp == ATT_W_MMA) {
         // ================= MMA issuer =================
         // All 32 lanes walk the schedule (identical values in every lane, so they live in uniform registers) and one
         // elected lane issues the tcgen05 instructions: under a divergent `lane == 0` branch the compiler wraps every
@@ -267,10 +278,14 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                 if (pv_done) return;
                 const int st = (int)(g % (uint32_t)p.v_stages);
                 const uint32_t vph = (g / (uint32_t)p.v_stages) & 1u, pph = (g >> 1) & 1u;
+                const bool first = cur.j == 0;                                        // overwrites O: the aux warps must have read it
+                const uint32_t oph = (cur.a & 1u) ^ 1u;
                 if (block) {
                     mbar_wait(&vfull[st], vph);
                     mbar_wait(&pfull[g & 1u], pph);
-                } else if (!__all_sync(0xffffffffu, mbar_test(&pfull[g & 1u], pph) && mbar_test(&vfull[st], vph))) {
+                    if (first) mbar_wait(oempty, oph);
+                } else if (!__all_sync(0xffffffffu, mbar_test(&pfull[g & 1u], pph) && mbar_test(&vfull[st], vph) &&
+                                                       (!first || mbar_test(oempty, oph)))) {
                     return;
                 }
                 ATT_TRACE(1, 250 + cur.j);
@@ -292,34 +307,30 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
             // S of tile c (global index gs); the pending P V of the current tile is slipped in as soon as it is ready
             auto issue_s = [&](const Cur &c, uint32_t gs) {
                 ATT_TRACE(1, 200 + c.j);
-                if (c.j == 0)
-                    while (!__all_sync(0xffffffffu, mbar_test(&qtfull[c.a & 1u], (c.a >> 1) & 1u))) try_pv(false);
+                // plain blocking waits and one uninterrupted burst of MMAs: probing the P barrier between the k-chunks
+                // (mbarrier.test_wait costs ~150 cycles a probe) stretched the issue of one S tile from ~100 to ~1500 cycles
+                if (c.j == 0) mbar_wait(&qtfull[c.a & 1u], (c.a >> 1) & 1u);
                 const int st = (int)(gs % (uint32_t)p.k_stages);
-                while (!__all_sync(0xffffffffu, mbar_test(&kfull[st], (gs / (uint32_t)p.k_stages) & 1u))) try_pv(false);
+                mbar_wait(&kfull[st], (gs / (uint32_t)p.k_stages) & 1u);
                 ATT_TRACE(1, 220 + c.j);
                 tc_fence_after();
                 const uint32_t k_base = smem_u32(sK + (uint32_t)st * kstage_bytes);
                 const uint32_t q_tmem = tmem_base + ((c.a & 1u) ? ATT_Q_COL1 : ATT_Q_COL0);
                 const uint32_t d_s = tmem_base + ((gs & 1u) ? ATT_S_COL1 : ATT_S_COL0);
-                for (int cc = 0; cc < p.nchunk; ++cc) {
-                    uint32_t b_base;
-                    if (cc == 0) b_base = k_base;
-                    else if (p.e_resident) b_base = smem_u32(sE + (uint32_t)(c.j * ne + cc - 1) * ATT_CHUNK);
-                    else b_base = k_base + (uint32_t)cc * ATT_CHUNK;
-                    if (elect_one()) {
+                const uint32_t e_base = p.e_resident ? smem_u32(sE + (uint32_t)(c.j * ne) * ATT_CHUNK) : k_base + ATT_CHUNK;
+                if (elect_one()) {
+                    for (int cc = 0; cc < p.nchunk; ++cc) {
+                        const uint32_t b_base = (cc == 0) ? k_base : e_base + (uint32_t)(cc - 1) * ATT_CHUNK;
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
                             const uint64_t bd = make_smem_desc_sw128(b_base + ks * 32, 1024);
                             umma_bf16_ts(d_s, q_tmem + (uint32_t)(cc * 32 + ks * 8), bd, idesc_s, (cc | ks) ? 1u : 0u);
                         }
-                        if (cc == p.nchunk - 1) {
-                            umma_commit(&sfull[gs & 1u]);
-                            umma_commit(&kempty[st]);                                 // K(+E) slot may be refilled
-                        }
                     }
-                    __syncwarp();
-                    if (cc + 1 < p.nchunk) try_pv(false);
+                    umma_commit(&sfull[gs & 1u]);
+                    umma_commit(&kempty[st]);                                         // K(+E) slot may be refilled
                 }
+                __syncwarp();
             };
             if (cur.valid) issue_s(cur, 0);
             while (cur.valid) {
@@ -331,24 +342,23 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                 ++g;
             }
         }
-    } else {
-        // ================= softmax / output =================
-        const int q = warp & 3, hf = warp >> 2;                  // TMEM lane quarter, half of the keys of a tile
-        const int r = q * 32 + lane;                             // row in the tile == TMEM lane
+    } else if (warp >= ATT_SM_WARPS) {
+        // ================= auxiliary warps: Q staging -> TMEM, output =================
+        const int q = warp & 3;                                  // TMEM lane quarter (ATT_SM_WARPS is a multiple of 4)
+        const int r = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        uint32_t g = 0, xr = 0, na = 0;                          // key tiles, exchange rounds, active items seen
-        int tr_n = (threadIdx.x == 0) ? 0 : ATT_TRACE_EVENTS;
-        // copy the staged Qe tile of active item #a into TMEM buffer a&1: this thread moves its half of row r
+        uint32_t g = 0, na = 0;                                  // key tiles passed, active items seen
+        // the whole row r of the staged Qe tile of active item #a -> TMEM buffer a&1
         auto copy_q = [&](uint32_t a) {
             mbar_wait(qfull, a & 1u);
-            const uint32_t q_tmem = tmem_base + ((a & 1u) ? ATT_Q_COL1 : ATT_Q_COL0) + lane_base + (uint32_t)(hf * p.nchunk * 16);
+            const uint32_t q_tmem = tmem_base + ((a & 1u) ? ATT_Q_COL1 : ATT_Q_COL0) + lane_base;
 #pragma unroll
-            for (int u = 0; u < ATT_MAXCHUNK; ++u) {
-                if (u < p.nchunk) {
+            for (int u = 0; u < 2 * ATT_MAXCHUNK; ++u) {
+                if (u < 2 * p.nchunk) {
                     uint32_t w[16];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const int pi = hf * p.nchunk * 4 + u * 4 + k;                  // 16-byte piece of the row
+                        const int pi = u * 4 + k;                                    // 16-byte piece of the row
                         const uint4 t = *reinterpret_cast<const uint4 *>(sQ + (uint32_t)(pi >> 3) * ATT_CHUNK + sw128_offset(r, pi & 7));
                         w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w;
                     }
@@ -367,15 +377,116 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int b, hd, qt;
             decode(item, b, hd, qt);
-            const int Tk = valid_keys(b);
-            const int ntiles = (Tk + ATT_BK - 1) / ATT_BK;
+            const int ntiles = (valid_keys(b) + ATT_BK - 1) / ATT_BK;
             if (ntiles == 0) {
                 // no keys: emit zeros like the SIMT path
                 const int i = qt * ATT_BQ + r;
                 if (i < p.T)
-                    for (int c = hf; c < p.dh; c += 2) p.ctx[((int64_t)b * p.T + i) * p.d + hd * p.dh + c] = __float2bfloat16_rn(0.0f);
+                    for (int c = 0; c < p.dh; ++c) p.ctx[((int64_t)b * p.T + i) * p.d + hd * p.dh + c] = __float2bfloat16_rn(0.0f);
                 continue;
             }
+            // one item ahead: the TMEM buffer (na+1)&1 was last read by item na-1, whose output (previous iteration) waited
+            // for all of its MMAs
+            {
+                const int nx = next_active(item + gridDim.x);
+                if (nx < p.n_items) copy_q(na + 1);
+            }
+            g += (uint32_t)ntiles;
+            // ---- output: O / l -> ctx (head-major columns hd*dh .. +dh), fragment layout, two 16-row halves ----
+            mbar_wait(lfull, na & 1u);
+            const int rin = lane >> 2, qd = lane & 3;
+            float inv[2][2];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int rowA = q * 32 + hh * 16 + rin, rowB = rowA + 8;
+                const float lA = xl[rowA] + xl[128 + rowA], lB = xl[rowB] + xl[128 + rowB];
+                inv[hh][0] = (lA > 0.0f) ? 1.0f / lA : 0.0f;
+                inv[hh][1] = (lB > 0.0f) ? 1.0f / lB : 0.0f;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(lempty);
+            mbar_wait(&pvdone[(g - 1) & 1u], ((g - 1) >> 1) & 1u);
+            tc_fence_after();
+            const bool odd = qd & 1;
+            const bool vec_ok = (p.dh % 4 == 0) && (p.d % 4 == 0);                     // 8-byte aligned row segments
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int rowA = q * 32 + hh * 16 + rin, rowB = rowA + 8;             // rows of the tile
+                const float invA = inv[hh][0], invB = inv[hh][1];
+                uint32_t o0[16], o1[4];
+                const uint32_t o_addr = tmem_base + ATT_O_COL + ((uint32_t)(q * 32 + hh * 16) << 16);
+                tmem_ld_16x256b_x4(o_addr, o0);
+                tmem_ld_16x256b_x1(o_addr + 32, o1);
+                tmem_ld_wait_dep(o0); tmem_ld_wait_dep(o1);
+                // packed pairs: pa[gq] = row A columns 8*gq + 2*qd, +1
+                uint32_t pa[5], pb[5];
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) {
+                    pa[gq] = attn_pack_bf16x2(__uint_as_float(o0[4 * gq]) * invA, __uint_as_float(o0[4 * gq + 1]) * invA);
+                    pb[gq] = attn_pack_bf16x2(__uint_as_float(o0[4 * gq + 2]) * invB, __uint_as_float(o0[4 * gq + 3]) * invB);
+                }
+                pa[4] = attn_pack_bf16x2(__uint_as_float(o1[0]) * invA, __uint_as_float(o1[1]) * invA);
+                pb[4] = attn_pack_bf16x2(__uint_as_float(o1[2]) * invB, __uint_as_float(o1[3]) * invB);
+                const int iA = qt * ATT_BQ + rowA, iB = qt * ATT_BQ + rowB;           // frame inside the line
+                const bool okA = iA < p.T, okB = iB < p.T;
+                __nv_bfloat16 *dA = p.ctx + ((int64_t)b * p.T + iA) * p.d + hd * p.dh;
+                __nv_bfloat16 *dB = p.ctx + ((int64_t)b * p.T + iB) * p.d + hd * p.dh;
+#pragma unroll
+                for (int gq = 0; gq < 4; gq += 2) {
+                    // neighbouring lanes swap one pair: every lane then owns 4 consecutive columns (8 bytes)
+                    const uint32_t sA = odd ? pa[gq] : pa[gq + 1], sB = odd ? pb[gq] : pb[gq + 1];
+                    const uint32_t rA = __shfl_xor_sync(0xffffffffu, sA, 1), rB = __shfl_xor_sync(0xffffffffu, sB, 1);
+                    const int col = odd ? 8 * (gq + 1) + 2 * (qd - 1) : 8 * gq + 2 * qd;
+                    const uint2 oA = odd ? make_uint2(rA, pa[gq + 1]) : make_uint2(pa[gq], rA);
+                    const uint2 oB = odd ? make_uint2(rB, pb[gq + 1]) : make_uint2(pb[gq], rB);
+                    if (vec_ok && col + 4 <= p.dh) {
+                        if (okA) *reinterpret_cast<uint2 *>(dA + col) = oA;
+                        if (okB) *reinterpret_cast<uint2 *>(dB + col) = oB;
+                    } else {
+                        const __nv_bfloat16 *hA = reinterpret_cast<const __nv_bfloat16 *>(&oA), *hB = reinterpret_cast<const __nv_bfloat16 *>(&oB);
+                        for (int e = 0; e < 4; ++e) {
+                            if (col + e < p.dh) {
+                                if (okA) dA[col + e] = hA[e];
+                                if (okB) dB[col + e] = hB[e];
+                            }
+                        }
+                    }
+                }
+                {
+                    const int col = 32 + 2 * qd;
+                    const __nv_bfloat16 *hA = reinterpret_cast<const __nv_bfloat16 *>(&pa[4]), *hB = reinterpret_cast<const __nv_bfloat16 *>(&pb[4]);
+                    if (col + 2 <= p.dh && (p.dh % 2 == 0) && (p.d % 2 == 0)) {
+                        if (okA) *reinterpret_cast<uint32_t *>(dA + col) = pa[4];
+                        if (okB) *reinterpret_cast<uint32_t *>(dB + col) = pb[4];
+                    } else {
+                        for (int e = 0; e < 2; ++e) {
+                            if (col + e < p.dh) {
+                                if (okA) dA[col + e] = hA[e];
+                                if (okB) dB[col + e] = hB[e];
+                            }
+                        }
+                    }
+                }
+            }
+            // O has been read (wait::ld): the first P V of the next item may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(oempty);
+            ++na;
+        }
+    } else {
+        // ================= softmax =================
+        const int q = warp & 3, hf = warp >> 2;                  // TMEM lane quarter, half of the keys of a tile
+        const int r = q * 32 + lane;                             // row in the tile == TMEM lane
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        uint32_t g = 0, xr = 0, na = 0;                          // key tiles, exchange rounds, active items seen
+        int tr_n = (threadIdx.x == 0) ? 0 : ATT_TRACE_EVENTS;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int b, hd, qt;
+            decode(item, b, hd, qt);
+            const int Tk = valid_keys(b);
+            const int ntiles = (Tk + ATT_BK - 1) / ATT_BK;
+            if (ntiles == 0) continue;                           // the aux warps write the zero rows
             float m_run = -INFINITY, l_run = 0.0f;
             for (int j = 0; j < ntiles; ++j, ++g) {
                 const uint32_t sb = g & 1u;
@@ -400,12 +511,14 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                 float t0 = -INFINITY, t1 = -INFINITY;
 #pragma unroll
                 for (int e = 0; e < 32; ++e) { t0 = fmaxf(t0, __uint_as_float(v0[e])); t1 = fmaxf(t1, __uint_as_float(v1[e])); }
-                // row maximum over both halves (the partner warp holds the other 64 keys); the barrier also orders the
-                // partner's S loads before this warp's P stores into the same TMEM columns
-                float *xb = xch + (xr & 1u) * 256;
-                xb[hf * 128 + r] = fmaxf(t0, t1);
+                // row maximum over both halves (the partner warp holds the other 64 keys), exchanged as bf16: BOTH warps use
+                // the rounded values of both halves, so they agree bit for bit on the reference point (any reference near
+                // the maximum is valid).  The barrier also orders the partner's S loads before this warp's P stores into
+                // the same TMEM columns.
+                __nv_bfloat16 *xb = xmax + (xr & 1u) * 256;
+                xb[hf * 128 + r] = __float2bfloat16_rn(fmaxf(t0, t1));
                 named_bar_sync(1 + q, 64);
-                const float m_new = fmaxf(m_run, fmaxf(fmaxf(t0, t1), xb[(hf ^ 1) * 128 + r]));
+                const float m_new = fmaxf(m_run, fmaxf(__bfloat162float(xb[r]), __bfloat162float(xb[128 + r])));
                 ++xr;
                 if (j == 0) {
                     m_run = m_new;
@@ -461,89 +574,19 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&pfull[sb]);
                 ATT_TRACE(0, 340 + j);
-                if (j == 0) {
-                    // one item ahead: stage the next active item's Q into the other TMEM buffer
-                    const int nx = next_active(item + gridDim.x);
-                    if (nx < p.n_items) copy_q(na + 1);
-                }
             }
+            // hand the row sums to the aux warps (single buffer: wait until they have read the previous item's)
+            mbar_wait(lempty, (na & 1u) ^ 1u);
+            xl[hf * 128 + r] = l_run;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(lfull);
             ++na;
-            // ---- output: O / l -> ctx (head-major columns hd*dh .. +dh), fragment layout, 16 rows per warp ----
-            float *xb = xch + (xr & 1u) * 256;
-            xb[hf * 128 + r] = l_run;
-            named_bar_sync(1 + q, 64);
-            ++xr;
-            const int rin = lane >> 2, qd = lane & 3;
-            const int rowA = q * 32 + hf * 16 + rin, rowB = rowA + 8;                 // rows of the tile
-            const float lA = xb[rowA] + xb[128 + rowA], lB = xb[rowB] + xb[128 + rowB];
-            const float invA = (lA > 0.0f) ? 1.0f / lA : 0.0f, invB = (lB > 0.0f) ? 1.0f / lB : 0.0f;
-            ATT_TRACE(0, 350);
-            mbar_wait(&pvdone[(g - 1) & 1u], ((g - 1) >> 1) & 1u);
-            ATT_TRACE(0, 351);
-            tc_fence_after();
-            uint32_t o0[16], o1[4];
-            const uint32_t o_addr = tmem_base + ATT_O_COL + ((uint32_t)(q * 32 + hf * 16) << 16);
-            tmem_ld_16x256b_x4(o_addr, o0);
-            tmem_ld_16x256b_x1(o_addr + 32, o1);
-            tmem_ld_wait_dep(o0); tmem_ld_wait_dep(o1);
-            // packed pairs: pa[gq] = row A columns 8*gq + 2*qd, +1
-            uint32_t pa[5], pb[5];
-#pragma unroll
-            for (int gq = 0; gq < 4; ++gq) {
-                pa[gq] = attn_pack_bf16x2(__uint_as_float(o0[4 * gq]) * invA, __uint_as_float(o0[4 * gq + 1]) * invA);
-                pb[gq] = attn_pack_bf16x2(__uint_as_float(o0[4 * gq + 2]) * invB, __uint_as_float(o0[4 * gq + 3]) * invB);
-            }
-            pa[4] = attn_pack_bf16x2(__uint_as_float(o1[0]) * invA, __uint_as_float(o1[1]) * invA);
-            pb[4] = attn_pack_bf16x2(__uint_as_float(o1[2]) * invB, __uint_as_float(o1[3]) * invB);
-            const int iA = qt * ATT_BQ + rowA, iB = qt * ATT_BQ + rowB;               // frame inside the line
-            const bool okA = iA < p.T, okB = iB < p.T;
-            __nv_bfloat16 *dA = p.ctx + ((int64_t)b * p.T + iA) * p.d + hd * p.dh;
-            __nv_bfloat16 *dB = p.ctx + ((int64_t)b * p.T + iB) * p.d + hd * p.dh;
-            const bool odd = qd & 1;
-            const bool vec_ok = (p.dh % 4 == 0) && (p.d % 4 == 0);                     // 8-byte aligned row segments
-#pragma unroll
-            for (int gq = 0; gq < 4; gq += 2) {
-                // neighbouring lanes swap one pair: every lane then owns 4 consecutive columns (8 bytes)
-                const uint32_t sA = odd ? pa[gq] : pa[gq + 1], sB = odd ? pb[gq] : pb[gq + 1];
-                const uint32_t rA = __shfl_xor_sync(0xffffffffu, sA, 1), rB = __shfl_xor_sync(0xffffffffu, sB, 1);
-                const int col = odd ? 8 * (gq + 1) + 2 * (qd - 1) : 8 * gq + 2 * qd;
-                const uint2 oA = odd ? make_uint2(rA, pa[gq + 1]) : make_uint2(pa[gq], rA);
-                const uint2 oB = odd ? make_uint2(rB, pb[gq + 1]) : make_uint2(pb[gq], rB);
-                if (vec_ok && col + 4 <= p.dh) {
-                    if (okA) *reinterpret_cast<uint2 *>(dA + col) = oA;
-                    if (okB) *reinterpret_cast<uint2 *>(dB + col) = oB;
-                } else {
-                    const __nv_bfloat16 *hA = reinterpret_cast<const __nv_bfloat16 *>(&oA), *hB = reinterpret_cast<const __nv_bfloat16 *>(&oB);
-                    for (int e = 0; e < 4; ++e) {
-                        if (col + e < p.dh) {
-                            if (okA) dA[col + e] = hA[e];
-                            if (okB) dB[col + e] = hB[e];
-                        }
-                    }
-                }
-            }
-            {
-                const int col = 32 + 2 * qd;
-                const __nv_bfloat16 *hA = reinterpret_cast<const __nv_bfloat16 *>(&pa[4]), *hB = reinterpret_cast<const __nv_bfloat16 *>(&pb[4]);
-                if (col + 2 <= p.dh && (p.dh % 2 == 0) && (p.d % 2 == 0)) {
-                    if (okA) *reinterpret_cast<uint32_t *>(dA + col) = pa[4];
-                    if (okB) *reinterpret_cast<uint32_t *>(dB + col) = pb[4];
-                } else {
-                    for (int e = 0; e < 2; ++e) {
-                        if (col + e < p.dh) {
-                            if (okA) dA[col + e] = hA[e];
-                            if (okB) dB[col + e] = hB[e];
-                        }
-                    }
-                }
-            }
             ATT_TRACE(0, 360);
-            // the O reads above are complete (wait::ld); the next item's first P V is ordered behind them by pfull
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == ATT_SM_WARPS + 1) {
+    if (warp == ATT_W_MMA) {
         tc_fence_after();
         tmem_dealloc(tmem_base, ATT_TMEM_COLS);
     }

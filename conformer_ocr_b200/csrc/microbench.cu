@@ -104,6 +104,80 @@ __global__ void __launch_bounds__(320, 1) k_tmem_ld_bench(int iters, int depth, 
     if (warp == 9) { tc_fence_after(); tmem_dealloc(tb, 512); }
 }
 
+// MMA rate under TMEM load/store traffic from the other warps: warp 8 issues `groups` groups of 12 TS N=128 MMAs (commit +
+// wait per group, like one S tile of the attention kernel) while warps 0-7 loop over tcgen05.ld (mode 1), ld + st (mode 2)
+// or stay idle (mode 0).
+__global__ void __launch_bounds__(320, 1) k_mma_contention_bench(int groups, int mode, int a_tmem, long long *out) {
+    using namespace tc;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    __shared__ volatile int stop;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (64 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); stop = 0; }
+    if (warp == 9) tmem_alloc(&slot, 512);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = slot;
+    if (warp < 8) {
+        if (mode > 0) {
+            const uint32_t base = tb + ((uint32_t)((warp & 3) * 32) << 16) + 128u + (uint32_t)((warp >> 2) * 64);   // the "other" S buffer
+            uint32_t acc = 0;
+            while (!stop) {
+                uint32_t a[32];
+                tmem_ld_32x32b_x32(base, a);
+                tmem_ld_wait_dep(a);
+                acc ^= a[0] ^ a[31];
+                if (mode > 1) {
+                    tmem_st_32x32b_x32(base + 32u, a);
+                    tmem_st_wait();
+                }
+            }
+            if (acc == 0x12345u) out[7] = acc;
+        }
+    } else if (warp == 8) {
+        const uint32_t idesc = make_idesc_bf16(128, 128);
+        const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem + 16384);
+        const long long t0 = clock64();
+        for (int n = 0; n < groups; ++n) {
+            if (elect_one()) {
+#pragma unroll
+                for (int i = 0; i < 12; ++i) {
+                    const uint64_t bd = make_smem_desc_sw128(b_base + (uint32_t)(i >> 2) * 16384u * 0u + (i & 3) * 32, 1024);
+                    if (a_tmem) umma_bf16_ts(tb, tb + 320u + (uint32_t)(i * 8), bd, idesc, i ? 1u : 0u);
+                    else umma_bf16_ss(tb, make_smem_desc_sw128(a_base + (i & 3) * 32, 1024), bd, idesc, i ? 1u : 0u);
+                }
+                umma_commit(&bar);
+            }
+            __syncwarp();
+            mbar_wait(&bar, n & 1);
+        }
+        const long long t1 = clock64();
+        if (threadIdx.x == 256) { out[0] = t1 - t0; stop = 1; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) { tc_fence_after(); tmem_dealloc(tb, 512); }
+}
+
+int selftest_mma_contention(int device, int mode, int a_tmem, double *cycles_per_group) {
+    const int groups = 200;
+    long long *d = nullptr, hres[8] = {0};
+    cudaMalloc((void **)&d, 64);
+    cudaMemset(d, 0, 64);
+    cudaFuncSetAttribute(k_mma_contention_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    k_mma_contention_bench<<<1, 320, 64 * 1024>>>(groups, mode, a_tmem, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(d); return set_error(nullptr, COCR_ERR_CUDA, "mma contention bench: %s", cudaGetErrorString(e)); }
+    cudaMemcpy(hres, d, 64, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (cycles_per_group) *cycles_per_group = (double)hres[0] / groups;
+    return COCR_OK;
+}
+
 int selftest_tmem_bench(int device, int depth, int with_mma, int shape, double *bytes_per_cycle) {
     const int iters = 2000;
     long long *d = nullptr, hres[8] = {0};
