@@ -315,6 +315,18 @@ static int launch_resid_ln(cocr_handle *h, float *x, const bf16 *y, float alpha,
     return COCR_OK;
 }
 
+// private quad-interleaved layout of the residual stream (GemmArgs::x) -> plain row-major rows
+__global__ void k_resid_unpermute(const float *__restrict__ x, float *__restrict__ out, int64_t M, int d) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // one float4 of the private layout
+    const int per_row = d / 4;
+    if (i >= M * per_row) return;
+    const int64_t row = i / per_row;
+    const int s4 = (int)(i - row * per_row), gp = s4 >> 2, q = s4 & 3;
+    const float4 t = *reinterpret_cast<const float4 *>(x + row * d + (int64_t)s4 * 4);
+    float *o = out + row * d + 16 * gp + 2 * q;
+    o[0] = t.x; o[1] = t.y; o[8] = t.z; o[9] = t.w;
+}
+
 __global__ void k_unpack_best(const unsigned long long *__restrict__ packed, int64_t M, float *__restrict__ val,
                               int32_t *__restrict__ idx) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -342,6 +354,8 @@ static int xn_pitch(const cocr_handle *h) {
     static const bool pad = getenv("COCR_XN_PAD") != nullptr;
     return (pad && h->dm.d == 8 * GEMM_RESID_NG) ? (h->dm.d + 63) / 64 * 64 : h->dm.d;
 }
+
+static bool resid_fused(const cocr_handle *h) { return h->dm.d == 8 * GEMM_RESID_NG && !getenv("COCR_SPLIT_RESIDUAL"); }
 
 static bool use_tc_attn(const cocr_handle *h) { return h->bf && h->bf->tc_attn; }
 
@@ -750,7 +764,7 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
     }
     // Residual-stream GEMMs: with encoder_dim 144 the update x += alpha*(..) and the LayerNorm feeding the next module
     // run in the GEMM epilogue (EPI_RESID); otherwise GEMM -> bf16 y -> k_resid_ln.
-    const bool fused = (d == 8 * GEMM_RESID_NG) && !getenv("COCR_SPLIT_RESIDUAL");
+    const bool fused = resid_fused(h);
     // rows [r0, r0 + rows) of the residual stream; A points at the first of those rows
     auto resid_rows = [&](const bf16 *A, int K, const float *Wf, const float *bias, float alpha, int init, const float *gf,
                           const float *bfin, const float *g1, const float *b1, const char *tag, int r0, int rows) -> int {
@@ -841,6 +855,12 @@ int bf16_encode(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_
                 cudaStream_t st, float *enc_out, int32_t *out_lens) {
     Bf16Plan p;
     COCR_TRY(bf16_forward(h, img, sb, sw, sh, widths, B, W, st, out_lens, p));
+    if (resid_fused(h)) {       // the fused residual epilogues keep x in their private layout
+        const int64_t n4 = (int64_t)p.M * (h->dm.d / 4);
+        k_resid_unpermute<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>((const float *)(h->ws.base + p.off_x), enc_out, p.M, h->dm.d);
+        COCR_LAUNCHED(h);
+        return COCR_OK;
+    }
     COCR_CUDA(h, cudaMemcpyAsync(enc_out, h->ws.base + p.off_x, (size_t)p.M * h->dm.d * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return COCR_OK;
 }
@@ -1033,6 +1053,8 @@ int selftest_resid(int device, int M, int N, int K, int flags, double *max_err) 
         cudaMemcpy(gx.data(), x, gx.size() * 4, cudaMemcpyDeviceToHost);
         cudaMemcpy(gn.data(), xn, gn.size() * 2, cudaMemcpyDeviceToHost);
         std::vector<double> v(N);
+        // logical column -> position in the private layout of the residual stream (GemmArgs::x)
+        auto xperm = [](int n) { const int gp = n >> 4, hh = (n >> 3) & 1, q = (n >> 1) & 3, e = n & 1; return 16 * gp + 4 * q + 2 * hh + e; };
         auto lnorm = [&](const float *g, const float *b) {
             double mu = 0, var = 0;
             for (int n = 0; n < N; ++n) mu += v[n];
@@ -1044,10 +1066,10 @@ int selftest_resid(int device, int M, int N, int K, int flags, double *max_err) 
         };
         for (int m = 0; m < M; ++m) {
             for (int n = 0; n < N; ++n)
-                v[n] = init ? (double)href[(size_t)m * N + n] : (double)hx[(size_t)m * N + n] + alpha * (double)href[(size_t)m * N + n];
+                v[n] = init ? (double)href[(size_t)m * N + n] : (double)hx[(size_t)m * N + xperm(n)] + alpha * (double)href[(size_t)m * N + n];
             if (fin) lnorm(hln.data(), hln.data() + N);
             for (int n = 0; n < N; ++n) {
-                double err = fabs((double)gx[(size_t)m * N + n] - v[n]) / (1.0 + fabs(v[n]));
+                double err = fabs((double)gx[(size_t)m * N + xperm(n)] - v[n]) / (1.0 + fabs(v[n]));
                 if (!(err == err)) err = 1e9;
                 worst = fmax(worst, err * 8.0);      // fp32 stream: weighted 8x so one threshold covers both outputs
             }

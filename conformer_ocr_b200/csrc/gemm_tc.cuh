@@ -62,7 +62,11 @@ struct GemmArgs {
     const float *omega;         // (n_omega) angular frequencies: the angle of pair m at frame t is t * omega[m]
     int n_omega, T;             // row r of the GEMM is frame t = r % T of its line
     // EPI_RESID
-    float *x;                   // (M, N) fp32 residual stream, updated in place
+    float *x;                   // (M, N) fp32 residual stream, updated in place.  PRIVATE LAYOUT (only these epilogues and
+                                // k_resid_unpermute touch it): inside a row, each pair of 8-column groups (16 columns) is
+                                // stored as 4 x float4, one per lane of the owning quad: float4 q of pair gp holds columns
+                                // (16gp + 2q, +1, 16gp + 8 + 2q, +1).  Every lane then moves 16 bytes per access and a quad
+                                // covers 64 contiguous bytes: half the memory requests of the plain fragment layout.
     float alpha;                // module factor (0.5 for the half-step FFNs)
     int init;                   // 1: x = acc + bias (start of the stream)
     const float *gf, *bf;       // block-final LayerNorm applied to x itself (or null)
@@ -355,12 +359,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const int64_t rowA = (int64_t)grow0 + hh * 16 + r_in, rowB = rowA + 8;
                     const bool okA = rowA < p.M, okB = rowB < p.M;
                     float2 va[NG], vb[NG];
-                    float *xa = p.x + rowA * (8 * NG) + 2 * qd, *xb = p.x + rowB * (8 * NG) + 2 * qd;
+                    float *xa = p.x + rowA * (8 * NG) + 4 * qd, *xb = p.x + rowB * (8 * NG) + 4 * qd;
                     if (!p.init) {
 #pragma unroll
-                        for (int g = 0; g < NG; ++g) {
-                            va[g] = okA ? *reinterpret_cast<const float2 *>(xa + 8 * g) : make_float2(0.f, 0.f);
-                            vb[g] = okB ? *reinterpret_cast<const float2 *>(xb + 8 * g) : make_float2(0.f, 0.f);
+                        for (int gp = 0; gp < NG / 2; ++gp) {
+                            const float4 ta = okA ? *reinterpret_cast<const float4 *>(xa + 16 * gp) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float4 tb = okB ? *reinterpret_cast<const float4 *>(xb + 16 * gp) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            va[2 * gp] = make_float2(ta.x, ta.y); va[2 * gp + 1] = make_float2(ta.z, ta.w);
+                            vb[2 * gp] = make_float2(tb.x, tb.y); vb[2 * gp + 1] = make_float2(tb.z, tb.w);
                         }
                     }
                     GEMM_TRACE(0, 410 + hh);
@@ -425,11 +431,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             vb[g].x = (vb[g].x - mB) * rB * gg.x + bb.x; vb[g].y = (vb[g].y - mB) * rB * gg.y + bb.y;
                         }
                     }
-                    // x_new: 8 rows x 32-byte sectors per store instruction
+                    // x_new: 8 rows x 64 contiguous bytes per store instruction (private layout, see GemmArgs::x)
 #pragma unroll
-                    for (int g = 0; g < NG; ++g) {
-                        if (okA) *reinterpret_cast<float2 *>(xa + 8 * g) = va[g];
-                        if (okB) *reinterpret_cast<float2 *>(xb + 8 * g) = vb[g];
+                    for (int gp = 0; gp < NG / 2; ++gp) {
+                        if (okA) *reinterpret_cast<float4 *>(xa + 16 * gp) = make_float4(va[2 * gp].x, va[2 * gp].y, va[2 * gp + 1].x, va[2 * gp + 1].y);
+                        if (okB) *reinterpret_cast<float4 *>(xb + 16 * gp) = make_float4(vb[2 * gp].x, vb[2 * gp].y, vb[2 * gp + 1].x, vb[2 * gp + 1].y);
                     }
                     // xn = bf16(LayerNorm_next(x_new)) (or bf16(x_new))
                     float mA = 0.f, rA = 1.f, mB = 0.f, rB = 1.f;

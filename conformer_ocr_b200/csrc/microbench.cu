@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(320, 1) k_mma_contention_bench(int groups, int
     tc_fence_after();
     const uint32_t tb = slot;
     if (warp < 8) {
-        if (mode > 0) {
+        if ((mode % 10) > 0) {
             const uint32_t base = tb + ((uint32_t)((warp & 3) * 32) << 16) + 128u + (uint32_t)((warp >> 2) * 64);   // the "other" S buffer
             uint32_t acc = 0;
             while (!stop) {
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(320, 1) k_mma_contention_bench(int groups, int
                 tmem_ld_32x32b_x32(base, a);
                 tmem_ld_wait_dep(a);
                 acc ^= a[0] ^ a[31];
-                if (mode > 1) {
+                if ((mode % 10) > 1) {
                     tmem_st_32x32b_x32(base + 32u, a);
                     tmem_st_wait();
                 }
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(320, 1) k_mma_contention_bench(int groups, int
             if (elect_one()) {
 #pragma unroll
                 for (int i = 0; i < 12; ++i) {
-                    const uint64_t bd = make_smem_desc_sw128(b_base + (uint32_t)(i >> 2) * 16384u * 0u + (i & 3) * 32, 1024);
+                    const uint64_t bd = make_smem_desc_sw128(b_base + (uint32_t)(i >> 2) * 16384u * (uint32_t)(mode >= 10) + (i & 3) * 32, 1024);
                     if (a_tmem) umma_bf16_ts(tb, tb + 320u + (uint32_t)(i * 8), bd, idesc, i ? 1u : 0u);
                     else umma_bf16_ss(tb, make_smem_desc_sw128(a_base + (i & 3) * 32, 1024), bd, idesc, i ? 1u : 0u);
                 }
