@@ -161,14 +161,18 @@ k_dw_fast(const bf16 *__restrict__ x, const float2 *__restrict__ taps /* [K][P] 
     uint32_t *xs0 = reinterpret_cast<uint32_t *>(ws + K * P);   // 2 x [ROWS][P] bf16x2
     const int nthr = blockDim.x;
     const int c8n = d >> 3;                                 // 16-byte chunks per row
+    // thread -> (first row, 16-byte chunk) of the staging copy, fixed for the whole kernel when the block size is a multiple
+    // of the chunks per row (576 = 32 x 18 for d = 144): no divisions inside the copy loop
+    const int st_row0 = threadIdx.x / c8n, st_c8 = threadIdx.x - st_row0 * c8n;
+    const int st_step = nthr / c8n;                        // rows advanced per pass (nthr % c8n == 0, checked by the launcher)
     auto stage = [&](int item, int buf) {
         const int b = item / n_tt, t0 = (item - b * n_tt) * DWF_TT;
         uint32_t *xs = xs0 + buf * ROWS * P;
-        for (int e = threadIdx.x; e < ROWS * c8n; e += nthr) {
-            const int row = e / c8n, c8 = e - row * c8n;
+        const bf16 *src = x + (int64_t)b * T * d + st_c8 * 8;
+        for (int row = st_row0; row < ROWS; row += st_step) {
             const int t = t0 - pad + row;
             const bool ok = t >= 0 && t < T;
-            cp_async16(xs + row * P + c8 * 4, x + ((int64_t)b * T + (ok ? t : 0)) * d + c8 * 8, ok);
+            cp_async16(xs + row * P + st_c8 * 4, src + (int64_t)(ok ? t : 0) * d, ok);
         }
         cp_async_commit();
     };
@@ -222,7 +226,7 @@ int launch_dw_fast(cocr_handle *h, const bf16 *x, const float *taps_dev, const f
     const Dims &dm = h->dm;
     const int P = dm.d / 2;
     const int nthr = P * (DWF_TT / DWF_SEG);
-    if (dm.K != 31 || (dm.d & 7) != 0 || nthr > 576 || !taps_dev) return COCR_ERR_UNSUPPORTED;
+    if (dm.K != 31 || (dm.d & 7) != 0 || nthr > 576 || !taps_dev || nthr % (dm.d / 8) != 0) return COCR_ERR_UNSUPPORTED;
     const size_t smem = (size_t)2 * (DWF_TT + 30) * P * 4 + (size_t)31 * P * 8;
     static bool attr = false;
     if (!attr) {
