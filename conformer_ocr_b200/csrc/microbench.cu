@@ -211,3 +211,54 @@ int selftest_mma_bench(int device, int N, int chains, int a_tmem_and_count, doub
 }
 
 }  // namespace cocr
+
+// MUFU throughput: 8 warps x `iters` x 16 independent ops per thread; kind 0 ex2.f32, 1 ex2.f16x2, 2 tanh.f32, 3 tanh.f16x2,
+// 4 ex2.bf16x2, 5 rcp.f32.  Reports cycles per warp-instruction per SM sub-partition (2 warps per scheduler).
+namespace cocr {
+template <int kind>
+__global__ void __launch_bounds__(256, 1) k_mufu_bench(int iters, long long *out, float *sink) {
+    float f[16];
+    uint32_t u[16];
+    for (int i = 0; i < 16; ++i) { f[i] = 0.001f * (threadIdx.x + i); u[i] = 0x3c003c00u + threadIdx.x + i; }
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (kind == 0) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(f[i]));
+            else if (kind == 1) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(u[i]));
+            else if (kind == 2) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(f[i]));
+            else if (kind == 3) asm volatile("tanh.approx.f16x2 %0, %0;" : "+r"(u[i]));
+            else if (kind == 4) asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(u[i]));
+            else asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(f[i]));
+        }
+    }
+    const long long t1 = clock64();
+    float s = 0.f;
+    for (int i = 0; i < 16; ++i) s += f[i] + __uint_as_float(u[i]);
+    if (s == 12345.678f) sink[0] = s;
+    if (threadIdx.x == 0) out[0] = t1 - t0;
+}
+
+int selftest_mufu_bench(int device, int kind, double *cycles_per_inst) {
+    const int iters = 2000;
+    long long *d = nullptr, hres = 0;
+    float *sink = nullptr;
+    cudaMalloc((void **)&d, 8); cudaMalloc((void **)&sink, 4);
+    switch (kind) {
+        case 0: k_mufu_bench<0><<<1, 256>>>(iters, d, sink); break;
+        case 1: k_mufu_bench<1><<<1, 256>>>(iters, d, sink); break;
+        case 2: k_mufu_bench<2><<<1, 256>>>(iters, d, sink); break;
+        case 3: k_mufu_bench<3><<<1, 256>>>(iters, d, sink); break;
+        case 4: k_mufu_bench<4><<<1, 256>>>(iters, d, sink); break;
+        default: k_mufu_bench<5><<<1, 256>>>(iters, d, sink); break;
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(d); cudaFree(sink); return set_error(nullptr, COCR_ERR_CUDA, "mufu bench: %s", cudaGetErrorString(e)); }
+    cudaMemcpy(&hres, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d); cudaFree(sink);
+    // 8 warps on 4 schedulers: 2 warps x 16 x iters instructions per scheduler
+    if (cycles_per_inst) *cycles_per_inst = (double)hres / (2.0 * 16.0 * iters);
+    return COCR_OK;
+}
+}  // namespace cocr

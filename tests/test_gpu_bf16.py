@@ -178,3 +178,29 @@ def test_bf16_ragged_mask_mode(cuda_device):
         n = int(ol[i])
         err = rel_err(a[i, :n], b[i, :n])
         assert err < BF16_TOL, f'line {i} (width {widths[i]}): rel err {err}'
+
+
+@pytest.mark.parametrize('B,W', [(1, 5), (3, 100), (5, 1025), (2, 3001), (7, 513), (130, 64)])
+def test_bf16_odd_shapes_against_fp32(B, W, cuda_device):
+    """Degenerate and ragged tile shapes (one frame per line, partial M / query / key tiles, more lines than one CTA wave
+    of work items, streamed E table) on the tensor-core path against the fp32 CUDA path."""
+    from conformer_ocr_b200 import PytorchRecognitionModel
+    hp = dict(O.DEFAULT_HPARAMS)
+    hp['num_encoder_layers'] = 2
+    C = 97
+    w = O.make_weights(hp, C, seed=51)
+    img, lens = O.make_lines(B, 96, W, seed=52 + B)
+    x = torch.from_numpy(img).to(cuda_device)
+    tl = torch.from_numpy(lens)
+    net16 = build_net(hp, C, w, cuda_device)
+    net32 = PytorchRecognitionModel(num_classes=C, codec=None, precision='fp32', **hp, **DROP)
+    net32.nn.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=False)
+    l16, ol16 = net16(x, tl)
+    l32, ol32 = net32(x, tl)
+    assert torch.equal(ol16.cpu(), ol32.cpu())
+    a, b = l16.cpu().numpy(), l32.cpu().numpy()
+    assert np.isfinite(a).all()
+    assert rel_err(a, b) < BF16_TOL
+    got = net16.predict_labels(x, tl)
+    ref = [O.greedy_decoder(a[i, :int(ol16[i])].T) for i in range(B)]
+    assert [[t[:3] for t in l] for l in got] == [[t[:3] for t in l] for l in ref]
