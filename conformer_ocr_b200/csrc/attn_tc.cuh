@@ -46,6 +46,8 @@ struct AttnArgs {
     int n_items;                // B * nh * nqt
     int e_resident;             // 1: E table resident in shared memory
     int k_stages, v_stages;     // ring slots of the K(+E) tiles and of the V tiles
+    int kv_resident;            // 1: a CTA takes whole (line, head) groups; the group's K and V tiles are loaded once into
+                                //    slots 0..tiles-1 and reused by all of its query tiles (needs e_resident, tiles <= stages)
     const int32_t *lens;        // ragged mode: valid frames per line, else null
     __nv_bfloat16 *ctx;         // (B*T, d) head-major context
     float scale_log2;           // log2(e) / sqrt(dh)
@@ -71,13 +73,14 @@ constexpr int ATT_BK = 128;
 constexpr uint32_t ATT_CHUNK = 128 * 128;      // bytes of a 128-row x 64-col bf16 SWIZZLE_128B tile
 constexpr int ATT_MAXCHUNK = 3;
 constexpr int ATT_MAXSTAGES = 4;
+constexpr uint32_t ATT_QSLOTS = 2;             // Qe staging: 64-column chunks pass through two slots on their way to TMEM
 constexpr int ATT_ERES_TILES = 3;              // E resident for T <= 384
 constexpr int ATT_DV = 64;                     // padded head dim of the V operand / O accumulator
 constexpr uint32_t ATT_TMEM_COLS = 512;
 constexpr uint32_t ATT_S_COL0 = 0, ATT_S_COL1 = 128, ATT_O_COL = 256, ATT_Q_COL0 = 320, ATT_Q_COL1 = 416;
 constexpr float ATT_LAZY_LOG2 = 8.0f;          // rescale only when the maximum grew by more than 2^8
 constexpr uint32_t ATT_XCH_BYTES = 2 * 2 * 128 * 2 + 2 * 128 * 4;   // row maxima [parity][half][row] bf16 + row sums [half][row] fp32
-constexpr uint32_t ATT_BAR_BYTES = 256;
+constexpr uint32_t ATT_BAR_BYTES = 288;          // 32 mbarriers + the TMEM base slot
 
 __host__ __device__ inline uint32_t attn_kstage_bytes(int nchunk, int e_resident) {
     return (uint32_t)(e_resident ? 1 : nchunk) * ATT_CHUNK;              // K chunk 0 [+ E chunks]
@@ -86,7 +89,7 @@ __host__ __device__ inline uint32_t attn_eres_bytes(int nchunk, int T) {
     return (uint32_t)((T + ATT_BK - 1) / ATT_BK) * (uint32_t)(nchunk - 1) * ATT_CHUNK;
 }
 __host__ __device__ inline uint32_t attn_smem_bytes(int nchunk, int e_resident, int k_stages, int v_stages, int T) {
-    return (uint32_t)nchunk * ATT_CHUNK + (e_resident ? attn_eres_bytes(nchunk, T) : 0u) +
+    return ATT_QSLOTS * ATT_CHUNK + (e_resident ? attn_eres_bytes(nchunk, T) : 0u) +
            (uint32_t)k_stages * attn_kstage_bytes(nchunk, e_resident) + (uint32_t)v_stages * ATT_CHUNK + ATT_XCH_BYTES + ATT_BAR_BYTES;
 }
 
@@ -107,21 +110,21 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     extern __shared__ __align__(1024) uint8_t smem[];          // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t kstage_bytes = attn_kstage_bytes(p.nchunk, p.e_resident);
     const int ne = p.nchunk - 1;                                         // E chunks per key tile
-    uint8_t *sQ = smem;                                                  // Q staging: nchunk tiles
-    uint8_t *sE = sQ + (uint32_t)p.nchunk * ATT_CHUNK;                   // resident E: [key tile][chunk]
+    uint8_t *sQ = smem;                                                  // Q staging: ATT_QSLOTS chunk slots
+    uint8_t *sE = sQ + ATT_QSLOTS * ATT_CHUNK;                           // resident E: [key tile][chunk]
     uint8_t *sK = sE + (p.e_resident ? attn_eres_bytes(p.nchunk, p.T) : 0u);
     uint8_t *sV = sK + (uint32_t)p.k_stages * kstage_bytes;
     __nv_bfloat16 *xmax = reinterpret_cast<__nv_bfloat16 *>(sV + (uint32_t)p.v_stages * ATT_CHUNK);   // [2][2][128] row maxima
     float *xl = reinterpret_cast<float *>(xmax + 2 * 2 * 128);                                           // [2][128] row sums
     uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(xmax) + ATT_XCH_BYTES);
-    uint64_t *qfull = bars;             // [1]  Q staging filled by TMA
-    uint64_t *qsempty = bars + 1;       // [1]  Q staging copied out (aux warps)
-    uint64_t *efull = bars + 2;         // [1]
-    uint64_t *qtfull = bars + 3;        // [2]  Q copy in TMEM buffer complete (aux warps)
-    uint64_t *sfull = bars + 5;         // [2]
-    uint64_t *pfull = bars + 7;         // [2]  (8 warps)
-    uint64_t *pvdone = bars + 9;        // [2]
-    uint64_t *kfull = bars + 11;        // [k_stages]
+    uint64_t *qcfull = bars;            // [2]  Q chunk slot filled by TMA
+    uint64_t *qcempty = bars + 2;       // [2]  Q chunk slot copied out (aux warps)
+    uint64_t *efull = bars + 4;         // [1]
+    uint64_t *qtfull = bars + 5;        // [2]  Q copy in TMEM buffer complete (aux warps)
+    uint64_t *sfull = bars + 7;         // [2]
+    uint64_t *pfull = bars + 9;         // [2]  (8 warps)
+    uint64_t *pvdone = bars + 11;       // [2]
+    uint64_t *kfull = bars + 13;        // [k_stages]
     uint64_t *kempty = kfull + ATT_MAXSTAGES;
     uint64_t *vfull = kempty + ATT_MAXSTAGES;   // [v_stages]
     uint64_t *vempty = vfull + ATT_MAXSTAGES;
@@ -133,32 +136,50 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qe_cols = 48 + p.d;                                         // columns of one head's Qe block
 
-    auto decode = [&](int item, int &b, int &hd, int &qt) {
-        qt = item % p.nqt;
-        const int bh = item / p.nqt;
-        hd = bh % p.nh;
-        b = bh / p.nh;
-    };
     auto valid_keys = [&](int b) { return p.lens ? min(max(p.lens[b], 0), p.T) : p.T; };   // keys beyond are masked
     const int full_tiles = (p.T + ATT_BK - 1) / ATT_BK;
-    auto key_tiles = [&](int item) {
-        if (!p.lens) return full_tiles;                                   // unmasked: no per-line lookup (and no divisions)
-        int b, hd, qt;
-        decode(item, b, hd, qt);
-        return (valid_keys(b) + ATT_BK - 1) / ATT_BK;
+    // The CTA's work sequence.  Streaming mode deals single items (line, head, query tile) round-robin, q-tile fastest, so
+    // that concurrent CTAs share K/V in L2; kv_resident mode deals whole (line, head) groups and walks the group's query
+    // tiles.  A position is kept in mixed radix (b, hd, qt) and advanced by the CTA stride without any division (a runtime
+    // integer division costs ~100 cycles, and every role walks the sequence on its critical path).
+    struct Pos { int b, hd, qt; };
+    int dqt, dhd, db;                                                    // stride between two units of this CTA
+    Pos pos0;
+    if (p.kv_resident) {
+        dqt = 0; dhd = (int)gridDim.x % p.nh; db = (int)gridDim.x / p.nh;
+        pos0.qt = 0; pos0.hd = (int)blockIdx.x % p.nh; pos0.b = (int)blockIdx.x / p.nh;
+    } else {
+        const int gq = (int)gridDim.x / p.nqt, bq = (int)blockIdx.x / p.nqt;
+        dqt = (int)gridDim.x % p.nqt; dhd = gq % p.nh; db = gq / p.nh;
+        pos0.qt = (int)blockIdx.x % p.nqt; pos0.hd = bq % p.nh; pos0.b = bq / p.nh;
+    }
+    auto seq_valid = [&](const Pos &s) { return s.b < p.B; };
+    auto seq_next = [&](Pos s) {
+        if (p.kv_resident) {
+            if (++s.qt < p.nqt) return s;
+            s.qt = 0;
+        } else {
+            s.qt += dqt;
+            if (s.qt >= p.nqt) { s.qt -= p.nqt; ++s.hd; }
+        }
+        s.hd += dhd;
+        if (s.hd >= p.nh) { s.hd -= p.nh; ++s.b; }
+        s.b += db;
+        return s;
     };
-    // first item >= `item` of this CTA's sequence that has at least one key tile (n_items when there is none)
-    auto next_active = [&](int item) {
-        if (!p.lens) return min(item, p.n_items);
-        for (; item < p.n_items; item += gridDim.x)
-            if (key_tiles(item) > 0) return item;
-        return p.n_items;
+    auto key_tiles = [&](const Pos &s) { return p.lens ? (valid_keys(s.b) + ATT_BK - 1) / ATT_BK : full_tiles; };
+    // first position from s on whose item has at least one key tile (or the end)
+    auto next_active = [&](Pos s) {
+        if (p.lens)
+            while (seq_valid(s) && key_tiles(s) == 0) s = seq_next(s);
+        return s;
     };
 
     if (threadIdx.x == 0) {
         if ((smem_u32(smem) & 1023u) != 0u) __trap();
         prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmE);
-        mbar_init(qfull, 1); mbar_init(qsempty, ATT_AUX_WARPS); mbar_init(efull, 1);
+        for (int s = 0; s < (int)ATT_QSLOTS; ++s) { mbar_init(&qcfull[s], 1); mbar_init(&qcempty[s], ATT_AUX_WARPS); }
+        mbar_init(efull, 1);
         mbar_init(lfull, ATT_SM_WARPS); mbar_init(lempty, ATT_AUX_WARPS); mbar_init(oempty, ATT_AUX_WARPS);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&qtfull[s], ATT_AUX_WARPS); mbar_init(&sfull[s], 1); mbar_init(&pfull[s], ATT_SM_WARPS); mbar_init(&pvdone[s], 1);
@@ -183,11 +204,13 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                     for (int c = 0; c < ne; ++c)
                         tma_load_2d(sE + (uint32_t)(j * ne + c) * ATT_CHUNK, &tmE, efull, c * 64, j * ATT_BK);
             }
-            uint32_t g = 0, nq = 0;                                       // global key-tile counter, Q loads issued
+            uint32_t g = 0, qc = 0, kpar = 0;                             // key tiles loaded, Q chunks loaded, slot parities
             int tr_n = 0;
             auto load_k = [&](int b, int hd, int j) {
-                const int st = (int)(g % (uint32_t)p.k_stages);
-                const uint32_t ph = (g / (uint32_t)p.k_stages) & 1u;
+                int st;
+                uint32_t ph;
+                if (p.kv_resident) { st = j; ph = (kpar >> j) & 1u; kpar ^= 1u << j; }
+                else { st = (int)(g % (uint32_t)p.k_stages); ph = (g / (uint32_t)p.k_stages) & 1u; }
                 mbar_wait(&kempty[st], ph ^ 1u);
                 ATT_TRACE(2, 110 + j);
                 mbar_expect_tx(&kfull[st], kstage_bytes);
@@ -198,53 +221,55 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                 ++g;
             };
             // the tiles of the NEXT item are requested into L2 while the current one is processed: the activations do
-            // not fit L2 between kernels, so a tile fetched only when its ring slot frees would pay HBM latency
-            auto prefetch_item = [&](int item) {
-                if (item >= p.n_items) return;
-                int b, hd, qt;
-                decode(item, b, hd, qt);
-                const int ntiles = key_tiles(item);
+            // not fit L2 between kernels, so a tile fetched only when its slot frees would pay HBM latency
+            auto prefetch_item = [&](const Pos &s) {
+                if (!seq_valid(s)) return;
+                const int ntiles = key_tiles(s);
                 if (ntiles == 0) return;
-                for (int c = 0; c < p.nchunk; ++c) tma_prefetch_2d(&tmQ, hd * qe_cols + c * 64, b * p.T + qt * ATT_BQ);
-                for (int j = 0; j < ntiles; ++j) tma_prefetch_2d(&tmK, hd * 64, b * p.T + j * ATT_BK);
+                for (int c = 0; c < p.nchunk; ++c) tma_prefetch_2d(&tmQ, s.hd * qe_cols + c * 64, s.b * p.T + s.qt * ATT_BQ);
+                if (!p.kv_resident || s.qt == 0)
+                    for (int j = 0; j < ntiles; ++j) tma_prefetch_2d(&tmK, s.hd * 64, s.b * p.T + j * ATT_BK);
             };
-            prefetch_item(blockIdx.x);
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                int b, hd, qt;
-                decode(item, b, hd, qt);
-                const int ntiles = key_tiles(item);
-                prefetch_item(item + gridDim.x);
+            prefetch_item(pos0);
+            for (Pos s = pos0; seq_valid(s); s = seq_next(s)) {
+                const int b = s.b, hd = s.hd, qt = s.qt;
+                const int ntiles = key_tiles(s);
+                prefetch_item(seq_next(s));
                 if (ntiles == 0) continue;
-                load_k(b, hd, 0);                                         // does not depend on the Q staging buffer
-                mbar_wait(qsempty, (nq & 1u) ^ 1u);                       // the previous Q has been copied into TMEM
-                ATT_TRACE(2, 121);
-                mbar_expect_tx(qfull, (uint32_t)p.nchunk * ATT_CHUNK);
-                for (int c = 0; c < p.nchunk; ++c)
-                    tma_load_2d(sQ + (uint32_t)c * ATT_CHUNK, &tmQ, qfull, hd * qe_cols + c * 64, b * p.T + qt * ATT_BQ);
-                ++nq;
-                for (int j = 1; j < ntiles; ++j) load_k(b, hd, j);
+                const bool need_k = !p.kv_resident || qt == 0;            // resident mode: the group's K tiles are loaded once
+                if (need_k) load_k(b, hd, 0);                             // does not depend on the Q staging slots
+                for (int c = 0; c < p.nchunk; ++c, ++qc) {
+                    const uint32_t sl = qc % ATT_QSLOTS;
+                    mbar_wait(&qcempty[sl], ((qc / ATT_QSLOTS) & 1u) ^ 1u);   // the slot's previous chunk has been copied into TMEM
+                    ATT_TRACE(2, 121 + c);
+                    mbar_expect_tx(&qcfull[sl], ATT_CHUNK);
+                    tma_load_2d(sQ + sl * ATT_CHUNK, &tmQ, &qcfull[sl], hd * qe_cols + c * 64, b * p.T + qt * ATT_BQ);
+                }
+                if (need_k)
+                    for (int j = 1; j < ntiles; ++j) load_k(b, hd, j);
             }
         }
     } else if (warp == ATT_W_LOADV) {
         // ================= TMA producer of V =================
         if (lane == 0) {
-            uint32_t g = 0;
-            auto prefetch_item = [&](int item) {
-                if (item >= p.n_items) return;
-                int b, hd, qt;
-                decode(item, b, hd, qt);
-                const int ntiles = key_tiles(item);
-                for (int j = 0; j < ntiles; ++j) tma_prefetch_2d(&tmV, hd * 64, b * p.T + j * ATT_BK);
+            uint32_t g = 0, vpar = 0;
+            auto prefetch_item = [&](const Pos &s) {
+                if (!seq_valid(s) || (p.kv_resident && s.qt != 0)) return;
+                const int ntiles = key_tiles(s);
+                for (int j = 0; j < ntiles; ++j) tma_prefetch_2d(&tmV, s.hd * 64, s.b * p.T + j * ATT_BK);
             };
-            prefetch_item(blockIdx.x);
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                int b, hd, qt;
-                decode(item, b, hd, qt);
-                const int ntiles = key_tiles(item);
-                prefetch_item(item + gridDim.x);
+            prefetch_item(pos0);
+            for (Pos s = pos0; seq_valid(s); s = seq_next(s)) {
+                const int b = s.b, hd = s.hd;
+                const int ntiles = key_tiles(s);
+                prefetch_item(seq_next(s));
+                if (p.kv_resident && s.qt != 0) continue;
                 for (int j = 0; j < ntiles; ++j, ++g) {
-                    const int st = (int)(g % (uint32_t)p.v_stages);
-                    mbar_wait(&vempty[st], ((g / (uint32_t)p.v_stages) & 1u) ^ 1u);
+                    int st;
+                    uint32_t ph;
+                    if (p.kv_resident) { st = j; ph = (vpar >> j) & 1u; vpar ^= 1u << j; }
+                    else { st = (int)(g % (uint32_t)p.v_stages); ph = (g / (uint32_t)p.v_stages) & 1u; }
+                    mbar_wait(&vempty[st], ph ^ 1u);
                     mbar_expect_tx(&vfull[st], ATT_CHUNK);
                     tma_load_2d(sV + (uint32_t)st * ATT_CHUNK, &tmV, &vfull[st], hd * 64, b * p.T + j * ATT_BK);
                 }
@@ -260,34 +285,37 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
             const uint32_t idesc_o = make_idesc_bf16(ATT_BQ, ATT_DV, 0, 1);           // O += P V     (P in TMEM, V MN-major)
             if (p.e_resident) mbar_wait(efull, 0);
             // flat walk over (item, key tile) with one tile of look-ahead
-            struct Cur { int item, j, ntiles; uint32_t a; bool valid; };             // a = index among the active items
-            auto first_from = [&](int item, uint32_t a) {
-                Cur c{next_active(item), 0, 0, a, false};
-                if (c.item < p.n_items) { c.ntiles = key_tiles(c.item); c.valid = true; }
+            // s = position in the CTA's sequence, a = index among the active items; first/last = first/last query tile
+            // of a K/V-resident group (both true in streaming mode: every item loads and releases its own tiles)
+            struct Cur { Pos s; int j, ntiles; uint32_t a; bool first, last, valid; };
+            auto first_from = [&](const Pos &s, uint32_t a) {
+                Cur c{next_active(s), 0, 0, a, true, true, false};
+                if (seq_valid(c.s)) {
+                    c.ntiles = key_tiles(c.s);
+                    c.valid = true;
+                    if (p.kv_resident) { c.first = c.s.qt == 0; c.last = c.s.qt == p.nqt - 1; }
+                }
                 return c;
             };
             auto next_of = [&](const Cur &c) {
-                if (c.j + 1 < c.ntiles) return Cur{c.item, c.j + 1, c.ntiles, c.a, true};
-                return first_from(c.item + gridDim.x, c.a + 1);
+                if (c.j + 1 < c.ntiles) { Cur n = c; ++n.j; return n; }
+                return first_from(seq_next(c.s), c.a + 1);
             };
             int tr_n = (lane == 0) ? 0 : ATT_TRACE_EVENTS;
-            uint32_t g = 0;
-            Cur cur = first_from(blockIdx.x, 0);
-            bool pv_done = true;                                                      // no P V pending before the first tile
-            auto try_pv = [&](bool block) {
-                if (pv_done) return;
-                const int st = (int)(g % (uint32_t)p.v_stages);
-                const uint32_t vph = (g / (uint32_t)p.v_stages) & 1u, pph = (g >> 1) & 1u;
-                const bool first = cur.j == 0;                                        // overwrites O: the aux warps must have read it
-                const uint32_t oph = (cur.a & 1u) ^ 1u;
-                if (block) {
-                    mbar_wait(&vfull[st], vph);
-                    mbar_wait(&pfull[g & 1u], pph);
-                    if (first) mbar_wait(oempty, oph);
-                } else if (!__all_sync(0xffffffffu, mbar_test(&pfull[g & 1u], pph) && mbar_test(&vfull[st], vph) &&
-                                                       (!first || mbar_test(oempty, oph)))) {
-                    return;
+            uint32_t g = 0, kpar = 0, vpar = 0;                                       // resident mode: per-slot barrier parities
+            Cur cur = first_from(pos0, 0);
+            // P V of the current tile (global index g)
+            auto issue_pv = [&]() {
+                int st;
+                if (p.kv_resident) {
+                    st = cur.j;
+                    if (cur.first) { mbar_wait(&vfull[st], (vpar >> st) & 1u); vpar ^= 1u << st; }
+                } else {
+                    st = (int)(g % (uint32_t)p.v_stages);
+                    mbar_wait(&vfull[st], (g / (uint32_t)p.v_stages) & 1u);
                 }
+                mbar_wait(&pfull[g & 1u], (g >> 1) & 1u);
+                if (cur.j == 0) mbar_wait(oempty, (cur.a & 1u) ^ 1u);                 // overwrites O: the aux warps must have read it
                 ATT_TRACE(1, 250 + cur.j);
                 tc_fence_after();
                 const uint32_t v_base = smem_u32(sV + (uint32_t)st * ATT_CHUNK);
@@ -298,11 +326,10 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                         const uint64_t bd = make_smem_desc_sw128(v_base + ks * 2048, 1024);
                         umma_bf16_ts(tmem_base + ATT_O_COL, p_tmem + (uint32_t)ks * 8u, bd, idesc_o, (cur.j | ks) ? 1u : 0u);
                     }
-                    umma_commit(&vempty[st]);          // V slot may be refilled
-                    umma_commit(&pvdone[g & 1u]);      // O up to date
+                    if (cur.last) umma_commit(&vempty[st]);   // V slot may be refilled
+                    umma_commit(&pvdone[g & 1u]);             // O up to date
                 }
                 __syncwarp();
-                pv_done = true;
             };
             // S of tile c (global index gs); the pending P V of the current tile is slipped in as soon as it is ready
             auto issue_s = [&](const Cur &c, uint32_t gs) {
@@ -310,8 +337,14 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                 // plain blocking waits and one uninterrupted burst of MMAs: probing the P barrier between the k-chunks
                 // (mbarrier.test_wait costs ~150 cycles a probe) stretched the issue of one S tile from ~100 to ~1500 cycles
                 if (c.j == 0) mbar_wait(&qtfull[c.a & 1u], (c.a >> 1) & 1u);
-                const int st = (int)(gs % (uint32_t)p.k_stages);
-                mbar_wait(&kfull[st], (gs / (uint32_t)p.k_stages) & 1u);
+                int st;
+                if (p.kv_resident) {
+                    st = c.j;
+                    if (c.first) { mbar_wait(&kfull[st], (kpar >> st) & 1u); kpar ^= 1u << st; }
+                } else {
+                    st = (int)(gs % (uint32_t)p.k_stages);
+                    mbar_wait(&kfull[st], (gs / (uint32_t)p.k_stages) & 1u);
+                }
                 ATT_TRACE(1, 220 + c.j);
                 tc_fence_after();
                 const uint32_t k_base = smem_u32(sK + (uint32_t)st * kstage_bytes);
@@ -328,16 +361,15 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                         }
                     }
                     umma_commit(&sfull[gs & 1u]);
-                    umma_commit(&kempty[st]);                                         // K(+E) slot may be refilled
+                    if (c.last) umma_commit(&kempty[st]);                             // K(+E) slot may be refilled
                 }
                 __syncwarp();
             };
             if (cur.valid) issue_s(cur, 0);
             while (cur.valid) {
                 const Cur nxt = next_of(cur);
-                pv_done = false;
                 if (nxt.valid) issue_s(nxt, g + 1);
-                try_pv(true);
+                issue_pv();
                 cur = nxt;
                 ++g;
             }
@@ -347,37 +379,36 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
         const int q = warp & 3;                                  // TMEM lane quarter (ATT_SM_WARPS is a multiple of 4)
         const int r = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        uint32_t g = 0, na = 0;                                  // key tiles passed, active items seen
-        // the whole row r of the staged Qe tile of active item #a -> TMEM buffer a&1
+        uint32_t g = 0, na = 0, qc = 0;                          // key tiles passed, active items seen, Q chunks copied
+        // row r of the Qe tile of active item #a, chunk by chunk from the staging slots -> TMEM buffer a&1
         auto copy_q = [&](uint32_t a) {
-            mbar_wait(qfull, a & 1u);
             const uint32_t q_tmem = tmem_base + ((a & 1u) ? ATT_Q_COL1 : ATT_Q_COL0) + lane_base;
+            for (int c = 0; c < p.nchunk; ++c, ++qc) {
+                const uint32_t sl = qc % ATT_QSLOTS;
+                mbar_wait(&qcfull[sl], (qc / ATT_QSLOTS) & 1u);
+                const uint8_t *src = sQ + sl * ATT_CHUNK;
 #pragma unroll
-            for (int u = 0; u < 2 * ATT_MAXCHUNK; ++u) {
-                if (u < 2 * p.nchunk) {
+                for (int u = 0; u < 2; ++u) {
                     uint32_t w[16];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int pi = u * 4 + k;                                    // 16-byte piece of the row
-                        const uint4 t = *reinterpret_cast<const uint4 *>(sQ + (uint32_t)(pi >> 3) * ATT_CHUNK + sw128_offset(r, pi & 7));
+                    for (int k = 0; k < 4; ++k) {                                    // 16-byte pieces of the row
+                        const uint4 t = *reinterpret_cast<const uint4 *>(src + sw128_offset(r, u * 4 + k));
                         w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w;
                     }
-                    tmem_st_32x32b_x16n(q_tmem + (uint32_t)u * 16u, w);
+                    tmem_st_32x32b_x16n(q_tmem + (uint32_t)(c * 32 + u * 16), w);
                 }
+                __syncwarp();                                                        // the stores consumed the shared-memory reads
+                if (lane == 0) mbar_arrive(&qcempty[sl]);
             }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(qsempty); mbar_arrive(&qtfull[a & 1u]); }
+            if (lane == 0) mbar_arrive(&qtfull[a & 1u]);
         };
-        {
-            const int first = next_active(blockIdx.x);
-            if (first < p.n_items) copy_q(0);
-        }
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-            int b, hd, qt;
-            decode(item, b, hd, qt);
-            const int ntiles = (valid_keys(b) + ATT_BK - 1) / ATT_BK;
+        if (seq_valid(next_active(pos0))) copy_q(0);
+        for (Pos s = pos0; seq_valid(s); s = seq_next(s)) {
+            const int b = s.b, hd = s.hd, qt = s.qt;
+            const int ntiles = key_tiles(s);
             if (ntiles == 0) {
                 // no keys: emit zeros like the SIMT path
                 const int i = qt * ATT_BQ + r;
@@ -387,10 +418,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
             }
             // one item ahead: the TMEM buffer (na+1)&1 was last read by item na-1, whose output (previous iteration) waited
             // for all of its MMAs
-            {
-                const int nx = next_active(item + gridDim.x);
-                if (nx < p.n_items) copy_q(na + 1);
-            }
+            if (seq_valid(next_active(seq_next(s)))) copy_q(na + 1);
             g += (uint32_t)ntiles;
             // ---- output: O / l -> ctx (head-major columns hd*dh .. +dh), fragment layout, two 16-row halves ----
             mbar_wait(lfull, na & 1u);
@@ -481,10 +509,8 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         uint32_t g = 0, xr = 0, na = 0;                          // key tiles, exchange rounds, active items seen
         int tr_n = (threadIdx.x == 0) ? 0 : ATT_TRACE_EVENTS;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-            int b, hd, qt;
-            decode(item, b, hd, qt);
-            const int Tk = valid_keys(b);
+        for (Pos s = pos0; seq_valid(s); s = seq_next(s)) {
+            const int Tk = valid_keys(s.b);
             const int ntiles = (Tk + ATT_BK - 1) / ATT_BK;
             if (ntiles == 0) continue;                           // the aux warps write the zero rows
             float m_run = -INFINITY, l_run = 0.0f;

@@ -575,9 +575,16 @@ static int launch_attn_tc(cocr_handle *h, const bf16 *qkvx, const int32_t *lens,
     // E table resident in shared memory when it leaves room for the Q tile and two-deep K and V rings
     const uint32_t cap = (uint32_t)bs->smem_optin;
     a.e_resident = (a.nqt <= ATT_ERES_TILES && attn_smem_bytes(bs->nchunk, 1, 2, 2, T) <= cap && !getenv("COCR_ATTN_STREAM_E")) ? 1 : 0;
-    a.k_stages = 2; a.v_stages = 2;
-    while (a.k_stages < ATT_MAXSTAGES && attn_smem_bytes(bs->nchunk, a.e_resident, a.k_stages + 1, a.v_stages, T) <= cap) ++a.k_stages;
-    while (a.v_stages < ATT_MAXSTAGES && attn_smem_bytes(bs->nchunk, a.e_resident, a.k_stages, a.v_stages + 1, T) <= cap) ++a.v_stages;
+    // K/V-resident groups: every K and V tile of a (line, head) is read once instead of once per query tile
+    a.kv_resident = (a.e_resident && a.nqt >= 2 && a.nqt <= ATT_MAXSTAGES && attn_smem_bytes(bs->nchunk, 1, a.nqt, a.nqt, T) <= cap &&
+                     !getenv("COCR_ATTN_STREAM_KV")) ? 1 : 0;
+    if (a.kv_resident) {
+        a.k_stages = a.v_stages = a.nqt;
+    } else {
+        a.k_stages = 2; a.v_stages = 2;
+        while (a.k_stages < ATT_MAXSTAGES && attn_smem_bytes(bs->nchunk, a.e_resident, a.k_stages + 1, a.v_stages, T) <= cap) ++a.k_stages;
+        while (a.v_stages < ATT_MAXSTAGES && attn_smem_bytes(bs->nchunk, a.e_resident, a.k_stages, a.v_stages + 1, T) <= cap) ++a.v_stages;
+    }
     const uint32_t smem = attn_smem_bytes(bs->nchunk, a.e_resident, a.k_stages, a.v_stages, T);
     if (smem > cap) return set_error(h, COCR_ERR_UNSUPPORTED, "attention tiles do not fit shared memory");
     static bool attr = false;
@@ -585,7 +592,8 @@ static int launch_attn_tc(cocr_handle *h, const bf16 *qkvx, const int32_t *lens,
         COCR_CUDA(h, cudaFuncSetAttribute(k_attn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->smem_optin));
         attr = true;
     }
-    const int grid = a.n_items < h->num_sms ? a.n_items : h->num_sms;
+    const int n_units = a.kv_resident ? B * dm.nh : a.n_items;              // what the CTAs deal out among themselves
+    const int grid = n_units < h->num_sms ? n_units : h->num_sms;
     a.trace = nullptr;
     static int traced = 0;
     const char *trace_path = getenv("COCR_ATTN_TRACE");

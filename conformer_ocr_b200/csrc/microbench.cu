@@ -194,6 +194,143 @@ int selftest_tmem_bench(int device, int depth, int with_mma, int shape, double *
     return COCR_OK;
 }
 
+// The attention kernel's tensor-pipe sequence without any softmax: per key tile one S group (12 TS MMAs, N=128, K-major B,
+// alternating accumulators) and one P V group (8 TS MMAs into O).  mode bits: 1 = P V with MN-major B (as in the kernel),
+// 2 = P V with N=48 instead of 64, 4 = no P V, 8 = no S, 16 = wait for every group's commit (else every 4th pair),
+// 32 = P V as 4 MMAs of K=32?? (not available for bf16: ignored), 64 = S as 6 MMAs with N=256 (two key tiles per group).
+// bits 128 / 256 / 512: warps 2-9 loop like the softmax warps: 128 = tcgen05.ld of 2 x 32 columns + tcgen05.st of 32,
+// 256 = 64 x (fma, ex2, add) + 32 packs per thread, 512 = a shared-memory exchange + 64-thread named barrier.
+__global__ void __launch_bounds__(320, 1) k_attn_mma_bench(int pairs, int mode, long long *out) {
+    using namespace tc;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    __shared__ volatile int stop;
+    __shared__ float xch[256];
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (128 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); stop = 0; }
+    if (warp == 0) tmem_alloc(&slot, 512);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = slot;
+    if (warp == 1) {
+        const int nv = (mode & 2) ? 48 : 64;
+        const uint32_t idesc_s = make_idesc_bf16(128, 128), idesc_s2 = make_idesc_bf16(128, 256);
+        const uint32_t idesc_o = make_idesc_bf16(128, nv, 0, (mode & 1) ? 1 : 0);
+        const uint32_t k_base = smem_u32(smem), v_base = smem_u32(smem + 65536);
+        uint32_t ph = 0;
+        long long t_issue = 0;
+        const long long t0 = clock64();
+        for (int n = 0; n < pairs; ++n) {
+            const long long ti = clock64();
+            if (elect_one()) {
+                if (!(mode & 8)) {
+                    if (mode & 64) {
+                        if (!(n & 1))
+                            for (int i = 0; i < 12; ++i)
+                                umma_bf16_ts(tb, tb + 320u + (uint32_t)(i * 8), make_smem_desc_sw128(k_base + (uint32_t)(i >> 2) * 16384u + (i & 3) * 32, 1024), idesc_s2, i ? 1u : 0u);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 12; ++i)
+                            umma_bf16_ts(tb + (uint32_t)((n & 1) * 128), tb + 320u + (uint32_t)(i * 8),
+                                         make_smem_desc_sw128(k_base + (uint32_t)(i >> 2) * 16384u + (i & 3) * 32, 1024), idesc_s, i ? 1u : 0u);
+                    }
+                }
+                if (!(mode & 4)) {
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint64_t bd = (mode & 1) ? make_smem_desc_sw128(v_base + ks * 2048, 1024) : make_smem_desc_sw128(v_base + (ks & 3) * 32, 1024);
+                        umma_bf16_ts(tb + 256u, tb + (uint32_t)(((n + 1) & 1) * 128) + (uint32_t)ks * 8u, bd, idesc_o, ks ? 1u : 0u);
+                    }
+                }
+                if ((mode & 16) || (n & 3) == 3 || n == pairs - 1) umma_commit(&bar);
+            }
+            __syncwarp();
+            t_issue += clock64() - ti;
+            if ((mode & 16) || (n & 3) == 3 || n == pairs - 1) { mbar_wait(&bar, ph); ph ^= 1u; }
+        }
+        const long long t1 = clock64();
+        if (threadIdx.x == 32) { out[0] = t1 - t0; out[1] = t_issue; stop = 1; }
+    } else if (warp >= 2 && (mode & (128 | 256 | 512))) {
+        const int w = warp - 2, q = warp & 3, hf = w >> 2, r = q * 32 + (threadIdx.x & 31);
+        const uint32_t base = tb + ((uint32_t)(q * 32) << 16) + 384u + (uint32_t)(hf * 64);   // columns the MMAs do not touch
+        uint32_t v0[32], v1[32];
+        for (int e = 0; e < 32; ++e) { v0[e] = __float_as_uint(0.001f * (threadIdx.x + e)); v1[e] = __float_as_uint(0.002f * (threadIdx.x - e)); }
+        float acc = 0.f;
+        long long n = 0;
+        // with the named barrier both warps of a pair must run the same number of rounds: fixed count that outlasts the MMAs
+        for (;;) {
+            if ((mode & 512) ? (n >= 2 * pairs) : (stop != 0)) break;
+            if (mode & 128) {
+                tmem_ld_32x32b_x32(base, v0);
+                tmem_ld_32x32b_x32(base + 32, v1);
+                tmem_ld_wait_dep(v0); tmem_ld_wait_dep(v1);
+            }
+            float mb = acc * 1e-9f;
+            if (mode & 512) {
+                xch[hf * 128 + r] = __uint_as_float(v0[3]);
+                named_bar_sync(1 + q, 64);
+                mb += xch[r] + xch[128 + r];
+            }
+            uint32_t pk[32];
+            if (mode & 256) {
+                float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    float p0, p1;
+                    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v0[2 * e]), 0.3f, -mb)));
+                    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v0[2 * e + 1]), 0.3f, -mb)));
+                    ps0 += p0; ps1 += p1;
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+                    pk[e] = *reinterpret_cast<uint32_t *>(&h2);
+                }
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    float p0, p1;
+                    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v1[2 * e]), 0.3f, -mb)));
+                    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v1[2 * e + 1]), 0.3f, -mb)));
+                    ps0 += p0; ps1 += p1;
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+                    pk[16 + e] = *reinterpret_cast<uint32_t *>(&h2);
+                }
+                acc += ps0 + ps1;
+            } else {
+                for (int e = 0; e < 32; ++e) pk[e] = v0[e] ^ v1[e];
+            }
+            if (mode & 128) {
+                tmem_st_32x32b_x32(base, pk);
+                tmem_st_wait();
+            } else {
+                for (int e = 0; e < 32; ++e) acc += __uint_as_float(pk[e]);
+            }
+            ++n;
+        }
+        if (acc == 12345.678f) out[7] = 1;
+        if (threadIdx.x == 64) out[2] = n;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tb, 512); }
+}
+
+int selftest_attn_mma_bench(int device, int mode, int what, double *cycles_per_pair) {
+    const int pairs = 400;
+    long long *d = nullptr, hres[8] = {0};
+    cudaMalloc((void **)&d, 64);
+    cudaMemset(d, 0, 64);
+    cudaFuncSetAttribute(k_attn_mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    k_attn_mma_bench<<<1, 320, 128 * 1024>>>(pairs, mode, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(d); return set_error(nullptr, COCR_ERR_CUDA, "attention mma bench: %s", cudaGetErrorString(e)); }
+    cudaMemcpy(hres, d, 64, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (cycles_per_pair) *cycles_per_pair = what == 2 ? (double)hres[0] / (double)(hres[2] > 0 ? hres[2] : 1) : (double)hres[what ? 1 : 0] / pairs;
+    return COCR_OK;
+}
+
 int selftest_mma_bench(int device, int N, int chains, int a_tmem_and_count, double *cycles_per_mma) {
     const int a_tmem = a_tmem_and_count % 10;
     const int count = a_tmem_and_count >= 10 ? a_tmem_and_count / 10 : 64;     // MMAs per commit group

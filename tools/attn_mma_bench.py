@@ -1,0 +1,16 @@
+"""Tensor-pipe cost of the attention kernel's MMA sequence (cocr_selftest 44): cycles per key tile, total and issue-side,
+alone and with eight warps imitating the softmax warps (TMEM traffic / MUFU+FMA work / named barriers)."""
+import ctypes, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from conformer_ocr_b200 import _lib
+lib = _lib.load()
+names = {1: 'PV MN-major', 2: 'PV N=48', 4: 'no PV', 8: 'no S', 16: 'commit+wait every group', 64: 'S as N=256',
+         128: 'sm:tmem', 256: 'sm:ex2', 512: 'sm:barrier'}
+modes = [int(a) for a in sys.argv[1:]] or [1, 1 + 128, 1 + 256, 1 + 512, 1 + 128 + 256, 1 + 128 + 256 + 512, 17 + 128 + 256 + 512, 4 + 128 + 256 + 512, 9 + 128 + 256 + 512]
+for mode in modes:
+    tot, iss, sm = ctypes.c_double(-1), ctypes.c_double(-1), ctypes.c_double(-1)
+    rc = lib.cocr_selftest(0, 44, mode, 0, 0, ctypes.byref(tot))
+    rc |= lib.cocr_selftest(0, 44, mode, 1, 0, ctypes.byref(iss))
+    rc |= lib.cocr_selftest(0, 44, mode, 2, 0, ctypes.byref(sm))
+    desc = ', '.join(v for k, v in names.items() if mode & k) or 'S(12xN128) + PV(8xN64 K-major)'
+    print(f'mode {mode:4d} [{desc}]: {tot.value:7.1f} cycles/tile, issue thread busy {iss.value:7.1f}, softmax-like loop {sm.value:7.1f} cycles/iter rc={rc}')
