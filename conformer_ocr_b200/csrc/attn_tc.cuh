@@ -78,6 +78,7 @@ constexpr int ATT_ERES_TILES = 3;              // E resident for T <= 384
 constexpr int ATT_DV = 64;                     // padded head dim of the V operand / O accumulator
 constexpr uint32_t ATT_TMEM_COLS = 512;
 constexpr uint32_t ATT_S_COL0 = 0, ATT_S_COL1 = 128, ATT_O_COL = 256, ATT_Q_COL0 = 320, ATT_Q_COL1 = 416;
+constexpr int ATT_POLY_EVERY = 64;
 constexpr float ATT_LAZY_LOG2 = 8.0f;          // rescale only when the maximum grew by more than 2^8
 constexpr uint32_t ATT_XCH_BYTES = 2 * 2 * 128 * 2 + 2 * 128 * 4;   // row maxima [parity][half][row] bf16 + row sums [half][row] fp32
 constexpr uint32_t ATT_BAR_BYTES = 288;          // 32 mbarriers + the TMEM base slot
@@ -97,6 +98,39 @@ __device__ __forceinline__ float ex2_fast(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+// packed fp32 pairs (FFMA2 / FADD2): one issue slot for two elements
+__device__ __forceinline__ float2 attn_fma2(float2 a, float2 b, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)),
+        "l"(*reinterpret_cast<unsigned long long *>(&c)));
+    return *reinterpret_cast<float2 *>(&r);
+}
+__device__ __forceinline__ float2 attn_add2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+    return *reinterpret_cast<float2 *>(&r);
+}
+// 2^x for a pair on the FMA pipe (the MUFU unit is the softmax bottleneck: 8 cycles per warp instruction): round-to-nearest
+// split x = n + f, f in [-0.5, 0.5], by the 1.5*2^23 trick, cubic minimax polynomial for 2^f (relative error 1.0e-4, far
+// below the bf16 rounding of P), exponent added as an integer.  x <= 0 up to the lazy-rescale slack; -inf (masked) -> 0.
+__device__ __forceinline__ float2 attn_ex2_poly2(float2 x) {
+    const float magic = 12582912.0f;                                    // 1.5 * 2^23
+    x.x = fmaxf(x.x, -125.0f); x.y = fmaxf(x.y, -125.0f);
+    const float2 t = attn_add2(x, make_float2(magic, magic));           // integer part in the low mantissa bits
+    const float2 n = attn_add2(t, make_float2(-magic, -magic));
+    const float2 f = attn_add2(x, make_float2(-n.x, -n.y));
+    float2 q = attn_fma2(f, make_float2(0.05500843f, 0.05500843f), make_float2(0.24220999f, 0.24220999f));
+    q = attn_fma2(q, f, make_float2(0.69328287f, 0.69328287f));
+    q = attn_fma2(q, f, make_float2(1.0f, 1.0f));
+    q.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
+    q.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
+    return q;
+}
+__device__ __forceinline__ float attn_max3(float a, float b, float c) {       // FMNMX3: one issue slot for two comparisons
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
 }
 __device__ __forceinline__ uint32_t attn_pack_bf16x2(float a, float b) {
     __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
@@ -536,7 +570,10 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                 }
                 float t0 = -INFINITY, t1 = -INFINITY;
 #pragma unroll
-                for (int e = 0; e < 32; ++e) { t0 = fmaxf(t0, __uint_as_float(v0[e])); t1 = fmaxf(t1, __uint_as_float(v1[e])); }
+                for (int e = 0; e < 32; e += 2) {
+                    t0 = attn_max3(t0, __uint_as_float(v0[e]), __uint_as_float(v0[e + 1]));
+                    t1 = attn_max3(t1, __uint_as_float(v1[e]), __uint_as_float(v1[e + 1]));
+                }
                 // row maximum over both halves (the partner warp holds the other 64 keys), exchanged as bf16: BOTH warps use
                 // the rounded values of both halves, so they agree bit for bit on the reference point (any reference near
                 // the maximum is valid).  The barrier also orders the partner's S loads before this warp's P stores into
@@ -577,22 +614,21 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                 ATT_TRACE(0, 320 + j);
                 // probabilities -> packed bf16 in TMEM: keys [hf*64, hf*64+64) of P live in columns [hf*32, hf*32+32)
                 const float mb = m_run * p.scale_log2;
-                float ps0 = 0.f, ps1 = 0.f;
+                const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nmb2 = make_float2(-mb, -mb);
+                float2 ps = make_float2(0.f, 0.f);
                 uint32_t pk[32];
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const float p0 = ex2_fast(fmaf(__uint_as_float(v0[2 * e]), p.scale_log2, -mb));
-                    const float p1 = ex2_fast(fmaf(__uint_as_float(v0[2 * e + 1]), p.scale_log2, -mb));
-                    ps0 += p0; ps1 += p1;
-                    pk[e] = attn_pack_bf16x2(p0, p1);
+                for (int e = 0; e < 32; ++e) {
+                    const float2 s2 = e < 16 ? make_float2(__uint_as_float(v0[2 * e]), __uint_as_float(v0[2 * e + 1]))
+                                             : make_float2(__uint_as_float(v1[2 * e - 32]), __uint_as_float(v1[2 * e - 31]));
+                    const float2 x = attn_fma2(s2, sc2, nmb2);
+                    float2 pr;
+                    if (e % ATT_POLY_EVERY == ATT_POLY_EVERY - 1) pr = attn_ex2_poly2(x);      // this pair on the FMA pipe
+                    else pr = make_float2(ex2_fast(x.x), ex2_fast(x.y));
+                    ps = attn_add2(ps, pr);
+                    pk[e] = attn_pack_bf16x2(pr.x, pr.y);
                 }
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const float p0 = ex2_fast(fmaf(__uint_as_float(v1[2 * e]), p.scale_log2, -mb));
-                    const float p1 = ex2_fast(fmaf(__uint_as_float(v1[2 * e + 1]), p.scale_log2, -mb));
-                    ps0 += p0; ps1 += p1;
-                    pk[16 + e] = attn_pack_bf16x2(p0, p1);
-                }
+                const float ps0 = ps.x, ps1 = ps.y;
                 tmem_st_32x32b_x32(s_base + (uint32_t)(hf * 32), pk);
                 l_run += ps0 + ps1;
                 tmem_st_wait();

@@ -200,16 +200,18 @@ int selftest_tmem_bench(int device, int depth, int with_mma, int shape, double *
 // 32 = P V as 4 MMAs of K=32?? (not available for bf16: ignored), 64 = S as 6 MMAs with N=256 (two key tiles per group).
 // bits 128 / 256 / 512: warps 2-9 loop like the softmax warps: 128 = tcgen05.ld of 2 x 32 columns + tcgen05.st of 32,
 // 256 = 64 x (fma, ex2, add) + 32 packs per thread, 512 = a shared-memory exchange + 64-thread named barrier.
-__global__ void __launch_bounds__(320, 1) k_attn_mma_bench(int pairs, int mode, long long *out) {
+// bit 2048: warp 10 streams 16 KB bulk copies (global -> shared, two in flight) into a spare shared-memory region.
+__global__ void __launch_bounds__(352, 1) k_attn_mma_bench(int pairs, int mode, long long *out, const uint8_t *src) {
     using namespace tc;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t slot;
     __shared__ volatile int stop;
     __shared__ float xch[256];
+    __shared__ uint64_t cbar[2];
     const int warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < (128 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;
-    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); stop = 0; }
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&cbar[0], 1); mbar_init(&cbar[1], 1); mbar_fence_init(); stop = 0; }
     if (warp == 0) tmem_alloc(&slot, 512);
     fence_proxy_async_smem();
     tc_fence_before();
@@ -253,7 +255,29 @@ __global__ void __launch_bounds__(320, 1) k_attn_mma_bench(int pairs, int mode, 
             if ((mode & 16) || (n & 3) == 3 || n == pairs - 1) { mbar_wait(&bar, ph); ph ^= 1u; }
         }
         const long long t1 = clock64();
-        if (threadIdx.x == 32) { out[0] = t1 - t0; out[1] = t_issue; stop = 1; }
+        if (threadIdx.x == 32) { if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t_issue; } stop = 1; }
+    } else if (warp == 10) {
+        if ((mode & 2048) && (threadIdx.x & 31) == 0) {
+            long long n = 0;
+            const uint8_t *my = src + (size_t)blockIdx.x * (64 * 1024);
+            for (; !stop; ++n) {
+                const int sl = (int)(n & 1);
+                if (n >= 2) mbar_wait(&cbar[sl], (uint32_t)((n >> 1) - 1) & 1u);
+                mbar_expect_tx(&cbar[sl], 16384);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(smem_u32(smem + 96 * 1024 + sl * 16384)), "l"(my + (n & 3) * 16384), "r"(16384), "r"(smem_u32(&cbar[sl])) : "memory");
+            }
+            // drain
+            if (n >= 1) mbar_wait(&cbar[(n - 1) & 1], (uint32_t)(((n - 1) >> 1)) & 1u);
+            if (n >= 2) mbar_wait(&cbar[(n - 2) & 1], (uint32_t)(((n - 2) >> 1)) & 1u);
+            if (blockIdx.x == 0) out[3] = n;
+        }
+    } else if (warp >= 2 && (mode & (4096 | 8192))) {
+        // pollers: every lane (4096) or lane 0 only (8192) spins on a barrier that never completes
+        long long n = 0;
+        if ((mode & 4096) || (threadIdx.x & 31) == 0)
+            while (!stop) { if (mbar_try_wait(&cbar[1], 1u ^ 1u ^ 0u)) break; ++n; }
+        if (threadIdx.x == 64 && blockIdx.x == 0) out[2] = n;
     } else if (warp >= 2 && (mode & (128 | 256 | 512))) {
         const int w = warp - 2, q = warp & 3, hf = w >> 2, r = q * 32 + (threadIdx.x & 31);
         const uint32_t base = tb + ((uint32_t)(q * 32) << 16) + 384u + (uint32_t)(hf * 64);   // columns the MMAs do not touch
@@ -309,25 +333,81 @@ __global__ void __launch_bounds__(320, 1) k_attn_mma_bench(int pairs, int mode, 
             ++n;
         }
         if (acc == 12345.678f) out[7] = 1;
-        if (threadIdx.x == 64) out[2] = n;
+        if (threadIdx.x == 64 && blockIdx.x == 0) out[2] = n;
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) { tc_fence_after(); tmem_dealloc(tb, 512); }
 }
 
-int selftest_attn_mma_bench(int device, int mode, int what, double *cycles_per_pair) {
+int selftest_attn_mma_bench(int device, int mode, int what, int grid, double *cycles_per_pair) {
     const int pairs = 400;
     long long *d = nullptr, hres[8] = {0};
+    uint8_t *src = nullptr;
+    if (grid < 1) grid = 1;
     cudaMalloc((void **)&d, 64);
+    cudaMalloc((void **)&src, (size_t)grid * 64 * 1024);
     cudaMemset(d, 0, 64);
+    cudaMemset(src, 0x3c, (size_t)grid * 64 * 1024);
     cudaFuncSetAttribute(k_attn_mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-    k_attn_mma_bench<<<1, 320, 128 * 1024>>>(pairs, mode, d);
+    k_attn_mma_bench<<<grid, 352, 128 * 1024>>>(pairs, mode, d, src);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { cudaFree(d); return set_error(nullptr, COCR_ERR_CUDA, "attention mma bench: %s", cudaGetErrorString(e)); }
     cudaMemcpy(hres, d, 64, cudaMemcpyDeviceToHost);
     cudaFree(d);
+    cudaFree(src);
+    if (what == 3) { if (cycles_per_pair) *cycles_per_pair = 16384.0 * (double)hres[3] / (double)hres[0]; return COCR_OK; }   // copy bytes per cycle
     if (cycles_per_pair) *cycles_per_pair = what == 2 ? (double)hres[0] / (double)(hres[2] > 0 ? hres[2] : 1) : (double)hres[what ? 1 : 0] / pairs;
+    return COCR_OK;
+}
+
+// mbarrier hand-shake latency: warps 0 and 1 play ping-pong over two mbarriers (`rounds` round trips); mode 0: every lane
+// waits with try_wait, 1: lane 0 waits with try_wait then __syncwarp, 2: every lane spins on test_wait, 3: lane 0 spins on
+// test_wait then __syncwarp.  +16: warps 2..13 sit suspended in try_wait on a barrier that completes only at the end.
+// +32: the "pong" is a tcgen05.commit instead of a plain arrive (warp 1 elects one lane).
+__global__ void __launch_bounds__(448, 1) k_mbar_pingpong(int rounds, int mode, long long *out) {
+    using namespace tc;
+    __shared__ uint64_t bars[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_fence_init(); }
+    __syncthreads();
+    const int wm = mode & 3;
+    auto wait = [&](uint64_t *b, uint32_t par) {
+        if (wm == 0) mbar_wait(b, par);
+        else if (wm == 1) { if (lane == 0) mbar_wait(b, par); __syncwarp(); }
+        else if (wm == 2) { while (!mbar_test(b, par)) {} }
+        else { if (lane == 0) { while (!mbar_test(b, par)) {} } __syncwarp(); }
+    };
+    if (warp == 0) {
+        const long long t0 = clock64();
+        for (int i = 0; i < rounds; ++i) {
+            if (lane == 0) mbar_arrive(&bars[0]);
+            wait(&bars[1], i & 1);
+        }
+        const long long t1 = clock64();
+        if (lane == 0) { out[0] = t1 - t0; mbar_arrive(&bars[2]); }
+    } else if (warp == 1) {
+        for (int i = 0; i < rounds; ++i) {
+            wait(&bars[0], i & 1);
+            if (mode & 32) { if (elect_one()) umma_commit(&bars[1]); __syncwarp(); }
+            else if (lane == 0) mbar_arrive(&bars[1]);
+        }
+    } else if (mode & 16) {
+        mbar_wait(&bars[2], 0);
+    }
+}
+
+int selftest_mbar_pingpong(int device, int mode, double *cycles_per_hop) {
+    const int rounds = 2000;
+    long long *d = nullptr, hres = 0;
+    cudaMalloc((void **)&d, 8);
+    cudaMemset(d, 0, 8);
+    k_mbar_pingpong<<<1, 448>>>(rounds, mode, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(d); return set_error(nullptr, COCR_ERR_CUDA, "mbarrier ping-pong: %s", cudaGetErrorString(e)); }
+    cudaMemcpy(&hres, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (cycles_per_hop) *cycles_per_hop = (double)hres / (2.0 * rounds);
     return COCR_OK;
 }
 
