@@ -11,6 +11,7 @@
 #include "common.h"
 #include "gemm_tc.cuh"
 #include "attn_tc.cuh"
+#include "ffn_tc.cuh"
 
 namespace cocr {
 
@@ -32,6 +33,8 @@ struct Bf16State {
     bf16 *w_pw1g = nullptr;       // (L, 2d, d)
     float *b_pw1g = nullptr;      // (L, 2d)
     bf16 *w_fe_pw2 = nullptr;     // (cc, 2 cc): [Wpw | Wpw] for the hi/lo split 1x1 conv GEMM of the front-end
+    bf16 *w_ffn2p = nullptr;      // (L, 2, ff, d): FFN-down weights cut into 144-column k-chunks stacked along the rows
+                                  // (row c*144 + n, column k = W2[n][c*144 + k]) for the fused FFN kernel (ffn_tc.cuh)
     float *dw_taps = nullptr;     // (L, K*d + d): depthwise taps [k][pair](2) * bn_scale / 2, then bn_shift / 2
     int tab_T = 0;
 };
@@ -624,6 +627,76 @@ static int launch_attn_tc(cocr_handle *h, const bf16 *qkvx, const int32_t *lens,
     return COCR_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// fused feed-forward module (ffn_tc.cuh)
+// ------------------------------------------------------------------------------------------
+static bool ffn_fused_ok(const cocr_handle *h) {
+    return h->dm.d == FFN_D && h->dm.ff % FFN_D == 0 && h->dm.ff / FFN_D <= FFN_MAX_NC && !getenv("COCR_FFN_SPLIT") && !getenv("COCR_SPLIT_RESIDUAL");
+}
+
+// W2 (d, ff) -> (ff, d): row c*d + n, column k  <-  W2[n][c*d + k]
+__global__ void k_pack_ffn2(const bf16 *w2, bf16 *out, int d, int ff) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d * ff) return;
+    const int row = i / d, k = i - row * d;
+    const int c = row / d, n = row - c * d;
+    out[i] = w2[(size_t)n * ff + c * d + k];
+}
+
+// x <- x + alpha * FFN(xn) [-> LN_final]; xn_out = bf16(LN_next(x)).  w1: (ff, d) bf16 scaled by 1/2, b1 scaled by 1/2,
+// w2p: packed by k_pack_ffn2.  xn_out may alias xn (a tile is written after it has been read, and only by its own CTA).
+static int launch_ffn_fused(cocr_handle *h, const bf16 *xn, int ldx, const bf16 *w1, const float *b1, const bf16 *w2p, const float *b2,
+                            float *x, bf16 *xn_out, int ldo, float alpha, const float *gf, const float *bfin, const float *g1, const float *b1n,
+                            int M, int ff, cudaStream_t st, const char *tag) {
+    if (M <= 0) return COCR_OK;
+    if (ff % FFN_D != 0 || ff / FFN_D > FFN_MAX_NC || ldx % 8 != 0 || ldo % 4 != 0)
+        return set_error(h, COCR_ERR_UNSUPPORTED, "fused FFN needs ff = 144 * n (n <= %d) and aligned rows (ff=%d ldx=%d ldo=%d)", FFN_MAX_NC, ff, ldx, ldo);
+    if (FFN_SMEM_BYTES > (uint32_t)h->bf->smem_optin) return set_error(h, COCR_ERR_UNSUPPORTED, "fused FFN does not fit shared memory");
+    FfnArgs a;
+    a.M = M; a.NC = ff / FFN_D; a.m_tiles = (M + 127) / 128;
+    a.b1 = b1; a.b2 = b2; a.x = x; a.xn_out = xn_out; a.ldo = ldo; a.alpha = alpha;
+    a.gf = gf; a.bf = bfin; a.g1 = g1; a.b1n = b1n;
+    { static const int dbg = getenv("COCR_FFN_DBG") ? atoi(getenv("COCR_FFN_DBG")) : 0; a.dbg = dbg; }
+    CUtensorMap tmX, tmW1, tmW2;
+    COCR_TRY(make_tmap_bf16(h, &tmX, xn, M, FFN_D, ldx, 128));
+    COCR_TRY(make_tmap_bf16(h, &tmW1, w1, ff, FFN_D, FFN_D, FFN_D));
+    COCR_TRY(make_tmap_bf16(h, &tmW2, w2p, ff, FFN_D, FFN_D, FFN_D));
+    static bool attr = false;
+    if (!attr) {
+        COCR_CUDA(h, cudaFuncSetAttribute(k_ffn_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FFN_SMEM_BYTES));
+        attr = true;
+    }
+    const int grid = a.m_tiles < h->num_sms ? a.m_tiles : h->num_sms;
+    ProfScope ps(h, tag, st, 4.0 * M * (double)ff * FFN_D, (double)M * FFN_D * (2.0 + 2.0 + 4.0 + 4.0) + 4.0 * ff * FFN_D);
+    // COCR_FFN_TRACE=<file>: the 5th launch writes a (role, tag, clock) trace of CTA 0
+    a.trace = nullptr;
+    long long *trace_dev = nullptr;
+    const char *trace_file = getenv("COCR_FFN_TRACE");
+    {
+        static int seen = 0;
+        if (trace_file && ++seen == 5) {
+            COCR_CUDA(h, cudaMalloc((void **)&trace_dev, (size_t)3 * GEMM_TRACE_EVENTS * 16));
+            COCR_CUDA(h, cudaMemset(trace_dev, 0, (size_t)3 * GEMM_TRACE_EVENTS * 16));
+            a.trace = trace_dev;
+        }
+    }
+    k_ffn_fused<<<grid, FFN_THREADS, FFN_SMEM_BYTES, st>>>(tmX, tmW1, tmW2, a);
+    COCR_LAUNCHED(h);
+    if (trace_dev) {
+        COCR_CUDA(h, cudaStreamSynchronize(st));
+        std::vector<long long> hb((size_t)3 * GEMM_TRACE_EVENTS * 2);
+        COCR_CUDA(h, cudaMemcpy(hb.data(), trace_dev, hb.size() * 8, cudaMemcpyDeviceToHost));
+        cudaFree(trace_dev);
+        if (FILE *fp = fopen(trace_file, "w")) {
+            for (int role = 0; role < 3; ++role)
+                for (int e = 0; e < GEMM_TRACE_EVENTS; ++e)
+                    if (hb[((size_t)role * GEMM_TRACE_EVENTS + e) * 2]) fprintf(fp, "%d %lld %lld\n", role, hb[((size_t)role * GEMM_TRACE_EVENTS + e) * 2], hb[((size_t)role * GEMM_TRACE_EVENTS + e) * 2 + 1]);
+            fclose(fp);
+        }
+    }
+    return COCR_OK;
+}
+
 int bf16_init(cocr_handle *h) {
     const Dims &dm = h->dm;
     if (dm.d % 16 != 0 || dm.ff % 16 != 0 || dm.feat % 16 != 0 || dm.d > 32 * ROW_MAXPER)
@@ -648,6 +721,17 @@ int bf16_init(cocr_handle *h) {
             k_scale_f32<<<(dm.ff + 255) / 256, 256>>>(h->arena + (h->layers[l].ffn_b1[f] - h->arena), (size_t)dm.ff, 0.5f);
         }
     COCR_LAUNCHED(h);
+    if (bs->w_ffn2p) { cudaFree(bs->w_ffn2p); bs->w_ffn2p = nullptr; }
+    if (ffn_fused_ok(h) && dm.L > 0) {
+        const size_t nw = (size_t)dm.ff * dm.d;
+        void *pw = nullptr;
+        COCR_CUDA(h, cudaMalloc(&pw, (size_t)dm.L * 2 * nw * sizeof(bf16)));
+        bs->w_ffn2p = (bf16 *)pw;
+        for (int l = 0; l < dm.L; ++l)
+            for (int f = 0; f < 2; ++f)
+                k_pack_ffn2<<<(unsigned)((nw + 255) / 256), 256>>>(bs->arena + (h->layers[l].ffn_w2[f] - h->arena), bs->w_ffn2p + ((size_t)l * 2 + f) * nw, dm.d, dm.ff);
+        COCR_LAUNCHED(h);
+    }
     {
         // pw1 for the GLU epilogue (convolution.py:138-139): GEMM column 2c = value channel c, 2c+1 = gate channel d + c
         const int d = dm.d;
@@ -721,6 +805,7 @@ void bf16_destroy(cocr_handle *h) {
     if (bs->b_pw1g) cudaFree(bs->b_pw1g);
     if (bs->dw_taps) cudaFree(bs->dw_taps);
     if (bs->w_fe_pw2) cudaFree(bs->w_fe_pw2);
+    if (bs->w_ffn2p) cudaFree(bs->w_ffn2p);
     delete h->bf;
     h->bf = nullptr;
 }
@@ -803,6 +888,9 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
     const int ffn_lines = chunk_lines((size_t)dm.ff * 2, "COCR_FFN_CHUNKS");
     auto ffn_module = [&](int l, int f, const float *gf, const float *bfin, const float *g1, const float *b1, const char *tag_down) -> int {
         const LayerF32 &lw = h->layers[l];
+        if (fused && h->bf->w_ffn2p)      // one kernel, the hidden activation stays on the SM
+            return launch_ffn_fused(h, xn, ldx, WB(h, lw.ffn_w1[f]), lw.ffn_b1[f], h->bf->w_ffn2p + ((size_t)l * 2 + f) * dm.ff * d, lw.ffn_b2[f], x, xn,
+                                    ldx, dm.ffn_factor, gf, bfin, g1, b1, M, dm.ff, st, f ? "ffn_fused_final" : "ffn_fused");
         for (int b0 = 0; b0 < B; b0 += ffn_lines) {
             const int nb = std::min(ffn_lines, B - b0), r0 = b0 * p.T, rows = nb * p.T;
             COCR_TRY(launch_gemm_tc(h, EPI_BF16_SILU, xn + (size_t)r0 * ldx, ldx, WB(h, lw.ffn_w1[f]), d, lw.ffn_b1[f], hb, dm.ff, nullptr, rows,
@@ -1096,6 +1184,109 @@ int selftest_resid(int device, int M, int N, int K, int flags, double *max_err) 
     }
     if (max_err) *max_err = worst;
     cudaFree(A); cudaFree(Wt); cudaFree(xn); cudaFree(bias); cudaFree(ref); cudaFree(x); cudaFree(ln);
+    cocr_destroy(h);
+    return rc;
+}
+
+
+// fused FFN kernel against a host reference: M rows, ff = 144 * NC; flags: 2 block-final LayerNorm, 4 next LayerNorm;
+// 8: time 20 launches and print us per launch to stderr
+int selftest_ffn(int device, int M, int NC, int flags, double *max_err) {
+    cocr_hparams hp = {96, 144, 0, 4, 4, 2, 31, 1, 32, 4, 0, COCR_FP32, 0};
+    cocr_handle *h = nullptr;
+    int rc = cocr_create(&hp, device, &h);
+    if (rc != COCR_OK) return rc;
+    h->bf = new Bf16State();
+    cudaDeviceGetAttribute(&h->bf->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    const int d = FFN_D, ff = NC * FFN_D;
+    bf16 *xn, *w1, *w2, *w2p, *xo;
+    float *b1, *b2, *x, *ln, *href;
+    cudaMalloc((void **)&xn, (size_t)M * d * 2); cudaMalloc((void **)&xo, (size_t)M * d * 2);
+    cudaMalloc((void **)&w1, (size_t)ff * d * 2); cudaMalloc((void **)&w2, (size_t)ff * d * 2); cudaMalloc((void **)&w2p, (size_t)ff * d * 2);
+    cudaMalloc((void **)&b1, (size_t)ff * 4); cudaMalloc((void **)&b2, (size_t)d * 4); cudaMalloc((void **)&x, (size_t)M * d * 4);
+    cudaMalloc((void **)&ln, (size_t)4 * d * 4); cudaMalloc((void **)&href, (size_t)M * ff * 4);
+    k_fill_bf16<<<(unsigned)(((size_t)M * d + 255) / 256), 256>>>(xn, (size_t)M * d, 11u, 1.0f);
+    k_fill_bf16<<<(unsigned)(((size_t)ff * d + 255) / 256), 256>>>(w1, (size_t)ff * d, 12u, 0.2f);
+    k_fill_bf16<<<(unsigned)(((size_t)ff * d + 255) / 256), 256>>>(w2, (size_t)ff * d, 13u, 0.1f);
+    k_fill_f32<<<(ff + 255) / 256, 256>>>(b1, (size_t)ff, 14u, 0.5f);
+    k_fill_f32<<<(d + 255) / 256, 256>>>(b2, (size_t)d, 15u, 0.5f);
+    k_fill_f32<<<(unsigned)(((size_t)M * d + 255) / 256), 256>>>(x, (size_t)M * d, 16u, 2.0f);
+    k_fill_f32<<<(4 * d + 255) / 256, 256>>>(ln, (size_t)4 * d, 17u, 1.0f);
+    k_pack_ffn2<<<(unsigned)(((size_t)ff * d + 255) / 256), 256>>>(w2, w2p, d, ff);
+    k_ref_gemm<<<(unsigned)(((size_t)M * ff + 255) / 256), 256>>>(xn, w1, b1, href, M, ff, d, 0);     // h = xn W1^T + b1 (the "half" pre-activation)
+    std::vector<float> hx((size_t)M * d), hh((size_t)M * ff), hln(4 * d), hb2(d);
+    std::vector<uint16_t> hw2((size_t)ff * d);
+    cudaMemcpy(hx.data(), x, hx.size() * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(hh.data(), href, hh.size() * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(hln.data(), ln, hln.size() * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(hb2.data(), b2, hb2.size() * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(hw2.data(), w2, hw2.size() * 2, cudaMemcpyDeviceToHost);
+    const bool fin = flags & 2, nxt = flags & 4;
+    const float alpha = 0.5f;
+    rc = launch_ffn_fused(h, xn, d, w1, b1, w2p, b2, x, xo, d, alpha, fin ? ln : nullptr, fin ? ln + d : nullptr, nxt ? ln + 2 * d : nullptr,
+                          nxt ? ln + 3 * d : nullptr, M, ff, 0, "selftest_ffn");
+    cudaError_t e = cudaDeviceSynchronize();
+    if (rc == COCR_OK && e != cudaSuccess) rc = set_error(h, COCR_ERR_CUDA, "selftest_ffn: %s", cudaGetErrorString(e));
+    double worst = 0.0;
+    if (rc == COCR_OK) {
+        std::vector<float> gx((size_t)M * d);
+        std::vector<uint16_t> gn((size_t)M * d);
+        cudaMemcpy(gx.data(), x, gx.size() * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(gn.data(), xo, gn.size() * 2, cudaMemcpyDeviceToHost);
+        auto bf2f = [](uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; };
+        auto f2bf_rn = [](float f) { uint32_t u; memcpy(&u, &f, 4); u += 0x7FFFu + ((u >> 16) & 1u); return (uint16_t)(u >> 16); };
+        auto xperm = [](int n) { const int gp = n >> 4, hh2 = (n >> 3) & 1, q = (n >> 1) & 3, e2 = n & 1; return 16 * gp + 4 * q + 2 * hh2 + e2; };
+        std::vector<double> v(d), act(ff);
+        auto lnorm = [&](const float *g, const float *b) {
+            double mu = 0, var = 0;
+            for (int n = 0; n < d; ++n) mu += v[n];
+            mu /= d;
+            for (int n = 0; n < d; ++n) var += (v[n] - mu) * (v[n] - mu);
+            var /= d;
+            const double r = 1.0 / sqrt(var + 1e-5);
+            for (int n = 0; n < d; ++n) v[n] = (v[n] - mu) * r * g[n] + b[n];
+        };
+        for (int m = 0; m < M; ++m) {
+            for (int j = 0; j < ff; ++j) {
+                const double hv = hh[(size_t)m * ff + j];
+                act[j] = bf2f(f2bf_rn((float)(hv + hv * tanh(hv))));          // silu(2h), rounded to bf16 like the kernel's operand
+            }
+            for (int n = 0; n < d; ++n) {
+                double acc = hb2[n];
+                for (int j = 0; j < ff; ++j) acc += act[j] * (double)bf2f(hw2[(size_t)n * ff + j]);
+                v[n] = (double)hx[(size_t)m * d + xperm(n)] + alpha * acc;
+            }
+            if (fin) lnorm(hln.data(), hln.data() + d);
+            for (int n = 0; n < d; ++n) {
+                double err = fabs((double)gx[(size_t)m * d + xperm(n)] - v[n]) / (1.0 + fabs(v[n]));
+                if (!(err == err)) err = 1e9;
+                worst = fmax(worst, err);
+            }
+            if (nxt) lnorm(hln.data() + 2 * d, hln.data() + 3 * d);
+            for (int n = 0; n < d; ++n) {
+                double err = fabs((double)bf2f(gn[(size_t)m * d + n]) - v[n]) / (1.0 + fabs(v[n]));
+                if (!(err == err)) err = 1e9;
+                worst = fmax(worst, err);
+            }
+        }
+        if (flags & 8) {
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0); cudaEventCreate(&e1);
+            cudaEventRecord(e0);
+            for (int i = 0; i < 20; ++i)
+                launch_ffn_fused(h, xn, d, w1, b1, w2p, b2, x, xo, d, alpha, nullptr, nullptr, ln + 2 * d, ln + 3 * d, M, ff, 0, "selftest_ffn");
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            fprintf(stderr, "selftest_ffn M=%d ff=%d: %.1f us per launch\n", M, ff, ms * 1000.0f / 20.0f);
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+        }
+    } else {
+        set_global_error(h->err.c_str());
+    }
+    if (max_err) *max_err = worst;
+    cudaFree(xn); cudaFree(xo); cudaFree(w1); cudaFree(w2); cudaFree(w2p); cudaFree(b1); cudaFree(b2); cudaFree(x); cudaFree(ln); cudaFree(href);
     cocr_destroy(h);
     return rc;
 }

@@ -268,6 +268,20 @@ __device__ __forceinline__ void tmem_st_32x32b_x16n(uint32_t taddr, const uint32
                  : "memory");
 }
 
+// 32 lanes x 8 columns
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+// registers r[OFF .. OFF+3] -> 32 lanes x 4 columns
+template <int OFF, int NR>
+__device__ __forceinline__ void tmem_st_32x32b_x4_at(uint32_t taddr, const uint32_t (&r)[NR]) {
+    static_assert(NR >= OFF + 4, "register array too small");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[OFF]), "r"(r[OFF + 1]), "r"(r[OFF + 2]), "r"(r[OFF + 3]) : "memory");
+}
+
 // ---- descriptors -------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (PTX ISA "tcgen05 matrix descriptor"): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), base_offset [49,52)=0, layout type [61,64).

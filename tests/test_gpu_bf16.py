@@ -55,6 +55,18 @@ def test_residual_layernorm_epilogue_selftest(M, N, K, flags, cuda_device):
     assert 0.0 <= err.value < 6e-3, f'max err {err.value}'
 
 
+@pytest.mark.parametrize('M,NC,flags', [(128, 4, 4), (300, 4, 6), (1000, 4, 0), (777, 2, 2), (4096, 4, 4), (2500, 1, 6), (19000, 4, 6), (20481, 4, 4)])
+def test_fused_ffn_selftest(M, NC, flags, cuda_device):
+    """ffn_tc.cuh against a host reference: x + 0.5 * (W2 silu(W1 xn + b1) + b2), LayerNorm(s), bf16 hidden operand."""
+    from conformer_ocr_b200 import _lib
+    lib = _lib.load()
+    err = ctypes.c_double(-1.0)
+    rc = lib.cocr_selftest(0, 21, M, NC, flags, ctypes.byref(err))
+    _lib.raise_for_status(rc, None)
+    # the fp32 stream differs by accumulation order and tanh.approx (both ~1e-3 of the module output); xn adds bf16 rounding
+    assert 0.0 <= err.value < 6e-3, f'max err {err.value}'
+
+
 def build_net(hp, C, w, device, **kw):
     from conformer_ocr_b200 import PytorchRecognitionModel
     net = PytorchRecognitionModel(num_classes=C, codec=None, precision='bf16', **hp, **DROP, **kw)
