@@ -33,8 +33,9 @@ struct Bf16State {
     bf16 *w_pw1g = nullptr;       // (L, 2d, d)
     float *b_pw1g = nullptr;      // (L, 2d)
     bf16 *w_fe_pw2 = nullptr;     // (cc, 2 cc): [Wpw | Wpw] for the hi/lo split 1x1 conv GEMM of the front-end
-    bf16 *w_ffn2p = nullptr;      // (L, 2, ff, d): FFN-down weights cut into 144-column k-chunks stacked along the rows
-                                  // (row c*144 + n, column k = W2[n][c*144 + k]) for the fused FFN kernel (ffn_tc.cuh)
+    bf16 *w_ffn2p = nullptr;      // (L, 2, ff/96 * d, 96): FFN-down weights cut into 96-column k-chunks stacked along the rows
+                                  // (row c*d + n, column k = W2[n][c*96 + k]) for the fused FFN kernel (ffn_tc.cuh)
+    std::vector<float> b1_host;   // (L, 2, ff) FFN-up biases (scaled by 1/2) on the host: they travel as kernel parameters
     float *dw_taps = nullptr;     // (L, K*d + d): depthwise taps [k][pair](2) * bn_scale / 2, then bn_shift / 2
     int tab_T = 0;
 };
@@ -631,36 +632,39 @@ static int launch_attn_tc(cocr_handle *h, const bf16 *qkvx, const int32_t *lens,
 // fused feed-forward module (ffn_tc.cuh)
 // ------------------------------------------------------------------------------------------
 static bool ffn_fused_ok(const cocr_handle *h) {
-    return h->dm.d == FFN_D && h->dm.ff % FFN_D == 0 && h->dm.ff / FFN_D <= FFN_MAX_NC && !getenv("COCR_FFN_SPLIT") && !getenv("COCR_SPLIT_RESIDUAL");
+    return h->dm.d == FFN_D && h->dm.ff % FFN_HC == 0 && h->dm.ff / FFN_HC <= FFN_MAX_NC && !getenv("COCR_FFN_SPLIT") && !getenv("COCR_SPLIT_RESIDUAL");
 }
 
-// W2 (d, ff) -> (ff, d): row c*d + n, column k  <-  W2[n][c*d + k]
-__global__ void k_pack_ffn2(const bf16 *w2, bf16 *out, int d, int ff) {
+// W2 (d, ff) -> (ff/hc * d, hc): row c*d + n, column k  <-  W2[n][c*hc + k]
+__global__ void k_pack_ffn2(const bf16 *w2, bf16 *out, int d, int ff, int hc) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d * ff) return;
-    const int row = i / d, k = i - row * d;
+    const int row = i / hc, k = i - row * hc;
     const int c = row / d, n = row - c * d;
-    out[i] = w2[(size_t)n * ff + c * d + k];
+    out[i] = w2[(size_t)n * ff + c * hc + k];
 }
 
-// x <- x + alpha * FFN(xn) [-> LN_final]; xn_out = bf16(LN_next(x)).  w1: (ff, d) bf16 scaled by 1/2, b1 scaled by 1/2,
-// w2p: packed by k_pack_ffn2.  xn_out may alias xn (a tile is written after it has been read, and only by its own CTA).
-static int launch_ffn_fused(cocr_handle *h, const bf16 *xn, int ldx, const bf16 *w1, const float *b1, const bf16 *w2p, const float *b2,
+// x <- x + alpha * FFN(xn) [-> LN_final]; xn_out = bf16(LN_next(x)).  w1: (ff, d) bf16 scaled by 1/2, b1_host: HOST copy of
+// the bias scaled by 1/2, w2p: packed by k_pack_ffn2.  xn_out may alias xn (a tile is written after it has been read, and
+// only by its own CTA).
+static int launch_ffn_fused(cocr_handle *h, const bf16 *xn, int ldx, const bf16 *w1, const float *b1_host, const bf16 *w2p, const float *b2,
                             float *x, bf16 *xn_out, int ldo, float alpha, const float *gf, const float *bfin, const float *g1, const float *b1n,
                             int M, int ff, cudaStream_t st, const char *tag) {
     if (M <= 0) return COCR_OK;
-    if (ff % FFN_D != 0 || ff / FFN_D > FFN_MAX_NC || ldx % 8 != 0 || ldo % 4 != 0)
-        return set_error(h, COCR_ERR_UNSUPPORTED, "fused FFN needs ff = 144 * n (n <= %d) and aligned rows (ff=%d ldx=%d ldo=%d)", FFN_MAX_NC, ff, ldx, ldo);
+    if (ff % FFN_HC != 0 || ff / FFN_HC > FFN_MAX_NC || ldx % 8 != 0 || ldo % 4 != 0)
+        return set_error(h, COCR_ERR_UNSUPPORTED, "fused FFN needs ff = 96 * n (n <= %d) and aligned rows (ff=%d ldx=%d ldo=%d)", FFN_MAX_NC, ff, ldx, ldo);
     if (FFN_SMEM_BYTES > (uint32_t)h->bf->smem_optin) return set_error(h, COCR_ERR_UNSUPPORTED, "fused FFN does not fit shared memory");
     FfnArgs a;
-    a.M = M; a.NC = ff / FFN_D; a.m_tiles = (M + 127) / 128;
-    a.b1 = b1; a.b2 = b2; a.x = x; a.xn_out = xn_out; a.ldo = ldo; a.alpha = alpha;
+    a.M = M; a.NC = ff / FFN_HC; a.m_tiles = (M + 127) / 128;
+    memset(a.b1, 0, sizeof(a.b1));
+    memcpy(a.b1, b1_host, (size_t)ff * sizeof(float));
+    a.b2 = b2; a.x = x; a.xn_out = xn_out; a.ldo = ldo; a.alpha = alpha;
     a.gf = gf; a.bf = bfin; a.g1 = g1; a.b1n = b1n;
     { static const int dbg = getenv("COCR_FFN_DBG") ? atoi(getenv("COCR_FFN_DBG")) : 0; a.dbg = dbg; }
     CUtensorMap tmX, tmW1, tmW2;
     COCR_TRY(make_tmap_bf16(h, &tmX, xn, M, FFN_D, ldx, 128));
-    COCR_TRY(make_tmap_bf16(h, &tmW1, w1, ff, FFN_D, FFN_D, FFN_D));
-    COCR_TRY(make_tmap_bf16(h, &tmW2, w2p, ff, FFN_D, FFN_D, FFN_D));
+    COCR_TRY(make_tmap_bf16(h, &tmW1, w1, ff, FFN_D, FFN_D, FFN_HC));
+    COCR_TRY(make_tmap_bf16(h, &tmW2, w2p, (int64_t)a.NC * FFN_D, FFN_HC, FFN_HC, FFN_D));
     static bool attr = false;
     if (!attr) {
         COCR_CUDA(h, cudaFuncSetAttribute(k_ffn_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FFN_SMEM_BYTES));
@@ -674,7 +678,8 @@ static int launch_ffn_fused(cocr_handle *h, const bf16 *xn, int ldx, const bf16 
     const char *trace_file = getenv("COCR_FFN_TRACE");
     {
         static int seen = 0;
-        if (trace_file && ++seen == 5) {
+        static const int at = getenv("COCR_FFN_TRACE_AT") ? atoi(getenv("COCR_FFN_TRACE_AT")) : 5;
+        if (trace_file && ++seen == at) {
             COCR_CUDA(h, cudaMalloc((void **)&trace_dev, (size_t)3 * GEMM_TRACE_EVENTS * 16));
             COCR_CUDA(h, cudaMemset(trace_dev, 0, (size_t)3 * GEMM_TRACE_EVENTS * 16));
             a.trace = trace_dev;
@@ -729,8 +734,13 @@ int bf16_init(cocr_handle *h) {
         bs->w_ffn2p = (bf16 *)pw;
         for (int l = 0; l < dm.L; ++l)
             for (int f = 0; f < 2; ++f)
-                k_pack_ffn2<<<(unsigned)((nw + 255) / 256), 256>>>(bs->arena + (h->layers[l].ffn_w2[f] - h->arena), bs->w_ffn2p + ((size_t)l * 2 + f) * nw, dm.d, dm.ff);
+                k_pack_ffn2<<<(unsigned)((nw + 255) / 256), 256>>>(bs->arena + (h->layers[l].ffn_w2[f] - h->arena), bs->w_ffn2p + ((size_t)l * 2 + f) * nw, dm.d, dm.ff, FFN_HC);
         COCR_LAUNCHED(h);
+        COCR_CUDA(h, cudaDeviceSynchronize());
+        bs->b1_host.resize((size_t)dm.L * 2 * dm.ff);
+        for (int l = 0; l < dm.L; ++l)
+            for (int f = 0; f < 2; ++f)
+                COCR_CUDA(h, cudaMemcpy(bs->b1_host.data() + ((size_t)l * 2 + f) * dm.ff, h->layers[l].ffn_b1[f], (size_t)dm.ff * sizeof(float), cudaMemcpyDeviceToHost));
     }
     {
         // pw1 for the GLU epilogue (convolution.py:138-139): GEMM column 2c = value channel c, 2c+1 = gate channel d + c
@@ -889,7 +899,7 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
     auto ffn_module = [&](int l, int f, const float *gf, const float *bfin, const float *g1, const float *b1, const char *tag_down) -> int {
         const LayerF32 &lw = h->layers[l];
         if (fused && h->bf->w_ffn2p)      // one kernel, the hidden activation stays on the SM
-            return launch_ffn_fused(h, xn, ldx, WB(h, lw.ffn_w1[f]), lw.ffn_b1[f], h->bf->w_ffn2p + ((size_t)l * 2 + f) * dm.ff * d, lw.ffn_b2[f], x, xn,
+            return launch_ffn_fused(h, xn, ldx, WB(h, lw.ffn_w1[f]), h->bf->b1_host.data() + ((size_t)l * 2 + f) * dm.ff, h->bf->w_ffn2p + ((size_t)l * 2 + f) * dm.ff * d, lw.ffn_b2[f], x, xn,
                                     ldx, dm.ffn_factor, gf, bfin, g1, b1, M, dm.ff, st, f ? "ffn_fused_final" : "ffn_fused");
         for (int b0 = 0; b0 < B; b0 += ffn_lines) {
             const int nb = std::min(ffn_lines, B - b0), r0 = b0 * p.T, rows = nb * p.T;
@@ -1189,7 +1199,7 @@ int selftest_resid(int device, int M, int N, int K, int flags, double *max_err) 
 }
 
 
-// fused FFN kernel against a host reference: M rows, ff = 144 * NC; flags: 2 block-final LayerNorm, 4 next LayerNorm;
+// fused FFN kernel against a host reference: M rows, ff = 96 * NC; flags: 2 block-final LayerNorm, 4 next LayerNorm;
 // 8: time 20 launches and print us per launch to stderr
 int selftest_ffn(int device, int M, int NC, int flags, double *max_err) {
     cocr_hparams hp = {96, 144, 0, 4, 4, 2, 31, 1, 32, 4, 0, COCR_FP32, 0};
@@ -1198,7 +1208,7 @@ int selftest_ffn(int device, int M, int NC, int flags, double *max_err) {
     if (rc != COCR_OK) return rc;
     h->bf = new Bf16State();
     cudaDeviceGetAttribute(&h->bf->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    const int d = FFN_D, ff = NC * FFN_D;
+    const int d = FFN_D, ff = NC * FFN_HC;
     bf16 *xn, *w1, *w2, *w2p, *xo;
     float *b1, *b2, *x, *ln, *href;
     cudaMalloc((void **)&xn, (size_t)M * d * 2); cudaMalloc((void **)&xo, (size_t)M * d * 2);
@@ -1212,9 +1222,10 @@ int selftest_ffn(int device, int M, int NC, int flags, double *max_err) {
     k_fill_f32<<<(d + 255) / 256, 256>>>(b2, (size_t)d, 15u, 0.5f);
     k_fill_f32<<<(unsigned)(((size_t)M * d + 255) / 256), 256>>>(x, (size_t)M * d, 16u, 2.0f);
     k_fill_f32<<<(4 * d + 255) / 256, 256>>>(ln, (size_t)4 * d, 17u, 1.0f);
-    k_pack_ffn2<<<(unsigned)(((size_t)ff * d + 255) / 256), 256>>>(w2, w2p, d, ff);
+    k_pack_ffn2<<<(unsigned)(((size_t)ff * d + 255) / 256), 256>>>(w2, w2p, d, ff, FFN_HC);
     k_ref_gemm<<<(unsigned)(((size_t)M * ff + 255) / 256), 256>>>(xn, w1, b1, href, M, ff, d, 0);     // h = xn W1^T + b1 (the "half" pre-activation)
-    std::vector<float> hx((size_t)M * d), hh((size_t)M * ff), hln(4 * d), hb2(d);
+    std::vector<float> hx((size_t)M * d), hh((size_t)M * ff), hln(4 * d), hb2(d), hb1(ff);
+    cudaMemcpy(hb1.data(), b1, hb1.size() * 4, cudaMemcpyDeviceToHost);
     std::vector<uint16_t> hw2((size_t)ff * d);
     cudaMemcpy(hx.data(), x, hx.size() * 4, cudaMemcpyDeviceToHost);
     cudaMemcpy(hh.data(), href, hh.size() * 4, cudaMemcpyDeviceToHost);
@@ -1223,7 +1234,7 @@ int selftest_ffn(int device, int M, int NC, int flags, double *max_err) {
     cudaMemcpy(hw2.data(), w2, hw2.size() * 2, cudaMemcpyDeviceToHost);
     const bool fin = flags & 2, nxt = flags & 4;
     const float alpha = 0.5f;
-    rc = launch_ffn_fused(h, xn, d, w1, b1, w2p, b2, x, xo, d, alpha, fin ? ln : nullptr, fin ? ln + d : nullptr, nxt ? ln + 2 * d : nullptr,
+    rc = launch_ffn_fused(h, xn, d, w1, hb1.data(), w2p, b2, x, xo, d, alpha, fin ? ln : nullptr, fin ? ln + d : nullptr, nxt ? ln + 2 * d : nullptr,
                           nxt ? ln + 3 * d : nullptr, M, ff, 0, "selftest_ffn");
     cudaError_t e = cudaDeviceSynchronize();
     if (rc == COCR_OK && e != cudaSuccess) rc = set_error(h, COCR_ERR_CUDA, "selftest_ffn: %s", cudaGetErrorString(e));
@@ -1274,7 +1285,7 @@ int selftest_ffn(int device, int M, int NC, int flags, double *max_err) {
             cudaEventCreate(&e0); cudaEventCreate(&e1);
             cudaEventRecord(e0);
             for (int i = 0; i < 20; ++i)
-                launch_ffn_fused(h, xn, d, w1, b1, w2p, b2, x, xo, d, alpha, nullptr, nullptr, ln + 2 * d, ln + 3 * d, M, ff, 0, "selftest_ffn");
+                launch_ffn_fused(h, xn, d, w1, hb1.data(), w2p, b2, x, xo, d, alpha, nullptr, nullptr, ln + 2 * d, ln + 3 * d, M, ff, 0, "selftest_ffn");
             cudaEventRecord(e1);
             cudaEventSynchronize(e1);
             float ms = 0.f;

@@ -7,29 +7,50 @@
 // separate GEMMs wrote and re-read it through HBM and were bound by exactly that traffic (97 us per module against
 // 26 us of unavoidable x / xn traffic).
 //
-// Built for encoder_dim 144 and ff = 144 * NC.  A persistent CTA takes 128-row tiles; per tile and hidden chunk c (144
+// Built for encoder_dim 144 and ff = 96 * NC.  A persistent CTA takes 128-row tiles; per tile and hidden chunk c (96
 // hidden units):
-//     G1(c):  H_c  = xn_tile (128 x 144, smem)   * W1_c^T (144 x 144, smem)  -> TMEM accumulator (fp32, double-buffered)
-//     E1(c):  H_c <- bf16(silu(H_c + b1_c)) written IN PLACE as packed pairs over the first 72 columns of the accumulator
-//     G2(c):  Y   += H_c (TMEM A operand)         * W2_c^T (144 x 144, smem)  -> TMEM accumulator Y
-// and after the last chunk the residual / LayerNorm epilogue of EPI_RESID (gemm_tc.cuh) drains Y.
-// The weight chunks (2 * NC * 41 KB per tile) stream from L2 through a two-slot ring in the order the MMAs consume
-// them; the xn tile is double-buffered so the next tile's first G1 overlaps the current tile's tail.
+//     G1(c):  H_c  = xn_tile (128 x 144, smem)   * W1_c^T (96 x 144, smem)   -> TMEM accumulator (fp32, double-buffered)
+//     E1(c):  H_c <- bf16(silu(H_c + b1_c)) written IN PLACE as packed pairs over the first 48 columns of the accumulator
+//     G2(c):  Y   += H_c (TMEM A operand, K = 96) * W2_c^T (144 x 96, smem)   -> TMEM accumulator Y (double-buffered by tile)
+// and after the last chunk the residual / LayerNorm epilogue of EPI_RESID (gemm_tc.cuh) drains Y while the next tile
+// is already running.  The weight chunks (36 KB each) stream from L2 through a three-slot ring in the order the MMAs
+// consume them; the xn tiles are double-buffered and requested a tile ahead.
 //
 // Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (G1 runs one chunk ahead of G2), warps 2..9 = E1
-// (two per TMEM lane quarter, 72 of the 144 hidden columns each), warps 10..17 = final epilogue (two per lane quarter).
-// TMEM (512 columns): H0 at 0, H1 at 144, Y at 288.
+// (two per TMEM lane quarter, 48 of the 96 hidden columns each), warps 10..13 = final epilogue (one per lane quarter).
+// E1 is MUFU bound (one tanh per hidden element); it therefore reads nothing from memory: the bias comes from the
+// kernel-parameter constant bank as an immediate operand (the chunk index is unrolled), because shared-memory loads
+// queue behind the final epilogue's global loads / stores / shuffles in the same memory pipeline.
+// TMEM (512 columns): H0 at 0, H1 at 96, Y0 at 192, Y1 at 336.
 #pragma once
 
 #include "gemm_tc.cuh"
 
 namespace cocr {
 
+constexpr int FFN_D = 144;
+constexpr int FFN_HC = 96;                                        // hidden units per chunk
+constexpr int FFN_NG = FFN_D / 8;                                 // 8-column groups per row
+constexpr int FFN_MAX_NC = 8;                                     // ff <= 768
+constexpr int FFN_EPI_WARPS = 8;                                  // E1 warps (two per TMEM lane quarter)
+constexpr int FFN_FIN_WARPS = 4;                                  // final-epilogue warps (one per lane quarter)
+constexpr int FFN_THREADS = 64 + 32 * (FFN_EPI_WARPS + FFN_FIN_WARPS);
+constexpr int FFN_WSTAGES = 3;
+constexpr uint32_t FFN_A_CHUNK = 128 * 128;                       // one 64-column k-chunk of the xn tile (SWIZZLE_128B)
+constexpr uint32_t FFN_A_BYTES = 3 * FFN_A_CHUNK;                 // k = 64 + 64 + 16 (the last chunk is mostly padding)
+constexpr uint32_t FFN_W1_CHUNK = FFN_HC * 128;                   // W1_c: 96 rows, k-chunks 64 + 64 + 16
+constexpr uint32_t FFN_W2_CHUNK = FFN_D * 128;                    // W2_c: 144 rows, k-chunks 64 + 32
+constexpr uint32_t FFN_W_BYTES = 3 * FFN_W1_CHUNK;                // = 2 * FFN_W2_CHUNK = 36 KB
+static_assert(3 * FFN_W1_CHUNK == 2 * FFN_W2_CHUNK, "one ring slot holds either kind of weight chunk");
+constexpr uint32_t FFN_H_COL0 = 0, FFN_H_COL1 = 96, FFN_Y_COL0 = 192, FFN_Y_COL1 = 336;
+constexpr uint32_t FFN_TMEM_COLS = 512;
+constexpr uint32_t FFN_FLOATS = FFN_D + 4 * FFN_D;                // b2 | gf bf g1 b1n
+constexpr uint32_t FFN_SMEM_BYTES = 2 * FFN_A_BYTES + FFN_WSTAGES * FFN_W_BYTES + FFN_FLOATS * 4 + 256;
+
 struct FfnArgs {
     int M;                      // rows
-    int NC;                     // hidden chunks of 144 (ff = 144 * NC)
+    int NC;                     // hidden chunks of 96 (ff = 96 * NC)
     int m_tiles;
-    const float *b1;            // (ff) FFN-up bias, pre-scaled by 1/2 like the weights (silu from half, gemm_tc.cuh)
     const float *b2;            // (144)
     float *x;                   // (M, 144) fp32 residual stream in the private layout of GemmArgs::x, updated in place
     __nv_bfloat16 *xn_out;      // (M, ldo) bf16 LayerNorm_next(x)
@@ -38,46 +59,56 @@ struct FfnArgs {
     const float *gf, *bf;       // block-final LayerNorm applied to x itself (or null)
     const float *g1, *b1n;      // LayerNorm of the next module -> xn_out (null: xn_out = bf16(x))
     long long *trace;           // debug: (tag, clock) pairs of CTA 0 (COCR_FFN_TRACE=<file>), else null
-    int dbg;                    // experiments (COCR_FFN_DBG, results are garbage): 1 no weight loads, 2 no silu math, 4 no final
-                                //    epilogue memory traffic, 8 no MMAs, 16 no xn tile loads
+    int dbg;                    // experiments (COCR_FFN_DBG, results are garbage): 1 no weight loads, 4 no final epilogue
+                                //    memory traffic, 8 no MMAs, 16 no xn tile loads
+    float b1[FFN_MAX_NC * FFN_HC];   // FFN-up bias, pre-scaled by 1/2 like the weights (silu from half, gemm_tc.cuh); lives in the
+                                     // constant bank with the other kernel parameters
 };
 
-constexpr int FFN_D = 144;
-constexpr int FFN_NG = FFN_D / 8;                                 // 8-column groups per row
-constexpr int FFN_MAX_NC = 8;
-constexpr int FFN_EPI_WARPS = 8;                                  // E1 warps (two per TMEM lane quarter)
-constexpr int FFN_FIN_WARPS = 8;                                  // final-epilogue warps (two per lane quarter, 16 rows each)
-constexpr int FFN_THREADS = 64 + 32 * (FFN_EPI_WARPS + FFN_FIN_WARPS);
-constexpr int FFN_WSTAGES = 2;
-constexpr uint32_t FFN_A_CHUNK = 128 * 128;                       // one 64-column k-chunk of the xn tile (SWIZZLE_128B)
-constexpr uint32_t FFN_A_BYTES = 3 * FFN_A_CHUNK;                 // k = 64 + 64 + 16 (the last chunk is mostly padding)
-constexpr uint32_t FFN_W_CHUNK = FFN_D * 128;                     // one 64-column k-chunk of a 144-row weight chunk
-constexpr uint32_t FFN_W_BYTES = 3 * FFN_W_CHUNK;
-constexpr uint32_t FFN_H_COL0 = 0, FFN_H_COL1 = 144, FFN_Y_COL = 288;
-constexpr uint32_t FFN_TMEM_COLS = 512;
-constexpr uint32_t FFN_FLOATS = FFN_MAX_NC * FFN_D + FFN_D + 4 * FFN_D;   // b1 | b2 | gf bf g1 b1n
-constexpr uint32_t FFN_SMEM_BYTES = 2 * FFN_A_BYTES + FFN_WSTAGES * FFN_W_BYTES + FFN_FLOATS * 4 + 256;
+// E1 arithmetic for hidden chunk C, column half HF: 48 accumulator columns -> 24 packed bf16 pairs
+template <int C, int HF>
+__device__ __forceinline__ void ffn_e1_math(const FfnArgs &p, const uint32_t (&r0)[32], const uint32_t (&r1)[16], uint32_t (&pk)[24]) {
+#pragma unroll
+    for (int e = 0; e < 24; ++e) {
+        const uint32_t u0 = e < 16 ? r0[2 * e] : r1[2 * e - 32], u1 = e < 16 ? r0[2 * e + 1] : r1[2 * e - 31];
+        const float2 h = make_float2(__uint_as_float(u0) + p.b1[C * FFN_HC + HF * 48 + 2 * e], __uint_as_float(u1) + p.b1[C * FFN_HC + HF * 48 + 2 * e + 1]);
+        const float2 sv = silu_from_half(h);
+        pk[e] = pack_bf16x2(sv.x, sv.y);
+    }
+}
+template <int HF>
+__device__ __forceinline__ void ffn_e1_math_c(const FfnArgs &p, int c, const uint32_t (&r0)[32], const uint32_t (&r1)[16], uint32_t (&pk)[24]) {
+    switch (c) {
+        case 0: ffn_e1_math<0, HF>(p, r0, r1, pk); break;
+        case 1: ffn_e1_math<1, HF>(p, r0, r1, pk); break;
+        case 2: ffn_e1_math<2, HF>(p, r0, r1, pk); break;
+        case 3: ffn_e1_math<3, HF>(p, r0, r1, pk); break;
+        case 4: ffn_e1_math<4, HF>(p, r0, r1, pk); break;
+        case 5: ffn_e1_math<5, HF>(p, r0, r1, pk); break;
+        case 6: ffn_e1_math<6, HF>(p, r0, r1, pk); break;
+        default: ffn_e1_math<7, HF>(p, r0, r1, pk); break;
+    }
+}
 
 __global__ void __launch_bounds__(FFN_THREADS, 1)
 k_ffn_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
-            const __grid_constant__ CUtensorMap tmW2, const FfnArgs p) {
+            const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ FfnArgs p) {
     using namespace tc;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sA = smem;                                            // [2] xn tiles
     uint8_t *sW = smem + 2 * FFN_A_BYTES;                          // [FFN_WSTAGES] weight chunks
-    float *sb1 = reinterpret_cast<float *>(sW + FFN_WSTAGES * FFN_W_BYTES);   // [NC * 144]
-    float *sb2 = sb1 + FFN_MAX_NC * FFN_D;                         // [144]
+    float *sb2 = reinterpret_cast<float *>(sW + FFN_WSTAGES * FFN_W_BYTES);   // [144]
     float *sln = sb2 + FFN_D;                                      // [4][144] gf, bf, g1, b1n
     uint64_t *bars = reinterpret_cast<uint64_t *>(sln + 4 * FFN_D);
     uint64_t *afull = bars;              // [2]  xn tile loaded
     uint64_t *aempty = bars + 2;         // [2]  every G1 of the tile has run
     uint64_t *wfull = bars + 4;          // [FFN_WSTAGES]
-    uint64_t *wempty = bars + 6;         // [FFN_WSTAGES]
-    uint64_t *h1full = bars + 8;         // [2]  G1 done: fp32 hidden chunk in TMEM
-    uint64_t *hbfull = bars + 10;        // [2]  bf16 hidden chunk written (epilogue warps)
-    uint64_t *yfull = bars + 12;         // [1]  last G2 of a tile done
-    uint64_t *yempty = bars + 13;        // [1]  Y drained (epilogue warps)
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 14);
+    uint64_t *wempty = bars + 8;         // [FFN_WSTAGES]
+    uint64_t *h1full = bars + 12;        // [2]  G1 done: fp32 hidden chunk in TMEM
+    uint64_t *hbfull = bars + 14;        // [2]  bf16 hidden chunk written (E1 warps)
+    uint64_t *yfull = bars + 16;         // [2]  last G2 of a tile done
+    uint64_t *yempty = bars + 18;        // [2]  Y drained (final warps)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 20);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NC = p.NC;
@@ -90,13 +121,12 @@ k_ffn_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
         for (int s = 0; s < 2; ++s) {
             mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1);
             mbar_init(&h1full[s], 1); mbar_init(&hbfull[s], FFN_EPI_WARPS);
+            mbar_init(&yfull[s], 1); mbar_init(&yempty[s], FFN_FIN_WARPS);
         }
         for (int s = 0; s < FFN_WSTAGES; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
-        mbar_init(yfull, 1); mbar_init(yempty, FFN_FIN_WARPS);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, FFN_TMEM_COLS);
-    for (int c = threadIdx.x; c < NC * FFN_D; c += FFN_THREADS) sb1[c] = p.b1[c];
     for (int c = threadIdx.x; c < FFN_D; c += FFN_THREADS) {
         sb2[c] = p.b2 ? p.b2[c] : 0.0f;
         sln[c] = p.gf ? p.gf[c] : 1.0f;
@@ -121,7 +151,12 @@ k_ffn_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
                 GEMM_TRACE(2, 110 + c);
                 if (p.dbg & 1) { mbar_arrive(&wfull[sl]); ++wq; return; }
                 mbar_expect_tx(&wfull[sl], FFN_W_BYTES);
-                for (int kc = 0; kc < 3; ++kc) tma_load_2d(sW + sl * FFN_W_BYTES + (uint32_t)kc * FFN_W_CHUNK, tm, &wfull[sl], kc * 64, c * FFN_D);
+                uint8_t *dst = sW + sl * FFN_W_BYTES;
+                if (tm == &tmW1) {
+                    for (int kc = 0; kc < 3; ++kc) tma_load_2d(dst + (uint32_t)kc * FFN_W1_CHUNK, tm, &wfull[sl], kc * 64, c * FFN_HC);
+                } else {
+                    for (int kc = 0; kc < 2; ++kc) tma_load_2d(dst + (uint32_t)kc * FFN_W2_CHUNK, tm, &wfull[sl], kc * 64, c * FFN_D);
+                }
                 ++wq;
             };
             auto load_a = [&](int t) {                             // t = local tile index
@@ -148,11 +183,14 @@ k_ffn_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        const uint32_t idesc = make_idesc_bf16(128, FFN_D);
+        const uint32_t idesc1 = make_idesc_bf16(128, FFN_HC), idesc2 = make_idesc_bf16(128, FFN_D);
         uint32_t wq = 0;
         int tr_n = (lane == 0) ? 0 : GEMM_TRACE_EVENTS;
+        // (tile, chunk) of G1 and of G2 advance separately (no division on the issue path)
+        int t1 = 0, c1 = 0, t2 = 0, c2 = 0;
         auto g1 = [&](int n) {                                     // H(n & 1) = xn_tile * W1_c^T
-            const int t = n / NC, c = n - t * NC;
+            const int t = t1, c = c1;
+            if (++c1 == NC) { c1 = 0; ++t1; }
             const int sa = t & 1;
             GEMM_TRACE(1, 200 + c);
             if (c == 0) mbar_wait(&afull[sa], ((uint32_t)t >> 1) & 1u);
@@ -169,7 +207,7 @@ k_ffn_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
                     if (p.dbg & 8) break;
                     const uint32_t off = (uint32_t)(k >> 2), ks = (uint32_t)(k & 3);
                     umma_bf16_ss(d_tmem, make_smem_desc_sw128(a_base + off * FFN_A_CHUNK + ks * 32, 1024),
-                                 make_smem_desc_sw128(b_base + off * FFN_W_CHUNK + ks * 32, 1024), idesc, k ? 1u : 0u);
+                                 make_smem_desc_sw128(b_base + off * FFN_W1_CHUNK + ks * 32, 1024), idesc1, k ? 1u : 0u);
                 }
                 umma_commit(&wempty[sl]);
                 umma_commit(&h1full[n & 1]);
@@ -178,8 +216,9 @@ k_ffn_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
             __syncwarp();
             GEMM_TRACE(1, 220 + c);
         };
-        auto g2 = [&](int n) {                                     // Y += bf16 H(n & 1) (TMEM) * W2_c^T
-            const int t = n / NC, c = n - t * NC;
+        auto g2 = [&](int n) {                                     // Y(t & 1) += bf16 H(n & 1) (TMEM) * W2_c^T
+            const int t = t2, c = c2;
+            if (++c2 == NC) { c2 = 0; ++t2; }
             const uint32_t sl = wq % FFN_WSTAGES;
             GEMM_TRACE(1, 230 + c);
             mbar_wait(&wfull[sl], (wq / FFN_WSTAGES) & 1u);
@@ -187,21 +226,22 @@ k_ffn_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
             GEMM_TRACE(1, 240 + c);
             mbar_wait(&hbfull[n & 1], ((uint32_t)n >> 1) & 1u);
             GEMM_TRACE(1, 250 + c);
-            if (c == 0) mbar_wait(yempty, ((uint32_t)t & 1u) ^ 1u);   // the previous tile's Y has been drained
+            if (c == 0) mbar_wait(&yempty[t & 1], (((uint32_t)t >> 1) & 1u) ^ 1u);   // Y of tile t-2 has been drained
             GEMM_TRACE(1, 260 + c);
             tc_fence_after();
             const uint32_t b_base = smem_u32(sW + sl * FFN_W_BYTES);
             const uint32_t a_tmem = tmem_base + ((n & 1) ? FFN_H_COL1 : FFN_H_COL0);
+            const uint32_t y_tmem = tmem_base + ((t & 1) ? FFN_Y_COL1 : FFN_Y_COL0);
             if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < FFN_D / 16; ++k) {
+                for (int k = 0; k < FFN_HC / 16; ++k) {
                     if (p.dbg & 8) break;
                     const uint32_t off = (uint32_t)(k >> 2), ks = (uint32_t)(k & 3);
-                    umma_bf16_ts(tmem_base + FFN_Y_COL, a_tmem + (uint32_t)k * 8u, make_smem_desc_sw128(b_base + off * FFN_W_CHUNK + ks * 32, 1024), idesc,
+                    umma_bf16_ts(y_tmem, a_tmem + (uint32_t)k * 8u, make_smem_desc_sw128(b_base + off * FFN_W2_CHUNK + ks * 32, 1024), idesc2,
                                  (c | k) ? 1u : 0u);
                 }
                 umma_commit(&wempty[sl]);
-                if (c == NC - 1) umma_commit(yfull);
+                if (c == NC - 1) umma_commit(&yfull[t & 1]);
             }
             __syncwarp();
             GEMM_TRACE(1, 270 + c);
@@ -212,72 +252,57 @@ k_ffn_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
             g2(n);
         }
     } else if (warp < 2 + FFN_EPI_WARPS) {
-        // ================= E1 warps =================
+        // ================= E1 warps: H <- bf16(silu(H + b1)), thread = row, 48 columns =================
         const int q = warp & 3;                                    // TMEM lane quarter
         const int hf = (warp - 2) >> 2;                            // half of the hidden columns
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         int tr_n = (threadIdx.x == 64) ? 0 : GEMM_TRACE_EVENTS;
+        int t = 0, c = 0;
         for (int n = 0; n < n_total; ++n) {
-            const int t = n / NC, c = n - t * NC;
             GEMM_TRACE(0, 300 + c);
             if (c == 0) {
-                // request this tile's rows of the residual stream into L2: the final epilogue reads them ~4 chunks from now
+                // request this tile's rows of the residual stream into L2: the final epilogue reads them a tile from now
                 const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
                 const int64_t rows = min((int64_t)128, (int64_t)p.M - tile * 128);
                 const char *xb = reinterpret_cast<const char *>(p.x + tile * 128 * FFN_D);
                 for (int64_t o = (int64_t)(threadIdx.x - 64) * 128; o < rows * FFN_D * 4; o += (int64_t)FFN_EPI_WARPS * 32 * 128)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + o));
             }
-            // ---- E1: H <- bf16(silu(H + b1)), thread = row, 72 columns ----
-            {
-                const uint32_t hcol = tmem_base + ((n & 1) ? FFN_H_COL1 : FFN_H_COL0) + lane_base;
-                mbar_wait(&h1full[n & 1], ((uint32_t)n >> 1) & 1u);
-                GEMM_TRACE(0, 310 + c);
-                tc_fence_after();
-                uint32_t r0[32], r1[32], r2[8];
-                tmem_ld_32x32b_x32(hcol + (uint32_t)(hf * 72), r0);
-                tmem_ld_32x32b_x32(hcol + (uint32_t)(hf * 72 + 32), r1);
-                tmem_ld_32x32b_x8(hcol + (uint32_t)(hf * 72 + 64), r2);
-                tmem_ld_wait_dep(r0); tmem_ld_wait_dep(r1); tmem_ld_wait_dep(r2);
-                // the packed output of the upper half lands on columns 36..71, which the lower half has just read as fp32
-                named_bar_sync(1 + q, 64);
-                GEMM_TRACE(0, 320 + c);
-                const float *bb = sb1 + c * FFN_D + hf * 72;
-                uint32_t pk[36];
-#pragma unroll
-                for (int e4 = 0; e4 < 18; ++e4) {
-                    const float4 b4 = *reinterpret_cast<const float4 *>(bb + 4 * e4);
-                    float2 v0, v1;
-                    if (e4 < 8) { v0 = make_float2(__uint_as_float(r0[4 * e4]), __uint_as_float(r0[4 * e4 + 1])); v1 = make_float2(__uint_as_float(r0[4 * e4 + 2]), __uint_as_float(r0[4 * e4 + 3])); }
-                    else if (e4 < 16) { v0 = make_float2(__uint_as_float(r1[4 * e4 - 32]), __uint_as_float(r1[4 * e4 - 31])); v1 = make_float2(__uint_as_float(r1[4 * e4 - 30]), __uint_as_float(r1[4 * e4 - 29])); }
-                    else { v0 = make_float2(__uint_as_float(r2[4 * e4 - 64]), __uint_as_float(r2[4 * e4 - 63])); v1 = make_float2(__uint_as_float(r2[4 * e4 - 62]), __uint_as_float(r2[4 * e4 - 61])); }
-                    float2 s0 = fadd2(v0, make_float2(b4.x, b4.y)), s1 = fadd2(v1, make_float2(b4.z, b4.w));
-                    if (!(p.dbg & 2)) { s0 = silu_from_half(s0); s1 = silu_from_half(s1); }
-                    pk[2 * e4] = pack_bf16x2(s0.x, s0.y);
-                    pk[2 * e4 + 1] = pack_bf16x2(s1.x, s1.y);
-                }
-                GEMM_TRACE(0, 340 + c);
-                tmem_st_32x32b_x32(hcol + (uint32_t)(hf * 36), pk);
-                tmem_st_32x32b_x4_at<32>(hcol + (uint32_t)(hf * 36 + 32), pk);
-                tmem_st_wait();
-                GEMM_TRACE(0, 350 + c);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&hbfull[n & 1]);
-                GEMM_TRACE(0, 330 + c);
-            }
+            const uint32_t hcol = tmem_base + ((n & 1) ? FFN_H_COL1 : FFN_H_COL0) + lane_base;
+            mbar_wait(&h1full[n & 1], ((uint32_t)n >> 1) & 1u);
+            GEMM_TRACE(0, 310 + c);
+            tc_fence_after();
+            uint32_t r0[32], r1[16];
+            tmem_ld_32x32b_x32(hcol + (uint32_t)(hf * 48), r0);
+            tmem_ld_32x32b_x16(hcol + (uint32_t)(hf * 48 + 32), r1);
+            tmem_ld_wait_dep(r0); tmem_ld_wait_dep(r1);
+            // the packed output of the upper half lands on columns 24..47, which the lower half has just read as fp32
+            named_bar_sync(1 + q, 64);
+            GEMM_TRACE(0, 320 + c);
+            uint32_t pk[24];
+            if (hf == 0) ffn_e1_math_c<0>(p, c, r0, r1, pk);
+            else ffn_e1_math_c<1>(p, c, r0, r1, pk);
+            GEMM_TRACE(0, 340 + c);
+            tmem_st_32x32b_x16n(hcol + (uint32_t)(hf * 24), pk);
+            tmem_st_32x32b_x8_at<16>(hcol + (uint32_t)(hf * 24 + 16), pk);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&hbfull[n & 1]);
+            GEMM_TRACE(0, 330 + c);
+            if (++c == NC) { c = 0; ++t; }
         }
     } else {
         // ================= final-epilogue warps =================
         // x <- x + alpha * (Y + b2) [-> LN_final]; xn = bf16(LN_next(x)); fragment layout (see EPI_RESID in gemm_tc.cuh),
-        // two warps per lane quarter, 16 rows each.  Their own warps: the x / xn traffic of a tile (184 KB through the LSU)
-        // and the LayerNorm arithmetic overlap the next tile's GEMMs and E1 instead of stalling them, and Y is released
-        // as soon as it sits in registers (x is loaded before Y is complete, so nothing but the TMEM loads is in between).
+        // one warp per lane quarter, two 16-row halves.  Their own warps: the x / xn traffic of a tile (184 KB through the
+        // LSU) and the LayerNorm arithmetic overlap the next tile's GEMMs and E1 instead of stalling them; Y is double-
+        // buffered, so they have a whole tile period for it.
         const int q = warp & 3;
-        const int hf = (warp - 2 - FFN_EPI_WARPS) >> 2;
         int tr_n = GEMM_TRACE_EVENTS;
         for (int t = 0; t < my_tiles; ++t) {
-            {
+#pragma unroll 1
+            for (int hf = 0; hf < 2; ++hf) {
                 constexpr int NG = FFN_NG;
                 const int r_in = lane >> 2, qd = lane & 3;
                 const float inv_n = 1.0f / (float)FFN_D;
@@ -293,18 +318,20 @@ k_ffn_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
                     va[2 * gp] = make_float2(ta.x, ta.y); va[2 * gp + 1] = make_float2(ta.z, ta.w);
                     vb[2 * gp] = make_float2(tb.x, tb.y); vb[2 * gp + 1] = make_float2(tb.z, tb.w);
                 }
-                mbar_wait(yfull, (uint32_t)t & 1u);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + FFN_Y_COL + ((uint32_t)(q * 32 + hf * 16) << 16);
+                if (hf == 0) {
+                    mbar_wait(&yfull[t & 1], ((uint32_t)t >> 1) & 1u);
+                    tc_fence_after();
+                }
+                const uint32_t taddr = tmem_base + ((t & 1) ? FFN_Y_COL1 : FFN_Y_COL0) + ((uint32_t)(q * 32 + hf * 16) << 16);
 #pragma unroll
                 for (int blk = 0; blk < NG / 2; ++blk) {
                     uint32_t t1[8];
                     tmem_ld_16x256b_x2(taddr + 16u * blk, t1);
                     tmem_ld_wait_dep(t1);
-                    if (blk == NG / 2 - 1) {                       // Y is in registers: the next tile's first G2 may overwrite it
+                    if (blk == NG / 2 - 1 && hf == 1) {            // Y is in registers: tile t+2 may overwrite it
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(yempty);
+                        if (lane == 0) mbar_arrive(&yempty[t & 1]);
                     }
 #pragma unroll
                     for (int gg = 0; gg < 2; ++gg) {

@@ -28,7 +28,7 @@ extern "C" int cocr_selftest(int device, int which, int64_t p0, int64_t p1, int6
         if (p0 < 1 || p1 < 16 || p2 < 16) return cocr::set_error(nullptr, COCR_ERR_BAD_ARG, "cocr_selftest: bad GEMM shape");
         return cocr::selftest_resid(device, (int)p0, (int)p1, (int)(p2 % 100000), (int)(p2 / 100000), max_err);
     }
-    if (which == 21) return cocr::selftest_ffn(device, (int)p0, (int)p1, (int)p2, max_err);   // fused FFN module: p0 = M, p1 = ff / 144, p2 = flags
+    if (which == 21) return cocr::selftest_ffn(device, (int)p0, (int)p1, (int)p2, max_err);   // fused FFN module: p0 = M, p1 = ff / 96, p2 = flags
     if (which == 45) return cocr::selftest_mbar_pingpong(device, (int)p0, max_err);   // mbarrier hand-shake latency: cycles per hop
     if (which == 44) return cocr::selftest_attn_mma_bench(device, (int)p0, (int)p1, (int)p2, max_err);   // attention S + P V MMA sequence: cycles per key tile
     if (which == 43) return cocr::selftest_mufu_bench(device, (int)p0, max_err);   // MUFU throughput: cycles per warp instruction per scheduler

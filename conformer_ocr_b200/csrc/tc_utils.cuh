@@ -282,6 +282,15 @@ __device__ __forceinline__ void tmem_st_32x32b_x4_at(uint32_t taddr, const uint3
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[OFF]), "r"(r[OFF + 1]), "r"(r[OFF + 2]), "r"(r[OFF + 3]) : "memory");
 }
 
+// registers r[OFF .. OFF+7] -> 32 lanes x 8 columns
+template <int OFF, int NR>
+__device__ __forceinline__ void tmem_st_32x32b_x8_at(uint32_t taddr, const uint32_t (&r)[NR]) {
+    static_assert(NR >= OFF + 8, "register array too small");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[OFF]), "r"(r[OFF + 1]), "r"(r[OFF + 2]),
+                 "r"(r[OFF + 3]), "r"(r[OFF + 4]), "r"(r[OFF + 5]), "r"(r[OFF + 6]), "r"(r[OFF + 7])
+                 : "memory");
+}
+
 // ---- descriptors -------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (PTX ISA "tcgen05 matrix descriptor"): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), base_offset [49,52)=0, layout type [61,64).

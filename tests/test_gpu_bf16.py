@@ -55,7 +55,7 @@ def test_residual_layernorm_epilogue_selftest(M, N, K, flags, cuda_device):
     assert 0.0 <= err.value < 6e-3, f'max err {err.value}'
 
 
-@pytest.mark.parametrize('M,NC,flags', [(128, 4, 4), (300, 4, 6), (1000, 4, 0), (777, 2, 2), (4096, 4, 4), (2500, 1, 6), (19000, 4, 6), (20481, 4, 4)])
+@pytest.mark.parametrize('M,NC,flags', [(128, 6, 4), (300, 6, 6), (1000, 6, 0), (777, 2, 2), (4096, 6, 4), (2500, 1, 6), (19000, 6, 6), (20481, 8, 4), (5000, 3, 2)])
 def test_fused_ffn_selftest(M, NC, flags, cuda_device):
     """ffn_tc.cuh against a host reference: x + 0.5 * (W2 silu(W1 xn + b1) + b2), LayerNorm(s), bf16 hidden operand."""
     from conformer_ocr_b200 import _lib
