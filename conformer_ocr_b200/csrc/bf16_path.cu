@@ -35,7 +35,8 @@ struct Bf16State {
     bf16 *w_fe_pw2 = nullptr;     // (cc, 2 cc): [Wpw | Wpw] for the hi/lo split 1x1 conv GEMM of the front-end
     bf16 *w_ffn2p = nullptr;      // (L, 2, ff/96 * d, 96): FFN-down weights cut into 96-column k-chunks stacked along the rows
                                   // (row c*d + n, column k = W2[n][c*96 + k]) for the fused FFN kernel (ffn_tc.cuh)
-    std::vector<float> b1_host;   // (L, 2, ff) FFN-up biases (scaled by 1/2) on the host: they travel as kernel parameters
+    bf16 *w_ffn1p = nullptr;      // (L, 2, ff, 160): FFN-up weights (scaled by 1/2) with the bias split into bf16 hi / lo parts in
+                                  // columns 144 / 145 (the xn rows carry ones there), zeros up to column 159
     float *dw_taps = nullptr;     // (L, K*d + d): depthwise taps [k][pair](2) * bn_scale / 2, then bn_shift / 2
     int tab_T = 0;
 };
@@ -354,8 +355,10 @@ struct Bf16Plan {
 // a multiple of 64 elements so that every 128-byte TMA box row stays inside one cache line (with d = 144 three of four
 // rows straddle two lines); measured on B200 it changes nothing (pw1 27.0 us either way), so the A stream is not bound
 // by L2 request count.
+static bool ffn_fused_ok(const cocr_handle *h);
 static int xn_pitch(const cocr_handle *h) {
     static const bool pad = getenv("COCR_XN_PAD") != nullptr;
+    if (ffn_fused_ok(h)) return FFN_K1;          // the fused FFN reads two columns of ones behind the features (ffn_tc.cuh)
     return (pad && h->dm.d == 8 * GEMM_RESID_NG) ? (h->dm.d + 63) / 64 * 64 : h->dm.d;
 }
 
@@ -635,6 +638,27 @@ static bool ffn_fused_ok(const cocr_handle *h) {
     return h->dm.d == FFN_D && h->dm.ff % FFN_HC == 0 && h->dm.ff / FFN_HC <= FFN_MAX_NC && !getenv("COCR_FFN_SPLIT") && !getenv("COCR_SPLIT_RESIDUAL");
 }
 
+// W1 (ff, d) bf16 + bias (ff) -> (ff, kp): [W1 row | bias hi | bias lo | 0 ...]
+__global__ void k_pack_ffn1(const bf16 *w1, const float *b1, bf16 *out, int d, int ff, int kp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ff * kp) return;
+    const int row = i / kp, k = i - row * kp;
+    bf16 v = __float2bfloat16_rn(0.0f);
+    if (k < d) v = w1[(size_t)row * d + k];
+    else if (k == d) v = __float2bfloat16_rn(b1[row]);
+    else if (k == d + 1) v = __float2bfloat16_rn(b1[row] - __bfloat162float(__float2bfloat16_rn(b1[row])));
+    out[i] = v;
+}
+// pad columns of the xn buffer: (1, 1, 0, ...) behind the d features of every row
+__global__ void k_xn_pad_init(bf16 *xn, int64_t M, int d, int ld) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int np = ld - d;
+    if (i >= M * np) return;
+    const int64_t row = i / np;
+    const int k = (int)(i - row * np);
+    xn[row * ld + d + k] = __float2bfloat16_rn(k < 2 ? 1.0f : 0.0f);
+}
+
 // W2 (d, ff) -> (ff/hc * d, hc): row c*d + n, column k  <-  W2[n][c*hc + k]
 __global__ void k_pack_ffn2(const bf16 *w2, bf16 *out, int d, int ff, int hc) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -644,26 +668,24 @@ __global__ void k_pack_ffn2(const bf16 *w2, bf16 *out, int d, int ff, int hc) {
     out[i] = w2[(size_t)n * ff + c * hc + k];
 }
 
-// x <- x + alpha * FFN(xn) [-> LN_final]; xn_out = bf16(LN_next(x)).  w1: (ff, d) bf16 scaled by 1/2, b1_host: HOST copy of
-// the bias scaled by 1/2, w2p: packed by k_pack_ffn2.  xn_out may alias xn (a tile is written after it has been read, and
-// only by its own CTA).
-static int launch_ffn_fused(cocr_handle *h, const bf16 *xn, int ldx, const bf16 *w1, const float *b1_host, const bf16 *w2p, const float *b2,
+// x <- x + alpha * FFN(xn) [-> LN_final]; xn_out = bf16(LN_next(x)).  xn: rows of 144 features followed by (1, 1, 0 x 14)
+// (k_xn_pad_init), w1p: packed by k_pack_ffn1, w2p: packed by k_pack_ffn2.  xn_out may alias xn (a tile is written after it
+// has been read, and only by its own CTA; the pad columns are never written).
+static int launch_ffn_fused(cocr_handle *h, const bf16 *xn, int ldx, const bf16 *w1p, const bf16 *w2p, const float *b2,
                             float *x, bf16 *xn_out, int ldo, float alpha, const float *gf, const float *bfin, const float *g1, const float *b1n,
                             int M, int ff, cudaStream_t st, const char *tag) {
     if (M <= 0) return COCR_OK;
-    if (ff % FFN_HC != 0 || ff / FFN_HC > FFN_MAX_NC || ldx % 8 != 0 || ldo % 4 != 0)
+    if (ff % FFN_HC != 0 || ff / FFN_HC > FFN_MAX_NC || ldx % 8 != 0 || ldx < FFN_K1 || ldo % 4 != 0)
         return set_error(h, COCR_ERR_UNSUPPORTED, "fused FFN needs ff = 96 * n (n <= %d) and aligned rows (ff=%d ldx=%d ldo=%d)", FFN_MAX_NC, ff, ldx, ldo);
     if (FFN_SMEM_BYTES > (uint32_t)h->bf->smem_optin) return set_error(h, COCR_ERR_UNSUPPORTED, "fused FFN does not fit shared memory");
     FfnArgs a;
     a.M = M; a.NC = ff / FFN_HC; a.m_tiles = (M + 127) / 128;
-    memset(a.b1, 0, sizeof(a.b1));
-    memcpy(a.b1, b1_host, (size_t)ff * sizeof(float));
     a.b2 = b2; a.x = x; a.xn_out = xn_out; a.ldo = ldo; a.alpha = alpha;
     a.gf = gf; a.bf = bfin; a.g1 = g1; a.b1n = b1n;
     { static const int dbg = getenv("COCR_FFN_DBG") ? atoi(getenv("COCR_FFN_DBG")) : 0; a.dbg = dbg; }
     CUtensorMap tmX, tmW1, tmW2;
-    COCR_TRY(make_tmap_bf16(h, &tmX, xn, M, FFN_D, ldx, 128));
-    COCR_TRY(make_tmap_bf16(h, &tmW1, w1, ff, FFN_D, FFN_D, FFN_HC));
+    COCR_TRY(make_tmap_bf16(h, &tmX, xn, M, FFN_K1, ldx, 128));
+    COCR_TRY(make_tmap_bf16(h, &tmW1, w1p, ff, FFN_K1, FFN_K1, FFN_HC));
     COCR_TRY(make_tmap_bf16(h, &tmW2, w2p, (int64_t)a.NC * FFN_D, FFN_HC, FFN_HC, FFN_D));
     static bool attr = false;
     if (!attr) {
@@ -727,20 +749,21 @@ int bf16_init(cocr_handle *h) {
         }
     COCR_LAUNCHED(h);
     if (bs->w_ffn2p) { cudaFree(bs->w_ffn2p); bs->w_ffn2p = nullptr; }
+    if (bs->w_ffn1p) { cudaFree(bs->w_ffn1p); bs->w_ffn1p = nullptr; }
     if (ffn_fused_ok(h) && dm.L > 0) {
-        const size_t nw = (size_t)dm.ff * dm.d;
+        const size_t nw = (size_t)dm.ff * dm.d, nw1 = (size_t)dm.ff * FFN_K1;
         void *pw = nullptr;
         COCR_CUDA(h, cudaMalloc(&pw, (size_t)dm.L * 2 * nw * sizeof(bf16)));
         bs->w_ffn2p = (bf16 *)pw;
+        COCR_CUDA(h, cudaMalloc(&pw, (size_t)dm.L * 2 * nw1 * sizeof(bf16)));
+        bs->w_ffn1p = (bf16 *)pw;
         for (int l = 0; l < dm.L; ++l)
-            for (int f = 0; f < 2; ++f)
+            for (int f = 0; f < 2; ++f) {
                 k_pack_ffn2<<<(unsigned)((nw + 255) / 256), 256>>>(bs->arena + (h->layers[l].ffn_w2[f] - h->arena), bs->w_ffn2p + ((size_t)l * 2 + f) * nw, dm.d, dm.ff, FFN_HC);
+                k_pack_ffn1<<<(unsigned)((nw1 + 255) / 256), 256>>>(bs->arena + (h->layers[l].ffn_w1[f] - h->arena), h->layers[l].ffn_b1[f],
+                                                                     bs->w_ffn1p + ((size_t)l * 2 + f) * nw1, dm.d, dm.ff, FFN_K1);
+            }
         COCR_LAUNCHED(h);
-        COCR_CUDA(h, cudaDeviceSynchronize());
-        bs->b1_host.resize((size_t)dm.L * 2 * dm.ff);
-        for (int l = 0; l < dm.L; ++l)
-            for (int f = 0; f < 2; ++f)
-                COCR_CUDA(h, cudaMemcpy(bs->b1_host.data() + ((size_t)l * 2 + f) * dm.ff, h->layers[l].ffn_b1[f], (size_t)dm.ff * sizeof(float), cudaMemcpyDeviceToHost));
     }
     {
         // pw1 for the GLU epilogue (convolution.py:138-139): GEMM column 2c = value channel c, 2c+1 = gate channel d + c
@@ -816,6 +839,7 @@ void bf16_destroy(cocr_handle *h) {
     if (bs->dw_taps) cudaFree(bs->dw_taps);
     if (bs->w_fe_pw2) cudaFree(bs->w_fe_pw2);
     if (bs->w_ffn2p) cudaFree(bs->w_ffn2p);
+    if (bs->w_ffn1p) cudaFree(bs->w_ffn1p);
     delete h->bf;
     h->bf = nullptr;
 }
@@ -838,6 +862,11 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
     bf16 *xn = (bf16 *)(ws + p.off_xn), *y = (bf16 *)(ws + p.off_y), *hb = (bf16 *)(ws + p.off_h), *g = (bf16 *)(ws + p.off_g);
     const int M = p.M, d = dm.d;
     const int ldx = xn_pitch(h);
+    if (ldx > d && ffn_fused_ok(h)) {           // ones columns behind the features (bias of the fused FFN's first GEMM)
+        const int64_t n = (int64_t)M * (ldx - d);
+        k_xn_pad_init<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(xn, M, d, ldx);
+        COCR_LAUNCHED(h);
+    }
 
     if (out_lens) COCR_TRY(launch_out_lens(h, widths, B, W, out_lens, st));
     const int32_t *lens_dev = nullptr;
@@ -899,7 +928,7 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
     auto ffn_module = [&](int l, int f, const float *gf, const float *bfin, const float *g1, const float *b1, const char *tag_down) -> int {
         const LayerF32 &lw = h->layers[l];
         if (fused && h->bf->w_ffn2p)      // one kernel, the hidden activation stays on the SM
-            return launch_ffn_fused(h, xn, ldx, WB(h, lw.ffn_w1[f]), h->bf->b1_host.data() + ((size_t)l * 2 + f) * dm.ff, h->bf->w_ffn2p + ((size_t)l * 2 + f) * dm.ff * d, lw.ffn_b2[f], x, xn,
+            return launch_ffn_fused(h, xn, ldx, h->bf->w_ffn1p + ((size_t)l * 2 + f) * dm.ff * FFN_K1, h->bf->w_ffn2p + ((size_t)l * 2 + f) * dm.ff * d, lw.ffn_b2[f], x, xn,
                                     ldx, dm.ffn_factor, gf, bfin, g1, b1, M, dm.ff, st, f ? "ffn_fused_final" : "ffn_fused");
         for (int b0 = 0; b0 < B; b0 += ffn_lines) {
             const int nb = std::min(ffn_lines, B - b0), r0 = b0 * p.T, rows = nb * p.T;
@@ -1209,9 +1238,10 @@ int selftest_ffn(int device, int M, int NC, int flags, double *max_err) {
     h->bf = new Bf16State();
     cudaDeviceGetAttribute(&h->bf->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     const int d = FFN_D, ff = NC * FFN_HC;
-    bf16 *xn, *w1, *w2, *w2p, *xo;
+    bf16 *xn, *w1, *w2, *w2p, *xo, *xnp, *w1p;
     float *b1, *b2, *x, *ln, *href;
     cudaMalloc((void **)&xn, (size_t)M * d * 2); cudaMalloc((void **)&xo, (size_t)M * d * 2);
+    cudaMalloc((void **)&xnp, (size_t)M * FFN_K1 * 2); cudaMalloc((void **)&w1p, (size_t)ff * FFN_K1 * 2);
     cudaMalloc((void **)&w1, (size_t)ff * d * 2); cudaMalloc((void **)&w2, (size_t)ff * d * 2); cudaMalloc((void **)&w2p, (size_t)ff * d * 2);
     cudaMalloc((void **)&b1, (size_t)ff * 4); cudaMalloc((void **)&b2, (size_t)d * 4); cudaMalloc((void **)&x, (size_t)M * d * 4);
     cudaMalloc((void **)&ln, (size_t)4 * d * 4); cudaMalloc((void **)&href, (size_t)M * ff * 4);
@@ -1223,9 +1253,11 @@ int selftest_ffn(int device, int M, int NC, int flags, double *max_err) {
     k_fill_f32<<<(unsigned)(((size_t)M * d + 255) / 256), 256>>>(x, (size_t)M * d, 16u, 2.0f);
     k_fill_f32<<<(4 * d + 255) / 256, 256>>>(ln, (size_t)4 * d, 17u, 1.0f);
     k_pack_ffn2<<<(unsigned)(((size_t)ff * d + 255) / 256), 256>>>(w2, w2p, d, ff, FFN_HC);
+    k_pack_ffn1<<<(unsigned)(((size_t)ff * FFN_K1 + 255) / 256), 256>>>(w1, b1, w1p, d, ff, FFN_K1);
+    cudaMemcpy2D(xnp, (size_t)FFN_K1 * 2, xn, (size_t)d * 2, (size_t)d * 2, (size_t)M, cudaMemcpyDeviceToDevice);
+    k_xn_pad_init<<<(unsigned)(((size_t)M * (FFN_K1 - d) + 255) / 256), 256>>>(xnp, M, d, FFN_K1);
     k_ref_gemm<<<(unsigned)(((size_t)M * ff + 255) / 256), 256>>>(xn, w1, b1, href, M, ff, d, 0);     // h = xn W1^T + b1 (the "half" pre-activation)
-    std::vector<float> hx((size_t)M * d), hh((size_t)M * ff), hln(4 * d), hb2(d), hb1(ff);
-    cudaMemcpy(hb1.data(), b1, hb1.size() * 4, cudaMemcpyDeviceToHost);
+    std::vector<float> hx((size_t)M * d), hh((size_t)M * ff), hln(4 * d), hb2(d);
     std::vector<uint16_t> hw2((size_t)ff * d);
     cudaMemcpy(hx.data(), x, hx.size() * 4, cudaMemcpyDeviceToHost);
     cudaMemcpy(hh.data(), href, hh.size() * 4, cudaMemcpyDeviceToHost);
@@ -1234,7 +1266,7 @@ int selftest_ffn(int device, int M, int NC, int flags, double *max_err) {
     cudaMemcpy(hw2.data(), w2, hw2.size() * 2, cudaMemcpyDeviceToHost);
     const bool fin = flags & 2, nxt = flags & 4;
     const float alpha = 0.5f;
-    rc = launch_ffn_fused(h, xn, d, w1, hb1.data(), w2p, b2, x, xo, d, alpha, fin ? ln : nullptr, fin ? ln + d : nullptr, nxt ? ln + 2 * d : nullptr,
+    rc = launch_ffn_fused(h, xnp, FFN_K1, w1p, w2p, b2, x, xo, d, alpha, fin ? ln : nullptr, fin ? ln + d : nullptr, nxt ? ln + 2 * d : nullptr,
                           nxt ? ln + 3 * d : nullptr, M, ff, 0, "selftest_ffn");
     cudaError_t e = cudaDeviceSynchronize();
     if (rc == COCR_OK && e != cudaSuccess) rc = set_error(h, COCR_ERR_CUDA, "selftest_ffn: %s", cudaGetErrorString(e));
@@ -1285,7 +1317,7 @@ int selftest_ffn(int device, int M, int NC, int flags, double *max_err) {
             cudaEventCreate(&e0); cudaEventCreate(&e1);
             cudaEventRecord(e0);
             for (int i = 0; i < 20; ++i)
-                launch_ffn_fused(h, xn, d, w1, hb1.data(), w2p, b2, x, xo, d, alpha, nullptr, nullptr, ln + 2 * d, ln + 3 * d, M, ff, 0, "selftest_ffn");
+                launch_ffn_fused(h, xnp, FFN_K1, w1p, w2p, b2, x, xo, d, alpha, nullptr, nullptr, ln + 2 * d, ln + 3 * d, M, ff, 0, "selftest_ffn");
             cudaEventRecord(e1);
             cudaEventSynchronize(e1);
             float ms = 0.f;
@@ -1297,7 +1329,7 @@ int selftest_ffn(int device, int M, int NC, int flags, double *max_err) {
         set_global_error(h->err.c_str());
     }
     if (max_err) *max_err = worst;
-    cudaFree(xn); cudaFree(xo); cudaFree(w1); cudaFree(w2); cudaFree(w2p); cudaFree(b1); cudaFree(b2); cudaFree(x); cudaFree(ln); cudaFree(href);
+    cudaFree(xnp); cudaFree(w1p); cudaFree(xn); cudaFree(xo); cudaFree(w1); cudaFree(w2); cudaFree(w2p); cudaFree(b1); cudaFree(b2); cudaFree(x); cudaFree(ln); cudaFree(href);
     cocr_destroy(h);
     return rc;
 }

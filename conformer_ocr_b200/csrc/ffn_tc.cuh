@@ -18,9 +18,12 @@
 //
 // Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (G1 runs one chunk ahead of G2), warps 2..9 = E1
 // (two per TMEM lane quarter, 48 of the 96 hidden columns each), warps 10..13 = final epilogue (one per lane quarter).
-// E1 is MUFU bound (one tanh per hidden element); it therefore reads nothing from memory: the bias comes from the
-// kernel-parameter constant bank as an immediate operand (the chunk index is unrolled), because shared-memory loads
-// queue behind the final epilogue's global loads / stores / shuffles in the same memory pipeline.
+// E1 is MUFU bound (one tanh per hidden element) and reads nothing from memory: the FFN-up bias rides in the GEMM.  The
+// xn rows carry two extra columns of ones (144, 145; the xn buffer has a pitch of 160 and its pad columns are initialised
+// once per forward pass) and W1 carries the bias split into a bf16 high and low part in the same two columns, so
+// G1 has K = 160 (one more k-step) and its accumulator already holds W1 xn + b1 to fp32 accuracy.  (Bias reads from
+// shared memory queued behind the final epilogue's global loads / stores / shuffles in the same memory pipeline, and
+// reads from the constant bank missed the constant cache: both made E1 2-3x slower than its MUFU bound.)
 // TMEM (512 columns): H0 at 0, H1 at 96, Y0 at 192, Y1 at 336.
 #pragma once
 
@@ -29,6 +32,7 @@
 namespace cocr {
 
 constexpr int FFN_D = 144;
+constexpr int FFN_K1 = 160;                                       // K of G1: 144 features + (1, 1) for the bias + 14 zeros
 constexpr int FFN_HC = 96;                                        // hidden units per chunk
 constexpr int FFN_NG = FFN_D / 8;                                 // 8-column groups per row
 constexpr int FFN_MAX_NC = 8;                                     // ff <= 768
@@ -61,34 +65,7 @@ struct FfnArgs {
     long long *trace;           // debug: (tag, clock) pairs of CTA 0 (COCR_FFN_TRACE=<file>), else null
     int dbg;                    // experiments (COCR_FFN_DBG, results are garbage): 1 no weight loads, 4 no final epilogue
                                 //    memory traffic, 8 no MMAs, 16 no xn tile loads
-    float b1[FFN_MAX_NC * FFN_HC];   // FFN-up bias, pre-scaled by 1/2 like the weights (silu from half, gemm_tc.cuh); lives in the
-                                     // constant bank with the other kernel parameters
 };
-
-// E1 arithmetic for hidden chunk C, column half HF: 48 accumulator columns -> 24 packed bf16 pairs
-template <int C, int HF>
-__device__ __forceinline__ void ffn_e1_math(const FfnArgs &p, const uint32_t (&r0)[32], const uint32_t (&r1)[16], uint32_t (&pk)[24]) {
-#pragma unroll
-    for (int e = 0; e < 24; ++e) {
-        const uint32_t u0 = e < 16 ? r0[2 * e] : r1[2 * e - 32], u1 = e < 16 ? r0[2 * e + 1] : r1[2 * e - 31];
-        const float2 h = make_float2(__uint_as_float(u0) + p.b1[C * FFN_HC + HF * 48 + 2 * e], __uint_as_float(u1) + p.b1[C * FFN_HC + HF * 48 + 2 * e + 1]);
-        const float2 sv = silu_from_half(h);
-        pk[e] = pack_bf16x2(sv.x, sv.y);
-    }
-}
-template <int HF>
-__device__ __forceinline__ void ffn_e1_math_c(const FfnArgs &p, int c, const uint32_t (&r0)[32], const uint32_t (&r1)[16], uint32_t (&pk)[24]) {
-    switch (c) {
-        case 0: ffn_e1_math<0, HF>(p, r0, r1, pk); break;
-        case 1: ffn_e1_math<1, HF>(p, r0, r1, pk); break;
-        case 2: ffn_e1_math<2, HF>(p, r0, r1, pk); break;
-        case 3: ffn_e1_math<3, HF>(p, r0, r1, pk); break;
-        case 4: ffn_e1_math<4, HF>(p, r0, r1, pk); break;
-        case 5: ffn_e1_math<5, HF>(p, r0, r1, pk); break;
-        case 6: ffn_e1_math<6, HF>(p, r0, r1, pk); break;
-        default: ffn_e1_math<7, HF>(p, r0, r1, pk); break;
-    }
-}
 
 __global__ void __launch_bounds__(FFN_THREADS, 1)
 k_ffn_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
@@ -203,7 +180,7 @@ k_ffn_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
             const uint32_t d_tmem = tmem_base + ((n & 1) ? FFN_H_COL1 : FFN_H_COL0);
             if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < FFN_D / 16; ++k) {
+                for (int k = 0; k < FFN_K1 / 16; ++k) {
                     if (p.dbg & 8) break;
                     const uint32_t off = (uint32_t)(k >> 2), ks = (uint32_t)(k & 3);
                     umma_bf16_ss(d_tmem, make_smem_desc_sw128(a_base + off * FFN_A_CHUNK + ks * 32, 1024),
@@ -280,8 +257,12 @@ k_ffn_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
             named_bar_sync(1 + q, 64);
             GEMM_TRACE(0, 320 + c);
             uint32_t pk[24];
-            if (hf == 0) ffn_e1_math_c<0>(p, c, r0, r1, pk);
-            else ffn_e1_math_c<1>(p, c, r0, r1, pk);
+#pragma unroll
+            for (int e = 0; e < 24; ++e) {
+                const uint32_t u0 = e < 16 ? r0[2 * e] : r1[2 * e - 32], u1 = e < 16 ? r0[2 * e + 1] : r1[2 * e - 31];
+                const float2 sv = silu_from_half(make_float2(__uint_as_float(u0), __uint_as_float(u1)));
+                pk[e] = pack_bf16x2(sv.x, sv.y);
+            }
             GEMM_TRACE(0, 340 + c);
             tmem_st_32x32b_x16n(hcol + (uint32_t)(hf * 24), pk);
             tmem_st_32x32b_x8_at<16>(hcol + (uint32_t)(hf * 24 + 16), pk);
