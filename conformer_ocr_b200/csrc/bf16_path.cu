@@ -1315,6 +1315,8 @@ int selftest_ffn(int device, int M, int NC, int flags, double *max_err) {
         if (flags & 8) {
             cudaEvent_t e0, e1;
             cudaEventCreate(&e0); cudaEventCreate(&e1);
+            for (int i = 0; i < 1500; ++i)      // ~100 ms of warm-up: the SM clock ramps up only under sustained load
+                launch_ffn_fused(h, xnp, FFN_K1, w1p, w2p, b2, x, xo, d, alpha, nullptr, nullptr, ln + 2 * d, ln + 3 * d, M, ff, 0, "selftest_ffn");
             cudaEventRecord(e0);
             for (int i = 0; i < 20; ++i)
                 launch_ffn_fused(h, xnp, FFN_K1, w1p, w2p, b2, x, xo, d, alpha, nullptr, nullptr, ln + 2 * d, ln + 3 * d, M, ff, 0, "selftest_ffn");

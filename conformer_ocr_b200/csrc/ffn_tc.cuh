@@ -10,14 +10,14 @@
 // Built for encoder_dim 144 and ff = 96 * NC.  A persistent CTA takes 128-row tiles; per tile and hidden chunk c (96
 // hidden units):
 //     G1(c):  H_c  = xn_tile (128 x 144, smem)   * W1_c^T (96 x 144, smem)   -> TMEM accumulator (fp32, double-buffered)
-//     E1(c):  H_c <- bf16(silu(H_c + b1_c)) written IN PLACE as packed pairs over the first 48 columns of the accumulator
+//     E1(c):  H_c <- bf16(silu(H_c + b1_c)) written IN PLACE as packed pairs (columns 0..23 and 72..95 of the accumulator)
 //     G2(c):  Y   += H_c (TMEM A operand, K = 96) * W2_c^T (144 x 96, smem)   -> TMEM accumulator Y (double-buffered by tile)
 // and after the last chunk the residual / LayerNorm epilogue of EPI_RESID (gemm_tc.cuh) drains Y while the next tile
 // is already running.  The weight chunks (36 KB each) stream from L2 through a three-slot ring in the order the MMAs
 // consume them; the xn tiles are double-buffered and requested a tile ahead.
 //
 // Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (G1 runs one chunk ahead of G2), warps 2..9 = E1
-// (two per TMEM lane quarter, 48 of the 96 hidden columns each), warps 10..13 = final epilogue (one per lane quarter).
+// (two per TMEM lane quarter, 48 of the 96 hidden columns each), warps 10..17 = final epilogue (two per lane quarter).
 // E1 is MUFU bound (one tanh per hidden element) and reads nothing from memory: the FFN-up bias rides in the GEMM.  The
 // xn rows carry two extra columns of ones (144, 145; the xn buffer has a pitch of 160 and its pad columns are initialised
 // once per forward pass) and W1 carries the bias split into a bf16 high and low part in the same two columns, so
@@ -37,7 +37,7 @@ constexpr int FFN_HC = 96;                                        // hidden unit
 constexpr int FFN_NG = FFN_D / 8;                                 // 8-column groups per row
 constexpr int FFN_MAX_NC = 8;                                     // ff <= 768
 constexpr int FFN_EPI_WARPS = 8;                                  // E1 warps (two per TMEM lane quarter)
-constexpr int FFN_FIN_WARPS = 4;                                  // final-epilogue warps (one per lane quarter)
+constexpr int FFN_FIN_WARPS = 8;                                  // final-epilogue warps (two per lane quarter, 16 rows each)
 constexpr int FFN_THREADS = 64 + 32 * (FFN_EPI_WARPS + FFN_FIN_WARPS);
 constexpr int FFN_WSTAGES = 3;
 constexpr uint32_t FFN_A_CHUNK = 128 * 128;                       // one 64-column k-chunk of the xn tile (SWIZZLE_128B)
@@ -214,7 +214,7 @@ k_ffn_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
                 for (int k = 0; k < FFN_HC / 16; ++k) {
                     if (p.dbg & 8) break;
                     const uint32_t off = (uint32_t)(k >> 2), ks = (uint32_t)(k & 3);
-                    umma_bf16_ts(y_tmem, a_tmem + (uint32_t)k * 8u, make_smem_desc_sw128(b_base + off * FFN_W2_CHUNK + ks * 32, 1024), idesc2,
+                    umma_bf16_ts(y_tmem, a_tmem + (uint32_t)(k < 3 ? k * 8 : 72 + (k - 3) * 8), make_smem_desc_sw128(b_base + off * FFN_W2_CHUNK + ks * 32, 1024), idesc2,
                                  (c | k) ? 1u : 0u);
                 }
                 umma_commit(&wempty[sl]);
@@ -253,8 +253,6 @@ k_ffn_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
             tmem_ld_32x32b_x32(hcol + (uint32_t)(hf * 48), r0);
             tmem_ld_32x32b_x16(hcol + (uint32_t)(hf * 48 + 32), r1);
             tmem_ld_wait_dep(r0); tmem_ld_wait_dep(r1);
-            // the packed output of the upper half lands on columns 24..47, which the lower half has just read as fp32
-            named_bar_sync(1 + q, 64);
             GEMM_TRACE(0, 320 + c);
             uint32_t pk[24];
 #pragma unroll
@@ -264,8 +262,10 @@ k_ffn_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
                 pk[e] = pack_bf16x2(sv.x, sv.y);
             }
             GEMM_TRACE(0, 340 + c);
-            tmem_st_32x32b_x16n(hcol + (uint32_t)(hf * 24), pk);
-            tmem_st_32x32b_x8_at<16>(hcol + (uint32_t)(hf * 24 + 16), pk);
+            // each warp packs into columns it has read itself (lower half -> 0..23, upper half -> 72..95): no ordering
+            // between the two warps of a quarter is needed; G2 takes its k-steps 0-2 / 3-5 from the two ranges
+            tmem_st_32x32b_x16n(hcol + (uint32_t)(hf * 72), pk);
+            tmem_st_32x32b_x8_at<16>(hcol + (uint32_t)(hf * 72 + 16), pk);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -275,31 +275,32 @@ k_ffn_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
         }
     } else {
         // ================= final-epilogue warps =================
-        // x <- x + alpha * (Y + b2) [-> LN_final]; xn = bf16(LN_next(x)); fragment layout (see EPI_RESID in gemm_tc.cuh),
-        // one warp per lane quarter, two 16-row halves.  Their own warps: the x / xn traffic of a tile (184 KB through the
-        // LSU) and the LayerNorm arithmetic overlap the next tile's GEMMs and E1 instead of stalling them; Y is double-
-        // buffered, so they have a whole tile period for it.
+        // x <- x + alpha * (Y + b2) [-> LN_final]; xn = bf16(LN_next(x)); fragment layout (see EPI_RESID in gemm_tc.cuh).
+        // Their own warps: the x / xn traffic of a tile (184 KB through the LSU) and the LayerNorm arithmetic overlap the
+        // next tile's GEMMs and E1 instead of stalling them; Y is double-buffered, so they have a whole tile period for it.
+        // Two warps per lane quarter, 16 rows each, ONE row per lane quad at a time (two passes over the warp's Y rows: the
+        // 16x256b load returns rows r and r+8 together and the pass keeps one of them): half the registers of the two-row
+        // form, which is what lets eight of these warps sit next to the E1 warps.
         const int q = warp & 3;
+        const int hf = (warp - 2 - FFN_EPI_WARPS) >> 2;
         int tr_n = GEMM_TRACE_EVENTS;
         for (int t = 0; t < my_tiles; ++t) {
 #pragma unroll 1
-            for (int hf = 0; hf < 2; ++hf) {
+            for (int pass = 0; pass < 2; ++pass) {
                 constexpr int NG = FFN_NG;
                 const int r_in = lane >> 2, qd = lane & 3;
                 const float inv_n = 1.0f / (float)FFN_D;
                 const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
-                const int64_t rowA = tile * 128 + q * 32 + hf * 16 + r_in, rowB = rowA + 8;
-                const bool okA = rowA < p.M && !(p.dbg & 4), okB = rowB < p.M && !(p.dbg & 4);
-                float2 va[NG], vb[NG];
-                float *xa = p.x + rowA * FFN_D + 4 * qd, *xb = p.x + rowB * FFN_D + 4 * qd;
+                const int64_t row = tile * 128 + q * 32 + hf * 16 + pass * 8 + r_in;
+                const bool ok = row < p.M && !(p.dbg & 4);
+                float2 v[NG];
+                float *xr = p.x + row * FFN_D + 4 * qd;
 #pragma unroll
                 for (int gp = 0; gp < NG / 2; ++gp) {
-                    const float4 ta = okA ? *reinterpret_cast<const float4 *>(xa + 16 * gp) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float4 tb = okB ? *reinterpret_cast<const float4 *>(xb + 16 * gp) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    va[2 * gp] = make_float2(ta.x, ta.y); va[2 * gp + 1] = make_float2(ta.z, ta.w);
-                    vb[2 * gp] = make_float2(tb.x, tb.y); vb[2 * gp + 1] = make_float2(tb.z, tb.w);
+                    const float4 ta = ok ? *reinterpret_cast<const float4 *>(xr + 16 * gp) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[2 * gp] = make_float2(ta.x, ta.y); v[2 * gp + 1] = make_float2(ta.z, ta.w);
                 }
-                if (hf == 0) {
+                if (pass == 0) {
                     mbar_wait(&yfull[t & 1], ((uint32_t)t >> 1) & 1u);
                     tc_fence_after();
                 }
@@ -309,7 +310,7 @@ k_ffn_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
                     uint32_t t1[8];
                     tmem_ld_16x256b_x2(taddr + 16u * blk, t1);
                     tmem_ld_wait_dep(t1);
-                    if (blk == NG / 2 - 1 && hf == 1) {            // Y is in registers: tile t+2 may overwrite it
+                    if (blk == NG / 2 - 1 && pass == 1) {          // Y is in registers: tile t+2 may overwrite it
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&yempty[t & 1]);
@@ -318,74 +319,65 @@ k_ffn_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
                     for (int gg = 0; gg < 2; ++gg) {
                         const int g = 2 * blk + gg;
                         const float2 b2 = *reinterpret_cast<const float2 *>(sb2 + 8 * g + 2 * qd);
-                        va[g].x = fmaf(p.alpha, __uint_as_float(t1[4 * gg]) + b2.x, va[g].x);
-                        va[g].y = fmaf(p.alpha, __uint_as_float(t1[4 * gg + 1]) + b2.y, va[g].y);
-                        vb[g].x = fmaf(p.alpha, __uint_as_float(t1[4 * gg + 2]) + b2.x, vb[g].x);
-                        vb[g].y = fmaf(p.alpha, __uint_as_float(t1[4 * gg + 3]) + b2.y, vb[g].y);
+                        const float y0 = __uint_as_float(pass ? t1[4 * gg + 2] : t1[4 * gg]), y1 = __uint_as_float(pass ? t1[4 * gg + 3] : t1[4 * gg + 1]);
+                        v[g].x = fmaf(p.alpha, y0 + b2.x, v[g].x);
+                        v[g].y = fmaf(p.alpha, y1 + b2.y, v[g].y);
                     }
                 }
-                // LayerNorm statistics of rows A and B (two passes in registers; a row lives in one quad of lanes)
-                auto stats = [&](float &meanA, float &rstdA, float &meanB, float &rstdB) {
-                    float sA = 0.f, sB = 0.f;
+                // LayerNorm statistics (two passes in registers; the row lives in one quad of lanes)
+                auto stats = [&](float &mean, float &rstd) {
+                    float sA = 0.f;
 #pragma unroll
-                    for (int g = 0; g < NG; ++g) { sA += va[g].x + va[g].y; sB += vb[g].x + vb[g].y; }
-                    sA += __shfl_xor_sync(0xffffffffu, sA, 1); sB += __shfl_xor_sync(0xffffffffu, sB, 1);
-                    sA += __shfl_xor_sync(0xffffffffu, sA, 2); sB += __shfl_xor_sync(0xffffffffu, sB, 2);
-                    meanA = sA * inv_n; meanB = sB * inv_n;
-                    float qA = 0.f, qB = 0.f;
+                    for (int g = 0; g < NG; ++g) sA += v[g].x + v[g].y;
+                    sA += __shfl_xor_sync(0xffffffffu, sA, 1);
+                    sA += __shfl_xor_sync(0xffffffffu, sA, 2);
+                    mean = sA * inv_n;
+                    float qA = 0.f;
 #pragma unroll
                     for (int g = 0; g < NG; ++g) {
-                        float d0 = va[g].x - meanA, d1 = va[g].y - meanA;
+                        const float d0 = v[g].x - mean, d1 = v[g].y - mean;
                         qA = fmaf(d0, d0, qA); qA = fmaf(d1, d1, qA);
-                        d0 = vb[g].x - meanB; d1 = vb[g].y - meanB;
-                        qB = fmaf(d0, d0, qB); qB = fmaf(d1, d1, qB);
                     }
-                    qA += __shfl_xor_sync(0xffffffffu, qA, 1); qB += __shfl_xor_sync(0xffffffffu, qB, 1);
-                    qA += __shfl_xor_sync(0xffffffffu, qA, 2); qB += __shfl_xor_sync(0xffffffffu, qB, 2);
-                    rstdA = rsqrtf(qA * inv_n + 1e-5f); rstdB = rsqrtf(qB * inv_n + 1e-5f);
+                    qA += __shfl_xor_sync(0xffffffffu, qA, 1);
+                    qA += __shfl_xor_sync(0xffffffffu, qA, 2);
+                    rstd = rsqrtf(qA * inv_n + 1e-5f);
                 };
                 if (p.gf) {   // block-final LayerNorm replaces the residual stream (encoder.py:99)
-                    float mA, rA, mB, rB;
-                    stats(mA, rA, mB, rB);
+                    float m, r;
+                    stats(m, r);
 #pragma unroll
                     for (int g = 0; g < NG; ++g) {
                         const float2 gg = *reinterpret_cast<const float2 *>(sln + 8 * g + 2 * qd);
                         const float2 bb = *reinterpret_cast<const float2 *>(sln + FFN_D + 8 * g + 2 * qd);
-                        va[g].x = (va[g].x - mA) * rA * gg.x + bb.x; va[g].y = (va[g].y - mA) * rA * gg.y + bb.y;
-                        vb[g].x = (vb[g].x - mB) * rB * gg.x + bb.x; vb[g].y = (vb[g].y - mB) * rB * gg.y + bb.y;
+                        v[g].x = (v[g].x - m) * r * gg.x + bb.x; v[g].y = (v[g].y - m) * r * gg.y + bb.y;
                     }
                 }
 #pragma unroll
-                for (int gp = 0; gp < NG / 2; ++gp) {
-                    if (okA) *reinterpret_cast<float4 *>(xa + 16 * gp) = make_float4(va[2 * gp].x, va[2 * gp].y, va[2 * gp + 1].x, va[2 * gp + 1].y);
-                    if (okB) *reinterpret_cast<float4 *>(xb + 16 * gp) = make_float4(vb[2 * gp].x, vb[2 * gp].y, vb[2 * gp + 1].x, vb[2 * gp + 1].y);
-                }
-                float mA = 0.f, rA = 1.f, mB = 0.f, rB = 1.f;
-                if (p.g1) stats(mA, rA, mB, rB);
-                uint32_t pa[NG], pb[NG];
+                for (int gp = 0; gp < NG / 2; ++gp)
+                    if (ok) *reinterpret_cast<float4 *>(xr + 16 * gp) = make_float4(v[2 * gp].x, v[2 * gp].y, v[2 * gp + 1].x, v[2 * gp + 1].y);
+                float m = 0.f, r = 1.f;
+                if (p.g1) stats(m, r);
+                uint32_t pa[NG];
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    float a0 = va[g].x, a1 = va[g].y, c0 = vb[g].x, c1 = vb[g].y;
+                    float a0 = v[g].x, a1 = v[g].y;
                     if (p.g1) {
                         const float2 gg = *reinterpret_cast<const float2 *>(sln + 2 * FFN_D + 8 * g + 2 * qd);
                         const float2 bb = *reinterpret_cast<const float2 *>(sln + 3 * FFN_D + 8 * g + 2 * qd);
-                        a0 = (a0 - mA) * rA * gg.x + bb.x; a1 = (a1 - mA) * rA * gg.y + bb.y;
-                        c0 = (c0 - mB) * rB * gg.x + bb.x; c1 = (c1 - mB) * rB * gg.y + bb.y;
+                        a0 = (a0 - m) * r * gg.x + bb.x; a1 = (a1 - m) * r * gg.y + bb.y;
                     }
                     pa[g] = pack_bf16x2(a0, a1);
-                    pb[g] = pack_bf16x2(c0, c1);
                 }
-                __nv_bfloat16 *na = p.xn_out + rowA * p.ldo, *nb = p.xn_out + rowB * p.ldo;
+                // neighbouring lanes swap one packed pair: every lane stores 8 bytes, a quad the 32 contiguous bytes of two groups
+                __nv_bfloat16 *na = p.xn_out + row * p.ldo;
                 const bool odd = qd & 1;
 #pragma unroll
                 for (int g = 0; g < NG; g += 2) {
-                    const uint32_t sendA = odd ? pa[g] : pa[g + 1], sendB = odd ? pb[g] : pb[g + 1];
-                    const uint32_t recvA = __shfl_xor_sync(0xffffffffu, sendA, 1), recvB = __shfl_xor_sync(0xffffffffu, sendB, 1);
+                    const uint32_t send = odd ? pa[g] : pa[g + 1];
+                    const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
                     const int col = odd ? 8 * (g + 1) + 2 * (qd - 1) : 8 * g + 2 * qd;
-                    const uint2 oA = odd ? make_uint2(recvA, pa[g + 1]) : make_uint2(pa[g], recvA);
-                    const uint2 oB = odd ? make_uint2(recvB, pb[g + 1]) : make_uint2(pb[g], recvB);
-                    if (okA) *reinterpret_cast<uint2 *>(na + col) = oA;
-                    if (okB) *reinterpret_cast<uint2 *>(nb + col) = oB;
+                    const uint2 o = odd ? make_uint2(recv, pa[g + 1]) : make_uint2(pa[g], recv);
+                    if (ok) *reinterpret_cast<uint2 *>(na + col) = o;
                 }
             }
         }
