@@ -17,6 +17,14 @@ namespace cocr {
 
 typedef __nv_bfloat16 bf16;
 
+struct LayerGraph {      // captured encoder-layer sequence for one (batch, frames, mask, buffers) combination
+    int B, T;
+    const void *lens, *ws, *etab, *pos;
+    cudaGraphExec_t exec;
+    int64_t launches;
+    int state;           // 1 seen once (ran eagerly), 2 captured, -1 capture failed: always eager
+};
+
 struct Bf16State {
     bf16 *arena = nullptr;        // bf16 mirror of the fp32 weight arena (same offsets)
     int smem_optin = 0;
@@ -39,6 +47,9 @@ struct Bf16State {
                                   // columns 144 / 145 (the xn rows carry ones there), zeros up to column 159
     float *dw_taps = nullptr;     // (L, K*d + d): depthwise taps [k][pair](2) * bn_scale / 2, then bn_shift / 2
     int tab_T = 0;
+    std::vector<LayerGraph> graphs;
+    cudaStream_t gstream = nullptr;
+    cudaEvent_t g_in = nullptr, g_out = nullptr;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -732,6 +743,8 @@ int bf16_init(cocr_handle *h) {
                          "(got %d, %d, %d)", 32 * ROW_MAXPER, dm.d, dm.ff, dm.feat);
     if (!h->bf) h->bf = new Bf16State();
     Bf16State *bs = h->bf;
+    for (LayerGraph &e : bs->graphs) if (e.exec) cudaGraphExecDestroy(e.exec);   // captured weight pointers die with the arena
+    bs->graphs.clear();
     if (bs->arena) { cudaFree(bs->arena); bs->arena = nullptr; }
     void *p = nullptr;
     COCR_CUDA(h, cudaMalloc(&p, h->arena_floats * sizeof(bf16)));
@@ -840,6 +853,10 @@ void bf16_destroy(cocr_handle *h) {
     if (bs->w_fe_pw2) cudaFree(bs->w_fe_pw2);
     if (bs->w_ffn2p) cudaFree(bs->w_ffn2p);
     if (bs->w_ffn1p) cudaFree(bs->w_ffn1p);
+    for (LayerGraph &e : bs->graphs) if (e.exec) cudaGraphExecDestroy(e.exec);
+    if (bs->g_in) cudaEventDestroy(bs->g_in);
+    if (bs->g_out) cudaEventDestroy(bs->g_out);
+    if (bs->gstream) cudaStreamDestroy(bs->gstream);
     delete h->bf;
     h->bf = nullptr;
 }
@@ -940,6 +957,9 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
     };
     const float *g0 = dm.L > 0 ? h->layers[0].ffn_ln_g[0] : nullptr, *b0 = dm.L > 0 ? h->layers[0].ffn_ln_b[0] : nullptr;
     COCR_TRY(resid_gemm(feat, dm.feat, h->sub_wout, h->sub_bout, 1.f, 1, nullptr, nullptr, g0, b0, "gemm_sub_out"));
+    // the encoder layers: ~11 launches per layer that touch nothing but the workspace and the packed weights, so the
+    // sequence is replayed as a CUDA graph (see below); every lambda above launches on `st` by reference
+    auto run_layers = [&]() -> int {
     for (int l = 0; l < dm.L; ++l) {
         const LayerF32 &lw = h->layers[l];
         // FFN 1 (feed_forward.py:45-55; half-step residual encoder.py:68-75) -> LayerNorm of the attention module
@@ -983,6 +1003,69 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
         const float *nb = (l + 1 < dm.L) ? h->layers[l + 1].ffn_ln_b[0] : nullptr;
         COCR_TRY(ffn_module(l, 1, lw.final_ln_g, lw.final_ln_b, ng, nb, "gemm_ffn_down_final"));
     }
+    return COCR_OK;
+    };
+
+    // CUDA graph of the layer sequence, keyed by everything its kernel arguments depend on.  First call with a key runs
+    // eagerly (it also settles the one-time function attributes), the second captures, later ones replay.  The graph
+    // runs on the handle's own stream, fenced against the caller's stream with two events, because the caller's stream
+    // may be the legacy default stream, which cannot be captured.  Measured: 7.49 -> 7.19 ms per step (launch gaps).
+    Bf16State *bs = h->bf;
+    static const bool no_graph = getenv("COCR_NO_GRAPH") != nullptr || getenv("COCR_FFN_TRACE") || getenv("COCR_ATTN_TRACE") || getenv("COCR_GEMM_TRACE");
+    bool use_graph = !no_graph && !h->profiling && dm.L > 0;
+    if (use_graph) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); use_graph = false; }
+    }
+    if (!use_graph) return run_layers();
+    LayerGraph *lg = nullptr;
+    for (LayerGraph &e : bs->graphs)
+        if (e.B == B && e.T == p.T && e.lens == (const void *)lens_dev && e.ws == ws && e.etab == (const void *)bs->etab && e.pos == (const void *)h->pos_proj) lg = &e;
+    if (!lg) {
+        if (bs->graphs.size() >= 16) {                        // shapes keep changing: do not hoard graphs
+            for (LayerGraph &e : bs->graphs) if (e.exec) cudaGraphExecDestroy(e.exec);
+            bs->graphs.clear();
+        }
+        bs->graphs.push_back({B, p.T, (const void *)lens_dev, ws, (const void *)bs->etab, (const void *)h->pos_proj, nullptr, 0, 1});
+        return run_layers();
+    }
+    if (lg->state < 0) return run_layers();
+    if (!bs->gstream) {
+        COCR_CUDA(h, cudaStreamCreateWithFlags(&bs->gstream, cudaStreamNonBlocking));
+        COCR_CUDA(h, cudaEventCreateWithFlags(&bs->g_in, cudaEventDisableTiming));
+        COCR_CUDA(h, cudaEventCreateWithFlags(&bs->g_out, cudaEventDisableTiming));
+    }
+    if (lg->state == 1) {
+        const int64_t launches0 = h->launches;
+        cudaStream_t caller = st;
+        cudaGraph_t graph = nullptr;
+        bool ok = cudaStreamBeginCapture(bs->gstream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        int rc = COCR_OK;
+        if (ok) {
+            st = bs->gstream;
+            rc = run_layers();
+            st = caller;
+            ok = cudaStreamEndCapture(bs->gstream, &graph) == cudaSuccess && rc == COCR_OK && graph;
+        }
+        if (ok) ok = cudaGraphInstantiate(&lg->exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        lg->launches = h->launches - launches0;
+        h->launches = launches0;                             // nothing has run yet
+        if (!ok) {
+            cudaGetLastError();
+            h->err.clear();
+            lg->state = -1;
+            lg->exec = nullptr;
+            return run_layers();
+        }
+        lg->state = 2;
+    }
+    COCR_CUDA(h, cudaEventRecord(bs->g_in, st));
+    COCR_CUDA(h, cudaStreamWaitEvent(bs->gstream, bs->g_in, 0));
+    COCR_CUDA(h, cudaGraphLaunch(lg->exec, bs->gstream));
+    h->launches += lg->launches;
+    COCR_CUDA(h, cudaEventRecord(bs->g_out, bs->gstream));
+    COCR_CUDA(h, cudaStreamWaitEvent(st, bs->g_out, 0));
     return COCR_OK;
 }
 
