@@ -184,8 +184,9 @@ def run_ours(args):
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'INFO'):
-            os.environ['NCCL_DEBUG'] = 'WARN'       # NCCL prints its banner on stdout; this script prints ONE JSON line
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION', 'INFO'):
+            os.environ['NCCL_DEBUG'] = 'WARN'       # NCCL prints its banner on stdout (also when a config file asks for it);
+                                                    # this script prints ONE JSON line
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     assert torch.cuda.is_available(), 'bench.py (our arm) needs a CUDA device; there is no CPU fallback'
     dev = torch.device('cuda', local_rank)
