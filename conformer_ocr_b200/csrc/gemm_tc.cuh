@@ -88,10 +88,11 @@ constexpr int GEMM_TRACE_EVENTS = 1024;    // per role: 0 epilogue warp 0, 1 MMA
 
 // epilogue warps: the thread-per-row bf16 epilogues are chains of dependent latencies (TMEM load -> math -> staging ->
 // proxy fence -> TMA store), so they run 16 warps (4 per scheduler, <= 112 registers) to overlap them.  The residual
-// epilogue keeps 8 warps: with 16 (and 96 registers) it spilled and measured slower - it is bound by the number of
-// 32-byte sector requests its fragment-layout loads/stores generate, not by latency.
+// epilogue also runs 16 warps since it handles ONE row per lane quad (96 registers, no spills; the two-row form needed
+// 168 and spilled at 16 warps): it is bound by the latency of its own x loads / stores, so rows in flight per SM are what
+// counts (attention-out / pw2: 37 -> 34 us).
 __host__ __device__ constexpr bool gemm_row_pieces(int epi) { return epi == 0 || epi == 1 || epi == 4 || epi == 6; }
-__host__ __device__ constexpr int gemm_ne(int epi) { return gemm_row_pieces(epi) ? 16 : 8; }
+__host__ __device__ constexpr int gemm_ne(int epi) { return (gemm_row_pieces(epi) || epi == 5) ? 16 : 8; }
 __host__ __device__ constexpr int gemm_threads(int epi) { return 64 + 32 * gemm_ne(epi); }
 __host__ __device__ constexpr int gemm_nstg(int epi) { return gemm_row_pieces(epi) ? 2 : 4; }     // staging tiles per warp
 constexpr int GEMM_BM = 128;
@@ -220,7 +221,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(bfull, 1);
         mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
-        constexpr uint32_t drainers = (EPI == EPI_RESID) ? GEMM_NE / 2 : GEMM_NE;   // warps draining one accumulator stage
+        constexpr uint32_t drainers = GEMM_NE;                                       // warps draining one accumulator stage
         mbar_init(&tempty[0], drainers); mbar_init(&tempty[1], drainers);
         mbar_fence_init();
     }
@@ -348,128 +349,115 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             };
 
             if constexpr (EPI == EPI_RESID) {
-                // ---- fp32 residual update + LayerNorm(s), fragment layout, alternate tiles per warp ----
-                if ((j & 1) != half) continue;
+                // ---- fp32 residual update + LayerNorm(s), fragment layout: 16 warps, 8 rows of the tile each, ONE row per lane
+                // quad (the 16x256b load returns rows r and r+8 together; a warp keeps the one it owns).  The epilogue is
+                // bound by the latency of its own x loads and stores, so what counts is how many rows are in flight per SM.
                 GEMM_TRACE(0, 400);
                 constexpr int NG = GEMM_RESID_NG;
                 const int r_in = lane >> 2, qd = lane & 3;
+                const int hh = half >> 1, pass = half & 1;            // 16-row half of the lane quarter, row r / r+8 of the load
                 const float inv_n = 1.0f / (float)(8 * NG);
-#pragma unroll 1
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int64_t rowA = (int64_t)grow0 + hh * 16 + r_in, rowB = rowA + 8;
-                    const bool okA = rowA < p.M, okB = rowB < p.M;
-                    float2 va[NG], vb[NG];
-                    float *xa = p.x + rowA * (8 * NG) + 4 * qd, *xb = p.x + rowB * (8 * NG) + 4 * qd;
-                    if (!p.init) {
-#pragma unroll
-                        for (int gp = 0; gp < NG / 2; ++gp) {
-                            const float4 ta = okA ? *reinterpret_cast<const float4 *>(xa + 16 * gp) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            const float4 tb = okB ? *reinterpret_cast<const float4 *>(xb + 16 * gp) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            va[2 * gp] = make_float2(ta.x, ta.y); va[2 * gp + 1] = make_float2(ta.z, ta.w);
-                            vb[2 * gp] = make_float2(tb.x, tb.y); vb[2 * gp + 1] = make_float2(tb.z, tb.w);
-                        }
-                    }
-                    GEMM_TRACE(0, 410 + hh);
-                    if (hh == 0) {
-                        mbar_wait(&tfull[acc], acc_phase);
-                        tc_fence_after();
-                    }
-                    GEMM_TRACE(0, 420 + hh);
-                    // accumulator in three column blocks (64 + 64 + 16) to bound the live registers
-                    const uint32_t taddr = t_acc + ((uint32_t)(q * 32 + hh * 16) << 16);
-                    auto combine = [&](int g, float a0, float a1, float c0, float c1) {
-                        const float2 b2 = *reinterpret_cast<const float2 *>(sb + 8 * g + 2 * qd);
-                        a0 += b2.x; a1 += b2.y; c0 += b2.x; c1 += b2.y;
-                        if (p.init) {
-                            va[g] = make_float2(a0, a1);
-                            vb[g] = make_float2(c0, c1);
-                        } else {
-                            va[g].x = fmaf(p.alpha, a0, va[g].x); va[g].y = fmaf(p.alpha, a1, va[g].y);
-                            vb[g].x = fmaf(p.alpha, c0, vb[g].x); vb[g].y = fmaf(p.alpha, c1, vb[g].y);
-                        }
-                    };
-#pragma unroll
-                    for (int blk = 0; blk < NG / 2; ++blk) {              // 16 columns (two groups) per load keeps the live set small
-                        uint32_t t1[8];
-                        tmem_ld_16x256b_x2(taddr + 16u * blk, t1);
-                        tmem_ld_wait_dep(t1);
-                        if (blk == NG / 2 - 1 && hh == 1) release_acc();
-#pragma unroll
-                        for (int gg = 0; gg < 2; ++gg)
-                            combine(2 * blk + gg, __uint_as_float(t1[4 * gg]), __uint_as_float(t1[4 * gg + 1]), __uint_as_float(t1[4 * gg + 2]),
-                                    __uint_as_float(t1[4 * gg + 3]));
-                    }
-                    GEMM_TRACE(0, 430 + hh);
-                    // LayerNorm statistics of rows A and B (two passes in registers; a row lives in one quad of lanes)
-                    auto stats = [&](float &meanA, float &rstdA, float &meanB, float &rstdB) {
-                        float sA = 0.f, sB = 0.f;
-#pragma unroll
-                        for (int g = 0; g < NG; ++g) { sA += va[g].x + va[g].y; sB += vb[g].x + vb[g].y; }
-                        sA += __shfl_xor_sync(0xffffffffu, sA, 1); sB += __shfl_xor_sync(0xffffffffu, sB, 1);
-                        sA += __shfl_xor_sync(0xffffffffu, sA, 2); sB += __shfl_xor_sync(0xffffffffu, sB, 2);
-                        meanA = sA * inv_n; meanB = sB * inv_n;
-                        float qA = 0.f, qB = 0.f;
-#pragma unroll
-                        for (int g = 0; g < NG; ++g) {
-                            float d0 = va[g].x - meanA, d1 = va[g].y - meanA;
-                            qA = fmaf(d0, d0, qA); qA = fmaf(d1, d1, qA);
-                            d0 = vb[g].x - meanB; d1 = vb[g].y - meanB;
-                            qB = fmaf(d0, d0, qB); qB = fmaf(d1, d1, qB);
-                        }
-                        qA += __shfl_xor_sync(0xffffffffu, qA, 1); qB += __shfl_xor_sync(0xffffffffu, qB, 1);
-                        qA += __shfl_xor_sync(0xffffffffu, qA, 2); qB += __shfl_xor_sync(0xffffffffu, qB, 2);
-                        rstdA = rsqrtf(qA * inv_n + 1e-5f); rstdB = rsqrtf(qB * inv_n + 1e-5f);
-                    };
-                    if (p.gf) {   // block-final LayerNorm replaces the residual stream (encoder.py:99)
-                        float mA, rA, mB, rB;
-                        stats(mA, rA, mB, rB);
-#pragma unroll
-                        for (int g = 0; g < NG; ++g) {
-                            const float2 gg = *reinterpret_cast<const float2 *>(sln + 8 * g + 2 * qd);
-                            const float2 bb = *reinterpret_cast<const float2 *>(sln + 256 + 8 * g + 2 * qd);
-                            va[g].x = (va[g].x - mA) * rA * gg.x + bb.x; va[g].y = (va[g].y - mA) * rA * gg.y + bb.y;
-                            vb[g].x = (vb[g].x - mB) * rB * gg.x + bb.x; vb[g].y = (vb[g].y - mB) * rB * gg.y + bb.y;
-                        }
-                    }
-                    // x_new: 8 rows x 64 contiguous bytes per store instruction (private layout, see GemmArgs::x)
+                const int64_t row = (int64_t)grow0 + hh * 16 + pass * 8 + r_in;
+                const bool ok = row < p.M;
+                float2 v[NG];
+                float *xr = p.x + row * (8 * NG) + 4 * qd;
+                if (!p.init) {
 #pragma unroll
                     for (int gp = 0; gp < NG / 2; ++gp) {
-                        if (okA) *reinterpret_cast<float4 *>(xa + 16 * gp) = make_float4(va[2 * gp].x, va[2 * gp].y, va[2 * gp + 1].x, va[2 * gp + 1].y);
-                        if (okB) *reinterpret_cast<float4 *>(xb + 16 * gp) = make_float4(vb[2 * gp].x, vb[2 * gp].y, vb[2 * gp + 1].x, vb[2 * gp + 1].y);
+                        const float4 ta = ok ? *reinterpret_cast<const float4 *>(xr + 16 * gp) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[2 * gp] = make_float2(ta.x, ta.y); v[2 * gp + 1] = make_float2(ta.z, ta.w);
                     }
-                    // xn = bf16(LayerNorm_next(x_new)) (or bf16(x_new))
-                    float mA = 0.f, rA = 1.f, mB = 0.f, rB = 1.f;
-                    if (p.g1) stats(mA, rA, mB, rB);
-                    uint32_t pa[NG], pb[NG];
+                    if (j + 1 < my_count) {
+                        // this warp's rows of the NEXT tile into L2 (8 rows x 576 B = 36 lines of 128 B)
+                        int mt2, nt2;
+                        tile_mn(j + 1, mt2, nt2);
+                        const int64_t r2 = (int64_t)mt2 * GEMM_BM + q * 32 + hh * 16 + pass * 8;
+                        const char *nb = reinterpret_cast<const char *>(p.x + r2 * (8 * NG));
+                        const int64_t lim = ((int64_t)p.M - r2) * (8 * NG) * 4;
+                        for (int o = lane * 128; o < 8 * 8 * NG * 4 && o < lim; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + o));
+                    }
+                }
+                GEMM_TRACE(0, 410);
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_after();
+                GEMM_TRACE(0, 420);
+                const uint32_t taddr = t_acc + ((uint32_t)(q * 32 + hh * 16) << 16);
+#pragma unroll
+                for (int blk = 0; blk < NG / 2; ++blk) {              // 16 columns (two groups) per load keeps the live set small
+                    uint32_t t1[8];
+                    tmem_ld_16x256b_x2(taddr + 16u * blk, t1);
+                    tmem_ld_wait_dep(t1);
+                    if (blk == NG / 2 - 1) release_acc();
+#pragma unroll
+                    for (int gg = 0; gg < 2; ++gg) {
+                        const int g = 2 * blk + gg;
+                        const float2 b2 = *reinterpret_cast<const float2 *>(sb + 8 * g + 2 * qd);
+                        const float a0 = __uint_as_float(pass ? t1[4 * gg + 2] : t1[4 * gg]) + b2.x;
+                        const float a1 = __uint_as_float(pass ? t1[4 * gg + 3] : t1[4 * gg + 1]) + b2.y;
+                        if (p.init) v[g] = make_float2(a0, a1);
+                        else { v[g].x = fmaf(p.alpha, a0, v[g].x); v[g].y = fmaf(p.alpha, a1, v[g].y); }
+                    }
+                }
+                GEMM_TRACE(0, 430);
+                // LayerNorm statistics (two passes in registers; the row lives in one quad of lanes)
+                auto stats = [&](float &mean, float &rstd) {
+                    float sA = 0.f;
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) sA += v[g].x + v[g].y;
+                    sA += __shfl_xor_sync(0xffffffffu, sA, 1);
+                    sA += __shfl_xor_sync(0xffffffffu, sA, 2);
+                    mean = sA * inv_n;
+                    float qA = 0.f;
 #pragma unroll
                     for (int g = 0; g < NG; ++g) {
-                        float a0 = va[g].x, a1 = va[g].y, c0 = vb[g].x, c1 = vb[g].y;
-                        if (p.g1) {
-                            const float2 gg = *reinterpret_cast<const float2 *>(sln + 512 + 8 * g + 2 * qd);
-                            const float2 bb = *reinterpret_cast<const float2 *>(sln + 768 + 8 * g + 2 * qd);
-                            a0 = (a0 - mA) * rA * gg.x + bb.x; a1 = (a1 - mA) * rA * gg.y + bb.y;
-                            c0 = (c0 - mB) * rB * gg.x + bb.x; c1 = (c1 - mB) * rB * gg.y + bb.y;
-                        }
-                        pa[g] = pack_bf16x2(a0, a1);
-                        pb[g] = pack_bf16x2(c0, c1);
+                        const float d0 = v[g].x - mean, d1 = v[g].y - mean;
+                        qA = fmaf(d0, d0, qA); qA = fmaf(d1, d1, qA);
                     }
-                    // neighbouring lanes swap one packed pair so that every lane stores 8 bytes and a quad writes the
-                    // 32 contiguous bytes of two column groups
-                    __nv_bfloat16 *na = reinterpret_cast<__nv_bfloat16 *>(p.out) + rowA * p.ldc;
-                    __nv_bfloat16 *nb = reinterpret_cast<__nv_bfloat16 *>(p.out) + rowB * p.ldc;
-                    const bool odd = qd & 1;
+                    qA += __shfl_xor_sync(0xffffffffu, qA, 1);
+                    qA += __shfl_xor_sync(0xffffffffu, qA, 2);
+                    rstd = rsqrtf(qA * inv_n + 1e-5f);
+                };
+                if (p.gf) {   // block-final LayerNorm replaces the residual stream (encoder.py:99)
+                    float m, r;
+                    stats(m, r);
 #pragma unroll
-                    for (int g = 0; g < NG; g += 2) {
-                        const uint32_t sendA = odd ? pa[g] : pa[g + 1], sendB = odd ? pb[g] : pb[g + 1];
-                        const uint32_t recvA = __shfl_xor_sync(0xffffffffu, sendA, 1), recvB = __shfl_xor_sync(0xffffffffu, sendB, 1);
-                        const int col = odd ? 8 * (g + 1) + 2 * (qd - 1) : 8 * g + 2 * qd;
-                        const uint2 oA = odd ? make_uint2(recvA, pa[g + 1]) : make_uint2(pa[g], recvA);
-                        const uint2 oB = odd ? make_uint2(recvB, pb[g + 1]) : make_uint2(pb[g], recvB);
-                        if (okA) *reinterpret_cast<uint2 *>(na + col) = oA;
-                        if (okB) *reinterpret_cast<uint2 *>(nb + col) = oB;
+                    for (int g = 0; g < NG; ++g) {
+                        const float2 gg = *reinterpret_cast<const float2 *>(sln + 8 * g + 2 * qd);
+                        const float2 bb = *reinterpret_cast<const float2 *>(sln + 256 + 8 * g + 2 * qd);
+                        v[g].x = (v[g].x - m) * r * gg.x + bb.x; v[g].y = (v[g].y - m) * r * gg.y + bb.y;
                     }
-                    GEMM_TRACE(0, 440 + hh);
                 }
+                // x_new: 8 rows x 64 contiguous bytes per store instruction (private layout, see GemmArgs::x)
+#pragma unroll
+                for (int gp = 0; gp < NG / 2; ++gp)
+                    if (ok) *reinterpret_cast<float4 *>(xr + 16 * gp) = make_float4(v[2 * gp].x, v[2 * gp].y, v[2 * gp + 1].x, v[2 * gp + 1].y);
+                // xn = bf16(LayerNorm_next(x_new)) (or bf16(x_new))
+                float m = 0.f, r = 1.f;
+                if (p.g1) stats(m, r);
+                uint32_t pa[NG];
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    float a0 = v[g].x, a1 = v[g].y;
+                    if (p.g1) {
+                        const float2 gg = *reinterpret_cast<const float2 *>(sln + 512 + 8 * g + 2 * qd);
+                        const float2 bb = *reinterpret_cast<const float2 *>(sln + 768 + 8 * g + 2 * qd);
+                        a0 = (a0 - m) * r * gg.x + bb.x; a1 = (a1 - m) * r * gg.y + bb.y;
+                    }
+                    pa[g] = pack_bf16x2(a0, a1);
+                }
+                // neighbouring lanes swap one packed pair so that every lane stores 8 bytes and a quad writes the
+                // 32 contiguous bytes of two column groups
+                __nv_bfloat16 *na = reinterpret_cast<__nv_bfloat16 *>(p.out) + row * p.ldc;
+                const bool odd = qd & 1;
+#pragma unroll
+                for (int g = 0; g < NG; g += 2) {
+                    const uint32_t send = odd ? pa[g] : pa[g + 1];
+                    const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                    const int col = odd ? 8 * (g + 1) + 2 * (qd - 1) : 8 * g + 2 * qd;
+                    const uint2 o = odd ? make_uint2(recv, pa[g + 1]) : make_uint2(pa[g], recv);
+                    if (ok) *reinterpret_cast<uint2 *>(na + col) = o;
+                }
+                GEMM_TRACE(0, 440);
             } else if constexpr (kRowPieces) {
                 // ---- bf16 output through per-warp staging tiles and TMA stores; TMEM loads run one piece ahead ----
                 const int my_np = (npieces - half + NSH - 1) / NSH;        // pieces half, half + 2, ...
