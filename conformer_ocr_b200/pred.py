@@ -155,13 +155,21 @@ class PytorchRecognitionModel(EngineOwner):
         o = o.transpose(1, 2).cpu().float().numpy()                   # pred.py:138
         return [self.ctc_decoder(seq[:, :int(seq_len)]) for seq, seq_len in zip(o, olens)]
 
+    def _strings(self, line: torch.Tensor, lens) -> List[str]:
+        if self.ctc_decoder is greedy_decoder and isinstance(self.codec, LabelCodec):
+            # collapsed labels stay a (B, T) block: one table look-up for the batch instead of a tuple per label
+            x = self._as_bwh(line)
+            res = self.engine_for(x.device).forward_decode(x, lens)
+            return self.codec.decode_strings(res['labels'].cpu().numpy(), res['counts'].cpu().numpy())
+        return [''.join(x[0] for x in self.codec.decode(locs)) for locs in self._decode(line, lens)]
+
     def predict(self, line: torch.Tensor, lens: Optional[torch.Tensor] = None) -> List[str]:
         """pred.py:124-145 (returns the decoded strings, as the reference's code does)."""
-        return [''.join(x[0] for x in self.codec.decode(locs)) for locs in self._decode(line, lens)]
+        return self._strings(line, lens)
 
     def predict_string(self, line: torch.Tensor, lens: Optional[torch.Tensor] = None) -> List[str]:
         """pred.py:148-163"""
-        return [''.join(x[0] for x in self.codec.decode(locs)) for locs in self._decode(line, lens)]
+        return self._strings(line, lens)
 
     def predict_labels(self, line: torch.Tensor, lens: Optional[torch.Tensor] = None) -> List[List[Tuple[int, int, int, float]]]:
         """pred.py:165-178: list of (class, start, end, max) per line."""

@@ -107,3 +107,32 @@ def test_product_synthetic_generator_equals_test_generator():
     # 4.95 GF/line at W=1024,C=200 ; 8.11 at 1536 ; 11.71 at 2048 ; 33.57 at 4096/10k
     for (W, C), want in {(1024, 200): 4.95, (1536, 200): 8.11, (2048, 200): 11.71, (4096, 10000): 33.57}.items():
         assert abs(S.flops_per_line(W, C, O.DEFAULT_HPARAMS) / 1e9 - want) < 0.01
+
+
+def test_label_codec_batched_strings_match_tuple_decode():
+    """the vectorised label -> string path gives the strings of `codec.decode` + join (pred.py:163)."""
+    import time
+    import numpy as np
+    from conformer_ocr_b200.codec import LabelCodec
+    rng = np.random.default_rng(7)
+    charset = [chr(c) for c in list(range(0x61, 0x7b)) + [0x20, 0xe9, 0x3b1, 0x4e2d, 0x1f600]]      # ASCII, Latin-1, Greek, CJK, astral
+    codec = LabelCodec(charset)
+    B, T = 64, 200
+    labels = rng.integers(-1, len(charset) + 4, size=(B, T)).astype(np.int32)                       # includes unknown labels
+    counts = rng.integers(0, T + 1, size=B).astype(np.int32)
+    counts[0], counts[1] = 0, T                                                                     # empty and full rows
+    want = [''.join(g for g, *_ in codec.decode([(int(l), 0, 0, 1.0) for l in row[:n]])) for row, n in zip(labels, counts)]
+    assert codec.decode_strings(labels, counts) == want
+    # multi-code-point graphemes fall back to the per-label join
+    c2 = LabelCodec({'ab': [1], 'c': [2]})
+    assert c2.decode_strings(np.array([[1, 2, 1, 9]]), np.array([4])) == ['abcab']
+    with pytest.raises(ValueError):
+        codec.decode_strings(labels, counts[:-1])
+    # and it is the faster of the two (what the row is for); generous factor so the test is not a benchmark
+    big_l = rng.integers(1, len(charset) + 1, size=(2048, 384)).astype(np.int32)
+    big_n = np.full(2048, 300, np.int32)
+    t0 = time.perf_counter(); s_fast = codec.decode_strings(big_l, big_n); t1 = time.perf_counter()
+    s_slow = [''.join(g for g, *_ in codec.decode(list(zip(r[:n].tolist(), [0] * n, [0] * n, [1.0] * n)))) for r, n in zip(big_l[:256], big_n[:256])]
+    t2 = time.perf_counter()
+    assert s_fast[:256] == s_slow
+    assert (t1 - t0) / 2048 < (t2 - t1) / 256
