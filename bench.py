@@ -287,6 +287,32 @@ def run_ours(args):
                    api='Engine.recognize_host_begin/_end -> cocr_recognize_host_begin/_end (pinned fp32 (N,1,H,W) in, decoded '
                        'records out; two slots, H2D of step i+1 overlaps the forward pass of step i)')
         assert int(r['counts'].sum()) >= 0
+        # the same loop on raw 8-bit pixels (an extension of the reference interface, reported beside
+        # the like-for-like fp32 number, never instead of it): a quarter of the bytes cross PCIe
+        if args.precision == 'bf16':
+            u_hosts = [torch.empty((B, 1, hp['height'], W), dtype=torch.uint8).pin_memory() for _ in range(2)]
+            for uh in u_hosts:
+                uh.copy_((x_dev * 255).round().clamp_(0, 255).to(torch.uint8))
+            for sl in (0, 1):
+                eng.recognize_host_begin(sl, u_hosts[sl], widths)
+            eng.recognize_host_end(0); eng.recognize_host_end(1)
+            fence()
+            t0 = time.perf_counter()
+            pending = None
+            for i in range(args.steps):
+                slot = i & 1
+                eng.recognize_host_begin(slot, u_hosts[slot], widths)
+                if pending is not None:
+                    eng.recognize_host_end(pending)
+                pending = slot
+            eng.recognize_host_end(pending)
+            torch.cuda.synchronize(dev)
+            dtu = time.perf_counter() - t0
+            tt = torch.tensor([dtu], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e['uint8_input'] = dict(value=world * B * args.steps / float(tt.item()), unit='lines/s',
+                                      h2d_bytes_per_step=in_bytes // 4 + 4 * B, d2h_bytes_per_step=d2h)
 
     # ---- per-kernel CUDA-event timing for the roofline of the dominant kernel (rank 0) ----
     roofline = None

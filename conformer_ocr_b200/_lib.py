@@ -47,6 +47,8 @@ SIGNATURES = {
     'cocr_forward_decode': (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
     'cocr_recognize_host': (C.c_int, [_P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
     'cocr_recognize_host_begin': (C.c_int, [_P, _I32, _P, _P, _I32, _I32, _P]),
+    'cocr_forward_decode_u8': (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
+    'cocr_recognize_host_u8_begin': (C.c_int, [_P, _I32, _P, _P, _I32, _I32, _P]),
     'cocr_recognize_host_end': (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _P]),
     'cocr_workspace_bytes': (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_size_t)]),
     'cocr_launch_count': (_I64, [_P]),

@@ -460,8 +460,25 @@ int cocr_forward_decode(cocr_handle *h, const float *img, int64_t sb, int64_t sw
                                 (int32_t *)(h->ws.base + p.off_best_idx), labels, starts, ends, conf, counts);
 }
 
-int cocr_recognize_host_begin(cocr_handle *h, int32_t slot, const float *img_host, const int32_t *widths_host, int32_t B, int32_t W,
-                              void *stream) {
+namespace {
+struct U8Scope {                      // marks the handle's current image pointer as uint8 for one call
+    cocr_handle *h;
+    explicit U8Scope(cocr_handle *h_) : h(h_) { if (h) h->img_u8 = true; }
+    ~U8Scope() { if (h) h->img_u8 = false; }
+};
+}  // namespace
+
+int cocr_forward_decode_u8(cocr_handle *h, const uint8_t *img, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths,
+                           int32_t B, int32_t W, void *stream, int32_t *labels, int32_t *starts, int32_t *ends, float *conf,
+                           int32_t *counts, int32_t *out_lens) {
+    if (h && h->hp.precision != COCR_BF16) return set_error(h, COCR_ERR_UNSUPPORTED, "uint8 input is implemented on the bf16 path only");
+    U8Scope scope(h);
+    return cocr_forward_decode(h, reinterpret_cast<const float *>(img), sb, sw, sh, widths, B, W, stream, labels, starts, ends, conf,
+                               counts, out_lens);
+}
+
+static int host_begin(cocr_handle *h, int32_t slot, const void *img_host, size_t pix_bytes, const int32_t *widths_host, int32_t B, int32_t W,
+                      void *stream) {
     COCR_TRY(check_call(h, img_host, B, W));
     if (slot < 0 || slot > 1) return set_error(h, COCR_ERR_BAD_ARG, "cocr_recognize_host_begin: slot must be 0 or 1");
     cocr_handle::HostSlot &sl = h->slots[slot];
@@ -474,7 +491,7 @@ int cocr_recognize_host_begin(cocr_handle *h, int32_t slot, const float *img_hos
         COCR_CUDA(h, cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
         COCR_CUDA(h, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
     }
-    const size_t img_bytes = sizeof(float) * (size_t)B * H * W;
+    const size_t img_bytes = pix_bytes * (size_t)B * H * W;
     if (img_bytes > sl.img_bytes) {
         if (sl.img) { COCR_CUDA(h, cudaDeviceSynchronize()); COCR_CUDA(h, cudaFree(sl.img)); sl.img = nullptr; sl.img_bytes = 0; }
         void *p = nullptr;
@@ -515,11 +532,26 @@ int cocr_recognize_host_begin(cocr_handle *h, int32_t slot, const float *img_hos
     int32_t *d_lab = (int32_t *)sl.res, *d_st = d_lab + bt, *d_en = d_st + bt;
     float *d_cf = (float *)(d_en + bt);
     int32_t *d_cnt = (int32_t *)(d_cf + bt), *d_len = d_cnt + B;
-    COCR_TRY(cocr_forward_decode(h, sl.img, (int64_t)H * W, 1, W, wd, B, W, stream, d_lab, d_st, d_en, d_cf, d_cnt, d_len));
+    if (pix_bytes == 1)
+        COCR_TRY(cocr_forward_decode_u8(h, reinterpret_cast<const uint8_t *>(sl.img), (int64_t)H * W, 1, W, wd, B, W, stream, d_lab, d_st, d_en,
+                                        d_cf, d_cnt, d_len));
+    else
+        COCR_TRY(cocr_forward_decode(h, sl.img, (int64_t)H * W, 1, W, wd, B, W, stream, d_lab, d_st, d_en, d_cf, d_cnt, d_len));
     COCR_CUDA(h, cudaMemcpyAsync(sl.res_host, sl.res, res_bytes, cudaMemcpyDeviceToHost, st));
     COCR_CUDA(h, cudaEventRecord(sl.done, st));
     sl.B = B; sl.T = T; sl.busy = true;
     return COCR_OK;
+}
+
+int cocr_recognize_host_begin(cocr_handle *h, int32_t slot, const float *img_host, const int32_t *widths_host, int32_t B, int32_t W,
+                              void *stream) {
+    return host_begin(h, slot, img_host, sizeof(float), widths_host, B, W, stream);
+}
+
+int cocr_recognize_host_u8_begin(cocr_handle *h, int32_t slot, const uint8_t *img_host, const int32_t *widths_host, int32_t B, int32_t W,
+                                 void *stream) {
+    if (h && h->hp.precision != COCR_BF16) return set_error(h, COCR_ERR_UNSUPPORTED, "uint8 input is implemented on the bf16 path only");
+    return host_begin(h, slot, img_host, 1, widths_host, B, W, stream);
 }
 
 int cocr_recognize_host_end(cocr_handle *h, int32_t slot, int32_t *labels, int32_t *starts, int32_t *ends, float *conf, int32_t *counts,

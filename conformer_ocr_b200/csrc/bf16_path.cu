@@ -898,6 +898,8 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
     // tensor-core GEMM whose (M*F, 32) output IS the (M, F*32) feature matrix of the 768 -> 144 projection
     bf16 *a2hl = (bf16 *)a2;                                       // (M*F, 2 cc) bf16 = the fp32 a2 region of the plan
     int rc_fe = getenv("COCR_FRONTEND_V1") ? COCR_ERR_UNSUPPORTED : launch_frontend_convs2(h, img, sb, sw, sh, B, W, a2hl, st);
+    if (rc_fe == COCR_ERR_UNSUPPORTED && h->img_u8)
+        return set_error(h, COCR_ERR_UNSUPPORTED, "uint8 input is implemented by the fused front-end only (subsampling_conv_channels = 32)");
     if (rc_fe == COCR_OK) {
         rc_fe = launch_gemm_tc(h, EPI_BF16, a2hl, 2 * dm.cc, h->bf->w_fe_pw2, 2 * dm.cc, h->sub_bpw, feat, dm.cc, nullptr, M * dm.F, dm.cc,
                                2 * dm.cc, st, 0, nullptr, "gemm_frontend_pw", nullptr, /*relu=*/1);

@@ -99,6 +99,7 @@ struct cocr_handle {
 
     std::vector<float> fe_weights;   // conv.0 / conv.2 weights + biases in kernel-parameter order (mem_kernels.cu: FrontendWeights)
     int64_t launches = 0;
+    bool img_u8 = false;             // set for the duration of a *_u8 entry point: the image pointer holds uint8 pixels
     cocr::Bf16State *bf = nullptr;
 
     // optional per-launch event timing (cocr_set_profiling)

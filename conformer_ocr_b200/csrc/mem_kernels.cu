@@ -434,8 +434,11 @@ __device__ __forceinline__ void dw_group(const FrontendWeights &fw, const uint8_
     }
 }
 
+// PixT = float: the reference's input (pixels already scaled to [0, 1]); PixT = uint8_t: raw 8-bit pixels, scaled here by the
+// correctly rounded p / 255 of torchvision's ToTensor, so both inputs give bit-identical results.
+template <typename PixT>
 __global__ void __launch_bounds__(FE2_THREADS, 2)
-k_frontend_convs2(const float *__restrict__ img, int64_t sb, int64_t sw, int64_t sh, const __grid_constant__ FrontendWeights fw,
+k_frontend_convs2(const PixT *__restrict__ img, int64_t sb, int64_t sw, int64_t sh, const __grid_constant__ FrontendWeights fw,
                   bf16 *__restrict__ a2, int W, int H, int T2, int T, int F2, int F) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
     constexpr int NW = 4 * FE2_TT + 3;              // input columns (time) needed
@@ -455,7 +458,10 @@ k_frontend_convs2(const float *__restrict__ img, int64_t sb, int64_t sw, int64_t
         else { wl = e / HP; y = e - wl * HP; }                  // (B,W,H) layout: height is contiguous
         const int w = w0 + wl, yy = y - 1;
         float v = 0.0f;
-        if (w >= 0 && w < W && yy >= 0 && yy < H) v = img[b * sb + w * sw + yy * sh];
+        if (w >= 0 && w < W && yy >= 0 && yy < H) {
+            if constexpr (sizeof(PixT) == 1) v = __fdiv_rn((float)img[b * sb + w * sw + yy * sh], 255.0f);
+            else v = img[b * sb + w * sw + yy * sh];
+        }
         patch[wl * HP + y] = v;
     }
     __syncthreads();
@@ -524,6 +530,7 @@ k_frontend_convs2(const float *__restrict__ img, int64_t sb, int64_t sw, int64_t
 // conv1 + depthwise conv -> a2 (B*T*F, 64) bf16 [hi | lo]; the caller runs the 1x1 conv as a K = 64 GEMM.  COCR_ERR_UNSUPPORTED when the
 // geometry is not covered.
 int launch_frontend_convs2(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, int B, int W, bf16 *a2, cudaStream_t st) {
+    const bool u8 = h->img_u8;                      // `img` then points at uint8 pixels
     const Dims &dm = h->dm;
     if (dm.cc != 32 || ((FE2_TT * dm.F) & 31) != 0 || h->fe_weights.size() != sizeof(FrontendWeights) / 4) return COCR_ERR_UNSUPPORTED;
     const int T2 = out_len1(W), T = out_len1(T2);
@@ -532,15 +539,17 @@ int launch_frontend_convs2(cocr_handle *h, const float *img, int64_t sb, int64_t
     if (smem > 200 * 1024) return COCR_ERR_UNSUPPORTED;
     static size_t attr = 0;
     if (smem > attr) {
-        COCR_CUDA(h, cudaFuncSetAttribute(k_frontend_convs2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        COCR_CUDA(h, cudaFuncSetAttribute(k_frontend_convs2<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        COCR_CUDA(h, cudaFuncSetAttribute(k_frontend_convs2<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
     FrontendWeights fw;
     memcpy(&fw, h->fe_weights.data(), sizeof(fw));
     dim3 grid((T + FE2_TT - 1) / FE2_TT, B);
     const double n1 = (double)B * T2 * dm.F2 * 32, n2 = (double)B * T * dm.F * 32;
-    ProfScope ps(h, "frontend_convs", st, 18.0 * n1 + 18.0 * n2, 4.0 * B * (double)W * dm.H + 2.0 * n2);
-    k_frontend_convs2<<<grid, FE2_THREADS, smem, st>>>(img, sb, sw, sh, fw, a2, W, dm.H, T2, T, dm.F2, dm.F);
+    ProfScope ps(h, "frontend_convs", st, 18.0 * n1 + 18.0 * n2, (u8 ? 1.0 : 4.0) * B * (double)W * dm.H + 2.0 * n2);
+    if (u8) k_frontend_convs2<uint8_t><<<grid, FE2_THREADS, smem, st>>>(reinterpret_cast<const uint8_t *>(img), sb, sw, sh, fw, a2, W, dm.H, T2, T, dm.F2, dm.F);
+    else k_frontend_convs2<float><<<grid, FE2_THREADS, smem, st>>>(img, sb, sw, sh, fw, a2, W, dm.H, T2, T, dm.F2, dm.F);
     COCR_LAUNCHED(h);
     return COCR_OK;
 }

@@ -95,7 +95,7 @@ class Engine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _prep(self, inputs: torch.Tensor, lens) -> Tuple[torch.Tensor, Optional[torch.Tensor], int, int]:
+    def _prep(self, inputs: torch.Tensor, lens, allow_u8: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor], int, int]:
         """inputs: (B, W, H) view (any strides) on this engine's device."""
         if inputs.dim() != 3:
             raise ValueError(f'expected (batch, width, height) input, got shape {tuple(inputs.shape)}')
@@ -103,7 +103,11 @@ class Engine:
             if inputs.device.type != 'cuda':
                 raise RuntimeError('input tensor is on the CPU; move it to the GPU (no CPU fallback)')
             raise RuntimeError(f'input on {inputs.device}, engine on {self.device}')
-        if inputs.dtype != torch.float32:
+        if inputs.dtype == torch.uint8 and not (allow_u8 and self.precision == 'bf16'):
+            # raw pixels -> ToTensor scaling.  A tensor divisor: dividing by a Python scalar multiplies by the rounded
+            # reciprocal on CUDA and differs from p / 255 in the last bit for some pixel values
+            inputs = inputs.float() / torch.full((), 255.0, device=inputs.device)
+        elif inputs.dtype not in (torch.float32, torch.uint8):   # uint8 kept: scaled by 1/255 inside the first kernel
             inputs = inputs.float()
         B, W, H = inputs.shape
         if H != self.height:
@@ -143,14 +147,15 @@ class Engine:
 
     def forward_decode(self, inputs: torch.Tensor, lens=None) -> Dict[str, torch.Tensor]:
         """Fused encoder -> projection -> argmax -> CTC collapse; results stay on the device."""
-        x, wd, B, W = self._prep(inputs, lens)
+        x, wd, B, W = self._prep(inputs, lens, allow_u8=True)
         T = int(self._lib.cocr_out_frames(W))
         i32 = dict(dtype=torch.int32, device=self.device)
         res = dict(labels=torch.empty((B, T), **i32), starts=torch.empty((B, T), **i32), ends=torch.empty((B, T), **i32),
                    conf=torch.empty((B, T), dtype=torch.float32, device=self.device),
                    counts=torch.empty((B,), **i32), out_lens=torch.empty((B,), **i32))
+        fn = self._lib.cocr_forward_decode_u8 if x.dtype == torch.uint8 else self._lib.cocr_forward_decode
         with torch.cuda.device(self.device):
-            self._check(self._lib.cocr_forward_decode(
+            self._check(fn(
                 self._h, self._ptr(x), x.stride(0), x.stride(1), x.stride(2), self._ptr(wd), B, W, self._stream(),
                 self._ptr(res['labels']), self._ptr(res['starts']), self._ptr(res['ends']), self._ptr(res['conf']),
                 self._ptr(res['counts']), self._ptr(res['out_lens'])))
@@ -200,17 +205,17 @@ class Engine:
         """Enqueue one host batch in `slot` (0 or 1) without waiting: H2D on the handle's copy stream, forward + decode
         + D2H on the current stream.  Keep `img` / `widths` alive and unchanged until `recognize_host_end(slot)`.
         Two slots let the copy of batch i+1 overlap the forward pass of batch i."""
-        if img.device.type != 'cpu' or img.dtype != torch.float32 or not img.is_contiguous():
-            raise ValueError('recognize_host_begin expects a contiguous fp32 host tensor (N,1,H,W)')
+        if img.device.type != 'cpu' or img.dtype not in (torch.float32, torch.uint8) or not img.is_contiguous():
+            raise ValueError('recognize_host_begin expects a contiguous fp32 (or uint8: raw pixels) host tensor (N,1,H,W)')
         B, ch, H, W = img.shape
         if ch != 1 or H != self.height:
             raise ValueError(f'expected (N,1,{self.height},W) input, got {tuple(img.shape)}')
         wh = None
         if widths is not None:
             wh = torch.as_tensor(widths).to(dtype=torch.int32).contiguous()
+        fn = self._lib.cocr_recognize_host_u8_begin if img.dtype == torch.uint8 else self._lib.cocr_recognize_host_begin
         with torch.cuda.device(self.device):
-            self._check(self._lib.cocr_recognize_host_begin(self._h, slot, C.c_void_p(img.data_ptr()), self._ptr(wh), B, W,
-                                                            self._stream()))
+            self._check(fn(self._h, slot, C.c_void_p(img.data_ptr()), self._ptr(wh), B, W, self._stream()))
         self._pending = getattr(self, '_pending', {})
         self._pending[slot] = (img, wh, B, int(self._lib.cocr_out_frames(W)))      # keeps the host buffers alive
 

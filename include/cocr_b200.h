@@ -150,6 +150,18 @@ int cocr_recognize_host_end(cocr_handle *h, int32_t slot,
                             int32_t *labels_host, int32_t *starts_host, int32_t *ends_host, float *conf_host,
                             int32_t *counts_host, int32_t *out_lens_host);
 
+/* uint8 input (extends dataset.py:158 / pred.py:119, whose batches are float tensors produced by
+ * torchvision's ToTensor from 8-bit line images): the same calls on raw 8-bit pixels.  The front-end kernel scales every
+ * pixel by the correctly rounded p / 255.0f, so the results are bit-identical to passing `img.float() / 255`; the
+ * host-to-device copy and the image read are four times smaller.  bf16 handles only (COCR_ERR_UNSUPPORTED otherwise).
+ * Strides are in elements, as for the float entry points. */
+int cocr_forward_decode_u8(cocr_handle *h, const uint8_t *img, int64_t sb, int64_t sw, int64_t sh,
+                           const int32_t *widths, int32_t B, int32_t W, void *stream,
+                           int32_t *labels, int32_t *starts, int32_t *ends, float *conf,
+                           int32_t *counts, int32_t *out_lens);
+int cocr_recognize_host_u8_begin(cocr_handle *h, int32_t slot, const uint8_t *img_host, const int32_t *widths_host,
+                                 int32_t B, int32_t W, void *stream);   /* collect with cocr_recognize_host_end */
+
 /* Bytes of device workspace the handle holds after a call with this (B, W). */
 int cocr_workspace_bytes(cocr_handle *h, int32_t B, int32_t W, size_t *bytes);
 

@@ -216,3 +216,46 @@ def test_bf16_odd_shapes_against_fp32(B, W, cuda_device):
     got = net16.predict_labels(x, tl)
     ref = [O.greedy_decoder(a[i, :int(ol16[i])].T) for i in range(B)]
     assert [[t[:3] for t in l] for l in got] == [[t[:3] for t in l] for l in ref]
+
+
+def test_uint8_input_is_bit_identical_to_scaled_float(cuda_device):
+    """raw 8-bit pixels through cocr_forward_decode_u8 / cocr_recognize_host_u8_begin give exactly what
+    `img.float() / 255` gives through the float entry points (the kernel divides by 255 with correct rounding)."""
+    from conformer_ocr_b200 import default_specs as D
+    from conformer_ocr_b200 import synthetic as S
+    from conformer_ocr_b200.engine import Engine
+    hp = dict(D.RECOGNITION_HYPER_PARAMS)
+    C_, B, W = 60, 5, 700
+    eng = Engine(height=hp['height'], encoder_dim=hp['encoder_dim'], num_layers=2, num_heads=hp['num_attention_heads'],
+                 ff_expansion=hp['feed_forward_expansion_factor'], conv_expansion=hp['conv_expansion_factor'],
+                 conv_kernel_size=hp['conv_kernel_size'], half_step_residual=hp['half_step_residual'],
+                 subsampling_conv_channels=hp['subsampling_conv_channels'], subsampling_factor=hp['subsampling_factor'],
+                 num_classes=C_, device=cuda_device, precision='bf16')
+    hp2 = dict(hp); hp2['num_encoder_layers'] = 2
+    eng.load_state_dict(S.make_weights(hp2, C_, seed=3))
+    g = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (B, 1, hp['height'], W), generator=g, dtype=torch.uint8)
+    lens = torch.tensor([700, 650, 700, 123, 400], dtype=torch.int32)
+    f32 = u8.float() / 255
+    a = eng.forward_decode(f32.to(cuda_device).squeeze(1).transpose(1, 2), lens)
+    b = eng.forward_decode(u8.to(cuda_device).squeeze(1).transpose(1, 2), lens)
+    for k in ('labels', 'starts', 'ends', 'counts', 'out_lens', 'conf'):
+        n = a['counts'].cpu().numpy()
+        x, y = a[k].cpu().numpy(), b[k].cpu().numpy()
+        if x.ndim == 2:
+            for i in range(B):
+                np.testing.assert_array_equal(x[i, :n[i]], y[i, :n[i]])
+        else:
+            np.testing.assert_array_equal(x, y)
+    # host entry points: uint8 pinned batch in, same records out
+    eng.recognize_host_begin(0, f32.contiguous().pin_memory(), lens)
+    eng.recognize_host_begin(1, u8.contiguous().pin_memory(), lens)
+    ra, rb = eng.recognize_host_end(0), eng.recognize_host_end(1)
+    np.testing.assert_array_equal(ra['counts'], rb['counts'])
+    for i in range(B):
+        np.testing.assert_array_equal(ra['labels'][i, :ra['counts'][i]], rb['labels'][i, :rb['counts'][i]])
+        np.testing.assert_array_equal(ra['conf'][i, :ra['counts'][i]], rb['conf'][i, :rb['counts'][i]])
+    # the encoder / logits calls accept uint8 too (converted on the device)
+    e1, _ = eng.encode(f32.to(cuda_device).squeeze(1).transpose(1, 2), lens)
+    e2, _ = eng.encode(u8.to(cuda_device).squeeze(1).transpose(1, 2), lens)
+    assert torch.equal(e1, e2)
