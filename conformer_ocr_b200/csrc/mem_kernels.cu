@@ -403,7 +403,7 @@ struct FrontendWeights {
     float w1[32 * 9], b1[32], wdw[32 * 9], bdw[32];
 };
 
-constexpr int FE2_TT = 8;
+constexpr int FE2_TT = 12;           // 25 x 48 conv1 positions = 4.7 passes of 256 threads (8 frames: 3.2 passes, the last one 81 % idle)
 constexpr int FE2_THREADS = 256;
 
 // 16-byte chunk g (8 channels) of position pos inside a1[pos][32 ch] bf16, xor-swizzled so that lanes writing / reading
