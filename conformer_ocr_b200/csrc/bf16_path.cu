@@ -187,10 +187,10 @@ int launch_gemm_tc(cocr_handle *h, int epi, const bf16 *A, int lda, const bf16 *
     }
 #define COCR_GEMM_CASE(E)                                                                                              \
     case E: {                                                                                                          \
-        static int attr_smem = 0;                                                                                      \
-        if ((int)smem > attr_smem) {                                                                                   \
+        static PerDevice<int> attr_smem;                                                                               \
+        if ((int)smem > attr_smem.get()) {                                                                             \
             COCR_CUDA(h, cudaFuncSetAttribute(k_gemm_tc<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget)); \
-            attr_smem = (int)budget;                                                                                   \
+            attr_smem.get() = (int)budget;                                                                             \
         }                                                                                                              \
         k_gemm_tc<E><<<grid, gemm_threads(E), smem, st>>>(tmA, tmB, tmC, p);                                                  \
         break;                                                                                                         \
@@ -605,10 +605,10 @@ static int launch_attn_tc(cocr_handle *h, const bf16 *qkvx, const int32_t *lens,
     }
     const uint32_t smem = attn_smem_bytes(bs->nchunk, a.e_resident, a.k_stages, a.v_stages, T);
     if (smem > cap) return set_error(h, COCR_ERR_UNSUPPORTED, "attention tiles do not fit shared memory");
-    static bool attr = false;
-    if (!attr) {
+    static PerDevice<bool> attr;
+    if (!attr.get()) {
         COCR_CUDA(h, cudaFuncSetAttribute(k_attn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->smem_optin));
-        attr = true;
+        attr.get() = true;
     }
     const int n_units = a.kv_resident ? B * dm.nh : a.n_items;              // what the CTAs deal out among themselves
     const int grid = n_units < h->num_sms ? n_units : h->num_sms;
@@ -698,10 +698,10 @@ static int launch_ffn_fused(cocr_handle *h, const bf16 *xn, int ldx, const bf16 
     COCR_TRY(make_tmap_bf16(h, &tmX, xn, M, FFN_K1, ldx, 128));
     COCR_TRY(make_tmap_bf16(h, &tmW1, w1p, ff, FFN_K1, FFN_K1, FFN_HC));
     COCR_TRY(make_tmap_bf16(h, &tmW2, w2p, (int64_t)a.NC * FFN_D, FFN_HC, FFN_HC, FFN_D));
-    static bool attr = false;
-    if (!attr) {
+    static PerDevice<bool> attr;
+    if (!attr.get()) {
         COCR_CUDA(h, cudaFuncSetAttribute(k_ffn_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FFN_SMEM_BYTES));
-        attr = true;
+        attr.get() = true;
     }
     const int grid = a.m_tiles < h->num_sms ? a.m_tiles : h->num_sms;
     ProfScope ps(h, tag, st, 4.0 * M * (double)ff * FFN_D, (double)M * FFN_D * (2.0 + 2.0 + 4.0 + 4.0) + 4.0 * ff * FFN_D);

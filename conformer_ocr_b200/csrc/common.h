@@ -152,6 +152,18 @@ struct ProfScope {
     }
 };
 
+// Function attributes (cudaFuncSetAttribute) belong to a device: the "already set" memo of every launcher is kept per
+// device so that handles on several GPUs of one process each get theirs.
+template <typename T>
+struct PerDevice {
+    T v[64] = {};
+    T &get() {
+        int d = 0;
+        cudaGetDevice(&d);
+        return v[d & 63];
+    }
+};
+
 inline int out_len1(int n) { return (n + 2 - 3) / 2 + 1; }   // one stride-2 3x3 pad-1 conv; n >= 1
 
 // ---- fp32 path (fp32_path.cu) ------------------------------------------------------------

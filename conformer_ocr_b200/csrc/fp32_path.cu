@@ -362,10 +362,10 @@ template <int DH, typename TA>
 static int launch_attn_t(cocr_handle *h, const TA *qkv, const float *pos, const float *ub, const float *vb,
                          const int32_t *lens, TA *ctx, int B, int T, int d, int nh, int dh, cudaStream_t st) {
     size_t smem = sizeof(float) * ((size_t)(2 * AKT + AQT + AKT - 1) * (DH + 1) + (size_t)AQT * (AKT + 1));
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDevice<bool> attr_done;
+    if (!attr_done.get()) {
         cudaFuncSetAttribute(k_attn_f32<DH, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
+        attr_done.get() = true;
     }
     dim3 grid((T + AQT - 1) / AQT, nh, B);
     ProfScope ps(h, "attention_f32", st, 6.0 * B * T * (double)T * d, 16.0 * B * T * d);
@@ -440,10 +440,10 @@ static int launch_glu_dw_any(cocr_handle *h, const TA *u, const LayerF32 &lw, TA
     const Dims &dm = h->dm;
     size_t smem = sizeof(float) * (size_t)(DW_TT + 2 * dm.K - 1) * dm.d;
     if (smem > 200 * 1024) return set_error(h, COCR_ERR_UNSUPPORTED, "conv module tile needs %zu B of shared memory", smem);
-    static size_t attr = 0;
-    if (smem > attr) {
+    static PerDevice<size_t> attr;
+    if (smem > attr.get()) {
         cudaFuncSetAttribute(k_glu_dw_bn_silu<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = smem;
+        attr.get() = smem;
     }
     dim3 grid((T + DW_TT - 1) / DW_TT, B);
     ProfScope ps(h, "glu_dwconv_bn_silu_f32", st, 2.0 * dm.K * B * (double)T * dm.d, 12.0 * B * T * dm.d);

@@ -106,10 +106,10 @@ int launch_glu_dw_fast(cocr_handle *h, const bf16 *u, const LayerF32 &lw, bf16 *
     const int nthr = P * (DWF_TT / DWF_SEG);
     if (dm.K != 31 || (dm.d & 7) != 0 || nthr > 576) return COCR_ERR_UNSUPPORTED;
     const size_t smem = (size_t)(DWF_TT + 30) * P * 4 + (size_t)31 * P * 8;
-    static bool attr = false;
-    if (!attr) {
+    static PerDevice<bool> attr;
+    if (!attr.get()) {
         COCR_CUDA(h, cudaFuncSetAttribute(k_glu_dw_fast<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
+        attr.get() = true;
     }
     dim3 grid((T + DWF_TT - 1) / DWF_TT, B);
     ProfScope ps(h, "glu_dwconv_bn_silu_bf16", st, 2.0 * 31 * B * (double)T * dm.d, 6.0 * B * T * dm.d);
@@ -228,10 +228,10 @@ int launch_dw_fast(cocr_handle *h, const bf16 *x, const float *taps_dev, const f
     const int nthr = P * (DWF_TT / DWF_SEG);
     if (dm.K != 31 || (dm.d & 7) != 0 || nthr > 576 || !taps_dev || nthr % (dm.d / 8) != 0) return COCR_ERR_UNSUPPORTED;
     const size_t smem = (size_t)2 * (DWF_TT + 30) * P * 4 + (size_t)31 * P * 8;
-    static bool attr = false;
-    if (!attr) {
+    static PerDevice<bool> attr;
+    if (!attr.get()) {
         COCR_CUDA(h, cudaFuncSetAttribute(k_dw_fast<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
+        attr.get() = true;
     }
     const int n_tt = (T + DWF_TT - 1) / DWF_TT, n_items = n_tt * B;
     int grid = 2 * h->num_sms;
@@ -374,10 +374,10 @@ int launch_frontend_fused(cocr_handle *h, const float *img, int64_t sb, int64_t 
     const int HP = (dm.H + 2 + 3) & ~3;
     const size_t smem = (size_t)(4 * FE_TT + 3) * HP * 4 + (size_t)(2 * FE_TT + 1) * dm.F2 * 32 * 2 + (size_t)FE_TT * dm.F * 32 * 4;
     if (smem > 200 * 1024) return COCR_ERR_UNSUPPORTED;
-    static size_t attr = 0;
-    if (smem > attr) {
+    static PerDevice<size_t> attr;
+    if (smem > attr.get()) {
         COCR_CUDA(h, cudaFuncSetAttribute(k_frontend_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
+        attr.get() = smem;
     }
     dim3 grid((T + FE_TT - 1) / FE_TT, B);
     const double n1 = (double)B * T2 * dm.F2 * 32, n2 = (double)B * T * dm.F * 32;
@@ -537,11 +537,11 @@ int launch_frontend_convs2(cocr_handle *h, const float *img, int64_t sb, int64_t
     const int HP = (dm.H + 2 + 3) & ~3;
     const size_t smem = (size_t)(4 * FE2_TT + 3) * HP * 4 + (size_t)(2 * FE2_TT + 1) * dm.F2 * 64;
     if (smem > 200 * 1024) return COCR_ERR_UNSUPPORTED;
-    static size_t attr = 0;
-    if (smem > attr) {
+    static PerDevice<size_t> attr;
+    if (smem > attr.get()) {
         COCR_CUDA(h, cudaFuncSetAttribute(k_frontend_convs2<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         COCR_CUDA(h, cudaFuncSetAttribute(k_frontend_convs2<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
+        attr.get() = smem;
     }
     FrontendWeights fw;
     memcpy(&fw, h->fe_weights.data(), sizeof(fw));

@@ -259,3 +259,20 @@ def test_uint8_input_is_bit_identical_to_scaled_float(cuda_device):
     e1, _ = eng.encode(f32.to(cuda_device).squeeze(1).transpose(1, 2), lens)
     e2, _ = eng.encode(u8.to(cuda_device).squeeze(1).transpose(1, 2), lens)
     assert torch.equal(e1, e2)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs in one process')
+def test_two_devices_in_one_process(cuda_device):
+    """Handles on two GPUs of the same process: per-device function attributes (dynamic shared memory opt-in), per-handle
+    workspaces and graphs; both devices give the same records for the same batch."""
+    from conformer_ocr_b200.pred import PytorchRecognitionModel
+    meta, _ = load_golden('default_equal')
+    hp, w, img, lens = golden_inputs(meta)
+    outs = []
+    for dev in (torch.device('cuda', 1), torch.device('cuda', 0)):          # second device first: nothing cached for it yet
+        net = build_net(hp, meta['num_classes'], w, dev)
+        x = torch.from_numpy(img).to(dev)
+        for _ in range(3):                                                  # eager, capture, replay
+            rec = net.predict_labels(x, torch.from_numpy(lens))
+        outs.append(rec)
+    assert [[r[0] for r in line] for line in outs[0]] == [[r[0] for r in line] for line in outs[1]]
