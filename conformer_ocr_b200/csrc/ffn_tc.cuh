@@ -16,8 +16,8 @@
 // is already running.  The weight chunks (36 KB each) stream from L2 through a three-slot ring in the order the MMAs
 // consume them; the xn tiles are double-buffered and requested a tile ahead.
 //
-// Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + issuer of G1, warps 2..9 = E1 (two per TMEM lane quarter, 48 of
-// the 96 hidden columns each), warps 10..17 = final epilogue (two per lane quarter), warp 18 = issuer of G2.
+// Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (G1 runs one chunk ahead of G2), warps 2..9 = E1
+// (two per TMEM lane quarter, 48 of the 96 hidden columns each), warps 10..17 = final epilogue (two per lane quarter).
 // E1 is MUFU bound (one tanh per hidden element) and reads nothing from memory: the FFN-up bias rides in the GEMM.  The
 // xn rows carry two extra columns of ones (144, 145; the xn buffer has a pitch of 160 and its pad columns are initialised
 // once per forward pass) and W1 carries the bias split into a bf16 high and low part in the same two columns, so
@@ -38,8 +38,7 @@ constexpr int FFN_NG = FFN_D / 8;                                 // 8-column gr
 constexpr int FFN_MAX_NC = 8;                                     // ff <= 768
 constexpr int FFN_EPI_WARPS = 8;                                  // E1 warps (two per TMEM lane quarter)
 constexpr int FFN_FIN_WARPS = 8;                                  // final-epilogue warps (two per lane quarter, 16 rows each)
-constexpr int FFN_W_G2 = 2 + FFN_EPI_WARPS + FFN_FIN_WARPS;       // the warp that issues the G2 MMAs
-constexpr int FFN_THREADS = 32 * (FFN_W_G2 + 1);
+constexpr int FFN_THREADS = 64 + 32 * (FFN_EPI_WARPS + FFN_FIN_WARPS);
 constexpr int FFN_WSTAGES = 3;
 constexpr uint32_t FFN_A_CHUNK = 128 * 128;                       // one 64-column k-chunk of the xn tile (SWIZZLE_128B)
 constexpr uint32_t FFN_A_BYTES = 3 * FFN_A_CHUNK;                 // k = 64 + 64 + 16 (the last chunk is mostly padding)
@@ -86,8 +85,7 @@ k_ffn_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
     uint64_t *hbfull = bars + 14;        // [2]  bf16 hidden chunk written (E1 warps)
     uint64_t *yfull = bars + 16;         // [2]  last G2 of a tile done
     uint64_t *yempty = bars + 18;        // [2]  Y drained (final warps)
-    uint64_t *hfree = bars + 20;         // [2]  G2 done with the bf16 hidden chunk: the accumulator may take a new G1
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 22);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 20);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NC = p.NC;
@@ -100,7 +98,7 @@ k_ffn_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
         for (int s = 0; s < 2; ++s) {
             mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1);
             mbar_init(&h1full[s], 1); mbar_init(&hbfull[s], FFN_EPI_WARPS);
-            mbar_init(&yfull[s], 1); mbar_init(&yempty[s], FFN_FIN_WARPS); mbar_init(&hfree[s], 1);
+            mbar_init(&yfull[s], 1); mbar_init(&yempty[s], FFN_FIN_WARPS);
         }
         for (int s = 0; s < FFN_WSTAGES; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
         mbar_fence_init();
@@ -160,76 +158,75 @@ k_ffn_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
                 load_w(&tmW2, n % NC);
             }
         }
-    } else if (warp == 1 || warp == FFN_W_G2) {
-        // ================= MMA issuers =================
-        // Two warps, one per GEMM: tcgen05.mma blocks the issuing thread while the tensor pipe's short queue is full, so
-        // a single issuer spends a whole G1 (~950 cycles) before it notices that E1 has finished and G2 may go, and the
-        // waits and commits of one GEMM serialise with the other.  The two streams touch disjoint accumulators and every
-        // commit tracks only the issuing thread's MMAs.  Weight chunks sit in the ring in consumption order
-        // W1(0), then W1(n+1), W2(n) for every n, so each issuer knows its slots without talking to the other.
-        auto ring_slot = [&](uint32_t idx, uint32_t &sl, uint32_t &ph) { sl = idx % FFN_WSTAGES; ph = (idx / FFN_WSTAGES) & 1u; };
-        int tr_n = (lane == 0 && warp == 1) ? 0 : GEMM_TRACE_EVENTS;
-        if (warp == 1) {
-            // ---- G1: H(n & 1) = xn_tile * W1_c^T, as soon as G2(n-2) has released the accumulator ----
-            const uint32_t idesc1 = make_idesc_bf16(128, FFN_HC);
-            int t = 0, c = 0;
-            for (int n = 0; n < n_total; ++n) {
-                const int sa = t & 1;
-                GEMM_TRACE(1, 200 + c);
-                if (n >= 2) mbar_wait(&hfree[n & 1], (((uint32_t)n >> 1) - 1u) & 1u);
-                if (c == 0) mbar_wait(&afull[sa], ((uint32_t)t >> 1) & 1u);
-                uint32_t sl, ph;
-                ring_slot(n == 0 ? 0u : 2u * (uint32_t)n - 1u, sl, ph);
-                mbar_wait(&wfull[sl], ph);
-                GEMM_TRACE(1, 210 + c);
-                tc_fence_after();
-                const uint32_t a_base = smem_u32(sA + (uint32_t)sa * FFN_A_BYTES), b_base = smem_u32(sW + sl * FFN_W_BYTES);
-                const uint32_t d_tmem = tmem_base + ((n & 1) ? FFN_H_COL1 : FFN_H_COL0);
-                if (elect_one()) {
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        const uint32_t idesc1 = make_idesc_bf16(128, FFN_HC), idesc2 = make_idesc_bf16(128, FFN_D);
+        uint32_t wq = 0;
+        int tr_n = (lane == 0) ? 0 : GEMM_TRACE_EVENTS;
+        // (tile, chunk) of G1 and of G2 advance separately (no division on the issue path)
+        int t1 = 0, c1 = 0, t2 = 0, c2 = 0;
+        auto g1 = [&](int n) {                                     // H(n & 1) = xn_tile * W1_c^T
+            const int t = t1, c = c1;
+            if (++c1 == NC) { c1 = 0; ++t1; }
+            const int sa = t & 1;
+            GEMM_TRACE(1, 200 + c);
+            if (c == 0) mbar_wait(&afull[sa], ((uint32_t)t >> 1) & 1u);
+            const uint32_t sl = wq % FFN_WSTAGES;
+            mbar_wait(&wfull[sl], (wq / FFN_WSTAGES) & 1u);
+            ++wq;
+            GEMM_TRACE(1, 210 + c);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(sA + (uint32_t)sa * FFN_A_BYTES), b_base = smem_u32(sW + sl * FFN_W_BYTES);
+            const uint32_t d_tmem = tmem_base + ((n & 1) ? FFN_H_COL1 : FFN_H_COL0);
+            if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < FFN_K1 / 16; ++k) {
-                        if (p.dbg & 8) break;
-                        const uint32_t off = (uint32_t)(k >> 2), ks = (uint32_t)(k & 3);
-                        umma_bf16_ss(d_tmem, make_smem_desc_sw128(a_base + off * FFN_A_CHUNK + ks * 32, 1024),
-                                     make_smem_desc_sw128(b_base + off * FFN_W1_CHUNK + ks * 32, 1024), idesc1, k ? 1u : 0u);
-                    }
-                    umma_commit(&wempty[sl]);
-                    umma_commit(&h1full[n & 1]);
-                    if (c == NC - 1) umma_commit(&aempty[sa]);
+                for (int k = 0; k < FFN_K1 / 16; ++k) {
+                    if (p.dbg & 8) break;
+                    const uint32_t off = (uint32_t)(k >> 2), ks = (uint32_t)(k & 3);
+                    umma_bf16_ss(d_tmem, make_smem_desc_sw128(a_base + off * FFN_A_CHUNK + ks * 32, 1024),
+                                 make_smem_desc_sw128(b_base + off * FFN_W1_CHUNK + ks * 32, 1024), idesc1, k ? 1u : 0u);
                 }
-                __syncwarp();
-                GEMM_TRACE(1, 220 + c);
-                if (++c == NC) { c = 0; ++t; }
+                umma_commit(&wempty[sl]);
+                umma_commit(&h1full[n & 1]);
+                if (c == NC - 1) umma_commit(&aempty[sa]);
             }
-        } else {
-            // ---- G2: Y(t & 1) += bf16 H(n & 1) (TMEM) * W2_c^T, as soon as E1 has written the chunk ----
-            const uint32_t idesc2 = make_idesc_bf16(128, FFN_D);
-            int t = 0, c = 0;
-            for (int n = 0; n < n_total; ++n) {
-                uint32_t sl, ph;
-                ring_slot(n == n_total - 1 ? 2u * (uint32_t)n + 1u : 2u * (uint32_t)n + 2u, sl, ph);
-                mbar_wait(&wfull[sl], ph);
-                mbar_wait(&hbfull[n & 1], ((uint32_t)n >> 1) & 1u);
-                if (c == 0) mbar_wait(&yempty[t & 1], (((uint32_t)t >> 1) & 1u) ^ 1u);   // Y of tile t-2 has been drained
-                tc_fence_after();
-                const uint32_t b_base = smem_u32(sW + sl * FFN_W_BYTES);
-                const uint32_t a_tmem = tmem_base + ((n & 1) ? FFN_H_COL1 : FFN_H_COL0);
-                const uint32_t y_tmem = tmem_base + ((t & 1) ? FFN_Y_COL1 : FFN_Y_COL0);
-                if (elect_one()) {
+            __syncwarp();
+            GEMM_TRACE(1, 220 + c);
+        };
+        auto g2 = [&](int n) {                                     // Y(t & 1) += bf16 H(n & 1) (TMEM) * W2_c^T
+            const int t = t2, c = c2;
+            if (++c2 == NC) { c2 = 0; ++t2; }
+            const uint32_t sl = wq % FFN_WSTAGES;
+            GEMM_TRACE(1, 230 + c);
+            mbar_wait(&wfull[sl], (wq / FFN_WSTAGES) & 1u);
+            ++wq;
+            GEMM_TRACE(1, 240 + c);
+            mbar_wait(&hbfull[n & 1], ((uint32_t)n >> 1) & 1u);
+            GEMM_TRACE(1, 250 + c);
+            if (c == 0) mbar_wait(&yempty[t & 1], (((uint32_t)t >> 1) & 1u) ^ 1u);   // Y of tile t-2 has been drained
+            GEMM_TRACE(1, 260 + c);
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(sW + sl * FFN_W_BYTES);
+            const uint32_t a_tmem = tmem_base + ((n & 1) ? FFN_H_COL1 : FFN_H_COL0);
+            const uint32_t y_tmem = tmem_base + ((t & 1) ? FFN_Y_COL1 : FFN_Y_COL0);
+            if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < FFN_HC / 16; ++k) {
-                        if (p.dbg & 8) break;
-                        const uint32_t off = (uint32_t)(k >> 2), ks = (uint32_t)(k & 3);
-                        umma_bf16_ts(y_tmem, a_tmem + (uint32_t)(k < 3 ? k * 8 : 72 + (k - 3) * 8), make_smem_desc_sw128(b_base + off * FFN_W2_CHUNK + ks * 32, 1024),
-                                     idesc2, (c | k) ? 1u : 0u);
-                    }
-                    umma_commit(&wempty[sl]);
-                    umma_commit(&hfree[n & 1]);
-                    if (c == NC - 1) umma_commit(&yfull[t & 1]);
+                for (int k = 0; k < FFN_HC / 16; ++k) {
+                    if (p.dbg & 8) break;
+                    const uint32_t off = (uint32_t)(k >> 2), ks = (uint32_t)(k & 3);
+                    umma_bf16_ts(y_tmem, a_tmem + (uint32_t)(k < 3 ? k * 8 : 72 + (k - 3) * 8), make_smem_desc_sw128(b_base + off * FFN_W2_CHUNK + ks * 32, 1024), idesc2,
+                                 (c | k) ? 1u : 0u);
                 }
-                __syncwarp();
-                if (++c == NC) { c = 0; ++t; }
+                umma_commit(&wempty[sl]);
+                if (c == NC - 1) umma_commit(&yfull[t & 1]);
             }
+            __syncwarp();
+            GEMM_TRACE(1, 270 + c);
+        };
+        if (n_total > 0) g1(0);
+        for (int n = 0; n < n_total; ++n) {
+            if (n + 1 < n_total) g1(n + 1);
+            g2(n);
         }
     } else if (warp < 2 + FFN_EPI_WARPS) {
         // ================= E1 warps: H <- bf16(silu(H + b1)), thread = row, 48 columns =================
@@ -276,7 +273,7 @@ k_ffn_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
             GEMM_TRACE(0, 330 + c);
             if (++c == NC) { c = 0; ++t; }
         }
-    } else if (warp < FFN_W_G2) {
+    } else {
         // ================= final-epilogue warps =================
         // x <- x + alpha * (Y + b2) [-> LN_final]; xn = bf16(LN_next(x)); fragment layout (see EPI_RESID in gemm_tc.cuh).
         // Their own warps: the x / xn traffic of a tile (184 KB through the LSU) and the LayerNorm arithmetic overlap the

@@ -276,3 +276,34 @@ def test_two_devices_in_one_process(cuda_device):
             rec = net.predict_labels(x, torch.from_numpy(lens))
         outs.append(rec)
     assert [[r[0] for r in line] for line in outs[0]] == [[r[0] for r in line] for line in outs[1]]
+
+
+def test_bf16_long_run_is_stable(cuda_device):
+    """300 back-to-back steps of the benchmark workload: every step must succeed and reproduce the first step's records.
+    (A variant of the fused FFN kernel with two MMA-issuing warps passed every parity test and died with an unspecified
+    launch failure about once in a hundred steps; short tests never saw it.)"""
+    from conformer_ocr_b200 import default_specs as D
+    from conformer_ocr_b200 import synthetic as S
+    from conformer_ocr_b200.engine import Engine
+    hp = dict(D.RECOGNITION_HYPER_PARAMS)
+    B, W, C_ = 256, 1536, 256
+    eng = Engine(height=hp['height'], encoder_dim=hp['encoder_dim'], num_layers=hp['num_encoder_layers'],
+                 num_heads=hp['num_attention_heads'], ff_expansion=hp['feed_forward_expansion_factor'],
+                 conv_expansion=hp['conv_expansion_factor'], conv_kernel_size=hp['conv_kernel_size'],
+                 half_step_residual=hp['half_step_residual'], subsampling_conv_channels=hp['subsampling_conv_channels'],
+                 subsampling_factor=hp['subsampling_factor'], num_classes=C_, device=cuda_device, precision='bf16')
+    eng.load_state_dict(S.make_weights(hp, C_, seed=0))
+    g = torch.Generator(device=cuda_device).manual_seed(99)
+    x = torch.rand((B, 1, hp['height'], W), generator=g, device=cuda_device).squeeze(1).transpose(1, 2)
+    lens = torch.full((B,), W, dtype=torch.int32)
+    first = None
+    for step in range(300):
+        res = eng.forward_decode(x, lens)
+        if step % 50 == 0 or step == 299:
+            torch.cuda.synchronize(cuda_device)
+            cur = (res['counts'].cpu(), res['labels'].cpu())
+            if first is None:
+                first = cur
+            else:
+                assert torch.equal(cur[0], first[0]) and torch.equal(cur[1], first[1]), f'step {step} differs from step 0'
+    torch.cuda.synchronize(cuda_device)
