@@ -182,11 +182,16 @@ def run_ours(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    json_fd = None
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION', 'INFO'):
-            os.environ['NCCL_DEBUG'] = 'WARN'       # NCCL prints its banner on stdout (also when a config file asks for it);
-                                                    # this script prints ONE JSON line
+            os.environ['NCCL_DEBUG'] = 'WARN'
+        # NCCL prints its version banner on the process's stdout from C (whatever NCCL_DEBUG says on some boxes); this
+        # script's stdout carries ONE JSON line, so file descriptor 1 points at stderr until that line is written
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     assert torch.cuda.is_available(), 'bench.py (our arm) needs a CUDA device; there is no CPU fallback'
     dev = torch.device('cuda', local_rank)
@@ -392,7 +397,12 @@ def run_ours(args):
                                   frac=step_tflops / peaks['tflops_sustained'], gflop_per_line=fl_line / 1e9,
                                   peak_source=peaks['source'] + ' (sustained bf16 cuBLAS)'),
                kernel_families=families, cpu_baseline=cpu_baseline)
-    print(json.dumps(out), flush=True)
+    if json_fd is not None:
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + '\n').encode())
+        os.close(json_fd)
+    else:
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
