@@ -235,8 +235,10 @@ int cocr_destroy(cocr_handle *h) {
         if (sl.res_host) cudaFreeHost(sl.res_host);
         if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
         if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.fwd_done) cudaEventDestroy(sl.fwd_done);
     }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     delete h;
     return COCR_OK;
 }
@@ -487,9 +489,11 @@ static int host_begin(cocr_handle *h, int32_t slot, const void *img_host, size_t
     const int H = h->dm.H;
     const int T = cocr_out_frames(W);
     if (!h->copy_stream) COCR_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (!h->d2h_stream) COCR_CUDA(h, cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
     if (!sl.h2d_done) {
         COCR_CUDA(h, cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
         COCR_CUDA(h, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+        COCR_CUDA(h, cudaEventCreateWithFlags(&sl.fwd_done, cudaEventDisableTiming));
     }
     const size_t img_bytes = pix_bytes * (size_t)B * H * W;
     if (img_bytes > sl.img_bytes) {
@@ -537,8 +541,11 @@ static int host_begin(cocr_handle *h, int32_t slot, const void *img_host, size_t
                                         d_cf, d_cnt, d_len));
     else
         COCR_TRY(cocr_forward_decode(h, sl.img, (int64_t)H * W, 1, W, wd, B, W, stream, d_lab, d_st, d_en, d_cf, d_cnt, d_len));
-    COCR_CUDA(h, cudaMemcpyAsync(sl.res_host, sl.res, res_bytes, cudaMemcpyDeviceToHost, st));
-    COCR_CUDA(h, cudaEventRecord(sl.done, st));
+    // the records leave on their own stream: the forward pass of the other slot, already queued on `stream`, starts at once
+    COCR_CUDA(h, cudaEventRecord(sl.fwd_done, st));
+    COCR_CUDA(h, cudaStreamWaitEvent(h->d2h_stream, sl.fwd_done, 0));
+    COCR_CUDA(h, cudaMemcpyAsync(sl.res_host, sl.res, res_bytes, cudaMemcpyDeviceToHost, h->d2h_stream));
+    COCR_CUDA(h, cudaEventRecord(sl.done, h->d2h_stream));
     sl.B = B; sl.T = T; sl.busy = true;
     return COCR_OK;
 }

@@ -91,11 +91,12 @@ struct cocr_handle {
         char *res = nullptr;           // device result block
         char *res_host = nullptr;      // pinned mirror
         size_t res_bytes = 0;
-        cudaEvent_t h2d_done = nullptr, done = nullptr;
+        cudaEvent_t h2d_done = nullptr, fwd_done = nullptr, done = nullptr;
         int B = 0, T = 0;
         bool busy = false;
     } slots[2];
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;       // H2D of the batches
+    cudaStream_t d2h_stream = nullptr;        // D2H of the result blocks (the next forward pass does not wait for it)
 
     std::vector<float> fe_weights;   // conv.0 / conv.2 weights + biases in kernel-parameter order (mem_kernels.cu: FrontendWeights)
     int64_t launches = 0;

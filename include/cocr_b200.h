@@ -140,7 +140,8 @@ int cocr_recognize_host(cocr_handle *h, const float *img_host, const int32_t *wi
                         int32_t *counts_host, int32_t *out_lens_host);
 
 /* The same, split in two so that a caller can keep two batches in flight (slot 0 / 1): `begin` enqueues the H2D copy
- * of the batch on the handle's copy stream, the forward pass + decode + D2H on `stream`, and returns without waiting;
+ * of the batch on the handle's copy stream, the forward pass + decode on `stream`, the D2H of the records on a third stream
+ * of the handle (so the other slot's forward pass, already queued on `stream`, starts at once), and returns without waiting;
  * `end` waits for that slot and unpacks the results.  While batch i computes, the H2D copy of batch i+1 (other slot)
  * proceeds: this is how a DataLoader loop (cli/test.py:185-191) hides PCIe behind the forward pass.  A slot must be
  * ended before it is begun again; img_host / widths_host must stay valid (and unchanged) until the slot is ended. */
