@@ -3,10 +3,14 @@
 
     python bench.py --gpus N --steps K --warmup W            # our arm (libcocr_b200.so on N B200s)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (port), host cores
+    python bench.py --config 1|2|5 ...                       # BASELINE.json configs[0|1|4] (default 2 = configs[1])
 
-One "step" = one pass of the hot path over one batch of synthetic text lines.  Workload at N=1 is
-BASELINE.json configs[1]: default-spec conformer, batch 256 lines, 96 x 1536 px, 256 classes, bf16.
-Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the meaning of every key.
+Workload (default, BASELINE.json configs[1]): default-spec conformer, batches of 256 lines, 96 x 1536 px, 256 classes,
+bf16.  One "step" = `--passes-per-step` (default 16) passes of the hot path over 256-line batches = 4096 lines per GPU:
+a slice of config 3's shard (100 000 lines over 8 GPUs), long enough that K = 20 steps time > 2 s.  At N > 1 every rank
+runs its own shard (no data-path collective) and the decoded records of the whole timed region are gathered over NCCL
+inside the timed region (one collective per shard).  Prints ONE JSON line (rank 0).  DESIGN.md 6 explains
+every key.
 """
 from __future__ import annotations
 
@@ -26,7 +30,14 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-DEFAULT_PRECISION = 'bf16'     # BASELINE.json configs[1]: bf16 inference (fp32 is the parity-grade path)
+CONFIGS = {
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case
+    1: dict(batch=8, width=1024, classes=256, precision='fp32', passes=1, name='configs[0]'),
+    # configs[1]: the configuration the metric is quoted on
+    2: dict(batch=256, width=1536, classes=256, precision='bf16', passes=16, name='configs[1]'),
+    # configs[4]: long lines, CJK-sized alphabet
+    5: dict(batch=64, width=4096, classes=10000, precision='bf16', passes=4, name='configs[4]'),
+}
 
 
 def parse_args():
@@ -35,15 +46,25 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
-    ap.add_argument('--precision', choices=['fp32', 'bf16'], default=DEFAULT_PRECISION)
-    ap.add_argument('--batch', type=int, default=256, help='lines per step per GPU')
-    ap.add_argument('--width', type=int, default=1536)
-    ap.add_argument('--classes', type=int, default=256)
+    ap.add_argument('--config', type=int, choices=sorted(CONFIGS), default=2)
+    ap.add_argument('--precision', choices=['fp32', 'bf16'], default=None)
+    ap.add_argument('--batch', type=int, default=None, help='lines per pass per GPU')
+    ap.add_argument('--width', type=int, default=None)
+    ap.add_argument('--classes', type=int, default=None)
+    ap.add_argument('--passes-per-step', type=int, default=None, help='hot-path passes (batches) per step')
     ap.add_argument('--cpu-sample-lines', type=int, default=16, help='lines per CPU-baseline pass')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--profile-steps', type=int, default=2, help='extra steps with per-kernel CUDA events (roofline)')
-    return ap.parse_args()
+    ap.add_argument('--no-eager-baseline', action='store_true')
+    ap.add_argument('--profile-steps', type=int, default=2, help='extra passes with per-kernel CUDA events (roofline)')
+    a = ap.parse_args()
+    c = CONFIGS[a.config]
+    a.batch = a.batch or c['batch']
+    a.width = a.width or c['width']
+    a.classes = a.classes or c['classes']
+    a.precision = a.precision or c['precision']
+    a.passes = a.passes_per_step or c['passes']
+    return a
 
 
 def load_peaks():
@@ -117,8 +138,50 @@ def arch_hp(hp):
 
 
 def workload_name(args):
-    return (f'default_specs conformer (d144 L16 h4 ff576 k31), batch {args.batch} lines/GPU, 96x{args.width} px, '
-            f'{args.classes} classes, {args.precision} inference + greedy CTC decode')
+    return (f'BASELINE {CONFIGS[args.config]["name"]}: default_specs conformer (d144 L16 h4 ff576 k31), batch {args.batch} lines/GPU, '
+            f'96x{args.width} px, {args.classes} classes, {args.precision} inference + greedy CTC decode')
+
+
+def out_frames(W):
+    return (((W - 1) // 2 + 1) - 1) // 2 + 1
+
+
+# ----------------------------------------------------------------------------------------------
+# Algorithmic work of every kernel family for ONE pass over a (B, W) batch: SURVEY.md 8(d).
+# FLOPs are 2*MAC of the reference's contractions (positional scores once per (i, j); the positional projection is
+# batch-level and excluded); bytes are each activation once in / once out at the path's storage types (bf16
+# activations, fp32 residual stream).  `bound` is 8(d)'s table: tensor pipe for GEMMs and attention, HBM for the
+# LayerNorm / depthwise / GLU / front-end-conv / arg-max / collapse kernels.  Nothing here depends on how a kernel is
+# launched (padding, fused columns, tile sizes): a kernel that moves or multiplies more than this is charged for it.
+# ----------------------------------------------------------------------------------------------
+def algorithmic_work(hp, B, W, C, in_bytes_per_px=4):
+    d = hp['encoder_dim']
+    ff = d * hp['feed_forward_expansion_factor']
+    cc = hp['subsampling_conv_channels']
+    K = hp['conv_kernel_size']
+    H = hp['height']
+    F2 = (H + 2 - 3) // 2 + 1
+    F = (F2 + 2 - 3) // 2 + 1
+    T2 = (W - 1) // 2 + 1
+    T = (T2 - 1) // 2 + 1
+    M = B * T
+    act, xs = 2 * d, 4 * d                                  # bytes of one bf16 activation row / one fp32 residual row
+    fam = {
+        'frontend_convs': dict(flops=B * (2 * 9 * cc * F2 * T2 + 2 * 9 * cc * F * T), bytes=B * H * W * in_bytes_per_px + M * F * cc * 2, bound='hbm'),
+        'gemm_frontend_pw': dict(flops=M * 2 * cc * cc * F, bytes=2 * M * F * cc * 2, bound='tensor'),
+        'gemm_sub_out': dict(flops=M * 2 * (cc * F) * d, bytes=M * (F * cc * 2 + xs + act), bound='tensor'),
+        'ffn_fused': dict(flops=M * 2 * (2 * d * ff), bytes=M * (act + xs + xs + act), bound='tensor'),
+        'gemm_qkvx_pos': dict(flops=M * 3 * (2 * d * d), bytes=M * (act + 3 * act), bound='tensor'),
+        'attention_tc': dict(flops=B * 3 * (2 * T * T * d), bytes=M * (3 * act + act), bound='tensor'),
+        'gemm_attn_out': dict(flops=M * 2 * d * d, bytes=M * (act + xs + xs + act), bound='tensor'),
+        'gemm_pw1_glu': dict(flops=M * 2 * d * 2 * d, bytes=M * (act + act), bound='tensor'),
+        'dwconv_bn_silu_bf16': dict(flops=M * 2 * K * d, bytes=M * (act + act), bound='hbm'),
+        'gemm_pw2': dict(flops=M * 2 * d * d, bytes=M * (act + xs + xs + act), bound='tensor'),
+        'gemm_ctc_argmax': dict(flops=M * 2 * d * C, bytes=M * (act + 8), bound='tensor'),
+        'ctc_collapse': dict(flops=0, bytes=M * (8 + 16), bound='hbm'),
+    }
+    fam['ffn_fused_final'] = dict(fam['ffn_fused'])
+    return fam
 
 
 # ----------------------------------------------------------------------------------------------
@@ -151,6 +214,11 @@ def time_cpu(args, reps: int, warm: int):
     return n, cores, times
 
 
+CPU_NOTE = ('port of the reference\'s ATen CPU operator sequence (oracle/torch_port.py; the reference package itself imports '
+            'kraken/lightning, absent here); the relative-position table is built once per pass, not repeated per batch '
+            'row as attention.py:145 does, which flatters the reference slightly')
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -158,17 +226,54 @@ def run_reference(args):
     n, cores, times = time_cpu(args, reps=max(1, args.steps), warm=max(1, min(args.warmup, 2)))
     total = sum(times)
     lps = n * len(times) / total
-    T = (((args.width - 1) // 2 + 1) - 1) // 2 + 1
+    T = out_frames(args.width)
     sample = f'{n} lines of 96x{args.width} px per step ({len(times)} steps), fp32, torch CPU ops, {cores} threads'
     out = dict(impl='reference', metric='text lines/sec', value=lps, unit='lines/s', n_gpus=args.gpus, steps=len(times),
                warmup=args.warmup, ms_per_step=1e3 * total / len(times), higher_is_better=True, scaling='weak',
                vs_baseline=None, dtype='f32', data='synthetic', frames_per_s=lps * T,
                config=dict(workload=workload_name(args).replace(args.precision + ' inference', 'fp32 CPU inference'),
-                           sample=sample),
+                           sample=sample, note=CPU_NOTE),
                cpu_baseline=dict(value=lps, unit='lines/s', cores=cores, kind='port', sample=sample),
                e2e=dict(value=lps, unit='lines/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                gpu_launches=0)
     print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# the practical bar: the reference's operator sequence run by torch on the SAME GPU, eager fp32 and bf16 autocast
+# (SURVEY.md 2.3 / 8d).  oracle/torch_port.py is the port of those modules; library kernels (cuBLAS / cuDNN / ATen).
+# ----------------------------------------------------------------------------------------------
+def gpu_eager_baseline(args, hp, dev, x_dev, reps=3):
+    from oracle import torch_port as TP          # baseline leg, same status as cpu_baseline
+    from conformer_ocr_b200 import synthetic as S
+    out = {}
+    try:
+        w = {k: v.to(dev) for k, v in TP.to_torch(S.make_weights(hp, args.classes, seed=0)).items()}
+        lens = torch.full((args.batch,), args.width, dtype=torch.int64)
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+
+        def run(autocast):
+            with torch.autocast('cuda', dtype=torch.bfloat16, enabled=autocast):
+                o, olens = TP.recognition_forward(x_dev, lens, w, hp)
+            o = o.transpose(1, 2).cpu().float().numpy()                     # pred.py:138: full-logit D2H
+            return [TP.greedy_decoder(seq[:, :int(n)]) for seq, n in zip(o, olens)]
+        for name, ac in (('fp32', False), ('bf16_autocast', True)):
+            run(ac)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                run(ac)
+            torch.cuda.synchronize(dev)
+            dt = (time.perf_counter() - t0) / reps
+            out[name] = dict(value=args.batch / dt, unit='lines/s', ms_per_pass=1e3 * dt)
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        out['what'] = (f'oracle/torch_port.py (the reference\'s ATen operator sequence) on this GPU, eager, batch {args.batch}, full-logit '
+                       f'D2H + host greedy decode as pred.py:138-143 does; {reps} passes after 1 warm-up')
+    except Exception as e:                                                   # an OOM of the O(T^2) fp32 scores is a result too
+        out['error'] = f'{type(e).__name__}: {str(e)[:200]}'
+        torch.cuda.empty_cache()
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -185,10 +290,8 @@ def run_ours(args):
     json_fd = None
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION', 'INFO'):
-            os.environ['NCCL_DEBUG'] = 'WARN'
-        # NCCL prints its version banner on the process's stdout from C (whatever NCCL_DEBUG says on some boxes); this
-        # script's stdout carries ONE JSON line, so file descriptor 1 points at stderr until that line is written
+        # NCCL prints its banner / INFO lines on the process's stdout from C; this script's stdout carries ONE JSON line, so
+        # file descriptor 1 points at stderr until that line is written (NCCL_DEBUG is left as the caller set it)
         sys.stdout.flush()
         json_fd = os.dup(1)
         os.dup2(2, 1)
@@ -198,14 +301,15 @@ def run_ours(args):
     torch.cuda.set_device(dev)
 
     hp = arch_hp(hparams())
-    B, W, C = args.batch, args.width, args.classes
-    T = (((W - 1) // 2 + 1) - 1) // 2 + 1
+    B, W, C, P = args.batch, args.width, args.classes, args.passes
+    T = out_frames(W)
     eng = Engine(height=hp['height'], encoder_dim=hp['encoder_dim'], num_layers=hp['num_encoder_layers'],
                  num_heads=hp['num_attention_heads'], ff_expansion=hp['feed_forward_expansion_factor'],
                  conv_expansion=hp['conv_expansion_factor'], conv_kernel_size=hp['conv_kernel_size'],
                  half_step_residual=hp['half_step_residual'], subsampling_conv_channels=hp['subsampling_conv_channels'],
                  subsampling_factor=hp['subsampling_factor'], num_classes=C, device=dev, precision=args.precision)
-    eng.load_state_dict(S.make_weights(hp, C, seed=0))
+    weights = S.make_weights(hp, C, seed=0)
+    eng.load_state_dict(weights)
 
     # synthetic lines: every rank its own shard (seeded by rank); inputs resident in HBM for `value`
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -213,16 +317,23 @@ def run_ours(args):
     widths = torch.full((B,), W, dtype=torch.int32)
     x_view = x_dev.squeeze(1).transpose(1, 2)
     in_bytes = x_dev.numel() * 4
+    n_pass = args.steps * P                                            # passes inside a timed region
+    lines_total = world * B * n_pass
 
-    def step():
-        res = eng.forward_decode(x_view, widths)
+    # the shard's decoded records [count | labels] per line, kept on the device until the exchange step
+    shard = torch.zeros((n_pass, B, T + 1), dtype=torch.int32, device=dev)
+    gathered = torch.empty((world,) + tuple(shard.shape), dtype=torch.int32, device=dev) if world > 1 else None
+    gathered_host = torch.empty((world,) + tuple(shard.shape), dtype=torch.int32).pin_memory() if world > 1 else None
+
+    def keep(i, res):
+        shard[i, :, 0].copy_(res['counts'])
+        shard[i, :, 1:].copy_(res['labels'])
+
+    def exchange():
+        """the path's one exchange step: all ranks receive the records of every shard, once per shard"""
         if world > 1:
-            # the path's one exchange step: gather the collapsed label records of every shard (NCCL/NVLink)
-            packed = torch.cat([res['counts'].view(B, 1), res['labels']], dim=1)
-            out = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=dev)
-            dist.all_gather_into_tensor(out, packed)
-            return out
-        return res
+            dist.all_gather_into_tensor(gathered, shard)
+            gathered_host.copy_(gathered, non_blocking=True)
 
     def fence():
         torch.cuda.synchronize(dev)
@@ -230,8 +341,9 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
-        step()
+    for i in range(args.warmup * P):
+        keep(i % n_pass, eng.forward_decode(x_view, widths))
+    exchange()
     fence()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -241,85 +353,116 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fence()
     e0.record()
-    for _ in range(args.steps):
-        step()
+    for i in range(n_pass):
+        keep(i, eng.forward_decode(x_view, widths))
+    exchange()
     e1.record()
     fence()
     ms_total = e0.elapsed_time(e1)
     launches = eng.launch_count - launches0
-    if sampler:
-        time.sleep(0.2)
-        sampler.stop()
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    lines_per_s = world * B * args.steps / (ms_total * 1e-3)
+    lines_per_s = lines_total / (ms_total * 1e-3)
 
     # ---- end to end through the host-buffer entry point (H2D + D2H inside the timed region) ----
     e2e = None
     if not args.no_e2e:
-        # two pinned host batches alternate through the handle's two slots: the H2D copy of step i+1 runs on the copy
-        # stream while step i computes; every step's input crosses PCIe and every step's records come back to the host
+        # two pinned host batches alternate through the handle's two slots: the H2D copy of pass i+1 runs on the copy
+        # stream while pass i computes; every pass's input crosses PCIe and every pass's records come back to the host.
+        # At N > 1 the device copy of the records also goes into the shard buffer and is gathered once, inside the region.
+        def host_loop(hosts):
+            for sl in (0, 1):                               # warm both slots (their buffers are allocated on first use)
+                eng.recognize_host_begin(sl, hosts[sl], widths)
+            eng.recognize_host_end(0); eng.recognize_host_end(1)
+            fence()
+            t0 = time.perf_counter()
+            pending = []
+            r = None
+
+            def finish(j, sl):
+                rr = eng.recognize_host_end(sl)
+                if world > 1:
+                    keep(j, eng.slot_records(sl))          # D2D on the compute stream, ahead of the slot's next pass
+                return rr
+            for i in range(n_pass):
+                slot = i & 1
+                if len(pending) == 2:
+                    r = finish(*pending.pop(0))
+                eng.recognize_host_begin(slot, hosts[slot], widths)
+                pending.append((i, slot))
+            while pending:
+                r = finish(*pending.pop(0))
+            exchange()
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            assert int(r['counts'].sum()) >= 0
+            return float(tt.item())
         x_hosts = [torch.empty((B, 1, hp['height'], W), dtype=torch.float32).pin_memory() for _ in range(2)]
         for xh in x_hosts:
             xh.copy_(x_dev)
-        for _ in range(2):                                  # warm both slots (their buffers are allocated on first use)
-            eng.recognize_host_begin(0, x_hosts[0], widths)
-            eng.recognize_host_begin(1, x_hosts[1], widths)
-            eng.recognize_host_end(0)
-            eng.recognize_host_end(1)
-        fence()
-        t0 = time.perf_counter()
-        pending = None
-        for i in range(args.steps):
-            slot = i & 1
-            eng.recognize_host_begin(slot, x_hosts[slot], widths)
-            if pending is not None:
-                r = eng.recognize_host_end(pending)
-            pending = slot
-        r = eng.recognize_host_end(pending)
-        torch.cuda.synchronize(dev)
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
+        dt = host_loop(x_hosts)
         d2h = 4 * (4 * B * T + 2 * B)
-        e2e = dict(value=world * B * args.steps / dt, unit='lines/s', h2d_bytes_per_step=in_bytes + 4 * B,
-                   d2h_bytes_per_step=d2h, ms_per_step=1e3 * dt / args.steps,
+        gather_bytes = (world * shard.numel() * 4) if world > 1 else 0
+        e2e = dict(value=lines_total / dt, unit='lines/s', h2d_bytes_per_step=P * (in_bytes + 4 * B),
+                   d2h_bytes_per_step=P * d2h + gather_bytes // args.steps, ms_per_step=1e3 * dt / args.steps,
                    api='Engine.recognize_host_begin/_end -> cocr_recognize_host_begin/_end (pinned fp32 (N,1,H,W) in, decoded '
-                       'records out; two slots, H2D of step i+1 overlaps the forward pass of step i)')
-        assert int(r['counts'].sum()) >= 0
-        # the same loop on raw 8-bit pixels (SURVEY §8f rank 2; an extension of the reference interface, reported beside
+                       'records out; two slots, H2D of pass i+1 overlaps the forward pass of pass i)'
+                       + ('; records of the whole shard all-gathered over NCCL and copied to every rank\'s host inside the timed region'
+                          if world > 1 else ''))
+        del x_hosts
+        # the same loop on raw 8-bit pixels (SURVEY 8f rank 2; an extension of the reference interface, reported beside
         # the like-for-like fp32 number, never instead of it): a quarter of the bytes cross PCIe
         if args.precision == 'bf16':
             u_hosts = [torch.empty((B, 1, hp['height'], W), dtype=torch.uint8).pin_memory() for _ in range(2)]
             for uh in u_hosts:
                 uh.copy_((x_dev * 255).round().clamp_(0, 255).to(torch.uint8))
-            for sl in (0, 1):
-                eng.recognize_host_begin(sl, u_hosts[sl], widths)
-            eng.recognize_host_end(0); eng.recognize_host_end(1)
-            fence()
-            t0 = time.perf_counter()
-            pending = None
-            for i in range(args.steps):
-                slot = i & 1
-                eng.recognize_host_begin(slot, u_hosts[slot], widths)
-                if pending is not None:
-                    eng.recognize_host_end(pending)
-                pending = slot
-            eng.recognize_host_end(pending)
-            torch.cuda.synchronize(dev)
-            dtu = time.perf_counter() - t0
-            tt = torch.tensor([dtu], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e['uint8_input'] = dict(value=world * B * args.steps / float(tt.item()), unit='lines/s',
-                                      h2d_bytes_per_step=in_bytes // 4 + 4 * B, d2h_bytes_per_step=d2h)
+            dtu = host_loop(u_hosts)
+            e2e['uint8_input'] = dict(value=lines_total / dtu, unit='lines/s', h2d_bytes_per_step=P * (in_bytes // 4 + 4 * B),
+                                      d2h_bytes_per_step=e2e['d2h_bytes_per_step'])
+            del u_hosts
 
-    # ---- per-kernel CUDA-event timing for the roofline of the dominant kernel (rank 0) ----
+    if sampler:
+        time.sleep(0.2)
+        sampler.stop()
+
+    # ---- the drop-in API: PytorchRecognitionModel.predict_string_stream, pinned host batches -> Python strings ----
+    e2e_api = None
+    if not args.no_e2e and rank == 0:
+        from conformer_ocr_b200 import PytorchRecognitionModel
+        from conformer_ocr_b200.codec import LabelCodec
+        kw = dict(input_dropout_p=0.1, feed_forward_dropout_p=0.1, attention_dropout_p=0.1, conv_dropout_p=0.1)
+        codec = LabelCodec([chr(0x4E00 + i) for i in range(C - 1)])
+        net = PytorchRecognitionModel(num_classes=C, codec=codec, precision=args.precision, **hp, **kw)
+        net.nn.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()}, strict=False)
+        net = net.to(dev)
+        hosts = [torch.empty((B, 1, hp['height'], W), dtype=torch.float32).pin_memory() for _ in range(2)]
+        for xh in hosts:
+            xh.copy_(x_dev)
+
+        def batches(n):
+            for i in range(n):
+                yield hosts[i & 1], widths
+        for _ in net.predict_string_stream(batches(4)):
+            pass
+        torch.cuda.synchronize(dev)
+        n_api = max(2, min(n_pass, 64))
+        t0 = time.perf_counter()
+        chars = 0
+        for strings in net.predict_string_stream(batches(n_api)):
+            chars += sum(len(s) for s in strings)
+        dt = time.perf_counter() - t0
+        e2e_api = dict(value=B * n_api / dt, unit='lines/s', passes=n_api, chars_decoded=chars,
+                       api='PytorchRecognitionModel.predict_string_stream (pinned host batches -> Python strings; LabelCodec LUT)',
+                       note='rank 0 only')
+        del net, hosts
+
+    # ---- per-kernel CUDA-event timing (rank 0): the roofline of every family against SURVEY 8(d)'s algorithmic work ----
     roofline = None
     families = {}
     if rank == 0 and args.profile_steps > 0:
@@ -331,37 +474,65 @@ def run_ours(args):
         buf = Ct.create_string_buffer(1 << 16)
         lib.cocr_profile_report(h, buf, len(buf))
         lib.cocr_set_profiling(h, 0)
+        peaks = load_peaks()
+        algo = algorithmic_work(hp, B, W, C)
+        traffic = {}
+        tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+        if os.path.exists(tpath) and (B, W) == (256, 1536):                  # the captures are of this workload
+            with open(tpath) as fp:
+                traffic = json.load(fp)
+        step_ms = 0.0
         for line in buf.value.decode().splitlines():
             name, n, ms, fl, by = line.split()
-            families[name] = dict(launches=int(n) // args.profile_steps, ms_per_step=float(ms) / args.profile_steps,
-                                  flops_per_step=float(fl) / args.profile_steps, bytes_per_step=float(by) / args.profile_steps)
-        peaks = load_peaks()
-        if families:
-            top = max(families, key=lambda k: families[k]['ms_per_step'])
-            f = families[top]
-            per_launch_ms = f['ms_per_step'] / max(f['launches'], 1)
-            tensor_bound = f['flops_per_step'] > 0 and (f['flops_per_step'] / max(f['bytes_per_step'], 1.0)) > (
-                peaks['tflops_sustained'] * 1e12 / (peaks['hbm_gbs'] * 1e9))
-            if tensor_bound:
-                ach = f['flops_per_step'] / (f['ms_per_step'] * 1e-3) / 1e12
-                roofline = dict(kernel=top, bound='tensor', achieved=ach, peak=peaks['tflops_sustained'], unit='TFLOP/s',
-                                frac=ach / peaks['tflops_sustained'], traffic=None)
-            else:
-                ach = f['bytes_per_step'] / (f['ms_per_step'] * 1e-3) / 1e9
-                roofline = dict(kernel=top, bound='hbm', achieved=ach, peak=peaks['hbm_gbs'], unit='GB/s',
-                                frac=ach / peaks['hbm_gbs'], traffic=None)
-            tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
-            if os.path.exists(tpath):
-                with open(tpath) as fp:
-                    tr = json.load(fp).get(top)
-                if tr and (args.batch, args.width) == (256, 1536):      # the capture is of this workload
-                    roofline['traffic'] = tr['dram_bytes_per_launch']
-                    roofline['traffic_source'] = tr['source']
-                    roofline['algorithmic_bytes_per_launch'] = f['bytes_per_step'] / max(f['launches'], 1)
-            roofline.update(peak_source=peaks['source'] + (' (sustained bf16 cuBLAS)' if tensor_bound else ' (copy)'),
-                            launches_per_step=f['launches'], avg_launch_ms=per_launch_ms,
-                            share_of_step=f['ms_per_step'] / max(sum(v['ms_per_step'] for v in families.values()), 1e-9),
-                            how=f'CUDA events around every launch of the family over {args.profile_steps} extra steps')
+            n_l = int(n) // args.profile_steps
+            ms_p = float(ms) / args.profile_steps
+            step_ms += ms_p
+            f = dict(launches=n_l, ms_per_pass=ms_p, avg_launch_ms=ms_p / max(n_l, 1))
+            a = algo.get(name)
+            if a:
+                # `a` is one launch's algorithmic work over the whole (B, W) batch
+                f['bound'] = a['bound']
+                f['algorithmic_flops_per_launch'] = a['flops']
+                f['algorithmic_bytes_per_launch'] = a['bytes']
+                sec = f['avg_launch_ms'] * 1e-3
+                if a['bound'] == 'tensor':
+                    f['achieved'] = a['flops'] / sec / 1e12
+                    f['unit'] = 'TFLOP/s'
+                    f['peak'] = peaks['tflops_sustained']
+                else:
+                    f['achieved'] = a['bytes'] / sec / 1e9
+                    f['unit'] = 'GB/s'
+                    f['peak'] = peaks['hbm_gbs']
+                f['frac'] = f['achieved'] / f['peak']
+                f['hbm_frac_of_algorithmic_bytes'] = a['bytes'] / sec / 1e9 / peaks['hbm_gbs']
+                tr = traffic.get(name)
+                if tr:
+                    f['traffic'] = tr['dram_bytes_per_launch']
+                    f['traffic_over_algorithmic'] = tr['dram_bytes_per_launch'] / a['bytes']
+                    f['traffic_source'] = tr['source']
+            f['as_launched_flops_per_launch'] = float(fl) / max(int(n), 1)
+            f['as_launched_bytes_per_launch'] = float(by) / max(int(n), 1)
+            families[name] = f
+        for f in families.values():
+            f['share_of_pass'] = f['ms_per_pass'] / max(step_ms, 1e-9)
+        rated = {k: v for k, v in families.items() if 'frac' in v}
+        if rated:
+            top = max(rated, key=lambda k: rated[k]['ms_per_pass'])
+            f = rated[top]
+            roofline = dict(kernel=top, bound=f['bound'], achieved=f['achieved'], peak=f['peak'], unit=f['unit'], frac=f['frac'],
+                            traffic=f.get('traffic'), traffic_over_algorithmic=f.get('traffic_over_algorithmic'),
+                            traffic_source=f.get('traffic_source'),
+                            algorithmic_flops_per_launch=f['algorithmic_flops_per_launch'],
+                            algorithmic_bytes_per_launch=f['algorithmic_bytes_per_launch'],
+                            peak_source=peaks['source'] + (' (sustained bf16 cuBLAS: the kernel is timed inside a long step)'
+                                                           if f['bound'] == 'tensor' else ' (copy)'),
+                            launches_per_pass=f['launches'], avg_launch_ms=f['avg_launch_ms'], share_of_pass=f['share_of_pass'],
+                            how=f'dominant kernel family by CUDA-event time (events around every launch over {args.profile_steps} extra '
+                                'passes); algorithmic FLOPs / bytes per SURVEY.md 8(d), not the launch\'s padded operands')
+
+    eager = None
+    if rank == 0 and not args.no_eager_baseline:
+        eager = gpu_eager_baseline(args, hp, dev, x_dev)
 
     if rank != 0:
         if world > 1:
@@ -369,34 +540,38 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # whole-step roofline against the tensor-core peak (SURVEY.md §8d algorithmic FLOPs per line)
+    # whole-step roofline against the tensor-core peak (SURVEY.md 8d algorithmic FLOPs per line)
     peaks = load_peaks()
     fl_line = S.flops_per_line(W, C, hp)
-    step_tflops = fl_line * B / (ms_step * 1e-3) / 1e12
+    step_tflops = fl_line * B * P / (ms_step * 1e-3) / 1e12
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
         n, cores, times = time_cpu(args, reps=3, warm=1)
         v = n * len(times) / sum(times)
         cpu_baseline = dict(value=v, unit='lines/s', cores=cores, kind='port',
-                            sample=f'{n} lines of 96x{W} px x {len(times)} passes, fp32, oracle/torch_port.py (the reference\'s '
-                                   f'ATen CPU operator sequence), {cores} threads')
+                            sample=f'{n} lines of 96x{W} px x {len(times)} passes, fp32, oracle/torch_port.py, {cores} threads',
+                            note=CPU_NOTE)
 
     clocks = sampler.summary() if sampler else dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
     out = dict(metric='text lines/sec', value=lines_per_s, unit='lines/s', n_gpus=world, steps=args.steps,
-               warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling='weak', vs_baseline=None,
-               dtype='bf16' if args.precision == 'bf16' else 'f32', data='synthetic',
+               warmup=args.warmup, ms_per_step=ms_step, ms_per_pass=ms_step / P, higher_is_better=True, scaling='weak',
+               vs_baseline=None, dtype='bf16' if args.precision == 'bf16' else 'f32', data='synthetic',
                frames_per_s=lines_per_s * T,
-               config=dict(workload=workload_name(args), lines_per_gpu=B, width_px=W, frames_per_line=T, classes=C,
-                           parallelism=f'dp{world} (lines sharded, decoded records all-gathered over NCCL)' if world > 1 else 'single GPU',
-                           l2='input batch is %.0f MB > 126 MB L2; no explicit flush' % (in_bytes / 1e6),
+               config=dict(workload=workload_name(args), lines_per_pass_per_gpu=B, passes_per_step=P, lines_per_step_per_gpu=B * P,
+                           lines_in_timed_region=lines_total, width_px=W, frames_per_line=T, classes=C,
+                           parallelism=(f'dp{world}: lines sharded, no data-path collective; the [count | labels] records of the whole timed '
+                                        f'region ({lines_total} lines) are all-gathered over NCCL once, inside the timed region')
+                           if world > 1 else 'single GPU',
+                           l2='input batch is %.0f MB > 126 MB L2; no explicit flush' % (in_bytes / 1e6) if in_bytes > 126e6 else
+                              'workspace of a pass (activations of 16 layers) exceeds the 126 MB L2; no explicit flush',
                            mask_mode='reference_unmasked'),
-               clocks=clocks, e2e=e2e, gpu_launches=launches,
+               clocks=clocks, e2e=e2e, e2e_api=e2e_api, gpu_launches=launches,
                roofline=roofline,
                roofline_step=dict(bound='tensor', achieved=step_tflops, peak=peaks['tflops_sustained'], unit='TFLOP/s',
-                                  frac=step_tflops / peaks['tflops_sustained'], gflop_per_line=fl_line / 1e9,
-                                  peak_source=peaks['source'] + ' (sustained bf16 cuBLAS)'),
-               kernel_families=families, cpu_baseline=cpu_baseline)
+                                  frac=step_tflops / peaks['tflops_sustained'], frac_of_burst=step_tflops / peaks['tflops_burst'],
+                                  gflop_per_line=fl_line / 1e9, peak_source=peaks['source'] + ' (sustained bf16 cuBLAS)'),
+               kernel_families=families, gpu_eager_baseline=eager, cpu_baseline=cpu_baseline)
     if json_fd is not None:
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(out) + '\n').encode())

@@ -99,7 +99,18 @@ class EngineOwner(nn.Module):
         self.mask_mode = mask_mode
         self._engine: Optional[Engine] = None
         self._engine_key = None
-        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_engine())
+        # `net.nn.load_state_dict(weights)` is the reference idiom (pred.py:193): torch runs the post hooks of the module
+        # load_state_dict was called on and of its descendants only, so the hook sits on every sub-module, not just on
+        # the owner.  Called after the parameter tree is complete.
+        import weakref
+        owner = weakref.ref(self)
+
+        def _invalidate(module, incompatible):
+            o = owner()
+            if o is not None:
+                o.invalidate_engine()
+        for m in self.modules():
+            m.register_load_state_dict_post_hook(_invalidate)
 
     def invalidate_engine(self):
         """Call after editing parameters in place; the next forward re-uploads the weights."""

@@ -438,45 +438,43 @@ int cocr_greedy_decode(cocr_handle *h, const float *logits, const int32_t *lens,
     return rc;
 }
 
-int cocr_forward_decode(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths,
-                        int32_t B, int32_t W, void *stream, int32_t *labels, int32_t *starts, int32_t *ends, float *conf,
-                        int32_t *counts, int32_t *out_lens) {
+static int forward_decode_any(cocr_handle *h, const void *img, bool u8, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths,
+                              int32_t B, int32_t W, void *stream, int32_t *labels, int32_t *starts, int32_t *ends, float *conf,
+                              int32_t *counts, int32_t *out_lens) {
     COCR_TRY(check_call(h, img, B, W));
     if (!labels || !starts || !ends || !conf || !counts || !out_lens)
         return set_error(h, COCR_ERR_BAD_ARG, "cocr_forward_decode: null output");
     if (h->dm.C <= 0) return set_error(h, COCR_ERR_STATE, "handle was created without a decoder (num_classes = 0)");
     cudaStream_t st = (cudaStream_t)stream;
     if (h->hp.precision == COCR_BF16)
-        return bf16_forward_decode(h, img, sb, sw, sh, widths, B, W, st, labels, starts, ends, conf, counts, out_lens);
+        return bf16_forward_decode(h, img, u8, sb, sw, sh, widths, B, W, st, labels, starts, ends, conf, counts, out_lens);
+    if (u8) return set_error(h, COCR_ERR_UNSUPPORTED, "uint8 input is implemented on the bf16 path only");
     // fp32: logits go through the `h` scratch tile by tile would save memory; they fit the workspace for the
     // parity-sized batches this path serves, so project into a dedicated block behind the plan.
+    const float *imgf = static_cast<const float *>(img);
     Fp32Plan p;
     fp32_plan(h, B, W, &p);
     size_t logits_off = p.total;
     size_t total = logits_off + (size_t)p.M * h->dm.C * sizeof(float);
     COCR_TRY(ensure_workspace(h, total));
-    COCR_TRY(fp32_encode(h, img, sb, sw, sh, widths, B, W, st, nullptr, out_lens));
+    COCR_TRY(fp32_encode(h, imgf, sb, sw, sh, widths, B, W, st, nullptr, out_lens));
     float *logits = (float *)(h->ws.base + logits_off);
     COCR_TRY(fp32_logits(h, (const float *)(h->ws.base + p.off_x), p.M, st, logits));
     return launch_greedy_decode(h, logits, out_lens, B, p.T, h->dm.C, st, (float *)(h->ws.base + p.off_best_val),
                                 (int32_t *)(h->ws.base + p.off_best_idx), labels, starts, ends, conf, counts);
 }
 
-namespace {
-struct U8Scope {                      // marks the handle's current image pointer as uint8 for one call
-    cocr_handle *h;
-    explicit U8Scope(cocr_handle *h_) : h(h_) { if (h) h->img_u8 = true; }
-    ~U8Scope() { if (h) h->img_u8 = false; }
-};
-}  // namespace
+int cocr_forward_decode(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths,
+                        int32_t B, int32_t W, void *stream, int32_t *labels, int32_t *starts, int32_t *ends, float *conf,
+                        int32_t *counts, int32_t *out_lens) {
+    return forward_decode_any(h, img, false, sb, sw, sh, widths, B, W, stream, labels, starts, ends, conf, counts, out_lens);
+}
 
 int cocr_forward_decode_u8(cocr_handle *h, const uint8_t *img, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths,
                            int32_t B, int32_t W, void *stream, int32_t *labels, int32_t *starts, int32_t *ends, float *conf,
                            int32_t *counts, int32_t *out_lens) {
     if (h && h->hp.precision != COCR_BF16) return set_error(h, COCR_ERR_UNSUPPORTED, "uint8 input is implemented on the bf16 path only");
-    U8Scope scope(h);
-    return cocr_forward_decode(h, reinterpret_cast<const float *>(img), sb, sw, sh, widths, B, W, stream, labels, starts, ends, conf,
-                               counts, out_lens);
+    return forward_decode_any(h, img, true, sb, sw, sh, widths, B, W, stream, labels, starts, ends, conf, counts, out_lens);
 }
 
 static int host_begin(cocr_handle *h, int32_t slot, const void *img_host, size_t pix_bytes, const int32_t *widths_host, int32_t B, int32_t W,
@@ -500,7 +498,7 @@ static int host_begin(cocr_handle *h, int32_t slot, const void *img_host, size_t
         if (sl.img) { COCR_CUDA(h, cudaDeviceSynchronize()); COCR_CUDA(h, cudaFree(sl.img)); sl.img = nullptr; sl.img_bytes = 0; }
         void *p = nullptr;
         COCR_CUDA(h, cudaMalloc(&p, img_bytes));
-        sl.img = (float *)p;
+        sl.img = p;
         sl.img_bytes = img_bytes;
     }
     if ((size_t)B > sl.widths_n) {
@@ -536,11 +534,7 @@ static int host_begin(cocr_handle *h, int32_t slot, const void *img_host, size_t
     int32_t *d_lab = (int32_t *)sl.res, *d_st = d_lab + bt, *d_en = d_st + bt;
     float *d_cf = (float *)(d_en + bt);
     int32_t *d_cnt = (int32_t *)(d_cf + bt), *d_len = d_cnt + B;
-    if (pix_bytes == 1)
-        COCR_TRY(cocr_forward_decode_u8(h, reinterpret_cast<const uint8_t *>(sl.img), (int64_t)H * W, 1, W, wd, B, W, stream, d_lab, d_st, d_en,
-                                        d_cf, d_cnt, d_len));
-    else
-        COCR_TRY(cocr_forward_decode(h, sl.img, (int64_t)H * W, 1, W, wd, B, W, stream, d_lab, d_st, d_en, d_cf, d_cnt, d_len));
+    COCR_TRY(forward_decode_any(h, sl.img, pix_bytes == 1, (int64_t)H * W, 1, W, wd, B, W, stream, d_lab, d_st, d_en, d_cf, d_cnt, d_len));
     // the records leave on their own stream: the forward pass of the other slot, already queued on `stream`, starts at once
     COCR_CUDA(h, cudaEventRecord(sl.fwd_done, st));
     COCR_CUDA(h, cudaStreamWaitEvent(h->d2h_stream, sl.fwd_done, 0));
@@ -590,6 +584,18 @@ int cocr_recognize_host(cocr_handle *h, const float *img_host, const int32_t *wi
     const int slot = (h && h->slots[0].busy) ? 1 : 0;
     COCR_TRY(cocr_recognize_host_begin(h, slot, img_host, widths_host, B, W, stream));
     return cocr_recognize_host_end(h, slot, labels, starts, ends, conf, counts, out_lens);
+}
+
+int cocr_slot_records_dev(cocr_handle *h, int32_t slot, void **records_dev, size_t *bytes, int32_t *B, int32_t *T) {
+    if (!h) return COCR_ERR_BAD_ARG;
+    if (slot < 0 || slot > 1 || !records_dev || !bytes) return set_error(h, COCR_ERR_BAD_ARG, "cocr_slot_records_dev: bad argument");
+    cocr_handle::HostSlot &sl = h->slots[slot];
+    if (!sl.res || sl.B < 1) return set_error(h, COCR_ERR_STATE, "cocr_slot_records_dev: slot %d has not held a batch", slot);
+    *records_dev = sl.res;
+    *bytes = 4 * (4 * (size_t)sl.B * sl.T + 2 * (size_t)sl.B);
+    if (B) *B = sl.B;
+    if (T) *T = sl.T;
+    return COCR_OK;
 }
 
 int cocr_workspace_bytes(cocr_handle *h, int32_t B, int32_t W, size_t *bytes) {

@@ -17,12 +17,13 @@ namespace cocr {
 
 typedef __nv_bfloat16 bf16;
 
-struct LayerGraph {      // captured encoder-layer sequence for one (batch, frames, mask, buffers) combination
-    int B, T;
+struct LayerGraph {      // captured encoder-layer sequence for one (batch, width, mask, buffers) combination
+    int B, T, T2;        // T2 (frames after the first conv) fixes the workspace offsets: widths that share T may differ in T2
     const void *lens, *ws, *etab, *pos;
     cudaGraphExec_t exec;
     int64_t launches;
     int state;           // 1 seen once (ran eagerly), 2 captured, -1 capture failed: always eager
+    uint64_t last_use;   // LRU stamp
 };
 
 struct Bf16State {
@@ -48,6 +49,7 @@ struct Bf16State {
     float *dw_taps = nullptr;     // (L, K*d + d): depthwise taps [k][pair](2) * bn_scale / 2, then bn_shift / 2
     int tab_T = 0;
     std::vector<LayerGraph> graphs;
+    uint64_t graph_clock = 0;
     cudaStream_t gstream = nullptr;
     cudaEvent_t g_in = nullptr, g_out = nullptr;
 };
@@ -551,7 +553,10 @@ static int pack_attention(cocr_handle *h) {
 // omega_m and the shared key-side table E(t) for a batch whose lines have T frames (embedding.py:42-47 angles)
 static int ensure_tables(cocr_handle *h, int T, cudaStream_t st) {
     Bf16State *bs = h->bf;
-    if (bs->tab_T == T) return COCR_OK;
+    // E(t) rows do not depend on the batch: the table only grows (a shorter batch reads a prefix through its tensor map),
+    // so batches of mixed widths neither stall on a device synchronise nor invalidate captured graphs
+    if (bs->tab_T >= T) return COCR_OK;
+    if (bs->tab_T > 0 && T < 2 * bs->tab_T) T = std::min(2 * bs->tab_T, 8192);       // amortise regrowth
     const int d = h->dm.d, np = d / 2, ecols = d - 16;
     if (bs->etab) { COCR_CUDA(h, cudaDeviceSynchronize()); cudaFree(bs->omega); cudaFree(bs->etab); bs->omega = nullptr; bs->etab = nullptr; }
     std::vector<float> om(np);
@@ -864,7 +869,7 @@ void bf16_destroy(cocr_handle *h) {
 static inline const bf16 *WB(const cocr_handle *h, const float *w) { return h->bf->arena + (w - h->arena); }
 
 // encoder forward; leaves x (fp32) and xn = bf16(x) in the workspace
-static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths, int B,
+static int bf16_forward(cocr_handle *h, const void *img_any, bool u8, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths, int B,
                         int W, cudaStream_t st, int32_t *out_lens, Bf16Plan &p) {
     const Dims &dm = h->dm;
     bf16_plan(h, B, W, &p);
@@ -873,6 +878,7 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
     if (tc_attn) COCR_TRY(ensure_tables(h, p.T, st));
     else COCR_TRY(ensure_pos_proj(h, p.T, st));
     char *ws = h->ws.base;
+    const float *img = static_cast<const float *>(img_any);        // only dereferenced as fp32 when !u8
     float *a1 = (float *)(ws + p.off_a1), *a2 = (float *)(ws + p.off_a2);
     bf16 *feat = (bf16 *)(ws + p.off_feat);
     float *x = (float *)(ws + p.off_x);
@@ -897,8 +903,8 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
     // conv1 + depthwise conv on CUDA cores -> a2 (M*F, [hi | lo] 2x32) bf16, then the 1x1 conv + ReLU as a K = 64
     // tensor-core GEMM whose (M*F, 32) output IS the (M, F*32) feature matrix of the 768 -> 144 projection
     bf16 *a2hl = (bf16 *)a2;                                       // (M*F, 2 cc) bf16 = the fp32 a2 region of the plan
-    int rc_fe = getenv("COCR_FRONTEND_V1") ? COCR_ERR_UNSUPPORTED : launch_frontend_convs2(h, img, sb, sw, sh, B, W, a2hl, st);
-    if (rc_fe == COCR_ERR_UNSUPPORTED && h->img_u8)
+    int rc_fe = getenv("COCR_FRONTEND_V1") ? COCR_ERR_UNSUPPORTED : launch_frontend_convs2(h, img_any, u8, sb, sw, sh, B, W, a2hl, st);
+    if (rc_fe == COCR_ERR_UNSUPPORTED && u8)
         return set_error(h, COCR_ERR_UNSUPPORTED, "uint8 input is implemented by the fused front-end only (subsampling_conv_channels = 32)");
     if (rc_fe == COCR_OK) {
         rc_fe = launch_gemm_tc(h, EPI_BF16, a2hl, 2 * dm.cc, h->bf->w_fe_pw2, 2 * dm.cc, h->sub_bpw, feat, dm.cc, nullptr, M * dm.F, dm.cc,
@@ -1022,13 +1028,18 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
     if (!use_graph) return run_layers();
     LayerGraph *lg = nullptr;
     for (LayerGraph &e : bs->graphs)
-        if (e.B == B && e.T == p.T && e.lens == (const void *)lens_dev && e.ws == ws && e.etab == (const void *)bs->etab && e.pos == (const void *)h->pos_proj) lg = &e;
+        if (e.B == B && e.T == p.T && e.T2 == p.T2 && e.lens == (const void *)lens_dev && e.ws == ws && e.etab == (const void *)bs->etab &&
+            e.pos == (const void *)h->pos_proj) lg = &e;
+    if (lg) lg->last_use = ++bs->graph_clock;
     if (!lg) {
-        if (bs->graphs.size() >= 16) {                        // shapes keep changing: do not hoard graphs
-            for (LayerGraph &e : bs->graphs) if (e.exec) cudaGraphExecDestroy(e.exec);
-            bs->graphs.clear();
+        if (bs->graphs.size() >= 16) {                        // shapes keep changing: evict the least recently used graph
+            size_t victim = 0;
+            for (size_t i = 1; i < bs->graphs.size(); ++i)
+                if (bs->graphs[i].last_use < bs->graphs[victim].last_use) victim = i;
+            if (bs->graphs[victim].exec) cudaGraphExecDestroy(bs->graphs[victim].exec);
+            bs->graphs.erase(bs->graphs.begin() + (long)victim);
         }
-        bs->graphs.push_back({B, p.T, (const void *)lens_dev, ws, (const void *)bs->etab, (const void *)h->pos_proj, nullptr, 0, 1});
+        bs->graphs.push_back({B, p.T, p.T2, (const void *)lens_dev, ws, (const void *)bs->etab, (const void *)h->pos_proj, nullptr, 0, 1, ++bs->graph_clock});
         return run_layers();
     }
     if (lg->state < 0) return run_layers();
@@ -1074,7 +1085,7 @@ static int bf16_forward(cocr_handle *h, const float *img, int64_t sb, int64_t sw
 int bf16_encode(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths, int B, int W,
                 cudaStream_t st, float *enc_out, int32_t *out_lens) {
     Bf16Plan p;
-    COCR_TRY(bf16_forward(h, img, sb, sw, sh, widths, B, W, st, out_lens, p));
+    COCR_TRY(bf16_forward(h, img, false, sb, sw, sh, widths, B, W, st, out_lens, p));
     if (resid_fused(h)) {       // the fused residual epilogues keep x in their private layout
         const int64_t n4 = (int64_t)p.M * (h->dm.d / 4);
         k_resid_unpermute<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>((const float *)(h->ws.base + p.off_x), enc_out, p.M, h->dm.d);
@@ -1088,17 +1099,17 @@ int bf16_encode(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_
 int bf16_logits(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths, int B, int W,
                 cudaStream_t st, float *logits, int32_t *out_lens) {
     Bf16Plan p;
-    COCR_TRY(bf16_forward(h, img, sb, sw, sh, widths, B, W, st, out_lens, p));
+    COCR_TRY(bf16_forward(h, img, false, sb, sw, sh, widths, B, W, st, out_lens, p));
     const Dims &dm = h->dm;
     return launch_gemm_tc(h, EPI_F32, (const bf16 *)(h->ws.base + p.off_xn), xn_pitch(h), WB(h, h->dec_w), dm.d, h->dec_b, logits, dm.C,
                           nullptr, p.M, dm.C, dm.d, st, 0, nullptr, "gemm_logits");
 }
 
-int bf16_forward_decode(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths, int B,
+int bf16_forward_decode(cocr_handle *h, const void *img, bool u8, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths, int B,
                         int W, cudaStream_t st, int32_t *labels, int32_t *starts, int32_t *ends, float *conf, int32_t *counts,
                         int32_t *out_lens) {
     Bf16Plan p;
-    COCR_TRY(bf16_forward(h, img, sb, sw, sh, widths, B, W, st, out_lens, p));
+    COCR_TRY(bf16_forward(h, img, u8, sb, sw, sh, widths, B, W, st, out_lens, p));
     const Dims &dm = h->dm;
     char *ws = h->ws.base;
     unsigned long long *best = (unsigned long long *)(ws + p.off_best);

@@ -84,7 +84,7 @@ struct cocr_handle {
     // staging for the *_host entry points: two slots so that the H2D copy of one batch (copy stream) overlaps the
     // forward pass of the previous one
     struct HostSlot {
-        float *img = nullptr;          // device image batch
+        void *img = nullptr;           // device image batch (fp32 or uint8 pixels)
         size_t img_bytes = 0;
         int32_t *widths = nullptr;
         size_t widths_n = 0;
@@ -100,7 +100,6 @@ struct cocr_handle {
 
     std::vector<float> fe_weights;   // conv.0 / conv.2 weights + biases in kernel-parameter order (mem_kernels.cu: FrontendWeights)
     int64_t launches = 0;
-    bool img_u8 = false;             // set for the duration of a *_u8 entry point: the image pointer holds uint8 pixels
     cocr::Bf16State *bf = nullptr;
 
     // optional per-launch event timing (cocr_set_profiling)
@@ -204,7 +203,7 @@ int launch_glu_dw_fast(cocr_handle *h, const __nv_bfloat16 *u, const LayerF32 &l
                        cudaStream_t st);
 int launch_dw_fast(cocr_handle *h, const __nv_bfloat16 *x, const float *taps_dev, const float *hshift_dev, __nv_bfloat16 *g, int B, int T,
                    cudaStream_t st);
-int launch_frontend_convs2(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, int B, int W, __nv_bfloat16 *a2,
+int launch_frontend_convs2(cocr_handle *h, const void *img, bool u8, int64_t sb, int64_t sw, int64_t sh, int B, int W, __nv_bfloat16 *a2,
                            cudaStream_t st);
 int launch_frontend_fused(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, int B, int W,
                           __nv_bfloat16 *feat, cudaStream_t st);
@@ -216,7 +215,8 @@ int bf16_encode(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_
                 int B, int W, cudaStream_t st, float *enc_out, int32_t *out_lens);
 size_t bf16_workspace_bytes(const cocr_handle *h, int B, int W);
 // decode straight from the bf16 path's final activations (fused projection + argmax)
-int bf16_forward_decode(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh,
+// img: fp32 pixels, or uint8 pixels when `u8` (scaled by 1/255 inside the first kernel)
+int bf16_forward_decode(cocr_handle *h, const void *img, bool u8, int64_t sb, int64_t sw, int64_t sh,
                         const int32_t *widths, int B, int W, cudaStream_t st, int32_t *labels, int32_t *starts,
                         int32_t *ends, float *conf, int32_t *counts, int32_t *out_lens);
 int bf16_logits(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths,

@@ -529,8 +529,8 @@ k_frontend_convs2(const PixT *__restrict__ img, int64_t sb, int64_t sw, int64_t 
 
 // conv1 + depthwise conv -> a2 (B*T*F, 64) bf16 [hi | lo]; the caller runs the 1x1 conv as a K = 64 GEMM.  COCR_ERR_UNSUPPORTED when the
 // geometry is not covered.
-int launch_frontend_convs2(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, int B, int W, bf16 *a2, cudaStream_t st) {
-    const bool u8 = h->img_u8;                      // `img` then points at uint8 pixels
+int launch_frontend_convs2(cocr_handle *h, const void *img_any, bool u8, int64_t sb, int64_t sw, int64_t sh, int B, int W, bf16 *a2, cudaStream_t st) {
+    const float *img = static_cast<const float *>(img_any);     // fp32 pixels unless `u8` (then uint8 pixels)
     const Dims &dm = h->dm;
     if (dm.cc != 32 || ((FE2_TT * dm.F) & 31) != 0 || h->fe_weights.size() != sizeof(FrontendWeights) / 4) return COCR_ERR_UNSUPPORTED;
     const int T2 = out_len1(W), T = out_len1(T2);
@@ -548,7 +548,7 @@ int launch_frontend_convs2(cocr_handle *h, const float *img, int64_t sb, int64_t
     dim3 grid((T + FE2_TT - 1) / FE2_TT, B);
     const double n1 = (double)B * T2 * dm.F2 * 32, n2 = (double)B * T * dm.F * 32;
     ProfScope ps(h, "frontend_convs", st, 18.0 * n1 + 18.0 * n2, (u8 ? 1.0 : 4.0) * B * (double)W * dm.H + 2.0 * n2);
-    if (u8) k_frontend_convs2<uint8_t><<<grid, FE2_THREADS, smem, st>>>(reinterpret_cast<const uint8_t *>(img), sb, sw, sh, fw, a2, W, dm.H, T2, T, dm.F2, dm.F);
+    if (u8) k_frontend_convs2<uint8_t><<<grid, FE2_THREADS, smem, st>>>(static_cast<const uint8_t *>(img_any), sb, sw, sh, fw, a2, W, dm.H, T2, T, dm.F2, dm.F);
     else k_frontend_convs2<float><<<grid, FE2_THREADS, smem, st>>>(img, sb, sw, sh, fw, a2, W, dm.H, T2, T, dm.F2, dm.F);
     COCR_LAUNCHED(h);
     return COCR_OK;

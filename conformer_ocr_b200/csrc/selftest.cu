@@ -8,12 +8,6 @@
 namespace cocr {
 int selftest_gemm(int device, int epi, int M, int N, int K, int block_n, double *max_err);
 int selftest_resid(int device, int M, int N, int K, int flags, double *max_err);
-int selftest_mma_bench(int device, int N, int chains, int a_tmem, double *cycles_per_mma);
-int selftest_tmem_bench(int device, int depth, int with_mma, int shape, double *bytes_per_cycle);
-int selftest_mma_contention(int device, int mode, int a_tmem, double *cycles_per_group);
-int selftest_mufu_bench(int device, int kind, double *cycles_per_inst);
-int selftest_attn_mma_bench(int device, int mode, int what, int grid, double *cycles_per_pair);
-int selftest_mbar_pingpong(int device, int mode, double *cycles_per_hop);
 int selftest_ffn(int device, int M, int NC, int flags, double *max_err);
 }
 
@@ -29,11 +23,5 @@ extern "C" int cocr_selftest(int device, int which, int64_t p0, int64_t p1, int6
         return cocr::selftest_resid(device, (int)p0, (int)p1, (int)(p2 % 100000), (int)(p2 / 100000), max_err);
     }
     if (which == 21) return cocr::selftest_ffn(device, (int)p0, (int)p1, (int)p2, max_err);   // fused FFN module: p0 = M, p1 = ff / 96, p2 = flags
-    if (which == 45) return cocr::selftest_mbar_pingpong(device, (int)p0, max_err);   // mbarrier hand-shake latency: cycles per hop
-    if (which == 44) return cocr::selftest_attn_mma_bench(device, (int)p0, (int)p1, (int)p2, max_err);   // attention S + P V MMA sequence: cycles per key tile
-    if (which == 43) return cocr::selftest_mufu_bench(device, (int)p0, max_err);   // MUFU throughput: cycles per warp instruction per scheduler
-    if (which == 42) return cocr::selftest_mma_contention(device, (int)p0, (int)p1, max_err);   // 12-MMA group cycles under TMEM traffic
-    if (which == 41) return cocr::selftest_tmem_bench(device, (int)p0, (int)p1, (int)p2, max_err);   // TMEM read bandwidth: *max_err = bytes per cycle per SM
-    if (which == 40) return cocr::selftest_mma_bench(device, (int)p0, (int)p1, (int)p2, max_err);   // tensor-pipe micro-benchmark: *max_err = cycles per MMA
     return cocr::set_error(nullptr, COCR_ERR_BAD_ARG, "cocr_selftest: unknown test %d", which);
 }

@@ -235,6 +235,25 @@ class Engine:
                                                           p(res['conf']), p(res['counts']), p(res['out_lens'])))
         return res
 
+    def slot_records(self, slot: int) -> Dict[str, torch.Tensor]:
+        """Device views (no copy) of the records of the batch last begun in `slot`: labels/starts/ends (B,T) int32,
+        conf (B,T) fp32, counts/out_lens (B,) int32.  Valid until the slot is begun again; complete after
+        `recognize_host_end(slot)`.  Used to feed the gather of decoded records across GPUs without a host round trip."""
+        ptr, nbytes, B, T = C.c_void_p(), C.c_size_t(), C.c_int32(), C.c_int32()
+        self._check(self._lib.cocr_slot_records_dev(self._h, slot, C.byref(ptr), C.byref(nbytes), C.byref(B), C.byref(T)))
+
+        class _Block:      # __cuda_array_interface__ v2 over library-owned memory
+            pass
+        blk = _Block()
+        blk.__cuda_array_interface__ = dict(shape=(nbytes.value // 4,), typestr='<i4', data=(ptr.value, False), version=2)
+        flat = torch.as_tensor(blk, device=self.device)
+        b, t = B.value, T.value
+        bt = b * t
+        out = dict(labels=flat[:bt].view(b, t), starts=flat[bt:2 * bt].view(b, t), ends=flat[2 * bt:3 * bt].view(b, t),
+                   conf=flat[3 * bt:4 * bt].view(torch.float32).view(b, t), counts=flat[4 * bt:4 * bt + b],
+                   out_lens=flat[4 * bt + b:4 * bt + 2 * b])
+        return out
+
     def workspace_bytes(self, B: int, W: int) -> int:
         n = C.c_size_t()
         self._check(self._lib.cocr_workspace_bytes(self._h, B, W, C.byref(n)))

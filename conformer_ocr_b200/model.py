@@ -13,12 +13,15 @@ from .engine import out_frames
 
 
 class RecognitionModel(EngineOwner):
-    def __init__(self, num_classes: int, height: int = 96, encoder_dim: int = 144, num_encoder_layers: int = 16,
-                 num_attention_heads: int = 4, feed_forward_expansion_factor: int = 4, conv_expansion_factor: int = 2,
+    def __init__(self, num_classes: int, height: int = 96, encoder_dim: int = 512, num_encoder_layers: int = 18,
+                 num_attention_heads: int = 8, feed_forward_expansion_factor: int = 4, conv_expansion_factor: int = 2,
                  input_dropout_p: float = 0.1, feed_forward_dropout_p: float = 0.1, attention_dropout_p: float = 0.1,
-                 conv_dropout_p: float = 0.1, conv_kernel_size: int = 31, half_step_residual: bool = True,
-                 subsampling_conv_channels: int = 32, subsampling_factor: int = 4, precision: str = 'fp32',
+                 conv_dropout_p: float = 0.1, conv_kernel_size: int = 9, half_step_residual: bool = True,
+                 subsampling_conv_channels: int = 256, subsampling_factor: int = 4, precision: str = 'fp32',
                  mask_mode: str = 'reference_unmasked', **kwargs):
+        """Signature defaults are the reference's (model.py:58-72: 512 / 18 / 8 / 9 / 256); the 144 / 16 / 4 / 31 / 32
+        default spec comes from `default_specs.RECOGNITION_HYPER_PARAMS` at the call site, as in the reference CLI
+        (cli/train.py:254-279).  Training-loop arguments (optimizer, schedule, ...) arrive in **kwargs and are ignored."""
         super().__init__()
         encoder = ConformerEncoder(in_channels=1, input_dim=height, encoder_dim=encoder_dim, num_layers=num_encoder_layers,
                                    num_attention_heads=num_attention_heads,

@@ -148,20 +148,78 @@ class PytorchRecognitionModel(EngineOwner):
 
     def _decode(self, line: torch.Tensor, lens) -> List[List[Tuple[int, int, int, float]]]:
         if self.ctc_decoder is greedy_decoder:
-            x = self._as_bwh(line)
-            eng = self.engine_for(x.device)
-            return unpack_decoded(eng.forward_decode(x, lens))
+            return unpack_decoded(self._decode_arrays(line, lens))
         o, olens = self.forward(line, lens)
         o = o.transpose(1, 2).cpu().float().numpy()                   # pred.py:138
         return [self.ctc_decoder(seq[:, :int(seq_len)]) for seq, seq_len in zip(o, olens)]
 
+    def _model_device(self) -> torch.device:
+        return self.nn['decoder'].weight.device
+
+    def _decode_arrays(self, line: torch.Tensor, lens) -> Dict[str, np.ndarray]:
+        """Fused device decode of one batch -> host arrays (labels/starts/ends/conf (B,T), counts/out_lens (B,)).
+        A host batch (the DataLoader hands out CPU tensors, cli/test.py:185-189) goes through
+        `cocr_recognize_host_begin/_end`: H2D, forward, decode and the D2H of the records all inside the library, with no
+        (N, C, T) logits and no per-label Python objects.  A device batch goes through `cocr_forward_decode`."""
+        if line.device.type == 'cpu':
+            eng = self.engine_for(self._model_device())
+            if line.dim() != 4 or line.shape[1] != 1:
+                raise ValueError(f'expected an (N, 1, H, W) line tensor, got {tuple(line.shape)}')
+            if line.dtype not in (torch.float32, torch.uint8):
+                line = line.float()
+            slot = 0 if 0 not in getattr(eng, '_pending', {}) else 1
+            eng.recognize_host_begin(slot, line.contiguous(), lens)
+            return eng.recognize_host_end(slot)
+        x = self._as_bwh(line)
+        res = self.engine_for(x.device).forward_decode(x, lens)
+        # one D2H per array, all queued before the first wait
+        host = {k: v.to('cpu', non_blocking=True) for k, v in res.items()}
+        torch.cuda.current_stream(x.device).synchronize()
+        return {k: v.numpy() for k, v in host.items()}
+
     def _strings(self, line: torch.Tensor, lens) -> List[str]:
         if self.ctc_decoder is greedy_decoder and isinstance(self.codec, LabelCodec):
             # collapsed labels stay a (B, T) block: one table look-up for the batch instead of a tuple per label
-            x = self._as_bwh(line)
-            res = self.engine_for(x.device).forward_decode(x, lens)
-            return self.codec.decode_strings(res['labels'].cpu().numpy(), res['counts'].cpu().numpy())
+            res = self._decode_arrays(line, lens)
+            return self.codec.decode_strings(res['labels'], res['counts'])
         return [''.join(x[0] for x in self.codec.decode(locs)) for locs in self._decode(line, lens)]
+
+    def predict_labels_arrays(self, line: torch.Tensor, lens: Optional[torch.Tensor] = None) -> Dict[str, np.ndarray]:
+        """`predict_labels` without the list-of-tuples packaging: the (label, start, end, max) columns of pred.py:165-178
+        as (B, T) arrays plus `counts` (records per line).  `unpack_decoded` turns them into the reference's format."""
+        if self.ctc_decoder is not greedy_decoder:
+            raise NotImplementedError('array output needs the built-in greedy decoder')
+        return self._decode_arrays(line, lens)
+
+    def predict_string_stream(self, batches, arrays: bool = False):
+        """Pipelined `predict_string` over an iterable of host batches `(line (N,1,H,W) fp32/uint8 CPU tensor, lens)`, e.g.
+        a DataLoader (cli/test.py:185-191).  Two batches are in flight: while batch i computes, batch i+1 is copied to
+        the device on the handle's copy stream and the records of batch i-1 travel back.  Yields one result per batch, in
+        order: the strings of `predict_string`, or the arrays of `predict_labels_arrays` when `arrays`.  Pinned batches
+        (DataLoader(pin_memory=True)) overlap fully; pageable ones still work."""
+        if self.ctc_decoder is not greedy_decoder or not (arrays or isinstance(self.codec, LabelCodec)):
+            for line, lens in batches:                      # no fused path: plain per-batch calls
+                yield self._strings(line, lens)
+            return
+        eng = self.engine_for(self._model_device())
+
+        def finish(slot):
+            res = eng.recognize_host_end(slot)
+            return res if arrays else self.codec.decode_strings(res['labels'], res['counts'])
+        pending: List[int] = []
+        slot = 0
+        for line, lens in batches:
+            if line.device.type != 'cpu':
+                raise ValueError('predict_string_stream takes host batches; call predict_string for device tensors')
+            if line.dtype not in (torch.float32, torch.uint8):
+                line = line.float()
+            if len(pending) == 2:
+                yield finish(pending.pop(0))
+            eng.recognize_host_begin(slot, line.contiguous(), lens)
+            pending.append(slot)
+            slot ^= 1
+        while pending:
+            yield finish(pending.pop(0))
 
     def predict(self, line: torch.Tensor, lens: Optional[torch.Tensor] = None) -> List[str]:
         """pred.py:124-145 (returns the decoded strings, as the reference's code does)."""

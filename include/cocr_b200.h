@@ -163,6 +163,12 @@ int cocr_forward_decode_u8(cocr_handle *h, const uint8_t *img, int64_t sb, int64
 int cocr_recognize_host_u8_begin(cocr_handle *h, int32_t slot, const uint8_t *img_host, const int32_t *widths_host,
                                  int32_t B, int32_t W, void *stream);   /* collect with cocr_recognize_host_end */
 
+/* Device copy of the records of the batch in `slot` (valid from cocr_recognize_host_begin until the slot is begun again;
+ * complete once cocr_recognize_host_end has returned): one block [labels | starts | ends | conf] (4 x (B,T) 32-bit) followed
+ * by [counts | out_lens] (2 x (B) int32).  This is what a multi-GPU caller hands to the collective that gathers the decoded
+ * records of all shards without a second trip through the host.  The library keeps ownership. */
+int cocr_slot_records_dev(cocr_handle *h, int32_t slot, void **records_dev, size_t *bytes, int32_t *B, int32_t *T);
+
 /* Bytes of device workspace the handle holds after a call with this (B, W). */
 int cocr_workspace_bytes(cocr_handle *h, int32_t B, int32_t W, size_t *bytes);
 

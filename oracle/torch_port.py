@@ -92,7 +92,7 @@ def recognition_forward(line: torch.Tensor, lens: torch.Tensor, w: Dict[str, tor
     b, c, t, f = y.shape
     y = F.linear(y.transpose(1, 2).reshape(b, t, -1), w[s + 'out.0.weight'], w[s + 'out.0.bias'])
     fac = 0.5 if hp.get('half_step_residual', True) else 1.0
-    pe = rel_pos(t, hp['encoder_dim'])
+    pe = rel_pos(t, hp['encoder_dim']).to(y.device)
     for i in range(hp['num_encoder_layers']):
         p = f'encoder.layers.{i}.sequential.'
         y = _ffn(y, w, p + '0.module.') * fac + y

@@ -136,3 +136,34 @@ def test_label_codec_batched_strings_match_tuple_decode():
     t2 = time.perf_counter()
     assert s_fast[:256] == s_slow
     assert (t1 - t0) / 2048 < (t2 - t1) / 256
+
+
+def test_load_state_dict_through_submodules_invalidates_engine():
+    """`net.nn.load_state_dict(weights)` is the reference idiom (pred.py:193); torch runs only the post hooks
+    of the module it was called on and its descendants, so every sub-module carries the invalidation hook."""
+    import torch
+    from conformer_ocr_b200 import PytorchRecognitionModel
+    from conformer_ocr_b200.default_specs import RECOGNITION_HYPER_PARAMS as HP
+    hp = {k: HP[k] for k in ('height', 'encoder_dim', 'num_attention_heads', 'feed_forward_expansion_factor', 'conv_expansion_factor',
+                             'conv_kernel_size', 'half_step_residual', 'subsampling_conv_channels', 'subsampling_factor')}
+    net = PytorchRecognitionModel(num_classes=7, num_encoder_layers=1, input_dropout_p=0.1, feed_forward_dropout_p=0.1,
+                                  attention_dropout_p=0.1, conv_dropout_p=0.1, **hp)
+    for target in (net, net.nn, net.nn['encoder'], net.nn['decoder']):
+        net._engine_key = ('stale',)
+        target.load_state_dict(target.state_dict())
+        assert net._engine_key is None, type(target).__name__
+    enc = net.nn['encoder']
+    enc._engine_key = ('stale',)
+    net.nn.load_state_dict(net.nn.state_dict())
+    assert enc._engine_key is None
+
+
+def test_recognition_model_signature_defaults_match_reference():
+    """model.py:58-72: RecognitionModel(num_classes) builds the 512 / 18 / 8 / 9 / 256 architecture, not the default spec."""
+    import inspect
+    from conformer_ocr_b200.model import RecognitionModel
+    sig = inspect.signature(RecognitionModel.__init__).parameters
+    want = dict(height=96, encoder_dim=512, num_encoder_layers=18, num_attention_heads=8, feed_forward_expansion_factor=4,
+                conv_expansion_factor=2, conv_kernel_size=9, half_step_residual=True, subsampling_conv_channels=256, subsampling_factor=4)
+    for k, v in want.items():
+        assert sig[k].default == v, k

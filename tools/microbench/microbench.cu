@@ -1,9 +1,24 @@
-// Micro-benchmarks of the tensor pipe (cocr_selftest which = 40): cycles of a chain of tcgen05.mma instructions for a
-// given N, number of independent accumulators the chain alternates between, and A operand source (shared / tensor memory).
-#include "common.h"
-#include "tc_utils.cuh"
+// Micro-benchmarks of the tensor pipe, TMEM, MUFU and mbarrier hand-shakes.  NOT part of the product library: built into
+// tools/microbench/libcocr_microbench.so (make -C tools/microbench) and called through `cocr_microbench` by tools/*_bench.py.
+//   which = 40: cycles of a chain of tcgen05.mma instructions for a given N, number of independent accumulators the chain
+//   alternates between, and A operand source (shared / tensor memory); 41-45: see the entry point at the end of the file.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../conformer_ocr_b200/csrc/common.h"
+#include "../../conformer_ocr_b200/csrc/tc_utils.cuh"
 
 namespace cocr {
+
+static char g_mb_err[512] = "";
+static int mb_error(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_mb_err, sizeof(g_mb_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define set_error(h, code, ...) mb_error(code, __VA_ARGS__)
 
 __global__ void __launch_bounds__(128, 1) k_mma_bench(int N, int chains, int a_tmem, int count, long long *out) {
     using namespace tc;
@@ -479,3 +494,20 @@ int selftest_mufu_bench(int device, int kind, double *cycles_per_inst) {
     return COCR_OK;
 }
 }  // namespace cocr
+
+extern "C" const char *cocr_microbench_error(void) { return cocr::g_mb_err; }
+
+// which: 40 tensor-pipe cycles per MMA (p0 = N, p1 = chains, p2 = A in TMEM); 41 TMEM read bandwidth in bytes per cycle per SM
+// (depth, with_mma, shape); 42 12-MMA group cycles under TMEM traffic (mode, a_tmem); 43 MUFU cycles per warp instruction
+// (kind); 44 attention S + P V MMA sequence, cycles per key tile (mode, what, grid); 45 mbarrier hand-shake cycles per hop (mode)
+extern "C" int cocr_microbench(int device, int which, long long p0, long long p1, long long p2, double *out) {
+    if (out) *out = -1.0;
+    if (cudaSetDevice(device) != cudaSuccess) return cocr::mb_error(COCR_ERR_CUDA, "cocr_microbench: bad device %d", device);
+    if (which == 45) return cocr::selftest_mbar_pingpong(device, (int)p0, out);
+    if (which == 44) return cocr::selftest_attn_mma_bench(device, (int)p0, (int)p1, (int)p2, out);
+    if (which == 43) return cocr::selftest_mufu_bench(device, (int)p0, out);
+    if (which == 42) return cocr::selftest_mma_contention(device, (int)p0, (int)p1, out);
+    if (which == 41) return cocr::selftest_tmem_bench(device, (int)p0, (int)p1, (int)p2, out);
+    if (which == 40) return cocr::selftest_mma_bench(device, (int)p0, (int)p1, (int)p2, out);
+    return cocr::mb_error(COCR_ERR_BAD_ARG, "cocr_microbench: unknown benchmark %d", which);
+}
