@@ -586,6 +586,26 @@ int cocr_recognize_host(cocr_handle *h, const float *img_host, const int32_t *wi
     return cocr_recognize_host_end(h, slot, labels, starts, ends, conf, counts, out_lens);
 }
 
+int cocr_log_softmax(cocr_handle *h, const float *logits, int64_t rows, int32_t C, void *stream, float *out) {
+    if (!h) return COCR_ERR_BAD_ARG;
+    if (!logits || !out || rows < 0 || C < 1) return set_error(h, COCR_ERR_BAD_ARG, "cocr_log_softmax: bad argument");
+    COCR_CUDA(h, cudaSetDevice(h->device));
+    return launch_log_softmax(h, logits, rows, C, (cudaStream_t)stream, out);
+}
+
+int cocr_ctc_loss(cocr_handle *h, const float *logits, const int32_t *targets, const int32_t *target_lens, const int32_t *input_lens,
+                  int32_t B, int32_t T, int32_t C, int32_t max_target_len, void *stream, float *loss_sum, float *loss_per_line,
+                  float *grad_logits) {
+    if (!h) return COCR_ERR_BAD_ARG;
+    if (!logits || !targets || !target_lens || !loss_sum || B < 1 || T < 1 || C < 2 || max_target_len < 0)
+        return set_error(h, COCR_ERR_BAD_ARG, "cocr_ctc_loss: bad argument");
+    if ((int64_t)B * T * (2 * (int64_t)max_target_len + 1) >= ((int64_t)1 << 31))
+        return set_error(h, COCR_ERR_UNSUPPORTED, "cocr_ctc_loss: alpha table too large (B*T*(2L+1) >= 2^31)");
+    COCR_CUDA(h, cudaSetDevice(h->device));
+    return launch_ctc_loss(h, logits, targets, target_lens, input_lens, B, T, C, max_target_len, (cudaStream_t)stream, loss_sum,
+                           loss_per_line, grad_logits);
+}
+
 int cocr_slot_records_dev(cocr_handle *h, int32_t slot, void **records_dev, size_t *bytes, int32_t *B, int32_t *T) {
     if (!h) return COCR_ERR_BAD_ARG;
     if (slot < 0 || slot > 1 || !records_dev || !bytes) return set_error(h, COCR_ERR_BAD_ARG, "cocr_slot_records_dev: bad argument");

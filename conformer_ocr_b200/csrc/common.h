@@ -198,6 +198,11 @@ int launch_glu_dw_bf16(cocr_handle *h, const __nv_bfloat16 *u, const LayerF32 &l
 int launch_layernorm(cocr_handle *h, const float *x, float *y, const float *g, const float *b, int M, int d,
                      cudaStream_t st);
 
+// ---- training-side tail (ctc_loss.cu)
+int launch_log_softmax(cocr_handle *h, const float *logits, int64_t rows, int C, cudaStream_t st, float *out);
+int launch_ctc_loss(cocr_handle *h, const float *logits, const int32_t *targets, const int32_t *target_lens, const int32_t *input_lens,
+                    int B, int T, int C, int max_target_len, cudaStream_t st, float *loss_sum, float *loss_per_line, float *grad);
+
 // ---- optimised memory-bound kernels (mem_kernels.cu); return COCR_ERR_UNSUPPORTED when the geometry is not covered
 int launch_glu_dw_fast(cocr_handle *h, const __nv_bfloat16 *u, const LayerF32 &lw, __nv_bfloat16 *g, int B, int T,
                        cudaStream_t st);

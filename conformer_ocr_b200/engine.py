@@ -235,6 +235,45 @@ class Engine:
                                                           p(res['conf']), p(res['counts']), p(res['out_lens'])))
         return res
 
+    # -- training-side tail (model.py:136-142) -------------------------------------------------
+    def log_softmax(self, logits: torch.Tensor) -> torch.Tensor:
+        """nn.functional.log_softmax(logits, dim=-1) (model.py:136) on device fp32 logits."""
+        if logits.device != self.device or logits.dtype != torch.float32:
+            logits = logits.to(device=self.device, dtype=torch.float32)
+        logits = logits.contiguous()
+        out = torch.empty_like(logits)
+        Cn = logits.shape[-1]
+        with torch.cuda.device(self.device):
+            self._check(self._lib.cocr_log_softmax(self._h, self._ptr(logits), logits.numel() // Cn, Cn, self._stream(), self._ptr(out)))
+        return out
+
+    def ctc_loss(self, logits: torch.Tensor, targets, input_lens, target_lens, want_grad: bool = False):
+        """nn.CTCLoss(reduction='sum', zero_infinity=True)(log_softmax(logits).transpose(0, 1), targets, input_lens,
+        target_lens) (model.py:119,136-142) from the RAW logits (B,T,C).  Returns (loss (0-d device tensor), per-line losses
+        (B,), grad wrt logits (B,T,C) or None)."""
+        if logits.device != self.device or logits.dtype != torch.float32:
+            logits = logits.to(device=self.device, dtype=torch.float32)
+        logits = logits.contiguous()
+        B, T, Cn = logits.shape
+        tl_host = torch.as_tensor(target_lens).to('cpu', torch.int64)
+        if tl_host.numel() != B:
+            raise ValueError(f'{tl_host.numel()} target lengths for a batch of {B}')
+        tg = torch.as_tensor(targets).to(device=self.device, dtype=torch.int32).contiguous().view(-1)
+        if int(tl_host.sum()) != tg.numel():
+            raise ValueError('targets must be the 1-D concatenation of the label sequences (model.py:131-133)')
+        if tg.numel() and (int(tg.min()) < 1 or int(tg.max()) >= Cn):
+            raise ValueError('target labels must lie in 1 .. num_classes-1 (0 is the CTC blank)')
+        tl = tl_host.to(device=self.device, dtype=torch.int32)
+        il = None if input_lens is None else torch.as_tensor(input_lens).to(device=self.device, dtype=torch.int32).contiguous()
+        loss = torch.zeros((), dtype=torch.float32, device=self.device)
+        per = torch.empty((B,), dtype=torch.float32, device=self.device)
+        grad = torch.empty_like(logits) if want_grad else None
+        with torch.cuda.device(self.device):
+            self._check(self._lib.cocr_ctc_loss(self._h, self._ptr(logits), self._ptr(tg), self._ptr(tl), self._ptr(il), B, T, Cn,
+                                                int(tl_host.max()) if B else 0, self._stream(), self._ptr(loss), self._ptr(per),
+                                                self._ptr(grad)))
+        return loss, per, grad
+
     def slot_records(self, slot: int) -> Dict[str, torch.Tensor]:
         """Device views (no copy) of the records of the batch last begun in `slot`: labels/starts/ends (B,T) int32,
         conf (B,T) fp32, counts/out_lens (B,) int32.  Valid until the slot is begun again; complete after

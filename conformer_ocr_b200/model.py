@@ -1,6 +1,8 @@
 """Host-side mirror of the hot-path slice of `conformer_ocr.model.RecognitionModel`
-(model.py:39-151): construction (`:99-116`) and `forward(x, seq_lens)` (`:125-127`).  The Lightning
-training loop, metrics and optimiser factory are out of scope."""
+(model.py:39-151): construction (`:99-116`), `forward(x, seq_lens)` (`:125-127`) and the forward half of `_step`
+(`:129-145`: encoder, decoder, log_softmax, CTC loss) including the gradient of the loss with respect to the decoder
+outputs.  The backward pass through the encoder, the Lightning training loop, metrics and the optimiser factory are not
+built."""
 from __future__ import annotations
 
 from typing import Optional, Tuple
@@ -57,3 +59,32 @@ class RecognitionModel(EngineOwner):
         logits, _ = eng.logits(x, seq_lens)
         lens = out_frames(seq_lens if seq_lens is not None else torch.full((x.shape[0],), x.shape[1]))
         return logits, lens
+
+    def _step(self, batch, want_grad: bool = False):
+        """model.py:129-151 in eval-mode arithmetic (dropout off, BatchNorm running statistics): encoder -> decoder ->
+        log_softmax -> CTCLoss(reduction='sum', zero_infinity=True).  The log-softmax is fused into the loss kernels
+        (only its per-frame normaliser is computed).  Returns the reference's dict {'loss', 'probits', 'output_lens'} plus
+        'loss_per_line' and, when `want_grad`, 'grad_probits' = d loss / d probits (what autograd would hand to the
+        decoder's backward).  Like the reference, an out-of-memory error skips the batch (returns None)."""
+        try:
+            input, target = batch['image'], batch['target']
+            input = input.squeeze(1).transpose(1, 2)
+            seq_lens, label_lens = batch['seq_lens'], batch['target_lens']
+            eng = self.engine_for(input.device)
+            probits, _ = eng.logits(input, seq_lens)
+            encoder_lens = out_frames(seq_lens)
+            loss, per_line, grad = eng.ctc_loss(probits, target, encoder_lens, label_lens, want_grad=want_grad)
+            out = {'loss': loss, 'probits': probits, 'output_lens': encoder_lens, 'loss_per_line': per_line}
+            if want_grad:
+                out['grad_probits'] = grad
+            return out
+        except RuntimeError as e:
+            if 'out of memory' in str(e).lower():                      # lightning's is_oom_error (model.py:146-149)
+                torch.cuda.empty_cache()
+                return None
+            raise
+
+    def validation_logprobs(self, x: torch.Tensor, seq_lens: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """log_softmax(decoder(encoder(x)), dim=-1) (model.py:134-136) as a materialised tensor."""
+        logits, lens = self.forward(x, seq_lens)
+        return self.engine_for(x.device).log_softmax(logits), lens

@@ -163,6 +163,21 @@ int cocr_forward_decode_u8(cocr_handle *h, const uint8_t *img, int64_t sb, int64
 int cocr_recognize_host_u8_begin(cocr_handle *h, int32_t slot, const uint8_t *img_host, const int32_t *widths_host,
                                  int32_t B, int32_t W, void *stream);   /* collect with cocr_recognize_host_end */
 
+/* Training-side tail of the path (RecognitionModel._step, model.py:135-142).
+ * cocr_log_softmax: nn.functional.log_softmax(probits, dim=-1) (model.py:136) over `rows` rows of C classes, fp32.
+ * cocr_ctc_loss:    nn.CTCLoss(reduction='sum', zero_infinity=True) (model.py:119,139-142; blank 0) applied to
+ *                   log_softmax(logits): logits_dev (B,T,C) RAW decoder outputs (the log-softmax is fused: only its
+ *                   per-frame normaliser is computed), targets_dev the 1-D concatenation of the label sequences,
+ *                   target_lens_dev / input_lens_dev (B) int32 (input_lens = encoder_lens; NULL = T), max_target_len an
+ *                   upper bound of target_lens.  Writes the summed loss (1 float), optionally the per-line losses (B;
+ *                   infinite losses already zeroed) and optionally grad_logits_dev (B,T,C) = d loss_sum / d logits, which is
+ *                   what autograd passes to the decoder's backward.  The gradient is summed in a fixed order
+ *                   (bit-reproducible). */
+int cocr_log_softmax(cocr_handle *h, const float *logits_dev, int64_t rows, int32_t C, void *stream, float *out_dev);
+int cocr_ctc_loss(cocr_handle *h, const float *logits_dev, const int32_t *targets_dev, const int32_t *target_lens_dev,
+                  const int32_t *input_lens_dev, int32_t B, int32_t T, int32_t C, int32_t max_target_len, void *stream,
+                  float *loss_sum_dev, float *loss_per_line_dev, float *grad_logits_dev);
+
 /* Device copy of the records of the batch in `slot` (valid from cocr_recognize_host_begin until the slot is begun again;
  * complete once cocr_recognize_host_end has returned): one block [labels | starts | ends | conf] (4 x (B,T) 32-bit) followed
  * by [counts | out_lens] (2 x (B) int32).  This is what a multi-GPU caller hands to the collective that gathers the decoded
