@@ -221,9 +221,98 @@ k_dw_fast(const bf16 *__restrict__ x, const float2 *__restrict__ taps /* [K][P] 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Second generation of the same kernel for the default spec (d = 144, K = 31), built to spend its issue slots on FFMA2:
+// the first one ran 112 instructions per output pair (31 of them FFMA2; ncu: issue slots 54 % busy, DRAM 8 %) because every
+// shared-memory index carried a runtime row pitch and a thread produced only 8 outputs per 38 inputs it unpacked.  Here
+// the geometry is compile time (all shared-memory offsets are immediates), a thread owns 16 consecutive frames of a
+// channel pair and slides a 16-deep register window over the 46 input rows it needs: per tap one LDS.64 (taps), one LDS.32
+// + two ALU ops (new input row) and 16 FFMA2.  Tiles of 96 frames: T = 384 gives 4 tiles per line, 1024 items = 6.92 per SM.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int DW2_D = 144, DW2_P = DW2_D / 2, DW2_K = 31, DW2_SEG = 16, DW2_TT = 96;
+constexpr int DW2_ROWS = DW2_TT + DW2_K - 1, DW2_THREADS = DW2_P * (DW2_TT / DW2_SEG);
+constexpr size_t DW2_SMEM = (size_t)2 * DW2_ROWS * DW2_P * 4 + (size_t)DW2_K * DW2_P * 8;
+
+__global__ void __launch_bounds__(DW2_THREADS, 1)
+k_dw_v2(const bf16 *__restrict__ x, const float2 *__restrict__ taps /* [K][P] w*scale/2 */, const float2 *__restrict__ hshift /* [P] */,
+        bf16 *__restrict__ g, int T, int n_tt, int n_items) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    constexpr int P = DW2_P, K = DW2_K, ROWS = DW2_ROWS, pad = (DW2_K - 1) / 2, C8 = DW2_D / 8;
+    float2 *ws = reinterpret_cast<float2 *>(sm_raw);                    // [K][P]
+    uint32_t *xs0 = reinterpret_cast<uint32_t *>(ws + K * P);           // 2 x [ROWS][P] bf16x2
+    const int st_row0 = threadIdx.x / C8, st_c8 = threadIdx.x - st_row0 * C8;
+    constexpr int st_step = DW2_THREADS / C8;                          // 24 rows per pass
+    static_assert(DW2_THREADS % C8 == 0, "staging map needs whole rows per pass");
+    auto stage = [&](int item, int buf) {
+        const int b = item / n_tt, t0 = (item - b * n_tt) * DW2_TT;
+        uint32_t *xs = xs0 + buf * ROWS * P;
+        const bf16 *src = x + (int64_t)b * T * DW2_D + st_c8 * 8;
+#pragma unroll
+        for (int i = 0; i < (ROWS + st_step - 1) / st_step; ++i) {
+            const int row = st_row0 + i * st_step;
+            if (row < ROWS) {
+                const int t = t0 - pad + row;
+                const bool ok = t >= 0 && t < T;
+                cp_async16(xs + row * P + st_c8 * 4, src + (int64_t)(ok ? t : 0) * DW2_D, ok);
+            }
+        }
+        cp_async_commit();
+    };
+    int item = blockIdx.x;
+    if (item < n_items) stage(item, 0);
+    for (int e = threadIdx.x; e < K * P; e += DW2_THREADS) ws[e] = taps[e];
+    const int pr = threadIdx.x % P, seg = threadIdx.x / P;
+    const float2 hs = hshift[pr];
+    int buf = 0;
+    for (; item < n_items; item += gridDim.x, buf ^= 1) {
+        cp_async_wait<0>();
+        __syncthreads();                                    // rows of `item` visible; everyone is done with the other buffer
+        if (item + (int)gridDim.x < n_items) stage(item + gridDim.x, buf ^ 1);
+        const int b = item / n_tt, t0 = (item - b * n_tt) * DW2_TT;
+        const uint32_t *xs = xs0 + buf * ROWS * P + (seg * DW2_SEG) * P + pr;      // row 0 of this thread's window
+        float2 win[DW2_SEG], acc[DW2_SEG];
+#pragma unroll
+        for (int i = 0; i < DW2_SEG - 1; ++i) win[i] = bf2_to_f2(xs[i * P]);
+#pragma unroll
+        for (int i = 0; i < DW2_SEG; ++i) acc[i] = hs;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            win[(k + DW2_SEG - 1) % DW2_SEG] = bf2_to_f2(xs[(k + DW2_SEG - 1) * P]);
+            const float2 w = ws[k * P + pr];
+#pragma unroll
+            for (int i = 0; i < DW2_SEG; ++i) acc[i] = dw_ffma2(w, win[(i + k) % DW2_SEG], acc[i]);
+        }
+        bf16 *dst = g + ((int64_t)b * T + t0 + seg * DW2_SEG) * DW2_D + 2 * pr;
+        const int nvalid = T - (t0 + seg * DW2_SEG);
+#pragma unroll
+        for (int i = 0; i < DW2_SEG; ++i) {
+            if (i < nvalid) {
+                const float2 hh = acc[i];
+                const float2 r = dw_ffma2(hh, make_float2(dw_tanh(hh.x), dw_tanh(hh.y)), hh);
+                *reinterpret_cast<uint32_t *>(dst + (int64_t)i * DW2_D) = f2_to_bf2(r.x, r.y);
+            }
+        }
+    }
+}
+
 // taps_dev: [K][P] float2 = w * bn_scale / 2 ; hshift_dev: [P] float2 = bn_shift / 2  (packed once per layer at load)
 int launch_dw_fast(cocr_handle *h, const bf16 *x, const float *taps_dev, const float *hshift_dev, bf16 *g, int B, int T, cudaStream_t st) {
     const Dims &dm = h->dm;
+    static const bool v1 = getenv("COCR_DW_V1") != nullptr;
+    if (dm.K == DW2_K && dm.d == DW2_D && taps_dev && !v1) {
+        static PerDevice<bool> attr2;
+        if (!attr2.get()) {
+            COCR_CUDA(h, cudaFuncSetAttribute(k_dw_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DW2_SMEM));
+            attr2.get() = true;
+        }
+        const int n_tt = (T + DW2_TT - 1) / DW2_TT, n_items = n_tt * B;
+        const int grid = n_items < h->num_sms ? n_items : h->num_sms;
+        ProfScope ps(h, "dwconv_bn_silu_bf16", st, 2.0 * 31 * B * (double)T * dm.d, 4.0 * B * T * dm.d);
+        k_dw_v2<<<grid, DW2_THREADS, DW2_SMEM, st>>>(x, reinterpret_cast<const float2 *>(taps_dev), reinterpret_cast<const float2 *>(hshift_dev), g, T,
+                                                     n_tt, n_items);
+        COCR_LAUNCHED(h);
+        return COCR_OK;
+    }
     const int P = dm.d / 2;
     const int nthr = P * (DWF_TT / DWF_SEG);
     if (dm.K != 31 || (dm.d & 7) != 0 || nthr > 576 || !taps_dev || nthr % (dm.d / 8) != 0) return COCR_ERR_UNSUPPORTED;
