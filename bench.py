@@ -531,7 +531,7 @@ def run_ours(args):
                                 'passes); algorithmic FLOPs / bytes per SURVEY.md 8(d), not the launch\'s padded operands')
 
     eager = None
-    if rank == 0 and not args.no_eager_baseline:
+    if rank == 0 and world == 1 and not args.no_eager_baseline:
         eager = gpu_eager_baseline(args, hp, dev, x_dev)
 
     if rank != 0:
@@ -546,7 +546,7 @@ def run_ours(args):
     step_tflops = fl_line * B * P / (ms_step * 1e-3) / 1e12
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:         # rank 0 at N = 1 only (the other ranks' barrier spins would share the cores)
         n, cores, times = time_cpu(args, reps=3, warm=1)
         v = n * len(times) / sum(times)
         cpu_baseline = dict(value=v, unit='lines/s', cores=cores, kind='port',

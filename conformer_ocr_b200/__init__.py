@@ -10,6 +10,9 @@ from .conformer.encoder import ConformerEncoder  # noqa: F401
 from .pred import PytorchRecognitionModel, greedy_decoder  # noqa: F401
 from .model import RecognitionModel  # noqa: F401
 from .default_specs import RECOGNITION_HYPER_PARAMS  # noqa: F401
+from .codec import LabelCodec  # noqa: F401
+from .collate import WidthBucketBatchSampler, collate_sequences  # noqa: F401
+from .convert import checkpoint_to_safetensors  # noqa: F401
 
-__all__ = ['ConformerEncoder', 'PytorchRecognitionModel', 'RecognitionModel', 'greedy_decoder',
-           'RECOGNITION_HYPER_PARAMS']
+__all__ = ['ConformerEncoder', 'PytorchRecognitionModel', 'RecognitionModel', 'greedy_decoder', 'RECOGNITION_HYPER_PARAMS',
+           'LabelCodec', 'WidthBucketBatchSampler', 'collate_sequences', 'checkpoint_to_safetensors']

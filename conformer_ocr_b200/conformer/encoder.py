@@ -75,8 +75,13 @@ def _attach(root: nn.Module, dotted: str, tensor: Tensor, buffer: bool):
         node.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
 
 
+_SKIP_INIT = False      # set by the safetensors fast path: every tensor is about to be overwritten by load_state_dict
+
+
 def _init_tensor(shape, kind: str) -> Tensor:
     t = torch.empty(shape, dtype=torch.float32)
+    if _SKIP_INIT:
+        return t.zero_()
     if kind == 'ones' or kind == 'buffer1':
         return t.fill_(1.0)
     if kind == 'zeros' or kind == 'buffer0':

@@ -236,18 +236,19 @@ class PytorchRecognitionModel(EngineOwner):
     # -- loaders (formats unchanged: SURVEY.md §5 "Checkpoint / resume") ------------------------
     @classmethod
     def load_safetensors(cls, path: 'PathLike', **engine_kwargs):
-        """tar{model.safetensors (keys without the `nn.` prefix), metadata.json} (pred.py:180-195)."""
-        import safetensors.torch
-        with tarfile.open(path, 'r') as tf:
-            metadata = json.load(tf.extractfile('metadata.json'))
-            if 'codec' not in metadata:
-                raise ValueError('No codec in metadata record')
-            if 'hyper_params' not in metadata:
-                raise ValueError('No hyperparameters in metadata record')
+        """tar{model.safetensors (keys without the `nn.` prefix), metadata.json} (pred.py:180-195).  The container is
+        parsed with numpy (convert.read_safetensors): the module's parameters become views of the archive's buffer (no random
+        initialisation, no second copy) and the device engine is fed from the same views on first use."""
+        from .convert import read_archive
+        from .conformer import encoder as _enc
+        metadata, weights = read_archive(path)
+        _enc._SKIP_INIT = True                       # parameters are overwritten below: skip xavier / kaiming draws
+        try:
             net = cls(**metadata['hyper_params'], codec=metadata['codec'], **engine_kwargs)
-            weights = safetensors.torch.load(tf.extractfile('model.safetensors').read())
-        net.nn.load_state_dict(weights)
-        net.invalidate_engine()
+        finally:
+            _enc._SKIP_INIT = False
+        state = {k: torch.from_numpy(np.array(v, copy=True) if not v.flags.writeable else v) for k, v in weights.items()}
+        net.nn.load_state_dict(state)
         return net.eval()
 
     @classmethod

@@ -272,3 +272,61 @@ def test_host_batches_stream_and_array_api(cuda_device):
     dev = eng.slot_records(0)
     for k in ('labels', 'starts', 'ends', 'conf', 'counts', 'out_lens'):
         np.testing.assert_array_equal(dev[k].cpu().numpy(), host[k])
+
+
+def test_archive_round_trip_runs_on_device(cuda_device, tmp_path):
+    """(f)4: Lightning checkpoint -> converter -> safetensors archive -> load_safetensors -> device; same logits as a
+    model built from the same tensors directly (pred.py:180-210 layouts)."""
+    from conformer_ocr_b200 import PytorchRecognitionModel, checkpoint_to_safetensors, synthetic as S
+    hp = dict(O.DEFAULT_HPARAMS)
+    hp['num_encoder_layers'] = 2
+    C = 20
+    w = S.make_weights(hp, C, seed=12)
+    codec = {chr(0x61 + i): [i + 1] for i in range(C - 1)}
+    ck = {'state_dict': {'nn.' + k: torch.from_numpy(v) for k, v in w.items()},
+          'hyper_parameters': dict(hp, num_classes=C, **DROP), 'TextLineDataModule': {'codec': codec}}
+    torch.save(ck, tmp_path / 'm.ckpt')
+    checkpoint_to_safetensors(tmp_path / 'm.ckpt', tmp_path / 'm.tar')
+    x = torch.rand((3, 1, hp['height'], 300), generator=torch.Generator().manual_seed(2)).to(cuda_device)
+    want, _ = build(hp, C, w, cuda_device, 'bf16')(x)
+    for net in (PytorchRecognitionModel.load_checkpoint(tmp_path / 'm.ckpt', precision='bf16'),
+                PytorchRecognitionModel.load_safetensors(tmp_path / 'm.tar', precision='bf16')):
+        got, _ = net.to(cuda_device)(x)
+        assert torch.equal(got, want)
+        s = net.predict_string(x)
+        assert len(s) == 3 and all(set(t) <= set(codec) for t in s)
+
+
+def test_bucketed_dataloader_pipeline_matches_cpu_port_batch_by_batch(cuda_device):
+    """(f)2: dataset -> WidthBucketBatchSampler -> collate_sequences (pinned) -> predict_string_stream.  Every batch is
+    also run through the CPU port of the reference with the same composition (the reference's unmasked attention makes
+    results depend on the batch's padded width), and the collapsed label sequences must be identical (fp32 path)."""
+    from torch.utils.data import DataLoader
+    from conformer_ocr_b200 import LabelCodec, PytorchRecognitionModel, WidthBucketBatchSampler, collate_sequences, synthetic as S
+    from conformer_ocr_b200.engine import unpack_decoded
+    hp = dict(O.DEFAULT_HPARAMS)
+    hp['num_encoder_layers'] = 2
+    C = 30
+    w = S.make_weights(hp, C, seed=21)
+    rng = np.random.RandomState(5)
+    widths = rng.randint(60, 420, size=37).tolist() + [400] * 6
+    g = torch.Generator().manual_seed(6)
+    data = [{'image': torch.rand((1, hp['height'], wd), generator=g), 'target': torch.tensor([1, 2])} for wd in widths]
+    sampler = WidthBucketBatchSampler(widths, batch_size=8)
+    loader = DataLoader(data, batch_sampler=sampler, collate_fn=lambda b: collate_sequences(b, pin=True))
+    net = PytorchRecognitionModel(num_classes=C, codec=LabelCodec([chr(0x61 + i) for i in range(C - 1)]), precision='fp32', **hp, **DROP)
+    net.nn.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=False)
+    net = net.to(cuda_device)
+    batches = [(b['image'], b['seq_lens']) for b in loader]
+    assert sum(b[0].shape[0] for b in batches) == len(widths)
+    got = list(net.predict_string_stream(batches, arrays=True))
+    tw = TP.to_torch(w)
+    n_lines = 0
+    for (img, lens), arr in zip(batches, got):
+        ref = TP.predict_labels(img, lens, tw, hp)
+        mine = unpack_decoded(arr)
+        assert [[t[:3] for t in l] for l in mine] == [[t[:3] for t in l] for l in ref]
+        n_lines += len(ref)
+    assert n_lines == len(widths)
+    strings = [s for b in net.predict_string_stream(batches) for s in b]
+    assert len(strings) == len(widths) and all(isinstance(s, str) for s in strings)
