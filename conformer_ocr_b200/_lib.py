@@ -52,6 +52,8 @@ SIGNATURES = {
     'cocr_recognize_host_end': (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _P]),
     'cocr_log_softmax': (C.c_int, [_P, _P, _I64, _I32, _P, _P]),
     'cocr_ctc_loss': (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
+    'cocr_project': (C.c_int, [_P, _P, _I64, _P, _P]),
+    'cocr_decoder_backward': (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P]),
     'cocr_slot_records_dev': (C.c_int, [_P, _I32, C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(_I32), C.POINTER(_I32)]),
     'cocr_workspace_bytes': (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_size_t)]),
     'cocr_launch_count': (_I64, [_P]),

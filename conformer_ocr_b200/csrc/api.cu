@@ -606,6 +606,26 @@ int cocr_ctc_loss(cocr_handle *h, const float *logits, const int32_t *targets, c
                            loss_per_line, grad_logits);
 }
 
+int cocr_project(cocr_handle *h, const float *enc, int64_t rows, void *stream, float *logits) {
+    if (!h) return COCR_ERR_BAD_ARG;
+    if (!h->finalized) return set_error(h, COCR_ERR_STATE, "weights not finalised (call cocr_finalize_weights)");
+    if (h->dm.C <= 0) return set_error(h, COCR_ERR_STATE, "handle was created without a decoder (num_classes = 0)");
+    if (!enc || !logits || rows < 1 || rows >= ((int64_t)1 << 31)) return set_error(h, COCR_ERR_BAD_ARG, "cocr_project: bad argument");
+    COCR_CUDA(h, cudaSetDevice(h->device));
+    return fp32_logits(h, enc, (int)rows, (cudaStream_t)stream, logits);
+}
+
+int cocr_decoder_backward(cocr_handle *h, const float *grad_logits, const float *enc, int64_t rows, void *stream, float *grad_w,
+                          float *grad_b, float *grad_enc) {
+    if (!h) return COCR_ERR_BAD_ARG;
+    if (!h->finalized) return set_error(h, COCR_ERR_STATE, "weights not finalised (call cocr_finalize_weights)");
+    if (h->dm.C <= 0) return set_error(h, COCR_ERR_STATE, "handle was created without a decoder (num_classes = 0)");
+    if (!grad_logits || !enc || !grad_w || !grad_b || rows < 1 || rows >= ((int64_t)1 << 31))
+        return set_error(h, COCR_ERR_BAD_ARG, "cocr_decoder_backward: bad argument");
+    COCR_CUDA(h, cudaSetDevice(h->device));
+    return launch_decoder_backward(h, grad_logits, enc, (int)rows, (cudaStream_t)stream, grad_w, grad_b, grad_enc);
+}
+
 int cocr_slot_records_dev(cocr_handle *h, int32_t slot, void **records_dev, size_t *bytes, int32_t *B, int32_t *T) {
     if (!h) return COCR_ERR_BAD_ARG;
     if (slot < 0 || slot > 1 || !records_dev || !bytes) return set_error(h, COCR_ERR_BAD_ARG, "cocr_slot_records_dev: bad argument");

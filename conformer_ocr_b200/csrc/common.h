@@ -203,6 +203,9 @@ int launch_log_softmax(cocr_handle *h, const float *logits, int64_t rows, int C,
 int launch_ctc_loss(cocr_handle *h, const float *logits, const int32_t *targets, const int32_t *target_lens, const int32_t *input_lens,
                     int B, int T, int C, int max_target_len, cudaStream_t st, float *loss_sum, float *loss_per_line, float *grad);
 
+int launch_decoder_backward(cocr_handle *h, const float *grad_logits, const float *enc, int M, cudaStream_t st, float *grad_w, float *grad_b,
+                            float *grad_enc);
+
 // ---- optimised memory-bound kernels (mem_kernels.cu); return COCR_ERR_UNSUPPORTED when the geometry is not covered
 int launch_glu_dw_fast(cocr_handle *h, const __nv_bfloat16 *u, const LayerF32 &lw, __nv_bfloat16 *g, int B, int T,
                        cudaStream_t st);

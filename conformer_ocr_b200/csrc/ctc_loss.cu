@@ -224,7 +224,104 @@ k_ctc_beta_grad(const float *__restrict__ logits, const float *__restrict__ lse,
     }
 }
 
+// ---- decoder backward (nn.Linear(d, C), pred.py:90 / model.py:114): dW = G^T E, db = colsum(G), dE = G W ----------------------
+// out[z][c][j] = sum over the z-th slice of rows m of G[m][c] * E1[m][j], with E1 = [E | 1] (column d carries the bias gradient).
+// 32 x 32 output tiles, 32 rows of m per shared-memory step; partial sums per slice are reduced in slice order by
+// k_dec_reduce (fixed order: bit-reproducible, no atomics).
+constexpr int DB_T = 32;
+__global__ void __launch_bounds__(256)
+k_dec_wgrad_partial(const float *__restrict__ G, const float *__restrict__ E, int M, int C, int d, int rows_per_slice,
+                    float *__restrict__ partial /* [Z][C][d + 1] */) {
+    __shared__ float sg[DB_T][DB_T + 1], se[DB_T][DB_T + 1];
+    const int c0 = blockIdx.x * DB_T, j0 = blockIdx.y * DB_T, z = blockIdx.z;
+    const int m_lo = z * rows_per_slice, m_hi = min(M, m_lo + rows_per_slice);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;               // 32 x 8 threads; thread -> (c = c0 + ty*4 + i, j = j0 + tx)
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int m0 = m_lo; m0 < m_hi; m0 += DB_T) {
+        for (int r = ty; r < DB_T; r += 8) {
+            const int m = m0 + r;
+            sg[r][tx] = (m < m_hi && c0 + tx < C) ? G[(int64_t)m * C + c0 + tx] : 0.0f;
+            const int j = j0 + tx;
+            se[r][tx] = (m < m_hi) ? (j < d ? E[(int64_t)m * d + j] : (j == d ? 1.0f : 0.0f)) : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int r = 0; r < DB_T; ++r) {
+            const float e = se[r][tx];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = fmaf(sg[r][ty * 4 + i], e, acc[i]);
+        }
+        __syncthreads();
+    }
+    const int j = j0 + tx;
+    if (j <= d)
+        for (int i = 0; i < 4; ++i) {
+            const int c = c0 + ty * 4 + i;
+            if (c < C) partial[((int64_t)z * C + c) * (d + 1) + j] = acc[i];
+        }
+}
+__global__ void k_dec_reduce(const float *__restrict__ partial, int Z, int C, int d, float *__restrict__ gw, float *__restrict__ gb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C * (d + 1)) return;
+    float s = 0.f;
+    for (int z = 0; z < Z; ++z) s += partial[(int64_t)z * C * (d + 1) + i];
+    const int c = i / (d + 1), j = i - c * (d + 1);
+    if (j < d) gw[(int64_t)c * d + j] = s;
+    else gb[c] = s;
+}
+// dE[m][j] = sum_c G[m][c] W[c][j]; one warp per row, W streamed through L1/L2 (C * d * 4 bytes, small)
+__global__ void __launch_bounds__(256)
+k_dec_dinput(const float *__restrict__ G, const float *__restrict__ W, int M, int C, int d, float *__restrict__ dE) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float *g = G + row * C;
+    for (int j0 = 0; j0 < d; j0 += 128) {                                // 4 output columns per lane per sweep
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < C; ++c) {
+            const float gv = g[c];                                       // warp-uniform broadcast
+            const float *w = W + (int64_t)c * d + j0 + lane;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (j0 + lane + 32 * i < d) a[i] = fmaf(gv, w[32 * i], a[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (j0 + lane + 32 * i < d) dE[row * d + j0 + lane + 32 * i] = a[i];
+    }
+}
+
 }  // namespace
+
+int launch_decoder_backward(cocr_handle *h, const float *G, const float *E, int M, cudaStream_t st, float *gw, float *gb, float *dE) {
+    const int C = h->dm.C, d = h->dm.d;
+    int Z = (M + 1023) / 1024;
+    if (Z > 64) Z = 64;
+    const int rows_per_slice = ((M + Z - 1) / Z + DB_T - 1) / DB_T * DB_T;
+    float *partial = nullptr;
+    COCR_CUDA(h, cudaMallocAsync((void **)&partial, (size_t)Z * C * (d + 1) * 4, st));
+    int rc = COCR_OK;
+    do {
+        {
+            ProfScope ps(h, "decoder_wgrad", st, 2.0 * M * (double)C * (d + 1), 4.0 * M * (double)(C + d));
+            dim3 grid((C + DB_T - 1) / DB_T, (d + 1 + DB_T - 1) / DB_T, Z);
+            k_dec_wgrad_partial<<<grid, 256, 0, st>>>(G, E, M, C, d, rows_per_slice, partial);
+            if ((rc = check_cuda(h, cudaGetLastError(), "k_dec_wgrad_partial")) != COCR_OK) break;
+            h->launches++;
+            k_dec_reduce<<<(C * (d + 1) + 255) / 256, 256, 0, st>>>(partial, Z, C, d, gw, gb);
+            if ((rc = check_cuda(h, cudaGetLastError(), "k_dec_reduce")) != COCR_OK) break;
+            h->launches++;
+        }
+        if (dE) {
+            ProfScope ps(h, "decoder_dinput", st, 2.0 * M * (double)C * d, 4.0 * M * (double)(C + d));
+            k_dec_dinput<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(G, h->dec_w, M, C, d, dE);
+            if ((rc = check_cuda(h, cudaGetLastError(), "k_dec_dinput")) != COCR_OK) break;
+            h->launches++;
+        }
+    } while (0);
+    cudaFreeAsync(partial, st);
+    return rc;
+}
 
 int launch_log_softmax(cocr_handle *h, const float *logits, int64_t rows, int C, cudaStream_t st, float *out) {
     if (rows <= 0) return COCR_OK;

@@ -274,6 +274,29 @@ class Engine:
                                                 self._ptr(grad)))
         return loss, per, grad
 
+    def project(self, enc: torch.Tensor) -> torch.Tensor:
+        """decoder nn.Linear on encoder outputs (..., d) -> logits (..., C), fp32 (pred.py:121, model.py:135)."""
+        enc = enc.to(device=self.device, dtype=torch.float32).contiguous()
+        out = torch.empty(enc.shape[:-1] + (self.num_classes,), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.cocr_project(self._h, self._ptr(enc), enc.numel() // enc.shape[-1], self._stream(), self._ptr(out)))
+        return out
+
+    def decoder_backward(self, grad_logits: torch.Tensor, enc: torch.Tensor, want_grad_enc: bool = True):
+        """Backward pass of the decoder nn.Linear: (grad_weight (C,d), grad_bias (C,), grad_enc like enc or None)."""
+        g = grad_logits.to(device=self.device, dtype=torch.float32).contiguous()
+        e = enc.to(device=self.device, dtype=torch.float32).contiguous()
+        rows = e.numel() // e.shape[-1]
+        if g.numel() != rows * self.num_classes:
+            raise ValueError('grad_logits and enc disagree on the number of frames')
+        gw = torch.empty((self.num_classes, self.encoder_dim), dtype=torch.float32, device=self.device)
+        gb = torch.empty((self.num_classes,), dtype=torch.float32, device=self.device)
+        ge = torch.empty_like(e) if want_grad_enc else None
+        with torch.cuda.device(self.device):
+            self._check(self._lib.cocr_decoder_backward(self._h, self._ptr(g), self._ptr(e), rows, self._stream(), self._ptr(gw),
+                                                        self._ptr(gb), self._ptr(ge)))
+        return gw, gb, ge
+
     def slot_records(self, slot: int) -> Dict[str, torch.Tensor]:
         """Device views (no copy) of the records of the batch last begun in `slot`: labels/starts/ends (B,T) int32,
         conf (B,T) fp32, counts/out_lens (B,) int32.  Valid until the slot is begun again; complete after

@@ -84,6 +84,26 @@ class RecognitionModel(EngineOwner):
                 return None
             raise
 
+    def decoder_training_step(self, batch, group=None):
+        """The part of a data-parallel training step (BASELINE configs[3]) this package computes on the device: encoder
+        forward, decoder projection, fused log-softmax + CTC loss (sum), its gradient with respect to the decoder outputs,
+        the decoder's weight / bias gradients and the gradient flowing back into the encoder outputs; then ONE all-reduce
+        (NCCL) of [loss | grad_weight | grad_bias] across the ranks of `group`.  Returns a dict with the local and the
+        all-reduced values.  The backward pass through the encoder is not built."""
+        from .sharding import allreduce_bucket
+        input = batch['image'].squeeze(1).transpose(1, 2)
+        seq_lens, label_lens = batch['seq_lens'], batch['target_lens']
+        eng = self.engine_for(input.device)
+        enc, _ = eng.encode(input, seq_lens)
+        probits = eng.project(enc)
+        encoder_lens = out_frames(seq_lens)
+        loss, per_line, grad = eng.ctc_loss(probits, batch['target'], encoder_lens, label_lens, want_grad=True)
+        gw, gb, ge = eng.decoder_backward(grad, enc)
+        loss_all, gw_all, gb_all = allreduce_bucket([loss, gw, gb], group=group)
+        return {'loss': loss, 'probits': probits, 'output_lens': encoder_lens, 'loss_per_line': per_line, 'grad_probits': grad,
+                'grad_decoder_weight': gw, 'grad_decoder_bias': gb, 'grad_encoder_outputs': ge,
+                'loss_allreduced': loss_all, 'grad_decoder_weight_allreduced': gw_all, 'grad_decoder_bias_allreduced': gb_all}
+
     def validation_logprobs(self, x: torch.Tensor, seq_lens: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """log_softmax(decoder(encoder(x)), dim=-1) (model.py:134-136) as a materialised tensor."""
         logits, lens = self.forward(x, seq_lens)

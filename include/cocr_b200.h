@@ -178,6 +178,16 @@ int cocr_ctc_loss(cocr_handle *h, const float *logits_dev, const int32_t *target
                   const int32_t *input_lens_dev, int32_t B, int32_t T, int32_t C, int32_t max_target_len, void *stream,
                   float *loss_sum_dev, float *loss_per_line_dev, float *grad_logits_dev);
 
+/* The decoder nn.Linear(encoder_dim, C) on its own (pred.py:90,121; model.py:114,135), fp32: logits = enc * W^T + b for
+ * `rows` encoder frames (enc_dev (rows, encoder_dim) as cocr_encode returns it), and its backward pass given
+ * grad_logits_dev (rows, C) (e.g. from cocr_ctc_loss): grad_weight_dev (C, encoder_dim), grad_bias_dev (C) and, when not
+ * NULL, grad_enc_dev (rows, encoder_dim) = what flows back into the encoder.  Sums run in a fixed order (bit-reproducible).
+ * These are the tensors a data-parallel training step all-reduces across GPUs (model.py:139-145 + DDP); the backward pass
+ * through the encoder itself is not built. */
+int cocr_project(cocr_handle *h, const float *enc_dev, int64_t rows, void *stream, float *logits_dev);
+int cocr_decoder_backward(cocr_handle *h, const float *grad_logits_dev, const float *enc_dev, int64_t rows, void *stream,
+                          float *grad_weight_dev, float *grad_bias_dev, float *grad_enc_dev);
+
 /* Device copy of the records of the batch in `slot` (valid from cocr_recognize_host_begin until the slot is begun again;
  * complete once cocr_recognize_host_end has returned): one block [labels | starts | ends | conf] (4 x (B,T) 32-bit) followed
  * by [counts | out_lens] (2 x (B) int32).  This is what a multi-GPU caller hands to the collective that gathers the decoded

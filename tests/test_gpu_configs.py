@@ -25,9 +25,10 @@ def build(hp, C, w, device, precision, **kw):
     return net.to(device)
 
 
-def elementwise_rel(a, b, floor=1e-2):
-    """max |a-b| / |b| over the elements with |b| > floor (reported next to the max-norm figure)."""
-    m = np.abs(b) > floor
+def elementwise_rel(a, b, frac=0.1):
+    """max |a-b| / |b| over the elements with |b| > frac * max|b| (reported next to the max-norm figure: a strictly
+    element-wise relative error is unbounded at the logits that happen to be near zero)."""
+    m = np.abs(b) > frac * np.abs(b).max()
     return float((np.abs(a - b)[m] / np.abs(b)[m]).max()) if m.any() else 0.0
 
 
@@ -57,7 +58,7 @@ def test_benched_config_b256_w1536_bf16(cuda_device):
     np.testing.assert_array_equal(ol.numpy()[pick], ref_lens)
     err = rel_err(a[pick], ref)
     top1 = float((a[pick].argmax(-1) == ref.argmax(-1)).mean())
-    print(f'cfg2 b256 w1536 bf16 vs CPU port (16 lines): max-norm rel err {err:.3e}, element-wise (|ref|>1e-2) '
+    print(f'cfg2 b256 w1536 bf16 vs CPU port (16 lines): max-norm rel err {err:.3e}, element-wise (|ref| > 0.1 max) '
           f'{elementwise_rel(a[pick], ref):.3e}, top-1 {top1:.5f}')
     assert err < BF16_TOL
     assert top1 >= TOP1_MIN
@@ -283,8 +284,10 @@ def test_archive_round_trip_runs_on_device(cuda_device, tmp_path):
     C = 20
     w = S.make_weights(hp, C, seed=12)
     codec = {chr(0x61 + i): [i + 1] for i in range(C - 1)}
-    ck = {'state_dict': {'nn.' + k: torch.from_numpy(v) for k, v in w.items()},
-          'hyper_parameters': dict(hp, num_classes=C, **DROP), 'TextLineDataModule': {'codec': codec}}
+    sd = {'nn.' + k: torch.from_numpy(v) for k, v in w.items()}
+    for i in range(hp['num_encoder_layers']):                 # BatchNorm counters are part of a real state dict (strict load, pred.py:194)
+        sd[f'nn.encoder.layers.{i}.sequential.2.module.sequential.5.num_batches_tracked'] = torch.tensor(3)
+    ck = {'state_dict': sd, 'hyper_parameters': dict(hp, num_classes=C, **DROP), 'TextLineDataModule': {'codec': codec}}
     torch.save(ck, tmp_path / 'm.ckpt')
     checkpoint_to_safetensors(tmp_path / 'm.ckpt', tmp_path / 'm.tar')
     x = torch.rand((3, 1, hp['height'], 300), generator=torch.Generator().manual_seed(2)).to(cuda_device)

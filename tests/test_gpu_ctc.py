@@ -3,9 +3,11 @@ the GPU through the C ABI, against the numpy oracle (oracle/conformer_oracle.py:
 torch's own CTCLoss + autograd for the gradient with respect to the decoder outputs.
 
 Tolerance: the checker is torch's CTCLoss + autograd in float64 on the host (exact to ~1e-12).  The kernels work in fp32
-log space: alpha + beta + nll reaches a few hundred to a few thousand, so a posterior carries an absolute error of about
-1e-7 x that magnitude; the gradient (entries in [-1, 1]) is compared at max(3e-5, 2e-7 x largest per-line loss), the loss at
-1e-5 relative.  torch's own fp32 CUDA implementation, run beside it, sits at the same distance from the float64 result."""
+log space like torch's own CUDA implementation (the arithmetic the reference actually runs): alpha and beta reach minus a few
+hundred to a few thousand, every log-add rounds at 6e-8 of that, so a posterior carries an absolute error of order 1e-6 x the
+line's loss.  The gradient (entries in [-1, 1]) must stay within max(3e-5, 2e-6 x largest per-line loss) of the float64 result
+AND within twice the distance torch's fp32 CUDA CTCLoss has from it (measured: 2.5e-3 against torch's 3.0e-3 at B=32, T=384);
+the loss within 1e-5 relative."""
 import numpy as np
 import pytest
 import torch
@@ -68,12 +70,13 @@ def test_ctc_loss_and_gradient_match_torch_and_oracle(B, T, C, lmin, lmax, ragge
     assert abs(float(per_line.sum()) - got) <= 1e-5 * max(1.0, abs(got))
     g = grad.cpu().numpy()
     assert np.isfinite(g).all()
-    atol = max(3e-5, 2e-7 * float(per_line.max()))
+    atol = max(3e-5, 2e-6 * float(per_line.max()))
     err = float(np.abs(g - want_grad).max())
     _, cuda_grad = torch_reference(logits, targets, il, tl, device=cuda_device, dtype=torch.float32)
     print(f'B={B} T={T} C={C}: loss {got:.4f} (float64 {want:.4f}); grad max err {err:.2e} (torch fp32 CUDA: '
           f'{float(np.abs(cuda_grad - want_grad).max()):.2e}; bound {atol:.1e})')
     assert err <= atol
+    assert err <= 2.0 * float(np.abs(cuda_grad - want_grad).max()) + 3e-5
     if B * T * C <= 4_000_000:                      # numpy oracle (float64 alpha recursion) on the small cases
         lp = O.log_softmax(logits.astype(np.float64))
         ref = O.ctc_loss_sum(lp.transpose(1, 0, 2), targets, il, tl)
@@ -117,6 +120,52 @@ def test_recognition_model_step_matches_reference_semantics(cuda_device):
     want, want_grad = torch_reference(out['probits'].cpu().numpy(), tg.astype(np.int64), out['output_lens'].numpy().astype(np.int64),
                                       tl.astype(np.int64))
     assert abs(float(out['loss']) - want) <= 1e-5 * abs(want)
-    np.testing.assert_allclose(out['grad_probits'].cpu().numpy(), want_grad, atol=5e-5, rtol=0)
+    np.testing.assert_allclose(out['grad_probits'].cpu().numpy(), want_grad, atol=max(3e-5, 2e-6 * float(out['loss_per_line'].max())), rtol=0)
     lp, _ = net.validation_logprobs(batch['image'].squeeze(1).transpose(1, 2), batch['seq_lens'])
     np.testing.assert_allclose(lp.cpu().numpy(), O.log_softmax(out['probits'].cpu().numpy().astype(np.float64)), atol=2e-5, rtol=1e-6)
+
+
+def test_decoder_backward_and_training_step_match_autograd(cuda_device):
+    """decoder_training_step: loss, d loss / d decoder.{weight,bias} and d loss / d encoder outputs equal torch autograd
+    through nn.Linear + log_softmax + CTCLoss on the same encoder outputs (fp32, TF32 off)."""
+    from conformer_ocr_b200.model import RecognitionModel
+    from conformer_ocr_b200 import synthetic as S
+    hp = dict(O.DEFAULT_HPARAMS)
+    hp['num_encoder_layers'] = 2
+    C, B, W = 70, 6, 600
+    w = S.make_weights(hp, C, seed=16)
+    net = RecognitionModel(num_classes=C, **hp)
+    net.nn.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=False)
+    net = net.to(cuda_device)
+    img, lens = S.make_lines(B, hp['height'], W, seed=17, widths=[600, 600, 580, 400, 333, 90])
+    rng = np.random.RandomState(18)
+    tl = np.array([30, 25, 12, 8, 3, 1])
+    tg = rng.randint(1, C, size=int(tl.sum()))
+    batch = dict(image=torch.from_numpy(img).to(cuda_device), target=torch.from_numpy(tg), seq_lens=torch.from_numpy(lens),
+                 target_lens=torch.from_numpy(tl))
+    out = net.decoder_training_step(batch)
+    enc, _ = net.engine_for(cuda_device).encode(batch['image'].squeeze(1).transpose(1, 2), batch['seq_lens'])
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        e = enc.double().requires_grad_(True)
+        lin = torch.nn.Linear(hp['encoder_dim'], C).to(cuda_device).double()
+        with torch.no_grad():
+            lin.weight.copy_(torch.from_numpy(w['decoder.weight']))
+            lin.bias.copy_(torch.from_numpy(w['decoder.bias']))
+        z = lin(e)
+        loss = torch.nn.CTCLoss(reduction='sum', zero_infinity=True)(
+            torch.nn.functional.log_softmax(z, -1).transpose(0, 1), batch['target'].to(cuda_device), out['output_lens'], batch['target_lens'])
+        loss.backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    np.testing.assert_allclose(out['probits'].cpu().numpy(), z.detach().cpu().numpy(), rtol=1e-4, atol=1e-4)
+    assert abs(float(out['loss']) - float(loss.detach())) <= 2e-5 * abs(float(loss.detach()))
+    scale = float(lin.weight.grad.abs().max())
+    np.testing.assert_allclose(out['grad_decoder_weight'].cpu().numpy(), lin.weight.grad.cpu().numpy(), rtol=0, atol=2e-4 * scale)
+    np.testing.assert_allclose(out['grad_decoder_bias'].cpu().numpy(), lin.bias.grad.cpu().numpy(), rtol=0, atol=2e-4 * float(lin.bias.grad.abs().max()))
+    np.testing.assert_allclose(out['grad_encoder_outputs'].cpu().numpy(), e.grad.cpu().numpy(), rtol=0, atol=2e-4 * float(e.grad.abs().max()))
+    # single process: the all-reduced values equal the local ones
+    assert torch.equal(out['loss_allreduced'], out['loss']) and torch.equal(out['grad_decoder_weight_allreduced'], out['grad_decoder_weight'])
+    again = net.decoder_training_step(batch)
+    assert torch.equal(again['grad_decoder_weight'], out['grad_decoder_weight'])       # bit-reproducible

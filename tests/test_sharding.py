@@ -86,3 +86,40 @@ def test_gather_records_world_size_2_gloo():
         assert p.exitcode == 0
     want = {i: fake_records(i) for i in range(len(widths))}
     assert got[0] == want and got[1] == want
+
+
+def _ar_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(100 + rank)
+        ts = [torch.rand((), generator=g), torch.rand((5, 3), generator=g), torch.rand((7,), generator=g).to(torch.float64)]
+        out = S.allreduce_bucket(ts)
+        q.put((rank, [t.clone() for t in ts], out))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allreduce_bucket_world_size_2_gloo():
+    """training exchange step: loss + gradients summed over ranks with one flat all-reduce (sum, not mean: model.py:119)"""
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ar_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {r: (a, b) for r, a, b in (q.get(timeout=120) for _ in range(2))}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for i in range(3):
+        want = got[0][0][i].double() + got[1][0][i].double()
+        for r in (0, 1):
+            assert got[r][1][i].shape == got[r][0][i].shape and got[r][1][i].dtype == got[r][0][i].dtype
+            torch.testing.assert_close(got[r][1][i].double(), want, rtol=1e-6, atol=1e-6)
+    solo = S.allreduce_bucket([torch.ones(3)])                 # no process group: identity
+    assert torch.equal(solo[0], torch.ones(3)) and S.allreduce_bucket([]) == []
