@@ -868,6 +868,34 @@ void bf16_destroy(cocr_handle *h) {
 
 static inline const bf16 *WB(const cocr_handle *h, const float *w) { return h->bf->arena + (w - h->arena); }
 
+// L2 residency of the residual stream (COCR_L2_PERSIST=<MB to keep>, experiment): x (fp32) and xn (bf16) are read and written by
+// every kernel of a layer while the wide intermediates (QKVX operands, 252 MB) stream through once; an access-policy window
+// marks [x | xn] as persisting so that the streams do not evict them.
+static int set_l2_window(cocr_handle *h, cudaStream_t st, void *base, size_t bytes) {
+    static const int want_mb = getenv("COCR_L2_PERSIST") ? atoi(getenv("COCR_L2_PERSIST")) : 0;
+    if (want_mb <= 0) return COCR_OK;
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
+    if (max_persist <= 0 || max_window <= 0) return COCR_OK;
+    size_t persist = std::min((size_t)want_mb << 20, (size_t)max_persist);
+    static PerDevice<size_t> limit;
+    if (limit.get() != persist) {
+        COCR_CUDA(h, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist));
+        limit.get() = persist;
+        fprintf(stderr, "cocr: persisting L2 %zu MB (device max %d MB, window max %d MB)\n", persist >> 20, max_persist >> 20, max_window >> 20);
+    }
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof(v));
+    v.accessPolicyWindow.base_ptr = base;
+    v.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)max_window);
+    v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)persist / (double)v.accessPolicyWindow.num_bytes);
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    COCR_CUDA(h, cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v));
+    return COCR_OK;
+}
+
 // encoder forward; leaves x (fp32) and xn = bf16(x) in the workspace
 static int bf16_forward(cocr_handle *h, const void *img_any, bool u8, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths, int B,
                         int W, cudaStream_t st, int32_t *out_lens, Bf16Plan &p) {
@@ -1019,6 +1047,16 @@ static int bf16_forward(cocr_handle *h, const void *img_any, bool u8, int64_t sb
     // runs on the handle's own stream, fenced against the caller's stream with two events, because the caller's stream
     // may be the legacy default stream, which cannot be captured.  Measured: 7.49 -> 7.19 ms per step (launch gaps).
     Bf16State *bs = h->bf;
+    if (!bs->gstream) {
+        COCR_CUDA(h, cudaStreamCreateWithFlags(&bs->gstream, cudaStreamNonBlocking));
+        COCR_CUDA(h, cudaEventCreateWithFlags(&bs->g_in, cudaEventDisableTiming));
+        COCR_CUDA(h, cudaEventCreateWithFlags(&bs->g_out, cudaEventDisableTiming));
+    }
+    {
+        const size_t span = (size_t)((char *)xn - (char *)x) + (size_t)M * ldx * 2;      // x and xn are neighbours in the plan
+        COCR_TRY(set_l2_window(h, st, x, span));
+        COCR_TRY(set_l2_window(h, bs->gstream, x, span));
+    }
     static const bool no_graph = getenv("COCR_NO_GRAPH") != nullptr || getenv("COCR_FFN_TRACE") || getenv("COCR_ATTN_TRACE") || getenv("COCR_GEMM_TRACE");
     bool use_graph = !no_graph && !h->profiling && dm.L > 0;
     if (use_graph) {
