@@ -931,10 +931,17 @@ static int bf16_forward(cocr_handle *h, const void *img_any, bool u8, int64_t sb
     // conv1 + depthwise conv on CUDA cores -> a2 (M*F, [hi | lo] 2x32) bf16, then the 1x1 conv + ReLU as a K = 64
     // tensor-core GEMM whose (M*F, 32) output IS the (M, F*32) feature matrix of the 768 -> 144 projection
     bf16 *a2hl = (bf16 *)a2;                                       // (M*F, 2 cc) bf16 = the fp32 a2 region of the plan
-    int rc_fe = getenv("COCR_FRONTEND_V1") ? COCR_ERR_UNSUPPORTED : launch_frontend_convs2(h, img_any, u8, sb, sw, sh, B, W, a2hl, st);
+    // third generation (frontend_tc.cu): conv1 and the 1x1 conv on tensor cores inside ONE kernel, image in -> features out
+    static const bool fe_v2 = getenv("COCR_FRONTEND_V2") != nullptr || getenv("COCR_FRONTEND_V1") != nullptr;
+    int rc_fe = fe_v2 ? COCR_ERR_UNSUPPORTED : launch_frontend_tc(h, img_any, u8, sb, sw, sh, B, W, h->bf->w_fe_pw2, feat, st);
+    const bool fe_done = rc_fe == COCR_OK;
+    if (rc_fe == COCR_ERR_UNSUPPORTED)
+        rc_fe = getenv("COCR_FRONTEND_V1") ? COCR_ERR_UNSUPPORTED : launch_frontend_convs2(h, img_any, u8, sb, sw, sh, B, W, a2hl, st);
     if (rc_fe == COCR_ERR_UNSUPPORTED && u8)
-        return set_error(h, COCR_ERR_UNSUPPORTED, "uint8 input is implemented by the fused front-end only (subsampling_conv_channels = 32)");
-    if (rc_fe == COCR_OK) {
+        return set_error(h, COCR_ERR_UNSUPPORTED, "uint8 input is implemented by the fused front-ends only (subsampling_conv_channels = 32)");
+    if (fe_done) {
+        // features are complete
+    } else if (rc_fe == COCR_OK) {
         rc_fe = launch_gemm_tc(h, EPI_BF16, a2hl, 2 * dm.cc, h->bf->w_fe_pw2, 2 * dm.cc, h->sub_bpw, feat, dm.cc, nullptr, M * dm.F, dm.cc,
                                2 * dm.cc, st, 0, nullptr, "gemm_frontend_pw", nullptr, /*relu=*/1);
     } else if (rc_fe == COCR_ERR_UNSUPPORTED) {

@@ -213,6 +213,9 @@ int launch_dw_fast(cocr_handle *h, const __nv_bfloat16 *x, const float *taps_dev
                    cudaStream_t st);
 int launch_frontend_convs2(cocr_handle *h, const void *img, bool u8, int64_t sb, int64_t sw, int64_t sh, int B, int W, __nv_bfloat16 *a2,
                            cudaStream_t st);
+// tensor-core front-end (frontend_tc.cu): image -> feature rows in one kernel; wpw2 = (32, 64) bf16 [Wpw | Wpw]
+int launch_frontend_tc(cocr_handle *h, const void *img, bool u8, int64_t sb, int64_t sw, int64_t sh, int B, int W, const __nv_bfloat16 *wpw2,
+                       __nv_bfloat16 *feat, cudaStream_t st);
 int launch_frontend_fused(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, int B, int W,
                           __nv_bfloat16 *feat, cudaStream_t st);
 
