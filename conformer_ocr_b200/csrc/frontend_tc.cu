@@ -10,8 +10,8 @@
 //      [hi(9 taps) | lo(9) | hi(9) | 0 x 5], hi + lo = the fp32 pixel to 16 mantissa bits (SWIZZLE_64B K-major A operand)
 //   M1 7 x 2 tcgen05.mma (128 x 32 x 16) against B1 = [w_hi | w_hi | w_lo | 0] per channel: hi*w_hi + lo*w_hi + hi*w_lo,
 //      i.e. conv1 to ~2^-16 relative accuracy with fp32 accumulation in TMEM (224 columns)
-//   3  TMEM -> registers: + bias, ReLU, bf16 -> a1[position][32 channels] in shared memory (zero rows outside the conv1
-//      output: the depthwise conv's zero padding in time)
+//      (the bias rides in two more columns of K; rows outside the conv1 output are all zero: the depthwise conv's zero padding)
+//   3  TMEM -> registers: bf16, packed ReLU -> a1[position][32 channels] in shared memory
 //   4  depthwise 3x3 s2 on CUDA cores (weights as constant operands) -> [hi(32) | lo(32)] rows of the 1x1 conv's A operand
 //      (192 rows, SWIZZLE_128B)
 //   M2 2 x 4 tcgen05.mma (128 x 32 x 16) against B2 = [Wpw | Wpw]
@@ -48,6 +48,7 @@ constexpr uint32_t FE3_SMEM = FE3_A1_BYTES + FE3_Y_BYTES + FE3_B1_BYTES + FE3_B2
 constexpr uint32_t FE3_TMEM_COLS = 256;
 static_assert(FE3_NW * FE3_HP * 4 <= FE3_Y_BYTES, "patch must fit the region it shares");
 static_assert(FE3_NPOS * 64 <= FE3_A1_BYTES && FE3_MT1 * 32 <= FE3_TMEM_COLS, "conv1 tiles");
+static_assert(FE3_ROWS2 % 64 == 0 && FE3_THREADS == 256, "phase 4 deals 64 positions to each pair of warps");
 
 constexpr uint64_t kLayoutSw64 = 4;
 __device__ __forceinline__ uint64_t fe3_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint64_t layout) {
@@ -68,25 +69,38 @@ __device__ __forceinline__ uint32_t fe3_pack(float a, float b) {
 }
 __device__ __forceinline__ float fe3_bf_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
-// depthwise conv of one (frame, f) position for channel group G (8 channels), weights as constant operands
-template <int G>
-__device__ __forceinline__ void fe3_dw_group(const FrontendWeights3 &fw, const uint8_t *a1, int tl, int f, float (&o)[8]) {
+// depthwise conv of NP (frame, f) positions for channel group G (8 channels).  The weights are constant operands fetched
+// once per tap and used for all NP positions (with one position per weight fetch the loop spent as many issue slots on
+// uniform constant loads as on FFMAs).  The only tap that can leave the conv1 output is kw = 0 at f = 0 (f2 = -1): its
+// operand is replaced by zero with a select instead of a branch.
+template <int G, int NP>
+__device__ __forceinline__ void fe3_dw_group(const FrontendWeights3 &fw, const uint8_t *a1, const int (&tl)[NP], const int (&f)[NP],
+                                             float (&o)[NP][8]) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) o[c] = fw.bdw[G * 8 + c];
+    for (int p = 0; p < NP; ++p)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o[p][c] = fw.bdw[G * 8 + c];
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
-        const int r = 2 * tl + kh;                               // local conv1 row (t2 = 2t - 1 + kh)
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-            const int f2 = 2 * f - 1 + kw;
-            if (f2 >= 0 && f2 < FE3_F2) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(a1 + fe3_a1_offset(r * FE3_F2 + f2, G));
-                const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+            uint4 v[NP];
 #pragma unroll
-                for (int c2 = 0; c2 < 4; ++c2) {
-                    const float2 x = fe3_bf2_to_f2(u[c2]);
-                    o[2 * c2] = fmaf(fw.wdw[(G * 8 + 2 * c2) * 9 + kh * 3 + kw], x.x, o[2 * c2]);
-                    o[2 * c2 + 1] = fmaf(fw.wdw[(G * 8 + 2 * c2 + 1) * 9 + kh * 3 + kw], x.y, o[2 * c2 + 1]);
+            for (int p = 0; p < NP; ++p) {
+                const int f2 = 2 * f[p] - 1 + kw;
+                const int pos = (2 * tl[p] + kh) * FE3_F2 + (kw == 0 ? max(f2, 0) : f2);      // local conv1 row 2t - 1 + kh
+                v[p] = *reinterpret_cast<const uint4 *>(a1 + fe3_a1_offset(pos, G));
+                if (kw == 0 && f2 < 0) v[p] = make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int c2 = 0; c2 < 4; ++c2) {
+                const float w0 = fw.wdw[(G * 8 + 2 * c2) * 9 + kh * 3 + kw], w1 = fw.wdw[(G * 8 + 2 * c2 + 1) * 9 + kh * 3 + kw];
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const uint32_t u = c2 == 0 ? v[p].x : (c2 == 1 ? v[p].y : (c2 == 2 ? v[p].z : v[p].w));
+                    const float2 x = fe3_bf2_to_f2(u);
+                    o[p][2 * c2] = fmaf(w0, x.x, o[p][2 * c2]);
+                    o[p][2 * c2 + 1] = fmaf(w1, x.y, o[p][2 * c2 + 1]);
                 }
             }
         }
@@ -126,8 +140,14 @@ k_frontend_tc(const PixT *__restrict__ img, int64_t sb, int64_t sw, int64_t sh, 
             const bf16 hi = __float2bfloat16_rn(w);
             row[k] = hi; row[9 + k] = hi; row[18 + k] = __float2bfloat16_rn(w - __bfloat162float(hi));
         }
+        // the conv1 bias rides in the GEMM: im2col columns 27, 28 hold 1.0 and B1 holds the bias split into bf16 hi + lo there
+        {
+            const float bb = fw.b1[c];
+            const bf16 bh = __float2bfloat16_rn(bb);
+            row[27] = bh; row[28] = __float2bfloat16_rn(bb - __bfloat162float(bh));
+        }
 #pragma unroll
-        for (int k = 27; k < 32; ++k) row[k] = __float2bfloat16_rn(0.0f);
+        for (int k = 29; k < 32; ++k) row[k] = __float2bfloat16_rn(0.0f);
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4 *>(sB1 + sw64_offset(c, ch)) = *reinterpret_cast<const uint4 *>(row + 8 * ch);
         sbias[c] = fw.b1[c];
@@ -157,31 +177,50 @@ k_frontend_tc(const PixT *__restrict__ img, int64_t sb, int64_t sw, int64_t sh, 
         // ---- phase 1: input patch (zero padded), patch[wl][y + 1].  All loads of a thread are issued before the first store:
         // the phase is bound by global-load latency, so what counts is how many loads are in flight (ncu: with a
         // load -> store loop this phase held 45 % of the kernel's stall samples) ----
-        {
+        if (sw == 1) {
+            // (N,1,H,W) layout, time contiguous: a warp takes whole image rows (lanes = 32 consecutive columns + 3 more), so the
+            // address arithmetic is one multiply per row instead of two divisions per element
+            constexpr int NR = (FE3_HP - 2 + 7) / 8;                      // rows y = 0 .. 97 dealt to 8 warps
+            float v0[NR], v1[NR];
+            const int wa = w0 + lane, wb = w0 + 32 + lane;
+            const bool oka = wa >= 0 && wa < W, okb = lane < FE3_NW - 32 && wb >= 0 && wb < W;
+            const PixT *pa = img + b * sb + (int64_t)(warp - 1) * sh + wa;      // row yy = warp - 1 + 8 i: one pointer bump per row
+            const int64_t step = 8 * sh;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const int yy = warp - 1 + 8 * i;
+                const bool row_ok = yy >= 0 && yy < FE3_H;
+                v0[i] = (row_ok && oka) ? (float)pa[0] : 0.0f;
+                v1[i] = (row_ok && okb) ? (float)pa[32] : 0.0f;
+                pa += step;
+            }
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const int y = warp + 8 * i;
+                if (y < FE3_HP - 2) {
+                    float a = v0[i], c = v1[i];
+                    if constexpr (sizeof(PixT) == 1) { a = __fdiv_rn(a, 255.0f); c = __fdiv_rn(c, 255.0f); }
+                    patch[lane * FE3_HP + y] = a;
+                    if (lane < FE3_NW - 32) patch[(32 + lane) * FE3_HP + y] = c;
+                }
+            }
+        } else {
             constexpr int NE = (FE3_NW * FE3_HP + FE3_THREADS - 1) / FE3_THREADS;      // 14 elements per thread
             float v[NE];
 #pragma unroll
             for (int i = 0; i < NE; ++i) {
                 const int e = threadIdx.x + i * FE3_THREADS;
-                int wl, y;
-                if (sw == 1) { y = e / FE3_NW; wl = e - y * FE3_NW; }       // (N,1,H,W) layout: time is contiguous
-                else { wl = e / FE3_HP; y = e - wl * FE3_HP; }              // (B,W,H) layout: height is contiguous
+                const int wl = e / FE3_HP, y = e - wl * FE3_HP;           // (B,W,H) layout: height is contiguous
                 const int w = w0 + wl, yy = y - 1;
                 v[i] = 0.0f;
-                if (e < FE3_NW * FE3_HP && w >= 0 && w < W && yy >= 0 && yy < FE3_H) {
-                    if constexpr (sizeof(PixT) == 1) v[i] = (float)img[b * sb + w * sw + yy * sh];
-                    else v[i] = img[b * sb + w * sw + yy * sh];
-                }
+                if (e < FE3_NW * FE3_HP && w >= 0 && w < W && yy >= 0 && yy < FE3_H) v[i] = (float)img[b * sb + w * sw + yy * sh];
             }
 #pragma unroll
             for (int i = 0; i < NE; ++i) {
                 const int e = threadIdx.x + i * FE3_THREADS;
-                int wl, y;
-                if (sw == 1) { y = e / FE3_NW; wl = e - y * FE3_NW; }
-                else { wl = e / FE3_HP; y = e - wl * FE3_HP; }
                 if (e < FE3_NW * FE3_HP) {
-                    if constexpr (sizeof(PixT) == 1) patch[wl * FE3_HP + y] = __fdiv_rn(v[i], 255.0f);
-                    else patch[wl * FE3_HP + y] = v[i];
+                    if constexpr (sizeof(PixT) == 1) patch[e] = __fdiv_rn(v[i], 255.0f);
+                    else patch[e] = v[i];
                 }
             }
         }
@@ -190,6 +229,13 @@ k_frontend_tc(const PixT *__restrict__ img, int64_t sb, int64_t sw, int64_t sh, 
         // ---- phase 2: im2col rows of conv1 (convolution.py:192-196; conv "height" = time, conv "width" = image height) ----
         for (int pos = threadIdx.x; pos < FE3_NPOS; pos += FE3_THREADS) {
             const int r = pos / FE3_F2, f2 = pos - r * FE3_F2;
+            uint8_t *row = sA1 + (uint32_t)(pos >> 7) * (128 * 64);
+            if (t20 + r < 0 || t20 + r >= T2) {
+                // outside the conv1 output = zero padding of the depthwise conv: an all-zero row (bias columns included) gives 0
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4 *>(row + sw64_offset(pos & 127, ch)) = make_uint4(0u, 0u, 0u, 0u);
+                continue;
+            }
             float hi[9], lo[9];
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh)
@@ -204,8 +250,7 @@ k_frontend_tc(const PixT *__restrict__ img, int64_t sb, int64_t sw, int64_t sh, 
             pk[0] = fe3_pack(hi[0], hi[1]); pk[1] = fe3_pack(hi[2], hi[3]); pk[2] = fe3_pack(hi[4], hi[5]); pk[3] = fe3_pack(hi[6], hi[7]);
             pk[4] = fe3_pack(hi[8], lo[0]); pk[5] = fe3_pack(lo[1], lo[2]); pk[6] = fe3_pack(lo[3], lo[4]); pk[7] = fe3_pack(lo[5], lo[6]);
             pk[8] = fe3_pack(lo[7], lo[8]); pk[9] = pk[0]; pk[10] = pk[1]; pk[11] = pk[2];
-            pk[12] = pk[3]; pk[13] = fe3_pack(hi[8], 0.0f); pk[14] = 0u; pk[15] = 0u;
-            uint8_t *row = sA1 + (uint32_t)(pos >> 7) * (128 * 64);
+            pk[12] = pk[3]; pk[13] = fe3_pack(hi[8], 1.0f); pk[14] = fe3_pack(1.0f, 0.0f); pk[15] = 0u;
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch)
                 *reinterpret_cast<uint4 *>(row + sw64_offset(pos & 127, ch)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
@@ -242,13 +287,12 @@ k_frontend_tc(const PixT *__restrict__ img, int64_t sb, int64_t sw, int64_t sh, 
                 tmem_ld_wait_dep(r32);
                 const int pos = mt * 128 + q * 32 + lane;
                 if (pos < FE3_NPOS) {
-                    const int t2 = t20 + pos / FE3_F2;
-                    const bool live = t2 >= 0 && t2 < T2;      // outside the conv1 output: zero padding of the depthwise conv
                     uint32_t pk[16];
 #pragma unroll
                     for (int c = 0; c < 32; c += 2) {
-                        const float o0 = fmaxf(__uint_as_float(r32[c]) + sbias[c], 0.0f), o1 = fmaxf(__uint_as_float(r32[c + 1]) + sbias[c + 1], 0.0f);
-                        pk[c >> 1] = live ? fe3_pack(o0, o1) : 0u;
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(r32[c]), __uint_as_float(r32[c + 1]));
+                        h2 = __hmax2(h2, __floats2bfloat162_rn(0.0f, 0.0f));           // ReLU on the packed pair
+                        pk[c >> 1] = *reinterpret_cast<uint32_t *>(&h2);
                     }
 #pragma unroll
                     for (int g = 0; g < 4; ++g)
@@ -259,27 +303,35 @@ k_frontend_tc(const PixT *__restrict__ img, int64_t sb, int64_t sw, int64_t sh, 
         tc_fence_before();
         __syncthreads();
 
-        // ---- phase 4: depthwise conv (convolution.py:200-205) -> [hi | lo] rows of the 1x1 conv's A operand (aliases the patch) ----
-        for (int it = threadIdx.x; it < 4 * FE3_ROWS2; it += FE3_THREADS) {
-            const int g = it / FE3_ROWS2, p2 = it - g * FE3_ROWS2;       // a warp stays inside one channel group (192 = 6 x 32)
-            const int tl = p2 / FE3_F, f = p2 - tl * FE3_F;
-            float o[8];
-            switch (g) {
-                case 0: fe3_dw_group<0>(fw, sA1, tl, f, o); break;
-                case 1: fe3_dw_group<1>(fw, sA1, tl, f, o); break;
-                case 2: fe3_dw_group<2>(fw, sA1, tl, f, o); break;
-                default: fe3_dw_group<3>(fw, sA1, tl, f, o); break;
-            }
-            uint32_t hi[4], lo[4];
+        // ---- phase 4: depthwise conv (convolution.py:200-205) -> [hi | lo] rows of the 1x1 conv's A operand (aliases the patch).
+        // Warps 2g, 2g+1 own channel group g; a thread takes positions j, j + 64, j + 128 of the 192 ----
+        {
+            constexpr int NP = FE3_ROWS2 / 64;
+            const int g = warp >> 1, j = threadIdx.x & 63;
+            int tl[NP], f[NP];
 #pragma unroll
-            for (int c2 = 0; c2 < 4; ++c2) {
-                hi[c2] = fe3_pack(o[2 * c2], o[2 * c2 + 1]);
-                const float2 hf = fe3_bf2_to_f2(hi[c2]);
-                lo[c2] = fe3_pack(o[2 * c2] - hf.x, o[2 * c2 + 1] - hf.y);
+            for (int p = 0; p < NP; ++p) { const int p2 = j + 64 * p; tl[p] = p2 / FE3_F; f[p] = p2 - tl[p] * FE3_F; }
+            float o[NP][8];
+            switch (g) {
+                case 0: fe3_dw_group<0, NP>(fw, sA1, tl, f, o); break;
+                case 1: fe3_dw_group<1, NP>(fw, sA1, tl, f, o); break;
+                case 2: fe3_dw_group<2, NP>(fw, sA1, tl, f, o); break;
+                default: fe3_dw_group<3, NP>(fw, sA1, tl, f, o); break;
             }
-            uint8_t *row = sY + (uint32_t)(p2 >> 7) * (128 * 128);
-            *reinterpret_cast<uint4 *>(row + sw128_offset(p2 & 127, g)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4 *>(row + sw128_offset(p2 & 127, 4 + g)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const int p2 = j + 64 * p;
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int c2 = 0; c2 < 4; ++c2) {
+                    hi[c2] = fe3_pack(o[p][2 * c2], o[p][2 * c2 + 1]);
+                    const float2 hf = fe3_bf2_to_f2(hi[c2]);
+                    lo[c2] = fe3_pack(o[p][2 * c2] - hf.x, o[p][2 * c2 + 1] - hf.y);
+                }
+                uint8_t *row = sY + (uint32_t)(p2 >> 7) * (128 * 128);
+                *reinterpret_cast<uint4 *>(row + sw128_offset(p2 & 127, g)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4 *>(row + sw128_offset(p2 & 127, 4 + g)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
         }
         fence_proxy_async_smem();
         __syncthreads();
