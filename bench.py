@@ -181,6 +181,9 @@ def algorithmic_work(hp, B, W, C, in_bytes_per_px=4):
         'ctc_collapse': dict(flops=0, bytes=M * (8 + 16), bound='hbm'),
     }
     fam['ffn_fused_final'] = dict(fam['ffn_fused'])
+    # the one-kernel front-end (frontend_tc.cu): conv1 + depthwise + 1x1 conv; image in, feature rows out
+    fam['frontend_tc'] = dict(flops=fam['frontend_convs']['flops'] + fam['gemm_frontend_pw']['flops'],
+                              bytes=B * H * W * in_bytes_per_px + M * F * cc * 2, bound='hbm')
     return fam
 
 
@@ -323,7 +326,9 @@ def run_ours(args):
     # the shard's decoded records [count | labels] per line, kept on the device until the exchange step
     shard = torch.zeros((n_pass, B, T + 1), dtype=torch.int32, device=dev)
     gathered = torch.empty((world,) + tuple(shard.shape), dtype=torch.int32, device=dev) if world > 1 else None
-    gathered_host = torch.empty((world,) + tuple(shard.shape), dtype=torch.int32).pin_memory() if world > 1 else None
+    # every rank receives every shard on its device (all-gather); rank 0, the consumer of the job's output, also brings the
+    # gathered block to its host
+    gathered_host = torch.empty((world,) + tuple(shard.shape), dtype=torch.int32).pin_memory() if (world > 1 and rank == 0) else None
 
     def keep(i, res):
         shard[i, :, 0].copy_(res['counts'])
@@ -333,7 +338,8 @@ def run_ours(args):
         """the path's one exchange step: all ranks receive the records of every shard, once per shard"""
         if world > 1:
             dist.all_gather_into_tensor(gathered, shard)
-            gathered_host.copy_(gathered, non_blocking=True)
+            if gathered_host is not None:
+                gathered_host.copy_(gathered, non_blocking=True)
 
     def fence():
         torch.cuda.synchronize(dev)
@@ -413,7 +419,7 @@ def run_ours(args):
                    d2h_bytes_per_step=P * d2h + gather_bytes // args.steps, ms_per_step=1e3 * dt / args.steps,
                    api='Engine.recognize_host_begin/_end -> cocr_recognize_host_begin/_end (pinned fp32 (N,1,H,W) in, decoded '
                        'records out; two slots, H2D of pass i+1 overlaps the forward pass of pass i)'
-                       + ('; records of the whole shard all-gathered over NCCL and copied to every rank\'s host inside the timed region'
+                       + ('; records of the whole shard all-gathered over NCCL (every rank) and copied to rank 0\'s host inside the timed region'
                           if world > 1 else ''))
         del x_hosts
         # the same loop on raw 8-bit pixels (an extension of the reference interface, reported beside

@@ -38,7 +38,7 @@ idx = [h2.index(w) for w in want if w in h2]
 full = [{h2[i]: r[i] for i in idx} for r in rr[2:]]
 json.dump(full, open(os.path.join(prof, f'{tag}_ncu_full_top_kernels.json'), 'w'), indent=1)
 fam = {'k_attn_tc': ['attention_tc'], 'k_gemm_tc<4>': ['gemm_qkvx_pos'], 'k_gemm_tc<1>': ['gemm_ffn_up'], 'k_gemm_tc<6>': ['gemm_pw1_glu'],
-       'k_dw_fast': ['dwconv_bn_silu_bf16'], 'k_dw_v2': ['dwconv_bn_silu_bf16'], 'k_frontend_convs2': ['frontend_convs'], 'k_ffn_fused': ['ffn_fused', 'ffn_fused_final']}
+       'k_dw_fast': ['dwconv_bn_silu_bf16'], 'k_dw_v2': ['dwconv_bn_silu_bf16'], 'k_frontend_convs2': ['frontend_convs'], 'k_frontend_tc': ['frontend_tc'], 'k_ffn_fused': ['ffn_fused', 'ffn_fused_final']}
 src = f'profiles/{tag}_ncu_full_top_kernels.json (ncu --set full, B=256 W=1536)'
 def dram(o):
     return (float(o['dram__bytes_read.sum']) + float(o['dram__bytes_write.sum'])) * 1e6
