@@ -124,7 +124,10 @@ int launch_gemm_tc(cocr_handle *h, int epi, const bf16 *A, int lda, const bf16 *
     p.n_omega = pos ? pos->n_omega : 0; p.T = pos ? pos->T : 1; p.piece_dst = pos ? pos->piece_dst : nullptr;
     if (epi == EPI_BF16_POS && (!pos || p.n_omega > 256 || N / 16 > 1024)) return set_error(h, COCR_ERR_BAD_ARG, "POS epilogue needs position tables");
     if (epi == EPI_BF16_GLU && (N % 32 != 0 || ldc % 8 != 0)) return set_error(h, COCR_ERR_BAD_ARG, "GLU epilogue needs N %% 32 == 0 and 16-byte aligned output rows");
-    if (p.n_tiles > 1 && p.block_n % 32 != 0) return set_error(h, COCR_ERR_BAD_ARG, "block_n %d must be a multiple of 32 with several N tiles", p.block_n);
+    // the TMA-store epilogues map 32-column pieces to output columns; the GLU epilogue stores 16 outputs per piece straight from
+    // registers and only needs 16-column granularity
+    if (p.n_tiles > 1 && p.block_n % (epi == EPI_BF16_GLU ? 16 : 32) != 0)
+        return set_error(h, COCR_ERR_BAD_ARG, "block_n %d must be a multiple of 32 with several N tiles", p.block_n);
     p.x = res ? res->x : nullptr; p.alpha = res ? res->alpha : 1.f; p.init = res ? res->init : 0;
     p.gf = res ? res->gf : nullptr; p.bf = res ? res->bf : nullptr; p.g1 = res ? res->g1 : nullptr; p.b1 = res ? res->b1 : nullptr;
     if (epi == EPI_RESID && (!res || p.n_tiles != 1 || p.block_n != N || N != 8 * GEMM_RESID_NG || ldc % 4 != 0))
@@ -1029,8 +1032,11 @@ static int bf16_forward(cocr_handle *h, const void *img_any, bool u8, int64_t sb
         if (d % 16 == 0) {
             // pointwise conv 1 with the GLU in its epilogue (value, gate interleaved) -> depthwise conv + BatchNorm + SiLU
             Bf16State *bs = h->bf;
+            // two N tiles of 144 (value / gate pairs of 72 channels each) instead of three of 96: A is read twice, not three
+            // times, and a CTA walks 10.4 instead of 15.7 M tiles (COCR_PW1_BN overrides)
+            static const int pw1_bn = getenv("COCR_PW1_BN") ? atoi(getenv("COCR_PW1_BN")) : (d == 144 ? 144 : 0);
             COCR_TRY(launch_gemm_tc(h, EPI_BF16_GLU, xn, ldx, bs->w_pw1g + (size_t)l * 2 * d * d, d, bs->b_pw1g + (size_t)l * 2 * d, hb, d,
-                                    nullptr, M, 2 * d, d, st, 0, nullptr, "gemm_pw1_glu"));
+                                    nullptr, M, 2 * d, d, st, pw1_bn, nullptr, "gemm_pw1_glu"));
             const float *taps = bs->dw_taps + (size_t)l * (dm.K + 1) * d;
             rc_dw = launch_dw_fast(h, hb, taps, taps + (size_t)dm.K * d, g, B, p.T, st);
         }

@@ -310,3 +310,46 @@ def test_bf16_long_run_is_stable(cuda_device):
             else:
                 assert torch.equal(cur[0], first[0]) and torch.equal(cur[1], first[1]), f'step {step} differs from step 0'
     torch.cuda.synchronize(cuda_device)
+
+
+def test_bf16_soak_many_shapes_both_mask_modes(cuda_device):
+    """2 400 forward passes cycling over six (batch, width) shapes in both mask modes on long-lived engines (graph capture,
+    replay, LRU cache, growing E table, ragged lengths): every pass must succeed and reproduce the first result of its
+    shape bit for bit.  (the 300-step test covers one shape; compute-sanitizer is not available on this pool.)"""
+    from conformer_ocr_b200 import default_specs as D
+    from conformer_ocr_b200 import synthetic as S
+    from conformer_ocr_b200.engine import Engine
+    hp = dict(D.RECOGNITION_HYPER_PARAMS)
+    hp2 = dict(hp); hp2['num_encoder_layers'] = 4
+    C_ = 120
+    w = S.make_weights(hp2, C_, seed=5)
+    shapes = [(32, 1536), (7, 700), (64, 512), (3, 4096), (16, 1534), (1, 37)]
+    for mask_mode in ('reference_unmasked', 'ragged'):
+        eng = Engine(height=hp['height'], encoder_dim=hp['encoder_dim'], num_layers=4, num_heads=hp['num_attention_heads'],
+                     ff_expansion=hp['feed_forward_expansion_factor'], conv_expansion=hp['conv_expansion_factor'],
+                     conv_kernel_size=hp['conv_kernel_size'], half_step_residual=hp['half_step_residual'],
+                     subsampling_conv_channels=hp['subsampling_conv_channels'], subsampling_factor=hp['subsampling_factor'],
+                     num_classes=C_, device=cuda_device, precision='bf16', mask_mode=mask_mode)
+        eng.load_state_dict(w)
+        g = torch.Generator(device=cuda_device).manual_seed(7)
+        inputs, first = [], {}
+        for B, W in shapes:
+            x = torch.rand((B, 1, hp['height'], W), generator=g, device=cuda_device).squeeze(1).transpose(1, 2)
+            lens = torch.randint(max(1, W // 2), W + 1, (B,), generator=torch.Generator().manual_seed(B + W), dtype=torch.int32)
+            lens[0] = W
+            inputs.append((x, lens))
+        for step in range(1200):
+            i = step % len(shapes) if step % 7 else (step // 7) % len(shapes)          # irregular order
+            x, lens = inputs[i]
+            res = eng.forward_decode(x, lens)
+            if step % 97 == 0 or step < len(shapes) * 7:
+                counts, labels = res['counts'].cpu(), res['labels'].cpu()
+                valid = torch.arange(labels.shape[1])[None, :] < counts[:, None]
+                cur = (counts, torch.where(valid, labels, torch.zeros_like(labels)))
+                if i not in first:
+                    first[i] = cur
+                else:
+                    assert torch.equal(cur[0], first[i][0]) and torch.equal(cur[1], first[i][1]), f'{mask_mode} step {step} shape {shapes[i]}'
+        torch.cuda.synchronize(cuda_device)
+        assert len(first) == len(shapes)
+        eng.close()
