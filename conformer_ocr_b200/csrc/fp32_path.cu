@@ -532,18 +532,33 @@ k_ctc_collapse(const float *__restrict__ best_val, const int32_t *__restrict__ b
             tot += warp_tot[w];
         }
         int pos = s_offset + woff + excl;
-        if (emit) {
-            int e = t;
-            float mx = val_at(t);
-            while (e + 1 < len && lab_at(e + 1) == lab) {
-                ++e;
-                mx = fmaxf(mx, val_at(e));
+        // Every run opened in this warp is walked by the WHOLE warp, 32 frames per step (ballot for the first frame whose label
+        // differs, shuffle maximum over the frames before it): a line that decodes to one long run costs T/32 steps instead of
+        // a T-long chain of dependent loads in one thread (the synthetic benchmark lines are exactly that case).
+        for (unsigned m = bal; m; m &= m - 1) {
+            const int src = __ffs(m) - 1;
+            const int t0 = __shfl_sync(0xffffffffu, t, src), lab0 = __shfl_sync(0xffffffffu, lab, src);
+            int e = t0;
+            float mx = val_at(t0);
+            for (int nb = t0 + 1;; nb += 32) {
+                const int tt = nb + lane;
+                const bool same = tt < len && lab_at(tt) == lab0;
+                const unsigned sm = __ballot_sync(0xffffffffu, same);
+                const int n = (sm == 0xffffffffu) ? 32 : __ffs(~sm) - 1;        // frames of this step that continue the run
+                float v = (lane < n) ? val_at(tt) : -INFINITY;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+                mx = fmaxf(mx, v);
+                e += n;
+                if (n < 32) break;
             }
-            int64_t o = (int64_t)b * T + pos;
-            labels[o] = lab;
-            starts[o] = t;
-            ends[o] = e;
-            conf[o] = mx;
+            if (lane == src) {
+                int64_t o = (int64_t)b * T + pos;
+                labels[o] = lab;
+                starts[o] = t;
+                ends[o] = e;
+                conf[o] = mx;
+            }
         }
         __syncthreads();
         if (tid == 0) s_offset += tot;
