@@ -51,6 +51,7 @@ struct AttnArgs {
     const int32_t *lens;        // ragged mode: valid frames per line, else null
     __nv_bfloat16 *ctx;         // (B*T, d) head-major context
     float scale_log2;           // log2(e) / sqrt(dh)
+    int dv_mma;                 // N of the P V MMA: ATT_DV_MMA (48) covers dh <= 40; ATT_DV (64) = the whole V tile (COCR_ATT_DV64)
     long long *trace;           // debug: (tag, clock) pairs of CTA 0 (COCR_ATTN_TRACE), else null
 };
 
@@ -75,7 +76,8 @@ constexpr int ATT_MAXCHUNK = 3;
 constexpr int ATT_MAXSTAGES = 4;
 constexpr uint32_t ATT_QSLOTS = 2;             // Qe staging: 64-column chunks pass through two slots on their way to TMEM
 constexpr int ATT_ERES_TILES = 3;              // E resident for T <= 384
-constexpr int ATT_DV = 64;                     // padded head dim of the V operand / O accumulator
+constexpr int ATT_DV = 64;                     // padded head dim of the V tile in shared memory
+constexpr int ATT_DV_MMA = 48;                 // N of the P V MMA / columns of O actually computed (dh <= 40 on this path)
 constexpr uint32_t ATT_TMEM_COLS = 512;
 constexpr uint32_t ATT_S_COL0 = 0, ATT_S_COL1 = 128, ATT_O_COL = 256, ATT_Q_COL0 = 320, ATT_Q_COL1 = 416;
 constexpr int ATT_POLY_EVERY = 64;
@@ -316,7 +318,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
         // UTCHMMA in an elect/branch loop that costs more than a 64-cycle MMA.
         {
             const uint32_t idesc_s = make_idesc_bf16(ATT_BQ, ATT_BK);                 // S = Qe Ke^T  (Q in TMEM, K/E K-major)
-            const uint32_t idesc_o = make_idesc_bf16(ATT_BQ, ATT_DV, 0, 1);           // O += P V     (P in TMEM, V MN-major)
+            const uint32_t idesc_o = make_idesc_bf16(ATT_BQ, p.dv_mma, 0, 1);   // O += P V  (P in TMEM, V MN-major)
             if (p.e_resident) mbar_wait(efull, 0);
             // flat walk over (item, key tile) with one tile of look-ahead
             // s = position in the CTA's sequence, a = index among the active items; first/last = first/last query tile

@@ -596,6 +596,7 @@ static int launch_attn_tc(cocr_handle *h, const bf16 *qkvx, const int32_t *lens,
     AttnArgs a;
     a.B = B; a.T = T; a.nh = dm.nh; a.dh = dm.dh; a.d = dm.d; a.nchunk = bs->nchunk; a.lens = lens; a.ctx = ctx;
     a.scale_log2 = 1.4426950408889634f / sqrtf((float)dm.dh);
+    { static const bool dv64 = getenv("COCR_ATT_DV64") != nullptr; a.dv_mma = (dv64 || dm.dh > 40) ? ATT_DV : ATT_DV_MMA; }
     a.nqt = (T + ATT_BQ - 1) / ATT_BQ;
     a.n_items = B * dm.nh * a.nqt;
     // E table resident in shared memory when it leaves room for the Q tile and two-deep K and V rings

@@ -167,3 +167,39 @@ def test_recognition_model_signature_defaults_match_reference():
                 conv_expansion_factor=2, conv_kernel_size=9, half_step_residual=True, subsampling_conv_channels=256, subsampling_factor=4)
     for k, v in want.items():
         assert sig[k].default == v, k
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` runs on the host cores (no GPU needed) and prints ONE JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1',
+                          '--cpu-sample-lines', '1', '--width', '256'], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
+              'dtype', 'data', 'config', 'cpu_baseline', 'e2e', 'gpu_launches'):
+        assert k in d, k
+    assert d['impl'] == 'reference' and d['unit'] == 'lines/s' and d['value'] > 0 and d['gpu_launches'] == 0
+    assert d['cpu_baseline']['kind'] == 'port' and d['e2e']['h2d_bytes_per_step'] == 0
+
+
+def test_bench_algorithmic_work_sums_to_survey_8d():
+    """bench.algorithmic_work (per kernel family) adds up to SURVEY 8(d)'s FLOPs per line, for configs[1] and configs[4]."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from conformer_ocr_b200 import synthetic as S
+    hp = bench.arch_hp(bench.hparams())
+    for B, W, C in ((256, 1536, 256), (64, 4096, 10000)):
+        a = bench.algorithmic_work(hp, B, W, C)
+        once = ('frontend_convs', 'gemm_frontend_pw', 'gemm_sub_out', 'gemm_ctc_argmax', 'ctc_collapse')
+        per_layer = ('ffn_fused', 'ffn_fused_final', 'gemm_qkvx_pos', 'attention_tc', 'gemm_attn_out', 'gemm_pw1_glu', 'dwconv_bn_silu_bf16', 'gemm_pw2')
+        total = sum(a[k]['flops'] for k in once) + hp['num_encoder_layers'] * sum(a[k]['flops'] for k in per_layer)
+        assert total == pytest.approx(B * S.flops_per_line(W, C, hp), rel=1e-12)
+        assert a['frontend_tc']['flops'] == a['frontend_convs']['flops'] + a['gemm_frontend_pw']['flops']
+        assert a['attention_tc']['bound'] == 'tensor' and a['dwconv_bn_silu_bf16']['bound'] == 'hbm'
