@@ -384,6 +384,13 @@ static bool use_tc_attn(const cocr_handle *h) { return h->bf && h->bf->tc_attn; 
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// the one-kernel tensor-core front-end (frontend_tc.cu) serves the default geometry and needs no intermediate in HBM
+static bool frontend_tc_selected(const cocr_handle *h) {
+    static const bool forced_off = getenv("COCR_FRONTEND_V2") != nullptr || getenv("COCR_FRONTEND_V1") != nullptr;
+    const Dims &dm = h->dm;
+    return !forced_off && dm.cc == 32 && dm.H == 96 && dm.F2 == 48 && dm.F == 24;
+}
+
 static void bf16_plan(const cocr_handle *h, int B, int W, Bf16Plan *p) {
     const Dims &dm = h->dm;
     p->B = B; p->W = W;
@@ -393,8 +400,10 @@ static void bf16_plan(const cocr_handle *h, int B, int W, Bf16Plan *p) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
     const size_t M = (size_t)p->M;
-    p->off_a1 = take((size_t)B * p->T2 * dm.F2 * dm.cc * 4);
-    p->off_a2 = take(M * dm.F * dm.cc * 4);
+    // conv1 / depthwise outputs of the fallback front-ends (1.5 GB at B = 256, W = 1536); the tensor-core front-end keeps them on chip
+    const bool fe_tc = frontend_tc_selected(h);
+    p->off_a1 = take(fe_tc ? 0 : (size_t)B * p->T2 * dm.F2 * dm.cc * 4);
+    p->off_a2 = take(fe_tc ? 0 : M * dm.F * dm.cc * 4);
     p->off_feat = take(M * dm.feat * 2);
     p->off_x = take(M * dm.d * 4);
     p->off_xn = take(M * (size_t)xn_pitch(h) * 2);
@@ -936,8 +945,9 @@ static int bf16_forward(cocr_handle *h, const void *img_any, bool u8, int64_t sb
     // tensor-core GEMM whose (M*F, 32) output IS the (M, F*32) feature matrix of the 768 -> 144 projection
     bf16 *a2hl = (bf16 *)a2;                                       // (M*F, 2 cc) bf16 = the fp32 a2 region of the plan
     // third generation (frontend_tc.cu): conv1 and the 1x1 conv on tensor cores inside ONE kernel, image in -> features out
-    static const bool fe_v2 = getenv("COCR_FRONTEND_V2") != nullptr || getenv("COCR_FRONTEND_V1") != nullptr;
-    int rc_fe = fe_v2 ? COCR_ERR_UNSUPPORTED : launch_frontend_tc(h, img_any, u8, sb, sw, sh, B, W, h->bf->w_fe_pw2, feat, st);
+    int rc_fe = !frontend_tc_selected(h) ? COCR_ERR_UNSUPPORTED : launch_frontend_tc(h, img_any, u8, sb, sw, sh, B, W, h->bf->w_fe_pw2, feat, st);
+    if (frontend_tc_selected(h) && rc_fe == COCR_ERR_UNSUPPORTED)
+        return set_error(h, COCR_ERR_STATE, "internal: the tensor-core front-end rejected a geometry the plan selected it for");
     const bool fe_done = rc_fe == COCR_OK;
     if (rc_fe == COCR_ERR_UNSUPPORTED)
         rc_fe = getenv("COCR_FRONTEND_V1") ? COCR_ERR_UNSUPPORTED : launch_frontend_convs2(h, img_any, u8, sb, sw, sh, B, W, a2hl, st);
