@@ -208,18 +208,26 @@ class PytorchRecognitionModel(EngineOwner):
             return res if arrays else self.codec.decode_strings(res['labels'], res['counts'])
         pending: List[int] = []
         slot = 0
-        for line, lens in batches:
-            if line.device.type != 'cpu':
-                raise ValueError('predict_string_stream takes host batches; call predict_string for device tensors')
-            if line.dtype not in (torch.float32, torch.uint8):
-                line = line.float()
-            if len(pending) == 2:
+        try:
+            for line, lens in batches:
+                if line.device.type != 'cpu':
+                    raise ValueError('predict_string_stream takes host batches; call predict_string for device tensors')
+                if line.dtype not in (torch.float32, torch.uint8):
+                    line = line.float()
+                if len(pending) == 2:
+                    yield finish(pending.pop(0))
+                eng.recognize_host_begin(slot, line.contiguous(), lens)
+                pending.append(slot)
+                slot ^= 1
+            while pending:
                 yield finish(pending.pop(0))
-            eng.recognize_host_begin(slot, line.contiguous(), lens)
-            pending.append(slot)
-            slot ^= 1
-        while pending:
-            yield finish(pending.pop(0))
+        finally:
+            # a consumer that stops early (or an exception) must not leave batches in the handle's slots
+            while pending:
+                try:
+                    eng.recognize_host_end(pending.pop(0))
+                except Exception:
+                    pass
 
     def predict(self, line: torch.Tensor, lens: Optional[torch.Tensor] = None) -> List[str]:
         """pred.py:124-145 (returns the decoded strings, as the reference's code does)."""

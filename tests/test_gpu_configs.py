@@ -262,6 +262,11 @@ def test_host_batches_stream_and_array_api(cuda_device):
         assert [[t[:3] for t in l] for l in unpack_decoded(arr)] == [[t[:3] for t in l] for l in recs]
         one = net.predict_labels_arrays(img, lens)
         np.testing.assert_array_equal(one['counts'], arr['counts'])
+    # a consumer that stops early leaves no batch behind in the handle's slots
+    gen = net.predict_string_stream(batches)
+    assert next(gen) == per_batch[0]
+    gen.close()
+    assert list(net.predict_string_stream(batches[:3])) == per_batch[:3]
     # uint8 host batches through the stream
     u8 = [((img * 255).round().to(torch.uint8), lens) for img, lens in batches[:2]]
     f8 = [(b[0].float() / 255, b[1]) for b in u8]
