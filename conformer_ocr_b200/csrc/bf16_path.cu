@@ -12,6 +12,7 @@
 #include "gemm_tc.cuh"
 #include "attn_tc.cuh"
 #include "ffn_tc.cuh"
+#include "ffn2_tc.cuh"
 
 namespace cocr {
 
@@ -664,8 +665,17 @@ static int launch_attn_tc(cocr_handle *h, const bf16 *qkvx, const int32_t *lens,
 // fused feed-forward module (ffn_tc.cuh)
 // ------------------------------------------------------------------------------------------
 static bool ffn_fused_ok(const cocr_handle *h) {
-    return h->dm.d == FFN_D && h->dm.ff % FFN_HC == 0 && h->dm.ff / FFN_HC <= FFN_MAX_NC && !getenv("COCR_FFN_SPLIT") && !getenv("COCR_SPLIT_RESIDUAL");
+    const bool v1_ok = h->dm.ff % FFN_HC == 0 && h->dm.ff / FFN_HC <= FFN_MAX_NC;
+    const bool v2_ok = h->dm.ff % FFN2_HC == 0 && h->dm.ff / FFN2_HC <= FFN2_MAX_NC && !getenv("COCR_FFN_V1");
+    return h->dm.d == FFN_D && (v1_ok || v2_ok) && !getenv("COCR_FFN_SPLIT") && !getenv("COCR_SPLIT_RESIDUAL");
 }
+
+// second generation (ffn2_tc.cuh): xn as a TMEM operand, hidden chunks of 64; COCR_FFN_V1 selects the first one
+static bool ffn_v2(int ff) {
+    static const bool v1 = getenv("COCR_FFN_V1") != nullptr;
+    return !v1 && ff % FFN2_HC == 0 && ff / FFN2_HC <= FFN2_MAX_NC;
+}
+static int ffn_hc(int ff) { return ffn_v2(ff) ? FFN2_HC : FFN_HC; }
 
 // W1 (ff, d) bf16 + bias (ff) -> (ff, kp): [W1 row | bias hi | bias lo | 0 ...]
 __global__ void k_pack_ffn1(const bf16 *w1, const float *b1, bf16 *out, int d, int ff, int kp) {
@@ -704,6 +714,29 @@ static int launch_ffn_fused(cocr_handle *h, const bf16 *xn, int ldx, const bf16 
                             float *x, bf16 *xn_out, int ldo, float alpha, const float *gf, const float *bfin, const float *g1, const float *b1n,
                             int M, int ff, cudaStream_t st, const char *tag) {
     if (M <= 0) return COCR_OK;
+    if (ffn_v2(ff)) {
+        if (ldx % 8 != 0 || ldx < FFN_K1 || ldo % 4 != 0) return set_error(h, COCR_ERR_UNSUPPORTED, "fused FFN needs aligned rows (ldx=%d ldo=%d)", ldx, ldo);
+        if (FFN2_SMEM_BYTES > (uint32_t)h->bf->smem_optin) return set_error(h, COCR_ERR_UNSUPPORTED, "fused FFN does not fit shared memory");
+        FfnArgs a;
+        a.M = M; a.NC = ff / FFN2_HC; a.m_tiles = (M + 127) / 128;
+        a.b2 = b2; a.x = x; a.xn_out = xn_out; a.ldo = ldo; a.alpha = alpha;
+        a.gf = gf; a.bf = bfin; a.g1 = g1; a.b1n = b1n; a.trace = nullptr;
+        { static const int dbg = getenv("COCR_FFN_DBG") ? atoi(getenv("COCR_FFN_DBG")) : 0; a.dbg = dbg; }
+        CUtensorMap tmX, tmW1, tmW2;
+        COCR_TRY(make_tmap_bf16(h, &tmX, xn, M, FFN_K1, ldx, 128));
+        COCR_TRY(make_tmap_bf16(h, &tmW1, w1p, ff, FFN_K1, FFN_K1, FFN2_HC));
+        COCR_TRY(make_tmap_bf16(h, &tmW2, w2p, (int64_t)a.NC * FFN_D, FFN2_HC, FFN2_HC, FFN_D));
+        static PerDevice<bool> attr2;
+        if (!attr2.get()) {
+            COCR_CUDA(h, cudaFuncSetAttribute(k_ffn_fused2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FFN2_SMEM_BYTES));
+            attr2.get() = true;
+        }
+        const int grid = a.m_tiles < h->num_sms ? a.m_tiles : h->num_sms;
+        ProfScope ps(h, tag, st, 4.0 * M * (double)ff * FFN_D, (double)M * FFN_D * (2.0 + 2.0 + 4.0 + 4.0) + 4.0 * ff * FFN_D);
+        k_ffn_fused2<<<grid, FFN_THREADS, FFN2_SMEM_BYTES, st>>>(tmX, tmW1, tmW2, a);
+        COCR_LAUNCHED(h);
+        return COCR_OK;
+    }
     if (ff % FFN_HC != 0 || ff / FFN_HC > FFN_MAX_NC || ldx % 8 != 0 || ldx < FFN_K1 || ldo % 4 != 0)
         return set_error(h, COCR_ERR_UNSUPPORTED, "fused FFN needs ff = 96 * n (n <= %d) and aligned rows (ff=%d ldx=%d ldo=%d)", FFN_MAX_NC, ff, ldx, ldo);
     if (FFN_SMEM_BYTES > (uint32_t)h->bf->smem_optin) return set_error(h, COCR_ERR_UNSUPPORTED, "fused FFN does not fit shared memory");
@@ -790,7 +823,7 @@ int bf16_init(cocr_handle *h) {
         bs->w_ffn1p = (bf16 *)pw;
         for (int l = 0; l < dm.L; ++l)
             for (int f = 0; f < 2; ++f) {
-                k_pack_ffn2<<<(unsigned)((nw + 255) / 256), 256>>>(bs->arena + (h->layers[l].ffn_w2[f] - h->arena), bs->w_ffn2p + ((size_t)l * 2 + f) * nw, dm.d, dm.ff, FFN_HC);
+                k_pack_ffn2<<<(unsigned)((nw + 255) / 256), 256>>>(bs->arena + (h->layers[l].ffn_w2[f] - h->arena), bs->w_ffn2p + ((size_t)l * 2 + f) * nw, dm.d, dm.ff, ffn_hc(dm.ff));
                 k_pack_ffn1<<<(unsigned)((nw1 + 255) / 256), 256>>>(bs->arena + (h->layers[l].ffn_w1[f] - h->arena), h->layers[l].ffn_b1[f],
                                                                      bs->w_ffn1p + ((size_t)l * 2 + f) * nw1, dm.d, dm.ff, FFN_K1);
             }
@@ -1395,7 +1428,7 @@ int selftest_ffn(int device, int M, int NC, int flags, double *max_err) {
     if (rc != COCR_OK) return rc;
     h->bf = new Bf16State();
     cudaDeviceGetAttribute(&h->bf->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    const int d = FFN_D, ff = NC * FFN_HC;
+    const int d = FFN_D, ff = NC * FFN_HC;                         // NC counts 96-unit chunks for either kernel generation
     bf16 *xn, *w1, *w2, *w2p, *xo, *xnp, *w1p;
     float *b1, *b2, *x, *ln, *href;
     cudaMalloc((void **)&xn, (size_t)M * d * 2); cudaMalloc((void **)&xo, (size_t)M * d * 2);
@@ -1410,7 +1443,7 @@ int selftest_ffn(int device, int M, int NC, int flags, double *max_err) {
     k_fill_f32<<<(d + 255) / 256, 256>>>(b2, (size_t)d, 15u, 0.5f);
     k_fill_f32<<<(unsigned)(((size_t)M * d + 255) / 256), 256>>>(x, (size_t)M * d, 16u, 2.0f);
     k_fill_f32<<<(4 * d + 255) / 256, 256>>>(ln, (size_t)4 * d, 17u, 1.0f);
-    k_pack_ffn2<<<(unsigned)(((size_t)ff * d + 255) / 256), 256>>>(w2, w2p, d, ff, FFN_HC);
+    k_pack_ffn2<<<(unsigned)(((size_t)ff * d + 255) / 256), 256>>>(w2, w2p, d, ff, ffn_hc(ff));
     k_pack_ffn1<<<(unsigned)(((size_t)ff * FFN_K1 + 255) / 256), 256>>>(w1, b1, w1p, d, ff, FFN_K1);
     cudaMemcpy2D(xnp, (size_t)FFN_K1 * 2, xn, (size_t)d * 2, (size_t)d * 2, (size_t)M, cudaMemcpyDeviceToDevice);
     k_xn_pad_init<<<(unsigned)(((size_t)M * (FFN_K1 - d) + 255) / 256), 256>>>(xnp, M, d, FFN_K1);
