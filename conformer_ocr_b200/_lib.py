@@ -28,6 +28,11 @@ class cocr_hparams(C.Structure):
         'num_classes', 'precision', 'mask_mode')]
 
 
+class cocr_train_config(C.Structure):
+    _fields_ = [('input_dropout_p', C.c_float), ('feed_forward_dropout_p', C.c_float), ('attention_dropout_p', C.c_float),
+                ('conv_dropout_p', C.c_float), ('bn_momentum', C.c_float), ('reserved', C.c_uint32), ('seed', C.c_uint64)]
+
+
 _P = C.c_void_p
 _I32 = C.c_int32
 _I64 = C.c_int64
@@ -54,6 +59,12 @@ SIGNATURES = {
     'cocr_ctc_loss': (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
     'cocr_project': (C.c_int, [_P, _P, _I64, _P, _P]),
     'cocr_decoder_backward': (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P]),
+    'cocr_train_layout': (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I32)]),
+    'cocr_train_entry': (C.c_int, [_P, _I32, C.c_char_p, C.c_size_t, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I32)]),
+    'cocr_train_workspace_bytes': (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_size_t)]),
+    'cocr_train_step': (C.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _I32, _I32, _P, _P, _I32, C.POINTER(cocr_train_config), _P, _P, _P, _P]),
+    'cocr_adamw_step': (C.c_int, [_P, _P, _P, _P, _P, _I64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _I32, _P]),
+    'cocr_dropout_mask': (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_float, _I64, _P, _P]),
     'cocr_slot_records_dev': (C.c_int, [_P, _I32, C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(_I32), C.POINTER(_I32)]),
     'cocr_workspace_bytes': (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_size_t)]),
     'cocr_launch_count': (_I64, [_P]),

@@ -225,6 +225,7 @@ int cocr_destroy(cocr_handle *h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     bf16_destroy(h);
+    train_destroy(h);
     if (h->arena) cudaFree(h->arena);
     if (h->ws.base) cudaFree(h->ws.base);
     if (h->pos_proj) cudaFree(h->pos_proj);
@@ -624,6 +625,51 @@ int cocr_decoder_backward(cocr_handle *h, const float *grad_logits, const float 
         return set_error(h, COCR_ERR_BAD_ARG, "cocr_decoder_backward: bad argument");
     COCR_CUDA(h, cudaSetDevice(h->device));
     return launch_decoder_backward(h, grad_logits, enc, (int)rows, (cudaStream_t)stream, grad_w, grad_b, grad_enc);
+}
+
+int cocr_train_layout(cocr_handle *h, int64_t *n_total, int64_t *n_trainable, int32_t *n_entries) {
+    if (!h) return COCR_ERR_BAD_ARG;
+    return train_layout(h, n_total, n_trainable, n_entries);
+}
+
+int cocr_train_entry(cocr_handle *h, int32_t index, char *key_buf, size_t key_cap, int64_t *offset, int64_t *numel, int32_t *trainable) {
+    if (!h) return COCR_ERR_BAD_ARG;
+    return train_entry(h, index, key_buf, key_cap, offset, numel, trainable);
+}
+
+int cocr_train_workspace_bytes(cocr_handle *h, int32_t B, int32_t W, size_t *bytes) {
+    if (!h || !bytes || B < 1 || W < 1) return set_error(h, COCR_ERR_BAD_ARG, "cocr_train_workspace_bytes: bad argument");
+    return train_workspace_bytes(h, B, W, bytes);
+}
+
+int cocr_train_step(cocr_handle *h, float *params, float *grads, const float *img, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths,
+                    int32_t B, int32_t W, const int32_t *targets, const int32_t *target_lens, int32_t max_target_len,
+                    const cocr_train_config *cfg, void *stream, float *loss_sum, float *loss_per_line, float *taps) {
+    if (!h) return COCR_ERR_BAD_ARG;
+    if (!params || !grads || !img || !targets || !target_lens || !cfg || !loss_sum || B < 1 || W < 1 || max_target_len < 0)
+        return set_error(h, COCR_ERR_BAD_ARG, "cocr_train_step: null or non-positive argument");
+    const float ps[4] = {cfg->input_dropout_p, cfg->feed_forward_dropout_p, cfg->attention_dropout_p, cfg->conv_dropout_p};
+    for (float p : ps)
+        if (!(p >= 0.0f && p < 1.0f)) return set_error(h, COCR_ERR_BAD_ARG, "dropout probability has to be in [0, 1), got %g", (double)p);
+    if ((int64_t)B * cocr_out_frames(W) >= (int64_t)1 << 31) return set_error(h, COCR_ERR_UNSUPPORTED, "batch too large");
+    COCR_CUDA(h, cudaSetDevice(h->device));
+    return train_step(h, params, grads, img, sb, sw, sh, widths, B, W, targets, target_lens, max_target_len, cfg, (cudaStream_t)stream, loss_sum,
+                      loss_per_line, taps);
+}
+
+int cocr_adamw_step(cocr_handle *h, float *params, const float *grads, float *m, float *v, int64_t n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int32_t step, void *stream) {
+    if (!h) return COCR_ERR_BAD_ARG;
+    if (!params || !grads || !m || !v || n < 0 || step < 1) return set_error(h, COCR_ERR_BAD_ARG, "cocr_adamw_step: bad argument");
+    COCR_CUDA(h, cudaSetDevice(h->device));
+    return adamw_step(h, params, grads, m, v, n, lr, beta1, beta2, eps, weight_decay, step, (cudaStream_t)stream);
+}
+
+int cocr_dropout_mask(cocr_handle *h, uint64_t seed, uint32_t site, float p, int64_t n, void *stream, float *out) {
+    if (!h) return COCR_ERR_BAD_ARG;
+    if (!out || n < 0 || !(p >= 0.0f && p < 1.0f)) return set_error(h, COCR_ERR_BAD_ARG, "cocr_dropout_mask: bad argument");
+    COCR_CUDA(h, cudaSetDevice(h->device));
+    return dropout_mask(h, seed, site, p, n, (cudaStream_t)stream, out);
 }
 
 int cocr_slot_records_dev(cocr_handle *h, int32_t slot, void **records_dev, size_t *bytes, int32_t *B, int32_t *T) {

@@ -53,6 +53,7 @@ struct Workspace {
 };
 
 struct Bf16State;   // defined in bf16_path.cu
+struct TrainState;  // defined in train.cu
 
 }  // namespace cocr
 
@@ -101,6 +102,7 @@ struct cocr_handle {
     std::vector<float> fe_weights;   // conv.0 / conv.2 weights + biases in kernel-parameter order (mem_kernels.cu: FrontendWeights)
     int64_t launches = 0;
     cocr::Bf16State *bf = nullptr;
+    cocr::TrainState *train = nullptr;   // training step state (train.cu), created on first use
 
     // optional per-launch event timing (cocr_set_profiling)
     bool profiling = false;
@@ -205,6 +207,18 @@ int launch_ctc_loss(cocr_handle *h, const float *logits, const int32_t *targets,
 
 int launch_decoder_backward(cocr_handle *h, const float *grad_logits, const float *enc, int M, cudaStream_t st, float *grad_w, float *grad_b,
                             float *grad_enc);
+
+// ---- training step (train.cu): flat parameter / gradient buffers owned by the caller
+void train_destroy(cocr_handle *h);
+int train_layout(cocr_handle *h, int64_t *n_total, int64_t *n_trainable, int32_t *n_entries);
+int train_entry(cocr_handle *h, int32_t i, char *key, size_t cap, int64_t *off, int64_t *numel, int32_t *trainable);
+int train_workspace_bytes(cocr_handle *h, int B, int W, size_t *bytes);
+int train_step(cocr_handle *h, float *params, float *grads, const float *img, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths, int B, int W,
+               const int32_t *targets, const int32_t *target_lens, int max_target_len, const cocr_train_config *cfg, cudaStream_t st, float *loss_out,
+               float *loss_per_line, float *taps);
+int adamw_step(cocr_handle *h, float *p, const float *g, float *m, float *v, int64_t n, float lr, float b1, float b2, float eps, float wd, int step,
+               cudaStream_t st);
+int dropout_mask(cocr_handle *h, uint64_t seed, uint32_t site, float prob, int64_t n, cudaStream_t st, float *out);
 
 // ---- optimised memory-bound kernels (mem_kernels.cu); return COCR_ERR_UNSUPPORTED when the geometry is not covered
 int launch_glu_dw_fast(cocr_handle *h, const __nv_bfloat16 *u, const LayerF32 &lw, __nv_bfloat16 *g, int B, int T,

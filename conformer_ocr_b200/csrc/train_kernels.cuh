@@ -1,0 +1,995 @@
+// Kernels of the training step (train.cu): fp32 CUDA-core forward in train() mode and the hand-written backward pass of
+// every module on the path.  Reference symbols: model.py:129-145 (_step), encoder.py:67-103, feed_forward.py:45-55,
+// attention.py:72-151, convolution.py:135-148,190-237, modules.py:31-32.  Everything here is memory- or FMA-bound fp32;
+// contractions accumulate in fp32 in a fixed order, column reductions (bias / LayerNorm / BatchNorm gradients) use atomics.
+#pragma once
+
+#include <math.h>
+
+#include "common.h"
+
+namespace cocr {
+namespace train {
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// dropout: Philox-4x32-10 keyed by (seed, site); element e uses word e & 3 of counter e >> 2.
+// keep (scale 1/(1-p)) when the word >= thresh = p * 2^32; thresh 0 = dropout off.
+// ------------------------------------------------------------------------------------------
+struct Drop {
+    uint64_t seed;
+    uint32_t site;
+    uint32_t thresh;
+    float inv_keep;
+};
+
+__device__ __forceinline__ uint4 philox4(uint64_t seed, uint32_t site, uint64_t ctr) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = site, c3 = 0x5eed5eedu;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ float drop_scale(const Drop &dr, uint64_t e) {
+    if (dr.thresh == 0) return 1.0f;
+    const uint4 r = philox4(dr.seed, dr.site, e >> 2);
+    const uint32_t w = (e & 2) ? ((e & 1) ? r.w : r.z) : ((e & 1) ? r.y : r.x);
+    return w >= dr.thresh ? dr.inv_keep : 0.0f;
+}
+
+__global__ void k_dropout_mask(Drop dr, int64_t n, float *out) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) out[e] = drop_scale(dr, (uint64_t)e);
+}
+
+// ------------------------------------------------------------------------------------------
+// generic fp32 GEMM  C[i,j] = act(sum_k A(i,k) B(k,j) + bias[j]) for k in this z-slice
+//   A_KC: A(i,k) = A[i*lda + k]  else A[k*lda + i];   B_KC: B(k,j) = B[j*ldb + k]  else B[k*ldb + j]
+//   NT (forward linear):  A_KC, B_KC      NN (dgrad): A_KC, !B_KC      TN (wgrad): !A_KC, !B_KC
+// ------------------------------------------------------------------------------------------
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(256)
+k_gemm_f32(const float *__restrict__ A, int lda, const float *__restrict__ Bp, int ldb, const float *__restrict__ bias,
+           float *__restrict__ C, int ldc, int M, int N, int K, int kchunk, size_t c_zstride, int act) {
+    __shared__ __align__(16) float As[16][64 + 4];
+    __shared__ __align__(16) float Bs[16][64 + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid % 16, ty = tid / 16;
+    const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+    const int kbeg = blockIdx.z * kchunk;
+    const int kend = min(K, kbeg + kchunk);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    const bool a_vec = ((lda & 3) == 0) && ((((uintptr_t)A) & 15) == 0);
+    const bool b_vec = ((ldb & 3) == 0) && ((((uintptr_t)Bp) & 15) == 0);
+
+    for (int k0 = kbeg; k0 < kend; k0 += 16) {
+        if (A_KC) {
+            const int lrow = tid / 4, lk = (tid % 4) * 4;
+            const int m = m0 + lrow;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (m < M) {
+                const float *p = A + (int64_t)m * lda + k0 + lk;
+                if (a_vec && k0 + lk + 3 < kend) {
+                    const float4 q = *reinterpret_cast<const float4 *>(p);
+                    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (k0 + lk + i < kend) v[i] = p[i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) As[lk + i][lrow] = v[i];
+        } else {
+            const int kk = tid / 16, c4 = (tid % 16) * 4;
+            const int k = k0 + kk;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (k < kend) {
+                const float *p = A + (int64_t)k * lda + m0 + c4;
+                if (a_vec && m0 + c4 + 3 < M) {
+                    const float4 q = *reinterpret_cast<const float4 *>(p);
+                    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (m0 + c4 + i < M) v[i] = p[i];
+                }
+            }
+            *reinterpret_cast<float4 *>(&As[kk][c4]) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        if (B_KC) {
+            const int lrow = tid / 4, lk = (tid % 4) * 4;
+            const int n = n0 + lrow;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (n < N) {
+                const float *p = Bp + (int64_t)n * ldb + k0 + lk;
+                if (b_vec && k0 + lk + 3 < kend) {
+                    const float4 q = *reinterpret_cast<const float4 *>(p);
+                    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (k0 + lk + i < kend) v[i] = p[i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Bs[lk + i][lrow] = v[i];
+        } else {
+            const int kk = tid / 16, c4 = (tid % 16) * 4;
+            const int k = k0 + kk;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (k < kend) {
+                const float *p = Bp + (int64_t)k * ldb + n0 + c4;
+                if (b_vec && n0 + c4 + 3 < N) {
+                    const float4 q = *reinterpret_cast<const float4 *>(p);
+                    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (n0 + c4 + i < N) v[i] = p[i];
+                }
+            }
+            *reinterpret_cast<float4 *>(&Bs[kk][c4]) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            const float4 a = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
+            const float4 w = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float *Cz = C + (size_t)blockIdx.z * c_zstride;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j] + (bias ? bias[n] : 0.0f);
+            if (act == 2) v = fmaxf(v, 0.0f);
+            Cz[(int64_t)m * ldc + n] = v;
+        }
+    }
+}
+
+// out[e] = sum_z part[z*n + e]
+__global__ void k_reduce_z(const float *__restrict__ part, int Z, int64_t n, float *__restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    float s = 0.f;
+    for (int z = 0; z < Z; ++z) s += part[(size_t)z * n + e];
+    out[e] = s;
+}
+
+// out[c] += sum_m A[m*lda + c]   (out zeroed by the caller)
+__global__ void k_colsum(const float *__restrict__ A, int lda, int M, int N, int rows_per_block, float *__restrict__ out) {
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    float s = 0.f;
+    for (int m = r0; m < r1; ++m) s += A[(int64_t)m * lda + c];
+    atomicAdd(out + c, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm (eps 1e-5, biased variance), one warp per row
+// ------------------------------------------------------------------------------------------
+__global__ void k_ln_fwd(const float *__restrict__ x, const float *__restrict__ g, const float *__restrict__ b, float *__restrict__ y,
+                         float *__restrict__ stats /* (M,2) mean, rstd; may be null */, int M, int d) {
+    const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float *xr = x + (int64_t)row * d;
+    float s = 0.f;
+    for (int c = lane; c < d; c += 32) s += xr[c];
+    const float mean = warp_sum_f(s) / (float)d;
+    float v = 0.f;
+    for (int c = lane; c < d; c += 32) { const float t = xr[c] - mean; v = fmaf(t, t, v); }
+    const float rstd = 1.0f / sqrtf(warp_sum_f(v) / (float)d + 1e-5f);
+    float *yr = y + (int64_t)row * d;
+    for (int c = lane; c < d; c += 32) yr[c] = (xr[c] - mean) * rstd * g[c] + b[c];
+    if (stats && lane == 0) { stats[2 * (int64_t)row] = mean; stats[2 * (int64_t)row + 1] = rstd; }
+}
+
+// dx_out[m] = (resid ? resid[m] : 0) + LN'(dy)[m]
+__global__ void k_ln_bwd(const float *__restrict__ dy, const float *__restrict__ x, const float *__restrict__ stats, const float *__restrict__ g,
+                         const float *resid, float *dx_out, int M, int d) {
+    const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float mean = stats[2 * (int64_t)row], rstd = stats[2 * (int64_t)row + 1];
+    const float *xr = x + (int64_t)row * d, *dr = dy + (int64_t)row * d;
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < d; c += 32) {
+        const float xh = (xr[c] - mean) * rstd, dh = dr[c] * g[c];
+        s1 += dh;
+        s2 = fmaf(dh, xh, s2);
+    }
+    s1 = warp_sum_f(s1) / (float)d;
+    s2 = warp_sum_f(s2) / (float)d;
+    for (int c = lane; c < d; c += 32) {
+        const float xh = (xr[c] - mean) * rstd, dh = dr[c] * g[c];
+        const float v = rstd * (dh - s1 - xh * s2);
+        dx_out[(int64_t)row * d + c] = (resid ? resid[(int64_t)row * d + c] : 0.0f) + v;
+    }
+}
+
+// dgamma[c] += sum_m dy*xhat, dbeta[c] += sum_m dy
+__global__ void k_ln_param_grad(const float *__restrict__ dy, const float *__restrict__ x, const float *__restrict__ stats, int M, int d,
+                                int rows_per_block, float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c >= d) return;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    float sg = 0.f, sb = 0.f;
+    for (int m = r0; m < r1; ++m) {
+        const float v = dy[(int64_t)m * d + c];
+        sg = fmaf(v, (x[(int64_t)m * d + c] - stats[2 * (int64_t)m]) * stats[2 * (int64_t)m + 1], sg);
+        sb += v;
+    }
+    atomicAdd(dgamma + c, sg);
+    atomicAdd(dbeta + c, sb);
+}
+
+// ------------------------------------------------------------------------------------------
+// element-wise pieces
+// ------------------------------------------------------------------------------------------
+// out = dropout(silu(h))
+__global__ void k_silu_drop(const float *__restrict__ h, float *__restrict__ out, int64_t n, Drop dr) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const float v = h[e];
+        out[e] = v * sigmoid_f(v) * drop_scale(dr, (uint64_t)e);
+    }
+}
+// dh = dact * mask * silu'(h)   (in place on dact)
+__global__ void k_silu_drop_bwd(const float *__restrict__ h, float *__restrict__ dact, int64_t n, Drop dr) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const float v = h[e], s = sigmoid_f(v);
+        dact[e] = dact[e] * drop_scale(dr, (uint64_t)e) * (s * (1.0f + v * (1.0f - s)));
+    }
+}
+// out = x + factor * dropout(y)      (x may be null: out = factor*dropout(y))
+__global__ void k_resid_drop(const float *x, const float *__restrict__ y, float *out, float factor, int64_t n, Drop dr) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+        out[e] = (x ? x[e] : 0.0f) + factor * y[e] * drop_scale(dr, (uint64_t)e);
+}
+// GLU over the feature axis: u (M, 2d) -> g (M, d) = u[:, :d] * sigmoid(u[:, d:])   (convolution.py:139)
+__global__ void k_glu_fwd(const float *__restrict__ u, float *__restrict__ g, int64_t M, int d) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < M * d; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = e / d;
+        const int c = (int)(e % d);
+        g[e] = u[m * 2 * d + c] * sigmoid_f(u[m * 2 * d + d + c]);
+    }
+}
+__global__ void k_glu_bwd(const float *__restrict__ u, const float *__restrict__ dg, float *__restrict__ du, int64_t M, int d) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < M * d; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = e / d;
+        const int c = (int)(e % d);
+        const float a = u[m * 2 * d + c], s = sigmoid_f(u[m * 2 * d + d + c]), v = dg[e];
+        du[m * 2 * d + c] = v * s;
+        du[m * 2 * d + d + c] = v * a * s * (1.0f - s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// depthwise Conv1d (kernel K, pad (K-1)/2, no bias, zero padding at the line edges): x, y (B,T,d); w (d,K)
+// flip: correlate with the reversed taps (= gradient with respect to the input)
+// ------------------------------------------------------------------------------------------
+constexpr int DWT = 32;
+__global__ void __launch_bounds__(256)
+k_dwconv1d(const float *__restrict__ x, const float *__restrict__ w, float *__restrict__ y, int T, int d, int K, int flip) {
+    extern __shared__ float sm[];
+    float *tile = sm;                               // [DWT + K - 1][d]
+    float *wt = sm + (size_t)(DWT + K - 1) * d;     // [K][d]
+    const int b = blockIdx.y, t0 = blockIdx.x * DWT, pad = (K - 1) / 2, rows = DWT + K - 1;
+    for (int e = threadIdx.x; e < rows * d; e += blockDim.x) {
+        const int r = e / d, c = e % d, t = t0 - pad + r;
+        tile[e] = (t >= 0 && t < T) ? x[((int64_t)b * T + t) * d + c] : 0.0f;
+    }
+    for (int e = threadIdx.x; e < K * d; e += blockDim.x) {
+        const int k = e / d, c = e % d;
+        wt[e] = w[c * K + (flip ? K - 1 - k : k)];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < DWT * d; e += blockDim.x) {
+        const int tt = e / d, c = e % d, t = t0 + tt;
+        if (t >= T) break;
+        float acc = 0.0f;
+        for (int k = 0; k < K; ++k) acc = fmaf(wt[k * d + c], tile[(tt + k) * d + c], acc);
+        y[((int64_t)b * T + t) * d + c] = acc;
+    }
+}
+// dw[c,k] += sum_{b,t} dy[b,t,c] * x[b,t+k-pad,c]
+__global__ void __launch_bounds__(256)
+k_dwconv1d_wgrad(const float *__restrict__ x, const float *__restrict__ dy, float *__restrict__ dw, int T, int d, int K) {
+    extern __shared__ float sm[];
+    float *tile = sm;                               // [DWT + K - 1][d]  x
+    float *dt = sm + (size_t)(DWT + K - 1) * d;     // [DWT][d]          dy
+    const int b = blockIdx.y, t0 = blockIdx.x * DWT, pad = (K - 1) / 2, rows = DWT + K - 1;
+    for (int e = threadIdx.x; e < rows * d; e += blockDim.x) {
+        const int r = e / d, c = e % d, t = t0 - pad + r;
+        tile[e] = (t >= 0 && t < T) ? x[((int64_t)b * T + t) * d + c] : 0.0f;
+    }
+    for (int e = threadIdx.x; e < DWT * d; e += blockDim.x) {
+        const int tt = e / d, c = e % d, t = t0 + tt;
+        dt[e] = (t < T) ? dy[((int64_t)b * T + t) * d + c] : 0.0f;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < K * d; e += blockDim.x) {
+        const int k = e / d, c = e % d;
+        float acc = 0.0f;
+#pragma unroll 8
+        for (int tt = 0; tt < DWT; ++tt) acc = fmaf(dt[tt * d + c], tile[(tt + k) * d + c], acc);
+        atomicAdd(dw + c * K + k, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm1d in training mode over the M = B*T rows of c (M, d)   (convolution.py:141; eps 1e-5, momentum 0.1)
+// ------------------------------------------------------------------------------------------
+__global__ void k_bn_sums(const float *__restrict__ c, int M, int d, int rows_per_block, double *__restrict__ sums /* [2][d] */) {
+    const int col = blockIdx.y * blockDim.x + threadIdx.x;
+    if (col >= d) return;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    double s = 0.0, q = 0.0;
+    for (int m = r0; m < r1; ++m) {
+        const double v = c[(int64_t)m * d + col];
+        s += v;
+        q += v * v;
+    }
+    atomicAdd(sums + col, s);
+    atomicAdd(sums + d + col, q);
+}
+__global__ void k_bn_finalize(const double *__restrict__ sums, int M, int d, float momentum, float *__restrict__ stat /* [2][d] mean, rstd */,
+                              float *running_mean, float *running_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d) return;
+    const double mean = sums[c] / M;
+    double var = sums[d + c] / M - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stat[c] = (float)mean;
+    stat[d + c] = (float)(1.0 / sqrt(var + 1e-5));
+    if (running_mean) {
+        const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+        running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mean;
+        running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+// z = silu(gamma * (c - mean) * rstd + beta)
+__global__ void k_bn_silu_fwd(const float *__restrict__ c, const float *__restrict__ stat, const float *__restrict__ gamma,
+                              const float *__restrict__ beta, float *__restrict__ z, int64_t M, int d) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < M * d; e += (int64_t)gridDim.x * blockDim.x) {
+        const int col = (int)(e % d);
+        const float y = gamma[col] * (c[e] - stat[col]) * stat[d + col] + beta[col];
+        z[e] = y * sigmoid_f(y);
+    }
+}
+// dy = dz * silu'(y) written over dz; sums[0][c] += dy, sums[1][c] += dy * chat
+__global__ void k_bn_bwd_reduce(const float *__restrict__ c, const float *__restrict__ stat, const float *__restrict__ gamma,
+                                const float *__restrict__ beta, float *__restrict__ dz, int M, int d, int rows_per_block, double *__restrict__ sums) {
+    const int col = blockIdx.y * blockDim.x + threadIdx.x;
+    if (col >= d) return;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    const float mean = stat[col], rstd = stat[d + col], ga = gamma[col], be = beta[col];
+    double s = 0.0, q = 0.0;
+    for (int m = r0; m < r1; ++m) {
+        const int64_t e = (int64_t)m * d + col;
+        const float ch = (c[e] - mean) * rstd, y = ga * ch + be, sg = sigmoid_f(y);
+        const float dy = dz[e] * (sg * (1.0f + y * (1.0f - sg)));
+        dz[e] = dy;
+        s += dy;
+        q += (double)dy * ch;
+    }
+    atomicAdd(sums + col, s);
+    atomicAdd(sums + d + col, q);
+}
+// dc = gamma * rstd * (dy - sum(dy)/M - chat * sum(dy*chat)/M)    (dy in, dc out, in place); block 0 also writes dgamma, dbeta
+__global__ void k_bn_bwd_apply(const float *__restrict__ c, const float *__restrict__ stat, const float *__restrict__ gamma,
+                               const double *__restrict__ sums, float *__restrict__ dy, int64_t M, int d, float *dgamma, float *dbeta) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < M * d; e += (int64_t)gridDim.x * blockDim.x) {
+        const int col = (int)(e % d);
+        const float rstd = stat[d + col], ch = (c[e] - stat[col]) * rstd;
+        const float s = (float)(sums[col] / (double)M), q = (float)(sums[d + col] / (double)M);
+        dy[e] = gamma[col] * rstd * (dy[e] - s - ch * q);
+    }
+    if (blockIdx.x == 0)
+        for (int col = threadIdx.x; col < d; col += blockDim.x) {
+            dbeta[col] = (float)sums[col];
+            dgamma[col] = (float)sums[d + col];
+        }
+}
+
+// ------------------------------------------------------------------------------------------
+// relative-position attention, reference formulation (attention.py:82-101), probabilities kept for the backward pass.
+//   qkv (M, 3d): q | k | v, head-major features; pos (2T-1, d); P (B, nh, T, T)
+// thread layout of the tile kernels: 256 threads = 32 rows x 8 column groups
+// ------------------------------------------------------------------------------------------
+constexpr int TQ = 32;    // rows per CTA
+constexpr int TK = 64;    // columns per step
+
+// S[b,h,i,j] = ((q_i+u).k_j + (q_i+v).pos[T-1-i+j]) / sqrt(dh)
+template <int DH>
+__global__ void __launch_bounds__(256)
+k_att_scores(const float *__restrict__ qkv, const float *__restrict__ pos, const float *__restrict__ ub, const float *__restrict__ vb,
+             float *__restrict__ S, int T, int d, int dh, float inv_sqrt) {
+    extern __shared__ float sm[];
+    constexpr int LD = DH + 1;
+    float *ks = sm;                         // [TK][LD]
+    float *ps = ks + TK * LD;               // [TQ+TK-1][LD]
+    float *st = ps + (TQ + TK - 1) * LD;    // [TQ][TK+1]
+    const int tid = threadIdx.x, ti = tid / 8, tj = tid % 8;
+    const int i0 = blockIdx.x * TQ, hd = blockIdx.y, b = blockIdx.z, i = i0 + ti;
+    const int ld = 3 * d;
+    const float *base = qkv + (int64_t)b * T * ld;
+    float qu[DH], qv[DH];
+#pragma unroll
+    for (int c = 0; c < DH; ++c) {
+        const float q = (c < dh && i < T) ? base[(int64_t)i * ld + hd * dh + c] : 0.0f;
+        qu[c] = (c < dh) ? q + ub[hd * dh + c] : 0.0f;
+        qv[c] = (c < dh) ? q + vb[hd * dh + c] : 0.0f;
+    }
+    float *Sb = S + ((int64_t)(b * gridDim.y + hd) * T) * T;
+    for (int j0 = 0; j0 < T; j0 += TK) {
+        __syncthreads();
+        for (int e = tid; e < TK * DH; e += 256) {
+            const int r = e / DH, c = e % DH, j = j0 + r;
+            ks[r * LD + c] = (j < T && c < dh) ? base[(int64_t)j * ld + d + hd * dh + c] : 0.0f;
+        }
+        const int pbase = T - 1 - (i0 + TQ - 1) + j0;
+        for (int e = tid; e < (TQ + TK - 1) * DH; e += 256) {
+            const int r = e / DH, c = e % DH, pr = pbase + r;
+            ps[r * LD + c] = (pr >= 0 && pr <= 2 * T - 2 && c < dh) ? pos[(int64_t)pr * d + hd * dh + c] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int n = 0; n < TK / 8; ++n) {
+            const int jl = tj + 8 * n;
+            const float *kr = ks + jl * LD, *pr = ps + (TQ - 1 - ti + jl) * LD;
+            float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < DH; ++c) {
+                c1 = fmaf(qu[c], kr[c], c1);
+                c2 = fmaf(qv[c], pr[c], c2);
+            }
+            st[ti * (TK + 1) + jl] = (c1 + c2) * inv_sqrt;
+        }
+        __syncthreads();
+        for (int e = tid; e < TQ * TK; e += 256) {
+            const int r = e / TK, c = e % TK;
+            if (i0 + r < T && j0 + c < T) Sb[(int64_t)(i0 + r) * T + j0 + c] = st[r * (TK + 1) + c];
+        }
+    }
+}
+
+// in-place softmax over rows of length T, one warp per row
+__global__ void k_softmax_rows(float *__restrict__ S, int64_t rows, int T) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float *p = S + row * T;
+    float mx = -INFINITY;
+    for (int j = lane; j < T; j += 32) mx = fmaxf(mx, p[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float s = 0.f;
+    for (int j = lane; j < T; j += 32) {
+        const float e = expf(p[j] - mx);
+        p[j] = e;
+        s += e;
+    }
+    s = warp_sum_f(s);
+    const float inv = 1.0f / s;
+    for (int j = lane; j < T; j += 32) p[j] *= inv;
+}
+
+// ctx[b,i,h*dh+c] = sum_j dropout(P)[b,h,i,j] * v[b,j,h,c]
+template <int DH>
+__global__ void __launch_bounds__(256)
+k_att_pv(const float *__restrict__ qkv, const float *__restrict__ P, float *__restrict__ ctx, int T, int d, int dh, Drop dr) {
+    extern __shared__ float sm[];
+    constexpr int LD = DH + 1;
+    float *vs = sm;                    // [TK][LD]
+    float *pt = vs + TK * LD;          // [TQ][TK+1]
+    const int tid = threadIdx.x, ti = tid / 8, tj = tid % 8;
+    const int i0 = blockIdx.x * TQ, hd = blockIdx.y, b = blockIdx.z, i = i0 + ti;
+    const int ld = 3 * d;
+    const float *base = qkv + (int64_t)b * T * ld;
+    const int64_t prow0 = ((int64_t)(b * gridDim.y + hd) * T);
+    float o[(DH + 7) / 8];
+#pragma unroll
+    for (int k = 0; k < (DH + 7) / 8; ++k) o[k] = 0.0f;
+    for (int j0 = 0; j0 < T; j0 += TK) {
+        __syncthreads();
+        for (int e = tid; e < TK * DH; e += 256) {
+            const int r = e / DH, c = e % DH, j = j0 + r;
+            vs[r * LD + c] = (j < T && c < dh) ? base[(int64_t)j * ld + 2 * d + hd * dh + c] : 0.0f;
+        }
+        for (int e = tid; e < TQ * TK; e += 256) {
+            const int r = e / TK, c = e % TK;
+            float v = 0.0f;
+            if (i0 + r < T && j0 + c < T) {
+                const int64_t idx = (prow0 + i0 + r) * T + j0 + c;
+                v = P[idx] * drop_scale(dr, (uint64_t)idx);
+            }
+            pt[r * (TK + 1) + c] = v;
+        }
+        __syncthreads();
+        for (int jl = 0; jl < TK; ++jl) {
+            const float p = pt[ti * (TK + 1) + jl];
+            const float *vr = vs + jl * LD;
+#pragma unroll
+            for (int k = 0; k < (DH + 7) / 8; ++k) {
+                const int c = tj + 8 * k;
+                if (c < DH) o[k] = fmaf(p, vr[c], o[k]);
+            }
+        }
+    }
+    if (i < T) {
+#pragma unroll
+        for (int k = 0; k < (DH + 7) / 8; ++k) {
+            const int c = tj + 8 * k;
+            if (c < dh) ctx[((int64_t)b * T + i) * d + hd * dh + c] = o[k];
+        }
+    }
+}
+
+// Row pass of the backward: dS = P * (mask * (dctx.v) - delta) / sqrt(dh) with delta_i = dctx_i . ctx_i, written to dS;
+// dq_i = sum_j dS[i,j] (k_j + pos[T-1-i+j]); du += sum_i sum_j dS k_j; dvb += sum_i sum_j dS pos
+template <int DH>
+__global__ void __launch_bounds__(256)
+k_att_bwd_rows(const float *__restrict__ qkv, const float *__restrict__ pos, const float *__restrict__ P, const float *__restrict__ ctx,
+               const float *__restrict__ dctx, float *__restrict__ dS, float *__restrict__ dqkv, float *__restrict__ du, float *__restrict__ dvb,
+               int T, int d, int dh, float inv_sqrt, Drop dr) {
+    extern __shared__ float sm[];
+    constexpr int LD = DH + 1;
+    float *ks = sm;                         // [TK][LD]
+    float *vs = ks + TK * LD;               // [TK][LD]
+    float *ps = vs + TK * LD;               // [TQ+TK-1][LD]
+    float *pt = ps + (TQ + TK - 1) * LD;    // [TQ][TK+1]
+    const int tid = threadIdx.x, ti = tid / 8, tj = tid % 8;
+    const int i0 = blockIdx.x * TQ, hd = blockIdx.y, b = blockIdx.z, i = i0 + ti;
+    const int ld = 3 * d;
+    const float *base = qkv + (int64_t)b * T * ld;
+    const int64_t prow0 = ((int64_t)(b * gridDim.y + hd) * T);
+    float dc[DH], accA[DH], accB[DH];
+    float delta = 0.f;
+#pragma unroll
+    for (int c = 0; c < DH; ++c) {
+        const bool ok = (c < dh && i < T);
+        dc[c] = ok ? dctx[((int64_t)b * T + i) * d + hd * dh + c] : 0.0f;
+        delta = fmaf(dc[c], ok ? ctx[((int64_t)b * T + i) * d + hd * dh + c] : 0.0f, delta);
+        accA[c] = 0.f;
+        accB[c] = 0.f;
+    }
+    for (int j0 = 0; j0 < T; j0 += TK) {
+        __syncthreads();
+        for (int e = tid; e < TK * DH; e += 256) {
+            const int r = e / DH, c = e % DH, j = j0 + r;
+            const bool ok = (j < T && c < dh);
+            ks[r * LD + c] = ok ? base[(int64_t)j * ld + d + hd * dh + c] : 0.0f;
+            vs[r * LD + c] = ok ? base[(int64_t)j * ld + 2 * d + hd * dh + c] : 0.0f;
+        }
+        const int pbase = T - 1 - (i0 + TQ - 1) + j0;
+        for (int e = tid; e < (TQ + TK - 1) * DH; e += 256) {
+            const int r = e / DH, c = e % DH, pr = pbase + r;
+            ps[r * LD + c] = (pr >= 0 && pr <= 2 * T - 2 && c < dh) ? pos[(int64_t)pr * d + hd * dh + c] : 0.0f;
+        }
+        for (int e = tid; e < TQ * TK; e += 256) {
+            const int r = e / TK, c = e % TK;
+            pt[r * (TK + 1) + c] = (i0 + r < T && j0 + c < T) ? P[(prow0 + i0 + r) * T + j0 + c] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int n = 0; n < TK / 8; ++n) {
+            const int jl = tj + 8 * n;
+            const float *vr = vs + jl * LD;
+            float dp = 0.f;
+#pragma unroll
+            for (int c = 0; c < DH; ++c) dp = fmaf(dc[c], vr[c], dp);
+            const float p = pt[ti * (TK + 1) + jl];
+            float ds = 0.0f;
+            if (i < T && j0 + jl < T) {
+                const int64_t idx = (prow0 + i) * T + j0 + jl;
+                ds = p * (dp * drop_scale(dr, (uint64_t)idx) - delta) * inv_sqrt;
+            }
+            pt[ti * (TK + 1) + jl] = ds;
+            const float *kr = ks + jl * LD, *pr = ps + (TQ - 1 - ti + jl) * LD;
+#pragma unroll
+            for (int c = 0; c < DH; ++c) {
+                accA[c] = fmaf(ds, kr[c], accA[c]);
+                accB[c] = fmaf(ds, pr[c], accB[c]);
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < TQ * TK; e += 256) {
+            const int r = e / TK, c = e % TK;
+            if (i0 + r < T && j0 + c < T) dS[(prow0 + i0 + r) * T + j0 + c] = pt[r * (TK + 1) + c];
+        }
+    }
+    // reduce over the 8 column groups of a row (lanes tj = 0..7 are consecutive lanes)
+#pragma unroll
+    for (int c = 0; c < DH; ++c) {
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            accA[c] += __shfl_xor_sync(0xffffffffu, accA[c], o);
+            accB[c] += __shfl_xor_sync(0xffffffffu, accB[c], o);
+        }
+    }
+    __syncthreads();
+    float *ra = sm, *rb = sm + TQ * LD;      // [TQ][LD] each (aliases the tiles)
+    if (tj == 0) {
+#pragma unroll
+        for (int c = 0; c < DH; ++c) {
+            ra[ti * LD + c] = accA[c];
+            rb[ti * LD + c] = accB[c];
+            if (i < T && c < dh) dqkv[((int64_t)b * T + i) * ld + hd * dh + c] = accA[c] + accB[c];
+        }
+    }
+    __syncthreads();
+    if (tid < dh) {
+        float sa = 0.f, sb = 0.f;
+        for (int r = 0; r < TQ; ++r) {
+            sa += ra[r * LD + tid];
+            sb += rb[r * LD + tid];
+        }
+        atomicAdd(du + hd * dh + tid, sa);
+        atomicAdd(dvb + hd * dh + tid, sb);
+    }
+}
+
+// Column pass: dv_j = sum_i dropout(P)[i,j] dctx_i ; dk_j = sum_i dS[i,j] (q_i + u).  256 threads = 32 columns j x 8 row groups
+template <int DH>
+__global__ void __launch_bounds__(256)
+k_att_bwd_cols(const float *__restrict__ qkv, const float *__restrict__ ub, const float *__restrict__ P, const float *__restrict__ dS,
+               const float *__restrict__ dctx, float *__restrict__ dqkv, int T, int d, int dh, Drop dr) {
+    extern __shared__ float sm[];
+    constexpr int LD = DH + 1;
+    float *qs = sm;                 // [TK][LD]  q + u
+    float *ds_ = qs + TK * LD;      // [TK][LD]  dctx
+    const int tid = threadIdx.x, tjj = tid % 32, tii = tid / 32;
+    const int j0 = blockIdx.x * 32, hd = blockIdx.y, b = blockIdx.z, j = j0 + tjj;
+    const int ld = 3 * d;
+    const float *base = qkv + (int64_t)b * T * ld;
+    const int64_t prow0 = ((int64_t)(b * gridDim.y + hd) * T);
+    float accV[DH], accK[DH];
+#pragma unroll
+    for (int c = 0; c < DH; ++c) { accV[c] = 0.f; accK[c] = 0.f; }
+    for (int i0 = 0; i0 < T; i0 += TK) {
+        __syncthreads();
+        for (int e = tid; e < TK * DH; e += 256) {
+            const int r = e / DH, c = e % DH, i = i0 + r;
+            const bool ok = (i < T && c < dh);
+            qs[r * LD + c] = ok ? base[(int64_t)i * ld + hd * dh + c] + ub[hd * dh + c] : 0.0f;
+            ds_[r * LD + c] = ok ? dctx[((int64_t)b * T + i) * d + hd * dh + c] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int n = 0; n < TK / 8; ++n) {
+            const int il = tii + 8 * n, i = i0 + il;
+            float p = 0.f, g = 0.f;
+            if (i < T && j < T) {
+                const int64_t idx = (prow0 + i) * T + j;
+                p = P[idx] * drop_scale(dr, (uint64_t)idx);
+                g = dS[idx];
+            }
+            const float *dr_ = ds_ + il * LD, *qr = qs + il * LD;
+#pragma unroll
+            for (int c = 0; c < DH; ++c) {
+                accV[c] = fmaf(p, dr_[c], accV[c]);
+                accK[c] = fmaf(g, qr[c], accK[c]);
+            }
+        }
+    }
+    // reduce over the 8 row groups through shared memory: red [8][32][LD]
+    __syncthreads();
+    float *red = sm;
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int c = 0; c < DH; ++c) red[(tii * 32 + tjj) * LD + c] = pass ? accK[c] : accV[c];
+        __syncthreads();
+        for (int e = tid; e < 32 * DH; e += 256) {
+            const int r = e / DH, c = e % DH;
+            if (j0 + r < T && c < dh) {
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) s += red[(w * 32 + r) * LD + c];
+                dqkv[((int64_t)b * T + j0 + r) * ld + (pass ? d : 2 * d) + hd * dh + c] = s;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// dpos[r, h*dh+c] += sum_{b,i} dS[b,h,i, r-(T-1)+i] * (q[b,i,h,c] + v_bias[h,c])   lanes <-> 32 consecutive r
+template <int DH>
+__global__ void __launch_bounds__(256)
+k_att_bwd_pos(const float *__restrict__ qkv, const float *__restrict__ vb, const float *__restrict__ dS, float *__restrict__ dpos,
+              int B, int T, int d, int dh, int nh, int b_per_block) {
+    extern __shared__ float sm[];
+    constexpr int LD = (DH + 3) / 4 * 4;
+    float *qt = sm;                       // [64][LD]  q + v_bias of 64 (b,i) rows
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int r0 = blockIdx.x * 32, hd = blockIdx.y, r = r0 + lane;
+    const int b0 = blockIdx.z * b_per_block, b1 = min(B, b0 + b_per_block);
+    const int ld = 3 * d;
+    const int ilo = max(0, T - 1 - (r0 + 31)), ihi = min(T - 1, 2 * T - 2 - r0);      // rows with at least one valid column
+    float acc[DH];
+#pragma unroll
+    for (int c = 0; c < DH; ++c) acc[c] = 0.f;
+    if (ihi >= ilo) {
+        const int ni = ihi - ilo + 1;
+        const int total = (b1 - b0) * ni;
+        for (int base = 0; base < total; base += 64) {
+            __syncthreads();
+            for (int e = tid; e < 64 * DH; e += 256) {
+                const int rr = e / DH, c = e % DH, t = base + rr;
+                float v = 0.f;
+                if (t < total && c < dh) {
+                    const int b = b0 + t / ni, i = ilo + t % ni;
+                    v = qkv[((int64_t)b * T + i) * ld + hd * dh + c] + vb[hd * dh + c];
+                }
+                qt[rr * LD + c] = v;
+            }
+            __syncthreads();
+#pragma unroll 1
+            for (int n = 0; n < 8; ++n) {
+                const int rr = w * 8 + n, t = base + rr;
+                if (t >= total) break;
+                const int b = b0 + t / ni, i = ilo + t % ni;
+                const int j = r - (T - 1) + i;
+                float g = 0.f;
+                if (r <= 2 * T - 2 && j >= 0 && j < T) g = dS[(((int64_t)(b * nh + hd) * T) + i) * T + j];
+                const float *qr = qt + rr * LD;
+#pragma unroll
+                for (int c = 0; c < DH; ++c) acc[c] = fmaf(g, qr[c], acc[c]);
+            }
+        }
+    }
+    __syncthreads();
+    float *red = sm;                      // [8][32][DH+1]
+    constexpr int LR = DH + 1;
+#pragma unroll
+    for (int c = 0; c < DH; ++c) red[(w * 32 + lane) * LR + c] = acc[c];
+    __syncthreads();
+    for (int e = tid; e < 32 * DH; e += 256) {
+        const int rr = e / DH, c = e % DH;
+        if (r0 + rr <= 2 * T - 2 && c < dh) {
+            float s = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < 8; ++ww) s += red[(ww * 32 + rr) * LR + c];
+            atomicAdd(dpos + (int64_t)(r0 + rr) * d + hd * dh + c, s);
+        }
+    }
+}
+
+// relative positional table rows k = 0..2T-2 <-> offset T-1-k (embedding.py:42-56)
+__global__ void k_rel_pos_table(float *__restrict__ pe, int T, int d) {
+    const int R = 2 * T - 1;
+    const float neg = -(logf(10000.0f) / (float)d);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < R * d; e += gridDim.x * blockDim.x) {
+        const int k = e / d, c = e % d, m = c & ~1;
+        const float arg = (float)(T - 1 - k) * expf((float)m * neg);
+        pe[e] = (c & 1) ? cosf(arg) : sinf(arg);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// convolutional front-end (convolution.py:190-237), channel-last activations: a1 (B,T2,F2,cc), a2 (B,T,F,cc)
+// ------------------------------------------------------------------------------------------
+__global__ void k_fe_conv1(const float *__restrict__ img, int64_t sb, int64_t sw, int64_t sh, const float *__restrict__ w1,
+                           const float *__restrict__ b1, float *__restrict__ a1, int B, int W, int H, int T2, int F2, int cc) {
+    const int64_t total = (int64_t)B * T2 * F2 * cc;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % cc);
+        int64_t r = idx / cc;
+        const int f2 = (int)(r % F2);
+        r /= F2;
+        const int t2 = (int)(r % T2), b = (int)(r / T2);
+        float acc = b1[c];
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int w = 2 * t2 - 1 + kh;
+            if (w < 0 || w >= W) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int y = 2 * f2 - 1 + kw;
+                if (y < 0 || y >= H) continue;
+                acc = fmaf(w1[c * 9 + kh * 3 + kw], img[b * sb + w * sw + y * sh], acc);
+            }
+        }
+        a1[idx] = fmaxf(acc, 0.0f);
+    }
+}
+__global__ void k_fe_dw(const float *__restrict__ a1, const float *__restrict__ wdw, const float *__restrict__ bdw, float *__restrict__ a2,
+                        int B, int T2, int F2, int T, int F, int cc) {
+    const int64_t total = (int64_t)B * T * F * cc;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % cc);
+        int64_t r = idx / cc;
+        const int f = (int)(r % F);
+        r /= F;
+        const int t = (int)(r % T), b = (int)(r / T);
+        float acc = bdw[c];
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int t2 = 2 * t - 1 + kh;
+            if (t2 < 0 || t2 >= T2) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int f2 = 2 * f - 1 + kw;
+                if (f2 < 0 || f2 >= F2) continue;
+                acc = fmaf(wdw[c * 9 + kh * 3 + kw], a1[(((int64_t)b * T2 + t2) * F2 + f2) * cc + c], acc);
+            }
+        }
+        a2[idx] = acc;
+    }
+}
+// in place: v = (act > 0) ? g : 0     (ReLU backward)
+__global__ void k_relu_bwd(const float *__restrict__ act, float *__restrict__ g, int64_t n) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+        if (!(act[e] > 0.0f)) g[e] = 0.0f;
+}
+// dwdw[c,kh,kw] += sum da2[b,t,f,c] * a1[b,2t-1+kh,2f-1+kw,c]; dbdw[c] += sum da2.   blockDim (256) % cc == 0
+__global__ void __launch_bounds__(256)
+k_fe_dw_wgrad(const float *__restrict__ a1, const float *__restrict__ da2, float *__restrict__ dw, float *__restrict__ db,
+              int B, int T2, int F2, int T, int F, int cc) {
+    __shared__ float red[256][11];
+    const int64_t total = (int64_t)B * T * F * cc;
+    float acc[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc[k] = 0.f;
+    for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
+        const int c = (int)(idx % cc);
+        int64_t r = idx / cc;
+        const int f = (int)(r % F);
+        r /= F;
+        const int t = (int)(r % T), b = (int)(r / T);
+        const float g = da2[idx];
+        acc[9] += g;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int t2 = 2 * t - 1 + kh;
+            if (t2 < 0 || t2 >= T2) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int f2 = 2 * f - 1 + kw;
+                if (f2 < 0 || f2 >= F2) continue;
+                acc[kh * 3 + kw] = fmaf(g, a1[(((int64_t)b * T2 + t2) * F2 + f2) * cc + c], acc[kh * 3 + kw]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 10; ++k) red[threadIdx.x][k] = acc[k];
+    __syncthreads();
+    for (int e = threadIdx.x; e < cc * 10; e += 256) {
+        const int c = e / 10, k = e % 10;
+        float s = 0.f;
+        for (int t = c; t < 256; t += cc) s += red[t][k];
+        if (k < 9) atomicAdd(dw + c * 9 + k, s);
+        else atomicAdd(db + c, s);
+    }
+}
+// da1 = relu'(a1) * conv_transpose(da2, wdw), written over a1
+__global__ void k_fe_dw_dgrad_relu(float *__restrict__ a1, const float *__restrict__ da2, const float *__restrict__ wdw,
+                                   int B, int T2, int F2, int T, int F, int cc) {
+    const int64_t total = (int64_t)B * T2 * F2 * cc;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % cc);
+        int64_t r = idx / cc;
+        const int f2 = (int)(r % F2);
+        r /= F2;
+        const int t2 = (int)(r % T2), b = (int)(r / T2);
+        float acc = 0.f;
+        if (a1[idx] > 0.0f) {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                const int tn = t2 + 1 - kh;
+                if (tn < 0 || (tn & 1)) continue;
+                const int t = tn >> 1;
+                if (t >= T) continue;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int fn = f2 + 1 - kw;
+                    if (fn < 0 || (fn & 1)) continue;
+                    const int f = fn >> 1;
+                    if (f >= F) continue;
+                    acc = fmaf(wdw[c * 9 + kh * 3 + kw], da2[(((int64_t)b * T + t) * F + f) * cc + c], acc);
+                }
+            }
+        }
+        a1[idx] = acc;
+    }
+}
+// dW1[c,kh,kw] += sum da1[b,t2,f2,c] * img[b,2t2-1+kh,2f2-1+kw]; db1[c] += sum da1
+__global__ void __launch_bounds__(256)
+k_fe_conv1_wgrad(const float *__restrict__ img, int64_t sb, int64_t sw, int64_t sh, const float *__restrict__ da1, float *__restrict__ dw,
+                 float *__restrict__ db, int B, int W, int H, int T2, int F2, int cc) {
+    __shared__ float red[256][11];
+    const int64_t total = (int64_t)B * T2 * F2 * cc;
+    float acc[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc[k] = 0.f;
+    for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
+        int64_t r = idx / cc;
+        const int f2 = (int)(r % F2);
+        r /= F2;
+        const int t2 = (int)(r % T2), b = (int)(r / T2);
+        const float g = da1[idx];
+        acc[9] += g;
+        if (g == 0.0f) continue;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int w = 2 * t2 - 1 + kh;
+            if (w < 0 || w >= W) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int y = 2 * f2 - 1 + kw;
+                if (y < 0 || y >= H) continue;
+                acc[kh * 3 + kw] = fmaf(g, img[b * sb + w * sw + y * sh], acc[kh * 3 + kw]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 10; ++k) red[threadIdx.x][k] = acc[k];
+    __syncthreads();
+    for (int e = threadIdx.x; e < cc * 10; e += 256) {
+        const int c = e / 10, k = e % 10;
+        float s = 0.f;
+        for (int t = c; t < 256; t += cc) s += red[t][k];
+        if (k < 9) atomicAdd(dw + c * 9 + k, s);
+        else atomicAdd(db + c, s);
+    }
+}
+// out.0.weight (d, cc*F) column c*F+f  <->  (d, F*cc) column f*cc+c ; to_raw: dst is the raw layout
+__global__ void k_permute_wout(const float *__restrict__ src, float *__restrict__ dst, int d, int cc, int F, int to_raw) {
+    const int n = d * cc * F;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int row = e / (cc * F), col = e % (cc * F);          // col in the channel-last layout: f*cc + c
+        const int f = col / cc, c = col % cc;
+        const int raw = row * cc * F + c * F + f;
+        if (to_raw) dst[raw] = src[e];
+        else dst[e] = src[raw];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// AdamW, the arithmetic of torch.optim.AdamW's single-tensor path (model.py:272-274)
+// ------------------------------------------------------------------------------------------
+__global__ void k_adamw(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, int64_t n,
+                        float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const float gr = g[e];
+        float pv = p[e] * (1.0f - lr * wd);
+        const float mv = m[e] + (gr - m[e]) * (1.0f - beta1);              // lerp, as torch does
+        const float vv = beta2 * v[e] + (1.0f - beta2) * gr * gr;
+        m[e] = mv;
+        v[e] = vv;
+        const float denom = sqrtf(vv) / bc2_sqrt + eps;
+        pv -= (lr / bc1) * (mv / denom);
+        p[e] = pv;
+    }
+}
+
+}  // namespace train
+}  // namespace cocr

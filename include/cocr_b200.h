@@ -208,6 +208,46 @@ int64_t cocr_launch_count(const cocr_handle *h);
 int cocr_set_profiling(cocr_handle *h, int enabled);
 int cocr_profile_report(cocr_handle *h, char *buf, size_t cap);
 
+/* ---- One data-parallel TRAINING step (BASELINE configs[3]) ------------------------------------
+ * Replaces, for one rank, RecognitionModel.training_step -> _step (model.py:129-158) + autograd's backward pass +
+ * torch.optim.AdamW.step (model.py:272-274): the encoder in train() mode (BatchNorm1d batch statistics with the
+ * running-statistics update, convolution.py:141; dropout where the reference has it: feed_forward.py:48-53,
+ * attention.py:99,134, convolution.py:146,225), decoder nn.Linear, log_softmax, CTCLoss(reduction='sum',
+ * zero_infinity=True), and hand-written backward kernels for every module on the path.  fp32.
+ *
+ * Parameters / gradients / optimiser moments are FLAT fp32 device buffers owned by the caller.  The layout is exported:
+ * cocr_train_layout gives the buffer length (n_total floats), the length of the trainable prefix (n_trainable: what a
+ * data-parallel caller all-reduces, what AdamW updates) and the number of entries; cocr_train_entry gives, per entry, the
+ * state-dict key (below the ModuleDict: "encoder...." / "decoder....", SURVEY.md 8a "Weights"), offset and element count,
+ * every tensor in the reference's own shape and element order.  The BatchNorm running statistics (not trainable) follow the
+ * trainable prefix.  The handle needs hyper-parameters only (no cocr_set_weight / cocr_finalize_weights).
+ *
+ * cocr_train_step: params_dev is read (running statistics are UPDATED in place), grads_dev (n_total floats) is overwritten
+ * with d loss / d param.  img/strides/widths as cocr_encode; targets_dev the 1-D int32 concatenation of the label sequences,
+ * target_lens_dev (B) int32, max_target_len an upper bound; loss_sum_dev 1 float; loss_per_line_dev (B) or NULL.  The mask of
+ * every dropout site is a pure function of (cfg->seed, site, element index) - cocr_dropout_mask returns the factors
+ * (0 or 1/(1-p)) so a checker can replay them.  Attention is unmasked, as in the reference (encoder.py:67-103).
+ * debug_taps_dev: NULL, or 2 * (1 + 5 * num_layers) * B * T * encoder_dim floats receiving the residual stream after the
+ * front-end and after each module of each block, followed by d loss / d (those tensors). */
+typedef struct cocr_train_config {
+    float input_dropout_p, feed_forward_dropout_p, attention_dropout_p, conv_dropout_p;   /* encoder.py:135-152 */
+    float bn_momentum;                                                                   /* nn.BatchNorm1d default 0.1 */
+    uint32_t reserved;
+    uint64_t seed;
+} cocr_train_config;
+
+int cocr_train_layout(cocr_handle *h, int64_t *n_total, int64_t *n_trainable, int32_t *n_entries);
+int cocr_train_entry(cocr_handle *h, int32_t index, char *key_buf, size_t key_cap, int64_t *offset, int64_t *numel, int32_t *trainable);
+int cocr_train_workspace_bytes(cocr_handle *h, int32_t B, int32_t W, size_t *bytes);
+int cocr_train_step(cocr_handle *h, float *params_dev, float *grads_dev, const float *img_dev, int64_t stride_b, int64_t stride_w,
+                    int64_t stride_h, const int32_t *widths_dev, int32_t B, int32_t W, const int32_t *targets_dev,
+                    const int32_t *target_lens_dev, int32_t max_target_len, const cocr_train_config *cfg, void *stream,
+                    float *loss_sum_dev, float *loss_per_line_dev, float *debug_taps_dev);
+/* torch.optim.AdamW single-tensor arithmetic over n floats; `step` counts from 1. */
+int cocr_adamw_step(cocr_handle *h, float *params_dev, const float *grads_dev, float *exp_avg_dev, float *exp_avg_sq_dev, int64_t n,
+                    float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, void *stream);
+int cocr_dropout_mask(cocr_handle *h, uint64_t seed, uint32_t site, float p, int64_t n, void *stream, float *out_dev);
+
 /* Built-in self checks of individual kernels against a scalar device reference; used by
  * tests/ on the GPU box.  `which`: see csrc/selftest.cu.  Returns COCR_OK or an error and
  * writes the max abs error into *max_err (may be NULL). */
