@@ -4,6 +4,7 @@
     python bench.py --gpus N --steps K --warmup W            # our arm (libcocr_b200.so on N B200s)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (port), host cores
     python bench.py --config 1|2|5 ...                       # BASELINE.json configs[0|1|4] (default 2 = configs[1])
+    python bench.py --config 4 ...                           # configs[3]: training step, 32 lines per GPU, CTC loss + all-reduce + AdamW
 
 Workload (default, BASELINE.json configs[1]): default-spec conformer, batches of 256 lines, 96 x 1536 px, 256 classes,
 bf16.  One "step" = `--passes-per-step` (default 16) passes of the hot path over 256-line batches = 4096 lines per GPU:
@@ -35,6 +36,9 @@ CONFIGS = {
     1: dict(batch=8, width=1024, classes=256, precision='fp32', passes=1, name='configs[0]'),
     # configs[1]: the configuration the metric is quoted on
     2: dict(batch=256, width=1536, classes=256, precision='bf16', passes=16, name='configs[1]'),
+    # configs[3]: one data-parallel TRAINING step (forward in train() mode, CTC loss, backward, gradient all-reduce, AdamW);
+    # 32 lines per GPU per step (the weak-scaling variant of SURVEY.md 8d cfg 4)
+    4: dict(batch=32, width=1536, classes=256, precision='fp32', passes=1, name='configs[3]'),
     # configs[4]: long lines, CJK-sized alphabet
     5: dict(batch=64, width=4096, classes=10000, precision='bf16', passes=4, name='configs[4]'),
 }
@@ -589,9 +593,280 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------
+# configs[3]: the training step
+# ----------------------------------------------------------------------------------------------
+def train_batch(args, hp, seed, device=None):
+    """SURVEY.md 8d cfg 4: B lines of 96 x W px, targets of length U{20..80}, labels U{1..C-1}."""
+    rng = np.random.RandomState(seed)
+    B, W, C = args.batch, args.width, args.classes
+    tl = rng.randint(20, 81, size=B).astype(np.int64)
+    tg = rng.randint(1, C, size=int(tl.sum())).astype(np.int64)
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand((B, 1, hp['height'], W), generator=g, dtype=torch.float32)
+    return {'image': img, 'seq_lens': torch.full((B,), W, dtype=torch.int64), 'target': torch.from_numpy(tg), 'target_lens': torch.from_numpy(tl)}
+
+
+def train_flops_per_line(W, C, hp):
+    """forward + data gradients + weight gradients = 3 x the forward contractions (attention: 3 forward, 6 backward)."""
+    from conformer_ocr_b200 import synthetic as S
+    return 3.0 * S.flops_per_line(W, C, hp)
+
+
+def port_train_step_factory(args, hp, device, n_lines, autocast=False):
+    """The reference's training step as torch runs it (oracle/torch_train_port.py: train()-mode modules, autograd,
+    torch.optim.AdamW) - baseline leg only."""
+    from oracle import torch_train_port as TTP
+    from conformer_ocr_b200 import synthetic as S
+    w = {k: torch.from_numpy(v.copy()).to(device) for k, v in S.make_weights(hp, args.classes, seed=0).items()}
+    for k, v in w.items():
+        v.requires_grad_(not k.endswith(('running_mean', 'running_var')))
+    opt = torch.optim.AdamW([v for v in w.values() if v.requires_grad], lr=1e-3, weight_decay=1e-3)
+    a = argparse.Namespace(**vars(args))
+    a.batch = n_lines
+    b = train_batch(a, hp, seed=77)
+    img, tg = b['image'].to(device), b['target'].to(device)
+
+    def one_step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast(device.type, dtype=torch.bfloat16, enabled=autocast):
+            probits, olens, _ = TTP.train_forward(img, b['seq_lens'], w, hp, dropout=0.1)
+        logp = torch.nn.functional.log_softmax(probits.float(), dim=-1)
+        loss = torch.nn.functional.ctc_loss(logp.transpose(0, 1), tg, olens, b['target_lens'], blank=0, reduction='sum', zero_infinity=True)
+        loss.backward()
+        opt.step()
+        return float(loss.item())
+    return one_step
+
+
+def time_cpu_train(args, hp, reps, warm):
+    torch.set_num_threads(os.cpu_count() or 1)
+    n = max(1, min(4, args.batch))
+    step = port_train_step_factory(args, hp, torch.device('cpu'), n)
+    for _ in range(warm):
+        step()
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    return n, torch.get_num_threads(), times
+
+
+TRAIN_CPU_NOTE = ('the reference\'s training step as torch runs it on the host cores: train()-mode port of its modules '
+                  '(oracle/torch_train_port.py, pinned to the unmodified reference modules by tests/golden/train_*.npz), autograd, '
+                  'torch.optim.AdamW; dropout 0.1')
+
+
+def run_reference_train(args):
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    hp = arch_hp(hparams())
+    n, cores, times = time_cpu_train(args, hp, reps=max(1, args.steps), warm=1)
+    total = sum(times)
+    lps = n * len(times) / total
+    sample = f'{n} lines of 96x{args.width} px per step ({len(times)} steps), fp32, torch CPU ops + autograd + AdamW, {cores} threads'
+    out = dict(impl='reference', metric='training lines/sec', value=lps, unit='lines/s', n_gpus=args.gpus, steps=len(times), warmup=args.warmup,
+               ms_per_step=1e3 * total / len(times), higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+               config=dict(workload=train_workload_name(args), sample=sample, note=TRAIN_CPU_NOTE),
+               cpu_baseline=dict(value=lps, unit='lines/s', cores=cores, kind='port', sample=sample),
+               e2e=dict(value=lps, unit='lines/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(out), flush=True)
+
+
+def train_workload_name(args):
+    return (f'BASELINE {CONFIGS[4]["name"]}: training step of the default_specs conformer (d144 L16 h4 ff576 k31), {args.batch} lines/GPU of '
+            f'96x{args.width} px, {args.classes} classes, targets U{{20..80}}, dropout 0.1, CTC loss (sum) + backward + gradient all-reduce + AdamW, fp32')
+
+
+def run_train(args):
+    import torch.distributed as dist
+    from conformer_ocr_b200 import synthetic as S
+    from conformer_ocr_b200.train import Trainer
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    json_fd = None
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    assert torch.cuda.is_available(), 'bench.py (our arm) needs a CUDA device; there is no CPU fallback'
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    hp = arch_hp(hparams())
+    B, W, C = args.batch, args.width, args.classes
+    T = out_frames(W)
+    tr = Trainer(num_classes=C, device=dev, lr=1e-3, weight_decay=1e-3, warmup=0, seed=1, input_dropout_p=0.1, feed_forward_dropout_p=0.1,
+                 attention_dropout_p=0.1, conv_dropout_p=0.1, **hp)
+    tr.load_state_dict(S.make_weights(hp, C, seed=0))                    # every rank the same initial weights (DDP broadcast)
+    host = train_batch(args, hp, seed=1234 + rank)                       # every rank its own shard of the global batch
+    dev_batch = {k: v.to(dev) for k, v in host.items()}
+    in_bytes = host['image'].numel() * 4 + host['target'].numel() * 4 + 2 * B * 4
+
+    def fence():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        tr.step(dev_batch)
+    fence()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = tr.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fence()
+    e0.record()
+    for _ in range(args.steps):
+        loss = tr.step(dev_batch)
+    e1.record()
+    fence()
+    ms_total = e0.elapsed_time(e1)
+    launches = tr.launch_count - launches0
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    lines_per_s = world * B * args.steps / (ms_total * 1e-3)
+    last_loss = float(loss.item())
+
+    # ---- end to end: the batch comes from pinned host memory every step, the loss goes back to the host every step ----
+    e2e = None
+    if not args.no_e2e:
+        pinned = {k: v.pin_memory() for k, v in host.items()}
+        fence()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            b = {'image': pinned['image'].to(dev, non_blocking=True), 'seq_lens': pinned['seq_lens'], 'target': pinned['target'].to(dev, non_blocking=True),
+                 'target_lens': pinned['target_lens']}
+            lv = tr.step(b).item()                                       # D2H of the loss: the step's result
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        assert np.isfinite(lv)
+        e2e = dict(value=world * B * args.steps / dt, unit='lines/s', h2d_bytes_per_step=in_bytes, d2h_bytes_per_step=4, ms_per_step=1e3 * dt / args.steps,
+                   api='Trainer.step(batch): pinned host batch (image, seq_lens, target, target_lens as the reference\'s collate hands them to '
+                       '_step) -> cocr_train_step -> all-reduce -> cocr_adamw_step -> loss.item()')
+    if sampler:
+        time.sleep(0.2)
+        sampler.stop()
+
+    # ---- per-kernel CUDA-event timing (rank 0) ----
+    families, roofline = {}, None
+    if rank == 0 and args.profile_steps > 0:
+        import ctypes as Ct
+        lib, h = tr._lib, tr._h
+        lib.cocr_set_profiling(h, 1)
+        for _ in range(args.profile_steps):
+            tr.step(dev_batch)
+        buf = Ct.create_string_buffer(1 << 16)
+        lib.cocr_profile_report(h, buf, len(buf))
+        lib.cocr_set_profiling(h, 0)
+        peaks = load_peaks()
+        tot = 0.0
+        for line in buf.value.decode().splitlines():
+            name, n, ms, fl, by = line.split()
+            n_l = int(n) // args.profile_steps
+            ms_p = float(ms) / args.profile_steps
+            tot += ms_p
+            f = dict(launches=n_l, ms_per_step=ms_p, avg_launch_ms=ms_p / max(n_l, 1), flops_per_launch=float(fl) / max(int(n), 1),
+                     bytes_per_launch=float(by) / max(int(n), 1))
+            sec = f['avg_launch_ms'] * 1e-3
+            if f['flops_per_launch'] > 0 and ('gemm' in name or 'att_' in name or name in ('train_ffn_up', 'train_ffn_down', 'train_qkv', 'train_att_out',
+                                                                                         'train_pw1', 'train_pw2', 'train_decoder', 'train_fe_pw',
+                                                                                         'train_fe_out', 'train_pos_proj')):
+                f.update(bound='tensor', achieved=f['flops_per_launch'] / sec / 1e12, unit='TFLOP/s', peak=peaks['tflops_sustained'])
+            else:
+                f.update(bound='hbm', achieved=f['bytes_per_launch'] / sec / 1e9, unit='GB/s', peak=peaks['hbm_gbs'])
+            f['frac'] = f['achieved'] / f['peak']
+            families[name] = f
+        for f in families.values():
+            f['share_of_step'] = f['ms_per_step'] / max(tot, 1e-9)
+        top = max(families, key=lambda k: families[k]['ms_per_step'])
+        f = families[top]
+        roofline = dict(kernel=top, bound=f['bound'], achieved=f['achieved'], peak=f['peak'], unit=f['unit'], frac=f['frac'], traffic=None,
+                        launches_per_step=f['launches'], avg_launch_ms=f['avg_launch_ms'], share_of_step=f['share_of_step'],
+                        peak_source=peaks['source'], how='dominant kernel family of the training step by CUDA-event time; exact 2*MAC FLOPs / '
+                        'operand bytes of each launch (no padding in these kernels)')
+
+    eager = None
+    if rank == 0 and world == 1 and not args.no_eager_baseline:
+        eager = {}
+        try:
+            tf32 = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            for name, ac in (('fp32', False), ('bf16_autocast', True)):
+                step = port_train_step_factory(args, hp, dev, B, autocast=ac)
+                step()
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    step()
+                torch.cuda.synchronize(dev)
+                dt = (time.perf_counter() - t0) / 3
+                eager[name] = dict(value=B / dt, unit='lines/s', ms_per_step=1e3 * dt)
+                del step
+                torch.cuda.empty_cache()
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            eager['what'] = (f'oracle/torch_train_port.py (the reference\'s modules in train() mode) + autograd + torch.optim.AdamW on this GPU, '
+                             f'eager, batch {B}; 3 steps after 1 warm-up')
+        except Exception as e:
+            eager['error'] = f'{type(e).__name__}: {str(e)[:200]}'
+            torch.cuda.empty_cache()
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    fl_line = train_flops_per_line(W, C, hp)
+    step_tflops = fl_line * B / (ms_step * 1e-3) / 1e12
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        n, cores, times = time_cpu_train(args, hp, reps=2, warm=1)
+        cpu_baseline = dict(value=n * len(times) / sum(times), unit='lines/s', cores=cores, kind='port',
+                            sample=f'{n} lines of 96x{W} px x {len(times)} steps, fp32 forward + backward + AdamW, {cores} threads', note=TRAIN_CPU_NOTE)
+    clocks = sampler.summary() if sampler else dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+    out = dict(metric='training lines/sec', value=lines_per_s, unit='lines/s', n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step,
+               higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', frames_per_s=lines_per_s * T,
+               config=dict(workload=train_workload_name(args), lines_per_step_per_gpu=B, global_batch=world * B, width_px=W, frames_per_line=T,
+                           classes=C, parameters=tr.n_trainable, workspace_bytes=tr.workspace_bytes(B, W), final_loss=last_loss,
+                           parallelism=(f'dp{world}: every rank its own {B} lines; ONE NCCL all-reduce(sum) of the flat gradient buffer '
+                                        f'({tr.n_trainable * 4 / 1e6:.1f} MB) per step; BatchNorm statistics per rank') if world > 1 else 'single GPU',
+                           l2='activations saved for the backward pass (%.1f GB) exceed the 126 MB L2; no explicit flush' % (tr.workspace_bytes(B, W) / 1e9)),
+               clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline,
+               roofline_step=dict(bound='tensor', achieved=step_tflops, peak=peaks['tflops_sustained'], unit='TFLOP/s',
+                                  frac=step_tflops / peaks['tflops_sustained'], gflop_per_line=fl_line / 1e9,
+                                  note='3 x SURVEY 8(d) forward FLOPs per line; the kernels are fp32 CUDA-core code rated against the bf16 tensor peak'),
+               kernel_families=families, gpu_eager_baseline=eager, cpu_baseline=cpu_baseline)
+    if json_fd is not None:
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + '\n').encode())
+        os.close(json_fd)
+    else:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
-    if args.impl == 'reference':
+    if args.config == 4:
+        (run_reference_train if args.impl == 'reference' else run_train)(args)
+    elif args.impl == 'reference':
         run_reference(args)
     else:
         run_ours(args)

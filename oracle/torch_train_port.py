@@ -19,17 +19,27 @@ from .torch_port import calc_length, rel_pos
 BN_MOMENTUM = 0.1          # nn.BatchNorm1d default (convolution.py:141)
 
 
-def _drop(x, p):
-    return F.dropout(x, p, training=True) if p > 0 else x
+_MASK_FN = None      # (site, shape) -> tensor of dropout factors (0 or 1/(1-p)); set by train_forward(mask_fn=...)
 
 
-def _ffn(x, w, p, pd):
+def _drop(x, p, site=None):
+    """nn.Dropout in train mode.  With a mask function installed the factors are REPLAYED (site numbering of csrc/train.cu:
+    0 = input; layer l: 16 l + 1 + {0,1: first FFN hidden/out, 2,3: attention probabilities/out, 4: conv out, 6,7: second FFN})
+    instead of drawn from torch's generator."""
+    if p <= 0:
+        return x
+    if _MASK_FN is not None:
+        return x * _MASK_FN(site, x.shape).to(x.dtype)
+    return F.dropout(x, p, training=True)
+
+
+def _ffn(x, w, p, pd, s0=None):
     y = F.layer_norm(x, x.shape[-1:], w[p + 'sequential.0.weight'], w[p + 'sequential.0.bias'])
-    y = _drop(F.silu(F.linear(y, w[p + 'sequential.1.linear.weight'], w[p + 'sequential.1.linear.bias'])), pd)
-    return _drop(F.linear(y, w[p + 'sequential.4.linear.weight'], w[p + 'sequential.4.linear.bias']), pd)
+    y = _drop(F.silu(F.linear(y, w[p + 'sequential.1.linear.weight'], w[p + 'sequential.1.linear.bias'])), pd, s0)
+    return _drop(F.linear(y, w[p + 'sequential.4.linear.weight'], w[p + 'sequential.4.linear.bias']), pd, None if s0 is None else s0 + 1)
 
 
-def _mhsa(x, w, p, h, pe, pd):
+def _mhsa(x, w, p, h, pe, pd, s0=None):
     B, T, d = x.shape
     dh = d // h
     a = p + 'attention.'
@@ -41,12 +51,12 @@ def _mhsa(x, w, p, h, pe, pd):
     content = torch.matmul((q + w[a + 'u_bias']).transpose(1, 2), k.transpose(2, 3))
     ps = torch.matmul((q + w[a + 'v_bias']).transpose(1, 2), pos.permute(0, 2, 3, 1))
     ps = F.pad(ps, (1, 0)).reshape(B, h, 2 * T, T)[:, :, 1:].reshape(B, h, T, 2 * T - 1)[..., :T]     # attention.py:105-113
-    attn = _drop(F.softmax((content + ps) / math.sqrt(dh), -1), pd)
+    attn = _drop(F.softmax((content + ps) / math.sqrt(dh), -1), pd, s0)
     ctx = torch.matmul(attn, v).transpose(1, 2).contiguous().view(B, T, d)
-    return _drop(F.linear(ctx, w[a + 'out_proj.linear.weight'], w[a + 'out_proj.linear.bias']), pd)
+    return _drop(F.linear(ctx, w[a + 'out_proj.linear.weight'], w[a + 'out_proj.linear.bias']), pd, None if s0 is None else s0 + 1)
 
 
-def _conv(x, w, p, K, pd, stats):
+def _conv(x, w, p, K, pd, stats, s0=None):
     d = x.shape[-1]
     y = F.layer_norm(x, (d,), w[p + 'sequential.0.weight'], w[p + 'sequential.0.bias']).transpose(1, 2)
     y = F.glu(F.conv1d(y, w[p + 'sequential.2.conv.weight'], w[p + 'sequential.2.conv.bias']), dim=1)
@@ -58,13 +68,15 @@ def _conv(x, w, p, K, pd, stats):
     stats[p + 'sequential.5.running_mean'] = rm
     stats[p + 'sequential.5.running_var'] = rv
     y = F.conv1d(F.silu(y), w[p + 'sequential.7.conv.weight'], w[p + 'sequential.7.conv.bias'])
-    return _drop(y.transpose(1, 2), pd)
+    return _drop(y.transpose(1, 2).contiguous(), pd, s0)
 
 
 def train_forward(line: torch.Tensor, lens: torch.Tensor, w: Dict[str, torch.Tensor], hp: Dict, dropout: float = 0.0,
-                  taps: Dict | None = None) -> Tuple[torch.Tensor, torch.Tensor, Dict[str, torch.Tensor]]:
+                  taps: Dict | None = None, mask_fn=None) -> Tuple[torch.Tensor, torch.Tensor, Dict[str, torch.Tensor]]:
     """(N,1,H,W) -> (probits (N,T,C), encoder_lens, new BatchNorm running statistics); model.py:131-135 in train mode.
     `taps`, when given, receives the residual stream after every module (retain_grad'ed) under 'x<layer>.<module>'."""
+    global _MASK_FN
+    _MASK_FN = mask_fn
     x = line.squeeze(1).transpose(1, 2)
     s = 'encoder.conv_subsample.'
     olens = calc_length(lens)
@@ -73,7 +85,7 @@ def train_forward(line: torch.Tensor, lens: torch.Tensor, w: Dict[str, torch.Ten
     y = F.conv2d(y, w[s + 'conv.2.weight'], w[s + 'conv.2.bias'], stride=2, padding=1, groups=y.shape[1])
     y = F.relu(F.conv2d(y, w[s + 'conv.3.weight'], w[s + 'conv.3.bias']))
     b, c, t, f = y.shape
-    y = _drop(F.linear(y.transpose(1, 2).reshape(b, t, -1), w[s + 'out.0.weight'], w[s + 'out.0.bias']), dropout)
+    y = _drop(F.linear(y.transpose(1, 2).reshape(b, t, -1), w[s + 'out.0.weight'], w[s + 'out.0.bias']), dropout, 0)
     fac = 0.5 if hp.get('half_step_residual', True) else 1.0
     pe = rel_pos(t, hp['encoder_dim']).to(device=y.device, dtype=y.dtype)
     stats: Dict[str, torch.Tensor] = {}
@@ -88,17 +100,17 @@ def train_forward(line: torch.Tensor, lens: torch.Tensor, w: Dict[str, torch.Ten
     y = tap('x0', y)
     for i in range(hp['num_encoder_layers']):
         p = f'encoder.layers.{i}.sequential.'
-        y = tap(f'x{i}.0', _ffn(y, w, p + '0.module.', dropout) * fac + y)
-        y = tap(f'x{i}.1', _mhsa(y, w, p + '1.module.', hp['num_attention_heads'], pe, dropout) + y)
-        y = tap(f'x{i}.2', _conv(y, w, p + '2.module.', hp['conv_kernel_size'], dropout, stats) + y)
-        y = tap(f'x{i}.3', _ffn(y, w, p + '3.module.', dropout) * fac + y)
+        y = tap(f'x{i}.0', _ffn(y, w, p + '0.module.', dropout, 16 * i + 1) * fac + y)
+        y = tap(f'x{i}.1', _mhsa(y, w, p + '1.module.', hp['num_attention_heads'], pe, dropout, 16 * i + 3) + y)
+        y = tap(f'x{i}.2', _conv(y, w, p + '2.module.', hp['conv_kernel_size'], dropout, stats, 16 * i + 5) + y)
+        y = tap(f'x{i}.3', _ffn(y, w, p + '3.module.', dropout, 16 * i + 7) * fac + y)
         y = tap(f'x{i}.4', F.layer_norm(y, y.shape[-1:], w[p + '4.weight'], w[p + '4.bias']))
     return F.linear(y, w['decoder.weight'], w['decoder.bias']), olens, stats
 
 
-def train_step_loss(line, lens, targets, target_lens, w, hp, dropout: float = 0.0, taps=None):
+def train_step_loss(line, lens, targets, target_lens, w, hp, dropout: float = 0.0, taps=None, mask_fn=None):
     """model.py:136-142: log_softmax, (N,T,C)->(T,N,C), CTCLoss(sum, zero_infinity).  Returns (loss, probits, lens, stats)."""
-    probits, olens, stats = train_forward(line, lens, w, hp, dropout, taps)
+    probits, olens, stats = train_forward(line, lens, w, hp, dropout, taps, mask_fn)
     logp = F.log_softmax(probits, dim=-1)
     loss = F.ctc_loss(logp.transpose(0, 1), targets, olens, target_lens, blank=0, reduction='sum', zero_infinity=True)
     return loss, probits, olens, stats

@@ -1,0 +1,166 @@
+"""One training step on the GPU through the C ABI (cocr_train_step / cocr_adamw_step; csrc/train.cu) against
+ (1) the golden vectors of the UNMODIFIED reference modules in train() mode (model.py:129-145; dropout 0),
+ (2) the torch port's autograd in float64 at the sequence length of BASELINE configs[3] (16 layers, 1536 px, C = 256),
+ (3) the same with dropout 0.1 everywhere, the port replaying the kernels' own masks (cocr_dropout_mask),
+ (4) torch.optim.AdamW.
+Tolerance: fp32 kernels against a float64 checker; a gradient tensor must be within 2e-4 of max(its own largest entry,
+1e-3 x the largest gradient entry of the model) - the floor covers tensors whose exact gradient is zero (key-projection
+bias: softmax is invariant to it)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR
+from oracle import conformer_oracle as O
+from oracle import torch_train_port as TP
+
+pytestmark = pytest.mark.gpu
+
+INDEX = json.load(open(os.path.join(GOLDEN_DIR, 'index_train.json')))
+HP_KEYS = ('height', 'encoder_dim', 'num_encoder_layers', 'num_attention_heads', 'feed_forward_expansion_factor',
+           'conv_expansion_factor', 'conv_kernel_size', 'half_step_residual', 'subsampling_conv_channels', 'subsampling_factor')
+
+
+def make_trainer(hp, C, device, dropout=0.0, **kw):
+    from conformer_ocr_b200.train import Trainer
+    return Trainer(num_classes=C, input_dropout_p=dropout, feed_forward_dropout_p=dropout, attention_dropout_p=dropout,
+                   conv_dropout_p=dropout, device=device, **{k: hp[k] for k in HP_KEYS}, **kw)
+
+
+def check_grads(tr, ref_grads, tol=2e-4):
+    keys = tr.trainable_keys()
+    gmax = max(float(np.abs(ref_grads[k]).max()) for k in keys)
+    worst = 0.0
+    for k in keys:
+        ref = np.asarray(ref_grads[k], dtype=np.float64)
+        got = tr.view(k, 'grads').cpu().double().numpy()
+        assert got.shape == ref.shape, k
+        e = np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-3 * gmax)
+        worst = max(worst, e)
+        assert e <= tol, f'{k}: gradient rel err {e:.3e}'
+    return worst
+
+
+@pytest.mark.parametrize('name', sorted(INDEX))
+def test_train_step_matches_reference_golden(cuda_device, name):
+    m = INDEX[name]
+    g = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
+    hp = m['hparams']
+    w = O.make_weights(hp, m['num_classes'], seed=m['weight_seed'])
+    img, lens = O.make_lines(m['batch'], hp['height'], m['width'], seed=m['input_seed'], widths=m['widths'])
+    tr = make_trainer(hp, m['num_classes'], cuda_device)
+    assert sorted(tr.layout) == sorted(k for k in w)
+    tr.load_state_dict(w)
+    batch = {'image': torch.from_numpy(img), 'seq_lens': torch.from_numpy(lens), 'target': torch.from_numpy(g['targets']),
+             'target_lens': torch.from_numpy(g['target_lens'])}
+    n0 = tr.launch_count
+    loss = tr.forward_backward(batch)
+    assert tr.launch_count > n0
+    assert abs(loss.item() - float(g['loss'])) <= 1e-5 * abs(float(g['loss']))
+    worst = check_grads(tr, {k: g['grad/' + k] for k in tr.trainable_keys()})
+    for k in tr.layout:
+        if k.endswith(('running_mean', 'running_var')):
+            assert np.abs(tr.view(k).cpu().numpy() - g['stat/' + k]).max() <= 1e-6, k
+    # a second pass over the same batch gives the same gradients (atomics reorder sums: 1e-5), statistics move again
+    g1 = tr.grads[:tr.n_trainable].clone()
+    tr.forward_backward(batch)
+    assert (tr.grads[:tr.n_trainable] - g1).abs().max().item() <= 1e-5 * g1.abs().max().item()
+    print(f'{name}: loss {loss.item():.6f}, worst gradient rel err {worst:.2e}')
+    tr.close()
+
+
+def synthetic_batch(B, H, W, C, seed, widths=None):
+    img, lens = O.make_lines(B, H, W, seed=seed, widths=widths)
+    rng = np.random.RandomState(seed + 1)
+    tl = rng.randint(20, 81, size=B).astype(np.int64)                     # SURVEY 8d cfg 4: target length U{20..80}
+    tg = rng.randint(1, C, size=int(tl.sum())).astype(np.int64)
+    return {'image': torch.from_numpy(img), 'seq_lens': torch.from_numpy(lens), 'target': torch.from_numpy(tg), 'target_lens': torch.from_numpy(tl)}
+
+
+def port_grads(batch, w, hp, device, mask_fn=None, dropout=0.0):
+    wt = {k: torch.from_numpy(v.copy()).to(device=device, dtype=torch.float64).requires_grad_(not k.endswith(('running_mean', 'running_var')))
+          for k, v in w.items()}
+    loss, _, _, stats = TP.train_step_loss(batch['image'].to(device).double(), batch['seq_lens'], batch['target'].to(device),
+                                           batch['target_lens'], wt, hp, dropout=dropout, mask_fn=mask_fn)
+    loss.backward()
+    return loss.item(), {k: wt[k].grad.cpu().numpy() for k in TP.trainable_keys(wt)}, {k: v.cpu().numpy() for k, v in stats.items()}
+
+
+@pytest.mark.parametrize('dropout', [0.0, 0.1])
+def test_train_step_default_spec_against_port(cuda_device, dropout):
+    """16 layers, d = 144, 1536 px (T = 384), C = 256, ragged widths; B = 3 keeps the float64 checker to seconds."""
+    hp = dict(O.DEFAULT_HPARAMS)
+    C, B, W = 256, 3, 1536
+    w = O.make_weights(hp, C, seed=31)
+    batch = synthetic_batch(B, hp['height'], W, C, seed=32, widths=[1536, 1400, 1111])
+    tr = make_trainer(hp, C, cuda_device, dropout=dropout, seed=5)
+    tr.load_state_dict(w)
+    loss = tr.forward_backward(batch)
+    seed = tr.cfg.seed
+    prob = dropout
+
+    def mask_fn(site, shape):
+        return tr.dropout_mask(site, prob, int(np.prod(shape)), seed=seed).view(shape)
+
+    ref_loss, ref_g, ref_stats = port_grads(batch, w, hp, cuda_device, mask_fn=mask_fn if dropout > 0 else None, dropout=dropout)
+    assert abs(loss.item() - ref_loss) <= 2e-5 * abs(ref_loss), (loss.item(), ref_loss)
+    worst = check_grads(tr, ref_g, tol=2e-3)     # 16 layers of fp32 accumulation against float64
+    for k, v in ref_stats.items():
+        assert np.abs(tr.view(k).cpu().numpy() - v).max() <= 1e-5, k
+    if dropout > 0:
+        mk = tr.dropout_mask(3, prob, 1 << 20, seed=seed)
+        keep = (mk > 0).float().mean().item()
+        assert abs(keep - (1 - prob)) < 2e-3 and abs(mk.max().item() - 1 / (1 - prob)) < 1e-6
+    print(f'default spec, dropout {dropout}: loss {loss.item():.4f} (port {ref_loss:.4f}), worst gradient rel err {worst:.2e}')
+    tr.close()
+
+
+def test_adamw_matches_torch(cuda_device):
+    hp = dict(O.DEFAULT_HPARAMS, num_encoder_layers=1)
+    tr = make_trainer(hp, 32, cuda_device, lr=3e-3, weight_decay=1e-2)
+    gen = torch.Generator(device='cpu').manual_seed(3)
+    n = tr.n_trainable
+    p0 = torch.randn(n, generator=gen)
+    tr.params[:n] = p0.to(cuda_device)
+    ref = torch.nn.Parameter(p0.clone().to(cuda_device))
+    opt = torch.optim.AdamW([ref], lr=3e-3, weight_decay=1e-2)
+    for step in range(3):
+        gr = torch.randn(n, generator=gen) * (10.0 ** (step - 1))
+        tr.grads[:n] = gr.to(cuda_device)
+        ref.grad = gr.to(cuda_device)
+        tr.optimizer_step()
+        opt.step()
+        assert (tr.params[:n] - ref.detach()).abs().max().item() <= 2e-6
+    tr.close()
+
+
+def test_training_reduces_the_loss(cuda_device):
+    """A few steps on one batch with the reference's optimiser settings: the loss goes down, parameters stay finite."""
+    hp = dict(O.DEFAULT_HPARAMS, num_encoder_layers=2)
+    C = 48
+    tr = make_trainer(hp, C, cuda_device, dropout=0.1, lr=1e-3, weight_decay=1e-3, seed=9)
+    tr.load_state_dict(O.make_weights(hp, C, seed=41))
+    batch = synthetic_batch(4, hp['height'], 512, C, seed=42)
+    batch['target_lens'] = torch.clamp(batch['target_lens'], max=40)
+    batch['target'] = batch['target'][:int(batch['target_lens'].sum())]
+    losses = [tr.step(batch).item() for _ in range(8)]
+    assert all(np.isfinite(losses)) and losses[-1] < 0.9 * losses[0], losses
+    assert torch.isfinite(tr.params).all()
+    tr.close()
+
+
+def test_train_rejects_bad_arguments(cuda_device):
+    hp = dict(O.DEFAULT_HPARAMS, num_encoder_layers=1)
+    tr = make_trainer(hp, 16, cuda_device)
+    with pytest.raises(ValueError):
+        tr.load_state_dict({'decoder.weight': np.zeros((16, 144), np.float32)})
+    batch = synthetic_batch(2, 64, 128, 16, seed=1)
+    with pytest.raises(ValueError):
+        tr.forward_backward(batch)                      # wrong line height
+    tr.cfg.conv_dropout_p = 1.5
+    with pytest.raises(ValueError):
+        tr.forward_backward(synthetic_batch(2, hp['height'], 128, 16, seed=1))
+    tr.close()
