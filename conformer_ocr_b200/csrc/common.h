@@ -208,6 +208,26 @@ int launch_ctc_loss(cocr_handle *h, const float *logits, const int32_t *targets,
 int launch_decoder_backward(cocr_handle *h, const float *grad_logits, const float *enc, int M, cudaStream_t st, float *grad_w, float *grad_b,
                             float *grad_enc);
 
+// ---- batched tcgen05 GEMM (bgemm_tc.cu): D[z] (M x N) = alpha * A[z] (M x K) * B[z] (N x K)^T (+ bias); z = (z1, z2)
+struct BgOperand {
+    const void *ptr;               // bf16
+    int mn;                        // 0: stored [m][k] (contraction index contiguous); 1: stored [k][m]
+    long long ld, z1_stride, z2_stride;   // elements; a stride of 0 = shared by the batch
+};
+struct BgProblem {
+    int M = 0, N = 0, K = 0, nz1 = 1, nz2 = 1;
+    BgOperand a = {}, b = {};
+    void *out = nullptr;
+    long long ldc = 0, out_z1 = 0, out_z2 = 0;
+    int out_mode = 0;              // 0 fp32 store, 1 bf16 store, 2 fp32 atomic add, 3 fp32 read-add-store
+    float alpha = 1.0f;
+    const float *bias = nullptr;   // (N)
+    int ksplit = 1;                // split of the contraction over CTAs (needs out_mode 2)
+    int relu = 0;
+};
+int launch_bgemm(cocr_handle *h, const BgProblem &g, cudaStream_t st, const char *tag);
+int selftest_bgemm(int device, int M, int N, int K, int flags, double *max_err);
+
 // ---- training step (train.cu): flat parameter / gradient buffers owned by the caller
 void train_destroy(cocr_handle *h);
 int train_layout(cocr_handle *h, int64_t *n_total, int64_t *n_trainable, int32_t *n_entries);
