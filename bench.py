@@ -38,7 +38,7 @@ CONFIGS = {
     2: dict(batch=256, width=1536, classes=256, precision='bf16', passes=16, name='configs[1]'),
     # configs[3]: one data-parallel TRAINING step (forward in train() mode, CTC loss, backward, gradient all-reduce, AdamW);
     # 32 lines per GPU per step (the weak-scaling variant of SURVEY.md 8d cfg 4)
-    4: dict(batch=32, width=1536, classes=256, precision='fp32', passes=1, name='configs[3]'),
+    4: dict(batch=32, width=1536, classes=256, precision='bf16', passes=1, name='configs[3]'),
     # configs[4]: long lines, CJK-sized alphabet
     5: dict(batch=64, width=4096, classes=10000, precision='bf16', passes=4, name='configs[4]'),
 }
@@ -676,7 +676,7 @@ def run_reference_train(args):
 
 def train_workload_name(args):
     return (f'BASELINE {CONFIGS[4]["name"]}: training step of the default_specs conformer (d144 L16 h4 ff576 k31), {args.batch} lines/GPU of '
-            f'96x{args.width} px, {args.classes} classes, targets U{{20..80}}, dropout 0.1, CTC loss (sum) + backward + gradient all-reduce + AdamW, fp32')
+            f'96x{args.width} px, {args.classes} classes, targets U{{20..80}}, dropout 0.1, CTC loss (sum) + backward + gradient all-reduce + AdamW, ' + ('bf16 tcgen05 operands, fp32 accumulation / master weights' if args.precision == 'bf16' else 'fp32 CUDA-core kernels'))
 
 
 def run_train(args):
@@ -701,7 +701,7 @@ def run_train(args):
     B, W, C = args.batch, args.width, args.classes
     T = out_frames(W)
     tr = Trainer(num_classes=C, device=dev, lr=1e-3, weight_decay=1e-3, warmup=0, seed=1, input_dropout_p=0.1, feed_forward_dropout_p=0.1,
-                 attention_dropout_p=0.1, conv_dropout_p=0.1, **hp)
+                 attention_dropout_p=0.1, conv_dropout_p=0.1, precision=args.precision, **hp)
     tr.load_state_dict(S.make_weights(hp, C, seed=0))                    # every rank the same initial weights (DDP broadcast)
     host = train_batch(args, hp, seed=1234 + rank)                       # every rank its own shard of the global batch
     dev_batch = {k: v.to(dev) for k, v in host.items()}
@@ -742,12 +742,12 @@ def run_train(args):
     e2e = None
     if not args.no_e2e:
         pinned = {k: v.pin_memory() for k, v in host.items()}
+        for _ in range(2):
+            tr.step(pinned)                      # the staging buffers are allocated (and the step re-captured for them) here
         fence()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            b = {'image': pinned['image'].to(dev, non_blocking=True), 'seq_lens': pinned['seq_lens'], 'target': pinned['target'].to(dev, non_blocking=True),
-                 'target_lens': pinned['target_lens']}
-            lv = tr.step(b).item()                                       # D2H of the loss: the step's result
+            lv = tr.step(pinned).item()          # H2D of the pinned host batch into the trainer's staging buffers; D2H of the loss
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -840,7 +840,7 @@ def run_train(args):
                             sample=f'{n} lines of 96x{W} px x {len(times)} steps, fp32 forward + backward + AdamW, {cores} threads', note=TRAIN_CPU_NOTE)
     clocks = sampler.summary() if sampler else dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
     out = dict(metric='training lines/sec', value=lines_per_s, unit='lines/s', n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step,
-               higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', frames_per_s=lines_per_s * T,
+               higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16' if args.precision == 'bf16' else 'f32', data='synthetic', frames_per_s=lines_per_s * T,
                config=dict(workload=train_workload_name(args), lines_per_step_per_gpu=B, global_batch=world * B, width_px=W, frames_per_line=T,
                            classes=C, parameters=tr.n_trainable, workspace_bytes=tr.workspace_bytes(B, W), final_loss=last_loss,
                            parallelism=(f'dp{world}: every rank its own {B} lines; ONE NCCL all-reduce(sum) of the flat gradient buffer '
@@ -849,7 +849,7 @@ def run_train(args):
                clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline,
                roofline_step=dict(bound='tensor', achieved=step_tflops, peak=peaks['tflops_sustained'], unit='TFLOP/s',
                                   frac=step_tflops / peaks['tflops_sustained'], gflop_per_line=fl_line / 1e9,
-                                  note='3 x SURVEY 8(d) forward FLOPs per line; the kernels are fp32 CUDA-core code rated against the bf16 tensor peak'),
+                                  note='3 x SURVEY 8(d) forward FLOPs per line (forward + data gradients + weight gradients)'),
                kernel_families=families, gpu_eager_baseline=eager, cpu_baseline=cpu_baseline)
     if json_fd is not None:
         sys.stdout.flush()

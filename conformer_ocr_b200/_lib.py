@@ -30,7 +30,7 @@ class cocr_hparams(C.Structure):
 
 class cocr_train_config(C.Structure):
     _fields_ = [('input_dropout_p', C.c_float), ('feed_forward_dropout_p', C.c_float), ('attention_dropout_p', C.c_float),
-                ('conv_dropout_p', C.c_float), ('bn_momentum', C.c_float), ('reserved', C.c_uint32), ('seed', C.c_uint64)]
+                ('conv_dropout_p', C.c_float), ('bn_momentum', C.c_float), ('compute', C.c_uint32), ('seed', C.c_uint64)]
 
 
 _P = C.c_void_p

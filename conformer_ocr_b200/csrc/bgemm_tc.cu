@@ -41,7 +41,7 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *m, uin
         : "memory");
 }
 
-constexpr int BG_STAGES = 3;
+constexpr int BG_STAGES = 3;               // at most; short contractions use fewer so that more CTAs share an SM
 constexpr uint32_t BG_A_BYTES = 128 * 128;      // 128 (m) x 64 (k) bf16, either major
 constexpr int BG_THREADS = 192;
 
@@ -55,8 +55,8 @@ struct BgArgs {
     float alpha;
     const float *bias;             // (N) or null; added by k-slice 0 only
     void *out;
-    long long ldc, out_z1, out_z2; // elements
-    int relu;
+    long long ldc, out_z1, out_z2, out_ks; // elements
+    int relu, stages;
     int a_u1, a_u2, b_u1, b_u2;    // 1 when the operand has its own block per z1 / z2 (0: shared by the batch)
 };
 
@@ -93,8 +93,8 @@ k_bgemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             prefetch_tmap(&tmA);
             prefetch_tmap(&tmB);
             for (int kc = 0; kc < nkc; ++kc) {
-                const int s = kc % BG_STAGES;
-                const uint32_t ph = (uint32_t)(kc / BG_STAGES) & 1u;
+                const int s = kc % p.stages;
+                const uint32_t ph = (uint32_t)(kc / p.stages) & 1u;
                 mbar_wait(&empty[s], ph ^ 1u);
                 uint8_t *a_dst = smem + (size_t)s * stage_bytes, *b_dst = a_dst + BG_A_BYTES;
                 mbar_expect_tx(&full[s], BG_A_BYTES + b_bytes);
@@ -116,8 +116,8 @@ k_bgemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     } else if (warp == 1) {
         const uint32_t idesc = make_idesc_bf16(128, p.block_n, p.a_mn, p.b_mn);
         for (int kc = 0; kc < nkc; ++kc) {
-            const int s = kc % BG_STAGES;
-            const uint32_t ph = (uint32_t)(kc / BG_STAGES) & 1u;
+            const int s = kc % p.stages;
+            const uint32_t ph = (uint32_t)(kc / p.stages) & 1u;
             mbar_wait(&full[s], ph);
             tc_fence_after();
             const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes), b_base = a_base + BG_A_BYTES;
@@ -139,7 +139,7 @@ k_bgemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         const int m = m0 + q * 32 + lane;
         mbar_wait(&tfull, 0);
         tc_fence_after();
-        const long long obase = (long long)z1 * p.out_z1 + (long long)z2 * p.out_z2 + (long long)m * p.ldc;
+        const long long obase = (long long)z1 * p.out_z1 + (long long)z2 * p.out_z2 + (long long)ks_idx * p.out_ks + (long long)m * p.ldc;
         const bool add_bias = p.bias && ks_idx == 0;
         for (int c0 = 0; c0 < p.block_n; c0 += 16) {
             uint32_t r[16];
@@ -241,6 +241,7 @@ int launch_bgemm(cocr_handle *h, const BgProblem &g, cudaStream_t st, const char
             if (g.N % c == 0) { bn = c; break; }
         if (!bn) bn = 256;
     }
+    if (g.K <= 128 && g.N > 128) bn = 128;        // short contraction, wide output: the epilogue dominates; 4 CTAs per SM overlap it
     if (g.b.mn && g.N > bn && bn % 64 != 0) bn = (bn + 63) / 64 * 64;
     if (bn > 256) bn = 256;
     p.block_n = bn;
@@ -253,8 +254,9 @@ int launch_bgemm(cocr_handle *h, const BgProblem &g, cudaStream_t st, const char
     p.kchunks = (nkc + ks - 1) / ks;
     p.ksplit = p.kchunks > 0 ? (nkc + p.kchunks - 1) / p.kchunks : 1;
     if (p.ksplit < 1) p.ksplit = 1;
-    if (p.ksplit > 1 && g.out_mode != 2) return set_error(h, COCR_ERR_BAD_ARG, "batched GEMM: a split contraction needs the atomic output mode");
-    p.out_mode = g.out_mode; p.alpha = g.alpha; p.bias = g.bias; p.out = g.out; p.ldc = g.ldc; p.out_z1 = g.out_z1; p.out_z2 = g.out_z2; p.relu = g.relu;
+    if (p.ksplit > 1 && g.out_mode != 2 && !(g.out_mode == 0 && g.out_ks > 0))
+        return set_error(h, COCR_ERR_BAD_ARG, "batched GEMM: a split contraction needs the atomic output mode or a stride between the partial results");
+    p.out_mode = g.out_mode; p.alpha = g.alpha; p.bias = g.bias; p.out = g.out; p.ldc = g.ldc; p.out_z1 = g.out_z1; p.out_z2 = g.out_z2; p.relu = g.relu; p.out_ks = g.out_ks;
     p.a_u1 = (g.nz1 > 1 && g.a.z1_stride == 0) ? 0 : 1; p.a_u2 = (g.nz2 > 1 && g.a.z2_stride == 0) ? 0 : 1;
     p.b_u1 = (g.nz1 > 1 && g.b.z1_stride == 0) ? 0 : 1; p.b_u2 = (g.nz2 > 1 && g.b.z2_stride == 0) ? 0 : 1;
     int tm = 32;
@@ -268,7 +270,8 @@ int launch_bgemm(cocr_handle *h, const BgProblem &g, cudaStream_t st, const char
     else COCR_TRY(make_tmap4(h, &tmB, g.b.ptr, g.b, g.K, g.N, g.nz2, g.nz1, 64, bn));
     const uint32_t b_bytes = g.b.mn ? (uint32_t)p.nbox_b * 8192u : (uint32_t)bn * 128u;
     const uint32_t stage_bytes = (BG_A_BYTES + b_bytes + 1023u) & ~1023u;
-    const size_t smem = (size_t)BG_STAGES * stage_bytes;
+    p.stages = p.kchunks < BG_STAGES ? (p.kchunks < 1 ? 1 : p.kchunks) : BG_STAGES;
+    const size_t smem = (size_t)p.stages * stage_bytes;
     static PerDevice<size_t> attr;
     if (smem > attr.get()) {
         COCR_CUDA(h, cudaFuncSetAttribute(k_bgemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BG_STAGES * (BG_A_BYTES + 32768))));

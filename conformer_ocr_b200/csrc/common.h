@@ -219,6 +219,7 @@ struct BgProblem {
     BgOperand a = {}, b = {};
     void *out = nullptr;
     long long ldc = 0, out_z1 = 0, out_z2 = 0;
+    long long out_ks = 0;          // out_mode 0 with a split contraction: element stride between the partial results of the k-slices
     int out_mode = 0;              // 0 fp32 store, 1 bf16 store, 2 fp32 atomic add, 3 fp32 read-add-store
     float alpha = 1.0f;
     const float *bias = nullptr;   // (N)

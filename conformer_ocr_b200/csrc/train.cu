@@ -38,6 +38,17 @@ struct TrainState {
     size_t ws_bytes = 0;
     float *pe = nullptr;        // (2T-1, d) relative positional table
     int pe_T = 0;
+    uint64_t *seed_dev = nullptr;   // [0]: seed of the running step, [1]: seed of cocr_dropout_mask
+    // the launch sequence of one step, captured per argument set and replayed (about 1 800 launches per step otherwise)
+    struct StepGraph {
+        std::vector<uint64_t> key;
+        cudaGraphExec_t exec = nullptr;
+        int64_t launches = 0;
+        int sightings = 0;
+    };
+    std::vector<StepGraph> graphs;
+    cudaStream_t gstream = nullptr;
+    cudaEvent_t g_in = nullptr, g_out = nullptr;
 };
 
 namespace {
@@ -54,7 +65,7 @@ size_t add_entry(TrainState *s, const std::string &key, size_t numel, bool train
 void build_layout(const Dims &dm, TrainState *s) {
     const size_t d = dm.d, ff = dm.ff, cc = dm.cc, K = dm.K;
     size_t cur = 0;
-    auto pad = [&]() { cur = (cur + 3) / 4 * 4; };
+    auto pad = [&]() { cur = (cur + 7) / 8 * 8; };       // 16 bytes in the bf16 mirror of the buffer (TMA operand alignment)
     auto add = [&](const std::string &k, size_t n) { pad(); return add_entry(s, k, n, true, cur); };
     const std::string sp = "encoder.conv_subsample.";
     s->sub_w1 = add(sp + "conv.0.weight", cc * 9);
@@ -126,12 +137,15 @@ void build_layout(const Dims &dm, TrainState *s) {
 int train_state(cocr_handle *h, TrainState **out) {
     if (!h->train) {
         const Dims &dm = h->dm;
-        if (dm.d % 4 != 0 || 256 % dm.cc != 0 || dm.C < 2)
-            return set_error(h, COCR_ERR_UNSUPPORTED, "training needs encoder_dim %% 4 == 0, conv channels dividing 256 and a decoder (d=%d cc=%d C=%d)",
+        if (dm.d % 8 != 0 || 256 % dm.cc != 0 || dm.C < 2)
+            return set_error(h, COCR_ERR_UNSUPPORTED, "training needs encoder_dim %% 8 == 0, conv channels dividing 256 and a decoder (d=%d cc=%d C=%d)",
                              dm.d, dm.cc, dm.C);
         if (dm.dh > 64) return set_error(h, COCR_ERR_UNSUPPORTED, "training attention supports head dim <= 64 (got %d)", dm.dh);
         h->train = new TrainState();
         build_layout(dm, h->train);
+        void *sp = nullptr;
+        COCR_CUDA(h, cudaMalloc(&sp, 16));
+        h->train->seed_dev = (uint64_t *)sp;
     }
     *out = h->train;
     return COCR_OK;
@@ -196,7 +210,7 @@ int gemm_tn(Ctx &c, const float *dY, int ldy, const float *X, int ldx, float *dW
     return COCR_OK;
 }
 int colsum(Ctx &c, const float *A, int lda, int M, int N, float *out) {
-    const int rpb = 128;
+    const int rpb = 32;
     dim3 grid((M + rpb - 1) / rpb, (N + 255) / 256);
     k_colsum<<<grid, 256, 0, c.st>>>(A, lda, M, N, rpb, out);
     TK_LAUNCHED(c);
@@ -212,7 +226,7 @@ int ln_fwd(Ctx &c, const float *x, const float *g, const float *b, float *y, flo
 int ln_bwd(Ctx &c, const float *dy, const float *x, const float *stats, const float *g, const float *resid, float *dx_out, float *dgamma,
            float *dbeta, int M, int d) {
     ProfScope ps(c.h, "train_layernorm_bwd", c.st, 0.0, 20.0 * M * d);
-    const int rpb = 128;
+    const int rpb = 32;
     k_ln_param_grad<<<dim3((M + rpb - 1) / rpb, (d + 255) / 256), 256, 0, c.st>>>(dy, x, stats, M, d, rpb, dgamma, dbeta);
     TK_LAUNCHED(c);
     k_ln_bwd<<<(M + 7) / 8, 256, 0, c.st>>>(dy, x, stats, g, resid, dx_out, M, d);
@@ -308,9 +322,12 @@ int dwconv_wgrad(Ctx &c, const float *x, const float *dy, float *dw, int B, int 
     return COCR_OK;
 }
 
+const uint64_t *g_seedp = nullptr;    // device seed word of the step being enqueued (set by train_step / dropout_mask)
+
 Drop make_drop(const cocr_train_config *cfg, float p, uint32_t site) {
     Drop dr;
-    dr.seed = cfg->seed;
+    (void)cfg;
+    dr.seedp = g_seedp;
     dr.site = site;
     if (!(p > 0.0f)) { dr.thresh = 0; dr.inv_keep = 1.0f; return dr; }
     double t = (double)p * 4294967296.0;
@@ -324,6 +341,7 @@ Drop make_drop(const cocr_train_config *cfg, float p, uint32_t site) {
 struct Bump {
     size_t off = 0;
     size_t take(size_t floats) { const size_t o = off; off = (off + floats * 4 + 255) / 256 * 256; return o; }
+    size_t take16(size_t halves) { return take((halves + 1) / 2); }
 };
 
 // workspace carve-up of one (B, W, max target length)
@@ -333,10 +351,13 @@ struct Plan {
     size_t a1, a2, a3, wperm, logits, glogits, lens;
     size_t t_d0, t_d1, t_d2, t_ff0, t_ff1, t_qkv, dS, dpos, part, bnsums, dx, dxn, gwperm;
     size_t part_floats;
+    // tensor-core path (bf16 operands): tc == 1
+    int tc, Tp, Rp, dhp, HP, Cp;
+    size_t pb, peb, xnb, zb, actb, dyb, wideb, ctxb, encb, glogb, dposb, qu, qv, kb, vb, dctxb, posb, Sc, PS, dSb, dPSb, delta, Pb16;
     size_t total;
 };
 
-void make_plan(const Dims &dm, int B, int W, Plan *p) {
+void make_plan(const Dims &dm, int B, int W, int tc, size_t n_total, Plan *p) {
     p->B = B; p->W = W;
     p->T2 = out_len1(W);
     p->T = out_len1(p->T2);
@@ -347,9 +368,15 @@ void make_plan(const Dims &dm, int B, int W, Plan *p) {
     p->xs = b.take((1 + 5 * L) * M * d);
     p->stats = b.take(5 * L * M * 2);
     p->h1 = b.take(2 * L * M * ff);
-    p->qkv = b.take(L * M * 3 * d);
-    p->pos = b.take(L * (size_t)p->R * d);
-    p->P = b.take(L * (size_t)B * dm.nh * p->T * p->T);
+    p->qkv = b.take((tc ? 1 : L) * M * 3 * d);
+    p->pos = b.take((tc ? 1 : L) * (size_t)p->R * d);
+    p->tc = tc;
+    p->Tp = (p->T + 7) / 8 * 8;
+    p->Rp = (p->R + 7) / 8 * 8;
+    p->dhp = (dm.dh + 7) / 8 * 8;
+    p->HP = dm.nh * p->dhp;
+    p->Cp = (dm.C + 7) / 8 * 8;
+    p->P = tc ? 0 : b.take(L * (size_t)B * dm.nh * p->T * p->T);
     p->ctx = b.take(L * M * d);
     p->u = b.take(L * M * 2 * d);
     p->cdw = b.take(L * M * d);
@@ -369,7 +396,35 @@ void make_plan(const Dims &dm, int B, int W, Plan *p) {
     p->t_ff0 = b.take(M * (wide > (size_t)dm.feat ? wide : (size_t)dm.feat));
     p->t_ff1 = b.take(M * (wide > (size_t)dm.feat ? wide : (size_t)dm.feat));
     p->t_qkv = b.take(M * 3 * d);
-    p->dS = b.take((size_t)B * dm.nh * p->T * p->T);
+    p->dS = tc ? 0 : b.take((size_t)B * dm.nh * p->T * p->T);
+    if (tc) {
+        const size_t bh = (size_t)B * dm.nh, R = p->R;
+        p->Pb16 = b.take16(2 * L * bh * p->T * p->Tp);        // per layer: P then dropout(P)
+        p->pb = b.take16(n_total);
+        p->peb = b.take16(R * d);
+        // operands saved per layer for the backward pass (bf16): LayerNorm outputs of the four modules, FFN activations,
+        // conv-module activation, attention context and the head-pitched q+u | q+v | k | v | p
+        p->xnb = b.take16(4 * L * M * d);
+        p->zb = b.take16(L * M * d);
+        p->actb = b.take16(2 * L * M * ff);
+        p->dyb = b.take16(M * d);
+        p->wideb = b.take16(M * (ff > 3 * d ? ff : 3 * d));
+        p->ctxb = b.take16(L * M * d);
+        p->encb = b.take16(M * d);
+        p->glogb = b.take16(M * (size_t)p->Cp);
+        p->dposb = b.take16(R * d);
+        p->qu = b.take16(L * M * p->HP);
+        p->qv = b.take16(L * M * p->HP);
+        p->kb = b.take16(L * M * p->HP);
+        p->vb = b.take16(L * M * p->HP);
+        p->dctxb = b.take16(M * p->HP);
+        p->posb = b.take16(L * R * p->HP);
+        p->Sc = b.take(bh * p->T * p->Tp);
+        p->PS = b.take(bh * p->T * p->Rp);
+        p->dSb = b.take16(bh * p->T * p->Tp);
+        p->dPSb = b.take16(bh * p->T * p->Rp);
+        p->delta = b.take(M * dm.nh);
+    }
     p->dpos = b.take((size_t)p->R * d);
     size_t biggest = ff * d;
     if ((size_t)dm.C * d > biggest) biggest = (size_t)dm.C * d;
@@ -609,12 +664,20 @@ int conv_backward_mod(Mod &m, const float *x_in, float *dx) {
     return COCR_OK;
 }
 
+#include "train_tc.cuh"
+
 }  // namespace
 
 void train_destroy(cocr_handle *h) {
     if (!h->train) return;
     if (h->train->ws) cudaFree(h->train->ws);
     if (h->train->pe) cudaFree(h->train->pe);
+    if (h->train->seed_dev) cudaFree(h->train->seed_dev);
+    for (auto &g : h->train->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (h->train->gstream) cudaStreamDestroy(h->train->gstream);
+    if (h->train->g_in) cudaEventDestroy(h->train->g_in);
+    if (h->train->g_out) cudaEventDestroy(h->train->g_out);
     delete h->train;
     h->train = nullptr;
 }
@@ -647,14 +710,18 @@ int train_workspace_bytes(cocr_handle *h, int B, int W, size_t *bytes) {
     TrainState *s;
     COCR_TRY(train_state(h, &s));
     Plan p;
-    make_plan(h->dm, B, W, &p);
+    make_plan(h->dm, B, W, 1, s->n_total, &p);
     *bytes = p.total;
     return COCR_OK;
 }
 
 int dropout_mask(cocr_handle *h, uint64_t seed, uint32_t site, float prob, int64_t n, cudaStream_t st, float *out) {
+    TrainState *s;
+    COCR_TRY(train_state(h, &s));
     cocr_train_config cfg = {};
-    cfg.seed = seed;
+    k_set_seed<<<1, 1, 0, st>>>(s->seed_dev + 1, seed);
+    COCR_LAUNCHED(h);
+    g_seedp = s->seed_dev + 1;
     k_dropout_mask<<<ew_grid(n), 256, 0, st>>>(make_drop(&cfg, prob, site), n, out);
     COCR_LAUNCHED(h);
     return COCR_OK;
@@ -670,6 +737,10 @@ int adamw_step(cocr_handle *h, float *p, const float *g, float *m, float *v, int
     return COCR_OK;
 }
 
+static int train_step_body(cocr_handle *h, TrainState *s, const Plan &p, float *params, float *grads, const float *img, int64_t sb, int64_t sw,
+                           int64_t sh, const int32_t *widths, int B, int W, const int32_t *targets, const int32_t *target_lens, int max_target_len,
+                           const cocr_train_config *cfg, cudaStream_t st, float *loss_out, float *loss_per_line, float *taps);
+
 int train_step(cocr_handle *h, float *params, float *grads, const float *img, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths, int B, int W,
                const int32_t *targets, const int32_t *target_lens, int max_target_len, const cocr_train_config *cfg, cudaStream_t st, float *loss_out,
                float *loss_per_line, float *taps) {
@@ -677,9 +748,82 @@ int train_step(cocr_handle *h, float *params, float *grads, const float *img, in
     COCR_TRY(train_state(h, &s));
     const Dims &dm = h->dm;
     Plan p;
-    make_plan(dm, B, W, &p);
+    const int tc = cfg->compute == 1 ? 1 : 0;
+    make_plan(dm, B, W, tc, s->n_total, &p);
     COCR_TRY(ensure_train_ws(h, s, p.total));
     COCR_TRY(ensure_pe(h, s, p.T, st));
+    // the seed lives in device memory: the captured step is replayed with a new one
+    k_set_seed<<<1, 1, 0, st>>>(s->seed_dev, cfg->seed);
+    COCR_LAUNCHED(h);
+    g_seedp = s->seed_dev;
+    static const bool no_graph = getenv("COCR_NO_GRAPH") != nullptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (taps || h->profiling || no_graph || cap != cudaStreamCaptureStatusNone)
+        return train_step_body(h, s, p, params, grads, img, sb, sw, sh, widths, B, W, targets, target_lens, max_target_len, cfg, st, loss_out,
+                               loss_per_line, taps);
+    auto bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return (uint64_t)u; };
+    std::vector<uint64_t> key = {(uint64_t)B, (uint64_t)W, (uint64_t)max_target_len, (uint64_t)tc, (uint64_t)params, (uint64_t)grads, (uint64_t)img,
+                                 (uint64_t)sb, (uint64_t)sw, (uint64_t)sh, (uint64_t)widths, (uint64_t)targets, (uint64_t)target_lens, (uint64_t)loss_out,
+                                 (uint64_t)loss_per_line, (uint64_t)s->ws, bits(cfg->input_dropout_p), bits(cfg->feed_forward_dropout_p),
+                                 bits(cfg->attention_dropout_p), bits(cfg->conv_dropout_p), bits(cfg->bn_momentum)};
+    TrainState::StepGraph *sg = nullptr;
+    for (auto &g : s->graphs)
+        if (g.key == key) { sg = &g; break; }
+    if (!sg) {
+        if (s->graphs.size() >= 8) {
+            if (s->graphs.front().exec) cudaGraphExecDestroy(s->graphs.front().exec);
+            s->graphs.erase(s->graphs.begin());
+        }
+        s->graphs.emplace_back();
+        sg = &s->graphs.back();
+        sg->key = key;
+    }
+    if (!s->gstream) {
+        COCR_CUDA(h, cudaStreamCreateWithFlags(&s->gstream, cudaStreamNonBlocking));
+        COCR_CUDA(h, cudaEventCreateWithFlags(&s->g_in, cudaEventDisableTiming));
+        COCR_CUDA(h, cudaEventCreateWithFlags(&s->g_out, cudaEventDisableTiming));
+    }
+    if (!sg->exec) {
+        if (++sg->sightings < 2)       // first call with these arguments: plain launches (also settles every lazily-set function attribute)
+            return train_step_body(h, s, p, params, grads, img, sb, sw, sh, widths, B, W, targets, target_lens, max_target_len, cfg, st, loss_out,
+                                   loss_per_line, nullptr);
+        const int64_t l0 = h->launches;
+        COCR_CUDA(h, cudaStreamBeginCapture(s->gstream, cudaStreamCaptureModeThreadLocal));
+        const int rc = train_step_body(h, s, p, params, grads, img, sb, sw, sh, widths, B, W, targets, target_lens, max_target_len, cfg, s->gstream,
+                                       loss_out, loss_per_line, nullptr);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(s->gstream, &graph);
+        if (rc != COCR_OK || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            if (rc != COCR_OK) return rc;
+            return set_error(h, COCR_ERR_CUDA, "capture of the training step failed: %s", cudaGetErrorString(e));
+        }
+        sg->launches = h->launches - l0;
+        h->launches = l0;
+        const cudaError_t ei = cudaGraphInstantiate(&sg->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) {
+            sg->exec = nullptr;
+            return set_error(h, COCR_ERR_CUDA, "cudaGraphInstantiate (training step): %s", cudaGetErrorString(ei));
+        }
+    }
+    // replay on the handle's own stream (the caller's may be the legacy default stream, which cannot be captured), fenced by two events
+    COCR_CUDA(h, cudaEventRecord(s->g_in, st));
+    COCR_CUDA(h, cudaStreamWaitEvent(s->gstream, s->g_in, 0));
+    COCR_CUDA(h, cudaGraphLaunch(sg->exec, s->gstream));
+    COCR_CUDA(h, cudaEventRecord(s->g_out, s->gstream));
+    COCR_CUDA(h, cudaStreamWaitEvent(st, s->g_out, 0));
+    h->launches += sg->launches;
+    return COCR_OK;
+}
+
+static int train_step_body(cocr_handle *h, TrainState *s, const Plan &p, float *params, float *grads, const float *img, int64_t sb, int64_t sw,
+                           int64_t sh, const int32_t *widths, int B, int W, const int32_t *targets, const int32_t *target_lens, int max_target_len,
+                           const cocr_train_config *cfg, cudaStream_t st, float *loss_out, float *loss_per_line, float *taps) {
+    const Dims &dm = h->dm;
+    const int tc = p.tc;
     char *ws = s->ws;
     Ctx c{h, st, (float *)(ws + p.part), p.part_floats};
     const int M = p.M, d = dm.d, L = dm.L, C = dm.C;
@@ -691,6 +835,13 @@ int train_step(cocr_handle *h, float *params, float *grads, const float *img, in
     int32_t *lens = (int32_t *)(ws + p.lens);
     COCR_TRY(launch_out_lens(h, widths, B, W, lens, st));
 
+    if (tc) {     // bf16 mirror of the parameters (same offsets) and of the positional table: the operands of every GEMM of this step
+        ProfScope ps(h, "train_tc_weight_cast", st, 0.0, 6.0 * s->n_total);
+        k_cast_bf16<<<ew_grid((int64_t)s->n_total), 256, 0, st>>>(P, (int64_t)s->n_total, (__nv_bfloat16 *)(ws + p.pb), (int64_t)s->n_total, 1, (int)s->n_total);
+        COCR_LAUNCHED(h);
+        k_cast_bf16<<<ew_grid((int64_t)p.R * d), 256, 0, st>>>(s->pe, d, (__nv_bfloat16 *)(ws + p.peb), d, p.R, d);
+        COCR_LAUNCHED(h);
+    }
     // ---------------- forward ----------------
     float *a1 = F(p.a1), *a2 = F(p.a2), *a3 = F(p.a3), *wperm = F(p.wperm);
     {
@@ -714,15 +865,29 @@ int train_step(cocr_handle *h, float *params, float *grads, const float *img, in
         Mod m{c, dm, p, ws, P, G, cfg, l};
         const TrainLayerOff &o = s->L[l];
         const int x0 = 5 * l;
-        COCR_TRY(ffn_forward(m, 0, xs(x0), xs(x0 + 1)));
-        COCR_TRY(att_forward_mod(m, xs(x0 + 1), xs(x0 + 2)));
-        COCR_TRY(conv_forward_mod(m, xs(x0 + 2), xs(x0 + 3), params));
-        COCR_TRY(ffn_forward(m, 1, xs(x0 + 3), xs(x0 + 4)));
+        if (tc) {
+            COCR_TRY(ffn_forward_tc(m, 0, xs(x0), xs(x0 + 1)));
+            COCR_TRY(att_forward_tc(m, xs(x0 + 1), xs(x0 + 2)));
+            COCR_TRY(conv_forward_tc(m, xs(x0 + 2), xs(x0 + 3), params));
+            COCR_TRY(ffn_forward_tc(m, 1, xs(x0 + 3), xs(x0 + 4)));
+        } else {
+            COCR_TRY(ffn_forward(m, 0, xs(x0), xs(x0 + 1)));
+            COCR_TRY(att_forward_mod(m, xs(x0 + 1), xs(x0 + 2)));
+            COCR_TRY(conv_forward_mod(m, xs(x0 + 2), xs(x0 + 3), params));
+            COCR_TRY(ffn_forward(m, 1, xs(x0 + 3), xs(x0 + 4)));
+        }
         COCR_TRY(ln_fwd(c, xs(x0 + 4), P + o.fin_g, P + o.fin_b, xs(x0 + 5), m.stats(4), M, d));
     }
     const float *enc = xs(5 * L);
     float *logits = F(p.logits), *glog = F(p.glogits);
-    COCR_TRY(gemm_nt(c, enc, d, P + s->dec_w, d, P + s->dec_b, logits, C, M, C, d, 0, "train_decoder"));
+    TcBuf tb = {};
+    if (tc) {
+        tb = tc_buffers(ws, p);
+        COCR_TRY(tc_cast(c, enc, d, tb.encb, d, M, d));
+        COCR_TRY(tc_linear(c, tb.encb, d, tb.pb + s->dec_w, P + s->dec_b, logits, C, M, C, d, "train_tc_decoder"));
+    } else {
+        COCR_TRY(gemm_nt(c, enc, d, P + s->dec_w, d, P + s->dec_b, logits, C, M, C, d, 0, "train_decoder"));
+    }
     COCR_TRY(launch_ctc_loss(h, logits, targets, target_lens, lens, B, p.T, C, max_target_len, st, loss_out, loss_per_line, glog));
     if (taps) COCR_CUDA(h, cudaMemcpyAsync(taps, xs(0), (size_t)(1 + 5 * L) * M * d * 4, cudaMemcpyDeviceToDevice, st));
 
@@ -733,9 +898,15 @@ int train_step(cocr_handle *h, float *params, float *grads, const float *img, in
         if (gtaps) COCR_CUDA(h, cudaMemcpyAsync(gtaps + (size_t)idx * M * d, dx, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, st));
         return COCR_OK;
     };
-    COCR_TRY(gemm_tn(c, glog, C, enc, d, G + s->dec_w, M, C, d));
+    if (tc) {
+        COCR_TRY(tc_cast(c, glog, C, tb.glogb, p.Cp, M, C));
+        COCR_TRY(tc_wgrad(c, tb.glogb, p.Cp, tb.encb, d, G + s->dec_w, M, C, d));
+        COCR_TRY(tc_dgrad(c, tb.glogb, p.Cp, tb.pb + s->dec_w, dx, d, M, C, d));
+    } else {
+        COCR_TRY(gemm_tn(c, glog, C, enc, d, G + s->dec_w, M, C, d));
+        COCR_TRY(gemm_nn(c, glog, C, P + s->dec_w, d, dx, d, M, C, d));
+    }
     COCR_TRY(colsum(c, glog, C, M, C, G + s->dec_b));
-    COCR_TRY(gemm_nn(c, glog, C, P + s->dec_w, d, dx, d, M, C, d));
     COCR_TRY(tap(5 * L));
     for (int l = L - 1; l >= 0; --l) {
         Mod m{c, dm, p, ws, P, G, cfg, l};
@@ -743,13 +914,13 @@ int train_step(cocr_handle *h, float *params, float *grads, const float *img, in
         const int x0 = 5 * l;
         COCR_TRY(ln_bwd(c, dx, xs(x0 + 4), m.stats(4), P + o.fin_g, nullptr, dx, G + o.fin_g, G + o.fin_b, M, d));
         COCR_TRY(tap(x0 + 4));
-        COCR_TRY(ffn_backward(m, 1, xs(x0 + 3), dx));
+        COCR_TRY(tc ? ffn_backward_tc(m, 1, xs(x0 + 3), dx) : ffn_backward(m, 1, xs(x0 + 3), dx));
         COCR_TRY(tap(x0 + 3));
-        COCR_TRY(conv_backward_mod(m, xs(x0 + 2), dx));
+        COCR_TRY(tc ? conv_backward_tc(m, xs(x0 + 2), dx) : conv_backward_mod(m, xs(x0 + 2), dx));
         COCR_TRY(tap(x0 + 2));
-        COCR_TRY(att_backward_mod(m, xs(x0 + 1), dx));
+        COCR_TRY(tc ? att_backward_tc(m, xs(x0 + 1), dx) : att_backward_mod(m, xs(x0 + 1), dx));
         COCR_TRY(tap(x0 + 1));
-        COCR_TRY(ffn_backward(m, 0, xs(x0), dx));
+        COCR_TRY(tc ? ffn_backward_tc(m, 0, xs(x0), dx) : ffn_backward(m, 0, xs(x0), dx));
         COCR_TRY(tap(x0));
     }
     // front-end

@@ -23,7 +23,7 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 // keep (scale 1/(1-p)) when the word >= thresh = p * 2^32; thresh 0 = dropout off.
 // ------------------------------------------------------------------------------------------
 struct Drop {
-    uint64_t seed;
+    const uint64_t *seedp;      // device word: the step's seed (read at run time so that a captured step replays with a new seed)
     uint32_t site;
     uint32_t thresh;
     float inv_keep;
@@ -44,7 +44,7 @@ __device__ __forceinline__ uint4 philox4(uint64_t seed, uint32_t site, uint64_t 
 
 __device__ __forceinline__ float drop_scale(const Drop &dr, uint64_t e) {
     if (dr.thresh == 0) return 1.0f;
-    const uint4 r = philox4(dr.seed, dr.site, e >> 2);
+    const uint4 r = philox4(__ldg(dr.seedp), dr.site, e >> 2);
     const uint32_t w = (e & 2) ? ((e & 1) ? r.w : r.z) : ((e & 1) ? r.y : r.x);
     return w >= dr.thresh ? dr.inv_keep : 0.0f;
 }
@@ -199,7 +199,7 @@ __global__ void k_colsum(const float *__restrict__ A, int lda, int M, int N, int
 // LayerNorm (eps 1e-5, biased variance), one warp per row
 // ------------------------------------------------------------------------------------------
 __global__ void k_ln_fwd(const float *__restrict__ x, const float *__restrict__ g, const float *__restrict__ b, float *__restrict__ y,
-                         float *__restrict__ stats /* (M,2) mean, rstd; may be null */, int M, int d) {
+                         float *__restrict__ stats /* (M,2) mean, rstd; may be null */, int M, int d, __nv_bfloat16 *__restrict__ yb = nullptr) {
     const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
     if (row >= M) return;
     const float *xr = x + (int64_t)row * d;
@@ -209,8 +209,11 @@ __global__ void k_ln_fwd(const float *__restrict__ x, const float *__restrict__ 
     float v = 0.f;
     for (int c = lane; c < d; c += 32) { const float t = xr[c] - mean; v = fmaf(t, t, v); }
     const float rstd = 1.0f / sqrtf(warp_sum_f(v) / (float)d + 1e-5f);
-    float *yr = y + (int64_t)row * d;
-    for (int c = lane; c < d; c += 32) yr[c] = (xr[c] - mean) * rstd * g[c] + b[c];
+    for (int c = lane; c < d; c += 32) {
+        const float v = (xr[c] - mean) * rstd * g[c] + b[c];
+        if (y) y[(int64_t)row * d + c] = v;
+        if (yb) yb[(int64_t)row * d + c] = __float2bfloat16_rn(v);
+    }
     if (stats && lane == 0) { stats[2 * (int64_t)row] = mean; stats[2 * (int64_t)row + 1] = rstd; }
 }
 
@@ -256,23 +259,31 @@ __global__ void k_ln_param_grad(const float *__restrict__ dy, const float *__res
 // element-wise pieces
 // ------------------------------------------------------------------------------------------
 // out = dropout(silu(h))
-__global__ void k_silu_drop(const float *__restrict__ h, float *__restrict__ out, int64_t n, Drop dr) {
+__global__ void k_silu_drop(const float *__restrict__ h, float *__restrict__ out, int64_t n, Drop dr, __nv_bfloat16 *__restrict__ outb = nullptr) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         const float v = h[e];
-        out[e] = v * sigmoid_f(v) * drop_scale(dr, (uint64_t)e);
+        const float r = v * sigmoid_f(v) * drop_scale(dr, (uint64_t)e);
+        if (out) out[e] = r;
+        if (outb) outb[e] = __float2bfloat16_rn(r);
     }
 }
 // dh = dact * mask * silu'(h)   (in place on dact)
-__global__ void k_silu_drop_bwd(const float *__restrict__ h, float *__restrict__ dact, int64_t n, Drop dr) {
+__global__ void k_silu_drop_bwd(const float *__restrict__ h, float *__restrict__ dact, int64_t n, Drop dr, __nv_bfloat16 *__restrict__ outb = nullptr) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         const float v = h[e], s = sigmoid_f(v);
-        dact[e] = dact[e] * drop_scale(dr, (uint64_t)e) * (s * (1.0f + v * (1.0f - s)));
+        const float r = dact[e] * drop_scale(dr, (uint64_t)e) * (s * (1.0f + v * (1.0f - s)));
+        dact[e] = r;
+        if (outb) outb[e] = __float2bfloat16_rn(r);
     }
 }
 // out = x + factor * dropout(y)      (x may be null: out = factor*dropout(y))
-__global__ void k_resid_drop(const float *x, const float *__restrict__ y, float *out, float factor, int64_t n, Drop dr) {
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
-        out[e] = (x ? x[e] : 0.0f) + factor * y[e] * drop_scale(dr, (uint64_t)e);
+__global__ void k_resid_drop(const float *x, const float *__restrict__ y, float *out, float factor, int64_t n, Drop dr,
+                             __nv_bfloat16 *__restrict__ outb = nullptr) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const float r = (x ? x[e] : 0.0f) + factor * y[e] * drop_scale(dr, (uint64_t)e);
+        out[e] = r;
+        if (outb) outb[e] = __float2bfloat16_rn(r);
+    }
 }
 // GLU over the feature axis: u (M, 2d) -> g (M, d) = u[:, :d] * sigmoid(u[:, d:])   (convolution.py:139)
 __global__ void k_glu_fwd(const float *__restrict__ u, float *__restrict__ g, int64_t M, int d) {
@@ -282,13 +293,19 @@ __global__ void k_glu_fwd(const float *__restrict__ u, float *__restrict__ g, in
         g[e] = u[m * 2 * d + c] * sigmoid_f(u[m * 2 * d + d + c]);
     }
 }
-__global__ void k_glu_bwd(const float *__restrict__ u, const float *__restrict__ dg, float *__restrict__ du, int64_t M, int d) {
+__global__ void k_glu_bwd(const float *__restrict__ u, const float *__restrict__ dg, float *__restrict__ du, int64_t M, int d,
+                          __nv_bfloat16 *__restrict__ dub = nullptr) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < M * d; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t m = e / d;
         const int c = (int)(e % d);
         const float a = u[m * 2 * d + c], s = sigmoid_f(u[m * 2 * d + d + c]), v = dg[e];
-        du[m * 2 * d + c] = v * s;
-        du[m * 2 * d + d + c] = v * a * s * (1.0f - s);
+        const float da = v * s, db = v * a * s * (1.0f - s);
+        du[m * 2 * d + c] = da;
+        du[m * 2 * d + d + c] = db;
+        if (dub) {
+            dub[m * 2 * d + c] = __float2bfloat16_rn(da);
+            dub[m * 2 * d + d + c] = __float2bfloat16_rn(db);
+        }
     }
 }
 
@@ -378,11 +395,13 @@ __global__ void k_bn_finalize(const double *__restrict__ sums, int M, int d, flo
 }
 // z = silu(gamma * (c - mean) * rstd + beta)
 __global__ void k_bn_silu_fwd(const float *__restrict__ c, const float *__restrict__ stat, const float *__restrict__ gamma,
-                              const float *__restrict__ beta, float *__restrict__ z, int64_t M, int d) {
+                              const float *__restrict__ beta, float *__restrict__ z, int64_t M, int d, __nv_bfloat16 *__restrict__ zb = nullptr) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < M * d; e += (int64_t)gridDim.x * blockDim.x) {
         const int col = (int)(e % d);
         const float y = gamma[col] * (c[e] - stat[col]) * stat[d + col] + beta[col];
-        z[e] = y * sigmoid_f(y);
+        const float r = y * sigmoid_f(y);
+        if (z) z[e] = r;
+        if (zb) zb[e] = __float2bfloat16_rn(r);
     }
 }
 // dy = dz * silu'(y) written over dz; sums[0][c] += dy, sums[1][c] += dy * chat
@@ -782,6 +801,157 @@ k_att_bwd_pos(const float *__restrict__ qkv, const float *__restrict__ vb, const
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------
+// pieces of the tensor-core (bf16 operand) path
+// ------------------------------------------------------------------------------------------
+// dst (rows, ldd) bf16 <- src (rows, lds) fp32, columns [0, cols)
+__global__ void k_cast_bf16(const float *__restrict__ src, int64_t lds, __nv_bfloat16 *__restrict__ dst, int64_t ldd, int64_t rows, int cols) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < rows * cols; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / cols;
+        const int c = (int)(e % cols);
+        dst[r * ldd + c] = __float2bfloat16_rn(src[r * lds + c]);
+    }
+}
+// head-pitched copy: dst (rows, nh*dhp) bf16 <- src (rows, lds) fp32 columns [col0 + h*dh + c] (+ bias[h*dh + c])
+__global__ void k_head_pitch(const float *__restrict__ src, int64_t lds, int col0, const float *__restrict__ bias, __nv_bfloat16 *__restrict__ dst,
+                             int64_t rows, int nh, int dh, int dhp) {
+    const int d = nh * dh;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < rows * d; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / d;
+        const int c = (int)(e % d), hd = c / dh, cc = c % dh;
+        dst[r * nh * dhp + hd * dhp + cc] = __float2bfloat16_rn(src[r * lds + col0 + c] + (bias ? bias[c] : 0.0f));
+    }
+}
+// qkv (M, 3d) fp32 -> q+u | q+v | k | v, each head-pitched (M, nh*dhp) bf16
+__global__ void k_att_prep(const float *__restrict__ qkv, const float *__restrict__ ub, const float *__restrict__ vb, __nv_bfloat16 *__restrict__ qu,
+                           __nv_bfloat16 *__restrict__ qv, __nv_bfloat16 *__restrict__ kb, __nv_bfloat16 *__restrict__ vbuf, int64_t M, int nh, int dh,
+                           int dhp) {
+    const int d = nh * dh;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < M * d; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / d;
+        const int c = (int)(e % d), hd = c / dh, cc = c % dh;
+        const int64_t o = r * nh * dhp + hd * dhp + cc;
+        const float q = qkv[r * 3 * d + c];
+        qu[o] = __float2bfloat16_rn(q + ub[c]);
+        qv[o] = __float2bfloat16_rn(q + vb[c]);
+        kb[o] = __float2bfloat16_rn(qkv[r * 3 * d + d + c]);
+        vbuf[o] = __float2bfloat16_rn(qkv[r * 3 * d + 2 * d + c]);
+    }
+}
+// dctx (M, d) fp32 -> head-pitched bf16, and delta[(b,i), h] = sum_c dctx * ctx
+__global__ void k_att_bwd_prep(const float *__restrict__ dctx, const float *__restrict__ ctx, __nv_bfloat16 *__restrict__ dctxb, float *__restrict__ delta,
+                               int64_t M, int nh, int dh, int dhp) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < M * nh; e += (int64_t)gridDim.x * blockDim.x) {
+        const float *a = dctx + e * dh, *b = ctx + e * dh;
+        __nv_bfloat16 *o = dctxb + (e / nh) * nh * dhp + (e % nh) * dhp;
+        float s = 0.f;
+        for (int c = 0; c < dh; ++c) {
+            s = fmaf(a[c], b[c], s);
+            o[c] = __float2bfloat16_rn(a[c]);
+        }
+        delta[e] = s;
+    }
+}
+// P = softmax((Sc + shift(PS)) / sqrt(dh)) per row; one warp per row (b, h, i).  Sc (rows, Tp) fp32, PS (rows, Rp) fp32: the shifted
+// positional scores of row i are the CONTIGUOUS segment PS[i, T-1-i .. 2T-2-i] (attention.py:105-113).  Writes P and dropout(P) as bf16.
+__global__ void k_att_softmax_tc(const float *__restrict__ Sc, const float *__restrict__ PS, __nv_bfloat16 *__restrict__ P, __nv_bfloat16 *__restrict__ Pd,
+                                 int64_t rows, int T, int Tp, int Rp, float inv_sqrt, Drop dr) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int i = (int)(row % T);
+    const float *sc = Sc + row * Tp, *ps = PS + row * Rp + (T - 1 - i);
+    if (T <= 512) {         // the row lives in registers: one read of the scores
+        float v[16];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int j = lane + 32 * k;
+            v[k] = j < T ? (sc[j] + ps[j]) * inv_sqrt : -INFINITY;
+            mx = fmaxf(mx, v[k]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            v[k] = (lane + 32 * k < T) ? expf(v[k] - mx) : 0.f;
+            s += v[k];
+        }
+        s = warp_sum_f(s);
+        const float inv = 1.0f / s;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int j = lane + 32 * k;
+            if (j >= Tp) break;
+            const float pv = v[k] * inv;
+            P[row * Tp + j] = __float2bfloat16_rn(pv);
+            if (Pd != P) Pd[row * Tp + j] = __float2bfloat16_rn(j < T ? pv * drop_scale(dr, (uint64_t)(row * T + j)) : 0.f);
+        }
+        return;
+    }
+    float mx = -INFINITY;
+    for (int j = lane; j < T; j += 32) mx = fmaxf(mx, (sc[j] + ps[j]) * inv_sqrt);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float s = 0.f;
+    for (int j = lane; j < T; j += 32) s += expf((sc[j] + ps[j]) * inv_sqrt - mx);
+    s = warp_sum_f(s);
+    const float inv = 1.0f / s;
+    for (int j = lane; j < Tp; j += 32) {
+        float pv = 0.f;
+        if (j < T) pv = expf((sc[j] + ps[j]) * inv_sqrt - mx) * inv;
+        P[row * Tp + j] = __float2bfloat16_rn(pv);
+        if (Pd != P) Pd[row * Tp + j] = __float2bfloat16_rn(pv * drop_scale(dr, (uint64_t)(row * T + j)));
+    }
+}
+// delta[(b,i), h] = sum_c dctx[b,i,h,c] * ctx[b,i,h,c]
+__global__ void k_att_delta(const float *__restrict__ dctx, const float *__restrict__ ctx, float *__restrict__ delta, int64_t M, int nh, int dh) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < M * nh; e += (int64_t)gridDim.x * blockDim.x) {
+        const float *a = dctx + e * dh, *b = ctx + e * dh;         // (M, nh*dh) row-major: element e covers dh consecutive columns
+        float s = 0.f;
+        for (int c = 0; c < dh; ++c) s = fmaf(a[c], b[c], s);
+        delta[e] = s;
+    }
+}
+// dS = P * (mask * dPd - delta) / sqrt(dh) -> dSb (rows, Tp) bf16 and its un-shifted copy dPSb (rows, Rp) bf16 (zeros outside the segment)
+__global__ void k_att_ds_tc(const __nv_bfloat16 *__restrict__ P, const float *__restrict__ dPd, const float *__restrict__ delta,
+                            __nv_bfloat16 *__restrict__ dSb, __nv_bfloat16 *__restrict__ dPSb, int64_t rows, int T, int Tp, int Rp, int nh,
+                            float inv_sqrt, Drop dr) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int i = (int)(row % T);
+    const int64_t bh = row / T;
+    const int hd = (int)(bh % nh);
+    const int64_t b = bh / nh;
+    const float dl = delta[(b * T + i) * nh + hd];
+    const int seg0 = T - 1 - i;
+    __nv_bfloat16 *ps = dPSb + row * Rp;
+    for (int r = lane; r < Rp; r += 32)
+        if (r < seg0 || r >= seg0 + T) ps[r] = __float2bfloat16_rn(0.0f);
+    for (int j = lane; j < Tp; j += 32) {
+        float ds = 0.f;
+        if (j < T) {
+            const float pv = __bfloat162float(P[row * Tp + j]);
+            ds = pv * (dPd[row * Tp + j] * drop_scale(dr, (uint64_t)(row * T + j)) - dl) * inv_sqrt;
+        }
+        const __nv_bfloat16 v = __float2bfloat16_rn(ds);
+        dSb[row * Tp + j] = v;
+        if (j < T) ps[seg0 + j] = v;
+    }
+}
+// dst[r, c] = a[r, c] + b[r, c] for c < cols (dst row pitch ldd)
+__global__ void k_add2(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ dst, int64_t ldd, int64_t rows, int cols) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < rows * cols; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / cols;
+        const int c = (int)(e % cols);
+        dst[r * ldd + c] = a[e] + b[e];
+    }
+}
+
+__global__ void k_set_seed(uint64_t *dst, uint64_t v) { *dst = v; }
 
 // relative positional table rows k = 0..2T-2 <-> offset T-1-k (embedding.py:42-56)
 __global__ void k_rel_pos_table(float *__restrict__ pe, int T, int d) {

@@ -26,7 +26,7 @@ class Trainer:
                  conv_dropout_p: float = 0.1, conv_kernel_size: int = 31, half_step_residual: bool = True,
                  subsampling_conv_channels: int = 32, subsampling_factor: int = 4, device='cuda', lr: float = 1e-3,
                  weight_decay: float = 1e-3, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, warmup: int = 0,
-                 seed: int = 0, group: Optional[dist.ProcessGroup] = None, **kwargs):
+                 seed: int = 0, group: Optional[dist.ProcessGroup] = None, precision: str = 'fp32', **kwargs):
         """Hyper-parameter names are RecognitionModel's (model.py:58-72); the remaining training-loop arguments arrive in
         **kwargs and are ignored."""
         self._lib = _lib.load()
@@ -40,7 +40,11 @@ class Trainer:
                                     _lib.COCR_MASK_REFERENCE_UNMASKED)
         self._h = C.c_void_p()
         _lib.raise_for_status(self._lib.cocr_create(C.byref(self.hp), self.device.index, C.byref(self._h)), None)
-        self.cfg = _lib.cocr_train_config(input_dropout_p, feed_forward_dropout_p, attention_dropout_p, conv_dropout_p, 0.1, 0, seed)
+        if precision not in ('fp32', 'bf16'):
+            raise ValueError(f"unknown precision {precision!r}; expected 'fp32' (CUDA-core parity path) or 'bf16' (tcgen05, fp32 master)")
+        self.precision = precision
+        self.cfg = _lib.cocr_train_config(input_dropout_p, feed_forward_dropout_p, attention_dropout_p, conv_dropout_p, 0.1,
+                                          1 if precision == 'bf16' else 0, seed)
         self.seed = int(seed)
         self.num_classes, self.encoder_dim, self.num_layers = num_classes, encoder_dim, num_encoder_layers
         self.lr, self.weight_decay, self.betas, self.eps, self.warmup = lr, weight_decay, betas, eps, warmup
@@ -67,6 +71,7 @@ class Trainer:
         self.exp_avg = torch.zeros(self.n_trainable, dtype=torch.float32, device=self.device)
         self.exp_avg_sq = torch.zeros(self.n_trainable, dtype=torch.float32, device=self.device)
         self._loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._stage: Dict[str, torch.Tensor] = {}
 
     # -- life cycle -------------------------------------------------------------------------
     def close(self):
@@ -121,17 +126,21 @@ class Trainer:
         img = batch['image']
         if img.dim() != 4 or img.shape[1] != 1:
             raise ValueError(f'expected an (N,1,H,W) image batch, got {tuple(img.shape)}')
-        img = img.to(self.device, dtype=torch.float32)
+        if img.shape[2] != self.hp.height:
+            raise ValueError(f'line height {img.shape[2]} does not match the model ({self.hp.height})')
+        # Persistent device staging: the library replays the step's launch sequence as a CUDA graph as long as the buffer
+        # addresses repeat, so host batches are copied into buffers that live as long as the trainer.
+        if not (img.is_cuda and img.dtype == torch.float32 and img.device == self.device):
+            img = self._staged('image', img, torch.float32)
         x = img.squeeze(1).transpose(1, 2)                                  # model.py:132: (N, W, H) view
         B, W, H = x.shape
-        if H != self.hp.height:
-            raise ValueError(f'line height {H} does not match the model ({self.hp.height})')
-        widths = torch.as_tensor(batch['seq_lens']).to(self.device, dtype=torch.int32).contiguous()
+        widths = self._staged('seq_lens', torch.as_tensor(batch['seq_lens']), torch.int32)
         tl_host = torch.as_tensor(batch['target_lens']).to('cpu', dtype=torch.int64)
-        tlens = tl_host.to(self.device, dtype=torch.int32).contiguous()
-        targets = torch.as_tensor(batch['target']).to(self.device, dtype=torch.int32).contiguous()
-        if targets.numel() != int(tl_host.sum()):
+        tlens = self._staged('target_lens', tl_host, torch.int32)
+        tg = torch.as_tensor(batch['target'])
+        if tg.numel() != int(tl_host.sum()):
             raise ValueError('target has to be the 1-D concatenation of the label sequences')
+        targets = self._staged('target', tg, torch.int32, capacity=max(int(tg.numel()), B * 128))
         taps = None
         if debug_taps:
             T = int(out_frames(torch.tensor([W]))[0])
@@ -143,6 +152,17 @@ class Trainer:
                                               int(tl_host.max()) if B else 0, C.byref(self.cfg), self._stream(),
                                               self._loss.data_ptr(), None, taps.data_ptr() if taps is not None else None))
         return (self._loss, taps) if debug_taps else self._loss
+
+    def _staged(self, name: str, src: torch.Tensor, dtype, capacity: Optional[int] = None) -> torch.Tensor:
+        """Copy `src` into a persistent device buffer (re-allocated only when it has to grow) and return the view of it."""
+        n = src.numel()
+        buf = self._stage.get(name)
+        if buf is None or buf.numel() < n or buf.dtype != dtype:
+            buf = torch.empty(max(n, capacity or n), dtype=dtype, device=self.device)
+            self._stage[name] = buf
+        view = buf[:n].view(src.shape)
+        view.copy_(src, non_blocking=True)
+        return view
 
     def allreduce_gradients(self):
         """ONE all-reduce(sum) of the trainable prefix of the flat gradient buffer plus the loss (NCCL over NVLink)."""

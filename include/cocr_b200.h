@@ -232,7 +232,7 @@ int cocr_profile_report(cocr_handle *h, char *buf, size_t cap);
 typedef struct cocr_train_config {
     float input_dropout_p, feed_forward_dropout_p, attention_dropout_p, conv_dropout_p;   /* encoder.py:135-152 */
     float bn_momentum;                                                                   /* nn.BatchNorm1d default 0.1 */
-    uint32_t reserved;
+    uint32_t compute;                 /* 0: fp32 CUDA-core kernels (parity path); 1: bf16 operands on tcgen05, fp32 accumulation / master copy */
     uint64_t seed;
 } cocr_train_config;
 
