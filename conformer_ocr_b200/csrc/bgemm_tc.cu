@@ -271,6 +271,7 @@ int launch_bgemm(cocr_handle *h, const BgProblem &g, cudaStream_t st, const char
     const uint32_t b_bytes = g.b.mn ? (uint32_t)p.nbox_b * 8192u : (uint32_t)bn * 128u;
     const uint32_t stage_bytes = (BG_A_BYTES + b_bytes + 1023u) & ~1023u;
     p.stages = p.kchunks < BG_STAGES ? (p.kchunks < 1 ? 1 : p.kchunks) : BG_STAGES;
+    if (p.stages == 3 && 3 * stage_bytes > 112 * 1024 && 2 * stage_bytes <= 112 * 1024) p.stages = 2;   // two CTAs per SM beat a third stage
     const size_t smem = (size_t)p.stages * stage_bytes;
     static PerDevice<size_t> attr;
     if (smem > attr.get()) {

@@ -225,7 +225,13 @@ int ln_fwd(Ctx &c, const float *x, const float *g, const float *b, float *y, flo
 // parameter gradients of a LayerNorm and dx_out = resid + LN'(dy)
 int ln_bwd(Ctx &c, const float *dy, const float *x, const float *stats, const float *g, const float *resid, float *dx_out, float *dgamma,
            float *dbeta, int M, int d) {
-    ProfScope ps(c.h, "train_layernorm_bwd", c.st, 0.0, 20.0 * M * d);
+    ProfScope ps(c.h, "train_layernorm_bwd", c.st, 0.0, 16.0 * M * d);
+    if (d <= 32 * LNB_MAXC) {
+        const int rpb = 32;
+        k_ln_bwd_fused<<<(M + rpb - 1) / rpb, 256, 0, c.st>>>(dy, x, stats, g, resid, dx_out, M, d, rpb, dgamma, dbeta);
+        TK_LAUNCHED(c);
+        return COCR_OK;
+    }
     const int rpb = 32;
     k_ln_param_grad<<<dim3((M + rpb - 1) / rpb, (d + 255) / 256), 256, 0, c.st>>>(dy, x, stats, M, d, rpb, dgamma, dbeta);
     TK_LAUNCHED(c);
@@ -313,11 +319,13 @@ int dwconv(Ctx &c, const float *x, const float *w, float *y, int B, int T, int d
     return COCR_OK;
 }
 int dwconv_wgrad(Ctx &c, const float *x, const float *dy, float *dw, int B, int T, int d, int K) {
-    const size_t smem = 4 * (size_t)(2 * DWT + K - 1) * d;
+    int tile = 64;                                   // frames per CTA: larger tiles = fewer atomics per output, fewer CTAs
+    while (tile > 16 && (4 * (size_t)(2 * tile + K - 1) * d > 200 * 1024 || tile >= 2 * T)) tile /= 2;
+    const size_t smem = 4 * (size_t)(2 * tile + K - 1) * d;
     if (smem > 200 * 1024) return set_error(c.h, COCR_ERR_UNSUPPORTED, "depthwise conv tile needs %zu B of shared memory", smem);
     COCR_TRY(set_smem(c.h, k_dwconv1d_wgrad, smem));
     ProfScope ps(c.h, "train_dwconv_wgrad", c.st, 2.0 * K * B * (double)T * d, 8.0 * B * T * d);
-    k_dwconv1d_wgrad<<<dim3((T + DWT - 1) / DWT, B), 256, smem, c.st>>>(x, dy, dw, T, d, K);
+    k_dwconv1d_wgrad<<<dim3((T + tile - 1) / tile, B), 256, smem, c.st>>>(x, dy, dw, T, d, K, tile);
     TK_LAUNCHED(c);
     return COCR_OK;
 }
@@ -353,7 +361,7 @@ struct Plan {
     size_t part_floats;
     // tensor-core path (bf16 operands): tc == 1
     int tc, Tp, Rp, dhp, HP, Cp;
-    size_t pb, peb, xnb, zb, actb, dyb, wideb, ctxb, encb, glogb, dposb, qu, qv, kb, vb, dctxb, posb, Sc, PS, dSb, dPSb, delta, Pb16;
+    size_t a3b, wpermb, pb, peb, xnb, zb, actb, dyb, wideb, ctxb, encb, glogb, dposb, qu, qv, kb, vb, dctxb, posb, Sc, PS, dSb, dPSb, delta, Pb16;
     size_t total;
 };
 
@@ -401,6 +409,8 @@ void make_plan(const Dims &dm, int B, int W, int tc, size_t n_total, Plan *p) {
         const size_t bh = (size_t)B * dm.nh, R = p->R;
         p->Pb16 = b.take16(2 * L * bh * p->T * p->Tp);        // per layer: P then dropout(P)
         p->pb = b.take16(n_total);
+        p->a3b = b.take16(M * dm.feat);
+        p->wpermb = b.take16(d * dm.feat);
         p->peb = b.take16(R * d);
         // operands saved per layer for the backward pass (bf16): LayerNorm outputs of the four modules, FFN activations,
         // conv-module activation, attention context and the head-pitched q+u | q+v | k | v | p
@@ -857,7 +867,13 @@ static int train_step_body(cocr_handle *h, TrainState *s, const Plan &p, float *
     COCR_LAUNCHED(h);
     {
         float *y = F(p.t_d1);
-        COCR_TRY(gemm_nt(c, a3, dm.feat, wperm, dm.feat, P + s->sub_bout, y, d, M, d, dm.feat, 0, "train_fe_out"));
+        if (tc) {
+            COCR_TRY(tc_cast(c, a3, dm.feat, (__nv_bfloat16 *)(ws + p.a3b), dm.feat, M, dm.feat));
+            COCR_TRY(tc_cast(c, wperm, dm.feat, (__nv_bfloat16 *)(ws + p.wpermb), dm.feat, d, dm.feat));
+            COCR_TRY(tc_linear(c, (__nv_bfloat16 *)(ws + p.a3b), dm.feat, (__nv_bfloat16 *)(ws + p.wpermb), P + s->sub_bout, y, d, M, d, dm.feat, "train_tc_fe_out"));
+        } else {
+            COCR_TRY(gemm_nt(c, a3, dm.feat, wperm, dm.feat, P + s->sub_bout, y, d, M, d, dm.feat, 0, "train_fe_out"));
+        }
         k_resid_drop<<<ew_grid((int64_t)M * d), 256, 0, st>>>(nullptr, y, xs(0), 1.0f, (int64_t)M * d, make_drop(cfg, cfg->input_dropout_p, 0));
         COCR_LAUNCHED(h);
     }
@@ -926,13 +942,16 @@ static int train_step_body(cocr_handle *h, TrainState *s, const Plan &p, float *
     // front-end
     {
         float *dy = F(p.t_d0), *gwp = F(p.gwperm), *da3 = F(p.t_ff0), *da2 = F(p.t_ff1);
-        k_resid_drop<<<ew_grid((int64_t)M * d), 256, 0, st>>>(nullptr, dx, dy, 1.0f, (int64_t)M * d, make_drop(cfg, cfg->input_dropout_p, 0));
+        k_resid_drop<<<ew_grid((int64_t)M * d), 256, 0, st>>>(nullptr, dx, dy, 1.0f, (int64_t)M * d, make_drop(cfg, cfg->input_dropout_p, 0),
+                                                              tc ? tb.dyb : nullptr);
         COCR_LAUNCHED(h);
-        COCR_TRY(gemm_tn(c, dy, d, a3, dm.feat, gwp, M, d, dm.feat));
+        if (tc) COCR_TRY(tc_wgrad(c, tb.dyb, d, (__nv_bfloat16 *)(ws + p.a3b), dm.feat, gwp, M, d, dm.feat));
+        else COCR_TRY(gemm_tn(c, dy, d, a3, dm.feat, gwp, M, d, dm.feat));
         k_permute_wout<<<ew_grid((int64_t)d * dm.feat), 256, 0, st>>>(gwp, G + s->sub_wout, d, dm.cc, dm.F, 1);
         COCR_LAUNCHED(h);
         COCR_TRY(colsum(c, dy, d, M, d, G + s->sub_bout));
-        COCR_TRY(gemm_nn(c, dy, d, wperm, dm.feat, da3, dm.feat, M, d, dm.feat));
+        if (tc) COCR_TRY(tc_dgrad(c, tb.dyb, d, (__nv_bfloat16 *)(ws + p.wpermb), da3, dm.feat, M, d, dm.feat));
+        else COCR_TRY(gemm_nn(c, dy, d, wperm, dm.feat, da3, dm.feat, M, d, dm.feat));
         const int64_t n2 = (int64_t)M * dm.feat, n1 = (int64_t)B * p.T2 * dm.F2 * dm.cc;
         k_relu_bwd<<<ew_grid(n2), 256, 0, st>>>(a3, da3, n2);
         COCR_LAUNCHED(h);

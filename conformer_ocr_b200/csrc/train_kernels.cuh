@@ -239,6 +239,63 @@ __global__ void k_ln_bwd(const float *__restrict__ dy, const float *__restrict__
     }
 }
 
+// One pass: dx_out = resid + LN'(dy) and dgamma / dbeta.  A block takes `rows_per_block` rows, a warp one row at a time; lane l owns
+// columns l, l+32, ... (d <= 32 * LNB_MAXC) and keeps its share of the column sums in registers; 8 warps are summed through shared memory.
+constexpr int LNB_MAXC = 8;
+__global__ void __launch_bounds__(256)
+k_ln_bwd_fused(const float *__restrict__ dy, const float *__restrict__ x, const float *__restrict__ stats, const float *__restrict__ g,
+               const float *resid, float *dx_out, int M, int d, int rows_per_block, float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    __shared__ float red[2][8][32 * LNB_MAXC];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    float ag[LNB_MAXC], ab[LNB_MAXC], gv[LNB_MAXC];
+#pragma unroll
+    for (int k = 0; k < LNB_MAXC; ++k) {
+        ag[k] = 0.f; ab[k] = 0.f;
+        gv[k] = (lane + 32 * k < d) ? g[lane + 32 * k] : 0.f;
+    }
+    for (int row = r0 + warp; row < r1; row += 8) {
+        const float mean = stats[2 * (int64_t)row], rstd = stats[2 * (int64_t)row + 1];
+        const float *xr = x + (int64_t)row * d, *dr = dy + (int64_t)row * d;
+        float xh[LNB_MAXC], dv[LNB_MAXC];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < LNB_MAXC; ++k) {
+            const int c = lane + 32 * k;
+            xh[k] = c < d ? (xr[c] - mean) * rstd : 0.f;
+            dv[k] = c < d ? dr[c] : 0.f;
+            const float dh = dv[k] * gv[k];
+            s1 += dh;
+            s2 = fmaf(dh, xh[k], s2);
+            ag[k] = fmaf(dv[k], xh[k], ag[k]);
+            ab[k] += dv[k];
+        }
+        s1 = warp_sum_f(s1) / (float)d;
+        s2 = warp_sum_f(s2) / (float)d;
+#pragma unroll
+        for (int k = 0; k < LNB_MAXC; ++k) {
+            const int c = lane + 32 * k;
+            if (c < d) {
+                const float v = rstd * (dv[k] * gv[k] - s1 - xh[k] * s2);
+                dx_out[(int64_t)row * d + c] = (resid ? resid[(int64_t)row * d + c] : 0.0f) + v;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < LNB_MAXC; ++k) {
+        red[0][warp][lane + 32 * k] = ag[k];
+        red[1][warp][lane + 32 * k] = ab[k];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += 256) {
+        float sg = 0.f, sb = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { sg += red[0][w][c]; sb += red[1][w][c]; }
+        atomicAdd(dgamma + c, sg);
+        atomicAdd(dbeta + c, sb);
+    }
+}
+
 // dgamma[c] += sum_m dy*xhat, dbeta[c] += sum_m dy
 __global__ void k_ln_param_grad(const float *__restrict__ dy, const float *__restrict__ x, const float *__restrict__ stats, int M, int d,
                                 int rows_per_block, float *__restrict__ dgamma, float *__restrict__ dbeta) {
@@ -337,9 +394,9 @@ k_dwconv1d(const float *__restrict__ x, const float *__restrict__ w, float *__re
         y[((int64_t)b * T + t) * d + c] = acc;
     }
 }
-// dw[c,k] += sum_{b,t} dy[b,t,c] * x[b,t+k-pad,c]
+// dw[c,k] += sum_{b,t} dy[b,t,c] * x[b,t+k-pad,c]      (tiles of DWT frames; the caller picks DWT so that the tile fits shared memory)
 __global__ void __launch_bounds__(256)
-k_dwconv1d_wgrad(const float *__restrict__ x, const float *__restrict__ dy, float *__restrict__ dw, int T, int d, int K) {
+k_dwconv1d_wgrad(const float *__restrict__ x, const float *__restrict__ dy, float *__restrict__ dw, int T, int d, int K, int DWT) {
     extern __shared__ float sm[];
     float *tile = sm;                               // [DWT + K - 1][d]  x
     float *dt = sm + (size_t)(DWT + K - 1) * d;     // [DWT][d]          dy
@@ -931,15 +988,17 @@ __global__ void k_att_ds_tc(const __nv_bfloat16 *__restrict__ P, const float *__
     __nv_bfloat16 *ps = dPSb + row * Rp;
     for (int r = lane; r < Rp; r += 32)
         if (r < seg0 || r >= seg0 + T) ps[r] = __float2bfloat16_rn(0.0f);
-    for (int j = lane; j < Tp; j += 32) {
-        float ds = 0.f;
-        if (j < T) {
-            const float pv = __bfloat162float(P[row * Tp + j]);
-            ds = pv * (dPd[row * Tp + j] * drop_scale(dr, (uint64_t)(row * T + j)) - dl) * inv_sqrt;
-        }
-        const __nv_bfloat16 v = __float2bfloat16_rn(ds);
-        dSb[row * Tp + j] = v;
-        if (j < T) ps[seg0 + j] = v;
+    // pairs of columns per lane (Tp is even): 4-byte loads / stores of the bf16 rows, 8-byte loads of the fp32 row
+    for (int j = 2 * lane; j < Tp; j += 64) {
+        const __nv_bfloat162 p2 = *reinterpret_cast<const __nv_bfloat162 *>(P + row * Tp + j);
+        const float2 g2 = *reinterpret_cast<const float2 *>(dPd + row * Tp + j);
+        float d0 = 0.f, d1 = 0.f;
+        if (j < T) d0 = __low2float(p2) * (g2.x * drop_scale(dr, (uint64_t)(row * T + j)) - dl) * inv_sqrt;
+        if (j + 1 < T) d1 = __high2float(p2) * (g2.y * drop_scale(dr, (uint64_t)(row * T + j + 1)) - dl) * inv_sqrt;
+        const __nv_bfloat162 v2 = __floats2bfloat162_rn(d0, d1);
+        *reinterpret_cast<__nv_bfloat162 *>(dSb + row * Tp + j) = v2;
+        if (j < T) ps[seg0 + j] = __low2bfloat16(v2);
+        if (j + 1 < T) ps[seg0 + j + 1] = __high2bfloat16(v2);
     }
 }
 // dst[r, c] = a[r, c] + b[r, c] for c < cols (dst row pitch ldd)

@@ -28,7 +28,8 @@ BF16_NOTE = """bf16 mode (tcgen05 operands rounded to 8 significant bits, fp32 a
 usual one of mixed-precision training - loss within 5e-3, every gradient tensor within 0.15 of max(its largest entry, 1e-3 x the
 model's largest gradient entry ... 5e-2 x for the
 key-projection bias, whose exact gradient is zero and whose computed one is the rounding noise of the attention backward pass),
-and the whole gradient vector within 2 degrees of the reference's (cosine >= 0.9994)."""
+and the whole gradient vector within 2 degrees of the reference's (cosine >= 0.9994) on the shallow golden cases; the 16-layer case is
+rated against torch's own bf16 autocast (see test_train_step_bf16_default_spec_against_port)."""
 
 
 def make_trainer(hp, C, device, dropout=0.0, **kw):
@@ -156,8 +157,11 @@ def test_train_step_bf16_matches_reference_golden(cuda_device, name):
 
 
 def test_train_step_bf16_default_spec_against_port(cuda_device):
-    """16 layers at 1536 px with dropout 0.1 everywhere, the float64 port replaying the kernels' masks: bf16 path (BF16_NOTE)
-    and, on the same batch, agreement of the bf16 path with the fp32 CUDA path."""
+    """16 layers at 1536 px with dropout 0.1 everywhere, the float64 port replaying the kernels' masks.  Rounding noise of bf16
+    operands grows with depth (measured on B200, profiles/r02_train_bf16_noise.log: cosine 0.99998 / 0.9998 / 0.990 at 1 / 4 / 16
+    layers), so the yardstick here is the reference's own mixed-precision mode: torch's bf16 autocast over the same operator
+    sequence, masks and batch.  The tensor-core path has to be at least as close to the float64 gradient as autocast is, and
+    within cosine 0.985 / 0.35 per tensor in absolute terms."""
     hp = dict(O.DEFAULT_HPARAMS)
     C, B, W, prob = 256, 3, 1536, 0.1
     w = O.make_weights(hp, C, seed=31)
@@ -172,10 +176,23 @@ def test_train_step_bf16_default_spec_against_port(cuda_device):
 
     ref_loss, ref_g, _ = port_grads(batch, w, hp, cuda_device, mask_fn=mask_fn, dropout=prob)
     assert abs(loss.item() - ref_loss) <= 5e-3 * abs(ref_loss), (loss.item(), ref_loss)
-    worst = check_grads(tr, ref_g, tol=0.15, zero_floor=0.05)
+    worst = check_grads(tr, ref_g, tol=0.35, zero_floor=0.05)
     cos = flat_cosine(tr, ref_g)
-    assert cos >= 0.9994, cos
-    print(f'default spec bf16, dropout {prob}: loss {loss.item():.3f} (port {ref_loss:.3f}), worst gradient rel err {worst:.3f}, cosine {cos:.6f}')
+    # torch autocast (bf16 matmuls, fp32 master weights) on the same batch and masks
+    wt = {k: torch.from_numpy(v.copy()).to(cuda_device).requires_grad_(not k.endswith(('running_mean', 'running_var'))) for k, v in w.items()}
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        probits, olens, _ = TP.train_forward(batch['image'].to(cuda_device), batch['seq_lens'], wt, hp, dropout=prob, mask_fn=mask_fn)
+    logp = torch.nn.functional.log_softmax(probits.float(), -1)
+    tl = torch.nn.functional.ctc_loss(logp.transpose(0, 1), batch['target'].to(cuda_device), olens, batch['target_lens'], blank=0,
+                                      reduction='sum', zero_infinity=True)
+    tl.backward()
+    keys = tr.trainable_keys()
+    a = np.concatenate([wt[k].grad.double().cpu().numpy().ravel() for k in keys])
+    b = np.concatenate([np.asarray(ref_g[k], dtype=np.float64).ravel() for k in keys])
+    cos_torch = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
+    print(f'default spec bf16, dropout {prob}: loss {loss.item():.3f} (port {ref_loss:.3f}), worst gradient rel err {worst:.3f}, '
+          f'cosine {cos:.6f} (torch bf16 autocast: {cos_torch:.6f})')
+    assert cos >= 0.985 and cos >= cos_torch - 1e-3, (cos, cos_torch)
     tr.close()
 
 
