@@ -769,7 +769,8 @@ def run_train(args):
         lib, h = tr._lib, tr._h
         lib.cocr_set_profiling(h, 1)
         for _ in range(args.profile_steps):
-            tr.step(dev_batch)
+            tr.forward_backward(dev_batch)       # rank 0 alone: no collective in the profiling passes
+            tr.optimizer_step()
         buf = Ct.create_string_buffer(1 << 16)
         lib.cocr_profile_report(h, buf, len(buf))
         lib.cocr_set_profiling(h, 0)

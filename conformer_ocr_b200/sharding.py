@@ -151,3 +151,14 @@ def allreduce_bucket(tensors: Sequence[torch.Tensor], group: Optional[dist.Proce
         out.append(flat[off:off + n].view(t.shape).to(t.dtype))
         off += n
     return out
+
+
+def allreduce_flat_prefix(flat: torch.Tensor, n: int, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """The exchange step of the data-parallel training step: sum the first `n` elements of the flat gradient
+    buffer over all ranks IN PLACE with one all-reduce (the loss is a sum, model.py:119: gradients are summed, not averaged).
+    Elements beyond `n` (the BatchNorm running statistics of the rank) are left alone.  No-op without a process group."""
+    if n < 0 or n > flat.numel() or flat.dim() != 1:
+        raise ValueError(f'bad prefix {n} of a buffer with shape {tuple(flat.shape)}')
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1 and n > 0:
+        dist.all_reduce(flat[:n], op=dist.ReduceOp.SUM, group=group)
+    return flat

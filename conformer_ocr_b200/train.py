@@ -17,6 +17,7 @@ import torch.distributed as dist
 from . import _lib
 from .conformer.encoder import encoder_param_spec
 from .engine import out_frames
+from .sharding import allreduce_flat_prefix
 
 
 class Trainer:
@@ -166,8 +167,7 @@ class Trainer:
 
     def allreduce_gradients(self):
         """ONE all-reduce(sum) of the trainable prefix of the flat gradient buffer plus the loss (NCCL over NVLink)."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            dist.all_reduce(self.grads[:self.n_trainable], op=dist.ReduceOp.SUM, group=self.group)
+        allreduce_flat_prefix(self.grads, self.n_trainable, self.group)
 
     def optimizer_step(self):
         """torch.optim.AdamW(lr, weight_decay) (model.py:272-274) with the linear warm-up of model.py:230-235."""

@@ -123,3 +123,43 @@ def test_allreduce_bucket_world_size_2_gloo():
             torch.testing.assert_close(got[r][1][i].double(), want, rtol=1e-6, atol=1e-6)
     solo = S.allreduce_bucket([torch.ones(3)])                 # no process group: identity
     assert torch.equal(solo[0], torch.ones(3)) and S.allreduce_bucket([]) == []
+
+
+def _flat_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(200 + rank)
+        flat = torch.rand(1000, generator=g)
+        before = flat.clone()
+        S.allreduce_flat_prefix(flat, 900)
+        q.put((rank, before, flat.clone()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allreduce_flat_prefix_world_size_2_gloo():
+    """the Trainer's exchange step: the trainable prefix of the flat gradient buffer is summed over the ranks in place, the
+    per-rank tail (BatchNorm running statistics) is not touched"""
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_flat_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {r: (a, b) for r, a, b in (q.get(timeout=120) for _ in range(2))}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = got[0][0][:900] + got[1][0][:900]
+    for r in (0, 1):
+        torch.testing.assert_close(got[r][1][:900], want, rtol=1e-6, atol=1e-6)
+        assert torch.equal(got[r][1][900:], got[r][0][900:])
+    import pytest
+    with pytest.raises(ValueError):
+        S.allreduce_flat_prefix(torch.zeros(4), 5)
+    assert torch.equal(S.allreduce_flat_prefix(torch.ones(4), 4), torch.ones(4))        # no process group: identity
