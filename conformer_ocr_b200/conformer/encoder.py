@@ -174,6 +174,9 @@ class ConformerEncoder(EngineOwner):
                             conv_expansion=conv_expansion_factor, conv_kernel_size=conv_kernel_size,
                             half_step_residual=half_step_residual, subsampling_conv_channels=subsampling_conv_channels,
                             subsampling_factor=subsampling_factor)
+        # dropout probabilities: the identity in inference, used by the training step (conformer_ocr_b200.train.Trainer)
+        self.dropout_ps = dict(input_dropout_p=input_dropout_p, feed_forward_dropout_p=feed_forward_dropout_p,
+                               attention_dropout_p=attention_dropout_p, conv_dropout_p=conv_dropout_p)
         for key, shape, kind in encoder_param_spec(input_dim, encoder_dim, num_layers, num_attention_heads,
                                                    feed_forward_expansion_factor, conv_kernel_size,
                                                    subsampling_conv_channels):
@@ -193,9 +196,9 @@ class ConformerEncoder(EngineOwner):
         """Dropout is the identity in inference; kept for interface parity (encoder.py:177-181)."""
 
     def train(self, mode: bool = True):
-        if mode:
-            raise NotImplementedError('conformer_ocr_b200 implements the inference path only')
-        return super().train(False)
+        """The encoder on its own has no training step (the loss lives in RecognitionModel, model.py:129-145): as a child of a
+        RecognitionModel mirror it follows the parent's mode; stand-alone `forward` always computes in eval-mode arithmetic."""
+        return super().train(mode)
 
     def _engine_kwargs(self):
         return dict(num_classes=0, **self.hparams)

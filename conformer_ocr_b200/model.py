@@ -1,8 +1,9 @@
 """Host-side mirror of the hot-path slice of `conformer_ocr.model.RecognitionModel`
-(model.py:39-151): construction (`:99-116`), `forward(x, seq_lens)` (`:125-127`) and the forward half of `_step`
-(`:129-145`: encoder, decoder, log_softmax, CTC loss) including the gradient of the loss with respect to the decoder
-outputs.  The backward pass through the encoder, the Lightning training loop, metrics and the optimiser factory are not
-built."""
+(model.py:39-158): construction (`:99-116`), `forward(x, seq_lens)` (`:125-127`), `_step` (`:129-145`: encoder, decoder,
+log_softmax, CTC loss) and `training_step` (`:153-158`) together with what Lightning does around it - backward pass, gradient
+all-reduce, `optimizer_step` with the reference's warm-up (`:226-235`) - through `conformer_ocr_b200.train.Trainer`
+(csrc/train.cu).  The Lightning loop itself, metrics, schedulers other than the warm-up and the data module are not built
+(SURVEY.md 2 C9/C10)."""
 from __future__ import annotations
 
 from typing import Optional, Tuple
@@ -49,9 +50,62 @@ class RecognitionModel(EngineOwner):
         return dict(self.nn.state_dict())
 
     def train(self, mode: bool = True):
-        if mode:
-            raise NotImplementedError('conformer_ocr_b200 implements the inference path only')
-        return super().train(False)
+        """train(True) selects the training step (`training_step`); leaving it copies the trained parameters and BatchNorm
+        statistics back into this module's tensors, so `forward` / `predict*` see them (the inference engine re-uploads)."""
+        if not mode and getattr(self, '_trainer', None) is not None and self._trainer_dirty:
+            self.sync_from_trainer()
+        return super().train(mode)
+
+    # -- training (model.py:153-158 + Lightning's backward / DDP / optimizer_step) ---------------------------------------
+    def configure_training(self, lr: float = 1e-3, weight_decay: float = 1e-3, warmup: int = 0, precision: str = 'bf16', seed: int = 0,
+                           group=None, **kwargs):
+        """The optimiser settings `_configure_optimizer_and_lr_scheduler` reads from hparams (model.py:255-274; AdamW only) and the
+        arithmetic of the step: 'bf16' = tcgen05 operands with fp32 accumulation and master weights, 'fp32' = CUDA-core parity path."""
+        self._train_cfg = dict(lr=lr, weight_decay=weight_decay, warmup=warmup, precision=precision, seed=seed, group=group)
+        self._trainer = None
+
+    def trainer_for(self, device):
+        from .train import Trainer
+        device = torch.device(device)
+        if getattr(self, '_trainer', None) is None or self._trainer.device != torch.device('cuda', device.index if device.index is not None else torch.cuda.current_device()):
+            cfg = dict(getattr(self, '_train_cfg', None) or dict(lr=1e-3, weight_decay=1e-3, warmup=0, precision='bf16', seed=0, group=None))
+            hp = dict(self.nn['encoder'].hparams)
+            dp = self.nn['encoder'].dropout_ps
+            self._trainer = Trainer(num_classes=self.num_classes, height=hp['height'], encoder_dim=hp['encoder_dim'],
+                                    num_encoder_layers=hp['num_layers'], num_attention_heads=hp['num_heads'],
+                                    feed_forward_expansion_factor=hp['ff_expansion'], conv_expansion_factor=hp['conv_expansion'],
+                                    conv_kernel_size=hp['conv_kernel_size'], half_step_residual=hp['half_step_residual'],
+                                    subsampling_conv_channels=hp['subsampling_conv_channels'], subsampling_factor=hp['subsampling_factor'],
+                                    device=device, **dp, **cfg)
+            self._trainer.load_state_dict(self.nn.state_dict())
+            self._trainer_dirty = False
+        return self._trainer
+
+    def training_step(self, batch, batch_idx: int = 0):
+        """model.py:153-158 plus the backward pass, the all-reduce of the gradients over the process group and the optimiser step.
+        Returns the batch's summed CTC loss (a 1-element device tensor).  Out-of-memory errors skip the batch like `_step`."""
+        if not self.training:
+            raise RuntimeError('call .train() before training_step')
+        try:
+            tr = self.trainer_for(batch['image'].device if batch['image'].is_cuda else torch.device('cuda', torch.cuda.current_device()))
+            loss = tr.step(batch)
+            self._trainer_dirty = True
+            return loss
+        except RuntimeError as e:
+            if 'out of memory' in str(e).lower():
+                torch.cuda.empty_cache()
+                return None
+            raise
+
+    def sync_from_trainer(self):
+        """Copy parameters and BatchNorm running statistics of the trainer's flat buffer into this module (state-dict keys)."""
+        sd = self._trainer.state_dict()
+        own = self.nn.state_dict()
+        with torch.no_grad():
+            for k, v in sd.items():
+                own[k].copy_(v.to(own[k].device))
+        self._trainer_dirty = False
+        self.invalidate_engine()
 
     def forward(self, x: torch.Tensor, seq_lens: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """x (N, W, H) as `_step` passes it (model.py:132-135) -> (logits (N,T,C), encoder_lens)."""

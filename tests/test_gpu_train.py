@@ -260,3 +260,36 @@ def test_train_rejects_bad_arguments(cuda_device):
     with pytest.raises(ValueError):
         tr.forward_backward(synthetic_batch(2, hp['height'], 128, 16, seed=1))
     tr.close()
+
+
+def test_recognition_model_training_step_interface(cuda_device):
+    """The drop-in interface: RecognitionModel.train() -> training_step(batch, idx) (model.py:153-158) -> eval() -> forward sees
+    the trained weights (parameters and BatchNorm statistics copied back into the module's state dict)."""
+    from conformer_ocr_b200 import RecognitionModel
+    hp = dict(O.DEFAULT_HPARAMS, num_encoder_layers=2)
+    C = 40
+    kw = dict(input_dropout_p=0.1, feed_forward_dropout_p=0.1, attention_dropout_p=0.1, conv_dropout_p=0.1)
+    net = RecognitionModel(num_classes=C, precision='fp32', **hp, **kw)
+    w = O.make_weights(hp, C, seed=61)
+    net.nn.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=False)
+    batch = synthetic_batch(4, hp['height'], 512, C, seed=62)
+    batch['target_lens'] = torch.clamp(batch['target_lens'], max=40)
+    batch['target'] = batch['target'][:int(batch['target_lens'].sum())]
+    x = batch['image'].to(cuda_device).squeeze(1).transpose(1, 2)
+    with pytest.raises(RuntimeError):
+        net.training_step(batch, 0)                                   # not in train mode
+    before, _ = net(x, batch['seq_lens'])
+    net.configure_training(lr=1e-3, weight_decay=1e-3, precision='bf16', seed=4)
+    net.train()
+    losses = [net.training_step(batch, i).item() for i in range(6)]
+    assert losses[-1] < 0.9 * losses[0], losses
+    net.eval()
+    after, _ = net(x, batch['seq_lens'])
+    assert (after - before).abs().max().item() > 1e-3                 # the inference engine was rebuilt from the trained weights
+    sd = net.nn.state_dict()
+    tsd = net._trainer.state_dict()
+    for k, v in tsd.items():
+        assert torch.equal(sd[k].cpu(), v.cpu()), k
+    # BatchNorm running statistics moved (train mode) and are what eval mode now uses
+    k = 'encoder.layers.0.sequential.2.module.sequential.5.running_mean'
+    assert (sd[k].cpu() - torch.from_numpy(w[k])).abs().max().item() > 1e-4
