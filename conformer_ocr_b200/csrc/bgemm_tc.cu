@@ -139,59 +139,95 @@ k_bgemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         const int m = m0 + q * 32 + lane;
         mbar_wait(&tfull, 0);
         tc_fence_after();
-        const long long obase = (long long)z1 * p.out_z1 + (long long)z2 * p.out_z2 + (long long)ks_idx * p.out_ks + (long long)m * p.ldc;
+        const long long zbase = (long long)z1 * p.out_z1 + (long long)z2 * p.out_z2 + (long long)ks_idx * p.out_ks;
+        const long long obase = zbase + (long long)m * p.ldc;
         const bool add_bias = p.bias && ks_idx == 0;
-        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-            uint32_t r[16];
-            tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            tmem_ld_wait_dep(r);
-            if (m >= p.M) continue;
-            float v[16];
+        // fp32 stores go through a per-warp staging tile so that a store instruction covers whole 128-byte rows (4 rows x 128 B)
+        // instead of 32 rows x 16 B: the L2 handles a quarter of the write transactions (97 MB score tiles: 87 -> see profiles/)
+        const bool staged = p.out_mode == 0 && (p.ldc & 3) == 0 && (((p.out_z1 | p.out_z2 | p.out_ks) & 3) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && ((p.block_n & 31) == 0 || p.block_n >= 32);
+        float *stg = reinterpret_cast<float *>(smem + (size_t)p.stages * stage_bytes) + (warp - 2) * 1024;      // [32 rows][32 floats], 16-byte chunks XOR-swizzled by row
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+            const int ncol = min(32, p.block_n - c0);          // 32 or 16 (block_n is a multiple of 16)
+            uint32_t r[32];
+            tmem_ld_32x32b_x16_lo(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            if (ncol > 16) {
+                uint32_t r2[16];
+                tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + 16), r2);
+                tmem_ld_wait_dep(r2);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
+                for (int e = 0; e < 16; ++e) r[16 + e] = r2[e];
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) r[16 + e] = 0u;
+            }
+            tmem_ld_wait_dep(r);
+            float v[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
                 const int n = n0 + c0 + e;
                 float t = __uint_as_float(r[e]) * p.alpha;
                 if (add_bias && n < p.N) t += p.bias[n];
                 if (p.relu) t = fmaxf(t, 0.0f);
                 v[e] = t;
             }
-            const int nvalid = min(16, p.N - (n0 + c0));
-            if (nvalid <= 0) continue;
+            const int nvalid = min(ncol, p.N - (n0 + c0));
+            if (staged) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<float4 *>(stg + lane * 32 + ((c ^ (lane & 7)) << 2)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                __syncwarp();
+                const int ch = lane & 7;                        // 16-byte chunk of the row this lane stores
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + (lane >> 3);
+                    const int mm = m0 + q * 32 + rr;
+                    const float4 w4 = *reinterpret_cast<const float4 *>(stg + rr * 32 + ((ch ^ (rr & 7)) << 2));
+                    if (mm < p.M && nvalid > 0) {
+                        float *o = (float *)p.out + zbase + (long long)mm * p.ldc + n0 + c0 + ch * 4;
+                        const int left = nvalid - ch * 4;
+                        if (left >= 4) *reinterpret_cast<float4 *>(o) = w4;
+                        else {
+                            if (left > 0) o[0] = w4.x;
+                            if (left > 1) o[1] = w4.y;
+                            if (left > 2) o[2] = w4.z;
+                        }
+                    }
+                }
+                __syncwarp();
+                continue;
+            }
+            if (m >= p.M || nvalid <= 0) continue;
             if (p.out_mode == 0) {
                 float *o = (float *)p.out + obase + n0 + c0;
-                if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
-                    for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4 *>(o + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e)
-                        if (e < nvalid) o[e] = v[e];
-                }
+                for (int e = 0; e < 32; ++e)
+                    if (e < nvalid) o[e] = v[e];
             } else if (p.out_mode == 1) {
                 __nv_bfloat16 *o = (__nv_bfloat16 *)p.out + obase + n0 + c0;
-                if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-                    uint32_t w[8];
+                if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                    uint32_t w[16];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
+                    for (int e = 0; e < 16; ++e) {
                         const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
                         w[e] = *reinterpret_cast<const uint32_t *>(&h2);
                     }
-                    *reinterpret_cast<uint4 *>(o) = make_uint4(w[0], w[1], w[2], w[3]);
-                    *reinterpret_cast<uint4 *>(o + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4 *>(o + 2 * e) = make_uint4(w[e], w[e + 1], w[e + 2], w[e + 3]);
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e)
+                    for (int e = 0; e < 32; ++e)
                         if (e < nvalid) o[e] = __float2bfloat16_rn(v[e]);
                 }
             } else if (p.out_mode == 2) {
                 float *o = (float *)p.out + obase + n0 + c0;
 #pragma unroll
-                for (int e = 0; e < 16; ++e)
+                for (int e = 0; e < 32; ++e)
                     if (e < nvalid) atomicAdd(o + e, v[e]);
             } else {
                 float *o = (float *)p.out + obase + n0 + c0;
 #pragma unroll
-                for (int e = 0; e < 16; ++e)
+                for (int e = 0; e < 32; ++e)
                     if (e < nvalid) o[e] += v[e];
             }
         }
@@ -271,12 +307,12 @@ int launch_bgemm(cocr_handle *h, const BgProblem &g, cudaStream_t st, const char
     const uint32_t b_bytes = g.b.mn ? (uint32_t)p.nbox_b * 8192u : (uint32_t)bn * 128u;
     const uint32_t stage_bytes = (BG_A_BYTES + b_bytes + 1023u) & ~1023u;
     p.stages = p.kchunks < BG_STAGES ? (p.kchunks < 1 ? 1 : p.kchunks) : BG_STAGES;
-    if (p.stages == 3 && 3 * stage_bytes > 112 * 1024 && 2 * stage_bytes <= 112 * 1024) p.stages = 2;   // two CTAs per SM beat a third stage
-    const size_t smem = (size_t)p.stages * stage_bytes;
+    if (p.stages == 3 && 3 * stage_bytes > 96 * 1024 && 2 * stage_bytes <= 96 * 1024) p.stages = 2;   // two CTAs per SM beat a third stage
+    const size_t smem = (size_t)p.stages * stage_bytes + 4 * 4096;      // + one 32 x 32 fp32 staging tile per epilogue warp
     static PerDevice<size_t> attr;
     if (smem > attr.get()) {
-        COCR_CUDA(h, cudaFuncSetAttribute(k_bgemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BG_STAGES * (BG_A_BYTES + 32768))));
-        attr.get() = BG_STAGES * (BG_A_BYTES + 32768);
+        COCR_CUDA(h, cudaFuncSetAttribute(k_bgemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BG_STAGES * (BG_A_BYTES + 32768) + 4 * 4096)));
+        attr.get() = BG_STAGES * (BG_A_BYTES + 32768) + 4 * 4096;
     }
     const long long nz = (long long)g.nz1 * g.nz2 * p.ksplit;
     if (nz > 65535) return set_error(h, COCR_ERR_UNSUPPORTED, "batched GEMM: %lld batch slices exceed the grid", nz);

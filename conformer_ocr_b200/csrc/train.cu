@@ -620,7 +620,7 @@ int conv_forward_mod(Mod &m, const float *x_in, float *x_out, float *params_rw) 
     TK_LAUNCHED(m.c);
     COCR_TRY(dwconv(m.c, g, m.P + o.w_dw, cd, B, T, d, dm.K, 0));
     COCR_CUDA(m.c.h, cudaMemsetAsync(sums, 0, (size_t)2 * d * 8, m.c.st));
-    const int rpb = 128;
+    const int rpb = 32;
     k_bn_sums<<<dim3((M + rpb - 1) / rpb, (d + 255) / 256), 256, 0, m.c.st>>>(cd, M, d, rpb, sums);
     TK_LAUNCHED(m.c);
     k_bn_finalize<<<(d + 255) / 256, 256, 0, m.c.st>>>(sums, M, d, m.cfg->bn_momentum, bst, params_rw ? params_rw + o.bn_rm : nullptr,
@@ -650,7 +650,7 @@ int conv_backward_mod(Mod &m, const float *x_in, float *dx) {
     COCR_TRY(gemm_nn(m.c, dy, d, m.P + o.w_pw2, d, dz, d, M, d, d));
     // BatchNorm backward (batch statistics): dz -> dy_bn -> dc, in place
     COCR_CUDA(m.c.h, cudaMemsetAsync(sums, 0, (size_t)2 * d * 8, m.c.st));
-    const int rpb = 128;
+    const int rpb = 32;
     k_bn_bwd_reduce<<<dim3((M + rpb - 1) / rpb, (d + 255) / 256), 256, 0, m.c.st>>>(cd, bst, m.P + o.bn_g, m.P + o.bn_b, dz, M, d, rpb, sums);
     TK_LAUNCHED(m.c);
     k_bn_bwd_apply<<<ew_grid((int64_t)M * d), 256, 0, m.c.st>>>(cd, bst, m.P + o.bn_g, sums, dz, M, d, m.G + o.bn_g, m.G + o.bn_b);

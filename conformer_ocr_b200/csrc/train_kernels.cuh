@@ -49,6 +49,18 @@ __device__ __forceinline__ float drop_scale(const Drop &dr, uint64_t e) {
     return w >= dr.thresh ? dr.inv_keep : 0.0f;
 }
 
+// the factors of the 4 consecutive elements e0 .. e0+3 (e0 % 4 == 0): one Philox call
+__device__ __forceinline__ float4 drop_scale4(const Drop &dr, uint64_t e0) {
+    if (dr.thresh == 0) return make_float4(1.f, 1.f, 1.f, 1.f);
+    const uint4 r = philox4(__ldg(dr.seedp), dr.site, e0 >> 2);
+    return make_float4(r.x >= dr.thresh ? dr.inv_keep : 0.f, r.y >= dr.thresh ? dr.inv_keep : 0.f, r.z >= dr.thresh ? dr.inv_keep : 0.f,
+                       r.w >= dr.thresh ? dr.inv_keep : 0.f);
+}
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16 *p, float4 v) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<uint2 *>(p) = make_uint2(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&b));
+}
+
 __global__ void k_dropout_mask(Drop dr, int64_t n, float *out) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) out[e] = drop_scale(dr, (uint64_t)e);
 }
@@ -342,6 +354,80 @@ __global__ void k_resid_drop(const float *x, const float *__restrict__ y, float 
         if (outb) outb[e] = __float2bfloat16_rn(r);
     }
 }
+// ---- 4-wide variants used by the tensor-core path (cols % 4 == 0, 16-byte aligned rows) -------------------------------------------
+// out = (x ? x : 0) + factor * dropout(y) over a (rows, cols) matrix; optional bf16 copy; optional colsum[c] += sum_rows out[., c]
+// (the bias gradient of the layer that produced y when this runs in the backward pass).  A block takes `rpb` rows.
+__global__ void __launch_bounds__(256)
+k_resid_drop_v4(const float *x, const float *__restrict__ y, float *out, float factor, int64_t rows, int cols, Drop dr, __nv_bfloat16 *__restrict__ outb,
+                float *__restrict__ colsum, int rpb) {
+    extern __shared__ float cs[];
+    if (colsum) {
+        for (int c = threadIdx.x; c < cols; c += 256) cs[c] = 0.f;
+        __syncthreads();
+    }
+    const int ncg = cols >> 2;
+    const int64_t r0 = (int64_t)blockIdx.x * rpb;
+    const int nr = (int)min((int64_t)rpb, rows - r0);
+    for (int idx = threadIdx.x; idx < nr * ncg; idx += 256) {
+        const int r = idx / ncg, c = (idx % ncg) << 2;
+        const int64_t e = (r0 + r) * cols + c;
+        const float4 yv = *reinterpret_cast<const float4 *>(y + e);
+        const float4 m = drop_scale4(dr, (uint64_t)e);
+        float4 o = make_float4(factor * yv.x * m.x, factor * yv.y * m.y, factor * yv.z * m.z, factor * yv.w * m.w);
+        if (x) {
+            const float4 xv = *reinterpret_cast<const float4 *>(x + e);
+            o.x += xv.x; o.y += xv.y; o.z += xv.z; o.w += xv.w;
+        }
+        *reinterpret_cast<float4 *>(out + e) = o;
+        if (outb) store_bf16x4(outb + e, o);
+        if (colsum) {
+            atomicAdd(&cs[c], o.x); atomicAdd(&cs[c + 1], o.y); atomicAdd(&cs[c + 2], o.z); atomicAdd(&cs[c + 3], o.w);
+        }
+    }
+    if (colsum) {
+        __syncthreads();
+        for (int c = threadIdx.x; c < cols; c += 256) atomicAdd(colsum + c, cs[c]);
+    }
+}
+// outb = bf16(dropout(silu(h)))
+__global__ void k_silu_drop_v4(const float *__restrict__ h, int64_t n, Drop dr, __nv_bfloat16 *__restrict__ outb) {
+    for (int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; e < n; e += (int64_t)gridDim.x * blockDim.x * 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(h + e);
+        const float4 m = drop_scale4(dr, (uint64_t)e);
+        store_bf16x4(outb + e, make_float4(v.x * sigmoid_f(v.x) * m.x, v.y * sigmoid_f(v.y) * m.y, v.z * sigmoid_f(v.z) * m.z, v.w * sigmoid_f(v.w) * m.w));
+    }
+}
+// dh = dact * mask * silu'(h) (in place, + bf16 copy) and colsum[c] += sum_rows dh[., c]
+__global__ void __launch_bounds__(256)
+k_silu_drop_bwd_v4(const float *__restrict__ h, float *__restrict__ dact, int64_t rows, int cols, Drop dr, __nv_bfloat16 *__restrict__ outb,
+                   float *__restrict__ colsum, int rpb) {
+    extern __shared__ float cs[];
+    for (int c = threadIdx.x; c < cols; c += 256) cs[c] = 0.f;
+    __syncthreads();
+    const int ncg = cols >> 2;
+    const int64_t r0 = (int64_t)blockIdx.x * rpb;
+    const int nr = (int)min((int64_t)rpb, rows - r0);
+    for (int idx = threadIdx.x; idx < nr * ncg; idx += 256) {
+        const int r = idx / ncg, c = (idx % ncg) << 2;
+        const int64_t e = (r0 + r) * cols + c;
+        const float4 hv = *reinterpret_cast<const float4 *>(h + e), dv = *reinterpret_cast<const float4 *>(dact + e);
+        const float4 m = drop_scale4(dr, (uint64_t)e);
+        const float hs[4] = {hv.x, hv.y, hv.z, hv.w}, ds[4] = {dv.x * m.x, dv.y * m.y, dv.z * m.z, dv.w * m.w};
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float sg = sigmoid_f(hs[i]);
+            o[i] = ds[i] * (sg * (1.0f + hs[i] * (1.0f - sg)));
+            atomicAdd(&cs[c + i], o[i]);
+        }
+        const float4 ov = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4 *>(dact + e) = ov;
+        if (outb) store_bf16x4(outb + e, ov);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < cols; c += 256) atomicAdd(colsum + c, cs[c]);
+}
+
 // GLU over the feature axis: u (M, 2d) -> g (M, d) = u[:, :d] * sigmoid(u[:, d:])   (convolution.py:139)
 __global__ void k_glu_fwd(const float *__restrict__ u, float *__restrict__ g, int64_t M, int d) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < M * d; e += (int64_t)gridDim.x * blockDim.x) {

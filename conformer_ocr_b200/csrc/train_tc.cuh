@@ -84,6 +84,19 @@ int tc_wgrad(Ctx &c, const bf16 *dyb, int ldy, const bf16 *xb, int ldx, float *d
     TK_LAUNCHED(c);
     return COCR_OK;
 }
+// out = (x ? x : 0) + factor * dropout(y) [+ bf16 copy] [+ column sums]: the 4-wide kernel when the shape allows, else the scalar ones
+int tc_resid_drop(Ctx &c, const float *x, const float *y, float *out, float factor, int64_t rows, int cols, const Drop &dr, bf16 *outb, float *colsum_out) {
+    if (cols % 4 == 0) {
+        const int rpb = 16;
+        k_resid_drop_v4<<<(unsigned)((rows + rpb - 1) / rpb), 256, colsum_out ? (size_t)cols * 4 : 0, c.st>>>(x, y, out, factor, rows, cols, dr, outb, colsum_out, rpb);
+        TK_LAUNCHED(c);
+        return COCR_OK;
+    }
+    k_resid_drop<<<ew_grid(rows * cols), 256, 0, c.st>>>(x, y, out, factor, rows * cols, dr, outb);
+    TK_LAUNCHED(c);
+    if (colsum_out) COCR_TRY(colsum(c, out, cols, (int)rows, cols, colsum_out));
+    return COCR_OK;
+}
 int tc_cast(Ctx &c, const float *src, int64_t lds, bf16 *dst, int64_t ldd, int64_t rows, int cols) {
     k_cast_bf16<<<ew_grid(rows * cols), 256, 0, c.st>>>(src, lds, dst, ldd, rows, cols);
     TK_LAUNCHED(c);
@@ -102,12 +115,11 @@ int ffn_forward_tc(Mod &m, int half, const float *x_in, float *x_out) {
     k_ln_fwd<<<(M + 7) / 8, 256, 0, m.c.st>>>(x_in, m.P + o.ffn_ln_g[half], m.P + o.ffn_ln_b[half], nullptr, m.stats(half ? 3 : 0), M, d, xnb);
     TK_LAUNCHED(m.c);
     COCR_TRY(tc_linear(m.c, xnb, d, t.pb + o.ffn_w1[half], m.P + o.ffn_b1[half], h1, ff, M, ff, d, "train_tc_ffn_up"));
-    k_silu_drop<<<ew_grid((int64_t)M * ff), 256, 0, m.c.st>>>(h1, nullptr, (int64_t)M * ff, m.drop(m.cfg->feed_forward_dropout_p, half ? 6 : 0), actb);
+    if (ff % 4 == 0) k_silu_drop_v4<<<ew_grid((int64_t)M * ff / 4), 256, 0, m.c.st>>>(h1, (int64_t)M * ff, m.drop(m.cfg->feed_forward_dropout_p, half ? 6 : 0), actb);
+    else k_silu_drop<<<ew_grid((int64_t)M * ff), 256, 0, m.c.st>>>(h1, nullptr, (int64_t)M * ff, m.drop(m.cfg->feed_forward_dropout_p, half ? 6 : 0), actb);
     TK_LAUNCHED(m.c);
     COCR_TRY(tc_linear(m.c, actb, ff, t.pb + o.ffn_w2[half], m.P + o.ffn_b2[half], y, d, M, d, ff, "train_tc_ffn_down"));
-    k_resid_drop<<<ew_grid((int64_t)M * d), 256, 0, m.c.st>>>(x_in, y, x_out, dm.ffn_factor, (int64_t)M * d,
-                                                              m.drop(m.cfg->feed_forward_dropout_p, half ? 7 : 1));
-    TK_LAUNCHED(m.c);
+    COCR_TRY(tc_resid_drop(m.c, x_in, y, x_out, dm.ffn_factor, M, d, m.drop(m.cfg->feed_forward_dropout_p, half ? 7 : 1), nullptr, nullptr));
     return COCR_OK;
 }
 
@@ -120,17 +132,21 @@ int ffn_backward_tc(Mod &m, int half, const float *x_in, float *dx) {
     float *dy = m.f(m.p.t_d0), *dxn = m.f(m.p.t_d2), *dact = m.f(m.p.t_ff1);
     const float *h1 = m.f(m.p.h1) + ((size_t)m.l * 2 + half) * M * ff;
     const bf16 *xnb = sv.xnb[half ? 3 : 0], *actb = sv.actb[half];
-    k_resid_drop<<<ew_grid((int64_t)M * d), 256, 0, m.c.st>>>(nullptr, dx, dy, dm.ffn_factor, (int64_t)M * d,
-                                                              m.drop(m.cfg->feed_forward_dropout_p, half ? 7 : 1), t.dyb);
-    TK_LAUNCHED(m.c);
+    // dy = factor * mask * dx, its bf16 copy and the bias gradient of the second linear layer in one pass
+    COCR_TRY(tc_resid_drop(m.c, nullptr, dx, dy, dm.ffn_factor, M, d, m.drop(m.cfg->feed_forward_dropout_p, half ? 7 : 1), t.dyb, m.G + o.ffn_b2[half]));
     const Drop d0 = m.drop(m.cfg->feed_forward_dropout_p, half ? 6 : 0);
     COCR_TRY(tc_wgrad(m.c, t.dyb, d, actb, ff, m.G + o.ffn_w2[half], M, d, ff));
-    COCR_TRY(colsum(m.c, dy, d, M, d, m.G + o.ffn_b2[half]));
     COCR_TRY(tc_dgrad(m.c, t.dyb, d, t.pb + o.ffn_w2[half], dact, ff, M, d, ff));
-    k_silu_drop_bwd<<<ew_grid((int64_t)M * ff), 256, 0, m.c.st>>>(h1, dact, (int64_t)M * ff, d0, t.wideb);
-    TK_LAUNCHED(m.c);
+    if (ff % 4 == 0) {
+        const int rpb = 8;
+        k_silu_drop_bwd_v4<<<(M + rpb - 1) / rpb, 256, (size_t)ff * 4, m.c.st>>>(h1, dact, M, ff, d0, t.wideb, m.G + o.ffn_b1[half], rpb);
+        TK_LAUNCHED(m.c);
+    } else {
+        k_silu_drop_bwd<<<ew_grid((int64_t)M * ff), 256, 0, m.c.st>>>(h1, dact, (int64_t)M * ff, d0, t.wideb);
+        TK_LAUNCHED(m.c);
+        COCR_TRY(colsum(m.c, dact, ff, M, ff, m.G + o.ffn_b1[half]));
+    }
     COCR_TRY(tc_wgrad(m.c, t.wideb, ff, xnb, d, m.G + o.ffn_w1[half], M, ff, d));
-    COCR_TRY(colsum(m.c, dact, ff, M, ff, m.G + o.ffn_b1[half]));
     COCR_TRY(tc_dgrad(m.c, t.wideb, ff, t.pb + o.ffn_w1[half], dxn, d, M, ff, d));
     COCR_TRY(ln_bwd(m.c, dxn, x_in, m.stats(half ? 3 : 0), m.P + o.ffn_ln_g[half], dx, dx, m.G + o.ffn_ln_g[half], m.G + o.ffn_ln_b[half], M, d));
     return COCR_OK;
@@ -204,8 +220,7 @@ int att_forward_tc(Mod &m, const float *x_in, float *x_out) {
     }
     COCR_TRY(tc_cast(m.c, ctx, d, sv.ctxb, d, M, d));
     COCR_TRY(tc_linear(m.c, sv.ctxb, d, t.pb + o.w_out, m.P + o.b_out, y, d, M, d, d, "train_tc_att_out"));
-    k_resid_drop<<<ew_grid((int64_t)M * d), 256, 0, m.c.st>>>(x_in, y, x_out, 1.0f, (int64_t)M * d, m.drop(m.cfg->attention_dropout_p, 3));
-    TK_LAUNCHED(m.c);
+    COCR_TRY(tc_resid_drop(m.c, x_in, y, x_out, 1.0f, M, d, m.drop(m.cfg->attention_dropout_p, 3), nullptr, nullptr));
     return COCR_OK;
 }
 
@@ -225,10 +240,8 @@ int att_backward_tc(Mod &m, const float *x_in, float *dx) {
     const bool adrop = m.cfg->attention_dropout_p > 0.0f;
     const bf16 *Pd = adrop ? Pl + pblk : Pl;
     const float inv_sqrt = 1.0f / sqrtf((float)dm.dh);
-    k_resid_drop<<<ew_grid((int64_t)M * d), 256, 0, m.c.st>>>(nullptr, dx, dy, 1.0f, (int64_t)M * d, m.drop(m.cfg->attention_dropout_p, 3), t.dyb);
-    TK_LAUNCHED(m.c);
+    COCR_TRY(tc_resid_drop(m.c, nullptr, dx, dy, 1.0f, M, d, m.drop(m.cfg->attention_dropout_p, 3), t.dyb, m.G + o.b_out));
     COCR_TRY(tc_wgrad(m.c, t.dyb, d, sv.ctxb, d, m.G + o.w_out, M, d, d));
-    COCR_TRY(colsum(m.c, dy, d, M, d, m.G + o.b_out));
     COCR_TRY(tc_dgrad(m.c, t.dyb, d, t.pb + o.w_out, dctx, d, M, d, d));
     {
         ProfScope ps(m.c.h, "train_tc_att_prep", m.c.st, 0.0, (double)M * (8.0 * d + 2.0 * a.HP));
@@ -321,7 +334,7 @@ int conv_forward_tc(Mod &m, const float *x_in, float *x_out, float *params_rw) {
     TK_LAUNCHED(m.c);
     COCR_TRY(dwconv(m.c, g, m.P + o.w_dw, cd, B, T, d, dm.K, 0));
     COCR_CUDA(m.c.h, cudaMemsetAsync(sums, 0, (size_t)2 * d * 8, m.c.st));
-    const int rpb = 128;
+    const int rpb = 32;
     k_bn_sums<<<dim3((M + rpb - 1) / rpb, (d + 255) / 256), 256, 0, m.c.st>>>(cd, M, d, rpb, sums);
     TK_LAUNCHED(m.c);
     k_bn_finalize<<<(d + 255) / 256, 256, 0, m.c.st>>>(sums, M, d, m.cfg->bn_momentum, bst, params_rw ? params_rw + o.bn_rm : nullptr,
@@ -330,8 +343,7 @@ int conv_forward_tc(Mod &m, const float *x_in, float *x_out, float *params_rw) {
     k_bn_silu_fwd<<<ew_grid((int64_t)M * d), 256, 0, m.c.st>>>(cd, bst, m.P + o.bn_g, m.P + o.bn_b, nullptr, M, d, sv.zb);
     TK_LAUNCHED(m.c);
     COCR_TRY(tc_linear(m.c, sv.zb, d, t.pb + o.w_pw2, m.P + o.b_pw2, y, d, M, d, d, "train_tc_pw2"));
-    k_resid_drop<<<ew_grid((int64_t)M * d), 256, 0, m.c.st>>>(x_in, y, x_out, 1.0f, (int64_t)M * d, m.drop(m.cfg->conv_dropout_p, 4));
-    TK_LAUNCHED(m.c);
+    COCR_TRY(tc_resid_drop(m.c, x_in, y, x_out, 1.0f, M, d, m.drop(m.cfg->conv_dropout_p, 4), nullptr, nullptr));
     return COCR_OK;
 }
 
@@ -343,14 +355,12 @@ int conv_backward_tc(Mod &m, const float *x_in, float *dx) {
     float *dy = m.f(m.p.t_d0), *dz = m.f(m.p.t_d2), *du = m.f(m.p.t_ff0), *g = m.f(m.p.t_ff1), *dg = m.f(m.p.t_d1);
     const float *u = m.f(m.p.u) + (size_t)m.l * M * 2 * d, *cd = m.f(m.p.cdw) + (size_t)m.l * M * d, *bst = m.f(m.p.bnstat) + (size_t)m.l * 2 * d;
     double *sums = (double *)m.f(m.p.bnsums);
-    k_resid_drop<<<ew_grid((int64_t)M * d), 256, 0, m.c.st>>>(nullptr, dx, dy, 1.0f, (int64_t)M * d, m.drop(m.cfg->conv_dropout_p, 4), t.dyb);
-    TK_LAUNCHED(m.c);
+    COCR_TRY(tc_resid_drop(m.c, nullptr, dx, dy, 1.0f, M, d, m.drop(m.cfg->conv_dropout_p, 4), t.dyb, m.G + o.b_pw2));
     const TcSaved sv = tc_saved(t, m.p, dm, m.l);
     COCR_TRY(tc_wgrad(m.c, t.dyb, d, sv.zb, d, m.G + o.w_pw2, M, d, d));
-    COCR_TRY(colsum(m.c, dy, d, M, d, m.G + o.b_pw2));
     COCR_TRY(tc_dgrad(m.c, t.dyb, d, t.pb + o.w_pw2, dz, d, M, d, d));
     COCR_CUDA(m.c.h, cudaMemsetAsync(sums, 0, (size_t)2 * d * 8, m.c.st));
-    const int rpb = 128;
+    const int rpb = 32;
     k_bn_bwd_reduce<<<dim3((M + rpb - 1) / rpb, (d + 255) / 256), 256, 0, m.c.st>>>(cd, bst, m.P + o.bn_g, m.P + o.bn_b, dz, M, d, rpb, sums);
     TK_LAUNCHED(m.c);
     k_bn_bwd_apply<<<ew_grid((int64_t)M * d), 256, 0, m.c.st>>>(cd, bst, m.P + o.bn_g, sums, dz, M, d, m.G + o.bn_g, m.G + o.bn_b);
