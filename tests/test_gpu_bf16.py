@@ -55,6 +55,25 @@ def test_residual_layernorm_epilogue_selftest(M, N, K, flags, cuda_device):
     assert 0.0 <= err.value < 6e-3, f'max err {err.value}'
 
 
+@pytest.mark.parametrize('M,N,K,flags', [
+    (128, 64, 64, 0), (128, 64, 64, 1), (128, 64, 64, 2), (128, 64, 64, 3),                      # every operand-major combination
+    (384, 384, 36, 4), (384, 767, 36, 4), (384, 36, 384, 6), (384, 36, 384, 7), (767, 36, 384, 7),   # attention shapes, batched 3 x 2
+    (300, 144, 576, 0), (300, 576, 144, 2), (1000, 288, 144, 0),                                   # linears and data gradients
+    (576, 144, 1000, 11), (144, 576, 1000, 11), (432, 144, 5000, 11),                              # weight gradients: split contraction
+    (26, 26, 16, 4), (26, 16, 26, 6), (51, 16, 26, 7), (10, 10, 16, 4), (250, 200, 100, 7), (77, 16, 40, 1),   # ragged edges
+])
+def test_bgemm_selftest(M, N, K, flags, cuda_device):
+    """Batched tcgen05 GEMM of the training step (bgemm_tc.cu) against a scalar device reference on the same bf16 operands.
+    flags: 1 A stored [k][m], 2 B stored [k][n], 4 batched 3 x 2 with strided blocks, 8 split contraction with atomic output.
+    Both sides accumulate in fp32; the difference is the summation order (<= 1e-3 absolute at K = 5000 with |a|,|b| <= 1)."""
+    from conformer_ocr_b200 import _lib
+    lib = _lib.load()
+    err = ctypes.c_double()
+    rc = lib.cocr_selftest(0, 30, M, N, K + 100000 * flags, ctypes.byref(err))
+    assert rc == 0, lib.cocr_last_error(None).decode()
+    assert 0 <= err.value < 1e-3, err.value
+
+
 @pytest.mark.parametrize('M,NC,flags', [(128, 6, 4), (300, 6, 6), (1000, 6, 0), (777, 2, 2), (4096, 6, 4), (2500, 1, 6), (19000, 6, 6), (20481, 8, 4), (5000, 3, 2)])
 def test_fused_ffn_selftest(M, NC, flags, cuda_device):
     """ffn_tc.cuh against a host reference: x + 0.5 * (W2 silu(W1 xn + b1) + b2), LayerNorm(s), bf16 hidden operand."""

@@ -161,7 +161,7 @@ def test_train_step_bf16_default_spec_against_port(cuda_device):
     operands grows with depth (measured on B200, profiles/r02_train_bf16_noise.log: cosine 0.99998 / 0.9998 / 0.990 at 1 / 4 / 16
     layers), so the yardstick here is the reference's own mixed-precision mode: torch's bf16 autocast over the same operator
     sequence, masks and batch.  The tensor-core path has to be at least as close to the float64 gradient as autocast is, and
-    within cosine 0.985 / 0.35 per tensor in absolute terms."""
+    within cosine 0.985 overall / 0.8 per tensor (measured 0.92) in absolute terms."""
     hp = dict(O.DEFAULT_HPARAMS)
     C, B, W, prob = 256, 3, 1536, 0.1
     w = O.make_weights(hp, C, seed=31)
@@ -176,7 +176,17 @@ def test_train_step_bf16_default_spec_against_port(cuda_device):
 
     ref_loss, ref_g, _ = port_grads(batch, w, hp, cuda_device, mask_fn=mask_fn, dropout=prob)
     assert abs(loss.item() - ref_loss) <= 5e-3 * abs(ref_loss), (loss.item(), ref_loss)
-    worst = check_grads(tr, ref_g, tol=0.35, zero_floor=0.05)
+    # per tensor: direction (cosine) rather than the largest single entry, which at layer 0 of 16 carries the noise of the whole chain
+    gnorm = np.sqrt(sum(float((np.asarray(v, np.float64) ** 2).sum()) for v in ref_g.values()))
+    worst = 1.0
+    for k in tr.trainable_keys():
+        r = np.asarray(ref_g[k], np.float64).ravel()
+        if np.linalg.norm(r) < 1e-3 * gnorm:
+            continue                                              # tensors with (near-)zero gradient: covered by the global cosine
+        gk = tr.view(k, 'grads').cpu().double().numpy().ravel()
+        ck = float(gk @ r / (np.linalg.norm(gk) * np.linalg.norm(r)))
+        worst = min(worst, ck)
+        assert ck >= 0.8, f'{k}: gradient cosine {ck:.4f}'        # measured minimum 0.92 (a bias gradient of layer 8)
     cos = flat_cosine(tr, ref_g)
     # torch autocast (bf16 matmuls, fp32 master weights) on the same batch and masks
     wt = {k: torch.from_numpy(v.copy()).to(cuda_device).requires_grad_(not k.endswith(('running_mean', 'running_var'))) for k, v in w.items()}
@@ -190,7 +200,7 @@ def test_train_step_bf16_default_spec_against_port(cuda_device):
     a = np.concatenate([wt[k].grad.double().cpu().numpy().ravel() for k in keys])
     b = np.concatenate([np.asarray(ref_g[k], dtype=np.float64).ravel() for k in keys])
     cos_torch = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
-    print(f'default spec bf16, dropout {prob}: loss {loss.item():.3f} (port {ref_loss:.3f}), worst gradient rel err {worst:.3f}, '
+    print(f'default spec bf16, dropout {prob}: loss {loss.item():.3f} (port {ref_loss:.3f}), worst per-tensor gradient cosine {worst:.4f}, '
           f'cosine {cos:.6f} (torch bf16 autocast: {cos_torch:.6f})')
     assert cos >= 0.985 and cos >= cos_torch - 1e-3, (cos, cos_torch)
     tr.close()
