@@ -67,6 +67,7 @@ SIGNATURES = {
     'cocr_dropout_mask': (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_float, _I64, _P, _P]),
     'cocr_slot_records_dev': (C.c_int, [_P, _I32, C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(_I32), C.POINTER(_I32)]),
     'cocr_workspace_bytes': (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_size_t)]),
+    'cocr_kernel_plan': (C.c_int, [_P, C.c_char_p, C.c_size_t, C.POINTER(_I32)]),
     'cocr_launch_count': (_I64, [_P]),
     'cocr_set_profiling': (C.c_int, [_P, C.c_int]),
     'cocr_profile_report': (C.c_int, [_P, C.c_char_p, C.c_size_t]),

@@ -693,6 +693,18 @@ int cocr_workspace_bytes(cocr_handle *h, int32_t B, int32_t W, size_t *bytes) {
     return COCR_OK;
 }
 
+int cocr_kernel_plan(cocr_handle *h, char *buf, size_t cap, int32_t *fallbacks) {
+    if (!h) return COCR_ERR_BAD_ARG;
+    if (fallbacks) *fallbacks = 0;
+    if (h->hp.precision != COCR_BF16) {
+        const char *msg = "all components: CUDA-core fp32 kernels (precision fp32 is the parity path)\n";
+        if (buf && cap) { strncpy(buf, msg, cap - 1); buf[cap - 1] = 0; }
+        return COCR_OK;
+    }
+    if (!h->finalized) return set_error(h, COCR_ERR_STATE, "weights not finalised (call cocr_finalize_weights)");
+    return bf16_kernel_plan(h, buf, cap, fallbacks);
+}
+
 int cocr_set_profiling(cocr_handle *h, int enabled) {
     if (!h) return COCR_ERR_BAD_ARG;
     h->profiling = enabled != 0;

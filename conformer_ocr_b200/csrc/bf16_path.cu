@@ -786,6 +786,34 @@ static int launch_ffn_fused(cocr_handle *h, const bf16 *xn, int ldx, const bf16 
     return COCR_OK;
 }
 
+// Which kernels these hyper-parameters select on the bf16 path, one "component: choice" per line; `fallbacks` counts the
+// components that run on a slower general kernel because the fast one is built for another geometry.
+int bf16_kernel_plan(const cocr_handle *h, char *buf, size_t cap, int *fallbacks) {
+    const Dims &dm = h->dm;
+    int nf = 0;
+    std::string s;
+    auto line = [&](const char *comp, bool fast, const char *a, const char *b) {
+        s += comp; s += ": "; s += fast ? a : b; s += "\n";
+        if (!fast) ++nf;
+    };
+    line("front-end", frontend_tc_selected(h), "k_frontend_tc (conv1 + depthwise + 1x1 conv on tcgen05, one kernel)",
+         "k_frontend_convs2 / CUDA-core convs + tcgen05 1x1-conv GEMM (fast kernel needs height 96, 32 conv channels)");
+    line("residual GEMMs", resid_fused(h), "tcgen05 GEMM with the residual update and LayerNorm(s) in the epilogue",
+         "tcgen05 GEMM + separate residual/LayerNorm kernel (fused epilogue needs encoder_dim 144)");
+    line("feed-forward module", ffn_fused_ok(h), ffn_v2(dm.ff) ? "k_ffn_fused2 (one kernel, hidden activation in TMEM)" : "k_ffn_fused (one kernel, hidden activation in TMEM)",
+         "two tcgen05 GEMMs with the hidden activation in HBM (fused kernel needs encoder_dim 144 and ff = 64 n or 96 n)");
+    line("attention", use_tc_attn(h), "k_attn_tc (tcgen05, rotation form of the relative-position term)",
+         "CUDA-core attention with the projected positional table (tcgen05 kernel needs head dim <= 40 and encoder_dim = 16 + 64 n)");
+    line("depthwise conv module", dm.d == 144 && dm.K == 31, "k_dw_v2 (compile-time geometry)", "general depthwise kernel (fast kernel needs encoder_dim 144, kernel size 31)");
+    if (buf && cap) {
+        const size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+        memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    if (fallbacks) *fallbacks = nf;
+    return COCR_OK;
+}
+
 int bf16_init(cocr_handle *h) {
     const Dims &dm = h->dm;
     if (dm.d % 16 != 0 || dm.ff % 16 != 0 || dm.feat % 16 != 0 || dm.d > 32 * ROW_MAXPER)

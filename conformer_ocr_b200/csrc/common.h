@@ -257,6 +257,7 @@ int launch_frontend_fused(cocr_handle *h, const float *img, int64_t sb, int64_t 
 // ---- bf16 path (bf16_path.cu) ------------------------------------------------------------
 int bf16_init(cocr_handle *h);       // pack weights; called from cocr_finalize_weights when precision == bf16
 void bf16_destroy(cocr_handle *h);
+int bf16_kernel_plan(const cocr_handle *h, char *buf, size_t cap, int *fallbacks);
 int bf16_encode(cocr_handle *h, const float *img, int64_t sb, int64_t sw, int64_t sh, const int32_t *widths,
                 int B, int W, cudaStream_t st, float *enc_out, int32_t *out_lens);
 size_t bf16_workspace_bytes(const cocr_handle *h, int B, int W);

@@ -310,6 +310,15 @@ int att_backward(Ctx &c, const float *qkv, const float *pos, const float *ub, co
 #define DISPATCH_DH(dh, call36, call16, call64) ((dh) <= 16 ? (call16) : (dh) <= 36 ? (call36) : (call64))
 
 int dwconv(Ctx &c, const float *x, const float *w, float *y, int B, int T, int d, int K, int flip) {
+    if (K == 31 && d % 2 == 0) {       // register sliding window: 8 outputs per thread and channel
+        constexpr int TT = 64;
+        const size_t smem = 4 * ((size_t)(TT + 30) * d + (size_t)31 * d);
+        COCR_TRY(set_smem(c.h, k_dwconv1d_k31, smem));
+        ProfScope ps(c.h, flip ? "train_dwconv_dgrad" : "train_dwconv", c.st, 2.0 * K * B * (double)T * d, 8.0 * B * T * d);
+        k_dwconv1d_k31<<<dim3((T + TT - 1) / TT, B), 256, smem, c.st>>>(x, w, y, T, d, flip);
+        TK_LAUNCHED(c);
+        return COCR_OK;
+    }
     const size_t smem = 4 * (size_t)(DWT + 2 * K - 1) * d;
     if (smem > 200 * 1024) return set_error(c.h, COCR_ERR_UNSUPPORTED, "depthwise conv tile needs %zu B of shared memory", smem);
     COCR_TRY(set_smem(c.h, k_dwconv1d, smem));

@@ -480,6 +480,48 @@ k_dwconv1d(const float *__restrict__ x, const float *__restrict__ w, float *__re
         y[((int64_t)b * T + t) * d + c] = acc;
     }
 }
+// K = 31: tiles of 64 frames; a thread owns a channel and 8 consecutive frames and slides a register window over its 38 input rows
+// (one shared-memory read per input row and per tap instead of two per multiply-add)
+__global__ void __launch_bounds__(256)
+k_dwconv1d_k31(const float *__restrict__ x, const float *__restrict__ w, float *__restrict__ y, int T, int d, int flip) {
+    constexpr int K = 31, TT = 64, OUT = 8;
+    extern __shared__ float sm[];
+    float *tile = sm;                          // [TT + 30][d]
+    float *wt = sm + (size_t)(TT + K - 1) * d; // [31][d]
+    const int b = blockIdx.y, t0 = blockIdx.x * TT, rows = TT + K - 1;
+    for (int e = threadIdx.x; e < rows * d; e += 256) {
+        const int r = e / d, c = e % d, t = t0 - 15 + r;
+        tile[e] = (t >= 0 && t < T) ? x[((int64_t)b * T + t) * d + c] : 0.0f;
+    }
+    for (int e = threadIdx.x; e < K * d; e += 256) {
+        const int k = e / d, c = e % d;
+        wt[e] = w[c * K + (flip ? K - 1 - k : k)];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < (TT / OUT) * d; e += 256) {
+        const int g = e / d, c = e % d;                    // group of 8 frames, channel (consecutive threads: consecutive channels)
+        float acc[OUT], wr[K];
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) acc[o] = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) wr[k] = wt[k * d + c];       // the channel's taps in registers
+        const float *in = tile + (size_t)(g * OUT) * d + c;
+#pragma unroll
+        for (int r = 0; r < OUT + K - 1; ++r) {            // input row r of the window contributes to outputs o = r - k
+            const float v = in[(size_t)r * d];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) {
+                const int k = r - o;
+                if (k >= 0 && k < K) acc[o] = fmaf(wr[k], v, acc[o]);
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) {
+            const int t = t0 + g * OUT + o;
+            if (t < T) y[((int64_t)b * T + t) * d + c] = acc[o];
+        }
+    }
+}
 // dw[c,k] += sum_{b,t} dy[b,t,c] * x[b,t+k-pad,c]      (tiles of DWT frames; the caller picks DWT so that the tile fits shared memory)
 __global__ void __launch_bounds__(256)
 k_dwconv1d_wgrad(const float *__restrict__ x, const float *__restrict__ dy, float *__restrict__ dw, int T, int d, int K, int DWT) {
@@ -1005,6 +1047,49 @@ __global__ void k_att_softmax_tc(const float *__restrict__ Sc, const float *__re
     if (row >= rows) return;
     const int i = (int)(row % T);
     const float *sc = Sc + row * Tp, *ps = PS + row * Rp + (T - 1 - i);
+    if (T <= 512 && (Tp & 3) == 0) {   // the row lives in registers, 4 consecutive columns per lane and step: 16-byte loads of the
+                                       // content scores, 8-byte stores of the bf16 rows, one Philox call per 4 probabilities
+        float v[16];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int j = 4 * lane + 128 * k;
+            float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < Tp) s4 = *reinterpret_cast<const float4 *>(sc + j);
+            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                v[4 * k + i] = (j + i < T) ? (sv[i] + ps[j + i]) * inv_sqrt : -INFINITY;
+                mx = fmaxf(mx, v[4 * k + i]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            v[k] = (v[k] > -INFINITY) ? expf(v[k] - mx) : 0.f;
+            s += v[k];
+        }
+        s = warp_sum_f(s);
+        const float inv = 1.0f / s;
+        const bool quad_rng = (T & 3) == 0;              // element index row*T + j is then a multiple of 4 with j
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int j = 4 * lane + 128 * k;
+            if (j >= Tp) break;
+            const float4 pv = make_float4(v[4 * k] * inv, v[4 * k + 1] * inv, v[4 * k + 2] * inv, v[4 * k + 3] * inv);
+            store_bf16x4(P + row * Tp + j, pv);
+            if (Pd != P) {
+                float4 m;
+                if (quad_rng) m = drop_scale4(dr, (uint64_t)(row * T + j));
+                else m = make_float4(drop_scale(dr, (uint64_t)(row * T + j)), drop_scale(dr, (uint64_t)(row * T + j + 1)),
+                                     drop_scale(dr, (uint64_t)(row * T + j + 2)), drop_scale(dr, (uint64_t)(row * T + j + 3)));
+                store_bf16x4(Pd + row * Tp + j, make_float4(pv.x * m.x, pv.y * m.y, pv.z * m.z, pv.w * m.w));
+            }
+        }
+        return;
+    }
     if (T <= 512) {         // the row lives in registers: one read of the scores
         float v[16];
         float mx = -INFINITY;

@@ -67,7 +67,7 @@ int tc_wgrad(Ctx &c, const bf16 *dyb, int ldy, const bf16 *xb, int ldx, float *d
     g.b = {xb, 1, ldx, 0, 0};
     const int bn = K <= 256 ? K : 256;
     const int tiles = ((N + 127) / 128) * ((K + bn - 1) / bn);
-    int ks = (148 * 2) / (tiles < 1 ? 1 : tiles);
+    int ks = 148 / (tiles < 1 ? 1 : tiles);            // one wave of CTAs: fewer partial products to sum, longer contraction per CTA
     const int nkc = (M + 63) / 64;
     if (ks > nkc) ks = nkc;
     while (ks > 1 && (size_t)ks * N * K > c.part_floats) --ks;

@@ -90,6 +90,21 @@ class Engine:
             self._check(self._lib.cocr_set_weight(self._h, key.encode(), arr.ctypes.data_as(C.c_void_p), arr.ndim, shape))
         self._check(self._lib.cocr_finalize_weights(self._h))
         self._loaded = True
+        plan, nf = self.kernel_plan()
+        if nf and not Engine._warned_fallback:
+            import warnings
+            Engine._warned_fallback = True
+            warnings.warn('conformer_ocr_b200: these hyper-parameters are outside the geometry the fastest kernels are built for; '
+                          f'{nf} component(s) run on general kernels:\n' + plan, RuntimeWarning, stacklevel=2)
+
+    _warned_fallback = False
+
+    def kernel_plan(self) -> Tuple[str, int]:
+        """(description of the kernels selected for these hyper-parameters, number of components on a general fallback kernel)."""
+        buf = C.create_string_buffer(2048)
+        nf = C.c_int32()
+        self._check(self._lib.cocr_kernel_plan(self._h, buf, len(buf), C.byref(nf)))
+        return buf.value.decode(), nf.value
 
     # -- helpers ----------------------------------------------------------------------------
     def _stream(self):

@@ -197,6 +197,11 @@ int cocr_slot_records_dev(cocr_handle *h, int32_t slot, void **records_dev, size
 /* Bytes of device workspace the handle holds after a call with this (B, W). */
 int cocr_workspace_bytes(cocr_handle *h, int32_t B, int32_t W, size_t *bytes);
 
+/* Which kernels the handle's hyper-parameters select (after cocr_finalize_weights): one "component: kernel" line per component,
+ * NUL-terminated in buf; *fallbacks = number of components that run on a slower general kernel because the fast one is built
+ * for the default geometry (encoder_dim 144, head dim 36, height 96, ...).  The Python shim warns once when it is non-zero. */
+int cocr_kernel_plan(cocr_handle *h, char *buf, size_t cap, int32_t *fallbacks);
+
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 int64_t cocr_launch_count(const cocr_handle *h);
 

@@ -372,3 +372,31 @@ def test_bf16_soak_many_shapes_both_mask_modes(cuda_device):
         torch.cuda.synchronize(cuda_device)
         assert len(first) == len(shapes)
         eng.close()
+
+
+def test_kernel_plan_reports_fallbacks(cuda_device):
+    """The default spec runs every component on its fast kernel; other hyper-parameters are served by general kernels and say so
+    (cocr_kernel_plan + one RuntimeWarning from the shim) instead of dropping to them silently."""
+    import warnings
+    from conformer_ocr_b200.engine import Engine
+    from conformer_ocr_b200 import synthetic as S
+    hp = dict(O.DEFAULT_HPARAMS, num_encoder_layers=1)
+    kw = dict(height=hp['height'], encoder_dim=hp['encoder_dim'], num_layers=1, num_heads=hp['num_attention_heads'],
+              ff_expansion=4, conv_expansion=2, conv_kernel_size=hp['conv_kernel_size'], half_step_residual=True,
+              subsampling_conv_channels=hp['subsampling_conv_channels'], subsampling_factor=4, num_classes=16, device=cuda_device, precision='bf16')
+    eng = Engine(**kw)
+    eng.load_state_dict(O.make_weights(hp, 16, seed=1))
+    plan, nf = eng.kernel_plan()
+    assert nf == 0 and 'k_attn_tc' in plan and 'k_frontend_tc' in plan, plan
+    eng.close()
+    tiny = dict(O.DEFAULT_HPARAMS, num_encoder_layers=1, encoder_dim=32, num_attention_heads=2, height=16, subsampling_conv_channels=4, conv_kernel_size=7)
+    kw.update(height=16, encoder_dim=32, num_heads=2, conv_kernel_size=7, subsampling_conv_channels=4)
+    Engine._warned_fallback = False
+    eng = Engine(**kw)
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter('always')
+        eng.load_state_dict(O.make_weights(tiny, 16, seed=1))
+    plan, nf = eng.kernel_plan()
+    assert nf >= 3 and 'CUDA-core attention' in plan, plan
+    assert any(issubclass(r.category, RuntimeWarning) and 'general kernels' in str(r.message) for r in rec)
+    eng.close()
