@@ -49,6 +49,8 @@ struct TrainState {
     std::vector<StepGraph> graphs;
     cudaStream_t gstream = nullptr;
     cudaEvent_t g_in = nullptr, g_out = nullptr;
+    cudaStream_t side = nullptr;            // weight-gradient stream of the tensor-core path
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -161,6 +163,26 @@ struct Ctx {
     cudaStream_t st;
     float *part;           // split-K partial sums
     size_t part_floats;
+    // Weight gradients only feed the optimiser at the end of the step, so the tensor-core path runs them on a side stream next to
+    // the data-gradient chain (fork after their operands exist, join before an operand buffer is written again).
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool side_busy = false;
+    int fork() {           // side stream waits for everything enqueued on the main stream so far
+        if (!side) return COCR_OK;
+        COCR_CUDA(h, cudaEventRecord(ev_fork, st));
+        COCR_CUDA(h, cudaStreamWaitEvent(side, ev_fork, 0));
+        side_busy = true;
+        return COCR_OK;
+    }
+    int join() {           // main stream waits for the side stream
+        if (!side || !side_busy) return COCR_OK;
+        COCR_CUDA(h, cudaEventRecord(ev_join, side));
+        COCR_CUDA(h, cudaStreamWaitEvent(st, ev_join, 0));
+        side_busy = false;
+        return COCR_OK;
+    }
+    cudaStream_t wstream() const { return side ? side : st; }
 };
 
 #define TK_LAUNCHED(c) COCR_LAUNCHED((c).h)
@@ -695,6 +717,9 @@ void train_destroy(cocr_handle *h) {
     for (auto &g : h->train->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     if (h->train->gstream) cudaStreamDestroy(h->train->gstream);
+    if (h->train->side) cudaStreamDestroy(h->train->side);
+    if (h->train->ev_fork) cudaEventDestroy(h->train->ev_fork);
+    if (h->train->ev_join) cudaEventDestroy(h->train->ev_join);
     if (h->train->g_in) cudaEventDestroy(h->train->g_in);
     if (h->train->g_out) cudaEventDestroy(h->train->g_out);
     delete h->train;
@@ -845,6 +870,15 @@ static int train_step_body(cocr_handle *h, TrainState *s, const Plan &p, float *
     const int tc = p.tc;
     char *ws = s->ws;
     Ctx c{h, st, (float *)(ws + p.part), p.part_floats};
+    static const bool no_side = getenv("COCR_TRAIN_NO_SIDE_STREAM") != nullptr;
+    if (tc && !no_side && !h->profiling) {
+        if (!s->side) {
+            COCR_CUDA(h, cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
+            COCR_CUDA(h, cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+            COCR_CUDA(h, cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+        }
+        c.side = s->side; c.ev_fork = s->ev_fork; c.ev_join = s->ev_join;
+    }
     const int M = p.M, d = dm.d, L = dm.L, C = dm.C;
     const float *P = params;
     float *G = grads;
@@ -925,6 +959,7 @@ static int train_step_body(cocr_handle *h, TrainState *s, const Plan &p, float *
     };
     if (tc) {
         COCR_TRY(tc_cast(c, glog, C, tb.glogb, p.Cp, M, C));
+        COCR_TRY(c.fork());
         COCR_TRY(tc_wgrad(c, tb.glogb, p.Cp, tb.encb, d, G + s->dec_w, M, C, d));
         COCR_TRY(tc_dgrad(c, tb.glogb, p.Cp, tb.pb + s->dec_w, dx, d, M, C, d));
     } else {
@@ -948,7 +983,9 @@ static int train_step_body(cocr_handle *h, TrainState *s, const Plan &p, float *
         COCR_TRY(tc ? ffn_backward_tc(m, 0, xs(x0), dx) : ffn_backward(m, 0, xs(x0), dx));
         COCR_TRY(tap(x0));
     }
-    // front-end
+    // front-end (its weight gradients are consumed right away: main stream only)
+    COCR_TRY(c.join());
+    c.side = nullptr;
     {
         float *dy = F(p.t_d0), *gwp = F(p.gwperm), *da3 = F(p.t_ff0), *da2 = F(p.t_ff1);
         k_resid_drop<<<ew_grid((int64_t)M * d), 256, 0, st>>>(nullptr, dx, dy, 1.0f, (int64_t)M * d, make_drop(cfg, cfg->input_dropout_p, 0),

@@ -73,14 +73,14 @@ int tc_wgrad(Ctx &c, const bf16 *dyb, int ldy, const bf16 *xb, int ldx, float *d
     while (ks > 1 && (size_t)ks * N * K > c.part_floats) --ks;
     if (ks <= 1) {
         g.out = dW; g.ldc = K;
-        return launch_bgemm(c.h, g, c.st, "train_tc_wgrad");
+        return launch_bgemm(c.h, g, c.wstream(), "train_tc_wgrad");
     }
     // partial products of the k-slices, summed in slice order (no atomics: bit-reproducible)
     const int kchunks = (nkc + ks - 1) / ks;
     ks = (nkc + kchunks - 1) / kchunks;
     g.out = c.part; g.ldc = K; g.out_ks = (long long)N * K; g.ksplit = ks;
-    COCR_TRY(launch_bgemm(c.h, g, c.st, "train_tc_wgrad"));
-    k_reduce_z<<<(unsigned)(((size_t)N * K + 255) / 256), 256, 0, c.st>>>(c.part, ks, (int64_t)N * K, dW);
+    COCR_TRY(launch_bgemm(c.h, g, c.wstream(), "train_tc_wgrad"));
+    k_reduce_z<<<(unsigned)(((size_t)N * K + 255) / 256), 256, 0, c.wstream()>>>(c.part, ks, (int64_t)N * K, dW);
     TK_LAUNCHED(c);
     return COCR_OK;
 }
@@ -132,9 +132,11 @@ int ffn_backward_tc(Mod &m, int half, const float *x_in, float *dx) {
     float *dy = m.f(m.p.t_d0), *dxn = m.f(m.p.t_d2), *dact = m.f(m.p.t_ff1);
     const float *h1 = m.f(m.p.h1) + ((size_t)m.l * 2 + half) * M * ff;
     const bf16 *xnb = sv.xnb[half ? 3 : 0], *actb = sv.actb[half];
+    COCR_TRY(m.c.join());      // the previous module's weight gradients still read dyb / wideb
     // dy = factor * mask * dx, its bf16 copy and the bias gradient of the second linear layer in one pass
     COCR_TRY(tc_resid_drop(m.c, nullptr, dx, dy, dm.ffn_factor, M, d, m.drop(m.cfg->feed_forward_dropout_p, half ? 7 : 1), t.dyb, m.G + o.ffn_b2[half]));
     const Drop d0 = m.drop(m.cfg->feed_forward_dropout_p, half ? 6 : 0);
+    COCR_TRY(m.c.fork());
     COCR_TRY(tc_wgrad(m.c, t.dyb, d, actb, ff, m.G + o.ffn_w2[half], M, d, ff));
     COCR_TRY(tc_dgrad(m.c, t.dyb, d, t.pb + o.ffn_w2[half], dact, ff, M, d, ff));
     if (ff % 4 == 0) {
@@ -146,6 +148,7 @@ int ffn_backward_tc(Mod &m, int half, const float *x_in, float *dx) {
         TK_LAUNCHED(m.c);
         COCR_TRY(colsum(m.c, dact, ff, M, ff, m.G + o.ffn_b1[half]));
     }
+    COCR_TRY(m.c.fork());
     COCR_TRY(tc_wgrad(m.c, t.wideb, ff, xnb, d, m.G + o.ffn_w1[half], M, ff, d));
     COCR_TRY(tc_dgrad(m.c, t.wideb, ff, t.pb + o.ffn_w1[half], dxn, d, M, ff, d));
     COCR_TRY(ln_bwd(m.c, dxn, x_in, m.stats(half ? 3 : 0), m.P + o.ffn_ln_g[half], dx, dx, m.G + o.ffn_ln_g[half], m.G + o.ffn_ln_b[half], M, d));
@@ -240,7 +243,9 @@ int att_backward_tc(Mod &m, const float *x_in, float *dx) {
     const bool adrop = m.cfg->attention_dropout_p > 0.0f;
     const bf16 *Pd = adrop ? Pl + pblk : Pl;
     const float inv_sqrt = 1.0f / sqrtf((float)dm.dh);
+    COCR_TRY(m.c.join());
     COCR_TRY(tc_resid_drop(m.c, nullptr, dx, dy, 1.0f, M, d, m.drop(m.cfg->attention_dropout_p, 3), t.dyb, m.G + o.b_out));
+    COCR_TRY(m.c.fork());
     COCR_TRY(tc_wgrad(m.c, t.dyb, d, sv.ctxb, d, m.G + o.w_out, M, d, d));
     COCR_TRY(tc_dgrad(m.c, t.dyb, d, t.pb + o.w_out, dctx, d, M, d, d));
     {
@@ -309,8 +314,10 @@ int att_backward_tc(Mod &m, const float *x_in, float *dx) {
         COCR_TRY(launch_bgemm(m.c.h, g, m.c.st, "train_tc_att_dpos"));
     }
     COCR_TRY(tc_cast(m.c, dpos, d, t.dposb, d, R, d));
+    COCR_TRY(m.c.fork());
     COCR_TRY(tc_wgrad(m.c, t.dposb, d, t.peb, d, m.G + o.w_pos, R, d, d));
     COCR_TRY(tc_cast(m.c, dqkv, 3 * d, t.wideb, 3 * d, M, 3 * d));
+    COCR_TRY(m.c.fork());
     COCR_TRY(tc_wgrad(m.c, t.wideb, 3 * d, sv.xnb[1], d, m.G + o.w_qkv, M, 3 * d, d));
     COCR_TRY(colsum(m.c, dqkv, 3 * d, M, 3 * d, m.G + o.b_qkv));
     COCR_TRY(tc_dgrad(m.c, t.wideb, 3 * d, t.pb + o.w_qkv, dxn, d, M, 3 * d, d));
@@ -355,8 +362,10 @@ int conv_backward_tc(Mod &m, const float *x_in, float *dx) {
     float *dy = m.f(m.p.t_d0), *dz = m.f(m.p.t_d2), *du = m.f(m.p.t_ff0), *g = m.f(m.p.t_ff1), *dg = m.f(m.p.t_d1);
     const float *u = m.f(m.p.u) + (size_t)m.l * M * 2 * d, *cd = m.f(m.p.cdw) + (size_t)m.l * M * d, *bst = m.f(m.p.bnstat) + (size_t)m.l * 2 * d;
     double *sums = (double *)m.f(m.p.bnsums);
+    COCR_TRY(m.c.join());
     COCR_TRY(tc_resid_drop(m.c, nullptr, dx, dy, 1.0f, M, d, m.drop(m.cfg->conv_dropout_p, 4), t.dyb, m.G + o.b_pw2));
     const TcSaved sv = tc_saved(t, m.p, dm, m.l);
+    COCR_TRY(m.c.fork());
     COCR_TRY(tc_wgrad(m.c, t.dyb, d, sv.zb, d, m.G + o.w_pw2, M, d, d));
     COCR_TRY(tc_dgrad(m.c, t.dyb, d, t.pb + o.w_pw2, dz, d, M, d, d));
     COCR_CUDA(m.c.h, cudaMemsetAsync(sums, 0, (size_t)2 * d * 8, m.c.st));
@@ -372,6 +381,7 @@ int conv_backward_tc(Mod &m, const float *x_in, float *dx) {
     COCR_TRY(dwconv(m.c, dc, m.P + o.w_dw, dg, B, T, d, dm.K, 1));
     k_glu_bwd<<<ew_grid((int64_t)M * d), 256, 0, m.c.st>>>(u, dg, du, M, d, t.wideb);
     TK_LAUNCHED(m.c);
+    COCR_TRY(m.c.fork());
     COCR_TRY(tc_wgrad(m.c, t.wideb, 2 * d, sv.xnb[2], d, m.G + o.w_pw1, M, 2 * d, d));
     COCR_TRY(colsum(m.c, du, 2 * d, M, 2 * d, m.G + o.b_pw1));
     float *dxn = dz;
