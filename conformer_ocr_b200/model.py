@@ -139,11 +139,11 @@ class RecognitionModel(EngineOwner):
             raise
 
     def decoder_training_step(self, batch, group=None):
-        """The part of a data-parallel training step (BASELINE configs[3]) this package computes on the device: encoder
-        forward, decoder projection, fused log-softmax + CTC loss (sum), its gradient with respect to the decoder outputs,
-        the decoder's weight / bias gradients and the gradient flowing back into the encoder outputs; then ONE all-reduce
-        (NCCL) of [loss | grad_weight | grad_bias] across the ranks of `group`.  Returns a dict with the local and the
-        all-reduced values.  The backward pass through the encoder is not built."""
+        """Training step with a FROZEN encoder (eval-mode arithmetic): encoder forward, decoder projection, fused log-softmax +
+        CTC loss (sum), its gradient with respect to the decoder outputs, the decoder's weight / bias gradients and the gradient
+        flowing back into the encoder outputs; then ONE all-reduce (NCCL) of [loss | grad_weight | grad_bias] across the ranks of
+        `group`.  Returns a dict with the local and the all-reduced values.  The full training step (encoder backward included,
+        BASELINE configs[3]) is `training_step`."""
         from .sharding import allreduce_bucket
         input = batch['image'].squeeze(1).transpose(1, 2)
         seq_lens, label_lens = batch['seq_lens'], batch['target_lens']

@@ -182,8 +182,8 @@ int cocr_ctc_loss(cocr_handle *h, const float *logits_dev, const int32_t *target
  * `rows` encoder frames (enc_dev (rows, encoder_dim) as cocr_encode returns it), and its backward pass given
  * grad_logits_dev (rows, C) (e.g. from cocr_ctc_loss): grad_weight_dev (C, encoder_dim), grad_bias_dev (C) and, when not
  * NULL, grad_enc_dev (rows, encoder_dim) = what flows back into the encoder.  Sums run in a fixed order (bit-reproducible).
- * These are the tensors a data-parallel training step all-reduces across GPUs (model.py:139-145 + DDP); the backward pass
- * through the encoder itself is not built. */
+ * (The whole training step, encoder backward included, is cocr_train_step below; these two entry points remain for callers
+ * that keep the encoder frozen.) */
 int cocr_project(cocr_handle *h, const float *enc_dev, int64_t rows, void *stream, float *logits_dev);
 int cocr_decoder_backward(cocr_handle *h, const float *grad_logits_dev, const float *enc_dev, int64_t rows, void *stream,
                           float *grad_weight_dev, float *grad_bias_dev, float *grad_enc_dev);
