@@ -807,8 +807,8 @@ def run_train(args):
                             launches_per_step=n, avg_launch_ms=ms / max(n, 1), share_of_step=ms / max(tot, 1e-9), flops_per_step=fl,
                             peak_source=peaks['source'] + ' (sustained bf16 cuBLAS)',
                             how='all launches of the batched tcgen05 GEMM by CUDA-event time; exact 2*MAC FLOPs of each launch (extents are not padded). '
-                                'At 32 lines per GPU the contractions are small (M = 12 288 frames, K or N = 144): a launch lasts 15-45 us, most of it '
-                                'fixed cost, which is what this fraction shows')
+                                'At 32 lines per GPU the contractions are small (M = 12 288 frames, K or N = 144): a launch lasts 15-45 us and is bound by '
+                                'writing its fp32 result (a 12 288 x 576 output is 28 MB), not by the tensor pipe')
         else:
             top = max(families, key=lambda k: families[k]['ms_per_step'])
             f = families[top]
