@@ -304,3 +304,33 @@ def test_recognition_model_training_step_interface(cuda_device):
     # BatchNorm running statistics moved (train mode) and are what eval mode now uses
     k = 'encoder.layers.0.sequential.2.module.sequential.5.running_mean'
     assert (sd[k].cpu() - torch.from_numpy(w[k])).abs().max().item() > 1e-4
+
+
+def test_training_soak_over_changing_shapes(cuda_device):
+    """45 optimiser steps cycling through three batch shapes (each shape: plain launches, capture, then graph replays; the
+    staging buffers grow with the widest batch): losses stay finite and fall for every shape, parameters stay finite, and a
+    fresh trainer replaying the same sequence lands on the same loss curve (within 2 %: the atomics of the bias / LayerNorm /
+    depthwise sums reorder additions, and 45 Adam steps amplify that to 1e-2 in individual parameters - measured)."""
+    hp = dict(O.DEFAULT_HPARAMS, num_encoder_layers=2)
+    C = 48
+    shapes = [(4, 512), (3, 768), (5, 384)]
+    batches = []
+    for i, (B, W) in enumerate(shapes):
+        b = synthetic_batch(B, hp['height'], W, C, seed=70 + i)
+        b['target_lens'] = torch.clamp(b['target_lens'], max=W // 16)
+        b['target'] = b['target'][:int(b['target_lens'].sum())]
+        batches.append(b)
+    finals = []
+    for run in range(2):
+        tr = make_trainer(hp, C, cuda_device, dropout=0.0, lr=5e-4, weight_decay=1e-3, seed=11, precision='bf16')
+        tr.load_state_dict(O.make_weights(hp, C, seed=71))
+        losses = {i: [] for i in range(len(shapes))}
+        for step in range(45):
+            i = step % len(shapes)
+            losses[i].append(tr.step(batches[i]).item())
+        for i, ls in losses.items():
+            assert all(np.isfinite(ls)) and ls[-1] < 0.9 * ls[0], (i, ls)
+        assert torch.isfinite(tr.params).all()
+        finals.append(np.array([ls[-1] for ls in losses.values()]))
+        tr.close()
+    assert np.abs(finals[0] - finals[1]).max() <= 0.02 * finals[0].max(), finals
