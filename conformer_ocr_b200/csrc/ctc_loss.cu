@@ -81,12 +81,24 @@ __device__ __forceinline__ CtcLine ctc_line(const int32_t *targets, const int32_
     return l;
 }
 
+// Frames of a line staged per chunk in shared memory: the recursions are chains of T dependent steps, and a step that waits for
+// global memory (its emission gather, the row the previous step wrote) costs a microsecond; from shared memory it costs ~0.1.
+__host__ __device__ inline int ctc_chunk(int Smax, int rows_per_frame) {
+    int tc = (64 * 1024) / (Smax * 4 * rows_per_frame);
+    return tc < 1 ? 1 : (tc > 32 ? 32 : tc);
+}
+
 // alpha recursion.  alpha: (B, T, Smax) global scratch (kept for the backward pass); nll: (B) = -log p(l | x), +inf when the
 // target cannot be emitted in T_b frames.  One block per line, thread = state (strided).
+// Dynamic shared memory: em[TC][Smax] emissions of the chunk | a[2][Smax] | lab[Smax] | skip[Smax].
 __global__ void __launch_bounds__(256)
 k_ctc_alpha(const float *__restrict__ logits, const float *__restrict__ lse, const int32_t *__restrict__ targets,
             const int32_t *__restrict__ target_lens, const int32_t *__restrict__ input_lens, int T, int C, int max_target_len, int Smax,
             float *__restrict__ alpha, float *__restrict__ nll) {
+    extern __shared__ float sm[];
+    const int TC = ctc_chunk(Smax, 1);
+    float *em = sm, *a0 = sm + (size_t)TC * Smax, *a1 = a0 + Smax;
+    int *lab = reinterpret_cast<int *>(a1 + Smax), *skip = lab + Smax;
     const int b = blockIdx.x;
     const CtcLine ln = ctc_line(targets, target_lens, input_lens, b, T, max_target_len);
     const float *lg = logits + (int64_t)b * T * C;
@@ -97,27 +109,40 @@ k_ctc_alpha(const float *__restrict__ logits, const float *__restrict__ lse, con
         return;
     }
     for (int s = threadIdx.x; s < ln.S; s += blockDim.x) {
-        float a = -INFINITY;
-        if (s == 0) a = lg[0] - ls[0];
-        else if (s == 1) a = lg[ln.tgt[0]] - ls[0];
-        al[s] = a;
+        const int l = (s & 1) ? ln.tgt[s >> 1] : 0;
+        lab[s] = l;
+        skip[s] = (s >= 2 && (s & 1) && l != ln.tgt[(s >> 1) - 1]) ? 1 : 0;
     }
     __syncthreads();
-    for (int t = 1; t < ln.Tn; ++t) {
-        const float *prev = al + (int64_t)(t - 1) * Smax;
-        float *cur = al + (int64_t)t * Smax;
-        const float l_t = ls[t];
-        for (int s = threadIdx.x; s < ln.S; s += blockDim.x) {
-            const int lab = (s & 1) ? ln.tgt[s >> 1] : 0;
-            float a = prev[s];
-            if (s >= 1) a = log_add(a, prev[s - 1]);
-            if (s >= 2 && (s & 1) && lab != ln.tgt[(s >> 1) - 1]) a = log_add(a, prev[s - 2]);
-            cur[s] = a + (lg[(int64_t)t * C + lab] - l_t);
+    for (int t0 = 0; t0 < ln.Tn; t0 += TC) {
+        const int nt = min(TC, ln.Tn - t0);
+        for (int e = threadIdx.x; e < nt * ln.S; e += blockDim.x) {         // the chunk's emissions, gathered in parallel
+            const int tt = e / ln.S, s_ = e - tt * ln.S;
+            em[tt * Smax + s_] = lg[(int64_t)(t0 + tt) * C + lab[s_]] - ls[t0 + tt];
         }
         __syncthreads();
+        for (int tt = 0; tt < nt; ++tt) {
+            const int t = t0 + tt;
+            const float *prev = (t & 1) ? a0 : a1;
+            float *cur = (t & 1) ? a1 : a0;
+            for (int s = threadIdx.x; s < ln.S; s += blockDim.x) {
+                float a;
+                if (t == 0) {
+                    a = (s <= 1) ? em[s] : -INFINITY;
+                } else {
+                    a = prev[s];
+                    if (s >= 1) a = log_add(a, prev[s - 1]);
+                    if (skip[s]) a = log_add(a, prev[s - 2]);
+                    a += em[tt * Smax + s];
+                }
+                cur[s] = a;
+                al[(int64_t)t * Smax + s] = a;
+            }
+            __syncthreads();
+        }
     }
     if (threadIdx.x == 0) {
-        const float *last = al + (int64_t)(ln.Tn - 1) * Smax;
+        const float *last = ((ln.Tn - 1) & 1) ? a1 : a0;
         const float tail = ln.S == 1 ? last[0] : log_add(last[ln.S - 1], last[ln.S - 2]);
         nll[b] = -tail;
     }
@@ -151,16 +176,19 @@ k_ctc_grad_init(const float *__restrict__ logits, const float *__restrict__ lse,
     for (int c = lane; c < C; c += 32) g[c] = live ? expf(p[c] - l) : 0.0f;
 }
 
-// beta recursion + posterior subtraction.  Dynamic shared memory: beta[2][Smax] | post[Smax] | nxt[Smax] (int).
+// beta recursion + posterior subtraction.  Dynamic shared memory: em[TC][Smax] | alc[TC][Smax] (emissions and alpha rows of the chunk
+// of frames being walked, loaded in parallel; alc is overwritten with the per-class posterior sums of the frame, which are
+// subtracted from the gradient in parallel after the chunk) | beta[2][Smax] | post[Smax] | nxt[Smax] | first[Smax] | lab[Smax] | skip[Smax] (int).
 //   nxt[s] (odd s): next odd state with the same label, or -1; `first` states own their class and sum their chain in order.
 __global__ void __launch_bounds__(256)
 k_ctc_beta_grad(const float *__restrict__ logits, const float *__restrict__ lse, const int32_t *__restrict__ targets,
                 const int32_t *__restrict__ target_lens, const int32_t *__restrict__ input_lens, int T, int C, int max_target_len, int Smax,
                 const float *__restrict__ alpha, const float *__restrict__ nll, float *__restrict__ grad) {
     extern __shared__ float sm[];
-    float *beta0 = sm, *beta1 = sm + Smax, *post = sm + 2 * Smax;
-    int *nxt = reinterpret_cast<int *>(sm + 3 * Smax);
-    int *first = nxt + Smax;
+    const int TC = ctc_chunk(Smax, 2);
+    float *em = sm, *alc = em + (size_t)TC * Smax, *beta0 = alc + (size_t)TC * Smax, *beta1 = beta0 + Smax, *post = beta1 + Smax;
+    int *nxt = reinterpret_cast<int *>(post + Smax);
+    int *first = nxt + Smax, *lab = first + Smax, *skip = lab + Smax;
     const int b = blockIdx.x;
     const CtcLine ln = ctc_line(targets, target_lens, input_lens, b, T, max_target_len);
     const float nl = nll[b];
@@ -173,52 +201,69 @@ k_ctc_beta_grad(const float *__restrict__ logits, const float *__restrict__ lse,
     for (int s = threadIdx.x; s < ln.S; s += blockDim.x) {
         nxt[s] = -1;
         first[s] = 0;
+        const int l = (s & 1) ? ln.tgt[s >> 1] : 0;
+        lab[s] = l;
+        skip[s] = (s + 2 < ln.S && (s & 1) && l != ln.tgt[(s >> 1) + 1]) ? 1 : 0;
         if (s & 1) {
-            const int lab = ln.tgt[s >> 1];
             int f = 1;
             for (int u = 1; u < s; u += 2)
-                if (ln.tgt[u >> 1] == lab) { f = 0; break; }
+                if (ln.tgt[u >> 1] == l) { f = 0; break; }
             first[s] = f;
             for (int u = s + 2; u < ln.S; u += 2)
-                if (ln.tgt[u >> 1] == lab) { nxt[s] = u; break; }
+                if (ln.tgt[u >> 1] == l) { nxt[s] = u; break; }
         }
     }
     __syncthreads();
-    for (int t = ln.Tn - 1; t >= 0; --t) {
-        float *cur = ((ln.Tn - 1 - t) & 1) ? beta1 : beta0;
-        const float *nx = ((ln.Tn - 1 - t) & 1) ? beta0 : beta1;
-        const float l_t = ls[t];
-        for (int s = threadIdx.x; s < ln.S; s += blockDim.x) {
-            const int lab = (s & 1) ? ln.tgt[s >> 1] : 0;
-            const float lp = lg[(int64_t)t * C + lab] - l_t;
-            float bt;
-            if (t == ln.Tn - 1) {
-                bt = (s >= ln.S - 2) ? lp : -INFINITY;             // the last blank and the last label may end the path
-            } else {
-                bt = nx[s];
-                if (s + 1 < ln.S) bt = log_add(bt, nx[s + 1]);
-                if (s + 2 < ln.S && (s & 1) && lab != ln.tgt[(s >> 1) + 1]) bt = log_add(bt, nx[s + 2]);
-                bt += lp;
-            }
-            cur[s] = bt;
-            // posterior of state s at frame t: alpha_t(s) beta_t(s) / (y_t(l'_s) p(l | x))   (beta includes y_t here)
-            const float lpost = al[(int64_t)t * Smax + s] + bt - lp + nl;
-            post[s] = (lpost > -INFINITY) ? expf(lpost) : 0.0f;
+    for (int thi = ln.Tn; thi > 0; thi -= TC) {                    // chunks of frames [tlo, thi), walked backwards
+        const int tlo = max(0, thi - TC), nt = thi - tlo;
+        for (int e = threadIdx.x; e < nt * ln.S; e += blockDim.x) {
+            const int tt = e / ln.S, s_ = e - tt * ln.S;
+            em[tt * Smax + s_] = lg[(int64_t)(tlo + tt) * C + lab[s_]] - ls[tlo + tt];
+            alc[tt * Smax + s_] = al[(int64_t)(tlo + tt) * Smax + s_];
         }
         __syncthreads();
-        // non-blank classes: the first state of every label sums its chain
-        for (int s = 1 + 2 * (int)threadIdx.x; s < ln.S; s += 2 * blockDim.x) {
-            if (!first[s]) continue;
-            float acc = 0.f;
-            for (int u = s; u >= 0; u = nxt[u]) acc += post[u];
-            gr[(int64_t)t * C + ln.tgt[s >> 1]] -= acc;
+        for (int tt = nt - 1; tt >= 0; --tt) {
+            const int t = tlo + tt;
+            float *cur = ((ln.Tn - 1 - t) & 1) ? beta1 : beta0;
+            const float *nx = ((ln.Tn - 1 - t) & 1) ? beta0 : beta1;
+            for (int s = threadIdx.x; s < ln.S; s += blockDim.x) {
+                const float lp = em[tt * Smax + s];
+                float bt;
+                if (t == ln.Tn - 1) {
+                    bt = (s >= ln.S - 2) ? lp : -INFINITY;         // the last blank and the last label may end the path
+                } else {
+                    bt = nx[s];
+                    if (s + 1 < ln.S) bt = log_add(bt, nx[s + 1]);
+                    if (skip[s]) bt = log_add(bt, nx[s + 2]);
+                    bt += lp;
+                }
+                cur[s] = bt;
+                // posterior of state s at frame t: alpha_t(s) beta_t(s) / (y_t(l'_s) p(l | x))   (beta includes y_t here)
+                const float lpost = alc[tt * Smax + s] + bt - lp + nl;
+                post[s] = (lpost > -INFINITY) ? expf(lpost) : 0.0f;
+            }
+            __syncthreads();
+            // (the alpha row of this frame has been consumed above: its slots now take the frame's per-class sums, applied after the chunk
+            // so that the read-modify-write of the gradient is not part of the sequential chain)
+            // non-blank classes: the first state of every label sums its chain
+            for (int s = 1 + 2 * (int)threadIdx.x; s < ln.S; s += 2 * blockDim.x) {
+                if (!first[s]) continue;
+                float acc = 0.f;
+                for (int u = s; u >= 0; u = nxt[u]) acc += post[u];
+                alc[tt * Smax + s] = acc;
+            }
+            // blank: warp 0, strided partial sums in a fixed order + shuffle tree
+            if (threadIdx.x < 32) {
+                float acc = 0.f;
+                for (int s = 2 * (int)threadIdx.x; s < ln.S; s += 64) acc += post[s];
+                acc = warp_sum(acc);
+                if (threadIdx.x == 0) alc[tt * Smax] = acc;
+            }
+            __syncthreads();
         }
-        // blank: warp 0, strided partial sums in a fixed order + shuffle tree
-        if (threadIdx.x < 32) {
-            float acc = 0.f;
-            for (int s = 2 * (int)threadIdx.x; s < ln.S; s += 64) acc += post[s];
-            acc = warp_sum(acc);
-            if (threadIdx.x == 0) gr[(int64_t)t * C] -= acc;
+        for (int e = threadIdx.x; e < nt * ln.S; e += blockDim.x) {          // one (frame, class) per element: no two touch the same address
+            const int tt = e / ln.S, s_ = e - tt * ln.S;
+            if (s_ == 0 || first[s_]) gr[(int64_t)(tlo + tt) * C + lab[s_]] -= alc[tt * Smax + s_];
         }
         __syncthreads();
     }
@@ -361,7 +406,16 @@ int launch_ctc_loss(cocr_handle *h, const float *logits, const int32_t *targets,
         }
         {
             ProfScope ps(h, "ctc_alpha", st, 0.0, (double)rows * Smax * 4.0);
-            k_ctc_alpha<<<B, 256, 0, st>>>(logits, lse, targets, target_lens, input_lens, T, C, max_target_len, Smax, alpha, nll);
+            const size_t asmem = ((size_t)ctc_chunk(Smax, 1) * Smax + (size_t)4 * Smax) * 4;
+            if (asmem > 48 * 1024) {
+                static PerDevice<size_t> aattr;
+                if (asmem > aattr.get()) {
+                    if ((rc = check_cuda(h, cudaFuncSetAttribute(k_ctc_alpha, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem),
+                                         "k_ctc_alpha shared memory")) != COCR_OK) break;
+                    aattr.get() = asmem;
+                }
+            }
+            k_ctc_alpha<<<B, 256, asmem, st>>>(logits, lse, targets, target_lens, input_lens, T, C, max_target_len, Smax, alpha, nll);
             if ((rc = check_cuda(h, cudaGetLastError(), "k_ctc_alpha")) != COCR_OK) break;
             h->launches++;
         }
@@ -375,7 +429,7 @@ int launch_ctc_loss(cocr_handle *h, const float *logits, const int32_t *targets,
                 if ((rc = check_cuda(h, cudaGetLastError(), "k_ctc_grad_init")) != COCR_OK) break;
                 h->launches++;
             }
-            const size_t smem = (size_t)Smax * 5 * 4;
+            const size_t smem = ((size_t)2 * ctc_chunk(Smax, 2) * Smax + (size_t)7 * Smax) * 4;
             if (smem > 48 * 1024) {
                 static PerDevice<size_t> attr;
                 if (smem > attr.get()) {
