@@ -334,3 +334,27 @@ def test_training_soak_over_changing_shapes(cuda_device):
         finals.append(np.array([ls[-1] for ls in losses.values()]))
         tr.close()
     assert np.abs(finals[0] - finals[1]).max() <= 0.02 * finals[0].max(), finals
+
+
+def test_train_step_long_lines_bf16_against_fp32_path(cuda_device):
+    """Lines of 2304 px (T = 576 > 512: the softmax kernel's streaming path, several key tiles and contraction chunks per GEMM, a
+    ragged batch) and an odd class count: the tensor-core mode against the fp32 CUDA-core mode on the same batch, one layer."""
+    hp = dict(O.DEFAULT_HPARAMS, num_encoder_layers=1)
+    C, W = 51, 2304
+    w = O.make_weights(hp, C, seed=81)
+    batch = synthetic_batch(2, hp['height'], W, C, seed=82, widths=[2304, 1999])
+    grads = {}
+    for prec in ('fp32', 'bf16'):
+        tr = make_trainer(hp, C, cuda_device, precision=prec)
+        tr.load_state_dict(w)
+        loss = tr.forward_backward(batch).item()
+        grads[prec] = (loss, tr.grads[:tr.n_trainable].double().cpu().numpy(), {k: tr.view(k, 'grads').cpu().double().numpy() for k in tr.trainable_keys()})
+        tr.close()
+    (l32, g32, k32), (l16, g16, k16) = grads['fp32'], grads['bf16']
+    assert abs(l16 - l32) <= 5e-3 * abs(l32), (l16, l32)
+    cos = float(g16 @ g32 / (np.linalg.norm(g16) * np.linalg.norm(g32)))
+    assert cos >= 0.9994, cos
+    gmax = max(np.abs(v).max() for v in k32.values())
+    for k, ref in k32.items():
+        e = np.abs(k16[k] - ref).max() / max(np.abs(ref).max(), 0.05 * gmax)
+        assert e <= 0.15, f'{k}: {e:.3f}'
