@@ -1130,6 +1130,44 @@ __global__ void k_att_ds_tc(const __nv_bfloat16 *__restrict__ P, const float *__
         if (j + 1 < T) ps[seg0 + j + 1] = __high2bfloat16(v2);
     }
 }
+// The same for T % 4 == 0 with every global access at least 8 bytes wide: 4 columns per lane and step (one Philox call), the un-shifted
+// row assembled in shared memory (zeros, then the segment) and written out as 16-byte chunks.  Dynamic shared memory: 8 warps x Rp bf16.
+__global__ void __launch_bounds__(256)
+k_att_ds_tc_v4(const __nv_bfloat16 *__restrict__ P, const float *__restrict__ dPd, const float *__restrict__ delta, __nv_bfloat16 *__restrict__ dSb,
+               __nv_bfloat16 *__restrict__ dPSb, int64_t rows, int T, int Tp, int Rp, int nh, float inv_sqrt, Drop dr) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __nv_bfloat16 *srow = reinterpret_cast<__nv_bfloat16 *>(smraw) + (size_t)warp * Rp;
+    const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+    if (row >= rows) return;
+    const int i = (int)(row % T);
+    const int64_t bh = row / T;
+    const float dl = delta[((bh / nh) * T + i) * nh + (int)(bh % nh)];
+    const int seg0 = T - 1 - i;
+    for (int c = lane; c < Rp / 8; c += 32) *reinterpret_cast<uint4 *>(srow + 8 * c) = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    for (int j = 4 * lane; j < Tp; j += 128) {
+        float4 ds = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < T) {                                     // T % 4 == 0: the four columns are valid together
+            const uint2 pw = *reinterpret_cast<const uint2 *>(P + row * Tp + j);
+            const __nv_bfloat162 p01 = *reinterpret_cast<const __nv_bfloat162 *>(&pw.x), p23 = *reinterpret_cast<const __nv_bfloat162 *>(&pw.y);
+            const float4 g = *reinterpret_cast<const float4 *>(dPd + row * Tp + j);
+            const float4 mk = drop_scale4(dr, (uint64_t)(row * T + j));
+            ds.x = __low2float(p01) * (g.x * mk.x - dl) * inv_sqrt;
+            ds.y = __high2float(p01) * (g.y * mk.y - dl) * inv_sqrt;
+            ds.z = __low2float(p23) * (g.z * mk.z - dl) * inv_sqrt;
+            ds.w = __high2float(p23) * (g.w * mk.w - dl) * inv_sqrt;
+        }
+        const __nv_bfloat162 a = __floats2bfloat162_rn(ds.x, ds.y), b = __floats2bfloat162_rn(ds.z, ds.w);
+        *reinterpret_cast<uint2 *>(dSb + row * Tp + j) = make_uint2(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&b));
+        if (j < T) {
+            srow[seg0 + j] = __low2bfloat16(a); srow[seg0 + j + 1] = __high2bfloat16(a);
+            srow[seg0 + j + 2] = __low2bfloat16(b); srow[seg0 + j + 3] = __high2bfloat16(b);
+        }
+    }
+    __syncwarp();
+    for (int c = lane; c < Rp / 8; c += 32) *reinterpret_cast<uint4 *>(dPSb + row * Rp + 8 * c) = *reinterpret_cast<const uint4 *>(srow + 8 * c);
+}
 // dst[r, c] = a[r, c] + b[r, c] for c < cols (dst row pitch ldd)
 __global__ void k_add2(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ dst, int64_t ldd, int64_t rows, int cols) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < rows * cols; e += (int64_t)gridDim.x * blockDim.x) {

@@ -264,8 +264,13 @@ int att_backward_tc(Mod &m, const float *x_in, float *dx) {
     {
         const int64_t rows = (int64_t)B * dm.nh * T;
         ProfScope ps(m.c.h, "train_tc_att_ds", m.c.st, 0.0, (double)rows * (6.0 * a.Tp + 2.0 * a.Tp + 2.0 * a.Rp));
-        k_att_ds_tc<<<(unsigned)((rows + 7) / 8), 256, 0, m.c.st>>>(Pl, t.Sc, t.delta, t.dSb, t.dPSb, rows, T, a.Tp, a.Rp, dm.nh, inv_sqrt,
-                                                                   m.drop(m.cfg->attention_dropout_p, 2));
+        const size_t ds_smem = (size_t)8 * a.Rp * 2;
+        if (T % 4 == 0 && ds_smem <= 48 * 1024)
+            k_att_ds_tc_v4<<<(unsigned)((rows + 7) / 8), 256, ds_smem, m.c.st>>>(Pl, t.Sc, t.delta, t.dSb, t.dPSb, rows, T, a.Tp, a.Rp, dm.nh, inv_sqrt,
+                                                                                m.drop(m.cfg->attention_dropout_p, 2));
+        else
+            k_att_ds_tc<<<(unsigned)((rows + 7) / 8), 256, 0, m.c.st>>>(Pl, t.Sc, t.delta, t.dSb, t.dPSb, rows, T, a.Tp, a.Rp, dm.nh, inv_sqrt,
+                                                                       m.drop(m.cfg->attention_dropout_p, 2));
         TK_LAUNCHED(m.c);
     }
     {   // dv_j = sum_i dropout(P)[i,j] dctx_i : A = Pd stored [i][j], B = dctx stored [i][c]

@@ -118,3 +118,28 @@ def train_step_loss(line, lens, targets, target_lens, w, hp, dropout: float = 0.
 
 def trainable_keys(w):
     return [k for k in w if not k.endswith(('running_mean', 'running_var', 'num_batches_tracked'))]
+
+
+def philox_dropout_factors(seed: int, site: int, p: float, n: int):
+    """numpy restatement of the kernels' dropout masks (csrc/dropout.cuh): Philox-4x32-10 with key = (seed low, seed high) and
+    counter = (e >> 2 low, e >> 2 high, site, 0x5eed5eed); element e takes word e & 3 and is kept (factor 1 / (1 - p)) when the
+    word >= floor(p * 2**32).  Returns float32 factors, shape (n,)."""
+    import numpy as np
+    if not p > 0:
+        return np.ones(n, dtype=np.float32)
+    thresh = np.uint64(min(max(int(p * 4294967296.0), 1), 4294967295))
+    nc = (n + 3) // 4
+    ctr = np.arange(nc, dtype=np.uint64)
+    M32 = np.uint64(0xFFFFFFFF)
+    c0, c1 = ctr & M32, ctr >> np.uint64(32)
+    c2 = np.full(nc, site, dtype=np.uint64)
+    c3 = np.full(nc, 0x5eed5eed, dtype=np.uint64)
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    A, B = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    for _ in range(10):
+        p0, p1 = A * c0, B * c2                      # 32 x 32 -> 64 bit products
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & M32, p1 >> np.uint64(32), p1 & M32
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ k0) & M32, lo1, (hi0 ^ c3 ^ k1) & M32, lo0
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & M32, (k1 + np.uint64(0xBB67AE85)) & M32
+    words = np.stack([c0, c1, c2, c3], axis=1).reshape(-1)[:n]
+    return np.where(words >= thresh, np.float32(1.0 / (1.0 - p)), np.float32(0.0)).astype(np.float32)

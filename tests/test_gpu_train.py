@@ -358,3 +358,15 @@ def test_train_step_long_lines_bf16_against_fp32_path(cuda_device):
     for k, ref in k32.items():
         e = np.abs(k16[k] - ref).max() / max(np.abs(ref).max(), 0.05 * gmax)
         assert e <= 0.15, f'{k}: {e:.3f}'
+
+
+@pytest.mark.parametrize('seed,site,p,n', [(0, 0, 0.1, 1000), (12345678901234567, 17, 0.1, 4099), (2 ** 63 + 5, 255, 0.5, 70001), (7, 3, 0.0, 64)])
+def test_dropout_masks_are_philox(cuda_device, seed, site, p, n):
+    """The masks of the training step are a pure function of (seed, site, element): cocr_dropout_mask against the numpy
+    restatement of Philox-4x32-10 in the oracle, bit for bit."""
+    hp = dict(O.DEFAULT_HPARAMS, num_encoder_layers=1)
+    tr = make_trainer(hp, 16, cuda_device)
+    got = tr.dropout_mask(site, p, n, seed=seed).cpu().numpy()
+    want = TP.philox_dropout_factors(seed, site, p, n)
+    assert got.dtype == want.dtype and np.array_equal(got, want)
+    tr.close()
