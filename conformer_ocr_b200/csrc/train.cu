@@ -248,6 +248,12 @@ int ln_fwd(Ctx &c, const float *x, const float *g, const float *b, float *y, flo
 int ln_bwd(Ctx &c, const float *dy, const float *x, const float *stats, const float *g, const float *resid, float *dx_out, float *dgamma,
            float *dbeta, int M, int d) {
     ProfScope ps(c.h, "train_layernorm_bwd", c.st, 0.0, 16.0 * M * d);
+    if (d % 4 == 0 && d <= 256) {
+        const int rpb = 32;
+        k_ln_bwd_fused_v4<<<(M + rpb - 1) / rpb, 256, 0, c.st>>>(dy, x, stats, g, resid, dx_out, M, d, rpb, dgamma, dbeta);
+        TK_LAUNCHED(c);
+        return COCR_OK;
+    }
     if (d <= 32 * LNB_MAXC) {
         const int rpb = 32;
         k_ln_bwd_fused<<<(M + rpb - 1) / rpb, 256, 0, c.st>>>(dy, x, stats, g, resid, dx_out, M, d, rpb, dgamma, dbeta);

@@ -1179,6 +1179,207 @@ __global__ void k_add2(const float *__restrict__ a, const float *__restrict__ b,
 
 __global__ void k_set_seed(uint64_t *dst, uint64_t v) { *dst = v; }
 
+
+// ------------------------------------------------------------------------------------------
+// 16-byte-access variants of the bandwidth-bound kernels (feature counts that are multiples of 4, which the default spec and
+// every test geometry are); the scalar kernels above stay as the general path.  Measured on the dS kernel: 2.2 -> 4.7 TB/s.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+
+// LayerNorm forward, one warp per row, d <= 256: lane owns the float4 chunks lane and lane + 32
+__global__ void k_ln_fwd_v4(const float *__restrict__ x, const float *__restrict__ g, const float *__restrict__ b, float *__restrict__ y,
+                            float *__restrict__ stats, int M, int d, __nv_bfloat16 *__restrict__ yb) {
+    const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const int nq = d >> 2;
+    const float *xr = x + (int64_t)row * d;
+    float4 v[2];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int q = lane + 32 * k;
+        v[k] = q < nq ? ld4(xr + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += v[k].x + v[k].y + v[k].z + v[k].w;
+    }
+    const float mean = warp_sum_f(s) / (float)d;
+    float var = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        if (lane + 32 * k < nq) {
+            const float a = v[k].x - mean, bb = v[k].y - mean, c = v[k].z - mean, e = v[k].w - mean;
+            var += a * a + bb * bb + c * c + e * e;
+        }
+    const float rstd = 1.0f / sqrtf(warp_sum_f(var) / (float)d + 1e-5f);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int q = lane + 32 * k;
+        if (q < nq) {
+            const float4 gg = ld4(g + 4 * q), bv = ld4(b + 4 * q);
+            const float4 o = make_float4((v[k].x - mean) * rstd * gg.x + bv.x, (v[k].y - mean) * rstd * gg.y + bv.y,
+                                         (v[k].z - mean) * rstd * gg.z + bv.z, (v[k].w - mean) * rstd * gg.w + bv.w);
+            if (y) st4(y + (int64_t)row * d + 4 * q, o);
+            if (yb) store_bf16x4(yb + (int64_t)row * d + 4 * q, o);
+        }
+    }
+    if (stats && lane == 0) { stats[2 * (int64_t)row] = mean; stats[2 * (int64_t)row + 1] = rstd; }
+}
+
+// fused LayerNorm backward (dx, dgamma, dbeta), d <= 256 and d % 4 == 0
+__global__ void __launch_bounds__(256)
+k_ln_bwd_fused_v4(const float *__restrict__ dy, const float *__restrict__ x, const float *__restrict__ stats, const float *__restrict__ g,
+                  const float *resid, float *dx_out, int M, int d, int rows_per_block, float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    __shared__ float red[2][8][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nq = d >> 2;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    float4 ag[2], ab[2], gv[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        ag[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ab[k] = ag[k];
+        gv[k] = (lane + 32 * k < nq) ? ld4(g + 4 * (lane + 32 * k)) : ag[k];
+    }
+    for (int row = r0 + warp; row < r1; row += 8) {
+        const float mean = stats[2 * (int64_t)row], rstd = stats[2 * (int64_t)row + 1];
+        const float *xr = x + (int64_t)row * d, *dr = dy + (int64_t)row * d;
+        float4 xh[2], dv[2];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int q = lane + 32 * k;
+            if (q < nq) {
+                const float4 xv = ld4(xr + 4 * q);
+                dv[k] = ld4(dr + 4 * q);
+                xh[k] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+            } else {
+                dv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                xh[k] = dv[k];
+            }
+            const float4 dh = make_float4(dv[k].x * gv[k].x, dv[k].y * gv[k].y, dv[k].z * gv[k].z, dv[k].w * gv[k].w);
+            s1 += dh.x + dh.y + dh.z + dh.w;
+            s2 += dh.x * xh[k].x + dh.y * xh[k].y + dh.z * xh[k].z + dh.w * xh[k].w;
+            ag[k].x = fmaf(dv[k].x, xh[k].x, ag[k].x); ag[k].y = fmaf(dv[k].y, xh[k].y, ag[k].y);
+            ag[k].z = fmaf(dv[k].z, xh[k].z, ag[k].z); ag[k].w = fmaf(dv[k].w, xh[k].w, ag[k].w);
+            ab[k].x += dv[k].x; ab[k].y += dv[k].y; ab[k].z += dv[k].z; ab[k].w += dv[k].w;
+        }
+        s1 = warp_sum_f(s1) / (float)d;
+        s2 = warp_sum_f(s2) / (float)d;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int q = lane + 32 * k;
+            if (q < nq) {
+                float4 o = make_float4(rstd * (dv[k].x * gv[k].x - s1 - xh[k].x * s2), rstd * (dv[k].y * gv[k].y - s1 - xh[k].y * s2),
+                                       rstd * (dv[k].z * gv[k].z - s1 - xh[k].z * s2), rstd * (dv[k].w * gv[k].w - s1 - xh[k].w * s2));
+                if (resid) {
+                    const float4 r = ld4(resid + (int64_t)row * d + 4 * q);
+                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                }
+                st4(dx_out + (int64_t)row * d + 4 * q, o);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int q = lane + 32 * k;
+        if (q < 64) {
+            st4(&red[0][warp][4 * q], ag[k]);
+            st4(&red[1][warp][4 * q], ab[k]);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += 256) {
+        float sg = 0.f, sb = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { sg += red[0][w][c]; sb += red[1][w][c]; }
+        atomicAdd(dgamma + c, sg);
+        atomicAdd(dbeta + c, sb);
+    }
+}
+
+// dst (rows, ldd) bf16 <- src (rows, lds) fp32, columns [0, cols); cols, lds, ldd multiples of 4
+__global__ void k_cast_bf16_v4(const float *__restrict__ src, int64_t lds, __nv_bfloat16 *__restrict__ dst, int64_t ldd, int64_t rows, int cols) {
+    const int nq = cols >> 2;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < rows * nq; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / nq;
+        const int c = (int)(e % nq) << 2;
+        store_bf16x4(dst + r * ldd + c, ld4(src + r * lds + c));
+    }
+}
+// qkv (M, 3d) fp32 -> q+u | q+v | k | v head-pitched bf16; dh % 4 == 0, dhp % 4 == 0
+__global__ void k_att_prep_v4(const float *__restrict__ qkv, const float *__restrict__ ub, const float *__restrict__ vb, __nv_bfloat16 *__restrict__ qu,
+                              __nv_bfloat16 *__restrict__ qv, __nv_bfloat16 *__restrict__ kb, __nv_bfloat16 *__restrict__ vbuf, int64_t M, int nh, int dh,
+                              int dhp) {
+    const int d = nh * dh, nq = d >> 2;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < M * nq; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / nq;
+        const int c = (int)(e % nq) << 2, hd = c / dh, cc = c % dh;
+        const int64_t o = r * nh * dhp + hd * dhp + cc;
+        const float4 q = ld4(qkv + r * 3 * d + c), u = ld4(ub + c), v = ld4(vb + c);
+        store_bf16x4(qu + o, make_float4(q.x + u.x, q.y + u.y, q.z + u.z, q.w + u.w));
+        store_bf16x4(qv + o, make_float4(q.x + v.x, q.y + v.y, q.z + v.z, q.w + v.w));
+        store_bf16x4(kb + o, ld4(qkv + r * 3 * d + d + c));
+        store_bf16x4(vbuf + o, ld4(qkv + r * 3 * d + 2 * d + c));
+    }
+}
+// dctx (M, d) fp32 -> head-pitched bf16 and delta[(b,i), h] = sum_c dctx * ctx; one thread per (row, head, 4 columns), quads of ... 
+// kept simple: one thread per (row, head), 16-byte loads, 8-byte stores
+__global__ void k_att_bwd_prep_v4(const float *__restrict__ dctx, const float *__restrict__ ctx, __nv_bfloat16 *__restrict__ dctxb, float *__restrict__ delta,
+                                  int64_t M, int nh, int dh, int dhp) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < M * nh; e += (int64_t)gridDim.x * blockDim.x) {
+        const float *a = dctx + e * dh, *b = ctx + e * dh;
+        __nv_bfloat16 *o = dctxb + (e / nh) * nh * dhp + (e % nh) * dhp;
+        float s = 0.f;
+        for (int c = 0; c < dh; c += 4) {
+            const float4 av = ld4(a + c), bv = ld4(b + c);
+            s += av.x * bv.x + av.y * bv.y + av.z * bv.z + av.w * bv.w;
+            store_bf16x4(o + c, av);
+        }
+        delta[e] = s;
+    }
+}
+// GLU forward / backward over (M, 2d) -> (M, d), d % 4 == 0
+__global__ void k_glu_fwd_v4(const float *__restrict__ u, float *__restrict__ g, int64_t M, int d) {
+    const int nq = d >> 2;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < M * nq; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = e / nq;
+        const int c = (int)(e % nq) << 2;
+        const float4 a = ld4(u + m * 2 * d + c), b = ld4(u + m * 2 * d + d + c);
+        st4(g + m * d + c, make_float4(a.x * sigmoid_f(b.x), a.y * sigmoid_f(b.y), a.z * sigmoid_f(b.z), a.w * sigmoid_f(b.w)));
+    }
+}
+__global__ void k_glu_bwd_v4(const float *__restrict__ u, const float *__restrict__ dg, float *__restrict__ du, int64_t M, int d,
+                             __nv_bfloat16 *__restrict__ dub) {
+    const int nq = d >> 2;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < M * nq; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = e / nq;
+        const int c = (int)(e % nq) << 2;
+        const float4 a = ld4(u + m * 2 * d + c), b = ld4(u + m * 2 * d + d + c), v = ld4(dg + m * d + c);
+        const float4 sg = make_float4(sigmoid_f(b.x), sigmoid_f(b.y), sigmoid_f(b.z), sigmoid_f(b.w));
+        const float4 da = make_float4(v.x * sg.x, v.y * sg.y, v.z * sg.z, v.w * sg.w);
+        const float4 db = make_float4(v.x * a.x * sg.x * (1.f - sg.x), v.y * a.y * sg.y * (1.f - sg.y), v.z * a.z * sg.z * (1.f - sg.z),
+                                      v.w * a.w * sg.w * (1.f - sg.w));
+        st4(du + m * 2 * d + c, da);
+        st4(du + m * 2 * d + d + c, db);
+        if (dub) {
+            store_bf16x4(dub + m * 2 * d + c, da);
+            store_bf16x4(dub + m * 2 * d + d + c, db);
+        }
+    }
+}
+// z = silu(BatchNorm(c)) -> bf16 only (the tensor-core path's operand), d % 4 == 0
+__global__ void k_bn_silu_fwd_v4(const float *__restrict__ c, const float *__restrict__ stat, const float *__restrict__ gamma,
+                                 const float *__restrict__ beta, int64_t M, int d, __nv_bfloat16 *__restrict__ zb) {
+    const int nq = d >> 2;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < M * nq; e += (int64_t)gridDim.x * blockDim.x) {
+        const int col = (int)(e % nq) << 2;
+        const float4 v = ld4(c + 4 * e), mu = ld4(stat + col), rs = ld4(stat + d + col), ga = ld4(gamma + col), be = ld4(beta + col);
+        const float y0 = ga.x * (v.x - mu.x) * rs.x + be.x, y1 = ga.y * (v.y - mu.y) * rs.y + be.y, y2 = ga.z * (v.z - mu.z) * rs.z + be.z,
+                    y3 = ga.w * (v.w - mu.w) * rs.w + be.w;
+        store_bf16x4(zb + 4 * e, make_float4(y0 * sigmoid_f(y0), y1 * sigmoid_f(y1), y2 * sigmoid_f(y2), y3 * sigmoid_f(y3)));
+    }
+}
+
 // relative positional table rows k = 0..2T-2 <-> offset T-1-k (embedding.py:42-56)
 __global__ void k_rel_pos_table(float *__restrict__ pe, int T, int d) {
     const int R = 2 * T - 1;

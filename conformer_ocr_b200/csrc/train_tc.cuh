@@ -98,7 +98,18 @@ int tc_resid_drop(Ctx &c, const float *x, const float *y, float *out, float fact
     return COCR_OK;
 }
 int tc_cast(Ctx &c, const float *src, int64_t lds, bf16 *dst, int64_t ldd, int64_t rows, int cols) {
-    k_cast_bf16<<<ew_grid(rows * cols), 256, 0, c.st>>>(src, lds, dst, ldd, rows, cols);
+    if (cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0))
+        k_cast_bf16_v4<<<ew_grid(rows * cols / 4), 256, 0, c.st>>>(src, lds, dst, ldd, rows, cols);
+    else
+        k_cast_bf16<<<ew_grid(rows * cols), 256, 0, c.st>>>(src, lds, dst, ldd, rows, cols);
+    TK_LAUNCHED(c);
+    return COCR_OK;
+}
+// LayerNorm forward straight to the bf16 GEMM operand (+ statistics for the backward pass)
+int tc_ln_fwd(Ctx &c, const float *x, const float *g, const float *b, float *stats, int M, int d, bf16 *yb) {
+    ProfScope ps(c.h, "train_layernorm", c.st, 0.0, 6.0 * M * d);
+    if (d % 4 == 0 && d <= 256) k_ln_fwd_v4<<<(M + 7) / 8, 256, 0, c.st>>>(x, g, b, nullptr, stats, M, d, yb);
+    else k_ln_fwd<<<(M + 7) / 8, 256, 0, c.st>>>(x, g, b, nullptr, stats, M, d, yb);
     TK_LAUNCHED(c);
     return COCR_OK;
 }
@@ -112,8 +123,7 @@ int ffn_forward_tc(Mod &m, int half, const float *x_in, float *x_out) {
     float *y = m.f(m.p.t_d1);
     float *h1 = m.f(m.p.h1) + ((size_t)m.l * 2 + half) * M * ff;
     bf16 *xnb = sv.xnb[half ? 3 : 0], *actb = sv.actb[half];
-    k_ln_fwd<<<(M + 7) / 8, 256, 0, m.c.st>>>(x_in, m.P + o.ffn_ln_g[half], m.P + o.ffn_ln_b[half], nullptr, m.stats(half ? 3 : 0), M, d, xnb);
-    TK_LAUNCHED(m.c);
+    COCR_TRY(tc_ln_fwd(m.c, x_in, m.P + o.ffn_ln_g[half], m.P + o.ffn_ln_b[half], m.stats(half ? 3 : 0), M, d, xnb));
     COCR_TRY(tc_linear(m.c, xnb, d, t.pb + o.ffn_w1[half], m.P + o.ffn_b1[half], h1, ff, M, ff, d, "train_tc_ffn_up"));
     if (ff % 4 == 0) k_silu_drop_v4<<<ew_grid((int64_t)M * ff / 4), 256, 0, m.c.st>>>(h1, (int64_t)M * ff, m.drop(m.cfg->feed_forward_dropout_p, half ? 6 : 0), actb);
     else k_silu_drop<<<ew_grid((int64_t)M * ff), 256, 0, m.c.st>>>(h1, nullptr, (int64_t)M * ff, m.drop(m.cfg->feed_forward_dropout_p, half ? 6 : 0), actb);
@@ -179,13 +189,13 @@ int att_forward_tc(Mod &m, const float *x_in, float *x_out) {
     bf16 *Pl = (bf16 *)(m.ws + m.p.Pb16) + (size_t)m.l * 2 * pblk;
     const bool adrop = m.cfg->attention_dropout_p > 0.0f;
     bf16 *Pd = adrop ? Pl + pblk : Pl;
-    k_ln_fwd<<<(M + 7) / 8, 256, 0, m.c.st>>>(x_in, m.P + o.att_ln_g, m.P + o.att_ln_b, nullptr, m.stats(1), M, d, sv.xnb[1]);
-    TK_LAUNCHED(m.c);
+    COCR_TRY(tc_ln_fwd(m.c, x_in, m.P + o.att_ln_g, m.P + o.att_ln_b, m.stats(1), M, d, sv.xnb[1]));
     COCR_TRY(tc_linear(m.c, sv.xnb[1], d, t.pb + o.w_qkv, m.P + o.b_qkv, qkv, 3 * d, M, 3 * d, d, "train_tc_qkv"));
     COCR_TRY(tc_linear(m.c, t.peb, d, t.pb + o.w_pos, nullptr, pos, d, R, d, d, "train_tc_pos_proj"));
     {
         ProfScope ps(m.c.h, "train_tc_att_prep", m.c.st, 0.0, (double)M * (12.0 * d + 8.0 * a.HP));
-        k_att_prep<<<ew_grid((int64_t)M * d), 256, 0, m.c.st>>>(qkv, m.P + o.u_bias, m.P + o.v_bias, sv.qu, sv.qv, sv.kb, sv.vb, M, dm.nh, dm.dh, a.dhp);
+        if (dm.dh % 4 == 0) k_att_prep_v4<<<ew_grid((int64_t)M * d / 4), 256, 0, m.c.st>>>(qkv, m.P + o.u_bias, m.P + o.v_bias, sv.qu, sv.qv, sv.kb, sv.vb, M, dm.nh, dm.dh, a.dhp);
+        else k_att_prep<<<ew_grid((int64_t)M * d), 256, 0, m.c.st>>>(qkv, m.P + o.u_bias, m.P + o.v_bias, sv.qu, sv.qv, sv.kb, sv.vb, M, dm.nh, dm.dh, a.dhp);
         TK_LAUNCHED(m.c);
         k_head_pitch<<<ew_grid((int64_t)R * d), 256, 0, m.c.st>>>(pos, d, 0, nullptr, sv.posb, R, dm.nh, dm.dh, a.dhp);
         TK_LAUNCHED(m.c);
@@ -250,7 +260,8 @@ int att_backward_tc(Mod &m, const float *x_in, float *dx) {
     COCR_TRY(tc_dgrad(m.c, t.dyb, d, t.pb + o.w_out, dctx, d, M, d, d));
     {
         ProfScope ps(m.c.h, "train_tc_att_prep", m.c.st, 0.0, (double)M * (8.0 * d + 2.0 * a.HP));
-        k_att_bwd_prep<<<ew_grid((int64_t)M * dm.nh), 256, 0, m.c.st>>>(dctx, ctx, t.dctxb, t.delta, M, dm.nh, dm.dh, a.dhp);
+        if (dm.dh % 4 == 0) k_att_bwd_prep_v4<<<ew_grid((int64_t)M * dm.nh), 256, 0, m.c.st>>>(dctx, ctx, t.dctxb, t.delta, M, dm.nh, dm.dh, a.dhp);
+        else k_att_bwd_prep<<<ew_grid((int64_t)M * dm.nh), 256, 0, m.c.st>>>(dctx, ctx, t.dctxb, t.delta, M, dm.nh, dm.dh, a.dhp);
         TK_LAUNCHED(m.c);
     }
     {   // d dropout(P) = dctx v^T : (T x T)
@@ -339,10 +350,10 @@ int conv_forward_tc(Mod &m, const float *x_in, float *x_out, float *params_rw) {
     float *u = m.f(m.p.u) + (size_t)m.l * M * 2 * d, *cd = m.f(m.p.cdw) + (size_t)m.l * M * d, *bst = m.f(m.p.bnstat) + (size_t)m.l * 2 * d;
     double *sums = (double *)m.f(m.p.bnsums);
     const TcSaved sv = tc_saved(t, m.p, dm, m.l);
-    k_ln_fwd<<<(M + 7) / 8, 256, 0, m.c.st>>>(x_in, m.P + o.conv_ln_g, m.P + o.conv_ln_b, nullptr, m.stats(2), M, d, sv.xnb[2]);
-    TK_LAUNCHED(m.c);
+    COCR_TRY(tc_ln_fwd(m.c, x_in, m.P + o.conv_ln_g, m.P + o.conv_ln_b, m.stats(2), M, d, sv.xnb[2]));
     COCR_TRY(tc_linear(m.c, sv.xnb[2], d, t.pb + o.w_pw1, m.P + o.b_pw1, u, 2 * d, M, 2 * d, d, "train_tc_pw1"));
-    k_glu_fwd<<<ew_grid((int64_t)M * d), 256, 0, m.c.st>>>(u, g, M, d);
+    if (d % 4 == 0) k_glu_fwd_v4<<<ew_grid((int64_t)M * d / 4), 256, 0, m.c.st>>>(u, g, M, d);
+    else k_glu_fwd<<<ew_grid((int64_t)M * d), 256, 0, m.c.st>>>(u, g, M, d);
     TK_LAUNCHED(m.c);
     COCR_TRY(dwconv(m.c, g, m.P + o.w_dw, cd, B, T, d, dm.K, 0));
     COCR_CUDA(m.c.h, cudaMemsetAsync(sums, 0, (size_t)2 * d * 8, m.c.st));
@@ -352,7 +363,8 @@ int conv_forward_tc(Mod &m, const float *x_in, float *x_out, float *params_rw) {
     k_bn_finalize<<<(d + 255) / 256, 256, 0, m.c.st>>>(sums, M, d, m.cfg->bn_momentum, bst, params_rw ? params_rw + o.bn_rm : nullptr,
                                                        params_rw ? params_rw + o.bn_rv : nullptr);
     TK_LAUNCHED(m.c);
-    k_bn_silu_fwd<<<ew_grid((int64_t)M * d), 256, 0, m.c.st>>>(cd, bst, m.P + o.bn_g, m.P + o.bn_b, nullptr, M, d, sv.zb);
+    if (d % 4 == 0) k_bn_silu_fwd_v4<<<ew_grid((int64_t)M * d / 4), 256, 0, m.c.st>>>(cd, bst, m.P + o.bn_g, m.P + o.bn_b, M, d, sv.zb);
+    else k_bn_silu_fwd<<<ew_grid((int64_t)M * d), 256, 0, m.c.st>>>(cd, bst, m.P + o.bn_g, m.P + o.bn_b, nullptr, M, d, sv.zb);
     TK_LAUNCHED(m.c);
     COCR_TRY(tc_linear(m.c, sv.zb, d, t.pb + o.w_pw2, m.P + o.b_pw2, y, d, M, d, d, "train_tc_pw2"));
     COCR_TRY(tc_resid_drop(m.c, x_in, y, x_out, 1.0f, M, d, m.drop(m.cfg->conv_dropout_p, 4), nullptr, nullptr));
@@ -380,11 +392,13 @@ int conv_backward_tc(Mod &m, const float *x_in, float *dx) {
     k_bn_bwd_apply<<<ew_grid((int64_t)M * d), 256, 0, m.c.st>>>(cd, bst, m.P + o.bn_g, sums, dz, M, d, m.G + o.bn_g, m.G + o.bn_b);
     TK_LAUNCHED(m.c);
     float *dc = dz;
-    k_glu_fwd<<<ew_grid((int64_t)M * d), 256, 0, m.c.st>>>(u, g, M, d);
+    if (d % 4 == 0) k_glu_fwd_v4<<<ew_grid((int64_t)M * d / 4), 256, 0, m.c.st>>>(u, g, M, d);
+    else k_glu_fwd<<<ew_grid((int64_t)M * d), 256, 0, m.c.st>>>(u, g, M, d);
     TK_LAUNCHED(m.c);
     COCR_TRY(dwconv_wgrad(m.c, g, dc, m.G + o.w_dw, B, T, d, dm.K));
     COCR_TRY(dwconv(m.c, dc, m.P + o.w_dw, dg, B, T, d, dm.K, 1));
-    k_glu_bwd<<<ew_grid((int64_t)M * d), 256, 0, m.c.st>>>(u, dg, du, M, d, t.wideb);
+    if (d % 4 == 0) k_glu_bwd_v4<<<ew_grid((int64_t)M * d / 4), 256, 0, m.c.st>>>(u, dg, du, M, d, t.wideb);
+    else k_glu_bwd<<<ew_grid((int64_t)M * d), 256, 0, m.c.st>>>(u, dg, du, M, d, t.wideb);
     TK_LAUNCHED(m.c);
     COCR_TRY(m.c.fork());
     COCR_TRY(tc_wgrad(m.c, t.wideb, 2 * d, sv.xnb[2], d, m.G + o.w_pw1, M, 2 * d, d));
