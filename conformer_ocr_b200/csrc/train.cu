@@ -356,6 +356,14 @@ int dwconv(Ctx &c, const float *x, const float *w, float *y, int B, int T, int d
     return COCR_OK;
 }
 int dwconv_wgrad(Ctx &c, const float *x, const float *dy, float *dw, int B, int T, int d, int K) {
+    if (K == 31 && 4 * (size_t)(64 + 30 + 64 + 31) * d <= 200 * 1024) {
+        const size_t smem = 4 * (size_t)(64 + 30 + 64 + 31) * d;
+        COCR_TRY(set_smem(c.h, k_dwconv1d_wgrad_k31, smem));
+        ProfScope ps(c.h, "train_dwconv_wgrad", c.st, 2.0 * K * B * (double)T * d, 8.0 * B * T * d);
+        k_dwconv1d_wgrad_k31<<<dim3((T + 63) / 64, B), 256, smem, c.st>>>(x, dy, dw, T, d);
+        TK_LAUNCHED(c);
+        return COCR_OK;
+    }
     int tile = 64;                                   // frames per CTA: larger tiles = fewer atomics per output, fewer CTAs
     while (tile > 16 && (4 * (size_t)(2 * tile + K - 1) * d > 200 * 1024 || tile >= 2 * T)) tile /= 2;
     const size_t smem = 4 * (size_t)(2 * tile + K - 1) * d;

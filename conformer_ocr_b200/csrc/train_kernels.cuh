@@ -480,6 +480,53 @@ k_dwconv1d_k31(const float *__restrict__ x, const float *__restrict__ w, float *
         }
     }
 }
+// Weight gradient for K = 31: a thread owns a channel and 8 consecutive frames, reads its 8 output gradients and 38 input rows once
+// and keeps the 31 tap sums in registers (46 shared-memory reads per 248 multiply-adds instead of 2 per 1); the 8 frame groups of a
+// channel meet in a shared-memory accumulator, one global atomic per (channel, tap) and CTA.
+__global__ void __launch_bounds__(256)
+k_dwconv1d_wgrad_k31(const float *__restrict__ x, const float *__restrict__ dy, float *__restrict__ dw, int T, int d) {
+    constexpr int K = 31, TT = 64, OUT = 8;
+    extern __shared__ float sm[];
+    float *tile = sm;                                // [TT + 30][d]  x
+    float *dt = tile + (size_t)(TT + K - 1) * d;     // [TT][d]       dy
+    float *accs = dt + (size_t)TT * d;               // [K][d]
+    const int b = blockIdx.y, t0 = blockIdx.x * TT, rows = TT + K - 1;
+    for (int e = threadIdx.x; e < rows * d; e += 256) {
+        const int r = e / d, c = e % d, t = t0 - 15 + r;
+        tile[e] = (t >= 0 && t < T) ? x[((int64_t)b * T + t) * d + c] : 0.0f;
+    }
+    for (int e = threadIdx.x; e < TT * d; e += 256) {
+        const int tt = e / d, c = e % d, t = t0 + tt;
+        dt[e] = (t < T) ? dy[((int64_t)b * T + t) * d + c] : 0.0f;
+    }
+    for (int e = threadIdx.x; e < K * d; e += 256) accs[e] = 0.0f;
+    __syncthreads();
+    for (int e = threadIdx.x; e < (TT / OUT) * d; e += 256) {
+        const int g = e / d, c = e % d;
+        float acc[K], dv[OUT];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) dv[o] = dt[(size_t)(g * OUT + o) * d + c];
+        const float *in = tile + (size_t)(g * OUT) * d + c;
+#pragma unroll
+        for (int r = 0; r < OUT + K - 1; ++r) {
+            const float v = in[(size_t)r * d];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) {
+                const int k = r - o;
+                if (k >= 0 && k < K) acc[k] = fmaf(dv[o], v, acc[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) atomicAdd(&accs[k * d + c], acc[k]);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < K * d; e += 256) {
+        const int k = e / d, c = e % d;
+        atomicAdd(dw + c * K + k, accs[e]);
+    }
+}
 // dw[c,k] += sum_{b,t} dy[b,t,c] * x[b,t+k-pad,c]      (tiles of DWT frames; the caller picks DWT so that the tile fits shared memory)
 __global__ void __launch_bounds__(256)
 k_dwconv1d_wgrad(const float *__restrict__ x, const float *__restrict__ dy, float *__restrict__ dw, int T, int d, int K, int DWT) {
@@ -1005,20 +1052,22 @@ __global__ void k_att_softmax_tc(const float *__restrict__ Sc, const float *__re
     if (row >= rows) return;
     const int i = (int)(row % T);
     const float *sc = Sc + row * Tp, *ps = PS + row * Rp + (T - 1 - i);
-    if (T <= 512 && (Tp & 3) == 0) {   // the row lives in registers, 4 consecutive columns per lane and step: 16-byte loads of the
-                                       // content scores, 8-byte stores of the bf16 rows, one Philox call per 4 probabilities
+    if (T <= 512) {   // the row lives in registers, 8 consecutive columns per lane and step (Tp is a multiple of 8): 16-byte loads of
+                      // the content scores, 16-byte stores of the bf16 rows, one Philox call per 4 probabilities
         float v[16];
         float mx = -INFINITY;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int j = 4 * lane + 128 * k;
-            float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < Tp) s4 = *reinterpret_cast<const float4 *>(sc + j);
-            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+        for (int k = 0; k < 2; ++k) {
+            const int j = 8 * lane + 256 * k;
+            float sv[8];
+            if (j < Tp) {
+                const float4 s0 = *reinterpret_cast<const float4 *>(sc + j), s1 = *reinterpret_cast<const float4 *>(sc + j + 4);
+                sv[0] = s0.x; sv[1] = s0.y; sv[2] = s0.z; sv[3] = s0.w; sv[4] = s1.x; sv[5] = s1.y; sv[6] = s1.z; sv[7] = s1.w;
+            }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                v[4 * k + i] = (j + i < T) ? (sv[i] + ps[j + i]) * inv_sqrt : -INFINITY;
-                mx = fmaxf(mx, v[4 * k + i]);
+            for (int i = 0; i < 8; ++i) {
+                v[8 * k + i] = (j + i < T) ? (sv[i] + ps[j + i]) * inv_sqrt : -INFINITY;
+                mx = fmaxf(mx, v[8 * k + i]);
             }
         }
 #pragma unroll
@@ -1033,17 +1082,33 @@ __global__ void k_att_softmax_tc(const float *__restrict__ Sc, const float *__re
         const float inv = 1.0f / s;
         const bool quad_rng = (T & 3) == 0;              // element index row*T + j is then a multiple of 4 with j
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int j = 4 * lane + 128 * k;
+        for (int k = 0; k < 2; ++k) {
+            const int j = 8 * lane + 256 * k;
             if (j >= Tp) break;
-            const float4 pv = make_float4(v[4 * k] * inv, v[4 * k + 1] * inv, v[4 * k + 2] * inv, v[4 * k + 3] * inv);
-            store_bf16x4(P + row * Tp + j, pv);
+            float pv[8], pd[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pv[i] = v[8 * k + i] * inv;
+            uint4 w;
+            {
+                const __nv_bfloat162 a = __floats2bfloat162_rn(pv[0], pv[1]), b = __floats2bfloat162_rn(pv[2], pv[3]),
+                                     c = __floats2bfloat162_rn(pv[4], pv[5]), e = __floats2bfloat162_rn(pv[6], pv[7]);
+                w = make_uint4(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&b), *reinterpret_cast<const uint32_t *>(&c),
+                               *reinterpret_cast<const uint32_t *>(&e));
+            }
+            *reinterpret_cast<uint4 *>(P + row * Tp + j) = w;
             if (Pd != P) {
-                float4 m;
-                if (quad_rng) m = drop_scale4(dr, (uint64_t)(row * T + j));
-                else m = make_float4(drop_scale(dr, (uint64_t)(row * T + j)), drop_scale(dr, (uint64_t)(row * T + j + 1)),
-                                     drop_scale(dr, (uint64_t)(row * T + j + 2)), drop_scale(dr, (uint64_t)(row * T + j + 3)));
-                store_bf16x4(Pd + row * Tp + j, make_float4(pv.x * m.x, pv.y * m.y, pv.z * m.z, pv.w * m.w));
+                if (quad_rng) {
+                    const float4 m0 = drop_scale4(dr, (uint64_t)(row * T + j)), m1 = drop_scale4(dr, (uint64_t)(row * T + j + 4));
+                    pd[0] = pv[0] * m0.x; pd[1] = pv[1] * m0.y; pd[2] = pv[2] * m0.z; pd[3] = pv[3] * m0.w;
+                    pd[4] = pv[4] * m1.x; pd[5] = pv[5] * m1.y; pd[6] = pv[6] * m1.z; pd[7] = pv[7] * m1.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) pd[i] = (j + i < T) ? pv[i] * drop_scale(dr, (uint64_t)(row * T + j + i)) : 0.f;
+                }
+                const __nv_bfloat162 a = __floats2bfloat162_rn(pd[0], pd[1]), b = __floats2bfloat162_rn(pd[2], pd[3]),
+                                     c = __floats2bfloat162_rn(pd[4], pd[5]), e = __floats2bfloat162_rn(pd[6], pd[7]);
+                *reinterpret_cast<uint4 *>(Pd + row * Tp + j) = make_uint4(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&b),
+                                                                            *reinterpret_cast<const uint32_t *>(&c), *reinterpret_cast<const uint32_t *>(&e));
             }
         }
         return;
