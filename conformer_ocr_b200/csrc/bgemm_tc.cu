@@ -2,13 +2,14 @@
 // bf16 operands fed by 4-D TMA tensor maps, fp32 accumulation in TMEM.  Either operand may be K-major (stored row-major
 // with the contraction index contiguous) or MN-major (stored [k][m]: the contraction index runs along the rows), so the
 // same kernel computes the forward linears (NT), the data gradients (NN: B = W stored (N_w, K_w) read MN-major), the weight
-// gradients (TN: both operands MN-major, contraction over the B*T frames, split over CTAs, fp32 atomics) and every
+// gradients (TN: both operands MN-major, contraction over the B*T frames split over CTAs into partial products or fp32 atomics) and every
 // contraction of the attention module per (line, head).  Out-of-range rows / columns / contraction indices of a batch
 // item are zero-filled by the tensor map (its extents are the batch item's own), so no operand needs padding.
 //
 // One CTA = one 128 x block_n output tile of one batch item and one k-slice: warp 0 TMA producer, warp 1 MMA issuer
-// (one elected lane), warps 2-5 epilogue (TMEM -> registers -> global).  Several CTAs are resident per SM (<= 64 KB of
-// shared memory, <= 256 TMEM columns each), which is what overlaps the loads of one tile with the MMAs of another.
+// (one elected lane), warps 2-5 epilogue (TMEM -> registers -> a swizzled per-warp staging tile -> global, so that a store
+// instruction covers whole 128-byte rows).  Several CTAs are resident per SM (<= 112 KB of shared memory, <= 256 TMEM columns
+// each), which is what overlaps the epilogue of one tile with the loads and MMAs of another.
 #include <cuda.h>
 
 #include "common.h"

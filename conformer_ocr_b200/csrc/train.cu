@@ -1,6 +1,8 @@
 // One training step of RecognitionModel (model.py:129-145) on one GPU: train()-mode forward (BatchNorm batch statistics,
 // dropout), log_softmax + CTCLoss(sum, zero_infinity), and the hand-written backward pass through the decoder, the 16
-// conformer blocks and the convolutional front-end; plus the AdamW update (model.py:272-274).  fp32 throughout.
+// conformer blocks and the convolutional front-end; plus the AdamW update (model.py:272-274).  Two arithmetic modes
+// (cocr_train_config.compute): 0 = fp32 CUDA-core kernels (this file + train_kernels.cuh: the parity path), 1 = every dense
+// contraction on tcgen05 with bf16 operands through the batched GEMM of bgemm_tc.cu (train_tc.cuh), fp32 everywhere else.
 //
 // Parameters, gradients and optimiser moments live in FLAT fp32 buffers owned by the caller (torch tensors); the layout
 // (state-dict key -> offset) is exported by cocr_train_entry.  Trainable tensors come first, the BatchNorm running

@@ -59,7 +59,8 @@ int tc_dgrad(Ctx &c, const bf16 *dyb, int ldy, const bf16 *Wb, float *dx, int ld
     g.out = dx; g.ldc = ldo;
     return launch_bgemm(c.h, g, c.st, "train_tc_dgrad");
 }
-// dW (N, K) fp32 += dy (M, N)^T x (M, K); contraction over the M frames split over CTAs (fp32 atomics into the zeroed gradient)
+// dW (N, K) fp32 = dy (M, N)^T x (M, K); the contraction over the M frames is split over one wave of CTAs into partial products
+// that are summed in slice order; runs on the weight-gradient stream (Ctx::fork / join)
 int tc_wgrad(Ctx &c, const bf16 *dyb, int ldy, const bf16 *xb, int ldx, float *dW, int M, int N, int K) {
     BgProblem g;
     g.M = N; g.N = K; g.K = M;
