@@ -10,6 +10,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -38,8 +39,9 @@ struct TrainState {
     std::vector<TrainLayerOff> L;
     char *ws = nullptr;
     size_t ws_bytes = 0;
-    float *pe = nullptr;        // (2T-1, d) relative positional table
+    float *pe = nullptr;        // (2T-1, d) relative positional table of the running step (an entry of `pes`)
     int pe_T = 0;
+    std::map<int, float *> pes; // one table per frame count, kept until the handle dies: captured steps hold their addresses
     uint64_t *seed_dev = nullptr;   // [0]: seed of the running step, [1]: seed of cocr_dropout_mask
     // the launch sequence of one step, captured per argument set and replayed (about 1 800 launches per step otherwise)
     struct StepGraph {
@@ -516,16 +518,17 @@ int ensure_train_ws(cocr_handle *h, TrainState *s, size_t bytes) {
 }
 
 int ensure_pe(cocr_handle *h, TrainState *s, int T, cudaStream_t st) {
-    if (s->pe && s->pe_T == T) return COCR_OK;
-    if (s->pe) {
-        COCR_CUDA(h, cudaDeviceSynchronize());
-        COCR_CUDA(h, cudaFree(s->pe));
-        s->pe = nullptr;
+    // A table is written once and never freed or rewritten while the handle lives: the step graphs captured for a width bake
+    // its address in, and batches of alternating widths must not stall on a device synchronise + free + malloc per step.
+    auto it = s->pes.find(T);
+    if (it != s->pes.end()) {
+        s->pe = it->second;
+        s->pe_T = T;
+        return COCR_OK;
     }
     const int R = 2 * T - 1, d = h->dm.d;
     void *p = nullptr;
     COCR_CUDA(h, cudaMalloc(&p, (size_t)R * d * 4));
-    s->pe = (float *)p;
     // embedding.py:42-56 in the reference's own fp32 steps (host), as ensure_pos_proj does for the inference path
     std::vector<float> pe((size_t)R * d);
     const float neg = (float)(-(log(10000.0) / (double)d));
@@ -537,8 +540,13 @@ int ensure_pe(cocr_handle *h, TrainState *s, int T, cudaStream_t st) {
             if (m + 1 < d) pe[(size_t)k * d + m + 1] = cosf(arg);
         }
     }
-    COCR_CUDA(h, cudaMemcpyAsync(s->pe, pe.data(), pe.size() * 4, cudaMemcpyHostToDevice, st));
-    COCR_CUDA(h, cudaStreamSynchronize(st));
+    cudaError_t e = cudaMemcpyAsync(p, pe.data(), pe.size() * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);        // `pe` is pageable host memory
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        COCR_CUDA(h, e);
+    }
+    s->pes[T] = s->pe = (float *)p;
     s->pe_T = T;
     return COCR_OK;
 }
@@ -728,7 +736,7 @@ int conv_backward_mod(Mod &m, const float *x_in, float *dx) {
 void train_destroy(cocr_handle *h) {
     if (!h->train) return;
     if (h->train->ws) cudaFree(h->train->ws);
-    if (h->train->pe) cudaFree(h->train->pe);
+    for (auto &kv : h->train->pes) cudaFree(kv.second);
     if (h->train->seed_dev) cudaFree(h->train->seed_dev);
     for (auto &g : h->train->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -825,7 +833,7 @@ int train_step(cocr_handle *h, float *params, float *grads, const float *img, in
     auto bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return (uint64_t)u; };
     std::vector<uint64_t> key = {(uint64_t)B, (uint64_t)W, (uint64_t)max_target_len, (uint64_t)tc, (uint64_t)params, (uint64_t)grads, (uint64_t)img,
                                  (uint64_t)sb, (uint64_t)sw, (uint64_t)sh, (uint64_t)widths, (uint64_t)targets, (uint64_t)target_lens, (uint64_t)loss_out,
-                                 (uint64_t)loss_per_line, (uint64_t)s->ws, bits(cfg->input_dropout_p), bits(cfg->feed_forward_dropout_p),
+                                 (uint64_t)loss_per_line, (uint64_t)s->ws, (uint64_t)s->pe, bits(cfg->input_dropout_p), bits(cfg->feed_forward_dropout_p),
                                  bits(cfg->attention_dropout_p), bits(cfg->conv_dropout_p), bits(cfg->bn_momentum)};
     TrainState::StepGraph *sg = nullptr;
     for (auto &g : s->graphs)

@@ -139,8 +139,13 @@ class Trainer:
         tl_host = torch.as_tensor(batch['target_lens']).to('cpu', dtype=torch.int64)
         tlens = self._staged('target_lens', tl_host, torch.int32)
         tg = torch.as_tensor(batch['target'])
+        if tl_host.numel() != B:
+            raise ValueError(f'{tl_host.numel()} target lengths for a batch of {B}')
         if tg.numel() != int(tl_host.sum()):
             raise ValueError('target has to be the 1-D concatenation of the label sequences')
+        if not tg.is_cuda and tg.numel() and (int(tg.min()) < 1 or int(tg.max()) >= self.num_classes):
+            # the loss kernels index the logits with the labels; a device-resident target is taken on trust (no host sync per step)
+            raise ValueError('target labels must lie in 1 .. num_classes-1 (0 is the CTC blank)')
         targets = self._staged('target', tg, torch.int32, capacity=max(int(tg.numel()), B * 128))
         taps = None
         if debug_taps:
@@ -166,7 +171,8 @@ class Trainer:
         return view
 
     def allreduce_gradients(self):
-        """ONE all-reduce(sum) of the trainable prefix of the flat gradient buffer plus the loss (NCCL over NVLink)."""
+        """ONE all-reduce(sum) of the trainable prefix of the flat gradient buffer (NCCL over NVLink).  The loss stays the
+        rank's own sum, as the value `training_step` logs per rank under Lightning's DDP (model.py:155-157)."""
         allreduce_flat_prefix(self.grads, self.n_trainable, self.group)
 
     def optimizer_step(self):

@@ -338,6 +338,40 @@ def test_training_soak_over_changing_shapes(cuda_device):
     assert np.abs(finals[0] - finals[1]).max() <= 0.02 * finals[0].max(), finals
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_step_graphs_survive_alternating_widths(cuda_device, precision):
+    """One trainer fed batches of two widths in turns (plain launches, capture, replays of both step graphs, back and forth):
+    every visit reproduces the loss and the gradient buffer of a FRESH trainer's first (plain-launch) step on that batch.
+    Dropout 0 and no optimiser step, so nothing but the BatchNorm running statistics (unused in train mode) changes between
+    visits.  Guards the addresses a captured step bakes in - the relative positional table of its frame count above all:
+    one table per frame count lives as long as the handle (csrc/train.cu ensure_pe), so a replay never reads a table that
+    was freed or rewritten for another width.  Tolerance: the fp32 atomics of the bias / LayerNorm sums reorder additions."""
+    hp = dict(O.DEFAULT_HPARAMS, num_encoder_layers=2)
+    C = 40
+    w = O.make_weights(hp, C, seed=91)
+    batches = {}
+    for name, (B, W, seed) in {'A': (3, 768, 92), 'B': (3, 512, 93)}.items():
+        b = synthetic_batch(B, hp['height'], W, C, seed=seed)
+        b['target_lens'] = torch.clamp(b['target_lens'], max=W // 16)
+        b['target'] = b['target'][:int(b['target_lens'].sum())]
+        batches[name] = b
+    fresh = {}
+    for name, b in batches.items():
+        tr = make_trainer(hp, C, cuda_device, precision=precision)
+        tr.load_state_dict(w)
+        fresh[name] = (tr.forward_backward(b).item(), tr.grads[:tr.n_trainable].clone())
+        tr.close()
+    tr = make_trainer(hp, C, cuda_device, precision=precision)
+    tr.load_state_dict(w)
+    for visit, name in enumerate('AAABBBAABBAB'):
+        loss = tr.forward_backward(batches[name]).item()
+        ref_loss, ref_g = fresh[name]
+        assert abs(loss - ref_loss) <= 1e-4 * abs(ref_loss), (visit, name, loss, ref_loss)
+        err = ((tr.grads[:tr.n_trainable] - ref_g).abs().max() / ref_g.abs().max()).item()
+        assert err <= 1e-3, (visit, name, err)
+    tr.close()
+
+
 def test_train_step_long_lines_bf16_against_fp32_path(cuda_device):
     """Lines of 2304 px (T = 576 > 512: the softmax kernel's streaming path, several key tiles and contraction chunks per GEMM, a
     ragged batch) and an odd class count: the tensor-core mode against the fp32 CUDA-core mode on the same batch, one layer."""
