@@ -195,22 +195,33 @@ def algorithmic_work(hp, B, W, C, in_bytes_per_px=4):
 # CPU baseline (reference arm): the port of the reference's ATen-CPU operator sequence (oracle/torch_port.py)
 # ----------------------------------------------------------------------------------------------
 def cpu_pass_factory(args):
+    """One pass of the reference's CPU implementation of the path over a bounded sample of the workload.  With `oracle/_ref`
+    (the reference's own encoder modules, compiled by oracle/build_ref.py) the pass is pred.py:171-178 over those modules
+    (kind 'reference'); without it, the port of their operator sequence (kind 'port')."""
     from oracle import torch_port as TP          # allowed here: cpu_baseline / --impl reference leg only
+    from oracle import ref_modules as RM
     from conformer_ocr_b200 import synthetic as S
     hp = arch_hp(hparams())
-    w = TP.to_torch(S.make_weights(hp, args.classes, seed=0))
+    wnp = S.make_weights(hp, args.classes, seed=0)
     n = max(1, min(args.cpu_sample_lines, args.batch))
     img, lens = S.make_lines(n, hp['height'], args.width, seed=1234)
     ti, tl = torch.from_numpy(img), torch.from_numpy(lens)
     torch.set_num_threads(os.cpu_count() or 1)
+    if RM.available() and not os.environ.get('COCR_BENCH_CPU_PORT'):
+        net = RM.build_model(hp, args.classes, wnp).eval()
+
+        def one_pass():
+            return RM.predict_labels(net, ti, tl)
+        return one_pass, n, torch.get_num_threads(), 'reference'
+    w = TP.to_torch(wnp)
 
     def one_pass():
         return TP.predict_labels(ti, tl, w, hp)
-    return one_pass, n, torch.get_num_threads()
+    return one_pass, n, torch.get_num_threads(), 'port'
 
 
 def time_cpu(args, reps: int, warm: int):
-    one_pass, n, cores = cpu_pass_factory(args)
+    one_pass, n, cores, kind = cpu_pass_factory(args)
     for _ in range(warm):
         one_pass()
     times = []
@@ -218,29 +229,35 @@ def time_cpu(args, reps: int, warm: int):
         t0 = time.perf_counter()
         one_pass()
         times.append(time.perf_counter() - t0)
-    return n, cores, times
+    return n, cores, times, kind
 
 
-CPU_NOTE = ('port of the reference\'s ATen CPU operator sequence (oracle/torch_port.py; the reference package itself imports '
-            'kraken/lightning, absent here); the relative-position table is built once per pass, not repeated per batch '
-            'row as attention.py:145 does, which flatters the reference slightly')
+CPU_NOTES = {
+    'reference': ('the reference\'s own conformer modules (oracle/_ref: conformer_ocr.conformer.* byte-compiled from the reference tree by '
+                  'oracle/build_ref.py) driven as pred.py:171-178 does: encoder -> nn.Linear -> transpose / D2H-style numpy copy -> greedy decode '
+                  'per line (kraken\'s greedy_decoder is absent: restated in oracle/conformer_oracle.py)'),
+    'port': ('port of the reference\'s ATen CPU operator sequence (oracle/torch_port.py; oracle/_ref is not built on this machine); the '
+             'relative-position table is built once per pass, not repeated per batch row as attention.py:145 does, which flatters the '
+             'reference slightly'),
+}
+CPU_WHAT = {'reference': 'reference modules (oracle/_ref)', 'port': 'oracle/torch_port.py'}
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    n, cores, times = time_cpu(args, reps=max(1, args.steps), warm=max(1, min(args.warmup, 2)))
+    n, cores, times, kind = time_cpu(args, reps=max(1, args.steps), warm=max(1, min(args.warmup, 2)))
     total = sum(times)
     lps = n * len(times) / total
     T = out_frames(args.width)
-    sample = f'{n} lines of 96x{args.width} px per step ({len(times)} steps), fp32, torch CPU ops, {cores} threads'
+    sample = f'{n} lines of 96x{args.width} px per step ({len(times)} steps), fp32, {CPU_WHAT[kind]}, torch CPU ops, {cores} threads'
     out = dict(impl='reference', metric='text lines/sec', value=lps, unit='lines/s', n_gpus=args.gpus, steps=len(times),
                warmup=args.warmup, ms_per_step=1e3 * total / len(times), higher_is_better=True, scaling='weak',
                vs_baseline=None, dtype='f32', data='synthetic', frames_per_s=lps * T,
                config=dict(workload=workload_name(args).replace(args.precision + ' inference', 'fp32 CPU inference'),
-                           sample=sample, note=CPU_NOTE),
-               cpu_baseline=dict(value=lps, unit='lines/s', cores=cores, kind='port', sample=sample),
+                           sample=sample, note=CPU_NOTES[kind]),
+               cpu_baseline=dict(value=lps, unit='lines/s', cores=cores, kind=kind, sample=sample),
                e2e=dict(value=lps, unit='lines/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                gpu_launches=0)
     print(json.dumps(out), flush=True)
@@ -557,11 +574,11 @@ def run_ours(args):
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:         # rank 0 at N = 1 only (the other ranks' barrier spins would share the cores)
-        n, cores, times = time_cpu(args, reps=3, warm=1)
+        n, cores, times, kind = time_cpu(args, reps=3, warm=1)
         v = n * len(times) / sum(times)
-        cpu_baseline = dict(value=v, unit='lines/s', cores=cores, kind='port',
-                            sample=f'{n} lines of 96x{W} px x {len(times)} passes, fp32, oracle/torch_port.py, {cores} threads',
-                            note=CPU_NOTE)
+        cpu_baseline = dict(value=v, unit='lines/s', cores=cores, kind=kind,
+                            sample=f'{n} lines of 96x{W} px x {len(times)} passes, fp32, {CPU_WHAT[kind]}, {cores} threads',
+                            note=CPU_NOTES[kind])
 
     clocks = sampler.summary() if sampler else dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
     out = dict(metric='text lines/sec', value=lines_per_s, unit='lines/s', n_gpus=world, steps=args.steps,
@@ -639,10 +656,23 @@ def port_train_step_factory(args, hp, device, n_lines, autocast=False):
     return one_step
 
 
+def ref_train_step_factory(args, hp, n_lines):
+    """The reference's training step over its own modules (oracle/_ref) on the host cores: model.py:129-145 + backward +
+    torch.optim.AdamW, train() mode with the default dropout 0.1 - baseline leg only."""
+    from oracle import ref_modules as RM
+    from conformer_ocr_b200 import synthetic as S
+    net = RM.build_model(hp, args.classes, S.make_weights(hp, args.classes, seed=0), dropout=0.1)
+    a = argparse.Namespace(**vars(args))
+    a.batch = n_lines
+    return RM.train_step_factory(net, train_batch(a, hp, seed=77), lr=1e-3, weight_decay=1e-3)
+
+
 def time_cpu_train(args, hp, reps, warm):
+    from oracle import ref_modules as RM
     torch.set_num_threads(os.cpu_count() or 1)
     n = max(1, min(4, args.batch))
-    step = port_train_step_factory(args, hp, torch.device('cpu'), n)
+    kind = 'reference' if RM.available() and not os.environ.get('COCR_BENCH_CPU_PORT') else 'port'
+    step = ref_train_step_factory(args, hp, n) if kind == 'reference' else port_train_step_factory(args, hp, torch.device('cpu'), n)
     for _ in range(warm):
         step()
     times = []
@@ -650,26 +680,31 @@ def time_cpu_train(args, hp, reps, warm):
         t0 = time.perf_counter()
         step()
         times.append(time.perf_counter() - t0)
-    return n, torch.get_num_threads(), times
+    return n, torch.get_num_threads(), times, kind
 
 
-TRAIN_CPU_NOTE = ('the reference\'s training step as torch runs it on the host cores: train()-mode port of its modules '
-                  '(oracle/torch_train_port.py, pinned to the unmodified reference modules by tests/golden/train_*.npz), autograd, '
-                  'torch.optim.AdamW; dropout 0.1')
+TRAIN_CPU_NOTES = {
+    'reference': ('the reference\'s training step on the host cores over its own modules in train() mode (oracle/_ref, byte-compiled from the '
+                  'reference tree): encoder -> decoder -> log_softmax -> CTCLoss(sum, zero_infinity) as model.py:129-145, autograd, '
+                  'torch.optim.AdamW; dropout 0.1'),
+    'port': ('the reference\'s training step as torch runs it on the host cores: train()-mode port of its modules '
+             '(oracle/torch_train_port.py, pinned to the unmodified reference modules by tests/golden/train_*.npz; oracle/_ref is not built '
+             'on this machine), autograd, torch.optim.AdamW; dropout 0.1'),
+}
 
 
 def run_reference_train(args):
     if int(os.environ.get('RANK', '0')) != 0:
         return
     hp = arch_hp(hparams())
-    n, cores, times = time_cpu_train(args, hp, reps=max(1, args.steps), warm=1)
+    n, cores, times, kind = time_cpu_train(args, hp, reps=max(1, args.steps), warm=1)
     total = sum(times)
     lps = n * len(times) / total
-    sample = f'{n} lines of 96x{args.width} px per step ({len(times)} steps), fp32, torch CPU ops + autograd + AdamW, {cores} threads'
+    sample = f'{n} lines of 96x{args.width} px per step ({len(times)} steps), fp32, {CPU_WHAT[kind]}, torch CPU ops + autograd + AdamW, {cores} threads'
     out = dict(impl='reference', metric='training lines/sec', value=lps, unit='lines/s', n_gpus=args.gpus, steps=len(times), warmup=args.warmup,
                ms_per_step=1e3 * total / len(times), higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-               config=dict(workload=train_workload_name(args), sample=sample, note=TRAIN_CPU_NOTE),
-               cpu_baseline=dict(value=lps, unit='lines/s', cores=cores, kind='port', sample=sample),
+               config=dict(workload=train_workload_name(args), sample=sample, note=TRAIN_CPU_NOTES[kind]),
+               cpu_baseline=dict(value=lps, unit='lines/s', cores=cores, kind=kind, sample=sample),
                e2e=dict(value=lps, unit='lines/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(out), flush=True)
 
@@ -852,9 +887,10 @@ def run_train(args):
     step_tflops = fl_line * B / (ms_step * 1e-3) / 1e12
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
-        n, cores, times = time_cpu_train(args, hp, reps=2, warm=1)
-        cpu_baseline = dict(value=n * len(times) / sum(times), unit='lines/s', cores=cores, kind='port',
-                            sample=f'{n} lines of 96x{W} px x {len(times)} steps, fp32 forward + backward + AdamW, {cores} threads', note=TRAIN_CPU_NOTE)
+        n, cores, times, kind = time_cpu_train(args, hp, reps=2, warm=1)
+        cpu_baseline = dict(value=n * len(times) / sum(times), unit='lines/s', cores=cores, kind=kind,
+                            sample=f'{n} lines of 96x{W} px x {len(times)} steps, fp32 forward + backward + AdamW, {CPU_WHAT[kind]}, {cores} threads',
+                            note=TRAIN_CPU_NOTES[kind])
     clocks = sampler.summary() if sampler else dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
     out = dict(metric='training lines/sec', value=lines_per_s, unit='lines/s', n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step,
                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16' if args.precision == 'bf16' else 'f32', data='synthetic', frames_per_s=lines_per_s * T,
