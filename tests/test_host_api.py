@@ -169,13 +169,20 @@ def test_recognition_model_signature_defaults_match_reference():
         assert sig[k].default == v, k
 
 
-def test_bench_reference_arm_prints_one_contract_line():
-    """`bench.py --impl reference` runs on the host cores (no GPU needed) and prints ONE JSON line with the contract's keys."""
+@pytest.mark.parametrize('force_port', [False, True])
+def test_bench_reference_arm_prints_one_contract_line(force_port):
+    """`bench.py --impl reference` runs on the host cores (no GPU needed) and prints ONE JSON line with the contract's keys:
+    over the reference's own modules where oracle/_ref is built (kind 'reference'), over the port otherwise (kind 'port')."""
     import json
     import subprocess
     import sys
+    from oracle import ref_modules as RM
+    env = dict(os.environ)
+    env.pop('COCR_BENCH_CPU_PORT', None)
+    if force_port:
+        env['COCR_BENCH_CPU_PORT'] = '1'
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1',
-                          '--cpu-sample-lines', '1', '--width', '256'], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          '--cpu-sample-lines', '1', '--width', '256'], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
@@ -184,7 +191,7 @@ def test_bench_reference_arm_prints_one_contract_line():
               'dtype', 'data', 'config', 'cpu_baseline', 'e2e', 'gpu_launches'):
         assert k in d, k
     assert d['impl'] == 'reference' and d['unit'] == 'lines/s' and d['value'] > 0 and d['gpu_launches'] == 0
-    assert d['cpu_baseline']['kind'] == 'port' and d['e2e']['h2d_bytes_per_step'] == 0
+    assert d['cpu_baseline']['kind'] == ('reference' if RM.available() and not force_port else 'port') and d['e2e']['h2d_bytes_per_step'] == 0
 
 
 def test_bench_algorithmic_work_sums_to_survey_8d():
