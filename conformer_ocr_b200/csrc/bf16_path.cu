@@ -1106,7 +1106,9 @@ static int bf16_forward(cocr_handle *h, const void *img_any, bool u8, int64_t sb
             Bf16State *bs = h->bf;
             // two N tiles of 144 (value / gate pairs of 72 channels each) instead of three of 96: A is read twice, not three
             // times, and a CTA walks 10.4 instead of 15.7 M tiles (COCR_PW1_BN overrides)
-            static const int pw1_bn = getenv("COCR_PW1_BN") ? atoi(getenv("COCR_PW1_BN")) : (d == 144 ? 144 : 0);
+            // (chosen per handle: a function-local static would freeze the choice of the first model the process ran)
+            static const int pw1_bn_env = getenv("COCR_PW1_BN") ? atoi(getenv("COCR_PW1_BN")) : -1;
+            const int pw1_bn = pw1_bn_env >= 0 ? pw1_bn_env : (d == 144 ? 144 : 0);
             COCR_TRY(launch_gemm_tc(h, EPI_BF16_GLU, xn, ldx, bs->w_pw1g + (size_t)l * 2 * d * d, d, bs->b_pw1g + (size_t)l * 2 * d, hb, d,
                                     nullptr, M, 2 * d, d, st, pw1_bn, nullptr, "gemm_pw1_glu"));
             const float *taps = bs->dw_taps + (size_t)l * (dm.K + 1) * d;
@@ -1307,13 +1309,14 @@ int selftest_gemm(int device, int epi, int M, int N, int K, int block_n, double 
     k_fill_bf16<<<(unsigned)(((size_t)N * K + 255) / 256), 256>>>(Wt, (size_t)N * K, 2u, 0.25f);
     k_fill_f32<<<(N + 255) / 256, 256>>>(bias, (size_t)N, 3u, 0.5f);
     k_ref_gemm<<<(unsigned)(((size_t)M * N + 255) / 256), 256>>>(A, Wt, bias, ref, M, N, K, epi == EPI_BF16_SILU);
-    rc = launch_gemm_tc(h, epi, A, K, Wt, K, bias, out, N, best, M, N, K, 0, block_n);
+    const int ldc = epi == EPI_BF16_GLU ? N / 2 : N;      // GLU: (value, gate) column pairs -> N/2 outputs per row
+    rc = launch_gemm_tc(h, epi, A, K, Wt, K, bias, out, ldc, best, M, N, K, 0, block_n);
     if (rc != COCR_OK) return fail(rc, "launch failed");
     if (getenv("COCR_SELFTEST_TIME")) {     // timing aid for experiments: mean of 5 launches after the first
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0, 0);
-        for (int i = 0; i < 5; ++i) launch_gemm_tc(h, epi, A, K, Wt, K, bias, out, N, best, M, N, K, 0, block_n);
+        for (int i = 0; i < 5; ++i) launch_gemm_tc(h, epi, A, K, Wt, K, bias, out, ldc, best, M, N, K, 0, block_n);
         cudaEventRecord(e1, 0);
         cudaEventSynchronize(e1);
         float ms = 0.f;
@@ -1353,6 +1356,23 @@ int selftest_gemm(int device, int epi, int M, int N, int K, int block_n, double 
             if (!(err == err)) err = 1e9;
             worst = fmax(worst, err);
         }
+    } else if (epi == EPI_BF16_GLU) {
+        // the epilogue receives (value / 2, gate / 2) in columns (2c, 2c + 1): out[:, c] = v * sigmoid(g) = hv + hv * tanh(hg).
+        // Every output of every N tile is checked (the buffer starts as NaN patterns): a tile must write its own columns only.
+        const int No = N / 2;
+        std::vector<uint16_t> ho((size_t)M * No);
+        cudaMemcpy(ho.data(), out, ho.size() * 2, cudaMemcpyDeviceToHost);
+        for (int m = 0; m < M; ++m)
+            for (int c = 0; c < No; ++c) {
+                const double hv = href[(size_t)m * N + 2 * c], hg = href[(size_t)m * N + 2 * c + 1];
+                const double want = hv + hv * tanh(hg);
+                uint32_t b = (uint32_t)ho[(size_t)m * No + c] << 16;
+                float v;
+                memcpy(&v, &b, 4);
+                double err = fabs((double)v - want) / (1.0 + fabs(want));
+                if (!(err == err)) err = 1e9;
+                worst = fmax(worst, err);
+            }
     } else {
         std::vector<uint16_t> ho((size_t)M * N);
         cudaMemcpy(ho.data(), out, ho.size() * 2, cudaMemcpyDeviceToHost);

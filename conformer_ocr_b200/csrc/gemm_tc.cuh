@@ -529,7 +529,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         if (grow < p.M) {
                             __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.out) + grow * p.ldc + (gcol >> 1);
                             *reinterpret_cast<uint4 *>(dst) = make_uint4(po[0], po[1], po[2], po[3]);
-                            if (gcol + 16 < p.N) *reinterpret_cast<uint4 *>(dst + 8) = make_uint4(po[4], po[5], po[6], po[7]);
+                            // a 16-column last piece (block_n = 144) holds 8 outputs: the other 8 belong to the NEXT N tile's first piece
+                            // (written by that tile's CTA) - storing the zero-filled half here raced with it
+                            if (p.block_n - c0 >= 32 && gcol + 16 < p.N) *reinterpret_cast<uint4 *>(dst + 8) = make_uint4(po[4], po[5], po[6], po[7]);
                         }
                         return;
                     }

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 BF16_TOL = 2e-2
 DROP = dict(input_dropout_p=0.1, feed_forward_dropout_p=0.1, attention_dropout_p=0.1, conv_dropout_p=0.1)
 
-EPI_BF16, EPI_SILU, EPI_F32, EPI_ARGMAX = 0, 1, 2, 3
+EPI_BF16, EPI_SILU, EPI_F32, EPI_ARGMAX, EPI_GLU = 0, 1, 2, 3, 6
 GEMM_CASES = [
     # (epilogue, M, N, K, block_n override)
     (EPI_BF16, 128, 64, 64, 0), (EPI_BF16, 128, 144, 144, 0), (EPI_BF16, 300, 144, 144, 0),
@@ -26,6 +26,10 @@ GEMM_CASES = [
     (EPI_BF16, 40000, 576, 144, 0), (EPI_BF16, 40000, 144, 576, 0), (EPI_BF16, 1000, 144, 144, 32), (EPI_BF16, 1000, 144, 144, 96),
     (EPI_BF16, 5000, 1280, 144, 0), (EPI_SILU, 777, 576, 144, 0), (EPI_BF16, 333, 288, 144, 0), (EPI_BF16, 1000, 600, 144, 0),
     (EPI_SILU, 60000, 576, 144, 0), (EPI_BF16, 129, 96, 48, 0),
+    # first pointwise conv + GLU of the conv module (convolution.py:139-141): the production tiling (two N tiles of 144, whose
+    # last 32-column piece is half a piece: it must not spill into the next tile's outputs), three tiles of 96, a tiny model
+    (EPI_GLU, 3000, 288, 144, 144), (EPI_GLU, 40000, 288, 144, 144), (EPI_GLU, 777, 288, 144, 144), (EPI_GLU, 3000, 288, 144, 0),
+    (EPI_GLU, 1000, 64, 32, 0),
 ]
 
 
@@ -38,7 +42,7 @@ def test_tcgen05_gemm_selftest(epi, M, N, K, bn, cuda_device):
     _lib.raise_for_status(rc, None)
     # bf16 outputs: error relative to 1+|ref| bounded by bf16 rounding (2^-8) (+ tanh.approx for SiLU);
     # fp32 / arg-max outputs: accumulation-order differences only
-    tol = {EPI_BF16: 6e-3, EPI_SILU: 8e-3, EPI_F32: 2e-3, EPI_ARGMAX: 2e-3}[epi]
+    tol = {EPI_BF16: 6e-3, EPI_SILU: 8e-3, EPI_F32: 2e-3, EPI_ARGMAX: 2e-3, EPI_GLU: 8e-3}[epi]
     assert 0.0 <= err.value < tol, f'max err {err.value}'
 
 

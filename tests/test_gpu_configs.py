@@ -1,7 +1,9 @@
 """Parity at the sizes BASELINE.json's configs are benchmarked on (the judge's round-1 gap: the benched shape was only
-compared with itself).  The checker is oracle/torch_port.py on the box's host cores (pinned to the reference's golden
-vectors by tests/test_oracle_golden.py) for sampled lines, and the fp32 CUDA path (pinned to the goldens within 1e-4 by
-tests/test_gpu_fp32.py) for whole batches.
+compared with itself).  The checker for sampled lines runs on the box's host cores: the reference's OWN modules where
+oracle/_ref travelled with the snapshot (oracle/ref_modules.py: conformer_ocr.conformer.* compiled from the reference tree),
+else oracle/torch_port.py (pinned to those modules by tests/test_ref_modules.py and to the goldens by
+tests/test_oracle_golden.py); for whole batches it is the fp32 CUDA path (pinned to the goldens within 1e-4 by
+tests/test_gpu_fp32.py).
 
 Tolerances (BASELINE.json north_star): bf16 logits max-norm relative error <= 2e-2, top-1 agreement >= 99.9 % of frames."""
 import numpy as np
@@ -10,11 +12,13 @@ import torch
 
 from conftest import rel_err
 from oracle import conformer_oracle as O
+from oracle import ref_modules as RM
 from oracle import torch_port as TP
 
 pytestmark = pytest.mark.gpu
 BF16_TOL = 2e-2
 TOP1_MIN = 0.999
+CHECKER = 'reference modules (oracle/_ref)' if RM.available() else 'CPU port'
 DROP = dict(input_dropout_p=0.1, feed_forward_dropout_p=0.1, attention_dropout_p=0.1, conv_dropout_p=0.1)
 
 
@@ -33,8 +37,13 @@ def elementwise_rel(a, b, frac=0.1):
 
 
 def cpu_logits(img, lens, w, hp):
+    """pred.py:116-122 on the host cores: the reference's own modules (oracle/_ref) when present, else their port."""
     torch.set_num_threads(max(1, torch.get_num_threads()))
-    o, ol = TP.recognition_forward(torch.from_numpy(img), torch.from_numpy(lens), TP.to_torch(w), hp)
+    if RM.available():
+        C = w['decoder.weight'].shape[0]
+        o, ol = RM.forward(RM.build_model(hp, C, w).eval(), torch.from_numpy(img), torch.from_numpy(lens))
+    else:
+        o, ol = TP.recognition_forward(torch.from_numpy(img), torch.from_numpy(lens), TP.to_torch(w), hp)
     return o.numpy(), ol.numpy()
 
 
@@ -58,7 +67,7 @@ def test_benched_config_b256_w1536_bf16(cuda_device):
     np.testing.assert_array_equal(ol.numpy()[pick], ref_lens)
     err = rel_err(a[pick], ref)
     top1 = float((a[pick].argmax(-1) == ref.argmax(-1)).mean())
-    print(f'cfg2 b256 w1536 bf16 vs CPU port (16 lines): max-norm rel err {err:.3e}, element-wise (|ref| > 0.1 max) '
+    print(f'cfg2 b256 w1536 bf16 vs {CHECKER} (16 lines): max-norm rel err {err:.3e}, element-wise (|ref| > 0.1 max) '
           f'{elementwise_rel(a[pick], ref):.3e}, top-1 {top1:.5f}')
     assert err < BF16_TOL
     assert top1 >= TOP1_MIN
@@ -71,7 +80,7 @@ def test_benched_config_b256_w1536_bf16(cuda_device):
     errb = rel_err(a, b)
     agree = float((a.argmax(-1) == b.argmax(-1)).mean())
     print(f'cfg2 b256 w1536: bf16 vs fp32 CUDA (256 lines, {a.shape[0] * a.shape[1]} frames): rel err {errb:.3e}, top-1 {agree:.5f}; '
-          f'fp32 CUDA vs CPU port {err32:.3e}')
+          f'fp32 CUDA vs {CHECKER} {err32:.3e}')
     assert errb < BF16_TOL
     assert agree >= TOP1_MIN
     # (c) fused projection + arg-max + collapse == greedy decode of the same path's logits, all 256 lines
@@ -111,7 +120,7 @@ def test_config2_ragged_widths_reference_unmasked(cuda_device):
         assert rel_err(b[i, :n], ref[j, :n]) < 1e-4
         agree += int((a[i, :n].argmax(-1) == ref[j, :n].argmax(-1)).sum())
         frames += n
-    print(f'cfg2 ragged (W {widths[-1]}..{W}) bf16 vs CPU port ({len(pick)} lines): rel err {worst:.3e}, top-1 {agree / frames:.5f}')
+    print(f'cfg2 ragged (W {widths[-1]}..{W}) bf16 vs {CHECKER} ({len(pick)} lines): rel err {worst:.3e}, top-1 {agree / frames:.5f}')
     assert worst < BF16_TOL
     assert agree / frames >= TOP1_MIN
     agree = frames = 0
@@ -147,7 +156,7 @@ def test_config5_long_lines_cjk_alphabet_full_depth(cuda_device):
     t_cpu = float((a[:1].argmax(-1) == ref.argmax(-1)).mean())
     errb = rel_err(a, b)
     agree = float((a.argmax(-1) == b.argmax(-1)).mean())
-    print(f'cfg5 w4096 C10000 L16: bf16 vs CPU port (1 line) {e_cpu:.3e} top-1 {t_cpu:.5f}; fp32 CUDA vs CPU port {e32:.3e}; '
+    print(f'cfg5 w4096 C10000 L16: bf16 vs {CHECKER} (1 line) {e_cpu:.3e} top-1 {t_cpu:.5f}; fp32 CUDA vs {CHECKER} {e32:.3e}; '
           f'bf16 vs fp32 CUDA ({B} lines) {errb:.3e} top-1 {agree:.5f}')
     assert e32 < 1e-4
     assert e_cpu < BF16_TOL and errb < BF16_TOL
@@ -329,9 +338,10 @@ def test_bucketed_dataloader_pipeline_matches_cpu_port_batch_by_batch(cuda_devic
     assert sum(b[0].shape[0] for b in batches) == len(widths)
     got = list(net.predict_string_stream(batches, arrays=True))
     tw = TP.to_torch(w)
+    ref_net = RM.build_model(hp, C, w).eval() if RM.available() else None
     n_lines = 0
     for (img, lens), arr in zip(batches, got):
-        ref = TP.predict_labels(img, lens, tw, hp)
+        ref = RM.predict_labels(ref_net, img, lens) if ref_net is not None else TP.predict_labels(img, lens, tw, hp)
         mine = unpack_decoded(arr)
         assert [[t[:3] for t in l] for l in mine] == [[t[:3] for t in l] for l in ref]
         n_lines += len(ref)
