@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE (checker / reported baseline only; never imported by conformer_ocr_b200/).
 
-Loader of `oracle/_ref/`: the reference's own `conformer_ocr.conformer` modules, byte-compiled from /root/reference by
-`oracle/build_ref.py` (compiled outputs only; nothing here reads /root/reference at run time).  Used
+Loader of `oracle/_ref/`: the reference's own `conformer_ocr.conformer` modules, compiled from /root/reference by
+`oracle/build_ref.py` into marshalled code objects (compiled outputs only; nothing here reads /root/reference at run time).  Used
   * by `tests/test_ref_modules.py` to pin the numpy oracle and the torch ports against the UNMODIFIED reference modules
     on fresh seeded inputs (the committed goldens under tests/golden/ were made from the same modules), and
   * by `bench.py --impl reference` / `cpu_baseline` as the reference's CPU implementation of the path (`kind: "reference"`);
@@ -16,6 +16,10 @@ restated below, each citing its source; `greedy_decoder` is kraken's (absent): `
 from __future__ import annotations
 
 import importlib
+import importlib.abc
+import importlib.machinery
+import importlib.util
+import marshal
 import os
 import sys
 from typing import Dict, List, Mapping, Optional, Tuple
@@ -31,24 +35,50 @@ _ENC = None
 _WHY = ''
 
 
+class _RefFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    """Serves `conformer_ocr`, `conformer_ocr.conformer` and `conformer_ocr.conformer.*` from oracle/_ref/<name>.mcode."""
+    PACKAGES = ('conformer_ocr', 'conformer_ocr.conformer')
+
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname != 'conformer_ocr' and not fullname.startswith('conformer_ocr.'):
+            return None
+        origin = os.path.join(REF_DIR, fullname + '.mcode')
+        if not os.path.isfile(origin):
+            return None
+        return importlib.machinery.ModuleSpec(fullname, self, origin=origin, is_package=fullname in self.PACKAGES)
+
+    def create_module(self, spec):
+        return None
+
+    def exec_module(self, module):
+        origin = module.__spec__.origin
+        with open(origin, 'rb') as fp:
+            if fp.read(len(importlib.util.MAGIC_NUMBER)) != importlib.util.MAGIC_NUMBER:
+                raise ImportError(f'{origin} was compiled by another interpreter version')
+            code = marshal.loads(fp.read())
+        module.__file__ = origin
+        exec(code, module.__dict__)
+
+
 def _load():
     global _ENC, _WHY
     if _ENC is not None or _WHY:
         return _ENC
-    if not os.path.isfile(os.path.join(REF_DIR, 'conformer_ocr', 'conformer', 'encoder.pyc')):
+    if not os.path.isfile(os.path.join(REF_DIR, 'conformer_ocr.conformer.encoder.mcode')):
         _WHY = 'oracle/_ref is not built (python oracle/build_ref.py in the build container)'
         return None
-    sys.path.insert(0, REF_DIR)
+    finder = _RefFinder()
+    sys.meta_path.insert(0, finder)
     try:
         mod = importlib.import_module('conformer_ocr.conformer.encoder')
         where = os.path.realpath(getattr(mod, '__file__', '') or '')
         if not where.startswith(os.path.realpath(REF_DIR) + os.sep) and not where.startswith('/root/reference/'):
             raise ImportError(f'conformer_ocr resolved to {where}, not to oracle/_ref')
         _ENC = mod
-    except Exception as e:                       # a stale .pyc (other interpreter) or a shadowing package: use the ports
+    except Exception as e:                       # stale code objects (other interpreter) or a shadowing package: use the ports
         _WHY = f'oracle/_ref cannot be imported: {type(e).__name__}: {e}'
     finally:
-        sys.path.remove(REF_DIR)
+        sys.meta_path.remove(finder)
     return _ENC
 
 
