@@ -748,8 +748,11 @@ def run_train(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
-        tr.step(dev_batch)
+    first_loss = None
+    for i in range(args.warmup):
+        lw = tr.step(dev_batch)
+        if i == 0:
+            first_loss = float(lw.item())        # loss of the initial weights: with `final_loss` it shows the timed steps train
     fence()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -895,7 +898,7 @@ def run_train(args):
     out = dict(metric='training lines/sec', value=lines_per_s, unit='lines/s', n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step,
                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16' if args.precision == 'bf16' else 'f32', data='synthetic', frames_per_s=lines_per_s * T,
                config=dict(workload=train_workload_name(args), lines_per_step_per_gpu=B, global_batch=world * B, width_px=W, frames_per_line=T,
-                           classes=C, parameters=tr.n_trainable, workspace_bytes=tr.workspace_bytes(B, W), final_loss=last_loss,
+                           classes=C, parameters=tr.n_trainable, workspace_bytes=tr.workspace_bytes(B, W), first_loss=first_loss, final_loss=last_loss,
                            parallelism=(f'dp{world}: every rank its own {B} lines; ONE NCCL all-reduce(sum) of the flat gradient buffer '
                                         f'({tr.n_trainable * 4 / 1e6:.1f} MB) per step; BatchNorm statistics per rank') if world > 1 else 'single GPU',
                            l2='activations saved for the backward pass (%.1f GB) exceed the 126 MB L2; no explicit flush' % (tr.workspace_bytes(B, W) / 1e9)),
