@@ -70,7 +70,7 @@ def write_safetensors(tensors: Mapping[str, np.ndarray]) -> bytes:
     rev = {np.dtype(v): k for k, v in _ST_DTYPES.items()}
     header, chunks, off = {}, [], 0
     for name in sorted(tensors):
-        a = np.ascontiguousarray(tensors[name])
+        a = np.require(tensors[name], requirements='C')          # (ascontiguousarray would turn a 0-d tensor, e.g. num_batches_tracked, into shape (1,))
         if a.dtype not in rev:
             raise ValueError(f'unsupported dtype {a.dtype} for {name}')
         raw = a.astype(a.dtype.newbyteorder('<'), copy=False).tobytes()
