@@ -94,3 +94,37 @@ def test_train_port_matches_the_reference_modules_in_train_mode(name):
     sd = net.state_dict()
     for k, v in stats.items():
         assert np.abs(v.numpy() - sd[k].numpy()).max() <= 1e-6, k
+
+
+def test_every_module_of_every_layer_matches_the_reference_modules():
+    """Rows A2-A8 one by one, fed with the REFERENCE's own input of each module (so an error cannot hide behind, or grow
+    from, an earlier module): sub-sampling, then per layer the half-step FFN, rel-pos MHSA, conv module, second FFN and
+    block-final LayerNorm of a 3-layer default-spec encoder on a ragged batch."""
+    hp, C, w, img, lens = _case('default_3layer_ragged')
+    net = RM.build_model(hp, C, w).eval()
+    enc = net['encoder']
+    taps = {}
+    hooks = [enc.conv_subsample.register_forward_hook(lambda m, i, o: taps.__setitem__('sub', (i[0].numpy().copy(), o[0].numpy().copy())))]
+    for l, layer in enumerate(enc.layers):
+        for j in range(5):
+            hooks.append(layer.sequential[j].register_forward_hook(
+                lambda m, i, o, key=(l, j): taps.__setitem__(key, (i[0].numpy().copy(), o.numpy().copy()))))
+    RM.forward(net, torch.from_numpy(img), torch.from_numpy(lens))
+    for h in hooks:
+        h.remove()
+    x_in, sub_out = taps['sub']
+    got, _ = O.conv2d_subsampling(x_in, lens, w, 'encoder.conv_subsample.')
+    assert rel_err(got, sub_out) < 2e-5
+    half = np.float32(0.5)
+    for l in range(hp['num_encoder_layers']):
+        p = f'encoder.layers.{l}.sequential.'
+        x, y = taps[(l, 0)]
+        assert rel_err(O.feed_forward(x, w, p + '0.module.') * half + x, y) < 2e-5, (l, 'ffn1')
+        x, y = taps[(l, 1)]
+        assert rel_err(O.rel_mhsa(x, w, p + '1.module.', hp['num_attention_heads']) + x, y) < 2e-5, (l, 'mhsa')
+        x, y = taps[(l, 2)]
+        assert rel_err(O.conv_module(x, w, p + '2.module.', hp['conv_kernel_size']) + x, y) < 2e-5, (l, 'conv')
+        x, y = taps[(l, 3)]
+        assert rel_err(O.feed_forward(x, w, p + '3.module.') * half + x, y) < 2e-5, (l, 'ffn2')
+        x, y = taps[(l, 4)]
+        assert rel_err(O.layer_norm(x, w[p + '4.weight'], w[p + '4.bias']), y) < 2e-5, (l, 'final LayerNorm')
