@@ -30,13 +30,15 @@ def encoder_param_spec(input_dim: int, encoder_dim: int, num_layers: int, num_at
             ('conv_subsample.conv.2.weight', (cc, 1, 3, 3), 'default'), ('conv_subsample.conv.2.bias', (cc,), 'default_b:9'),
             ('conv_subsample.conv.3.weight', (cc, cc, 1, 1), 'default'), ('conv_subsample.conv.3.bias', (cc,), f'default_b:{cc}'),
             ('conv_subsample.out.0.weight', (d, cc * f), 'default'), ('conv_subsample.out.0.bias', (d,), f'default_b:{cc * f}')]
+    def ffn(q):
+        return [(q + '0.weight', (d,), 'ones'), (q + '0.bias', (d,), 'zeros'),
+                (q + '1.linear.weight', (ff, d), 'xavier'), (q + '1.linear.bias', (ff,), 'zeros'),
+                (q + '4.linear.weight', (d, ff), 'xavier'), (q + '4.linear.bias', (d,), 'zeros')]
+    # Order = the reference's module registration order (encoder.py:67-103), i.e. the order of `parameters()` and
+    # `state_dict()`: optimizer states of a Lightning checkpoint are indexed by it.
     for i in range(num_layers):
         p = f'layers.{i}.sequential.'
-        for m in ('0', '3'):
-            q = f'{p}{m}.module.sequential.'
-            spec += [(q + '0.weight', (d,), 'ones'), (q + '0.bias', (d,), 'zeros'),
-                     (q + '1.linear.weight', (ff, d), 'xavier'), (q + '1.linear.bias', (ff,), 'zeros'),
-                     (q + '4.linear.weight', (d, ff), 'xavier'), (q + '4.linear.bias', (d,), 'zeros')]
+        spec += ffn(f'{p}0.module.sequential.')
         q = f'{p}1.module.'
         spec += [(q + 'layer_norm.weight', (d,), 'ones'), (q + 'layer_norm.bias', (d,), 'zeros'),
                  (q + 'attention.u_bias', (h, d // h), 'xavier'), (q + 'attention.v_bias', (h, d // h), 'xavier')]
@@ -54,6 +56,7 @@ def encoder_param_spec(input_dim: int, encoder_dim: int, num_layers: int, num_at
                  (q + '5.running_mean', (d,), 'buffer0'), (q + '5.running_var', (d,), 'buffer1'),
                  (q + '5.num_batches_tracked', (), 'counter'),
                  (q + '7.conv.weight', (d, d, 1), 'default'), (q + '7.conv.bias', (d,), f'default_b:{d}')]
+        spec += ffn(f'{p}3.module.sequential.')
         spec += [(p + '4.weight', (d,), 'ones'), (p + '4.bias', (d,), 'zeros')]
     return spec
 

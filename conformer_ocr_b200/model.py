@@ -40,6 +40,15 @@ class RecognitionModel(EngineOwner):
             p.requires_grad_(False)
         self.nn = nn.ModuleDict({'encoder': encoder, 'decoder': decoder})    # model.py:115
         self.num_classes = num_classes
+        # `self.save_hyperparameters()` (model.py:91): what a checkpoint stores under 'hyper_parameters'
+        self.hyper_parameters = dict(num_classes=num_classes, height=height, encoder_dim=encoder_dim, num_encoder_layers=num_encoder_layers,
+                                     num_attention_heads=num_attention_heads, feed_forward_expansion_factor=feed_forward_expansion_factor,
+                                     conv_expansion_factor=conv_expansion_factor, input_dropout_p=input_dropout_p,
+                                     feed_forward_dropout_p=feed_forward_dropout_p, attention_dropout_p=attention_dropout_p,
+                                     conv_dropout_p=conv_dropout_p, conv_kernel_size=conv_kernel_size, half_step_residual=half_step_residual,
+                                     subsampling_conv_channels=subsampling_conv_channels, subsampling_factor=subsampling_factor, **kwargs)
+        self.codec = None                 # c2l dict of the data module (dataset.py:169-175), carried through checkpoints
+        self._resume = None               # optimiser state of a checkpoint, handed to the trainer when it is created
         self._init_engine_state(precision, mask_mode)
         self.eval()
 
@@ -79,6 +88,10 @@ class RecognitionModel(EngineOwner):
                                     device=device, **dp, **cfg)
             self._trainer.load_state_dict(self.nn.state_dict())
             self._trainer_dirty = False
+            if self._resume is not None:                                     # resuming: AdamW moments and the step count of the checkpoint
+                self._trainer.load_optimizer_state_dict(self._resume['optimizer'], [k for k, _ in self.nn.named_parameters()])
+                self._trainer.global_step = int(self._resume['global_step'])
+                self._resume = None
         return self._trainer
 
     def training_step(self, batch, batch_idx: int = 0):
@@ -106,6 +119,51 @@ class RecognitionModel(EngineOwner):
                 own[k].copy_(v.to(own[k].device))
         self._trainer_dirty = False
         self.invalidate_engine()
+
+    # -- checkpoints (model.py:219-220 `save_checkpoint`; `load_from_checkpoint` as cli/train.py:328 and pred.py:229 call it) ----------
+    def save_checkpoint(self, filename, codec=None):
+        """Write a checkpoint with the layout of the reference's Lightning checkpoints: `state_dict` (keys `nn.*`, in the
+        reference's order), `hyper_parameters`, `TextLineDataModule` = {'codec': c2l} (what `PytorchRecognitionModel.load_checkpoint`,
+        pred.py:197-210, and the converter read), `global_step`, and - when a training step has run - `optimizer_states` in
+        `torch.optim.AdamW.state_dict()` form, indexed in `nn.parameters()` order like Lightning's."""
+        if getattr(self, '_trainer', None) is not None and self._trainer_dirty:
+            self.sync_from_trainer()
+        codec = codec if codec is not None else self.codec
+        if hasattr(codec, 'c2l'):
+            codec = codec.c2l
+        ck = {'state_dict': {'nn.' + k: v.detach().cpu().clone() for k, v in self.nn.state_dict().items()},
+              'hyper_parameters': dict(self.hyper_parameters), 'epoch': 0, 'global_step': 0}
+        if codec is not None:
+            ck['TextLineDataModule'] = {'codec': {k: list(v) for k, v in dict(codec).items()}}
+        tr = getattr(self, '_trainer', None)
+        if tr is not None:
+            ck['global_step'] = int(tr.global_step)
+            ck['optimizer_states'] = [tr.optimizer_state_dict([k for k, _ in self.nn.named_parameters()])]
+        elif self._resume is not None:
+            ck['global_step'] = int(self._resume['global_step'])
+            ck['optimizer_states'] = [self._resume['optimizer']]
+        torch.save(ck, filename)
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location='cpu', **kwargs):
+        """Lightning's classmethod as the reference uses it (cli/train.py:328-336, pred.py:229): the module is rebuilt from the
+        checkpoint's `hyper_parameters` (keyword arguments override them), `nn.*` tensors are loaded strictly, metric buffers of the
+        LightningModule are ignored; optimiser moments and the step count are kept for the next `training_step`."""
+        ck = torch.load(checkpoint_path, map_location=map_location, weights_only=False)
+        if 'hyper_parameters' not in ck:
+            raise ValueError('No hyperparameters in state_dict')
+        if 'state_dict' not in ck:
+            raise ValueError('Checkpoint does not contain a state_dict.')
+        hp = dict(ck['hyper_parameters'])
+        hp.update(kwargs)
+        model = cls(**hp)
+        own = {k[len('nn.'):]: v for k, v in ck['state_dict'].items() if k.startswith('nn.')}
+        model.nn.load_state_dict(own, strict=True)
+        if 'TextLineDataModule' in ck:
+            model.codec = ck['TextLineDataModule'].get('codec')
+        if ck.get('optimizer_states'):
+            model._resume = {'optimizer': ck['optimizer_states'][0], 'global_step': int(ck.get('global_step', 0))}
+        return model
 
     def forward(self, x: torch.Tensor, seq_lens: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """x (N, W, H) as `_step` passes it (model.py:132-135) -> (logits (N,T,C), encoder_lens)."""

@@ -20,6 +20,50 @@ from .engine import out_frames
 from .sharding import allreduce_flat_prefix
 
 
+def flat_to_adamw_state(layout: Mapping[str, Tuple[int, int, bool, Tuple[int, ...]]], exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor,
+                        step: int, param_names: Sequence[str], lr: float, betas: Tuple[float, float], eps: float, weight_decay: float) -> Dict:
+    """The flat AdamW moment buffers as `torch.optim.AdamW(...).state_dict()` (what Lightning stores under `optimizer_states`):
+    state[i] belongs to the i-th name of `param_names` (= `nn.parameters()` order).  Before the first step the state is empty,
+    like torch's."""
+    state = {}
+    if step > 0:
+        for i, k in enumerate(param_names):
+            off, num, trainable, shape = layout[k]
+            if not trainable:
+                raise ValueError(f'{k} is not a trainable parameter')
+            state[i] = {'step': torch.tensor(float(step)), 'exp_avg': exp_avg[off:off + num].detach().cpu().clone().view(shape),
+                        'exp_avg_sq': exp_avg_sq[off:off + num].detach().cpu().clone().view(shape)}
+    group = {'lr': lr, 'betas': tuple(betas), 'eps': eps, 'weight_decay': weight_decay, 'amsgrad': False, 'maximize': False, 'foreach': None,
+             'capturable': False, 'differentiable': False, 'fused': None, 'params': list(range(len(param_names)))}
+    return {'state': state, 'param_groups': [group]}
+
+
+def adamw_state_to_flat(layout: Mapping[str, Tuple[int, int, bool, Tuple[int, ...]]], opt_state: Mapping, param_names: Sequence[str],
+                        exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor) -> int:
+    """Inverse of `flat_to_adamw_state`: copies the moments of a `torch.optim.AdamW` state dict into the flat buffers (in place)
+    and returns the step count (0 for an empty state).  Parameters are matched by position in `param_names` and checked by shape."""
+    groups = opt_state.get('param_groups', [])
+    ids = [i for g in groups for i in g['params']]
+    if len(ids) != len(param_names):
+        raise ValueError(f'optimizer state covers {len(ids)} parameters, the model has {len(param_names)}')
+    steps = set()
+    exp_avg.zero_()
+    exp_avg_sq.zero_()
+    for pid, k in zip(ids, param_names):
+        st = opt_state['state'].get(pid)
+        if st is None:
+            continue
+        off, num, trainable, shape = layout[k]
+        if tuple(st['exp_avg'].shape) != tuple(shape):
+            raise ValueError(f'optimizer state {pid} has shape {tuple(st["exp_avg"].shape)}, parameter {k} has {tuple(shape)}')
+        exp_avg[off:off + num].copy_(st['exp_avg'].reshape(-1).to(torch.float32))
+        exp_avg_sq[off:off + num].copy_(st['exp_avg_sq'].reshape(-1).to(torch.float32))
+        steps.add(int(st['step']))
+    if len(steps) > 1:
+        raise ValueError(f'parameters disagree on the step count: {sorted(steps)}')
+    return steps.pop() if steps else 0
+
+
 class Trainer:
     def __init__(self, *, num_classes: int, height: int = 96, encoder_dim: int = 144, num_encoder_layers: int = 16,
                  num_attention_heads: int = 4, feed_forward_expansion_factor: int = 4, conv_expansion_factor: int = 2,
@@ -184,6 +228,16 @@ class Trainer:
         self._check(self._lib.cocr_adamw_step(self._h, self.params.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(),
                                               self.exp_avg_sq.data_ptr(), self.n_trainable, lr, self.betas[0], self.betas[1], self.eps,
                                               self.weight_decay, self.global_step, self._stream()))
+
+    def optimizer_state_dict(self, param_names: Optional[Sequence[str]] = None) -> Dict:
+        """`torch.optim.AdamW.state_dict()` form of the flat moment buffers (for checkpoints); `param_names` = `nn.parameters()`
+        order of the module the checkpoint belongs to (default: the trainable keys in layout order)."""
+        return flat_to_adamw_state(self.layout, self.exp_avg, self.exp_avg_sq, self.global_step, list(param_names or self.trainable_keys()),
+                                   self.lr, self.betas, self.eps, self.weight_decay)
+
+    def load_optimizer_state_dict(self, opt_state: Mapping, param_names: Optional[Sequence[str]] = None) -> None:
+        """Resume: moments and step count of a `torch.optim.AdamW` state dict (Lightning's `optimizer_states[0]`)."""
+        self.global_step = adamw_state_to_flat(self.layout, opt_state, list(param_names or self.trainable_keys()), self.exp_avg, self.exp_avg_sq)
 
     def step(self, batch: Mapping[str, torch.Tensor]) -> torch.Tensor:
         loss = self.forward_backward(batch)

@@ -166,3 +166,118 @@ def test_width_bucket_sampler_gives_equal_frame_batches():
     assert all(len(b) == 16 for b in full)
     with pytest.raises(ValueError):
         WidthBucketBatchSampler([10, 0], 4)
+
+
+def test_mirror_parameter_order_is_the_references():
+    """`nn.parameters()` / `state_dict()` order of the mirrors = the reference's module registration order (encoder.py:67-103):
+    Lightning indexes `optimizer_states` by it.  First layer spelled out; against the reference's own modules where oracle/_ref
+    is built."""
+    from conformer_ocr_b200 import RecognitionModel
+    hp = small_hp(2)
+    m = RecognitionModel(num_classes=9, **hp)
+    names = [k for k, _ in m.nn.named_parameters()]
+    p = 'encoder.layers.0.sequential.'
+    first = ['0.module.sequential.0.weight', '0.module.sequential.0.bias', '0.module.sequential.1.linear.weight', '0.module.sequential.1.linear.bias',
+             '0.module.sequential.4.linear.weight', '0.module.sequential.4.linear.bias', '1.module.layer_norm.weight', '1.module.layer_norm.bias',
+             '1.module.attention.u_bias', '1.module.attention.v_bias', '1.module.attention.query_proj.linear.weight',
+             '1.module.attention.query_proj.linear.bias', '1.module.attention.key_proj.linear.weight', '1.module.attention.key_proj.linear.bias',
+             '1.module.attention.value_proj.linear.weight', '1.module.attention.value_proj.linear.bias', '1.module.attention.pos_proj.linear.weight',
+             '1.module.attention.out_proj.linear.weight', '1.module.attention.out_proj.linear.bias', '2.module.sequential.0.weight',
+             '2.module.sequential.0.bias', '2.module.sequential.2.conv.weight', '2.module.sequential.2.conv.bias', '2.module.sequential.4.conv.weight',
+             '2.module.sequential.5.weight', '2.module.sequential.5.bias', '2.module.sequential.7.conv.weight', '2.module.sequential.7.conv.bias',
+             '3.module.sequential.0.weight', '3.module.sequential.0.bias', '3.module.sequential.1.linear.weight', '3.module.sequential.1.linear.bias',
+             '3.module.sequential.4.linear.weight', '3.module.sequential.4.linear.bias', '4.weight', '4.bias']
+    assert names[:8] == ['encoder.conv_subsample.conv.0.weight', 'encoder.conv_subsample.conv.0.bias', 'encoder.conv_subsample.conv.2.weight',
+                         'encoder.conv_subsample.conv.2.bias', 'encoder.conv_subsample.conv.3.weight', 'encoder.conv_subsample.conv.3.bias',
+                         'encoder.conv_subsample.out.0.weight', 'encoder.conv_subsample.out.0.bias']
+    assert names[8:8 + len(first)] == [p + k for k in first]
+    assert names[-2:] == ['decoder.weight', 'decoder.bias']
+    from oracle import ref_modules as RM
+    if RM.available():
+        ref = RM.build_model(hp, 9)
+        assert [k for k, _ in ref.named_parameters()] == names
+        assert [(k, tuple(v.shape), v.dtype) for k, v in ref.state_dict().items()] == [(k, tuple(v.shape), v.dtype) for k, v in m.nn.state_dict().items()]
+
+
+def test_adamw_state_mapping_between_flat_buffers_and_torch():
+    """The trainer keeps AdamW's moments in two flat buffers; checkpoints carry them as `torch.optim.AdamW.state_dict()` indexed in
+    `nn.parameters()` order.  A real torch optimiser's state -> flat -> state dict is the identity, and torch loads the result."""
+    from conformer_ocr_b200 import RecognitionModel
+    from conformer_ocr_b200.train import adamw_state_to_flat, flat_to_adamw_state
+    hp = small_hp(2)
+    m = RecognitionModel(num_classes=9, **hp)
+    names = [k for k, _ in m.nn.named_parameters()]
+    params = [torch.nn.Parameter(p.detach().clone()) for _, p in m.nn.named_parameters()]
+    # a layout like cocr_train_entry's: trainable tensors back to back, 8-element aligned, in an order of its own
+    layout, off = {}, 0
+    for k, p in sorted(zip(names, params), key=lambda kp: kp[0]):
+        off = (off + 7) // 8 * 8
+        layout[k] = (off, p.numel(), True, tuple(p.shape))
+        off += p.numel()
+    opt = torch.optim.AdamW(params, lr=3e-4, weight_decay=1e-5)
+    g = torch.Generator().manual_seed(0)
+    for _ in range(3):
+        for p in params:
+            p.grad = torch.randn(p.shape, generator=g)
+        opt.step()
+    want = opt.state_dict()
+    exp_avg, exp_avg_sq = torch.full((off,), 7.0), torch.full((off,), 7.0)
+    step = adamw_state_to_flat(layout, want, names, exp_avg, exp_avg_sq)
+    assert step == 3
+    for i, k in enumerate(names):
+        o, n, _, shape = layout[k]
+        assert torch.equal(exp_avg[o:o + n].view(shape), want['state'][i]['exp_avg'])
+        assert torch.equal(exp_avg_sq[o:o + n].view(shape), want['state'][i]['exp_avg_sq'])
+    got = flat_to_adamw_state(layout, exp_avg, exp_avg_sq, step, names, 3e-4, (0.9, 0.999), 1e-8, 1e-5)
+    assert got['param_groups'][0]['params'] == want['param_groups'][0]['params']
+    for i in range(len(names)):
+        assert float(got['state'][i]['step']) == 3.0
+        assert torch.equal(got['state'][i]['exp_avg'], want['state'][i]['exp_avg'])
+        assert torch.equal(got['state'][i]['exp_avg_sq'], want['state'][i]['exp_avg_sq'])
+    opt2 = torch.optim.AdamW([torch.nn.Parameter(p.detach().clone()) for p in params], lr=1.0)
+    opt2.load_state_dict(got)                                   # torch accepts it as its own
+    assert opt2.param_groups[0]['lr'] == 3e-4 and opt2.param_groups[0]['weight_decay'] == 1e-5
+    assert flat_to_adamw_state(layout, exp_avg, exp_avg_sq, 0, names, 1e-3, (0.9, 0.999), 1e-8, 0.0)['state'] == {}
+    with pytest.raises(ValueError):
+        adamw_state_to_flat(layout, want, names[:-1], exp_avg, exp_avg_sq)
+
+
+def test_recognition_model_checkpoint_round_trip(tmp_path):
+    """`RecognitionModel.save_checkpoint` (model.py:219-220) writes the layout the reference's loaders read:
+    `PytorchRecognitionModel.load_checkpoint` (pred.py:197-210), the converter and `load_from_checkpoint` (cli/train.py:328)."""
+    from conformer_ocr_b200 import RecognitionModel
+    hp, C = small_hp(2), 12
+    codec = {chr(0x61 + i): [i + 1] for i in range(C - 1)}
+    w = S.make_weights(hp, C, seed=3)
+    m = RecognitionModel(num_classes=C, lr=3e-4, optimizer='AdamW', **hp)
+    m.nn.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=False)
+    path = tmp_path / 'checkpoint_00.ckpt'
+    m.save_checkpoint(path, codec=codec)
+    ck = torch.load(path, weights_only=False)
+    assert list(ck['state_dict']) == ['nn.' + k for k in m.nn.state_dict()]
+    assert ck['hyper_parameters']['num_classes'] == C and ck['hyper_parameters']['lr'] == 3e-4 and ck['hyper_parameters']['optimizer'] == 'AdamW'
+    assert ck['TextLineDataModule'] == {'codec': codec} and 'optimizer_states' not in ck and ck['global_step'] == 0
+    net = PytorchRecognitionModel.load_checkpoint(path)
+    assert net.codec.c2l == codec
+    for k, v in w.items():
+        np.testing.assert_array_equal(net.nn.state_dict()[k].numpy(), v)
+    checkpoint_to_safetensors(path, tmp_path / 'm.tar')
+    net2 = PytorchRecognitionModel.load_safetensors(tmp_path / 'm.tar')
+    np.testing.assert_array_equal(net2.nn.state_dict()['decoder.weight'].numpy(), w['decoder.weight'])
+    back = RecognitionModel.load_from_checkpoint(path, precision='bf16')
+    assert back.precision == 'bf16' and back.codec == codec and back.hyper_parameters['lr'] == 3e-4 and back._resume is None
+    for k, v in w.items():
+        np.testing.assert_array_equal(back.nn.state_dict()[k].numpy(), v)
+    # a checkpoint WITH optimiser state (as Lightning writes it) keeps it through load -> save until a trainer takes it over
+    ck['optimizer_states'] = [{'state': {}, 'param_groups': [{'lr': 3e-4, 'params': list(range(len(list(m.nn.parameters()))))}]}]
+    ck['global_step'] = 41
+    torch.save(ck, tmp_path / 'resume.ckpt')
+    res = RecognitionModel.load_from_checkpoint(tmp_path / 'resume.ckpt')
+    assert res._resume['global_step'] == 41
+    res.save_checkpoint(tmp_path / 'again.ckpt')
+    again = torch.load(tmp_path / 'again.ckpt', weights_only=False)
+    assert again['global_step'] == 41 and again['optimizer_states'] == ck['optimizer_states'] and again['TextLineDataModule'] == {'codec': codec}
+    bad = {k: v for k, v in ck.items() if k != 'hyper_parameters'}
+    torch.save(bad, tmp_path / 'bad.ckpt')
+    with pytest.raises(ValueError, match='hyperparameters'):
+        RecognitionModel.load_from_checkpoint(tmp_path / 'bad.ckpt')
