@@ -210,3 +210,34 @@ def test_bench_algorithmic_work_sums_to_survey_8d():
         assert total == pytest.approx(B * S.flops_per_line(W, C, hp), rel=1e-12)
         assert a['frontend_tc']['flops'] == a['frontend_convs']['flops'] + a['gemm_frontend_pw']['flops']
         assert a['attention_tc']['bound'] == 'tensor' and a['dwconv_bn_silu_bf16']['bound'] == 'hbm'
+
+
+def test_tensor_core_kernels_hold_tcgen05_and_tma_instructions(lib):
+    """The hot kernels of the shipped library are tcgen05 / TMEM / TMA code, not a recompiled SIMT or mma.sync path: per kernel,
+    `cuobjdump -sass` shows UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld) and - where operands arrive by TMA - UTMALDG
+    (cp.async.bulk.tensor); mnemonics as in /opt/skills/guides/B200_PROFILING.md.  No GPU needed."""
+    import shutil
+    import subprocess
+    from conformer_ocr_b200 import _lib
+    tool = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(tool):
+        pytest.skip('cuobjdump not installed')
+    sass = subprocess.run([tool, '-sass', _lib.LIB_PATH], capture_output=True, text=True, timeout=300, check=True).stdout
+    counts = {}
+    for part in re.split(r'\n\s*Function : ', sass)[1:]:
+        name = part.split('\n', 1)[0].strip()
+        counts[name] = {m: len(re.findall(r'\b' + m, part)) for m in ('UTCHMMA', 'LDTM', 'STTM', 'UTMALDG', 'HMMA')}
+
+    def kernels(fragment):
+        hit = {k: v for k, v in counts.items() if fragment in k}
+        assert hit, f'no kernel named *{fragment}* in the library'
+        return hit
+    for frag, tma in (('k_gemm_tc', True), ('k_ffn_fused2', True), ('k_ffn_fused', True), ('k_attn_tc', True), ('k_bgemm_tc', True),
+                      ('k_frontend_tc', False)):          # the front-end gathers its image rows with plain loads (strided caller memory)
+        for name, c in kernels(frag).items():
+            assert c['UTCHMMA'] > 0 and c['LDTM'] > 0, (name, c)
+            assert not tma or c['UTMALDG'] > 0, (name, c)
+    assert len(kernels('k_gemm_tc')) == 7                   # one instantiation per epilogue
+    assert all(c['STTM'] > 0 for c in kernels('k_attn_tc').values())      # Q and P are written to TMEM as A operands
+    assert all(c['STTM'] > 0 for c in kernels('k_ffn_fused2').values())   # so are the LayerNorm'd rows of the fused FFN
+    assert not any(c['HMMA'] for c in counts.values())      # no mma.sync / wmma kernel anywhere in the library
