@@ -108,5 +108,5 @@ class LabelCodec:
             r = row[:n]
             if not r.all():
                 r = r[r != 0]                     # unknown labels (and a NUL grapheme, which kraken's codec never holds)
-            out.append(r.tobytes().decode('utf-32-le'))
+            out.append(r.tobytes().decode('utf-32-le', 'surrogatepass'))       # a codec may hold any code point a Python str can
         return out
