@@ -406,3 +406,29 @@ def test_dropout_masks_are_philox(cuda_device, seed, site, p, n):
     want = TP.philox_dropout_factors(seed, site, p, n)
     assert got.dtype == want.dtype and np.array_equal(got, want)
     tr.close()
+
+
+def test_train_step_benchmark_shape_bf16_against_fp32_path(cuda_device):
+    """BASELINE configs[3] exactly as `bench.py --config 4` runs it (32 lines of 96 x 1536 px, 256 classes, 16 layers; the
+    weight-gradient contractions are split over 28 slices at this size, 18 at the 3-line shape of the other default-spec tests):
+    the tensor-core mode against the fp32 CUDA-core mode (pinned to the reference's gradients to 1e-5 at the small shapes) on the
+    same batch, dropout off.  Loss within 5e-3; the whole gradient vector within 14 degrees (cosine >= 0.97; 0.990 was measured
+    against a float64 port at 16 layers and 3 lines, torch's own bf16 autocast reaches 0.958 there - profiles/r02_train_bf16_noise.log).
+    Measured on B200: loss 52 459.8 (fp32) / 52 511.9 (bf16), cosine 0.9958."""
+    hp = dict(O.DEFAULT_HPARAMS)
+    B, W, C = 32, 1536, 256
+    w = O.make_weights(hp, C, seed=0)
+    batch = synthetic_batch(B, hp['height'], W, C, seed=1234)
+    out = {}
+    for prec in ('fp32', 'bf16'):
+        tr = make_trainer(hp, C, cuda_device, precision=prec)
+        tr.load_state_dict(w)
+        loss = tr.forward_backward(batch).item()
+        out[prec] = (loss, tr.grads[:tr.n_trainable].double().cpu())
+        tr.close()
+    (l32, g32), (l16, g16) = out['fp32'], out['bf16']
+    assert np.isfinite(l32) and np.isfinite(l16) and torch.isfinite(g16).all()
+    cos = float((g32 * g16).sum() / (g32.norm() * g16.norm()))
+    print(f'training step at the benchmark shape: loss fp32 {l32:.3f} bf16 {l16:.3f}, gradient cosine {cos:.6f}')
+    assert abs(l16 - l32) <= 5e-3 * abs(l32), (l16, l32)
+    assert cos >= 0.97, cos
