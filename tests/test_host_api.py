@@ -241,3 +241,19 @@ def test_tensor_core_kernels_hold_tcgen05_and_tma_instructions(lib):
     assert all(c['STTM'] > 0 for c in kernels('k_attn_tc').values())      # Q and P are written to TMEM as A operands
     assert all(c['STTM'] > 0 for c in kernels('k_ffn_fused2').values())   # so are the LayerNorm'd rows of the fused FFN
     assert not any(c['HMMA'] for c in counts.values())      # no mma.sync / wmma kernel anywhere in the library
+
+
+def test_no_function_local_static_frozen_by_the_first_model():
+    """A function-local `static` whose initialiser reads the handle or its dimensions keeps the value of the FIRST model the
+    process ran (that is how the GPU suite, which starts with a tiny golden, ran another pw1 tiling than the benchmark did;
+    DESIGN.md 5).  Statics in the host code of the library may depend on the environment only."""
+    csrc = os.path.join(ROOT, 'conformer_ocr_b200', 'csrc')
+    bad = []
+    for fn in sorted(os.listdir(csrc)):
+        if not fn.endswith(('.cu', '.cuh', '.h')):
+            continue
+        for no, line in enumerate(open(os.path.join(csrc, fn)), 1):
+            m = re.match(r'\s*(?:\{\s*)?static\s+(?:const\s+)?(?:bool|int|size_t|float|unsigned|uint32_t|int64_t)\s+\w+\s*=\s*([^;]*)', line)
+            if m and 'constexpr' not in line and re.search(r'\bh->|\bdm\.|\bhp\.|\bd\s*==|\bp\.[A-Za-z]|\bB\b|\bT\b', m.group(1)):
+                bad.append(f'{fn}:{no}: {line.strip()}')
+    assert not bad, '\n'.join(bad)
